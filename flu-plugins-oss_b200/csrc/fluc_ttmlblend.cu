@@ -1,0 +1,1527 @@
+/*
+ * fluc_ttmlblend.cu -- host side of libfluc_ttmlblend.so: the C ABI declared in
+ * include/fluc_ttmlblend.h. Context (one per GPU), overlay cache, frame pool,
+ * multi-stream batch scheduler and the host-frame (PCIe) path.
+ *
+ * This is the native runtime around the kernels in ttmlblend_kernels.cu. It
+ * stands where the reference leaves compositing to GStreamer
+ * (/root/reference/plugins/ttml/README.md:45-48) and is shaped after the
+ * reference's own helper libraries: opaque object + monitor
+ * (/root/reference/libs/fluc/flu-codec-sdk/fluc/threads/fluc_monitor.c:15-70),
+ * worker thread draining a queue under that monitor
+ * (/root/reference/libs/flu/downloader/lib/fludownloader.c:490-532), stats
+ * copied out under the lock (.../bwmeter/fluc_bwmeter.c:71-76).
+ *
+ * No CPU fallback exists anywhere in this file: without a usable CUDA device
+ * every entry point fails with FLUC_TTMLBLEND_ERROR_NO_DEVICE / _CUDA.
+ */
+#include "../../include/fluc_ttmlblend.h"
+#include "ttmlblend_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+using namespace tb;
+
+namespace {
+
+/* ---------------------------------------------------------------------- */
+/* format geometry                                                        */
+
+enum FormatClass { FC_I420, FC_YV12, FC_NV12, FC_NV21, FC_AYUV, FC_ARGB, FC_ABGR, FC_RGBA, FC_BGRA, FC_COUNT };
+
+inline bool
+format_valid (int f)
+{
+  return f >= 0 && f < FLUC_TTMLBLEND_FORMAT_COUNT;
+}
+
+inline int
+format_planes (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_I420:
+    case FLUC_TTMLBLEND_FORMAT_YV12:
+      return 3;
+    case FLUC_TTMLBLEND_FORMAT_NV12:
+    case FLUC_TTMLBLEND_FORMAT_NV21:
+      return 2;
+    default:
+      return 1;
+  }
+}
+
+inline int
+plane_row_bytes (int f, int plane, int w)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_I420:
+    case FLUC_TTMLBLEND_FORMAT_YV12:
+      return plane == 0 ? w : (w + 1) / 2;
+    case FLUC_TTMLBLEND_FORMAT_NV12:
+    case FLUC_TTMLBLEND_FORMAT_NV21:
+      return plane == 0 ? w : 2 * ((w + 1) / 2);
+    default:
+      return 4 * w;
+  }
+}
+
+inline int
+plane_rows (int f, int plane, int h)
+{
+  return (format_planes (f) > 1 && plane > 0) ? (h + 1) / 2 : h;
+}
+
+inline int
+plane_kind (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_AYUV:
+    case FLUC_TTMLBLEND_FORMAT_ARGB:
+    case FLUC_TTMLBLEND_FORMAT_ABGR:
+      return PK_PACKED_A0;
+    case FLUC_TTMLBLEND_FORMAT_RGBA:
+    case FLUC_TTMLBLEND_FORMAT_BGRA:
+      return PK_PACKED_A3;
+    default:
+      return PK_PLANE8;
+  }
+}
+
+inline int ceil_div (int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up (size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+/* ---------------------------------------------------------------------- */
+/* overlay cache                                                          */
+
+struct Ctx;
+
+/* device copy of one rectangle's BGRA pixels (left/top clipped at 0) */
+struct RawRect {
+  uint8_t *dev = nullptr;
+  int pitch = 0, w = 0, h = 0;
+  int x = 0, y = 0;
+  int ga = 255;
+  bool premul = true;
+};
+
+/* everything frame-independent, for one (format, W, H) */
+struct Prepared {
+  int format = -1, W = 0, H = 0;
+  std::vector<void *> allocs;
+  std::vector<RectRef> h_rects[3];     /* per plane, host copy */
+  RectRef *d_rects[3] = { nullptr, nullptr, nullptr };
+  uint64_t overlay_px = 0;             /* sum of clipped w*h */
+  cudaEvent_t ready = nullptr;
+};
+
+struct Overlay {
+  Ctx *ctx = nullptr;
+  std::vector<RawRect> rects;
+  std::vector<std::unique_ptr<Prepared>> prepared;
+  ~Overlay ();
+};
+
+struct PendingFrame {
+  uint64_t ticket;
+  std::shared_ptr<Overlay> overlay;
+  Prepared *prep;
+  int kind;
+  std::vector<PlaneJob> jobs;
+  uint64_t algo_bytes;
+};
+
+struct Batch {
+  uint64_t last_ticket;
+  cudaEvent_t done;
+  cudaEvent_t t0, t1;                  /* profiling pair (may be null) */
+  std::vector<std::shared_ptr<Overlay>> keep;
+};
+
+struct TableSlot {
+  PlaneJob *h_jobs = nullptr, *d_jobs = nullptr;
+  uint32_t *h_begin = nullptr, *d_begin = nullptr;
+  size_t cap = 0;
+  cudaEvent_t copied = nullptr;
+};
+
+struct PoolEntry {
+  void *base;
+  size_t bytes;
+  int fmt, W, H, on_host;
+  FlucTtmlBlendFrame frame;
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint64_t ticket = 0;
+  bool busy = false;
+  uint8_t *dev = nullptr;
+  size_t dev_bytes = 0;
+  TableSlot table;
+  std::shared_ptr<Overlay> keep;
+};
+
+constexpr int kLanes = 4;
+constexpr int kTableSlots = 8;
+
+struct Ctx {
+  int device = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int sticky = 0;
+  std::string cuda_error;
+
+  cudaStream_t blend_stream = nullptr, up_stream = nullptr, reaper = nullptr;
+  cudaEvent_t ev_fence[kLanes + 2] = {};
+  cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+
+  std::unordered_map<uint32_t, std::shared_ptr<Overlay>> overlays;
+
+  std::vector<PendingFrame> pending;
+  std::chrono::steady_clock::time_point oldest_pending;
+  uint64_t next_ticket = 0, launched_ticket = 0, done_ticket = 0;
+  std::deque<Batch> batches;
+  std::vector<cudaEvent_t> event_pool;
+  TableSlot slots[kTableSlots];
+  int next_slot = 0;
+
+  uint32_t max_batch = 32, linger_us = 200;
+  bool profiling = false;
+  std::thread sched;
+  bool quit = false;
+
+  Lane lanes[kLanes];
+  int next_lane = 0;
+  std::map<uint64_t, int> lane_tickets;
+
+  std::vector<PoolEntry> pool_free, pool_used;
+  uint8_t *scrub = nullptr;
+  size_t scrub_bytes = 0;
+
+  FlucTtmlBlendStats stats = {};
+};
+
+#define CU(ctx, call) do {                                                   \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) {                                                 \
+      (ctx)->sticky = FLUC_TTMLBLEND_ERROR_CUDA;                             \
+      (ctx)->cuda_error = std::string (#call) + ": " + cudaGetErrorString (e_); \
+      return e_ == cudaErrorMemoryAllocation ?                               \
+          FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY : FLUC_TTMLBLEND_ERROR_CUDA;    \
+    }                                                                        \
+  } while (0)
+
+int
+log_level ()
+{
+  static int lvl = -1;
+  if (lvl < 0) {
+    const char *e = getenv ("FLUC_TTMLBLEND_DEBUG");
+    lvl = e ? atoi (e) : 0;
+  }
+  return lvl;
+}
+
+#define TBLOG(n, ...) do { if (log_level () >= (n)) { fprintf (stderr, "ttmlblend: " __VA_ARGS__); fputc ('\n', stderr); } } while (0)
+
+cudaEvent_t
+event_get (Ctx *c)
+{
+  if (!c->event_pool.empty ()) {
+    cudaEvent_t e = c->event_pool.back ();
+    c->event_pool.pop_back ();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+  return e;
+}
+
+/* Frees device memory once everything already queued on any of the
+ * context's streams has run: the reaper stream waits for a fence event on
+ * each of them, then frees in stream order. */
+void
+free_deferred (Ctx *c, const std::vector<void *> &ptrs)
+{
+  if (ptrs.empty ())
+    return;
+  cudaStream_t all[kLanes + 2];
+  int n = 0;
+  all[n++] = c->blend_stream;
+  all[n++] = c->up_stream;
+  for (int i = 0; i < kLanes; i++)
+    all[n++] = c->lanes[i].stream;
+  for (int i = 0; i < n; i++) {
+    if (!all[i])
+      continue;
+    cudaEventRecord (c->ev_fence[i], all[i]);
+    cudaStreamWaitEvent (c->reaper, c->ev_fence[i], 0);
+  }
+  for (void *p : ptrs)
+    cudaFreeAsync (p, c->reaper);
+}
+
+Overlay::~Overlay ()
+{
+  std::vector<void *> ptrs;
+  for (auto &r : rects)
+    if (r.dev)
+      ptrs.push_back (r.dev);
+  for (auto &p : prepared) {
+    for (void *a : p->allocs)
+      ptrs.push_back (a);
+    if (p->ready)
+      cudaEventDestroy (p->ready);
+  }
+  if (ctx)
+    free_deferred (ctx, ptrs);
+}
+
+/* ---------------------------------------------------------------------- */
+/* prepare: raw BGRA rectangle -> per-plane prepared overlay              */
+
+int
+dev_alloc (Ctx *c, Prepared *p, size_t bytes, uint8_t **out)
+{
+  void *ptr = nullptr;
+  CU (c, cudaMallocAsync (&ptr, std::max<size_t> (bytes, 16), c->up_stream));
+  p->allocs.push_back (ptr);
+  *out = static_cast<uint8_t *> (ptr);
+  return 0;
+}
+
+int
+prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
+{
+  for (auto &p : ov->prepared)
+    if (p->format == format && p->W == W && p->H == H) {
+      *out = p.get ();
+      return 0;
+    }
+
+  std::unique_ptr<Prepared> P (new Prepared ());
+  P->format = format;
+  P->W = W;
+  P->H = H;
+  const int kind = plane_kind (format);
+  const int n_planes = format_planes (format);
+
+  for (const RawRect &rr : ov->rects) {
+    /* gst_video_blend clipping: rr is already clipped at the left/top */
+    const int cx0 = rr.x, cy0 = rr.y;
+    const int cx1 = std::min (rr.x + rr.w, W), cy1 = std::min (rr.y + rr.h, H);
+    if (cx1 <= cx0 || cy1 <= cy0)
+      continue;
+    P->overlay_px += (uint64_t) (cx1 - cx0) * (uint64_t) (cy1 - cy0);
+    if (rr.ga == 0)
+      continue;                 /* asrc == 0 everywhere: blends nothing */
+
+    PrepareParams pp = {};
+    pp.raw = rr.dev;
+    pp.raw_pitch = rr.pitch;
+    pp.raw_w = rr.w;
+    pp.raw_h = rr.h;
+    pp.fx = rr.x;
+    pp.fy = rr.y;
+    pp.cx0 = cx0; pp.cy0 = cy0; pp.cx1 = cx1; pp.cy1 = cy1;
+    pp.ga = rr.ga;
+    pp.premul = rr.premul ? 1 : 0;
+
+    if (kind == PK_PLANE8) {
+      /* luma plane: byte == pixel */
+      {
+        RectRef ref = {};
+        ref.v0 = cx0 / 16;
+        ref.v1 = ceil_div (cx1, 16);
+        ref.y0 = cy0;
+        ref.y1 = cy1;
+        ref.pitch = (ref.v1 - ref.v0) * 16;
+        ref.ga = 255;
+        const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+        uint8_t *a, *y;
+        int rc;
+        if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &y)))
+          return rc;
+        ref.a = a;
+        ref.c = y;
+        pp.mode = PM_LUMA;
+        pp.out_a = a; pp.out_c = y; pp.out_c2 = nullptr;
+        pp.out_pitch = ref.pitch;
+        pp.v0 = ref.v0;
+        pp.row0 = cy0;
+        pp.rows = cy1 - cy0;
+        CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
+        c->stats.prepare_launches++;
+        P->h_rects[0].push_back (ref);
+      }
+      /* chroma: the samples sited on even x / even y */
+      const int bx0 = ceil_div (cx0, 2), bx1 = ceil_div (cx1, 2);
+      const int by0 = ceil_div (cy0, 2), by1 = ceil_div (cy1, 2);
+      if (bx1 > bx0 && by1 > by0) {
+        if (n_planes == 3) {
+          RectRef ref = {};
+          ref.v0 = bx0 / 16;
+          ref.v1 = ceil_div (bx1, 16);
+          ref.y0 = by0;
+          ref.y1 = by1;
+          ref.pitch = (ref.v1 - ref.v0) * 16;
+          ref.ga = 255;
+          const size_t bytes = (size_t) ref.pitch * (by1 - by0);
+          uint8_t *a, *u, *v;
+          int rc;
+          if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &u))
+              || (rc = dev_alloc (c, P.get (), bytes, &v)))
+            return rc;
+          pp.mode = PM_CHROMA_PLANAR;
+          pp.out_a = a; pp.out_c = u; pp.out_c2 = v;
+          pp.out_pitch = ref.pitch;
+          pp.v0 = ref.v0;
+          pp.row0 = by0;
+          pp.rows = by1 - by0;
+          CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
+          c->stats.prepare_launches++;
+          const int pu = format == FLUC_TTMLBLEND_FORMAT_I420 ? 1 : 2;
+          const int pv = 3 - pu;
+          ref.a = a;
+          ref.c = u;
+          P->h_rects[pu].push_back (ref);
+          ref.c = v;
+          P->h_rects[pv].push_back (ref);
+        } else {
+          RectRef ref = {};
+          ref.v0 = (2 * bx0) / 16;
+          ref.v1 = ceil_div (2 * bx1, 16);
+          ref.y0 = by0;
+          ref.y1 = by1;
+          ref.pitch = (ref.v1 - ref.v0) * 16;
+          ref.ga = 255;
+          const size_t bytes = (size_t) ref.pitch * (by1 - by0);
+          uint8_t *a, *uv;
+          int rc;
+          if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &uv)))
+            return rc;
+          pp.mode = format == FLUC_TTMLBLEND_FORMAT_NV12 ? PM_CHROMA_UV : PM_CHROMA_VU;
+          pp.out_a = a; pp.out_c = uv; pp.out_c2 = nullptr;
+          pp.out_pitch = ref.pitch;
+          pp.v0 = ref.v0;
+          pp.row0 = by0;
+          pp.rows = by1 - by0;
+          CU (c, launch_prepare (pp, ref.pitch / 2, c->up_stream));
+          c->stats.prepare_launches++;
+          ref.a = a;
+          ref.c = uv;
+          P->h_rects[1].push_back (ref);
+        }
+      }
+    } else {
+      RectRef ref = {};
+      ref.v0 = cx0 / 4;
+      ref.v1 = ceil_div (cx1, 4);
+      ref.y0 = cy0;
+      ref.y1 = cy1;
+      ref.pitch = (ref.v1 - ref.v0) * 16;
+      ref.ga = rr.ga;
+      const bool yuv = format == FLUC_TTMLBLEND_FORMAT_AYUV;
+      ref.src_premul = (!yuv && rr.premul) ? 1 : 0;
+      const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+      uint8_t *w;
+      int rc;
+      if ((rc = dev_alloc (c, P.get (), bytes, &w)))
+        return rc;
+      switch (format) {
+        case FLUC_TTMLBLEND_FORMAT_AYUV: pp.mode = PM_PACKED_AYUV; break;
+        case FLUC_TTMLBLEND_FORMAT_ARGB: pp.mode = PM_PACKED_ARGB; break;
+        case FLUC_TTMLBLEND_FORMAT_ABGR: pp.mode = PM_PACKED_ABGR; break;
+        case FLUC_TTMLBLEND_FORMAT_RGBA: pp.mode = PM_PACKED_RGBA; break;
+        default: pp.mode = PM_PACKED_BGRA; break;
+      }
+      pp.out_a = w; pp.out_c = nullptr; pp.out_c2 = nullptr;
+      pp.out_pitch = ref.pitch;
+      pp.v0 = ref.v0;
+      pp.row0 = cy0;
+      pp.rows = cy1 - cy0;
+      CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
+      c->stats.prepare_launches++;
+      ref.a = w;
+      ref.c = nullptr;
+      P->h_rects[0].push_back (ref);
+    }
+  }
+
+  /* rectangle tables */
+  for (int pl = 0; pl < 3; pl++) {
+    if (P->h_rects[pl].empty ())
+      continue;
+    if (P->h_rects[pl].size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+      return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+    uint8_t *d;
+    const size_t bytes = P->h_rects[pl].size () * sizeof (RectRef);
+    int rc;
+    if ((rc = dev_alloc (c, P.get (), bytes, &d)))
+      return rc;
+    /* pageable source: the copy has left the host buffer when this returns */
+    CU (c, cudaMemcpyAsync (d, P->h_rects[pl].data (), bytes, cudaMemcpyHostToDevice, c->up_stream));
+    P->d_rects[pl] = reinterpret_cast<RectRef *> (d);
+  }
+  CU (c, cudaEventCreateWithFlags (&P->ready, cudaEventDisableTiming));
+  CU (c, cudaEventRecord (P->ready, c->up_stream));
+  *out = P.get ();
+  ov->prepared.push_back (std::move (P));
+  return 0;
+}
+
+/* ---------------------------------------------------------------------- */
+/* plane jobs                                                             */
+
+bool
+spans_intersect (const RectRef &a, const RectRef &b)
+{
+  return a.v0 < b.v1 && b.v0 < a.v1 && a.y0 < b.y1 && b.y0 < a.y1;
+}
+
+void
+push_window (std::vector<PlaneJob> &jobs, PlaneJob base, int v0, int v1, int y0, int y1)
+{
+  if (v1 <= v0 || y1 <= y0)
+    return;
+  const uint32_t nv = (uint32_t) (v1 - v0);
+  /* magic division exactness: item * e < 2^32 with e = magic*nv - 2^32 < nv */
+  const uint64_t magic = ((1ull << 32) + nv - 1) / nv;
+  const uint64_t e = magic * nv - (1ull << 32);
+  uint64_t max_items = e ? ((1ull << 32) - 1) / e : (1ull << 31);
+  max_items = std::min<uint64_t> (max_items, 1ull << 31);
+  int max_rows = (int) std::max<uint64_t> (1, std::min<uint64_t> (max_items / nv, 1 << 30));
+  for (int r0 = y0; r0 < y1; r0 += max_rows) {
+    PlaneJob j = base;
+    j.win_v0 = v0;
+    j.win_nv = (int32_t) nv;
+    j.win_y0 = r0;
+    j.win_rows = std::min (max_rows, y1 - r0);
+    j.div_magic = (uint32_t) magic;     /* nv == 1 -> 2^32 truncates to 0; kernel special-cases it */
+    const uint64_t items = (uint64_t) nv * (uint64_t) j.win_rows;
+    j.n_chunks = (uint32_t) ((items + kItemsPerChunk - 1) / kItemsPerChunk);
+    jobs.push_back (j);
+  }
+}
+
+/* Builds the plane jobs of one frame. Returns algorithmic bytes moved. */
+uint64_t
+build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
+    const FlucTtmlBlendFrame *dst, const Prepared *prep, std::vector<PlaneJob> &jobs)
+{
+  const int n_planes = format_planes (format);
+  const bool inplace = src->plane[0] == dst->plane[0];
+  uint64_t bytes = 0;
+  for (int pl = 0; pl < n_planes; pl++) {
+    PlaneJob b = {};
+    b.src = static_cast<const uint8_t *> (src->plane[pl]);
+    b.dst = static_cast<uint8_t *> (dst->plane[pl]);
+    b.src_pitch = src->stride[pl];
+    b.dst_pitch = dst->stride[pl];
+    b.row_bytes = plane_row_bytes (format, pl, W);
+    b.kind = plane_kind (format);
+    const int rows = plane_rows (format, pl, H);
+    const bool aligned = (((uintptr_t) b.src | (uintptr_t) b.dst | (uintptr_t) b.src_pitch |
+            (uintptr_t) b.dst_pitch) & 15u) == 0;
+    b.flags = (aligned ? JF_VECTOR : 0) | (inplace ? JF_INPLACE : 0) |
+        ((frame_flags & FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA) ? JF_DST_PREMUL : 0);
+    const std::vector<RectRef> *rects = prep ? &prep->h_rects[pl] : nullptr;
+    b.rects = prep ? prep->d_rects[pl] : nullptr;
+    b.n_rects = rects ? (int32_t) rects->size () : 0;
+    const int nv_row = ceil_div (b.row_bytes, 16);
+    if (!inplace) {
+      push_window (jobs, b, 0, nv_row, 0, rows);
+      bytes += 2ull * (uint64_t) b.row_bytes * (uint64_t) rows;
+      continue;
+    }
+    if (b.n_rects == 0)
+      continue;
+    bool disjoint = true;
+    for (size_t i = 0; i < rects->size () && disjoint; i++)
+      for (size_t k = i + 1; k < rects->size (); k++)
+        if (spans_intersect ((*rects)[i], (*rects)[k])) {
+          disjoint = false;
+          break;
+        }
+    if (disjoint) {
+      for (const RectRef &r : *rects) {
+        const int v1 = std::min (r.v1, nv_row), y1 = std::min (r.y1, rows);
+        push_window (jobs, b, r.v0, v1, r.y0, y1);
+        if (v1 > r.v0 && y1 > r.y0)
+          bytes += 2ull * (uint64_t) std::min ((v1 - r.v0) * 16, b.row_bytes - r.v0 * 16) * (uint64_t) (y1 - r.y0);
+      }
+    } else {
+      int v0 = 1 << 30, v1 = 0, y0 = 1 << 30, y1 = 0;
+      for (const RectRef &r : *rects) {
+        v0 = std::min (v0, r.v0); v1 = std::max (v1, r.v1);
+        y0 = std::min (y0, r.y0); y1 = std::max (y1, r.y1);
+      }
+      v1 = std::min (v1, nv_row);
+      y1 = std::min (y1, rows);
+      push_window (jobs, b, v0, v1, y0, y1);
+      if (v1 > v0 && y1 > y0)
+        bytes += 2ull * (uint64_t) std::min ((v1 - v0) * 16, b.row_bytes - v0 * 16) * (uint64_t) (y1 - y0);
+    }
+  }
+  if (prep)
+    bytes += 4ull * prep->overlay_px;
+  return bytes;
+}
+
+int
+slot_reserve (Ctx *c, TableSlot &s, size_t n)
+{
+  if (s.cap >= n)
+    return 0;
+  const size_t cap = std::max<size_t> (256, n * 2);
+  if (s.h_jobs) cudaFreeHost (s.h_jobs);
+  if (s.h_begin) cudaFreeHost (s.h_begin);
+  if (s.d_jobs) cudaFree (s.d_jobs);
+  if (s.d_begin) cudaFree (s.d_begin);
+  s.cap = 0;
+  CU (c, cudaHostAlloc ((void **) &s.h_jobs, cap * sizeof (PlaneJob), cudaHostAllocDefault));
+  CU (c, cudaHostAlloc ((void **) &s.h_begin, cap * sizeof (uint32_t), cudaHostAllocDefault));
+  CU (c, cudaMalloc ((void **) &s.d_jobs, cap * sizeof (PlaneJob)));
+  CU (c, cudaMalloc ((void **) &s.d_begin, cap * sizeof (uint32_t)));
+  if (!s.copied)
+    CU (c, cudaEventCreateWithFlags (&s.copied, cudaEventDisableTiming));
+  s.cap = cap;
+  return 0;
+}
+
+/* Copies `jobs` (one PlaneKind) into a table slot and launches the kernel. */
+int
+launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, cudaStream_t stream,
+    cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr)
+{
+  if (n == 0)
+    return 0;
+  if (s.copied && s.cap)
+    CU (c, cudaEventSynchronize (s.copied));
+  int rc = slot_reserve (c, s, n);
+  if (rc)
+    return rc;
+  uint32_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    s.h_jobs[i] = jobs[i];
+    s.h_begin[i] = total;
+    total += jobs[i].n_chunks;
+  }
+  CU (c, cudaMemcpyAsync (s.d_jobs, s.h_jobs, n * sizeof (PlaneJob), cudaMemcpyHostToDevice, stream));
+  CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, n * sizeof (uint32_t), cudaMemcpyHostToDevice, stream));
+  CU (c, cudaEventRecord (s.copied, stream));
+  if (t0)
+    CU (c, cudaEventRecord (t0, stream));
+  CU (c, launch_blend (s.d_jobs, s.d_begin, (int) n, total, kind, stream));
+  if (t1)
+    CU (c, cudaEventRecord (t1, stream));
+  c->stats.launches++;
+  return 0;
+}
+
+void
+reap_batches (Ctx *c)
+{
+  while (!c->batches.empty ()) {
+    Batch &b = c->batches.front ();
+    if (cudaEventQuery (b.done) != cudaSuccess)
+      break;
+    if (b.t0 && b.t1) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime (&ms, b.t0, b.t1) == cudaSuccess) {
+        c->stats.kernel_ms += ms;
+        c->stats.kernel_ms_launches++;
+      }
+      cudaEventDestroy (b.t0);
+      cudaEventDestroy (b.t1);
+    }
+    c->done_ticket = b.last_ticket;
+    c->event_pool.push_back (b.done);
+    c->batches.pop_front ();
+  }
+}
+
+/* Launches everything pending as one batch (per plane kind). mu held. */
+int
+launch_pending (Ctx *c)
+{
+  if (c->pending.empty ())
+    return 0;
+  reap_batches (c);
+  Batch b = {};
+  b.last_ticket = c->pending.back ().ticket;
+  std::vector<PlaneJob> by_kind[3];
+  std::vector<Prepared *> waited;
+  for (PendingFrame &f : c->pending) {
+    for (const PlaneJob &j : f.jobs)
+      by_kind[f.kind].push_back (j);
+    if (f.overlay)
+      b.keep.push_back (f.overlay);
+    if (f.prep && std::find (waited.begin (), waited.end (), f.prep) == waited.end ()) {
+      waited.push_back (f.prep);
+      CU (c, cudaStreamWaitEvent (c->blend_stream, f.prep->ready, 0));
+    }
+    c->stats.frames_blended++;
+    c->stats.algorithmic_bytes += f.algo_bytes;
+  }
+  c->pending.clear ();
+  int n_kinds = 0;
+  for (int k = 0; k < 3; k++)
+    n_kinds += !by_kind[k].empty ();
+  if (c->profiling && n_kinds == 1) {
+    CU (c, cudaEventCreate (&b.t0));
+    CU (c, cudaEventCreate (&b.t1));
+  }
+  for (int k = 0; k < 3; k++) {
+    if (by_kind[k].empty ())
+      continue;
+    TableSlot &s = c->slots[c->next_slot];
+    c->next_slot = (c->next_slot + 1) % kTableSlots;
+    int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k, c->blend_stream, b.t0, b.t1);
+    if (rc)
+      return rc;
+  }
+  b.done = event_get (c);
+  CU (c, cudaEventRecord (b.done, c->blend_stream));
+  c->launched_ticket = b.last_ticket;
+  c->batches.push_back (std::move (b));
+  return 0;
+}
+
+void
+scheduler_main (Ctx *c)
+{
+  cudaSetDevice (c->device);
+  std::unique_lock<std::mutex> lk (c->mu);
+  while (!c->quit) {
+    if (c->pending.empty () || c->linger_us == 0) {
+      c->cv.wait (lk);
+      continue;
+    }
+    const auto deadline = c->oldest_pending + std::chrono::microseconds (c->linger_us);
+    if (std::chrono::steady_clock::now () >= deadline) {
+      if (!c->sticky)
+        launch_pending (c);
+      else
+        c->pending.clear ();
+    } else {
+      c->cv.wait_until (lk, deadline);
+    }
+  }
+}
+
+int
+check_frame (int fmt, int W, int H, const FlucTtmlBlendFrame *f)
+{
+  if (!f)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  if (!format_valid (fmt))
+    return FLUC_TTMLBLEND_ERROR_UNSUPPORTED_FORMAT;
+  if (W <= 0 || H <= 0 || W > 32768 || H > 32768)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  for (int pl = 0; pl < format_planes (fmt); pl++)
+    if (!f->plane[pl] || f->stride[pl] < plane_row_bytes (fmt, pl, W))
+      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  return 0;
+}
+
+/* Decomposes possibly overlapping region rectangles into disjoint ones that
+ * cover the same pixels, so that every pixel of the ttmlrender image is
+ * blended exactly once. */
+std::vector<FlucTtmlBlendRect>
+disjoint_cover (const std::vector<FlucTtmlBlendRect> &in)
+{
+  std::vector<int> ys;
+  for (auto &r : in) {
+    ys.push_back (r.y);
+    ys.push_back (r.y + r.h);
+  }
+  std::sort (ys.begin (), ys.end ());
+  ys.erase (std::unique (ys.begin (), ys.end ()), ys.end ());
+  std::vector<FlucTtmlBlendRect> out;
+  for (size_t i = 0; i + 1 < ys.size (); i++) {
+    const int y0 = ys[i], y1 = ys[i + 1];
+    std::vector<std::pair<int, int>> xs;
+    for (auto &r : in)
+      if (r.y <= y0 && r.y + r.h >= y1)
+        xs.push_back ({ r.x, r.x + r.w });
+    std::sort (xs.begin (), xs.end ());
+    std::vector<std::pair<int, int>> merged;
+    for (auto &x : xs) {
+      if (!merged.empty () && x.first <= merged.back ().second)
+        merged.back ().second = std::max (merged.back ().second, x.second);
+      else
+        merged.push_back (x);
+    }
+    for (auto &m : merged) {
+      bool grown = false;
+      for (auto &o : out)
+        if (o.x == m.first && o.w == m.second - m.first && o.y + o.h == y0) {
+          o.h += y1 - y0;
+          grown = true;
+          break;
+        }
+      if (!grown)
+        out.push_back ({ m.first, y0, m.second - m.first, y1 - y0 });
+    }
+  }
+  return out;
+}
+
+int
+overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n)
+{
+  std::shared_ptr<Overlay> ov (new Overlay ());
+  ov->ctx = c;
+  for (uint32_t i = 0; i < n; i++) {
+    const FlucTtmlBlendRectangle &r = rects[i];
+    if (!r.pixels || r.width <= 0 || r.height <= 0 || r.stride < r.width * 4)
+      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+    /* gst_video_blend: negative offsets skip source columns / rows */
+    const int xoff = r.x < 0 ? -r.x : 0, yoff = r.y < 0 ? -r.y : 0;
+    if (xoff >= r.width || yoff >= r.height)
+      continue;
+    RawRect rr;
+    rr.w = r.width - xoff;
+    rr.h = r.height - yoff;
+    rr.x = r.x + xoff;
+    rr.y = r.y + yoff;
+    rr.ga = (int) (255.0 * r.global_alpha);
+    rr.ga = std::max (0, std::min (255, rr.ga));
+    rr.premul = (r.flags & FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA) != 0;
+    rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
+    void *d = nullptr;
+    CU (c, cudaMallocAsync (&d, (size_t) rr.pitch * rr.h, c->up_stream));
+    rr.dev = static_cast<uint8_t *> (d);
+    ov->rects.push_back (rr);
+    CU (c, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
+            r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
+    c->stats.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+  }
+  /* the caller's pixels must be consumed before we return */
+  CU (c, cudaStreamSynchronize (c->up_stream));
+  c->overlays[stream] = ov;       /* frames already queued keep the old one */
+  c->stats.overlays_set++;
+  return 0;
+}
+
+int
+lane_reserve (Ctx *c, Lane &l, size_t bytes)
+{
+  if (l.dev_bytes >= bytes)
+    return 0;
+  if (l.dev)
+    CU (c, cudaFree (l.dev));
+  l.dev = nullptr;
+  l.dev_bytes = 0;
+  CU (c, cudaMalloc ((void **) &l.dev, bytes));
+  l.dev_bytes = bytes;
+  return 0;
+}
+
+}  // namespace
+
+struct _FlucTtmlBlend {
+  Ctx c;
+};
+
+#define ENTER(thiz)                                                          \
+  if (!(thiz)) return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;                 \
+  Ctx *c = &(thiz)->c;                                                       \
+  std::unique_lock<std::mutex> lk (c->mu);                                   \
+  if (c->sticky) return c->sticky;                                           \
+  cudaSetDevice (c->device)
+
+extern "C" {
+
+const char *
+fluc_ttmlblend_version (void)
+{
+  return "fluc_ttmlblend 0.1 (sm_100a)";
+}
+
+const char *
+fluc_ttmlblend_strerror (int err)
+{
+  switch (err) {
+    case FLUC_TTMLBLEND_OK: return "ok";
+    case FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT: return "invalid argument";
+    case FLUC_TTMLBLEND_ERROR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case FLUC_TTMLBLEND_ERROR_CUDA: return "CUDA error (context unusable)";
+    case FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY: return "out of memory";
+    case FLUC_TTMLBLEND_ERROR_UNSUPPORTED_FORMAT: return "unsupported video format";
+    case FLUC_TTMLBLEND_ERROR_NOT_FOUND: return "not found";
+    case FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES: return "too many rectangles";
+    default: return "unknown error";
+  }
+}
+
+int
+fluc_ttmlblend_device_count (void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess) {
+    cudaGetLastError ();
+    return 0;
+  }
+  return n;
+}
+
+int
+fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
+{
+  if (!out)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError ();
+    return FLUC_TTMLBLEND_ERROR_NO_DEVICE;
+  }
+  if (device < 0) {
+    const char *e = getenv ("FLUC_TTMLBLEND_DEVICE");
+    device = e ? atoi (e) : 0;
+  }
+  if (device >= n)
+    return FLUC_TTMLBLEND_ERROR_NO_DEVICE;
+  if (cudaSetDevice (device) != cudaSuccess) {
+    cudaGetLastError ();
+    return FLUC_TTMLBLEND_ERROR_NO_DEVICE;
+  }
+  FlucTtmlBlend *t = new (std::nothrow) FlucTtmlBlend ();
+  if (!t)
+    return FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY;
+  Ctx *c = &t->c;
+  c->device = device;
+  bool ok = true;
+  ok &= cudaStreamCreateWithFlags (&c->blend_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags (&c->up_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags (&c->reaper, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < kLanes + 2 && ok; i++)
+    ok &= cudaEventCreateWithFlags (&c->ev_fence[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < kLanes && ok; i++) {
+    ok &= cudaStreamCreateWithFlags (&c->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags (&c->lanes[i].done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok &= cudaEventCreate (&c->timer0) == cudaSuccess;
+  ok &= cudaEventCreate (&c->timer1) == cudaSuccess;
+  if (ok) {
+    /* keep freed overlay memory in the pool instead of returning it to the OS */
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool (&pool, device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  if (!ok) {
+    cudaGetLastError ();
+    delete t;
+    return FLUC_TTMLBLEND_ERROR_NO_DEVICE;
+  }
+  const char *e;
+  if ((e = getenv ("FLUC_TTMLBLEND_BATCH")))
+    c->max_batch = (uint32_t) std::max (1, std::min (1024, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_LINGER_US")))
+    c->linger_us = (uint32_t) std::max (0, atoi (e));
+  c->sched = std::thread (scheduler_main, c);
+  *out = t;
+  TBLOG (1, "context on device %d", device);
+  return 0;
+}
+
+void
+fluc_ttmlblend_free (FlucTtmlBlend *thiz)
+{
+  if (!thiz)
+    return;
+  Ctx *c = &thiz->c;
+  {
+    std::unique_lock<std::mutex> lk (c->mu);
+    c->quit = true;
+    c->cv.notify_all ();
+  }
+  if (c->sched.joinable ())
+    c->sched.join ();
+  cudaSetDevice (c->device);
+  cudaDeviceSynchronize ();
+  {
+    std::unique_lock<std::mutex> lk (c->mu);
+    c->pending.clear ();
+    for (auto &b : c->batches) {
+      if (b.t0) cudaEventDestroy (b.t0);
+      if (b.t1) cudaEventDestroy (b.t1);
+      cudaEventDestroy (b.done);
+    }
+    c->batches.clear ();
+    for (int i = 0; i < kLanes; i++)
+      c->lanes[i].keep.reset ();
+    c->overlays.clear ();       /* frees through the reaper stream */
+    cudaStreamSynchronize (c->reaper);
+    for (auto e : c->event_pool)
+      cudaEventDestroy (e);
+    auto free_slot = [](TableSlot &s) {
+      if (s.h_jobs) cudaFreeHost (s.h_jobs);
+      if (s.h_begin) cudaFreeHost (s.h_begin);
+      if (s.d_jobs) cudaFree (s.d_jobs);
+      if (s.d_begin) cudaFree (s.d_begin);
+      if (s.copied) cudaEventDestroy (s.copied);
+    };
+    for (auto &s : c->slots)
+      free_slot (s);
+    for (int i = 0; i < kLanes; i++) {
+      free_slot (c->lanes[i].table);
+      if (c->lanes[i].dev) cudaFree (c->lanes[i].dev);
+      if (c->lanes[i].done) cudaEventDestroy (c->lanes[i].done);
+      if (c->lanes[i].stream) cudaStreamDestroy (c->lanes[i].stream);
+    }
+    for (auto &p : c->pool_free) {
+      if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
+    }
+    for (auto &p : c->pool_used) {
+      if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
+    }
+    if (c->scrub) cudaFree (c->scrub);
+    for (auto e : c->ev_fence)
+      if (e) cudaEventDestroy (e);
+    if (c->timer0) cudaEventDestroy (c->timer0);
+    if (c->timer1) cudaEventDestroy (c->timer1);
+    cudaStreamDestroy (c->blend_stream);
+    cudaStreamDestroy (c->up_stream);
+    cudaStreamDestroy (c->reaper);
+  }
+  delete thiz;
+}
+
+const char *
+fluc_ttmlblend_last_cuda_error (FlucTtmlBlend *thiz)
+{
+  if (!thiz)
+    return "";
+  std::unique_lock<std::mutex> lk (thiz->c.mu);
+  return thiz->c.cuda_error.c_str ();
+}
+
+/* ---- overlay --------------------------------------------------------- */
+
+int
+fluc_ttmlblend_overlay_set_rectangles (FlucTtmlBlend *thiz, uint32_t stream,
+    const FlucTtmlBlendRectangle *rects, uint32_t n_rects)
+{
+  ENTER (thiz);
+  if (n_rects && !rects)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  if (n_rects > FLUC_TTMLBLEND_MAX_RECTANGLES)
+    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+  return overlay_install (c, stream, rects, n_rects);
+}
+
+int
+fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream, const uint8_t *bgra,
+    int32_t w, int32_t h, int32_t stride, const FlucTtmlBlendRect *rects, uint32_t n_rects)
+{
+  ENTER (thiz);
+  if (!bgra || w <= 0 || h <= 0 || stride < 4 * w || (n_rects && !rects))
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  std::vector<FlucTtmlBlendRect> in;
+  if (n_rects == 0) {
+    in.push_back ({ 0, 0, w, h });
+  } else {
+    for (uint32_t i = 0; i < n_rects; i++) {
+      /* region boxes clipped to the image ttmlrender drew them into */
+      const int x0 = std::max (rects[i].x, 0), y0 = std::max (rects[i].y, 0);
+      const int x1 = std::min (rects[i].x + rects[i].w, w), y1 = std::min (rects[i].y + rects[i].h, h);
+      if (x1 > x0 && y1 > y0)
+        in.push_back ({ x0, y0, x1 - x0, y1 - y0 });
+    }
+    in = disjoint_cover (in);
+  }
+  if (in.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+  std::vector<FlucTtmlBlendRectangle> rr;
+  for (auto &r : in) {
+    FlucTtmlBlendRectangle q;
+    q.pixels = bgra + (size_t) r.y * stride + (size_t) r.x * 4;
+    q.width = r.w;
+    q.height = r.h;
+    q.stride = stride;
+    q.x = r.x;
+    q.y = r.y;
+    q.global_alpha = 1.0f;
+    q.flags = FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA;   /* Cairo ARGB32, gstttmlrender.c:1446 */
+    rr.push_back (q);
+  }
+  return overlay_install (c, stream, rr.data (), (uint32_t) rr.size ());
+}
+
+int
+fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream)
+{
+  ENTER (thiz);
+  c->overlays.erase (stream);
+  return 0;
+}
+
+/* ---- device-resident frames ------------------------------------------ */
+
+int
+fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
+    int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
+    const FlucTtmlBlendFrame *dst, uint64_t *ticket)
+{
+  ENTER (thiz);
+  int rc;
+  if ((rc = check_frame (fmt, W, H, src)) || (rc = check_frame (fmt, W, H, dst)))
+    return rc;
+  PendingFrame f;
+  f.kind = plane_kind (fmt);
+  f.prep = nullptr;
+  auto it = c->overlays.find (stream);
+  if (it != c->overlays.end ()) {
+    f.overlay = it->second;
+    if ((rc = prepare_overlay (c, f.overlay.get (), fmt, W, H, &f.prep)))
+      return rc;
+  }
+  f.algo_bytes = build_jobs (fmt, W, H, frame_flags, src, dst, f.prep, f.jobs);
+  f.ticket = ++c->next_ticket;
+  if (ticket)
+    *ticket = f.ticket;
+  if (c->pending.empty ())
+    c->oldest_pending = std::chrono::steady_clock::now ();
+  c->pending.push_back (std::move (f));
+  if (c->pending.size () >= c->max_batch)
+    return launch_pending (c);
+  if (c->linger_us)
+    c->cv.notify_all ();
+  return 0;
+}
+
+int
+fluc_ttmlblend_flush (FlucTtmlBlend *thiz)
+{
+  ENTER (thiz);
+  return launch_pending (c);
+}
+
+int
+fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
+{
+  ENTER (thiz);
+  if (ticket == 0 || ticket > c->next_ticket)
+    return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
+  auto lt = c->lane_tickets.find (ticket);
+  if (lt != c->lane_tickets.end ()) {
+    Lane &l = c->lanes[lt->second];
+    cudaEvent_t ev = l.done;
+    lk.unlock ();
+    cudaError_t e = cudaEventSynchronize (ev);
+    lk.lock ();
+    if (e != cudaSuccess) {
+      c->sticky = FLUC_TTMLBLEND_ERROR_CUDA;
+      c->cuda_error = std::string ("wait: ") + cudaGetErrorString (e);
+      return c->sticky;
+    }
+    auto again = c->lane_tickets.find (ticket);
+    if (again != c->lane_tickets.end ()) {
+      Lane &l2 = c->lanes[again->second];
+      if (l2.ticket == ticket) {
+        l2.busy = false;
+        l2.keep.reset ();
+      }
+      c->lane_tickets.erase (again);
+    }
+    return 0;
+  }
+  if (!c->pending.empty () && ticket >= c->pending.front ().ticket) {
+    int rc = launch_pending (c);
+    if (rc)
+      return rc;
+  }
+  cudaEvent_t ev = nullptr;
+  for (auto &b : c->batches)
+    if (b.last_ticket >= ticket) {
+      ev = b.done;
+      break;
+    }
+  if (!ev) {
+    return 0;                   /* already reaped: finished */
+  }
+  /* the event stays valid while we wait: batches are only reaped under mu,
+   * and a reaped event goes back to the pool, not destroyed */
+  lk.unlock ();
+  cudaError_t e = cudaEventSynchronize (ev);
+  lk.lock ();
+  if (e != cudaSuccess) {
+    c->sticky = FLUC_TTMLBLEND_ERROR_CUDA;
+    c->cuda_error = std::string ("wait: ") + cudaGetErrorString (e);
+    return c->sticky;
+  }
+  reap_batches (c);
+  return 0;
+}
+
+int
+fluc_ttmlblend_sync (FlucTtmlBlend *thiz)
+{
+  ENTER (thiz);
+  int rc = launch_pending (c);
+  if (rc)
+    return rc;
+  CU (c, cudaStreamSynchronize (c->blend_stream));
+  for (int i = 0; i < kLanes; i++) {
+    CU (c, cudaStreamSynchronize (c->lanes[i].stream));
+    c->lanes[i].busy = false;
+    c->lanes[i].keep.reset ();
+  }
+  c->lane_tickets.clear ();
+  CU (c, cudaStreamSynchronize (c->up_stream));
+  reap_batches (c);
+  return 0;
+}
+
+int
+fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_frames, uint32_t linger_us)
+{
+  ENTER (thiz);
+  if (max_frames < 1 || max_frames > 1024)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  c->max_batch = max_frames;
+  c->linger_us = linger_us;
+  c->cv.notify_all ();
+  return 0;
+}
+
+/* ---- host-resident frames -------------------------------------------- */
+
+int
+fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
+    int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *hf, uint64_t *ticket)
+{
+  ENTER (thiz);
+  int rc;
+  if ((rc = check_frame (fmt, W, H, hf)))
+    return rc;
+  const uint64_t tk = ++c->next_ticket;
+  if (ticket)
+    *ticket = tk;
+  auto it = c->overlays.find (stream);
+  if (it == c->overlays.end ())
+    return 0;                   /* no overlay: the frame passes through untouched */
+  std::shared_ptr<Overlay> ov = it->second;
+  Prepared *prep = nullptr;
+  if ((rc = prepare_overlay (c, ov.get (), fmt, W, H, &prep)))
+    return rc;
+
+  Lane &l = c->lanes[c->next_lane];
+  const int lane_idx = c->next_lane;
+  c->next_lane = (c->next_lane + 1) % kLanes;
+  if (l.busy) {
+    CU (c, cudaEventSynchronize (l.done));
+    c->lane_tickets.erase (l.ticket);
+    l.busy = false;
+    l.keep.reset ();
+  }
+
+  /* device staging frame: same strides as a pool frame */
+  const int n_planes = format_planes (fmt);
+  FlucTtmlBlendFrame df = {};
+  size_t off = 0;
+  size_t plane_off[3];
+  for (int pl = 0; pl < n_planes; pl++) {
+    df.stride[pl] = (int32_t) align_up ((size_t) plane_row_bytes (fmt, pl, W), 256);
+    plane_off[pl] = off;
+    off += (size_t) df.stride[pl] * plane_rows (fmt, pl, H);
+  }
+  if ((rc = lane_reserve (c, l, off)))
+    return rc;
+  for (int pl = 0; pl < n_planes; pl++)
+    df.plane[pl] = l.dev + plane_off[pl];
+
+  std::vector<PlaneJob> jobs;
+  const uint64_t algo = build_jobs (fmt, W, H, frame_flags, &df, &df, prep, jobs);
+  if (jobs.empty ())
+    return 0;
+  CU (c, cudaStreamWaitEvent (l.stream, prep->ready, 0));
+
+  /* rows each window touches: host -> device */
+  struct Span { int pl, b0, nb, y0, rows; };
+  std::vector<Span> spans;
+  for (const PlaneJob &j : jobs) {
+    int pl = 0;
+    for (int q = 0; q < n_planes; q++)
+      if (j.dst == df.plane[q])
+        pl = q;
+    Span s;
+    s.pl = pl;
+    s.b0 = j.win_v0 * 16;
+    s.nb = std::min (j.win_nv * 16, j.row_bytes - s.b0);
+    s.y0 = j.win_y0;
+    s.rows = j.win_rows;
+    spans.push_back (s);
+  }
+  for (const Span &s : spans) {
+    uint8_t *d = static_cast<uint8_t *> (df.plane[s.pl]) + (size_t) s.y0 * df.stride[s.pl] + s.b0;
+    const uint8_t *h = static_cast<const uint8_t *> (hf->plane[s.pl]) + (size_t) s.y0 * hf->stride[s.pl] + s.b0;
+    CU (c, cudaMemcpy2DAsync (d, df.stride[s.pl], h, hf->stride[s.pl], s.nb, s.rows,
+            cudaMemcpyHostToDevice, l.stream));
+    c->stats.h2d_bytes += (uint64_t) s.nb * s.rows;
+  }
+  if ((rc = launch_jobs (c, l.table, jobs.data (), jobs.size (), plane_kind (fmt), l.stream)))
+    return rc;
+  for (const Span &s : spans) {
+    const uint8_t *d = static_cast<const uint8_t *> (df.plane[s.pl]) + (size_t) s.y0 * df.stride[s.pl] + s.b0;
+    uint8_t *h = static_cast<uint8_t *> (hf->plane[s.pl]) + (size_t) s.y0 * hf->stride[s.pl] + s.b0;
+    CU (c, cudaMemcpy2DAsync (h, hf->stride[s.pl], d, df.stride[s.pl], s.nb, s.rows,
+            cudaMemcpyDeviceToHost, l.stream));
+    c->stats.d2h_bytes += (uint64_t) s.nb * s.rows;
+  }
+  CU (c, cudaEventRecord (l.done, l.stream));
+  l.busy = true;
+  l.ticket = tk;
+  l.keep = ov;
+  c->lane_tickets[tk] = lane_idx;
+  c->stats.frames_blended++;
+  c->stats.algorithmic_bytes += algo;
+  return 0;
+}
+
+int
+fluc_ttmlblend_host_register (FlucTtmlBlend *thiz, void *ptr, size_t bytes)
+{
+  ENTER (thiz);
+  if (!ptr || !bytes)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostRegister (ptr, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError ();
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  }
+  return 0;
+}
+
+int
+fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr)
+{
+  ENTER (thiz);
+  cudaError_t e = cudaHostUnregister (ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError ();
+    return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
+  }
+  return 0;
+}
+
+/* ---- frame pool ------------------------------------------------------ */
+
+int
+fluc_ttmlblend_format_planes (FlucTtmlBlendFormat fmt)
+{
+  return format_valid (fmt) ? format_planes (fmt) : 0;
+}
+
+int
+fluc_ttmlblend_plane_row_bytes (FlucTtmlBlendFormat fmt, int plane, int32_t width)
+{
+  if (!format_valid (fmt) || plane < 0 || plane >= format_planes (fmt))
+    return 0;
+  return plane_row_bytes (fmt, plane, width);
+}
+
+int
+fluc_ttmlblend_plane_rows (FlucTtmlBlendFormat fmt, int plane, int32_t height)
+{
+  if (!format_valid (fmt) || plane < 0 || plane >= format_planes (fmt))
+    return 0;
+  return plane_rows (fmt, plane, height);
+}
+
+int
+fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt, int32_t W,
+    int32_t H, int on_host, FlucTtmlBlendFrame *out)
+{
+  ENTER (thiz);
+  if (!out || W <= 0 || H <= 0)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  if (!format_valid (fmt))
+    return FLUC_TTMLBLEND_ERROR_UNSUPPORTED_FORMAT;
+  on_host = on_host ? 1 : 0;
+  for (size_t i = 0; i < c->pool_free.size (); i++) {
+    PoolEntry &p = c->pool_free[i];
+    if (p.fmt == fmt && p.W == W && p.H == H && p.on_host == on_host) {
+      *out = p.frame;
+      c->pool_used.push_back (p);
+      c->pool_free.erase (c->pool_free.begin () + i);
+      return 0;
+    }
+  }
+  PoolEntry p = {};
+  p.fmt = fmt; p.W = W; p.H = H; p.on_host = on_host;
+  size_t off = 0, plane_off[3] = { 0, 0, 0 };
+  const int n_planes = format_planes (fmt);
+  for (int pl = 0; pl < n_planes; pl++) {
+    p.frame.stride[pl] = (int32_t) align_up ((size_t) plane_row_bytes (fmt, pl, W), 256);
+    plane_off[pl] = off;
+    off += (size_t) p.frame.stride[pl] * plane_rows (fmt, pl, H);
+  }
+  p.bytes = off;
+  if (on_host)
+    CU (c, cudaHostAlloc (&p.base, off, cudaHostAllocDefault));
+  else
+    CU (c, cudaMalloc (&p.base, off));
+  for (int pl = 0; pl < n_planes; pl++)
+    p.frame.plane[pl] = static_cast<uint8_t *> (p.base) + plane_off[pl];
+  *out = p.frame;
+  c->pool_used.push_back (p);
+  return 0;
+}
+
+int
+fluc_ttmlblend_frame_pool_release (FlucTtmlBlend *thiz, const FlucTtmlBlendFrame *frame)
+{
+  ENTER (thiz);
+  if (!frame)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < c->pool_used.size (); i++)
+    if (c->pool_used[i].frame.plane[0] == frame->plane[0]) {
+      c->pool_free.push_back (c->pool_used[i]);
+      c->pool_used.erase (c->pool_used.begin () + i);
+      return 0;
+    }
+  return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
+}
+
+static int
+frame_copy (Ctx *c, int fmt, int W, int H, const FlucTtmlBlendFrame *s, const FlucTtmlBlendFrame *d,
+    cudaMemcpyKind kind)
+{
+  int rc;
+  if ((rc = check_frame (fmt, W, H, s)) || (rc = check_frame (fmt, W, H, d)))
+    return rc;
+  for (int pl = 0; pl < format_planes (fmt); pl++) {
+    const size_t rb = (size_t) plane_row_bytes (fmt, pl, W);
+    CU (c, cudaMemcpy2DAsync (d->plane[pl], d->stride[pl], s->plane[pl], s->stride[pl], rb,
+            plane_rows (fmt, pl, H), kind, c->blend_stream));
+    if (kind == cudaMemcpyHostToDevice)
+      c->stats.h2d_bytes += rb * plane_rows (fmt, pl, H);
+    else
+      c->stats.d2h_bytes += rb * plane_rows (fmt, pl, H);
+  }
+  CU (c, cudaStreamSynchronize (c->blend_stream));
+  return 0;
+}
+
+int
+fluc_ttmlblend_frame_upload (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt, int32_t W, int32_t H,
+    const FlucTtmlBlendFrame *host_src, const FlucTtmlBlendFrame *dev_dst)
+{
+  ENTER (thiz);
+  return frame_copy (c, fmt, W, H, host_src, dev_dst, cudaMemcpyHostToDevice);
+}
+
+int
+fluc_ttmlblend_frame_download (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt, int32_t W, int32_t H,
+    const FlucTtmlBlendFrame *dev_src, const FlucTtmlBlendFrame *host_dst)
+{
+  ENTER (thiz);
+  int rc = launch_pending (c);
+  if (rc)
+    return rc;
+  return frame_copy (c, fmt, W, H, dev_src, host_dst, cudaMemcpyDeviceToHost);
+}
+
+/* ---- observability --------------------------------------------------- */
+
+void
+fluc_ttmlblend_stats_copy (FlucTtmlBlend *thiz, FlucTtmlBlendStats *out)
+{
+  if (!thiz || !out)
+    return;
+  std::unique_lock<std::mutex> lk (thiz->c.mu);
+  cudaSetDevice (thiz->c.device);
+  reap_batches (&thiz->c);
+  *out = thiz->c.stats;
+}
+
+void
+fluc_ttmlblend_stats_reset (FlucTtmlBlend *thiz)
+{
+  if (!thiz)
+    return;
+  std::unique_lock<std::mutex> lk (thiz->c.mu);
+  cudaSetDevice (thiz->c.device);
+  reap_batches (&thiz->c);
+  thiz->c.stats = FlucTtmlBlendStats ();
+}
+
+int
+fluc_ttmlblend_set_profiling (FlucTtmlBlend *thiz, int enabled)
+{
+  ENTER (thiz);
+  c->profiling = enabled != 0;
+  return 0;
+}
+
+int
+fluc_ttmlblend_timer_begin (FlucTtmlBlend *thiz)
+{
+  ENTER (thiz);
+  int rc = launch_pending (c);
+  if (rc)
+    return rc;
+  CU (c, cudaEventRecord (c->timer0, c->blend_stream));
+  return 0;
+}
+
+int
+fluc_ttmlblend_timer_end (FlucTtmlBlend *thiz, double *ms)
+{
+  ENTER (thiz);
+  int rc = launch_pending (c);
+  if (rc)
+    return rc;
+  CU (c, cudaEventRecord (c->timer1, c->blend_stream));
+  CU (c, cudaEventSynchronize (c->timer1));
+  float f = 0.f;
+  CU (c, cudaEventElapsedTime (&f, c->timer0, c->timer1));
+  if (ms)
+    *ms = f;
+  reap_batches (c);
+  return 0;
+}
+
+int
+fluc_ttmlblend_scrub_l2 (FlucTtmlBlend *thiz, size_t bytes)
+{
+  ENTER (thiz);
+  if (bytes > c->scrub_bytes) {
+    if (c->scrub)
+      CU (c, cudaFree (c->scrub));
+    c->scrub = nullptr;
+    c->scrub_bytes = 0;
+    CU (c, cudaMalloc ((void **) &c->scrub, bytes));
+    c->scrub_bytes = bytes;
+  }
+  CU (c, launch_scrub (c->scrub, bytes, c->blend_stream));
+  return 0;
+}
+
+void *
+fluc_ttmlblend_stream_handle (FlucTtmlBlend *thiz)
+{
+  return thiz ? (void *) thiz->c.blend_stream : nullptr;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,508 @@
+/*
+ * ttmlblend_kernels.cu -- hand-written sm_100a kernels of the TTML overlay
+ * blend: the per-frame blend and the once-per-cue overlay prepare.
+ *
+ * Arithmetic contract: docs/BLENDSPEC.md (gst-plugins-base video-blend.c /
+ * video-format.c as named by BASELINE.json's north_star).
+ * Every formula below is the integer formula of that spec; nothing is
+ * approximated. The kernels are HBM-bound byte work: 128-bit coalesced
+ * loads/stores of the frame rows, overlay vectors from the prepared cache
+ * (L2-resident across the frames of a batch), no tensor cores.
+ */
+#include "ttmlblend_kernels.cuh"
+
+namespace tb {
+
+/* ---------------------------------------------------------------------- */
+/* memory helpers                                                         */
+
+__device__ __forceinline__ uint4
+ld_frame16 (const uint8_t *p)
+{
+  uint4 r;
+  asm volatile ("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+      : "=r" (r.x), "=r" (r.y), "=r" (r.z), "=r" (r.w) : "l" (p));
+  return r;
+}
+
+__device__ __forceinline__ void
+st_frame16 (uint8_t *p, const uint4 &v)
+{
+  asm volatile ("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
+      :: "l" (p), "r" (v.x), "r" (v.y), "r" (v.z), "r" (v.w) : "memory");
+}
+
+/* prepared overlay: read-only for the kernel, re-read by every frame of the
+ * batch, so keep it cacheable */
+__device__ __forceinline__ uint4
+ld_overlay16 (const uint8_t *p)
+{
+  return __ldg (reinterpret_cast<const uint4 *> (p));
+}
+
+template <typename T>
+__device__ __forceinline__ T *
+ldg_ptr (T *const *pp)
+{
+  return reinterpret_cast<T *> (__ldg (reinterpret_cast<const unsigned long long *> (pp)));
+}
+
+/* byte-granular fall-back for unaligned frames and the tail of a row */
+__device__ __forceinline__ uint4
+ld_frame_bytes (const uint8_t *p, int nvalid)
+{
+  uint32_t w[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    if (i < nvalid)
+      w[i >> 2] |= (uint32_t) p[i] << (8 * (i & 3));
+  return make_uint4 (w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void
+st_frame_bytes (uint8_t *p, const uint4 &v, int nvalid)
+{
+  const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    if (i < nvalid)
+      p[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
+}
+
+/* ---------------------------------------------------------------------- */
+/* arithmetic                                                             */
+
+/* x / 255 (truncating) for 0 <= x <= 66298; every caller stays <= 65025 */
+__device__ __forceinline__ uint32_t
+div255 (uint32_t x)
+{
+  return (x * 32897u) >> 23;
+}
+
+/* PLANE8: four destination bytes. Opaque destination, straight source:
+ *   out = (Cs * asrc + Cd * (255 - asrc)) / 255        (OVER00, adst = 255)
+ * asrc == 0 leaves Cd untouched by the same formula, like the `continue`. */
+__device__ __forceinline__ uint32_t
+blend4_plane8 (uint32_t f, uint32_t a, uint32_t c)
+{
+  uint32_t out = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t ak = (a >> (8 * k)) & 0xffu;
+    const uint32_t ck = (c >> (8 * k)) & 0xffu;
+    const uint32_t fk = (f >> (8 * k)) & 0xffu;
+    out |= div255 (ck * ak + fk * (255u - ak)) << (8 * k);
+  }
+  return out;
+}
+
+__device__ __forceinline__ uint4
+blend16_plane8 (uint4 f, const uint4 &a, const uint4 &c)
+{
+  if (a.x) f.x = blend4_plane8 (f.x, a.x, c.x);
+  if (a.y) f.y = blend4_plane8 (f.y, a.y, c.y);
+  if (a.z) f.z = blend4_plane8 (f.z, a.z, c.z);
+  if (a.w) f.w = blend4_plane8 (f.w, a.w, c.w);
+  return f;
+}
+
+/* PACKED: one pixel word, alpha in byte AP, the other three bytes colours.
+ * gst_video_blend's BLENDLOOP with the four OVERxy operators. */
+template <int AP>
+__device__ __forceinline__ uint32_t
+blend_px_packed (uint32_t f, uint32_t o, uint32_t ga, bool sp, bool dp)
+{
+  const uint32_t a = (o >> (8 * AP)) & 0xffu;
+  const uint32_t asrc = (ga == 255u) ? a : (a * ga) / 255u;
+  if (asrc == 0u)
+    return f;
+  const uint32_t adst = (f >> (8 * AP)) & 0xffu;
+  const uint32_t na = 255u - asrc;
+  uint32_t out;
+  if (ga == 255u && adst == 255u && !dp) {
+    /* opaque straight destination: final_alpha = 255 */
+    out = 0xffu << (8 * AP);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k == AP)
+        continue;
+      const uint32_t cs = (o >> (8 * k)) & 0xffu;
+      const uint32_t cd = (f >> (8 * k)) & 0xffu;
+      /* OVER10: (cs*255 + cd*na)/255 = cs + (cd*na)/255, then MIN 255 */
+      const uint32_t v = sp ? min (255u, cs + div255 (cd * na))
+          : div255 (cs * asrc + cd * na);
+      out |= v << (8 * k);
+    }
+  } else {
+    uint32_t fa = asrc + adst * na / 255u;
+    out = fa << (8 * AP);
+    if (fa == 0u)
+      fa = 1u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k == AP)
+        continue;
+      const uint32_t cs = (o >> (8 * k)) & 0xffu;
+      const uint32_t cd = (f >> (8 * k)) & 0xffu;
+      uint32_t v;
+      if (!dp)
+        v = ((sp ? cs * ga : cs * asrc) + cd * adst * na / 255u) / fa;
+      else
+        v = ((sp ? cs * ga : cs * asrc) + cd * na) / 255u;
+      out |= min (v, 255u) << (8 * k);
+    }
+  }
+  return out;
+}
+
+template <int AP>
+__device__ __forceinline__ uint4
+blend16_packed (uint4 f, const uint4 &o, uint32_t ga, bool sp, bool dp)
+{
+  f.x = blend_px_packed<AP> (f.x, o.x, ga, sp, dp);
+  f.y = blend_px_packed<AP> (f.y, o.y, ga, sp, dp);
+  f.z = blend_px_packed<AP> (f.z, o.z, ga, sp, dp);
+  f.w = blend_px_packed<AP> (f.w, o.w, ga, sp, dp);
+  return f;
+}
+
+/* ---------------------------------------------------------------------- */
+/* the per-frame blend kernel                                             */
+
+struct RectGeom { int32_t v0, v1, y0, y1; };
+
+__device__ __forceinline__ RectGeom
+rect_geom (const RectRef *r)
+{
+  const int4 g = __ldg (reinterpret_cast<const int4 *> (&r->v0));
+  RectGeom o;
+  o.v0 = g.x; o.v1 = g.y; o.y0 = g.z; o.y1 = g.w;
+  return o;
+}
+
+__device__ __forceinline__ bool
+rect_hit (const RectGeom &g, int v, int y)
+{
+  return v >= g.v0 && v < g.v1 && y >= g.y0 && y < g.y1;
+}
+
+template <int KIND>
+__device__ __forceinline__ uint4
+blend_with_rect (uint4 f, const RectRef *r, const RectGeom &g, int v, int y,
+    bool dst_premul)
+{
+  const int32_t pitch = __ldg (&r->pitch);
+  const size_t off = (size_t) (y - g.y0) * pitch + (size_t) (v - g.v0) * 16;
+  const uint4 oa = ld_overlay16 (ldg_ptr (&r->a) + off);
+  if (KIND == PK_PLANE8) {
+    const uint4 oc = ld_overlay16 (ldg_ptr (&r->c) + off);
+    return blend16_plane8 (f, oa, oc);
+  } else {
+    const uint32_t ga = (uint32_t) __ldg (&r->ga);
+    const bool sp = __ldg (&r->src_premul) != 0;
+    return blend16_packed<KIND == PK_PACKED_A0 ? 0 : 3> (f, oa, ga, sp, dst_premul);
+  }
+}
+
+/* One CTA = one chunk of kItemsPerChunk 16-byte vectors of one plane window.
+ * Thread t owns items t, t+256, t+512, t+768 of the chunk: four independent
+ * 128-bit frame loads (and up to eight overlay loads) are in flight per
+ * thread before the first one is consumed. */
+template <int KIND>
+__global__ void __launch_bounds__ (kThreads)
+ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
+    const uint32_t *__restrict__ chunk_begin, int n_jobs)
+{
+  const uint32_t chunk = blockIdx.x;
+
+  /* which plane job does this chunk belong to: count begins <= chunk */
+  int cnt = 0;
+  for (int base = 0; base < n_jobs; base += kThreads) {
+    const int j = base + (int) threadIdx.x;
+    const int pred = (j < n_jobs) && (__ldg (chunk_begin + j) <= chunk);
+    cnt += __syncthreads_count (pred);
+  }
+  const PlaneJob *job = jobs + (cnt - 1);
+  const uint32_t local_chunk = chunk - __ldg (chunk_begin + (cnt - 1));
+
+  const uint8_t *src = ldg_ptr (&job->src);
+  uint8_t *dst = ldg_ptr (&job->dst);
+  const RectRef *rects = ldg_ptr (&job->rects);
+  const int n_rects = __ldg (&job->n_rects);
+  const int src_pitch = __ldg (&job->src_pitch);
+  const int dst_pitch = __ldg (&job->dst_pitch);
+  const int row_bytes = __ldg (&job->row_bytes);
+  const int win_v0 = __ldg (&job->win_v0);
+  const uint32_t win_nv = (uint32_t) __ldg (&job->win_nv);
+  const int win_y0 = __ldg (&job->win_y0);
+  const uint32_t total_items = win_nv * (uint32_t) __ldg (&job->win_rows);
+  const uint32_t magic = __ldg (&job->div_magic);
+  const int flags = __ldg (&job->flags);
+  const bool vec_ok = (flags & JF_VECTOR) != 0;
+  const bool inplace = (flags & JF_INPLACE) != 0;
+  const bool dst_premul = (flags & JF_DST_PREMUL) != 0;
+
+  const uint32_t item0 = local_chunk * kItemsPerChunk + threadIdx.x;
+
+  int vv[kUnroll], yy[kUnroll], hit[kUnroll];
+  bool act[kUnroll];
+#pragma unroll
+  for (int k = 0; k < kUnroll; k++) {
+    const uint32_t item = item0 + k * kThreads;
+    act[k] = item < total_items;
+    const uint32_t row = win_nv == 1u ? item : __umulhi (item, magic);
+    const uint32_t col = item - row * win_nv;
+    vv[k] = win_v0 + (int) col;
+    yy[k] = win_y0 + (int) row;
+    hit[k] = -1;
+  }
+
+  /* first rectangle (lowest index = first in blend order) covering each item */
+  for (int r = n_rects - 1; r >= 0; r--) {
+    const RectGeom g = rect_geom (rects + r);
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++)
+      if (rect_hit (g, vv[k], yy[k]))
+        hit[k] = r;
+  }
+
+  uint4 f[kUnroll];
+  int nvalid[kUnroll];
+#pragma unroll
+  for (int k = 0; k < kUnroll; k++) {
+    if (inplace && hit[k] < 0)
+      act[k] = false;
+    nvalid[k] = min (16, row_bytes - vv[k] * 16);
+    if (act[k]) {
+      const uint8_t *p = src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16;
+      if (vec_ok && nvalid[k] == 16)
+        f[k] = ld_frame16 (p);
+      else
+        f[k] = ld_frame_bytes (p, nvalid[k]);
+    }
+  }
+
+#pragma unroll
+  for (int k = 0; k < kUnroll; k++) {
+    if (act[k] && hit[k] >= 0) {
+      const RectRef *r = rects + hit[k];
+      const RectGeom g = rect_geom (r);
+      f[k] = blend_with_rect<KIND> (f[k], r, g, vv[k], yy[k], dst_premul);
+      /* overlapping rectangles: the later ones blend on top, in order */
+      for (int r2 = hit[k] + 1; r2 < n_rects; r2++) {
+        const RectGeom g2 = rect_geom (rects + r2);
+        if (rect_hit (g2, vv[k], yy[k]))
+          f[k] = blend_with_rect<KIND> (f[k], rects + r2, g2, vv[k], yy[k], dst_premul);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int k = 0; k < kUnroll; k++) {
+    if (act[k]) {
+      uint8_t *p = dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16;
+      if (vec_ok && nvalid[k] == 16)
+        st_frame16 (p, f[k]);
+      else
+        st_frame_bytes (p, f[k], nvalid[k]);
+    }
+  }
+}
+
+cudaError_t
+launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_jobs,
+    uint32_t total_chunks, int kind, cudaStream_t stream)
+{
+  if (n_jobs <= 0 || total_chunks == 0)
+    return cudaSuccess;
+  switch (kind) {
+    case PK_PLANE8:
+      ttmlblend_blend_kernel<PK_PLANE8><<<total_chunks, kThreads, 0, stream>>> (
+          d_jobs, d_chunk_begin, n_jobs);
+      break;
+    case PK_PACKED_A0:
+      ttmlblend_blend_kernel<PK_PACKED_A0><<<total_chunks, kThreads, 0, stream>>> (
+          d_jobs, d_chunk_begin, n_jobs);
+      break;
+    case PK_PACKED_A3:
+      ttmlblend_blend_kernel<PK_PACKED_A3><<<total_chunks, kThreads, 0, stream>>> (
+          d_jobs, d_chunk_begin, n_jobs);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError ();
+}
+
+/* ---------------------------------------------------------------------- */
+/* once-per-cue overlay prepare                                           */
+
+struct Ayuv { int a, y, u, v; };
+
+/* unpack_BGRA + matrix_prea_rgb_to_yuv / matrix_rgb_to_yuv of video-blend.c */
+__device__ __forceinline__ Ayuv
+bgra_to_ayuv (uint32_t px, bool premul)
+{
+  int b = px & 0xff, g = (px >> 8) & 0xff, r = (px >> 16) & 0xff;
+  const int a = px >> 24;
+  if (premul && a) {
+    r = (r * 255 + a / 2) / a;
+    g = (g * 255 + a / 2) / a;
+    b = (b * 255 + a / 2) / a;
+  }
+  Ayuv o;
+  o.a = a;
+  o.y = min (max ((47 * r + 157 * g + 16 * b + 4096) >> 8, 0), 255);
+  o.u = min (max ((-26 * r - 87 * g + 112 * b + 32768) >> 8, 0), 255);
+  o.v = min (max ((112 * r - 102 * g - 10 * b + 32768) >> 8, 0), 255);
+  return o;
+}
+
+__device__ __forceinline__ uint32_t
+raw_px (const PrepareParams &p, int x, int y)
+{
+  return *reinterpret_cast<const uint32_t *> (p.raw + (size_t) (y - p.fy) * p.raw_pitch
+      + (size_t) (x - p.fx) * 4);
+}
+
+/* One thread per prepared element: a pixel (luma, packed), a chroma sample
+ * (planar chroma) or a chroma pair (semi-planar chroma). */
+__global__ void __launch_bounds__ (256)
+ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (i >= n_elems || r >= p.rows)
+    return;
+  const size_t orow = (size_t) r * p.out_pitch;
+  const bool premul = p.premul != 0;
+
+  switch (p.mode) {
+    case PM_LUMA:{
+      const int x = p.v0 * 16 + i, y = p.row0 + r;
+      uint8_t a = 0, c = 0;
+      if (x >= p.cx0 && x < p.cx1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), premul);
+        const int asrc = s.a * p.ga / 255;
+        if (asrc) {
+          a = (uint8_t) asrc;
+          c = (uint8_t) s.y;
+        }
+      }
+      p.out_a[orow + i] = a;
+      p.out_c[orow + i] = c;
+      break;
+    }
+    case PM_CHROMA_PLANAR:{
+      const int bx = p.v0 * 16 + i, x = 2 * bx, y = 2 * (p.row0 + r);
+      uint8_t a = 0, u = 0, v = 0;
+      if (x >= p.cx0 && x < p.cx1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), premul);
+        const int asrc = s.a * p.ga / 255;
+        if (asrc) {
+          a = (uint8_t) asrc;
+          u = (uint8_t) s.u;
+          v = (uint8_t) s.v;
+        }
+      }
+      p.out_a[orow + i] = a;
+      p.out_c[orow + i] = u;
+      p.out_c2[orow + i] = v;
+      break;
+    }
+    case PM_CHROMA_UV:
+    case PM_CHROMA_VU:{
+      const int bx = p.v0 * 8 + i, x = 2 * bx, y = 2 * (p.row0 + r);
+      uint8_t a = 0, u = 0, v = 0;
+      if (x >= p.cx0 && x < p.cx1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), premul);
+        const int asrc = s.a * p.ga / 255;
+        if (asrc) {
+          a = (uint8_t) asrc;
+          u = (uint8_t) s.u;
+          v = (uint8_t) s.v;
+        }
+      }
+      p.out_a[orow + 2 * i] = a;
+      p.out_a[orow + 2 * i + 1] = a;
+      p.out_c[orow + 2 * i] = p.mode == PM_CHROMA_UV ? u : v;
+      p.out_c[orow + 2 * i + 1] = p.mode == PM_CHROMA_UV ? v : u;
+      break;
+    }
+    default:{
+      const int x = p.v0 * 4 + i, y = p.row0 + r;
+      uint32_t w = 0u;
+      if (x >= p.cx0 && x < p.cx1) {
+        const uint32_t px = raw_px (p, x, y);
+        const uint32_t b = px & 0xffu, g = (px >> 8) & 0xffu, rr = (px >> 16) & 0xffu,
+            a = px >> 24;
+        switch (p.mode) {
+          case PM_PACKED_AYUV:{
+            const Ayuv s = bgra_to_ayuv (px, premul);
+            w = (uint32_t) s.a | ((uint32_t) s.y << 8) | ((uint32_t) s.u << 16) |
+                ((uint32_t) s.v << 24);
+            break;
+          }
+          case PM_PACKED_ARGB:
+            w = a | (rr << 8) | (g << 16) | (b << 24);
+            break;
+          case PM_PACKED_ABGR:
+            w = a | (b << 8) | (g << 16) | (rr << 24);
+            break;
+          case PM_PACKED_RGBA:
+            w = rr | (g << 8) | (b << 16) | (a << 24);
+            break;
+          default:             /* PM_PACKED_BGRA */
+            w = px;
+            break;
+        }
+      }
+      reinterpret_cast<uint32_t *> (p.out_a + orow)[i] = w;
+      break;
+    }
+  }
+}
+
+cudaError_t
+launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream)
+{
+  if (n_elems <= 0 || p.rows <= 0)
+    return cudaSuccess;
+  const int rows_per_launch = 65535;
+  for (int r0 = 0; r0 < p.rows; r0 += rows_per_launch) {
+    PrepareParams q = p;
+    const int nr = min (rows_per_launch, p.rows - r0);
+    q.row0 = p.row0 + r0;
+    q.rows = nr;
+    q.out_a = p.out_a + (size_t) r0 * p.out_pitch;
+    if (p.out_c) q.out_c = p.out_c + (size_t) r0 * p.out_pitch;
+    if (p.out_c2) q.out_c2 = p.out_c2 + (size_t) r0 * p.out_pitch;
+    dim3 grid ((n_elems + 255) / 256, nr);
+    ttmlblend_prepare_kernel<<<grid, 256, 0, stream>>> (q, n_elems);
+  }
+  return cudaGetLastError ();
+}
+
+/* ---------------------------------------------------------------------- */
+
+__global__ void
+ttmlblend_scrub_kernel (uint4 *buf, size_t n_vec, uint32_t seed)
+{
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (; i < n_vec; i += stride)
+    buf[i] = make_uint4 (seed, (uint32_t) i, seed ^ 0x5a5a5a5au, 0u);
+}
+
+cudaError_t
+launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream)
+{
+  static uint32_t seed = 1;
+  if (bytes < 16)
+    return cudaSuccess;
+  ttmlblend_scrub_kernel<<<148 * 8, 256, 0, stream>>> (reinterpret_cast<uint4 *> (buf),
+      bytes / 16, seed++);
+  return cudaGetLastError ();
+}
+
+}  // namespace tb

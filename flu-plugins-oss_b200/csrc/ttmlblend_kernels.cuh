@@ -1,0 +1,113 @@
+/*
+ * ttmlblend_kernels.cuh -- device-side data layout and launch interface of
+ * the sm_100a blend / prepare kernels. Private to csrc/ (the public surface
+ * is include/fluc_ttmlblend.h).
+ *
+ * Data layout in HBM (DESIGN.md "Data layout"):
+ *   frames        planar / semi-planar / packed exactly as GStreamer maps them
+ *                 (plane pointer + stride per plane).
+ *   prepared      per overlay rectangle and per destination plane kind, the
+ *   overlay       rectangle's pixels after everything that does not depend on
+ *                 the frame has been done ONCE per cue change: BGRA unpack,
+ *                 un-premultiply + BT.709 matrix (YUV destinations), global
+ *                 alpha, 4:2:0 chroma siting (the even-x/even-y sample), and
+ *                 shifting onto the 16-byte vector grid of the destination
+ *                 plane. Two layouts:
+ *                   PLANE8  alpha bytes + colour bytes, one of each per
+ *                           destination byte (Y plane, U plane, V plane or
+ *                           interleaved UV plane);
+ *                   PACKED  one 32-bit word per pixel in the destination's
+ *                           own channel order (AYUV / ARGB / ABGR: alpha in
+ *                           byte 0, RGBA / BGRA: alpha in byte 3).
+ */
+#ifndef TTMLBLEND_KERNELS_CUH
+#define TTMLBLEND_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tb {
+
+enum PlaneKind : int32_t {
+  PK_PLANE8 = 0,
+  PK_PACKED_A0 = 1,
+  PK_PACKED_A3 = 2
+};
+
+enum JobFlags : int32_t {
+  JF_VECTOR = 1,        /* src, dst and both pitches are 16-byte aligned */
+  JF_INPLACE = 2,       /* dst == src: bytes no rectangle covers are not touched */
+  JF_DST_PREMUL = 4     /* destination frame is premultiplied (packed kinds) */
+};
+
+/* One prepared rectangle as seen from one destination plane. */
+struct alignas (16) RectRef {
+  const uint8_t *a;     /* PLANE8: alpha bytes. PACKED: pixel words */
+  const uint8_t *c;     /* PLANE8: colour bytes. PACKED: unused */
+  int32_t v0, v1;       /* 16-byte vector columns [v0, v1) of the plane row */
+  int32_t y0, y1;       /* plane rows [y0, y1); v0..y1 are read as one int4 */
+  int32_t pitch;        /* bytes per prepared row, multiple of 16 */
+  int32_t ga;           /* PACKED: global alpha 0..255 (PLANE8 folds it in) */
+  int32_t src_premul;   /* PACKED: source colours are premultiplied */
+  int32_t pad_;
+};
+
+/* One window of one plane of one frame. Items are 16-byte vectors, numbered
+ * row-major inside the window; a chunk is kItemsPerChunk consecutive items. */
+struct alignas (16) PlaneJob {
+  const uint8_t *src;
+  uint8_t *dst;
+  const RectRef *rects;
+  int32_t n_rects;
+  int32_t src_pitch, dst_pitch;
+  int32_t row_bytes;    /* valid bytes per plane row */
+  int32_t win_v0, win_nv, win_y0, win_rows;
+  uint32_t div_magic;   /* ceil (2^32 / win_nv): item / win_nv == umulhi (item, magic) */
+  int32_t kind;         /* PlaneKind */
+  int32_t flags;        /* JobFlags */
+  uint32_t n_chunks;
+};
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kItemsPerChunk = kThreads * kUnroll;
+constexpr int kSmemRects = 8;
+
+/* Parameters of the once-per-cue prepare kernels. Raw = device copy of the
+ * rectangle's BGRA bytes whose pixel (0,0) sits at frame (fx, fy). */
+struct PrepareParams {
+  const uint8_t *raw;
+  int32_t raw_pitch, raw_w, raw_h;
+  int32_t fx, fy;
+  int32_t cx0, cy0, cx1, cy1;   /* rectangle clipped to the frame */
+  int32_t ga;                   /* (int) (255.0 * global_alpha) */
+  int32_t premul;
+  /* output */
+  uint8_t *out_a, *out_c, *out_c2;
+  int32_t out_pitch;
+  int32_t v0;                   /* first vector column of the prepared span */
+  int32_t row0, rows;           /* first plane row and number of prepared rows */
+  int32_t mode;
+};
+
+enum PrepareMode : int32_t {
+  PM_LUMA = 0,          /* out_a = alpha, out_c = Y, per pixel */
+  PM_CHROMA_PLANAR = 1, /* out_a = alpha, out_c = U, out_c2 = V, per chroma sample */
+  PM_CHROMA_UV = 2,     /* out_a = alpha pairs, out_c = U,V interleaved */
+  PM_CHROMA_VU = 3,     /* out_a = alpha pairs, out_c = V,U interleaved */
+  PM_PACKED_AYUV = 4,   /* words (A,Y,U,V) */
+  PM_PACKED_ARGB = 5,
+  PM_PACKED_ABGR = 6,
+  PM_PACKED_RGBA = 7,
+  PM_PACKED_BGRA = 8
+};
+
+/* All jobs of one launch share one PlaneKind. */
+cudaError_t launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin,
+    int n_jobs, uint32_t total_chunks, int kind, cudaStream_t stream);
+/* n_elems = prepared elements per row (see PrepareMode). */
+cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
+cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);
+
+}  // namespace tb
+#endif

@@ -1,0 +1,337 @@
+"""ctypes binding of libfluc_ttmlblend.so (include/fluc_ttmlblend.h).
+
+Thin on purpose: every method is one C-ABI call. The library is the product;
+this module exists so that tests/ and bench.py can drive it the way an element
+written in C would (the cgo/ctypes stub a maintainer adds is in INTEGRATION.md).
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+is usable, construction raises.
+
+Reference interface mirrored (argument meaning / error behaviour):
+  gst_video_overlay_composition_blend / gst_video_blend (gst-plugins-base), fed
+  by ttmlrender's gen_buffer output, /root/reference/plugins/ttml/gstttmlrender.c:1427-1478.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfluc_ttmlblend.so")
+
+FORMATS = {
+    "I420": 0, "NV12": 1, "AYUV": 2, "RGBA": 3, "BGRA": 4,
+    "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8,
+}
+FLAG_PREMULTIPLIED_ALPHA = 1
+MAX_RECTANGLES = 64
+
+OK = 0
+ERROR_INVALID_ARGUMENT = -1
+ERROR_NO_DEVICE = -2
+ERROR_CUDA = -3
+ERROR_OUT_OF_MEMORY = -4
+ERROR_UNSUPPORTED_FORMAT = -5
+ERROR_NOT_FOUND = -6
+ERROR_TOO_MANY_RECTANGLES = -7
+
+
+class Rect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32)]
+
+
+class Rectangle(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32),
+                ("stride", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
+                ("global_alpha", C.c_float), ("flags", C.c_uint32)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 3), ("stride", C.c_int32 * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("frames_blended", C.c_uint64), ("launches", C.c_uint64),
+                ("prepare_launches", C.c_uint64), ("overlays_set", C.c_uint64),
+                ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("kernel_ms", C.c_double),
+                ("kernel_ms_launches", C.c_uint64)]
+
+
+# name -> (restype, argtypes); also the list tests check against the header
+PROTOTYPES = {
+    "fluc_ttmlblend_new": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "fluc_ttmlblend_free": (None, [C.c_void_p]),
+    "fluc_ttmlblend_strerror": (C.c_char_p, [C.c_int]),
+    "fluc_ttmlblend_last_cuda_error": (C.c_char_p, [C.c_void_p]),
+    "fluc_ttmlblend_device_count": (C.c_int, []),
+    "fluc_ttmlblend_version": (C.c_char_p, []),
+    "fluc_ttmlblend_overlay_set": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32,
+                                             C.c_int32, C.c_int32, C.POINTER(Rect), C.c_uint32]),
+    "fluc_ttmlblend_overlay_set_rectangles": (C.c_int, [C.c_void_p, C.c_uint32,
+                                                        C.POINTER(Rectangle), C.c_uint32]),
+    "fluc_ttmlblend_overlay_clear": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "fluc_ttmlblend_submit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
+                                        C.c_uint32, C.POINTER(Frame), C.POINTER(Frame),
+                                        C.POINTER(C.c_uint64)]),
+    "fluc_ttmlblend_flush": (C.c_int, [C.c_void_p]),
+    "fluc_ttmlblend_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "fluc_ttmlblend_sync": (C.c_int, [C.c_void_p]),
+    "fluc_ttmlblend_set_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "fluc_ttmlblend_blend_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
+                                            C.c_uint32, C.POINTER(Frame), C.POINTER(C.c_uint64)]),
+    "fluc_ttmlblend_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fluc_ttmlblend_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fluc_ttmlblend_frame_pool_acquire": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32,
+                                                    C.c_int, C.POINTER(Frame)]),
+    "fluc_ttmlblend_frame_pool_release": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
+    "fluc_ttmlblend_frame_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32,
+                                              C.POINTER(Frame), C.POINTER(Frame)]),
+    "fluc_ttmlblend_frame_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32,
+                                                C.POINTER(Frame), C.POINTER(Frame)]),
+    "fluc_ttmlblend_format_planes": (C.c_int, [C.c_int]),
+    "fluc_ttmlblend_plane_row_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int32]),
+    "fluc_ttmlblend_plane_rows": (C.c_int, [C.c_int, C.c_int, C.c_int32]),
+    "fluc_ttmlblend_stats_copy": (None, [C.c_void_p, C.POINTER(Stats)]),
+    "fluc_ttmlblend_stats_reset": (None, [C.c_void_p]),
+    "fluc_ttmlblend_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "fluc_ttmlblend_timer_begin": (C.c_int, [C.c_void_p]),
+    "fluc_ttmlblend_timer_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "fluc_ttmlblend_scrub_l2": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "fluc_ttmlblend_stream_handle": (C.c_void_p, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class TtmlBlendError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{what}: {code} ({detail})" if detail else f"{what}: {code}")
+
+
+def load_library(path: Optional[str] = None):
+    """Loads the C-ABI library. Fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            f"{p} is missing: build it with `make -C {os.path.dirname(p)}` "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def plane_layout(fmt: str, width: int, height: int):
+    """[(row_bytes, rows)] per plane, as GStreamer lays the format out."""
+    f = fmt.upper()
+    if f in ("I420", "YV12"):
+        cw, ch = (width + 1) // 2, (height + 1) // 2
+        return [(width, height), (cw, ch), (cw, ch)]
+    if f in ("NV12", "NV21"):
+        cw, ch = (width + 1) // 2, (height + 1) // 2
+        return [(width, height), (2 * cw, ch)]
+    return [(4 * width, height)]
+
+
+def frame_bytes(fmt: str, width: int, height: int) -> int:
+    return sum(rb * r for rb, r in plane_layout(fmt, width, height))
+
+
+def _frame_from_arrays(planes: Sequence[np.ndarray]) -> Frame:
+    f = Frame()
+    for i, p in enumerate(planes):
+        assert p.dtype == np.uint8 and p.ndim == 2 and p.strides[1] == 1
+        f.plane[i] = p.ctypes.data
+        f.stride[i] = p.strides[0]
+    return f
+
+
+class DeviceFrame:
+    """A pool frame in HBM (or pinned host memory when on_host)."""
+
+    def __init__(self, ctx: "TtmlBlend", fmt: str, width: int, height: int, on_host: bool = False):
+        self.ctx, self.fmt, self.width, self.height, self.on_host = ctx, fmt, width, height, on_host
+        self.c = Frame()
+        ctx._check(ctx.lib.fluc_ttmlblend_frame_pool_acquire(
+            ctx.h, FORMATS[fmt], width, height, 1 if on_host else 0, C.byref(self.c)), "frame_pool_acquire")
+        self._released = False
+
+    def release(self):
+        if not self._released:
+            self._released = True
+            self.ctx._check(self.ctx.lib.fluc_ttmlblend_frame_pool_release(self.ctx.h, C.byref(self.c)),
+                            "frame_pool_release")
+
+    def host_planes(self):
+        """numpy views of a pinned host frame's planes (on_host only)."""
+        assert self.on_host
+        out = []
+        for i, (rb, rows) in enumerate(plane_layout(self.fmt, self.width, self.height)):
+            stride = self.c.stride[i]
+            buf = (C.c_uint8 * (stride * rows)).from_address(self.c.plane[i])
+            out.append(np.frombuffer(buf, dtype=np.uint8).reshape(rows, stride)[:, :rb])
+        return out
+
+    def upload(self, planes: Sequence[np.ndarray]):
+        src = _frame_from_arrays(planes)
+        self.ctx._check(self.ctx.lib.fluc_ttmlblend_frame_upload(
+            self.ctx.h, FORMATS[self.fmt], self.width, self.height, C.byref(src), C.byref(self.c)),
+            "frame_upload")
+
+    def download(self):
+        planes = [np.zeros((rows, rb), dtype=np.uint8)
+                  for rb, rows in plane_layout(self.fmt, self.width, self.height)]
+        dst = _frame_from_arrays(planes)
+        self.ctx._check(self.ctx.lib.fluc_ttmlblend_frame_download(
+            self.ctx.h, FORMATS[self.fmt], self.width, self.height, C.byref(self.c), C.byref(dst)),
+            "frame_download")
+        return planes
+
+
+class TtmlBlend:
+    """One context per GPU (FlucTtmlBlend)."""
+
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        self.h = C.c_void_p()
+        rc = self.lib.fluc_ttmlblend_new(device, C.byref(self.h))
+        if rc != OK:
+            self.h = None
+            raise TtmlBlendError(rc, "fluc_ttmlblend_new", self.lib.fluc_ttmlblend_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fluc_ttmlblend_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != OK:
+            detail = self.lib.fluc_ttmlblend_strerror(rc).decode()
+            cuda = self.lib.fluc_ttmlblend_last_cuda_error(self.h).decode() if self.h else ""
+            raise TtmlBlendError(rc, what, f"{detail}; {cuda}" if cuda else detail)
+
+    # -- overlay cache ---------------------------------------------------
+    def overlay_set(self, stream: int, bgra: np.ndarray, rects: Iterable[Sequence[int]] = ()):
+        """ttmlrender form: H x W x 4 premultiplied BGRA image + region boxes (x, y, w, h)."""
+        assert bgra.dtype == np.uint8 and bgra.ndim == 3 and bgra.shape[2] == 4 and bgra.strides[2] == 1
+        rl = list(rects)
+        arr = (Rect * max(1, len(rl)))(*[Rect(*map(int, r)) for r in rl])
+        self._check(self.lib.fluc_ttmlblend_overlay_set(
+            self.h, stream, bgra.ctypes.data, bgra.shape[1], bgra.shape[0], bgra.strides[0],
+            arr if rl else None, len(rl)), "overlay_set")
+
+    def overlay_set_rectangles(self, stream: int, rectangles: Sequence[dict]):
+        """GstVideoOverlayComposition form. Each dict: pixels (h x w x 4 uint8 BGRA), x, y,
+        global_alpha (default 1.0), premultiplied (default True)."""
+        n = len(rectangles)
+        arr = (Rectangle * max(1, n))()
+        for i, r in enumerate(rectangles):
+            px = r["pixels"]
+            assert px.dtype == np.uint8 and px.ndim == 3 and px.shape[2] == 4 and px.strides[2] == 1
+            arr[i] = Rectangle(px.ctypes.data, px.shape[1], px.shape[0], px.strides[0],
+                               int(r.get("x", 0)), int(r.get("y", 0)),
+                               float(r.get("global_alpha", 1.0)),
+                               FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0)
+        self._check(self.lib.fluc_ttmlblend_overlay_set_rectangles(self.h, stream, arr, n),
+                    "overlay_set_rectangles")
+
+    def overlay_clear(self, stream: int):
+        self._check(self.lib.fluc_ttmlblend_overlay_clear(self.h, stream), "overlay_clear")
+
+    # -- device-resident frames -----------------------------------------
+    def submit(self, stream: int, fmt: str, width: int, height: int, src: Frame, dst: Frame,
+               frame_flags: int = 0) -> int:
+        t = C.c_uint64()
+        self._check(self.lib.fluc_ttmlblend_submit(
+            self.h, stream, FORMATS[fmt], width, height, frame_flags, C.byref(src), C.byref(dst),
+            C.byref(t)), "submit")
+        return t.value
+
+    def flush(self):
+        self._check(self.lib.fluc_ttmlblend_flush(self.h), "flush")
+
+    def wait(self, ticket: int):
+        self._check(self.lib.fluc_ttmlblend_wait(self.h, ticket), "wait")
+
+    def sync(self):
+        self._check(self.lib.fluc_ttmlblend_sync(self.h), "sync")
+
+    def set_batch(self, max_frames: int, linger_us: int):
+        self._check(self.lib.fluc_ttmlblend_set_batch(self.h, max_frames, linger_us), "set_batch")
+
+    # -- host-resident frames: gst_video_overlay_composition_blend ------
+    def blend_host(self, stream: int, fmt: str, width: int, height: int,
+                   planes: Sequence[np.ndarray], frame_flags: int = 0) -> int:
+        f = _frame_from_arrays(planes)
+        return self.blend_host_frame(stream, fmt, width, height, f, frame_flags)
+
+    def blend_host_frame(self, stream: int, fmt: str, width: int, height: int, frame: Frame,
+                         frame_flags: int = 0) -> int:
+        t = C.c_uint64()
+        self._check(self.lib.fluc_ttmlblend_blend_host(
+            self.h, stream, FORMATS[fmt], width, height, frame_flags, C.byref(frame), C.byref(t)),
+            "blend_host")
+        return t.value
+
+    def host_register(self, arr: np.ndarray):
+        self._check(self.lib.fluc_ttmlblend_host_register(self.h, arr.ctypes.data, arr.nbytes),
+                    "host_register")
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self.lib.fluc_ttmlblend_host_unregister(self.h, arr.ctypes.data), "host_unregister")
+
+    # -- pool / stats ----------------------------------------------------
+    def acquire(self, fmt: str, width: int, height: int, on_host: bool = False) -> DeviceFrame:
+        return DeviceFrame(self, fmt, width, height, on_host)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self.lib.fluc_ttmlblend_stats_copy(self.h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def stats_reset(self):
+        self.lib.fluc_ttmlblend_stats_reset(self.h)
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.fluc_ttmlblend_set_profiling(self.h, 1 if on else 0), "set_profiling")
+
+    def timer_begin(self):
+        self._check(self.lib.fluc_ttmlblend_timer_begin(self.h), "timer_begin")
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.fluc_ttmlblend_timer_end(self.h, C.byref(ms)), "timer_end")
+        return ms.value
+
+    def scrub_l2(self, nbytes: int = 256 << 20):
+        self._check(self.lib.fluc_ttmlblend_scrub_l2(self.h, nbytes), "scrub_l2")
+
+
+def composition_blend(ctx: TtmlBlend, stream: int, fmt: str, width: int, height: int,
+                      planes: Sequence[np.ndarray], frame_flags: int = 0):
+    """gst_video_overlay_composition_blend(comp, frame) on host planes, in place, synchronous."""
+    ctx.wait(ctx.blend_host(stream, fmt, width, height, planes, frame_flags))
+    return planes

@@ -1,0 +1,217 @@
+/*
+ * fluc_ttmlblend.h -- C ABI of the B200 TTML overlay-blend path.
+ *
+ * One shared library, libfluc_ttmlblend.so, plain pointers and sizes, no GLib,
+ * GStreamer, CUDA or torch types in any signature. Conventions follow the
+ * reference's libs/fluc helpers (opaque `typedef struct _X X`, first argument
+ * `thiz`, `fluc_<module>_<verb>`, FLUC_EXPORT, stats copied out under the
+ * object's lock):
+ *   /root/reference/libs/fluc/flu-codec-sdk/fluc/fluc_export.h:9-11
+ *   /root/reference/libs/fluc/flu-codec-sdk/fluc/bwmeter/fluc_bwmeter.h:17-46
+ *   /root/reference/libs/fluc/flu-codec-sdk/fluc/threads/fluc_monitor.h:15-44
+ *
+ * What it replaces. The reference's `ttmlrender` element produces one
+ * premultiplied BGRA image per timeline interval
+ * (/root/reference/plugins/ttml/gstttmlrender.c:1427-1478, caps :78-84) and
+ * leaves the per-frame compositing to GStreamer (the README pipeline,
+ * /root/reference/plugins/ttml/README.md:45-48), i.e. to gst-plugins-base:
+ *   gboolean gst_video_overlay_composition_blend (GstVideoOverlayComposition *comp,
+ *                                                 GstVideoFrame *video_buf);
+ *   gboolean gst_video_blend (GstVideoFrame *dest, GstVideoFrame *src,
+ *                             gint x, gint y, gfloat global_alpha);
+ * The functions below take over exactly that work, bit for bit
+ * (docs/BLENDSPEC.md), on the GPU. There is no CPU fallback: every entry point
+ * returns FLUC_TTMLBLEND_ERROR_NO_DEVICE / _CUDA when the GPU cannot be used.
+ *
+ * Threading: every function may be called from any thread; a context
+ * serialises internally (monitor = mutex + condition, fluc_monitor style).
+ * `overlay_set*` is meant for the subtitle streaming thread (once per cue
+ * change, the cadence of gst_ttmlbase_gen_buffer,
+ * /root/reference/plugins/ttml/gstttmlbase.c:93-198), `submit*`/`blend_host`
+ * for the video streaming threads of many elements at once.
+ */
+#ifndef _FLUC_TTMLBLEND_H_
+#define _FLUC_TTMLBLEND_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef FLUC_EXPORT
+#if defined(__GNUC__)
+#define FLUC_EXPORT __attribute__ ((visibility ("default")))
+#else
+#define FLUC_EXPORT
+#endif
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One context per GPU: overlay cache, frame pool, batch scheduler, streams. */
+typedef struct _FlucTtmlBlend FlucTtmlBlend;
+
+/* Destination frame formats (GstVideoFormat names). */
+typedef enum {
+  FLUC_TTMLBLEND_FORMAT_I420 = 0,
+  FLUC_TTMLBLEND_FORMAT_NV12 = 1,
+  FLUC_TTMLBLEND_FORMAT_AYUV = 2,
+  FLUC_TTMLBLEND_FORMAT_RGBA = 3,
+  FLUC_TTMLBLEND_FORMAT_BGRA = 4,
+  FLUC_TTMLBLEND_FORMAT_YV12 = 5,
+  FLUC_TTMLBLEND_FORMAT_NV21 = 6,
+  FLUC_TTMLBLEND_FORMAT_ARGB = 7,
+  FLUC_TTMLBLEND_FORMAT_ABGR = 8,
+  FLUC_TTMLBLEND_FORMAT_COUNT
+} FlucTtmlBlendFormat;
+
+/* Error codes: 0 = ok, negative = error. Never aborts. */
+typedef enum {
+  FLUC_TTMLBLEND_OK = 0,
+  FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT = -1,
+  FLUC_TTMLBLEND_ERROR_NO_DEVICE = -2,     /* no usable CUDA device */
+  FLUC_TTMLBLEND_ERROR_CUDA = -3,          /* sticky: context is unusable */
+  FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY = -4,
+  FLUC_TTMLBLEND_ERROR_UNSUPPORTED_FORMAT = -5,
+  FLUC_TTMLBLEND_ERROR_NOT_FOUND = -6,     /* unknown stream / ticket / frame */
+  FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES = -7
+} FlucTtmlBlendError;
+
+/* Mirrors GST_VIDEO_OVERLAY_FORMAT_FLAG_PREMULTIPLIED_ALPHA (rectangles) and
+ * GST_VIDEO_FLAG_PREMULTIPLIED_ALPHA (frames). */
+#define FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA 1u
+
+#define FLUC_TTMLBLEND_MAX_RECTANGLES 64u
+
+/* A region of the frame, in frame pixels; may extend beyond the frame.
+ * Source of these in the reference: GstTTMLRegion origin/extent,
+ * /root/reference/plugins/ttml/gstttmlrender.c:44-76,434-561. */
+typedef struct {
+  int32_t x, y, w, h;
+} FlucTtmlBlendRect;
+
+/* One overlay rectangle = GstVideoOverlayRectangle with render size equal to
+ * its pixel size: BGRA bytes (ARGB32 little endian), position, global alpha,
+ * premultiplied flag. */
+typedef struct {
+  const uint8_t *pixels;   /* host memory, read before the call returns */
+  int32_t width, height, stride;
+  int32_t x, y;
+  float global_alpha;      /* 1.0f for ttmlrender */
+  uint32_t flags;          /* FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA */
+} FlucTtmlBlendRectangle;
+
+/* Plane pointers + strides of one frame (GstVideoFrame data[]/stride[]).
+ * I420: Y,U,V. YV12: Y,V,U. NV12/NV21: Y,UV. Packed formats: plane[0]. */
+typedef struct {
+  void *plane[3];
+  int32_t stride[3];
+} FlucTtmlBlendFrame;
+
+/* Counters, copied out like fluc_bwmeter_stats_copy
+ * (/root/reference/libs/fluc/flu-codec-sdk/fluc/bwmeter/fluc_bwmeter.c:71-76). */
+typedef struct {
+  uint64_t frames_blended;      /* frames that went through a blend launch */
+  uint64_t launches;            /* blend kernel launches */
+  uint64_t prepare_launches;    /* overlay prepare kernel launches */
+  uint64_t overlays_set;
+  uint64_t algorithmic_bytes;   /* 2*frame bytes (or touched bytes in place) + 4*overlay px */
+  uint64_t h2d_bytes, d2h_bytes;
+  double kernel_ms;             /* sum of per-launch CUDA-event times (profiling on) */
+  uint64_t kernel_ms_launches;  /* launches included in kernel_ms */
+} FlucTtmlBlendStats;
+
+/* ---- lifetime -------------------------------------------------------- */
+FLUC_EXPORT int fluc_ttmlblend_new (int device, FlucTtmlBlend **out);
+FLUC_EXPORT void fluc_ttmlblend_free (FlucTtmlBlend *thiz);
+FLUC_EXPORT const char *fluc_ttmlblend_strerror (int err);
+/* Text of the last CUDA error seen by this context ("" if none). */
+FLUC_EXPORT const char *fluc_ttmlblend_last_cuda_error (FlucTtmlBlend *thiz);
+FLUC_EXPORT int fluc_ttmlblend_device_count (void);
+FLUC_EXPORT const char *fluc_ttmlblend_version (void);
+
+/* ---- overlay cache: once per cue change ------------------------------ */
+/* ttmlrender form: one W*H premultiplied BGRA image (gen_buffer output) plus
+ * the region rectangles that can hold non-transparent pixels. n_rects == 0
+ * means the whole image is one rectangle. Replaces the stream's previous
+ * overlay atomically; frames already submitted keep the old one. */
+FLUC_EXPORT int fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream,
+    const uint8_t *bgra_premul, int32_t w, int32_t h, int32_t stride,
+    const FlucTtmlBlendRect *rects, uint32_t n_rects);
+/* GstVideoOverlayComposition form: independent rectangles, blended in order. */
+FLUC_EXPORT int fluc_ttmlblend_overlay_set_rectangles (FlucTtmlBlend *thiz,
+    uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n_rects);
+/* The "clear" buffer ttmlrender pushes for timeline gaps
+ * (/root/reference/plugins/ttml/gstttmlevent.c:221-224): frames pass through. */
+FLUC_EXPORT int fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream);
+
+/* ---- per frame, device-resident (batched) ---------------------------- */
+/* Queues one frame. src/dst hold DEVICE pointers; dst == src (same plane[0])
+ * blends in place like gst_video_blend does, otherwise the whole frame is
+ * written to dst. frame_flags: FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA for a
+ * premultiplied destination. The batch is launched by flush(), by wait() on
+ * one of its tickets, when it reaches the batch limit, or by the scheduler
+ * thread after the linger time. */
+FLUC_EXPORT int fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream,
+    FlucTtmlBlendFormat fmt, int32_t width, int32_t height, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst,
+    uint64_t *ticket);
+FLUC_EXPORT int fluc_ttmlblend_flush (FlucTtmlBlend *thiz);
+FLUC_EXPORT int fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket);
+FLUC_EXPORT int fluc_ttmlblend_sync (FlucTtmlBlend *thiz);   /* flush + wait all */
+/* Scheduler knobs: frames per launch (default 32, 1..1024) and how long the
+ * scheduler thread lets a partial batch linger, in microseconds (default 200;
+ * 0 = no scheduler thread launches, only flush/wait/limit). */
+FLUC_EXPORT int fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_frames,
+    uint32_t linger_us);
+
+/* ---- per frame, host-resident: the drop-in for -----------------------
+ * gst_video_overlay_composition_blend (comp, frame). The frame is in HOST
+ * memory and is modified in place; only the rows the overlay can touch cross
+ * PCIe (host -> device, blend, device -> host). Asynchronous: the copy back
+ * has finished once wait(ticket) returns. Pinned memory (pool frames or
+ * host_register) keeps the copies asynchronous. */
+FLUC_EXPORT int fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream,
+    FlucTtmlBlendFormat fmt, int32_t width, int32_t height, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *host_frame, uint64_t *ticket);
+FLUC_EXPORT int fluc_ttmlblend_host_register (FlucTtmlBlend *thiz, void *ptr, size_t bytes);
+FLUC_EXPORT int fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr);
+
+/* ---- frame pool ------------------------------------------------------ */
+/* Device frames (HBM) or pinned host staging frames, recycled by geometry.
+ * Planes are 256-byte aligned with a 256-byte multiple stride. */
+FLUC_EXPORT int fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz,
+    FlucTtmlBlendFormat fmt, int32_t width, int32_t height, int on_host,
+    FlucTtmlBlendFrame *out);
+FLUC_EXPORT int fluc_ttmlblend_frame_pool_release (FlucTtmlBlend *thiz,
+    const FlucTtmlBlendFrame *frame);
+/* Synchronous whole-frame copies between a host frame and a device frame. */
+FLUC_EXPORT int fluc_ttmlblend_frame_upload (FlucTtmlBlend *thiz,
+    FlucTtmlBlendFormat fmt, int32_t width, int32_t height,
+    const FlucTtmlBlendFrame *host_src, const FlucTtmlBlendFrame *dev_dst);
+FLUC_EXPORT int fluc_ttmlblend_frame_download (FlucTtmlBlend *thiz,
+    FlucTtmlBlendFormat fmt, int32_t width, int32_t height,
+    const FlucTtmlBlendFrame *dev_src, const FlucTtmlBlendFrame *host_dst);
+/* Plane geometry of a format (rows and valid bytes per row). */
+FLUC_EXPORT int fluc_ttmlblend_format_planes (FlucTtmlBlendFormat fmt);
+FLUC_EXPORT int fluc_ttmlblend_plane_row_bytes (FlucTtmlBlendFormat fmt, int plane, int32_t width);
+FLUC_EXPORT int fluc_ttmlblend_plane_rows (FlucTtmlBlendFormat fmt, int plane, int32_t height);
+
+/* ---- observability --------------------------------------------------- */
+FLUC_EXPORT void fluc_ttmlblend_stats_copy (FlucTtmlBlend *thiz, FlucTtmlBlendStats *out);
+FLUC_EXPORT void fluc_ttmlblend_stats_reset (FlucTtmlBlend *thiz);
+/* Per-launch CUDA-event timing of the blend kernel into stats.kernel_ms. */
+FLUC_EXPORT int fluc_ttmlblend_set_profiling (FlucTtmlBlend *thiz, int enabled);
+/* Device timer on the blend stream: begin records an event, end records a
+ * second one, waits for it and returns the milliseconds in between. */
+FLUC_EXPORT int fluc_ttmlblend_timer_begin (FlucTtmlBlend *thiz);
+FLUC_EXPORT int fluc_ttmlblend_timer_end (FlucTtmlBlend *thiz, double *ms);
+/* Writes `bytes` of device memory on the blend stream (L2 flush for benches). */
+FLUC_EXPORT int fluc_ttmlblend_scrub_l2 (FlucTtmlBlend *thiz, size_t bytes);
+/* The cudaStream_t the batched blend launches on, as an opaque pointer. */
+FLUC_EXPORT void *fluc_ttmlblend_stream_handle (FlucTtmlBlend *thiz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* _FLUC_TTMLBLEND_H_ */

@@ -1,0 +1,112 @@
+"""ctypes binding of the CPU oracle (oracle/ttmlblend_ref.c).
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see ttmlblend_ref.h). Importable
+from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs only; never from the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FORMATS = {"I420": 0, "NV12": 1, "AYUV": 2, "RGBA": 3, "BGRA": 4,
+           "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8}
+FLAG_PREMULTIPLIED_ALPHA = 1
+
+
+class RefFrame(C.Structure):
+    _fields_ = [("format", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("flags", C.c_uint32), ("data", C.c_void_p * 3), ("stride", C.c_int32 * 3)]
+
+
+class RefRectangle(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32),
+                ("stride", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
+                ("global_alpha", C.c_float), ("flags", C.c_uint32)]
+
+
+def build(native: bool = False, out_dir: str = None) -> str:
+    """Compiles the oracle. native=True adds -march=native (CPU baseline on the box it runs on)."""
+    out_dir = out_dir or _HERE
+    name = "libttmlblend_ref_native.so" if native else "libttmlblend_ref.so"
+    out = os.path.join(out_dir, name)
+    src = os.path.join(_HERE, "ttmlblend_ref.c")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src) and not native:
+        return out
+    flags = ["-O3", "-fPIC", "-shared", "-std=c99", "-D_POSIX_C_SOURCE=200809L"]
+    if native:
+        flags.append("-march=native")
+    subprocess.check_call(["gcc", *flags, "-o", out, src, "-lpthread"])
+    return out
+
+
+_libs = {}
+
+
+def load(native: bool = False, out_dir: str = None):
+    key = (native, out_dir)
+    if key in _libs:
+        return _libs[key]
+    lib = C.CDLL(build(native, out_dir))
+    lib.tbref_video_blend.restype = C.c_int
+    lib.tbref_video_blend.argtypes = [C.POINTER(RefFrame), C.POINTER(RefRectangle)]
+    lib.tbref_composition_blend.restype = C.c_int
+    lib.tbref_composition_blend.argtypes = [C.POINTER(RefFrame), C.POINTER(RefRectangle), C.c_uint32]
+    lib.tbref_blend_many.restype = C.c_double
+    lib.tbref_blend_many.argtypes = [C.POINTER(RefFrame), C.c_uint32, C.POINTER(RefRectangle),
+                                     C.c_uint32, C.c_uint32]
+    for n in ("tbref_matrix_prea_rgb_to_yuv", "tbref_matrix_rgb_to_yuv", "tbref_matrix_yuv_to_rgb"):
+        getattr(lib, n).restype = None
+        getattr(lib, n).argtypes = [C.c_void_p, C.c_uint32]
+    _libs[key] = lib
+    return lib
+
+
+def make_frame(fmt: str, width: int, height: int, planes: Sequence[np.ndarray],
+               premultiplied: bool = False) -> RefFrame:
+    f = RefFrame()
+    f.format = FORMATS[fmt]
+    f.width, f.height = width, height
+    f.flags = FLAG_PREMULTIPLIED_ALPHA if premultiplied else 0
+    for i, p in enumerate(planes):
+        assert p.dtype == np.uint8 and p.ndim == 2 and p.strides[1] == 1
+        f.data[i] = p.ctypes.data
+        f.stride[i] = p.strides[0]
+    return f
+
+
+def make_rectangles(rectangles: Sequence[dict]):
+    """Same dicts as TtmlBlend.overlay_set_rectangles."""
+    arr = (RefRectangle * max(1, len(rectangles)))()
+    for i, r in enumerate(rectangles):
+        px = r["pixels"]
+        assert px.dtype == np.uint8 and px.ndim == 3 and px.shape[2] == 4 and px.strides[2] == 1
+        arr[i] = RefRectangle(px.ctypes.data, px.shape[1], px.shape[0], px.strides[0],
+                              int(r.get("x", 0)), int(r.get("y", 0)),
+                              float(r.get("global_alpha", 1.0)),
+                              FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0)
+    return arr
+
+
+def composition_blend(fmt: str, width: int, height: int, planes: Sequence[np.ndarray],
+                      rectangles: Sequence[dict], premultiplied_dest: bool = False, lib=None):
+    """gst_video_overlay_composition_blend on `planes`, in place. Returns planes."""
+    lib = lib or load()
+    f = make_frame(fmt, width, height, planes, premultiplied_dest)
+    arr = make_rectangles(rectangles)
+    ok = lib.tbref_composition_blend(C.byref(f), arr, len(rectangles))
+    if not ok and rectangles:
+        raise RuntimeError("tbref_composition_blend returned FALSE")
+    return planes
+
+
+def ttmlrender_rectangles(bgra: np.ndarray, rects: Sequence[Sequence[int]] = ()):
+    """What the reference pipeline blends: ttmlrender's frame-sized image as ONE
+    premultiplied rectangle at (0,0); `rects` is ignored on purpose (the region boxes only
+    tell the GPU path where non-transparent pixels can be)."""
+    return [dict(pixels=bgra, x=0, y=0, global_alpha=1.0, premultiplied=True)]

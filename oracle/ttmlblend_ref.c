@@ -1,0 +1,521 @@
+/*
+ * ttmlblend_ref.c -- CPU ORACLE (test infrastructure, never shipped).
+ *
+ * PARITY UNPINNED -- see ttmlblend_ref.h. A line-structured restatement of
+ * gst-plugins-base `gst_video_overlay_composition_blend` /
+ * `gst_video_blend` (gst-libs/gst/video/video-overlay-composition.c,
+ * video-blend.c) and the pack/unpack routines of video-format.c for the
+ * destination formats ttmlrender's overlay can meet. The structure is kept
+ * like upstream on purpose (unpack whole dest line -> unpack src segment ->
+ * matrix -> per-pixel OVER -> pack whole dest line) so that it can be
+ * diffed against the real file on a box that has it; docs/BLENDSPEC.md holds
+ * the frozen spec, SURVEY.md Appendix A the derivation.
+ *
+ * Overlay contents come from the reference:
+ *   /root/reference/plugins/ttml/gstttmlrender.c:1427-1478  gen_buffer():
+ *     W*H*4 bytes, stride W*4, Cairo ARGB32 (premultiplied, bytes B,G,R,A)
+ *   /root/reference/plugins/ttml/gstttmlrender.c:1235-1385  show_regions():
+ *     background colour / opacity are already baked into those pixels, so
+ *     the blend applies nothing but the per-pixel alpha.
+ */
+#include "ttmlblend_ref.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define TB_MIN(a, b) ((a) < (b) ? (a) : (b))
+#define TB_CLAMP(v, lo, hi) ((v) < (lo) ? (lo) : ((v) > (hi) ? (hi) : (v)))
+
+/* ---------------------------------------------------------------------- */
+/* geometry                                                               */
+
+static int
+is_yuv (int32_t f)
+{
+  return f == TBREF_FORMAT_I420 || f == TBREF_FORMAT_NV12 ||
+      f == TBREF_FORMAT_AYUV || f == TBREF_FORMAT_YV12 ||
+      f == TBREF_FORMAT_NV21;
+}
+
+int32_t
+tbref_n_planes (int32_t f)
+{
+  switch (f) {
+    case TBREF_FORMAT_I420:
+    case TBREF_FORMAT_YV12:
+      return 3;
+    case TBREF_FORMAT_NV12:
+    case TBREF_FORMAT_NV21:
+      return 2;
+    default:
+      return 1;
+  }
+}
+
+int32_t
+tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
+{
+  switch (f) {
+    case TBREF_FORMAT_I420:
+    case TBREF_FORMAT_YV12:
+      return plane == 0 ? w : (w + 1) / 2;
+    case TBREF_FORMAT_NV12:
+    case TBREF_FORMAT_NV21:
+      return plane == 0 ? w : 2 * ((w + 1) / 2);
+    default:
+      return 4 * w;
+  }
+}
+
+int32_t
+tbref_plane_rows (int32_t f, int32_t plane, int32_t h)
+{
+  if (tbref_n_planes (f) > 1 && plane > 0)
+    return (h + 1) / 2;
+  return h;
+}
+
+/* ---------------------------------------------------------------------- */
+/* video-format.c: unpack a whole line to (A, c1, c2, c3) 8-bit           */
+/* 4:2:0 -- unpack_planar_420 / unpack_NV12: chroma of row y>>1 replicated */
+/* over both pixels of a pair (ORC loadupdb); A = 0xff.                    */
+
+static void
+unpack_line (const TbRefFrame *f, int y, uint8_t *d, int width)
+{
+  int x;
+  switch (f->format) {
+    case TBREF_FORMAT_I420:
+    case TBREF_FORMAT_YV12:{
+      int pu = f->format == TBREF_FORMAT_I420 ? 1 : 2;
+      int pv = f->format == TBREF_FORMAT_I420 ? 2 : 1;
+      const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
+      const uint8_t *su = f->data[pu] + (size_t) f->stride[pu] * (y >> 1);
+      const uint8_t *sv = f->data[pv] + (size_t) f->stride[pv] * (y >> 1);
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = sy[x];
+        d[4 * x + 2] = su[x >> 1];
+        d[4 * x + 3] = sv[x >> 1];
+      }
+      break;
+    }
+    case TBREF_FORMAT_NV12:
+    case TBREF_FORMAT_NV21:{
+      int ou = f->format == TBREF_FORMAT_NV12 ? 0 : 1;
+      const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
+      const uint8_t *suv = f->data[1] + (size_t) f->stride[1] * (y >> 1);
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = sy[x];
+        d[4 * x + 2] = suv[(x >> 1) * 2 + ou];
+        d[4 * x + 3] = suv[(x >> 1) * 2 + (1 - ou)];
+      }
+      break;
+    }
+    case TBREF_FORMAT_AYUV:
+    case TBREF_FORMAT_ARGB:
+      memcpy (d, f->data[0] + (size_t) f->stride[0] * y, (size_t) width * 4);
+      break;
+    case TBREF_FORMAT_RGBA:{
+      const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = s[4 * x + 3];
+        d[4 * x + 1] = s[4 * x + 0];
+        d[4 * x + 2] = s[4 * x + 1];
+        d[4 * x + 3] = s[4 * x + 2];
+      }
+      break;
+    }
+    case TBREF_FORMAT_BGRA:{
+      const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = s[4 * x + 3];
+        d[4 * x + 1] = s[4 * x + 2];
+        d[4 * x + 2] = s[4 * x + 1];
+        d[4 * x + 3] = s[4 * x + 0];
+      }
+      break;
+    }
+    case TBREF_FORMAT_ABGR:{
+      const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = s[4 * x + 0];
+        d[4 * x + 1] = s[4 * x + 3];
+        d[4 * x + 2] = s[4 * x + 2];
+        d[4 * x + 3] = s[4 * x + 1];
+      }
+      break;
+    }
+  }
+}
+
+/* video-format.c: pack a whole (A,c1,c2,c3) line back.
+ * pack_planar_420 / pack_NV12: luma always; chroma ONLY on chroma lines
+ * (IS_CHROMA_LINE_420: progressive => even y) and ONLY from the even-x pixel
+ * of each pair (video_orc_pack_I420/NV12: select0wb); an odd trailing pixel
+ * writes its own chroma. No averaging anywhere. */
+static void
+pack_line (TbRefFrame *f, int y, const uint8_t *s, int width)
+{
+  int i, x;
+  switch (f->format) {
+    case TBREF_FORMAT_I420:
+    case TBREF_FORMAT_YV12:{
+      int pu = f->format == TBREF_FORMAT_I420 ? 1 : 2;
+      int pv = f->format == TBREF_FORMAT_I420 ? 2 : 1;
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      uint8_t *du = f->data[pu] + (size_t) f->stride[pu] * (y >> 1);
+      uint8_t *dv = f->data[pv] + (size_t) f->stride[pv] * (y >> 1);
+      if (!(y & 1)) {
+        for (i = 0; i < width / 2; i++) {
+          dy[i * 2 + 0] = s[i * 8 + 1];
+          dy[i * 2 + 1] = s[i * 8 + 5];
+          du[i] = s[i * 8 + 2];
+          dv[i] = s[i * 8 + 3];
+        }
+        if (width & 1) {
+          i = width - 1;
+          dy[i] = s[i * 4 + 1];
+          du[i >> 1] = s[i * 4 + 2];
+          dv[i >> 1] = s[i * 4 + 3];
+        }
+      } else {
+        for (x = 0; x < width; x++)
+          dy[x] = s[4 * x + 1];
+      }
+      break;
+    }
+    case TBREF_FORMAT_NV12:
+    case TBREF_FORMAT_NV21:{
+      int ou = f->format == TBREF_FORMAT_NV12 ? 0 : 1;
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      uint8_t *duv = f->data[1] + (size_t) f->stride[1] * (y >> 1);
+      if (!(y & 1)) {
+        for (i = 0; i < width / 2; i++) {
+          dy[i * 2 + 0] = s[i * 8 + 1];
+          dy[i * 2 + 1] = s[i * 8 + 5];
+          duv[i * 2 + ou] = s[i * 8 + 2];
+          duv[i * 2 + (1 - ou)] = s[i * 8 + 3];
+        }
+        if (width & 1) {
+          i = width - 1;
+          dy[i] = s[i * 4 + 1];
+          duv[i + ou] = s[i * 4 + 2];
+          duv[i + (1 - ou)] = s[i * 4 + 3];
+        }
+      } else {
+        for (x = 0; x < width; x++)
+          dy[x] = s[4 * x + 1];
+      }
+      break;
+    }
+    case TBREF_FORMAT_AYUV:
+    case TBREF_FORMAT_ARGB:
+      memcpy (f->data[0] + (size_t) f->stride[0] * y, s, (size_t) width * 4);
+      break;
+    case TBREF_FORMAT_RGBA:{
+      uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 3] = s[4 * x + 0];
+        d[4 * x + 0] = s[4 * x + 1];
+        d[4 * x + 1] = s[4 * x + 2];
+        d[4 * x + 2] = s[4 * x + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_BGRA:{
+      uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 3] = s[4 * x + 0];
+        d[4 * x + 2] = s[4 * x + 1];
+        d[4 * x + 1] = s[4 * x + 2];
+        d[4 * x + 0] = s[4 * x + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_ABGR:{
+      uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = s[4 * x + 0];
+        d[4 * x + 3] = s[4 * x + 1];
+        d[4 * x + 2] = s[4 * x + 2];
+        d[4 * x + 1] = s[4 * x + 3];
+      }
+      break;
+    }
+  }
+}
+
+/* unpack_BGRA for the overlay rectangle: bytes (B,G,R,A) -> (A,R,G,B). */
+static void
+unpack_src_bgra (const TbRefRectangle *r, int xoff, int yoff, uint8_t *d,
+    int width)
+{
+  const uint8_t *s = r->pixels + (size_t) r->stride * yoff + 4 * (size_t) xoff;
+  int x;
+  for (x = 0; x < width; x++) {
+    d[4 * x + 0] = s[4 * x + 3];
+    d[4 * x + 1] = s[4 * x + 2];
+    d[4 * x + 2] = s[4 * x + 1];
+    d[4 * x + 3] = s[4 * x + 0];
+  }
+}
+
+/* ---------------------------------------------------------------------- */
+/* video-blend.c colour matrices: BT.709, 8-bit, limited range            */
+
+void
+tbref_matrix_prea_rgb_to_yuv (uint8_t *t, uint32_t width)
+{
+  uint32_t i;
+  int a, r, g, b, y, u, v;
+  for (i = 0; i < width; i++) {
+    a = t[i * 4 + 0];
+    r = t[i * 4 + 1];
+    g = t[i * 4 + 2];
+    b = t[i * 4 + 3];
+    if (a) {
+      r = (r * 255 + a / 2) / a;
+      g = (g * 255 + a / 2) / a;
+      b = (b * 255 + a / 2) / a;
+    }
+    y = (47 * r + 157 * g + 16 * b + 4096) >> 8;
+    u = (-26 * r - 87 * g + 112 * b + 32768) >> 8;
+    v = (112 * r - 102 * g - 10 * b + 32768) >> 8;
+    t[i * 4 + 1] = TB_CLAMP (y, 0, 255);
+    t[i * 4 + 2] = TB_CLAMP (u, 0, 255);
+    t[i * 4 + 3] = TB_CLAMP (v, 0, 255);
+  }
+}
+
+void
+tbref_matrix_rgb_to_yuv (uint8_t *t, uint32_t width)
+{
+  uint32_t i;
+  int r, g, b, y, u, v;
+  for (i = 0; i < width; i++) {
+    r = t[i * 4 + 1];
+    g = t[i * 4 + 2];
+    b = t[i * 4 + 3];
+    y = (47 * r + 157 * g + 16 * b + 4096) >> 8;
+    u = (-26 * r - 87 * g + 112 * b + 32768) >> 8;
+    v = (112 * r - 102 * g - 10 * b + 32768) >> 8;
+    t[i * 4 + 1] = TB_CLAMP (y, 0, 255);
+    t[i * 4 + 2] = TB_CLAMP (u, 0, 255);
+    t[i * 4 + 3] = TB_CLAMP (v, 0, 255);
+  }
+}
+
+void
+tbref_matrix_yuv_to_rgb (uint8_t *t, uint32_t width)
+{
+  uint32_t i;
+  int y, u, v, r, g, b;
+  for (i = 0; i < width; i++) {
+    y = t[i * 4 + 1];
+    u = t[i * 4 + 2];
+    v = t[i * 4 + 3];
+    r = (298 * y + 459 * v - 63514) >> 8;
+    g = (298 * y - 55 * u - 136 * v + 19681) >> 8;
+    b = (298 * y + 541 * u - 73988) >> 8;
+    t[i * 4 + 1] = TB_CLAMP (r, 0, 255);
+    t[i * 4 + 2] = TB_CLAMP (g, 0, 255);
+    t[i * 4 + 3] = TB_CLAMP (b, 0, 255);
+  }
+}
+
+/* ---------------------------------------------------------------------- */
+/* video-blend.c: A OVER B, 8 bit. alphaG = global alpha (premultiplied    */
+/* source only), alphaA/colorA = source, alphaB/colorB = dest, alphaD =    */
+/* blended alpha (non-premultiplied dest only). Integer, truncating.       */
+
+#define OVER00(aG, aA, cA, aB, cB, aD) \
+  (((cA) * (aA) + (cB) * (aB) * (255 - (aA)) / 255) / (aD))
+#define OVER10(aG, aA, cA, aB, cB, aD) \
+  (((cA) * (aG) + (cB) * (aB) * (255 - (aA)) / 255) / (aD))
+#define OVER01(aG, aA, cA, aB, cB, aD) \
+  (((cA) * (aA) + (cB) * (255 - (aA))) / 255)
+#define OVER11(aG, aA, cA, aB, cB, aD) \
+  (((cA) * (aG) + (cB) * (255 - (aA))) / 255)
+
+#define BLENDC(op, aG, aA, cA, aB, cB, aD) do {                \
+    unsigned int c_ = op ((unsigned int) (aG), (aA),           \
+        (unsigned int) (cA), (aB), (unsigned int) (cB),        \
+        (unsigned int) (aD));                                  \
+    (cB) = (uint8_t) TB_MIN (c_, 255u);                        \
+  } while (0)
+
+#define BLENDLOOP(op) do {                                                  \
+    for (j = 0; j < src_width * 4; j += 4) {                                \
+      unsigned int asrc, adst;                                              \
+      int final_alpha;                                                      \
+      asrc = ((unsigned int) tmpsrc[j]) * (unsigned int) ga / 255u;         \
+      if (!asrc)                                                            \
+        continue;                                                           \
+      adst = dl[j];                                                         \
+      final_alpha = (int) (asrc + adst * (255u - asrc) / 255u);             \
+      dl[j] = (uint8_t) final_alpha;                                        \
+      if (final_alpha == 0)                                                 \
+        final_alpha = 1;                                                    \
+      BLENDC (op, ga, asrc, tmpsrc[j + 1], adst, dl[j + 1], final_alpha);   \
+      BLENDC (op, ga, asrc, tmpsrc[j + 2], adst, dl[j + 2], final_alpha);   \
+      BLENDC (op, ga, asrc, tmpsrc[j + 3], adst, dl[j + 3], final_alpha);   \
+    }                                                                       \
+  } while (0)
+
+int
+tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src)
+{
+  int i, j, ga, src_width, src_height, dest_width, dest_height;
+  int src_xoff = 0, src_yoff = 0, x = src->x, y = src->y;
+  int src_premul, dest_premul, mode_matrix = 0;
+  uint8_t *tmpdest, *tmpsrc;
+
+  if (!dest || !src || !src->pixels)
+    return 0;
+  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_ABGR)
+    return 0;
+
+  ga = (int) (255.0 * src->global_alpha);
+  dest_premul = (dest->flags & TBREF_FLAG_PREMULTIPLIED_ALPHA) != 0;
+  src_premul = (src->flags & TBREF_FLAG_PREMULTIPLIED_ALPHA) != 0;
+
+  src_width = src->width;
+  src_height = src->height;
+  dest_width = dest->width;
+  dest_height = dest->height;
+
+  /* completely outside the video: nothing to do, still TRUE */
+  if (x + src_width <= 0 || y + src_height <= 0 || x >= dest_width ||
+      y >= dest_height)
+    return 1;
+
+  /* overlay is RGB; a YUV dest needs the matrix. A premultiplied source is
+   * un-premultiplied by the matrix and treated as straight from then on. */
+  if (is_yuv (dest->format)) {
+    if (src_premul) {
+      mode_matrix = 2;
+      src_premul = 0;
+    } else {
+      mode_matrix = 1;
+    }
+  }
+
+  if (x < 0) {
+    src_xoff = -x;
+    src_width -= src_xoff;
+    x = 0;
+  }
+  if (y < 0) {
+    src_yoff = -y;
+    src_height -= src_yoff;
+    y = 0;
+  }
+  if (x + src_width > dest_width)
+    src_width = dest_width - x;
+  if (y + src_height > dest_height)
+    src_height = dest_height - y;
+
+  tmpdest = (uint8_t *) malloc ((size_t) (dest_width + 8) * 4);
+  tmpsrc = (uint8_t *) malloc ((size_t) (src_width + 8) * 4);
+  if (!tmpdest || !tmpsrc) {
+    free (tmpdest);
+    free (tmpsrc);
+    return 0;
+  }
+
+  for (i = y; i < y + src_height; i++, src_yoff++) {
+    uint8_t *dl;
+    unpack_line (dest, i, tmpdest, dest_width);
+    unpack_src_bgra (src, src_xoff, src_yoff, tmpsrc, src_width);
+    dl = tmpdest + 4 * x;
+
+    if (mode_matrix == 2)
+      tbref_matrix_prea_rgb_to_yuv (tmpsrc, (uint32_t) src_width);
+    else if (mode_matrix == 1)
+      tbref_matrix_rgb_to_yuv (tmpsrc, (uint32_t) src_width);
+
+    if (src_premul && dest_premul)
+      BLENDLOOP (OVER11);
+    else if (!src_premul && dest_premul)
+      BLENDLOOP (OVER01);
+    else if (src_premul && !dest_premul)
+      BLENDLOOP (OVER10);
+    else
+      BLENDLOOP (OVER00);
+
+    pack_line (dest, i, tmpdest, dest_width);
+  }
+
+  free (tmpdest);
+  free (tmpsrc);
+  return 1;
+}
+
+int
+tbref_composition_blend (TbRefFrame *dest, const TbRefRectangle *rects,
+    uint32_t n_rects)
+{
+  uint32_t n;
+  int ret = 1;
+  for (n = 0; n < n_rects; n++)
+    ret = tbref_video_blend (dest, &rects[n]);
+  return ret;
+}
+
+/* ---------------------------------------------------------------------- */
+/* CPU baseline driver (bench.py cpu_baseline / --impl reference)         */
+
+typedef struct {
+  TbRefFrame *frames;
+  uint32_t n_frames, first, step;
+  const TbRefRectangle *rects;
+  uint32_t n_rects;
+} TbRefWork;
+
+static void *
+blend_worker (void *arg)
+{
+  TbRefWork *w = (TbRefWork *) arg;
+  uint32_t i;
+  for (i = w->first; i < w->n_frames; i += w->step)
+    tbref_composition_blend (&w->frames[i], w->rects, w->n_rects);
+  return NULL;
+}
+
+double
+tbref_blend_many (TbRefFrame *frames, uint32_t n_frames,
+    const TbRefRectangle *rects, uint32_t n_rects, uint32_t n_threads)
+{
+  struct timespec t0, t1;
+  pthread_t *tids;
+  TbRefWork *work;
+  uint32_t t;
+
+  if (n_threads < 1)
+    n_threads = 1;
+  tids = (pthread_t *) calloc (n_threads, sizeof (pthread_t));
+  work = (TbRefWork *) calloc (n_threads, sizeof (TbRefWork));
+  clock_gettime (CLOCK_MONOTONIC, &t0);
+  for (t = 0; t < n_threads; t++) {
+    work[t].frames = frames;
+    work[t].n_frames = n_frames;
+    work[t].first = t;
+    work[t].step = n_threads;
+    work[t].rects = rects;
+    work[t].n_rects = n_rects;
+    if (t + 1 < n_threads)
+      pthread_create (&tids[t], NULL, blend_worker, &work[t]);
+  }
+  blend_worker (&work[n_threads - 1]);
+  for (t = 0; t + 1 < n_threads; t++)
+    pthread_join (tids[t], NULL);
+  clock_gettime (CLOCK_MONOTONIC, &t1);
+  free (tids);
+  free (work);
+  return (double) (t1.tv_sec - t0.tv_sec) +
+      1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+}

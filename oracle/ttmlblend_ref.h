@@ -1,0 +1,91 @@
+/*
+ * ttmlblend_ref.h -- CPU ORACLE for the TTML overlay-blend hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing in the product path (the package under
+ * flu-plugins-oss_b200/, include/) may include, link or call this. Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs use it, and only as the checker or the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the arithmetic restated here lives in GStreamer's
+ * gst-plugins-base (libgstvideo-1.0: gst-libs/gst/video/video-blend.c,
+ * video-overlay-composition.c, video-format.c), which the reference only
+ * requires as `gstreamer-video-1.0 >= 1.19` (/root/reference/meson.build:13-17)
+ * and does not vendor. The reference has no call site into it and no test
+ * that pins a pixel. This file restates the published
+ * algorithm (docs/BLENDSPEC.md); oracle/xcheck_gst.c diffs it against a real
+ * libgstvideo wherever one is installed.
+ *
+ * What the overlay contents are (premultiplied, native-endian ARGB32 = bytes
+ * B,G,R,A; cleared to 0) is fixed by the reference itself:
+ * /root/reference/plugins/ttml/gstttmlrender.c:1442-1452 (buffer W*H*4,
+ * CAIRO_FORMAT_ARGB32, stride W*4, CLEAR paint) and :78-84 (src caps BGRA).
+ */
+#ifndef TTMLBLEND_REF_H
+#define TTMLBLEND_REF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Destination frame formats (same numbering as include/fluc_ttmlblend.h). */
+enum {
+  TBREF_FORMAT_I420 = 0,
+  TBREF_FORMAT_NV12 = 1,
+  TBREF_FORMAT_AYUV = 2,
+  TBREF_FORMAT_RGBA = 3,
+  TBREF_FORMAT_BGRA = 4,
+  TBREF_FORMAT_YV12 = 5,
+  TBREF_FORMAT_NV21 = 6,
+  TBREF_FORMAT_ARGB = 7,
+  TBREF_FORMAT_ABGR = 8
+};
+
+#define TBREF_FLAG_PREMULTIPLIED_ALPHA 1u
+
+/* Shape of a mapped GstVideoFrame, reduced to what gst_video_blend reads. */
+typedef struct {
+  int32_t format;
+  int32_t width, height;
+  uint32_t flags;          /* TBREF_FLAG_PREMULTIPLIED_ALPHA on the DEST */
+  uint8_t *data[3];
+  int32_t stride[3];
+} TbRefFrame;
+
+/* Shape of a GstVideoOverlayRectangle with render size == pixel size. */
+typedef struct {
+  const uint8_t *pixels;   /* BGRA byte order (ARGB32 little endian) */
+  int32_t width, height, stride;
+  int32_t x, y;            /* position in the frame; may be negative */
+  float global_alpha;      /* 1.0 in every ttmlrender use */
+  uint32_t flags;          /* TBREF_FLAG_PREMULTIPLIED_ALPHA: Cairo data */
+} TbRefRectangle;
+
+/* gst_video_blend (dest, src, x, y, global_alpha): 1 = TRUE, 0 = FALSE. */
+int tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src);
+
+/* gst_video_overlay_composition_blend (comp, frame): rectangles in order. */
+int tbref_composition_blend (TbRefFrame *dest, const TbRefRectangle *rects,
+    uint32_t n_rects);
+
+/* The three colour matrices of video-blend.c, on an (A,c1,c2,c3) line. */
+void tbref_matrix_prea_rgb_to_yuv (uint8_t *line, uint32_t width);
+void tbref_matrix_rgb_to_yuv (uint8_t *line, uint32_t width);
+void tbref_matrix_yuv_to_rgb (uint8_t *line, uint32_t width);
+
+/* Plane geometry helpers shared by the tests and the bench. */
+int32_t tbref_n_planes (int32_t format);
+int32_t tbref_plane_row_bytes (int32_t format, int32_t plane, int32_t width);
+int32_t tbref_plane_rows (int32_t format, int32_t plane, int32_t height);
+
+/* CPU baseline driver: blends `n_frames` frames (one composition each,
+ * frames[i] in place) on `n_threads` pthreads, frames dealt round-robin.
+ * Returns wall seconds of the blending only. */
+double tbref_blend_many (TbRefFrame *frames, uint32_t n_frames,
+    const TbRefRectangle *rects, uint32_t n_rects, uint32_t n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTMLBLEND_REF_H */
