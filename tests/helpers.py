@@ -1,0 +1,196 @@
+"""Shared test helpers: a numpy model of the blend's NET semantics (independent of the
+oracle's line-by-line structure), random inputs, and GPU runners through the C ABI."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle
+import __graft_entry__ as graft
+
+pkg = graft.load_package()
+wl = pkg.workloads
+
+YUV_FORMATS = ("I420", "YV12", "NV12", "NV21", "AYUV")
+PLANAR_420 = ("I420", "YV12", "NV12", "NV21")
+PACKED = ("AYUV", "ARGB", "ABGR", "RGBA", "BGRA")
+ALL_FORMATS = PLANAR_420 + PACKED
+
+# byte positions of (A, c1, c2, c3) inside a packed pixel, c = (Y,U,V) or (R,G,B)
+PACKED_ORDER = {"AYUV": (0, 1, 2, 3), "ARGB": (0, 1, 2, 3), "ABGR": (0, 3, 2, 1),
+                "RGBA": (3, 0, 1, 2), "BGRA": (3, 2, 1, 0)}
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def random_frame(fmt, w, h, seed, opaque=True, pad=0):
+    """Planes with optional row padding (stride = row bytes + pad)."""
+    r = rng(seed)
+    planes = []
+    for rows, rb in wl.plane_shapes(fmt, w, h):
+        buf = r.integers(0, 256, size=(rows, rb + pad), dtype=np.uint8)
+        planes.append(buf[:, :rb])
+    ai = wl.alpha_byte_index(fmt)
+    if ai is not None and opaque:
+        planes[0][:, ai::4] = 255
+    return planes
+
+
+def random_overlay(w, h, seed, premultiplied=True, density=0.7, pad=0):
+    """h x w x 4 BGRA with a mix of transparent, opaque and partial pixels."""
+    r = rng(seed)
+    buf = np.zeros((h, w + pad, 4), dtype=np.uint8)
+    img = buf[:, :w, :]
+    a = r.integers(0, 256, size=(h, w), dtype=np.uint8)
+    kind = r.random((h, w))
+    a[kind > density] = 0
+    a[kind < 0.15] = 255
+    a[(kind > 0.15) & (kind < 0.2)] = 1
+    a[(kind > 0.2) & (kind < 0.25)] = 254
+    c = r.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    if premultiplied:
+        c = ((c.astype(np.uint32) * a[:, :, None].astype(np.uint32) + 127) // 255).astype(np.uint8)
+    img[:, :, :3] = c
+    img[:, :, 3] = a
+    return img
+
+
+def copy_planes(planes):
+    return [np.ascontiguousarray(p).copy() for p in planes]
+
+
+# ---------------------------------------------------------------------------
+# numpy model: per-plane net semantics (SURVEY.md Appendix A.4 / docs/BLENDSPEC.md)
+
+def _matrix_rgb_to_yuv(r, g, b):
+    y = np.clip((47 * r + 157 * g + 16 * b + 4096) >> 8, 0, 255)
+    u = np.clip((-26 * r - 87 * g + 112 * b + 32768) >> 8, 0, 255)
+    v = np.clip((112 * r - 102 * g - 10 * b + 32768) >> 8, 0, 255)
+    return y, u, v
+
+
+def _over(cs, cd, asrc, adst, ga, sp, dp):
+    """The four OVERxy operators on int64 arrays; returns (colour, alpha) for asrc > 0."""
+    fa = asrc + adst * (255 - asrc) // 255
+    fa1 = np.where(fa == 0, 1, fa)
+    num_s = cs * ga if sp else cs * asrc
+    if not dp:
+        v = (num_s + cd * adst * (255 - asrc) // 255) // fa1
+    else:
+        v = (num_s + cd * (255 - asrc)) // 255
+    return np.minimum(v, 255), fa
+
+
+def model_blend(fmt, w, h, planes, rectangles, dest_premul=False):
+    """Blends in place on `planes` and returns them."""
+    fmt = fmt.upper()
+    for rc in rectangles:
+        px = rc["pixels"].astype(np.int64)
+        ga = int(255.0 * float(np.float32(rc.get("global_alpha", 1.0))))
+        sp = bool(rc.get("premultiplied", True))
+        x, y = int(rc.get("x", 0)), int(rc.get("y", 0))
+        rh, rw = px.shape[:2]
+        x0, y0, x1, y1 = max(x, 0), max(y, 0), min(x + rw, w), min(y + rh, h)
+        if x1 <= x0 or y1 <= y0:
+            continue
+        sub = px[y0 - y:y1 - y, x0 - x:x1 - x]
+        b, g, r, a = sub[..., 0], sub[..., 1], sub[..., 2], sub[..., 3]
+        if fmt in YUV_FORMATS:
+            if sp:
+                an = np.where(a == 0, 1, a)
+                r = np.where(a > 0, (r * 255 + a // 2) // an, r)
+                g = np.where(a > 0, (g * 255 + a // 2) // an, g)
+                b = np.where(a > 0, (b * 255 + a // 2) // an, b)
+                sp = False
+            c1, c2, c3 = _matrix_rgb_to_yuv(r, g, b)
+        else:
+            c1, c2, c3 = r, g, b
+        asrc = a * ga // 255
+        m = asrc > 0
+        if fmt in PLANAR_420:
+            Y = planes[0]
+            yd = Y[y0:y1, x0:x1].astype(np.int64)
+            v, _ = _over(c1, yd, asrc, 255, ga, sp, dest_premul)
+            Y[y0:y1, x0:x1] = np.where(m, v, yd).astype(np.uint8)
+            # chroma sample (bx, by) <- overlay pixel at frame (2bx, 2by) only
+            ex0, ey0 = x0 + (x0 & 1), y0 + (y0 & 1)
+            if ex0 < x1 and ey0 < y1:
+                sl = (slice(ey0 - y0, None, 2), slice(ex0 - x0, None, 2))
+                cu, cv, ca, cm = c2[sl], c3[sl], asrc[sl], m[sl]
+                by0, bx0 = ey0 // 2, ex0 // 2
+                nby, nbx = cu.shape
+                if fmt in ("I420", "YV12"):
+                    pu, pv = (1, 2) if fmt == "I420" else (2, 1)
+                    for plane, cc in ((planes[pu], cu), (planes[pv], cv)):
+                        d = plane[by0:by0 + nby, bx0:bx0 + nbx].astype(np.int64)
+                        vv, _ = _over(cc, d, ca, 255, ga, sp, dest_premul)
+                        plane[by0:by0 + nby, bx0:bx0 + nbx] = np.where(cm, vv, d).astype(np.uint8)
+                else:
+                    ou, ov = (0, 1) if fmt == "NV12" else (1, 0)
+                    UV = planes[1]
+                    for off, cc in ((ou, cu), (ov, cv)):
+                        view = UV[by0:by0 + nby, 2 * bx0 + off:2 * (bx0 + nbx):2]
+                        d = view.astype(np.int64)
+                        vv, _ = _over(cc, d, ca, 255, ga, sp, dest_premul)
+                        view[...] = np.where(cm, vv, d).astype(np.uint8)
+        else:
+            ia, i1, i2, i3 = PACKED_ORDER[fmt]
+            P = planes[0]
+            rows = P[y0:y1, 4 * x0:4 * x1]
+            adst = rows[:, ia::4].astype(np.int64)
+            outs = {}
+            for idx, cs in ((i1, c1), (i2, c2), (i3, c3)):
+                cd = rows[:, idx::4].astype(np.int64)
+                v, fa = _over(cs, cd, asrc, adst, ga, sp, dest_premul)
+                outs[idx] = np.where(m, v, cd).astype(np.uint8)
+            outs[ia] = np.where(m, fa, adst).astype(np.uint8)
+            for idx, val in outs.items():
+                rows[:, idx::4] = val
+    return planes
+
+
+def oracle_blend(fmt, w, h, planes, rectangles, dest_premul=False):
+    return oracle.composition_blend(fmt, w, h, planes, rectangles, dest_premul)
+
+
+# ---------------------------------------------------------------------------
+# GPU runners (C ABI). mode: "out" (src -> dst), "inplace" (device frame), "host"
+
+def gpu_blend(ctx, fmt, w, h, planes, rectangles=None, mode="out", stream=1, dest_premul=False,
+              overlay=None, regions=(), set_overlay=True):
+    flags = pkg.ttmlblend.FLAG_PREMULTIPLIED_ALPHA if dest_premul else 0
+    if set_overlay:
+        if overlay is not None:
+            ctx.overlay_set(stream, overlay, regions)
+        elif rectangles is not None:
+            ctx.overlay_set_rectangles(stream, rectangles)
+    if mode == "host":
+        out = copy_planes(planes)
+        ctx.wait(ctx.blend_host(stream, fmt, w, h, out, flags))
+        return out
+    src = ctx.acquire(fmt, w, h)
+    try:
+        src.upload(planes)
+        if mode == "inplace":
+            ctx.wait(ctx.submit(stream, fmt, w, h, src.c, src.c, flags))
+            return src.download()
+        dst = ctx.acquire(fmt, w, h)
+        try:
+            ctx.wait(ctx.submit(stream, fmt, w, h, src.c, dst.c, flags))
+            return dst.download()
+        finally:
+            dst.release()
+    finally:
+        src.release()
+
+
+def assert_planes_equal(got, want, what=""):
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            y, x = bad[0]
+            raise AssertionError(
+                f"{what} plane {i}: {len(bad)} bytes differ; first at row {y} byte {x}: "
+                f"got {int(a[y, x])} want {int(b[y, x])}")

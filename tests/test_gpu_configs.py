@@ -1,0 +1,112 @@
+"""GPU parity at BASELINE.json's full sizes: every config's frames against the oracle
+(a few frames each, the oracle takes ~0.1-0.2 s per 4K frame) plus size-independent
+properties over the whole batch (in-place == out-of-place == host path, untouched bytes
+outside the regions, batch == one-by-one)."""
+import numpy as np
+import pytest
+
+from helpers import assert_planes_equal, copy_planes, oracle_blend, pkg, wl
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def run_batch(ctx, cfg, fmt, n_frames, stream=400, inplace=False):
+    srcs = [ctx.acquire(fmt, cfg.width, cfg.height) for _ in range(n_frames)]
+    dsts = srcs if inplace else [ctx.acquire(fmt, cfg.width, cfg.height) for _ in range(n_frames)]
+    frames = [wl.frame_for(cfg, i, fmt) for i in range(n_frames)]
+    for s, f in zip(srcs, frames):
+        s.upload(f)
+    tickets = [ctx.submit(stream, fmt, cfg.width, cfg.height, s.c, d.c) for s, d in zip(srcs, dsts)]
+    ctx.wait(tickets[-1])
+    outs = [d.download() for d in dsts]
+    for f in set(srcs) | set(dsts):
+        f.release()
+    return frames, outs
+
+
+@pytest.mark.parametrize("cfg_id,fmt,n_frames,n_check", [
+    (1, "I420", 4, 4), (2, "NV12", 4, 4), (3, "NV12", 32, 3),
+    (4, "RGBA", 8, 2), (4, "BGRA", 8, 2), (4, "AYUV", 8, 2), (5, "I420", 8, 3),
+])
+def test_config_matches_oracle(ctx, cfg_id, fmt, n_frames, n_check):
+    cfg = wl.CONFIGS[cfg_id]
+    ov = wl.overlay_for(cfg)
+    ctx.overlay_set(400, ov, wl.region_rects(cfg))
+    ctx.set_batch(max(32, n_frames), 0)
+    try:
+        before = ctx.stats()["launches"]
+        frames, outs = run_batch(ctx, cfg, fmt, n_frames)
+        assert ctx.stats()["launches"] - before == 1          # the whole batch in one launch
+        ref_rects = oracle.ttmlrender_rectangles(ov)
+        for i in list(range(n_check - 1)) + [n_frames - 1]:
+            want = oracle_blend(fmt, cfg.width, cfg.height, copy_planes(frames[i]), ref_rects)
+            assert_planes_equal(outs[i], want, f"cfg {cfg_id} {fmt} frame {i}")
+        # property: bytes outside the region rows are copied through untouched
+        y_lo = min(r.y for r in cfg.regions)
+        for fr, out in zip(frames, outs):
+            assert np.array_equal(out[0][:y_lo], fr[0][:y_lo])
+        # property: in place == out of place, for every frame of the batch
+        _, outs_ip = run_batch(ctx, cfg, fmt, n_frames, inplace=True)
+        for i, (a, b) in enumerate(zip(outs, outs_ip)):
+            assert_planes_equal(b, a, f"in-place frame {i}")
+    finally:
+        ctx.set_batch(32, 200)
+
+
+@pytest.mark.parametrize("cfg_id,fmt", [(2, "NV12"), (3, "NV12"), (4, "BGRA")])
+def test_host_path_matches_device_path(ctx, cfg_id, fmt):
+    """blend_host (the gst_video_overlay_composition_blend drop-in, host frames, PCIe rows
+    only) gives the same bytes as the device-resident path, pinned and pageable memory."""
+    cfg = wl.CONFIGS[cfg_id]
+    ov = wl.overlay_for(cfg)
+    ctx.overlay_set(401, ov, wl.region_rects(cfg))
+    frames = [wl.frame_for(cfg, i, fmt) for i in range(3)]
+    want = [oracle_blend(fmt, cfg.width, cfg.height, copy_planes(f), oracle.ttmlrender_rectangles(ov))
+            for f in frames]
+    # pageable numpy memory
+    for f, w in zip(frames, want):
+        got = copy_planes(f)
+        ctx.wait(ctx.blend_host(401, fmt, cfg.width, cfg.height, got))
+        assert_planes_equal(got, w, "pageable")
+    # pinned pool frames, several in flight
+    pinned = [ctx.acquire(fmt, cfg.width, cfg.height, on_host=True) for _ in frames]
+    for p, f in zip(pinned, frames):
+        for dst, src in zip(p.host_planes(), f):
+            dst[...] = src
+    tickets = [ctx.blend_host_frame(401, fmt, cfg.width, cfg.height, p.c) for p in pinned]
+    for t in tickets:
+        ctx.wait(t)
+    for p, w in zip(pinned, want):
+        assert_planes_equal([np.array(x) for x in p.host_planes()], w, "pinned")
+        p.release()
+
+
+def test_256_streams_each_with_its_own_cue(ctx):
+    """Config 5's shape on one GPU: many independent streams, one frame each, one launch."""
+    cfg = wl.CONFIGS[5]
+    n = 24
+    ctx.set_batch(64, 0)
+    try:
+        ovs = [wl.overlay_for(cfg, stream=s) for s in range(n)]
+        for s, ov in enumerate(ovs):
+            ctx.overlay_set(1000 + s, ov, wl.region_rects(cfg))
+        srcs = [ctx.acquire(cfg.fmt, cfg.width, cfg.height) for _ in range(n)]
+        dsts = [ctx.acquire(cfg.fmt, cfg.width, cfg.height) for _ in range(n)]
+        frames = [wl.frame_for(cfg, s) for s in range(n)]
+        for s_, f in zip(srcs, frames):
+            s_.upload(f)
+        before = ctx.stats()["launches"]
+        tk = [ctx.submit(1000 + s, cfg.fmt, cfg.width, cfg.height, srcs[s].c, dsts[s].c) for s in range(n)]
+        ctx.wait(tk[-1])
+        assert ctx.stats()["launches"] - before == 1
+        for s in (0, 7, n - 1):
+            want = oracle_blend(cfg.fmt, cfg.width, cfg.height, copy_planes(frames[s]),
+                                oracle.ttmlrender_rectangles(ovs[s]))
+            assert_planes_equal(dsts[s].download(), want, f"stream {s}")
+        for f in srcs + dsts:
+            f.release()
+        for s in range(n):
+            ctx.overlay_clear(1000 + s)
+    finally:
+        ctx.set_batch(32, 200)

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs -- bit-exact (integer/byte work, tolerance 0)."""
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from helpers import (ALL_FORMATS, PACKED, PLANAR_420, assert_planes_equal, copy_planes, gpu_blend,
+                     oracle_blend, pkg, random_frame, random_overlay, wl)
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+MODES = ("out", "inplace", "host")
+
+CASES = [
+    # w, h, [(rw, rh, x, y, global_alpha, premultiplied)], opaque dest, premultiplied dest
+    (64, 48, [(32, 16, 8, 8, 1.0, True)], True, False),
+    (63, 47, [(31, 15, 7, 9, 1.0, True)], True, False),
+    (1279, 719, [(1000, 100, 133, 575, 1.0, True)], True, False),
+    (64, 48, [(40, 30, -10, -7, 1.0, True)], True, False),
+    (64, 48, [(40, 30, 40, 30, 1.0, True)], True, False),
+    (33, 21, [(80, 60, -20, -20, 1.0, True)], True, False),
+    (64, 48, [(1, 1, 5, 5, 1.0, True), (1, 1, 6, 6, 1.0, True), (1, 1, 63, 47, 1.0, True)], True, False),
+    (200, 120, [(100, 50, 8, 8, 1.0, True), (100, 50, 60, 30, 1.0, True), (50, 90, 90, 20, 1.0, True)], True, False),
+    (64, 48, [(32, 16, 8, 8, 0.5, True), (20, 20, 30, 20, 0.8, False)], True, False),
+    (64, 48, [(32, 16, 8, 8, 1.0, False)], True, False),
+    (64, 48, [(32, 16, 9, 7, 1.0, True)], False, False),
+    (64, 48, [(32, 16, 9, 7, 0.7, True), (16, 16, 12, 10, 1.0, False)], False, True),
+    (640, 360, [(640, 60, 0, 290, 1.0, True), (300, 40, 170, 10, 1.0, True)], True, False),
+    (64, 48, [(30, 20, 70, 10, 1.0, True)], True, False),            # fully outside
+    (64, 48, [(30, 20, 3, 3, 0.0, True)], True, False),              # global alpha 0
+]
+
+
+def make_rects(case):
+    _, _, rects, _, _ = CASES[case]
+    return [dict(pixels=random_overlay(rw, rh, 900 + 10 * case + i, premultiplied=pm),
+                 x=x, y=y, global_alpha=ga, premultiplied=pm)
+            for i, (rw, rh, x, y, ga, pm) in enumerate(rects)]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_rectangles_match_oracle(ctx, fmt, case, mode):
+    w, h, _, opaque, dprem = CASES[case]
+    planes = random_frame(fmt, w, h, 300 + case, opaque=opaque)
+    rects = make_rects(case)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), rects, dprem)
+    got = gpu_blend(ctx, fmt, w, h, planes, rects, mode=mode, dest_premul=dprem)
+    assert_planes_equal(got, want, f"{fmt} case {case} {mode}")
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+def test_golden_fixtures(ctx, fmt):
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        manifest = json.load(f)
+    hits = [v for v in manifest["vectors"] if v["format"] == fmt]
+    assert hits, fmt
+    for v in hits:
+        z = np.load(os.path.join(GOLDEN, v["file"]))
+        n = int(z["n_planes"])
+        planes = [z[f"in{i}"] for i in range(n)]
+        rects = [dict(pixels=z[f"rect{i}"], x=int(z["pos"][i][0]), y=int(z["pos"][i][1]),
+                      global_alpha=float(z["ga"][i]), premultiplied=bool(z["premul"][i]))
+                 for i in range(int(z["n_rects"]))]
+        for mode in MODES:
+            got = gpu_blend(ctx, fmt, int(z["width"]), int(z["height"]), planes, rects, mode=mode,
+                            dest_premul=bool(z["dest_premul"]))
+            assert_planes_equal(got, [z[f"out{i}"] for i in range(n)], f"{v['file']} {mode}")
+
+
+@pytest.mark.parametrize("fmt", ("I420", "NV12", "AYUV", "BGRA"))
+def test_alpha_sweep(ctx, fmt):
+    """Every alpha 0..255 against every frame value 0..255 for a few overlay colours."""
+    w, h = 256, 256
+    planes = random_frame(fmt, w, h, 1)
+    ramp = np.tile(np.arange(256, dtype=np.uint8), (256, 1))
+    planes[0][:, : planes[0].shape[1]] = np.resize(ramp, planes[0].shape)
+    for colour in ((255, 255, 255), (0, 0, 0), (17, 130, 241)):
+        ov = np.zeros((h, w, 4), dtype=np.uint8)
+        a = np.arange(256, dtype=np.uint32)[:, None] * np.ones((1, w), dtype=np.uint32)
+        ov[:, :, 3] = a
+        for k in range(3):
+            ov[:, :, k] = (colour[k] * a + 127) // 255
+        rects = [dict(pixels=ov, x=0, y=0)]
+        want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+        got = gpu_blend(ctx, fmt, w, h, planes, rects, mode="out")
+        assert_planes_equal(got, want, f"{fmt} sweep {colour}")
+
+
+@pytest.mark.parametrize("fmt", ("NV12", "I420", "RGBA"))
+def test_unaligned_strides_take_the_byte_path(ctx, fmt):
+    """Strides / pointers that are not multiples of 16 (GStreamer only guarantees 4)."""
+    w, h = 150, 70
+    tb = pkg.ttmlblend
+    rects = [dict(pixels=random_overlay(90, 40, 5), x=31, y=13)]
+    planes = random_frame(fmt, w, h, 6)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+    ctx.overlay_set_rectangles(3, rects)
+    big = ctx.acquire(fmt, w + 64, h)      # roomy pool frame, we carve unaligned views out of it
+    out = ctx.acquire(fmt, w + 64, h)
+    try:
+        src_f, dst_f = tb.Frame(), tb.Frame()
+        host = []
+        for i, (rows, rb) in enumerate(wl.plane_shapes(fmt, w, h)):
+            stride = rb + 4 - (rb % 4) + 4          # multiple of 4, not of 16 in general
+            host.append((rows, rb, stride))
+            for f, pool in ((src_f, big), (dst_f, out)):
+                f.plane[i] = pool.c.plane[i] + 4    # 4-byte aligned base
+                f.stride[i] = stride
+        # upload through an unaligned-view frame: build host planes with that stride
+        hp = []
+        for (rows, rb, stride), p in zip(host, planes):
+            buf = np.zeros((rows, stride), dtype=np.uint8)
+            buf[:, :rb] = p
+            hp.append(buf[:, :rb])
+        hsrc = tb._frame_from_arrays(hp)
+        ctx._check(ctx.lib.fluc_ttmlblend_frame_upload(ctx.h, tb.FORMATS[fmt], w, h, hsrc, src_f), "up")
+        ctx.wait(ctx.submit(3, fmt, w, h, src_f, dst_f))
+        got = [np.zeros((rows, rb), dtype=np.uint8) for rows, rb, _ in host]
+        hdst = tb._frame_from_arrays(got)
+        ctx._check(ctx.lib.fluc_ttmlblend_frame_download(ctx.h, tb.FORMATS[fmt], w, h, dst_f, hdst), "down")
+        assert_planes_equal(got, want, f"{fmt} unaligned out-of-place")
+        ctx.wait(ctx.submit(3, fmt, w, h, src_f, src_f))
+        ctx._check(ctx.lib.fluc_ttmlblend_frame_download(ctx.h, tb.FORMATS[fmt], w, h, src_f, hdst), "down")
+        assert_planes_equal(got, want, f"{fmt} unaligned in place")
+    finally:
+        big.release()
+        out.release()
+
+
+@pytest.mark.parametrize("fmt", ("I420", "NV12", "BGRA", "AYUV"))
+def test_ttmlrender_form_equals_whole_image(ctx, fmt):
+    """overlay_set(image, region boxes) == blending the whole frame-sized image as the
+    reference pipeline does, also when the region boxes overlap or leave the frame."""
+    w, h = 320, 180
+    regions = [wl.Region(10, 100, 300, 60, (0, 0, 0, 255), 0.7),
+               wl.Region(100, 20, 150, 100, (10, 20, 200, 128), 1.0, ((255, 255, 0, 255),)),
+               wl.Region(250, 150, 100, 50, (200, 0, 0, 255), 0.5)]
+    ov = wl.make_overlay(w, h, regions, 77, cell=(8, 16))
+    boxes = [(r.x, r.y, r.w, r.h) for r in regions]
+    planes = random_frame(fmt, w, h, 8)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), oracle.ttmlrender_rectangles(ov))
+    for mode in MODES:
+        got = gpu_blend(ctx, fmt, w, h, planes, overlay=ov, regions=boxes, mode=mode)
+        assert_planes_equal(got, want, f"{fmt} regions {mode}")
+        got = gpu_blend(ctx, fmt, w, h, planes, overlay=ov, regions=(), mode=mode)
+        assert_planes_equal(got, want, f"{fmt} whole image {mode}")
+
+
+def test_clear_and_missing_overlay_pass_frames_through(ctx):
+    w, h = 128, 64
+    planes = random_frame("NV12", w, h, 2)
+    ctx.overlay_clear(55)
+    for mode in MODES:
+        got = gpu_blend(ctx, "NV12", w, h, planes, mode=mode, stream=55, set_overlay=False)
+        assert_planes_equal(got, planes, f"no overlay {mode}")
+    ctx.overlay_set_rectangles(55, [dict(pixels=random_overlay(50, 20, 3), x=5, y=5)])
+    got = gpu_blend(ctx, "NV12", w, h, planes, mode="out", stream=55, set_overlay=False)
+    assert not np.array_equal(got[0], planes[0])
+    ctx.overlay_clear(55)
+    got = gpu_blend(ctx, "NV12", w, h, planes, mode="out", stream=55, set_overlay=False)
+    assert_planes_equal(got, planes, "after clear")
+
+
+def test_queued_frames_keep_the_overlay_they_were_submitted_with(ctx):
+    """overlay_set replaces atomically: a frame queued before the cue change is blended with
+    the old cue (the [PTS, PTS+duration) lifetime of gst_ttmlbase_gen_buffer buffers)."""
+    w, h, fmt = 128, 64, "I420"
+    ctx.set_batch(32, 0)
+    try:
+        planes = random_frame(fmt, w, h, 4)
+        r_old = [dict(pixels=random_overlay(60, 30, 10), x=4, y=4)]
+        r_new = [dict(pixels=random_overlay(60, 30, 11), x=40, y=20)]
+        src, d0, d1 = (ctx.acquire(fmt, w, h) for _ in range(3))
+        src.upload(planes)
+        ctx.overlay_set_rectangles(9, r_old)
+        t0 = ctx.submit(9, fmt, w, h, src.c, d0.c)
+        ctx.overlay_set_rectangles(9, r_new)
+        t1 = ctx.submit(9, fmt, w, h, src.c, d1.c)
+        ctx.wait(t1)
+        ctx.wait(t0)
+        assert_planes_equal(d0.download(), oracle_blend(fmt, w, h, copy_planes(planes), r_old), "old cue")
+        assert_planes_equal(d1.download(), oracle_blend(fmt, w, h, copy_planes(planes), r_new), "new cue")
+        for f in (src, d0, d1):
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_mixed_batch_many_streams_one_launch(ctx):
+    """Frames of different formats, sizes and streams in one batch."""
+    ctx.set_batch(64, 0)
+    try:
+        jobs = []
+        for i, (fmt, w, h) in enumerate([("NV12", 320, 180), ("I420", 200, 100), ("BGRA", 160, 90),
+                                         ("AYUV", 96, 54), ("NV12", 322, 182), ("RGBA", 64, 64),
+                                         ("YV12", 130, 70), ("NV21", 128, 72), ("ARGB", 50, 40)] * 3):
+            planes = random_frame(fmt, w, h, 50 + i)
+            rects = [dict(pixels=random_overlay(w // 2, h // 3, 60 + i), x=w // 5 + (i % 3), y=h // 2 - (i % 5))]
+            ctx.overlay_set_rectangles(100 + i, rects)
+            src, dst = ctx.acquire(fmt, w, h), ctx.acquire(fmt, w, h)
+            src.upload(planes)
+            jobs.append((fmt, w, h, planes, rects, src, dst))
+        before = ctx.stats()["launches"]
+        tickets = [ctx.submit(100 + i, fmt, w, h, src.c, dst.c)
+                   for i, (fmt, w, h, _, _, src, dst) in enumerate(jobs)]
+        ctx.wait(tickets[-1])
+        assert ctx.stats()["launches"] - before == 3        # one per plane kind
+        for fmt, w, h, planes, rects, src, dst in jobs:
+            assert_planes_equal(dst.download(), oracle_blend(fmt, w, h, copy_planes(planes), rects), fmt)
+            src.release()
+            dst.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_scheduler_thread_launches_partial_batches(ctx):
+    """Without flush/wait the linger timer of the scheduler thread launches the batch."""
+    import time
+    w, h, fmt = 128, 64, "NV12"
+    ctx.set_batch(32, 500)
+    planes = random_frame(fmt, w, h, 12)
+    rects = [dict(pixels=random_overlay(64, 32, 13), x=10, y=10)]
+    ctx.overlay_set_rectangles(21, rects)
+    src, dst = ctx.acquire(fmt, w, h), ctx.acquire(fmt, w, h)
+    src.upload(planes)
+    before = ctx.stats()["launches"]
+    ctx.submit(21, fmt, w, h, src.c, dst.c)
+    deadline = time.time() + 5.0
+    while ctx.stats()["launches"] == before and time.time() < deadline:
+        time.sleep(0.005)
+    assert ctx.stats()["launches"] == before + 1
+    ctx.sync()
+    assert_planes_equal(dst.download(), oracle_blend(fmt, w, h, copy_planes(planes), rects), "linger")
+    src.release()
+    dst.release()
+    ctx.set_batch(32, 200)
+
+
+def test_concurrent_submitters(ctx):
+    """Many video streaming threads submit at once (one stream each)."""
+    w, h, fmt, n_threads, n_frames = 160, 90, "I420", 8, 6
+    results, errors = {}, []
+
+    def worker(t):
+        try:
+            rects = [dict(pixels=random_overlay(100, 30, 500 + t), x=20 + t, y=40 - t)]
+            ctx.overlay_set_rectangles(300 + t, rects)
+            outs = []
+            for i in range(n_frames):
+                planes = random_frame(fmt, w, h, 1000 + 10 * t + i)
+                src, dst = ctx.acquire(fmt, w, h), ctx.acquire(fmt, w, h)
+                src.upload(planes)
+                tk = ctx.submit(300 + t, fmt, w, h, src.c, dst.c)
+                outs.append((planes, rects, src, dst, tk))
+            for planes, rects, src, dst, tk in outs:
+                ctx.wait(tk)
+                got = dst.download()
+                want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+                assert_planes_equal(got, want, f"thread {t}")
+                src.release()
+                dst.release()
+            results[t] = True
+        except Exception as e:      # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errors, errors
+    assert len(results) == n_threads
+
+
+def test_error_codes(ctx):
+    tb = pkg.ttmlblend
+    f = tb.Frame()
+    assert ctx.lib.fluc_ttmlblend_submit(ctx.h, 1, 99, 64, 64, 0, f, f, None) == tb.ERROR_UNSUPPORTED_FORMAT
+    assert ctx.lib.fluc_ttmlblend_submit(ctx.h, 1, 0, 64, 64, 0, f, f, None) == tb.ERROR_INVALID_ARGUMENT
+    assert ctx.lib.fluc_ttmlblend_wait(ctx.h, 1 << 60) == tb.ERROR_NOT_FOUND
+    assert ctx.lib.fluc_ttmlblend_overlay_set(ctx.h, 1, None, 10, 10, 40, None, 0) == tb.ERROR_INVALID_ARGUMENT
+    assert ctx.lib.fluc_ttmlblend_frame_pool_release(ctx.h, f) == tb.ERROR_NOT_FOUND
+    # the context is still usable afterwards (errors are not sticky unless CUDA failed)
+    ctx.sync()
+
+
+def test_stats_count_algorithmic_bytes(ctx):
+    cfg = wl.CONFIGS[1]
+    ov = wl.overlay_for(cfg)
+    ctx.overlay_set(70, ov, wl.region_rects(cfg))
+    src, dst = ctx.acquire(cfg.fmt, cfg.width, cfg.height), ctx.acquire(cfg.fmt, cfg.width, cfg.height)
+    src.upload(wl.frame_for(cfg, 0))
+    ctx.sync()
+    ctx.stats_reset()
+    ctx.wait(ctx.submit(70, cfg.fmt, cfg.width, cfg.height, src.c, dst.c))
+    st = ctx.stats()
+    assert st["frames_blended"] == 1 and st["launches"] == 1
+    assert st["algorithmic_bytes"] == wl.algorithmic_bytes(cfg) == 3207168
+    src.release()
+    dst.release()

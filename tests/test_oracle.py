@@ -1,0 +1,212 @@
+"""CPU tests of the oracle (oracle/ttmlblend_ref.c): known answers from the published
+BT.709 8-bit matrix and OVER formulas, agreement with an independent numpy model of the
+net per-plane semantics, and the frozen golden fixtures. PARITY UNPINNED: the reference
+holds no vector for this path, so the fixtures are oracle-generated
+and only the known-answer tests come from outside the oracle."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (ALL_FORMATS, PACKED, PACKED_ORDER, PLANAR_420, copy_planes, model_blend,
+                     oracle_blend, random_frame, random_overlay, wl)
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_div255_magic_is_exact():
+    """(x * 32897) >> 23 == x / 255 on every numerator the kernels can form (<= 255*255)."""
+    x = np.arange(0, 66299, dtype=np.uint64)
+    assert np.array_equal((x * 32897) >> 23, x // 255)
+    assert ((66299 * 32897) >> 23) != 66299 // 255      # and the bound is tight
+
+
+def test_magic_row_division_is_exact():
+    """umulhi(item, ceil(2^32/nv)) == item / nv for every window the host accepts."""
+    for nv in (1, 2, 3, 5, 7, 80, 120, 240, 241, 480, 960, 1023, 2048):
+        if nv == 1:
+            continue
+        magic = ((1 << 32) + nv - 1) // nv
+        e = magic * nv - (1 << 32)
+        max_items = ((1 << 32) - 1) // e if e else 1 << 31
+        max_items = min(max_items, 1 << 31)
+        probe = np.unique(np.concatenate([
+            np.arange(0, min(max_items, 200000)),
+            np.arange(max(0, max_items - 200000), max_items),
+            (np.arange(1, 4000) * nv) - 1, np.arange(1, 4000) * nv])).astype(np.uint64)
+        probe = probe[probe < max_items]
+        assert np.array_equal((probe * np.uint64(magic)) >> np.uint64(32), probe // np.uint64(nv)), nv
+
+
+@pytest.mark.parametrize("rgb,yuv", [
+    ((255, 255, 255), (235, 127, 128)),     # white  -> Y 235; U row sums to -1 => 127
+    ((0, 0, 0), (16, 128, 128)),            # black  -> Y 16
+    ((255, 0, 0), (62, 102, 239)),          # red    (BT.709: 63 / 102 / 240 before truncation)
+    ((0, 255, 0), (172, 41, 26)),           # green
+    ((0, 0, 255), (31, 239, 118)),          # blue
+])
+def test_matrix_known_answers(oracle_lib, rgb, yuv):
+    line = np.array([255, *rgb], dtype=np.uint8)
+    oracle_lib.tbref_matrix_rgb_to_yuv(line.ctypes.data, 1)
+    assert tuple(line[1:]) == yuv
+    # premultiplied at alpha 128: un-premultiply must give the same colour back
+    a = 128
+    pre = np.array([a, *[(c * a + 127) // 255 for c in rgb]], dtype=np.uint8)
+    oracle_lib.tbref_matrix_prea_rgb_to_yuv(pre.ctypes.data, 1)
+    assert pre[0] == a and tuple(pre[1:]) == yuv
+
+
+def test_matrix_yuv_to_rgb_known_answers(oracle_lib):
+    for yuv, rgb in (((235, 128, 128), (254, 254, 255)), ((16, 128, 128), (0, 0, 0))):
+        line = np.array([255, *yuv], dtype=np.uint8)
+        oracle_lib.tbref_matrix_yuv_to_rgb(line.ctypes.data, 1)
+        assert tuple(line[1:]) == rgb
+
+
+def _one_px_overlay(b, g, r, a):
+    return np.array([[[b, g, r, a]]], dtype=np.uint8)
+
+
+def test_opaque_white_pixel_on_i420():
+    """a=255 white at an even/even position replaces Y and the sited chroma sample."""
+    planes = [np.full((4, 4), 50, np.uint8), np.full((2, 2), 60, np.uint8), np.full((2, 2), 70, np.uint8)]
+    oracle_blend("I420", 4, 4, planes, [dict(pixels=_one_px_overlay(255, 255, 255, 255), x=2, y=2)])
+    assert planes[0][2, 2] == 235 and (planes[0] == 50).sum() == 15
+    assert planes[1][1, 1] == 127 and planes[2][1, 1] == 128
+    assert (planes[1] == 60).sum() == 3 and (planes[2] == 70).sum() == 3
+
+
+def test_chroma_is_point_sampled_not_averaged():
+    """A pixel at odd x or odd y changes luma only: pack_I420/NV12 write chroma on even lines
+    from the even pixel of each pair (SURVEY.md finding 4)."""
+    for (x, y) in ((1, 0), (0, 1), (3, 3)):
+        for fmt in ("I420", "NV12"):
+            planes = random_frame(fmt, 6, 6, 3)
+            before = copy_planes(planes)
+            oracle_blend(fmt, 6, 6, planes, [dict(pixels=_one_px_overlay(10, 200, 30, 255), x=x, y=y)])
+            for p, q in zip(planes[1:], before[1:]):
+                assert np.array_equal(p, q)
+            assert (planes[0] != before[0]).sum() <= 1
+
+
+def test_half_alpha_known_answer_bgra():
+    """Premultiplied source on an opaque BGRA frame: out = Cs + Cd*(255-a)/255, alpha 255."""
+    frame = np.array([[10, 20, 30, 255]], dtype=np.uint8)          # B,G,R,A
+    ov = _one_px_overlay(64, 32, 100, 128)
+    oracle_blend("BGRA", 1, 1, [frame], [dict(pixels=ov, x=0, y=0)])
+    assert list(frame[0]) == [64 + 10 * 127 // 255, 32 + 20 * 127 // 255, 100 + 30 * 127 // 255, 255]
+
+
+def test_straight_alpha_known_answer_ayuv():
+    frame = np.array([[255, 100, 110, 120]], dtype=np.uint8)       # A,Y,U,V
+    ov = _one_px_overlay(255, 255, 255, 128)                        # straight white, a=128
+    oracle_blend("AYUV", 1, 1, [frame], [dict(pixels=ov, x=0, y=0, premultiplied=False)])
+    want = [255] + [(s * 128 + d * 127) // 255 for s, d in ((235, 100), (127, 110), (128, 120))]
+    assert list(frame[0]) == want
+
+
+def test_transparent_and_outside_are_no_ops():
+    for fmt in ALL_FORMATS:
+        planes = random_frame(fmt, 33, 17, 5)
+        before = copy_planes(planes)
+        ov = random_overlay(8, 8, 1)
+        ov[:, :, 3] = 0
+        oracle_blend(fmt, 33, 17, planes, [dict(pixels=ov, x=3, y=3),
+                                          dict(pixels=random_overlay(8, 8, 2), x=33, y=0),
+                                          dict(pixels=random_overlay(8, 8, 2), x=-8, y=5),
+                                          dict(pixels=random_overlay(8, 8, 2), x=0, y=17),
+                                          dict(pixels=random_overlay(8, 8, 2), x=2, y=-8)])
+        for p, q in zip(planes, before):
+            assert np.array_equal(p, q), fmt
+
+
+CASES = [
+    # w, h, [(rw, rh, x, y, global_alpha, premultiplied)], opaque dest, premultiplied dest
+    (64, 48, [(32, 16, 8, 8, 1.0, True)], True, False),
+    (63, 47, [(31, 15, 7, 9, 1.0, True)], True, False),                 # odd everything
+    (64, 48, [(40, 30, -10, -7, 1.0, True)], True, False),              # clipped left/top
+    (64, 48, [(40, 30, 40, 30, 1.0, True)], True, False),               # clipped right/bottom
+    (33, 21, [(80, 60, -20, -20, 1.0, True)], True, False),             # covers the whole frame
+    (64, 48, [(1, 1, 5, 5, 1.0, True), (1, 1, 6, 6, 1.0, True)], True, False),
+    (64, 48, [(32, 16, 8, 8, 1.0, True), (32, 16, 20, 12, 1.0, True)], True, False),   # overlap
+    (64, 48, [(32, 16, 8, 8, 0.5, True), (20, 20, 30, 20, 0.8, False)], True, False),  # global alpha
+    (64, 48, [(32, 16, 8, 8, 1.0, False)], True, False),                # straight source
+    (64, 48, [(32, 16, 9, 7, 1.0, True)], False, False),                # non-opaque dest alpha
+    (64, 48, [(32, 16, 9, 7, 0.7, True), (16, 16, 12, 10, 1.0, False)], False, True),  # premult dest
+]
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS)
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_oracle_matches_numpy_model(fmt, case):
+    w, h, rects, opaque, dprem = CASES[case]
+    planes = random_frame(fmt, w, h, 100 + case, opaque=opaque)
+    rectangles = [dict(pixels=random_overlay(rw, rh, 200 + 10 * case + i, premultiplied=pm),
+                       x=x, y=y, global_alpha=ga, premultiplied=pm)
+                  for i, (rw, rh, x, y, ga, pm) in enumerate(rects)]
+    a = oracle_blend(fmt, w, h, copy_planes(planes), rectangles, dprem)
+    b = model_blend(fmt, w, h, copy_planes(planes), rectangles, dprem)
+    for i, (p, q) in enumerate(zip(a, b)):
+        assert np.array_equal(p, q), (fmt, case, i, int((p != q).sum()))
+
+
+def test_invalid_premultiplied_input_is_still_defined(oracle_lib):
+    """colour > alpha never comes out of Cairo; the oracle (and the model) still agree on it."""
+    ov = np.random.default_rng(9).integers(0, 256, size=(16, 16, 4), dtype=np.uint8)
+    for fmt in ("NV12", "AYUV", "BGRA"):
+        planes = random_frame(fmt, 32, 32, 4)
+        rect = [dict(pixels=ov, x=4, y=4)]
+        a = oracle_blend(fmt, 32, 32, copy_planes(planes), rect)
+        b = model_blend(fmt, 32, 32, copy_planes(planes), rect)
+        for p, q in zip(a, b):
+            assert np.array_equal(p, q), fmt
+
+
+def _sha(planes):
+    h = hashlib.sha256()
+    for p in planes:
+        h.update(np.ascontiguousarray(p).tobytes())
+    return h.hexdigest()
+
+
+def test_golden_fixtures_match_oracle():
+    """tests/golden/*.npz were written by tests/golden/gen_golden.py from this oracle and are
+    frozen by hash in manifest.json (self-referential: see the module docstring)."""
+    with open(os.path.join(GOLDEN, "manifest.json")) as f:
+        manifest = json.load(f)
+    assert manifest["parity"] == "unpinned"
+    assert len(manifest["vectors"]) >= 9
+    for v in manifest["vectors"]:
+        z = np.load(os.path.join(GOLDEN, v["file"]))
+        n = int(z["n_planes"])
+        planes = [z[f"in{i}"].copy() for i in range(n)]
+        rects = [dict(pixels=z[f"rect{i}"], x=int(z["pos"][i][0]), y=int(z["pos"][i][1]),
+                      global_alpha=float(z["ga"][i]), premultiplied=bool(z["premul"][i]))
+                 for i in range(int(z["n_rects"]))]
+        out = oracle_blend(v["format"], int(z["width"]), int(z["height"]), planes, rects,
+                           bool(z["dest_premul"]))
+        want = [z[f"out{i}"] for i in range(n)]
+        for p, q in zip(out, want):
+            assert np.array_equal(p, q), v["file"]
+        assert _sha(want) == v["sha256"], v["file"]
+
+
+def test_baseline_byte_formula():
+    """B per frame of BASELINE.md section 2."""
+    assert wl.algorithmic_bytes(wl.CONFIGS[1]) == 3207168
+    assert wl.algorithmic_bytes(wl.CONFIGS[2]) == 8315136
+    assert wl.algorithmic_bytes(wl.CONFIGS[3]) == 32624640
+    assert wl.algorithmic_bytes(wl.CONFIGS[4]) == 74096640
+    assert wl.algorithmic_bytes(wl.CONFIGS[5]) == 7216128
+
+
+def test_workloads_are_deterministic_and_valid_premultiplied():
+    cfg = wl.CONFIGS[1]
+    a, b = wl.overlay_for(cfg), wl.overlay_for(cfg)
+    assert np.array_equal(a, b)
+    assert (a[:, :, :3].max(axis=2) <= a[:, :, 3]).all()
+    assert a[:576].max() == 0 and a[576:684, 128:1152, 3].max() == 255
+    assert wl.splitmix64(0, 1)[0] == np.uint64(0xE220A8397B1DCDAF)   # published first output for seed 0
