@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: frames/s and % of the HBM roofline for the 4K NV12
+TTML overlay blend (config 3: 3840x2160 NV12, two full-width cue regions, 32 frames per
+launch), with the reference's CPU blend timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 3]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one launch of the blend over one batch (32 device-resident 4K frames,
+src -> dst, whole frame read and written; 398 MB in + 398 MB out per step, i.e. inputs
+larger than the 126 MB L2). Per-GPU work is fixed as N grows (weak scaling, each rank its
+own frame batches, no collective on the data path); torch.distributed is only used for the
+barrier, the MAX over ranks of the device time and a gather of the result records.
+
+Numbers in the JSON line:
+  value        frames/s, frames resident in HBM, CUDA-event time on the blend stream.
+  e2e          frames/s through fluc_ttmlblend_blend_host (the drop-in for
+               gst_video_overlay_composition_blend): pinned HOST frames, the rows the
+               overlay touches go host->device, blend, device->host inside the timed region.
+  roofline     algorithmic bytes per launch (frame read + frame write +
+               4 B/px overlay) / mean per-launch CUDA-event time, against MEASURED_PEAKS.json.
+  cpu_baseline the CPU oracle (a port of gst_video_blend: GStreamer is not installable here)
+               on this box's host cores, bounded sample, rank 0 at N=1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "frames/sec, 4K NV12 TTML overlay blend"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:   # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float):
+        rows = [s for t, s in self.samples if t0 <= t <= t1]
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    device = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            device = torch.device("cuda", local)
+            dist_mod.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        else:
+            dist_mod.init_process_group("gloo", rank=rank, world_size=world)
+        dist = dist_mod
+    return dist, device, world, rank, local
+
+
+def barrier(dist, device):
+    if dist is not None:
+        if device is not None:
+            import torch
+            torch.cuda.synchronize(device)
+        dist.barrier()
+
+
+# ---------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+
+def cpu_reference_setup(cfg, wl, n_frames):
+    from oracle import oracle
+    lib = oracle.load(native=True, out_dir=tempfile.mkdtemp(prefix="ttmlblend_oracle_"))
+    ov = wl.overlay_for(cfg)
+    base = wl.frame_for(cfg, 0)
+    frames, keep = [], []
+    import ctypes as C
+    arr = (oracle.RefFrame * n_frames)()
+    for i in range(n_frames):
+        planes = [np.roll(p, i * 17, axis=1).copy() for p in base]
+        keep.append(planes)
+        arr[i] = oracle.make_frame(cfg.fmt, cfg.width, cfg.height, planes)
+    rects = oracle.make_rectangles(oracle.ttmlrender_rectangles(ov))
+    return lib, arr, rects, keep, ov, C
+
+
+def cpu_blend_fps(lib, arr, rects, n_frames, threads):
+    secs = lib.tbref_blend_many(arr, n_frames, rects, 1, threads)
+    return n_frames / secs, secs
+
+
+def run_cpu_baseline(cfg, wl, target_s=12.0):
+    cores = os.cpu_count() or 1
+    probe_n = cores
+    lib, arr, rects, keep, ov, C = cpu_reference_setup(cfg, wl, probe_n)
+    fps, secs = cpu_blend_fps(lib, arr, rects, probe_n, cores)       # probe (also warms caches)
+    rounds = max(1, int(target_s / max(secs, 1e-3)))
+    t = 0.0
+    for _ in range(rounds):
+        _, s = cpu_blend_fps(lib, arr, rects, probe_n, cores)
+        t += s
+    n = rounds * probe_n
+    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} frames of {cfg.width}x{cfg.height} {cfg.fmt} ({probe_n} buffers re-blended "
+                      f"{rounds}x), ttmlrender's frame-sized premultiplied BGRA image as one "
+                      f"rectangle (what the reference pipeline blends), oracle/ttmlblend_ref.c "
+                      f"-O3 -march=native, {cores} pthreads, {t:.1f} s"}
+
+
+def run_reference_arm(args, cfg, wl, dist, device, world, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; GStreamer
+    cannot be installed here) on all host threads. Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = cores                       # one frame per thread per step: a bounded sample
+    lib, arr, rects, keep, ov, C = cpu_reference_setup(cfg, wl, per_step)
+    for _ in range(args.warmup):
+        cpu_blend_fps(lib, arr, rects, per_step, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_blend_fps(lib, arr, rects, per_step, cores)[1]
+    fps = per_step * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": cfg.name, "format": cfg.fmt, "width": cfg.width, "height": cfg.height,
+                   "frames_per_step": per_step,
+                   "note": "CPU port of gst_video_overlay_composition_blend (oracle/ttmlblend_ref.c); "
+                           "GStreamer itself is not installed in this image"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} frames per step, frame-sized overlay rectangle"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--inplace", action="store_true", help="also time the in-place variant")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    pkg = graft.load_package()
+    wl = pkg.workloads
+    sh = pkg.sharding
+    cfg = wl.CONFIGS[args.config]
+    dist, device, world, rank, local = dist_setup(args.gpus)
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, wl, dist, device, world, rank)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ctx = pkg.TtmlBlend(local)             # raises without a GPU: there is no CPU fallback
+    fmt, W, H, batch = cfg.fmt, cfg.width, cfg.height, cfg.batch
+    B = wl.algorithmic_bytes(cfg)
+    ov = wl.overlay_for(cfg)
+    stream_id = 1
+    ctx.overlay_set(stream_id, ov, wl.region_rects(cfg))
+    ctx.set_batch(batch, 0)                # one launch per `batch` frames, no linger timer
+
+    base = wl.frame_for(cfg, rank)
+    srcs = [ctx.acquire(fmt, W, H) for _ in range(batch)]
+    dsts = [ctx.acquire(fmt, W, H) for _ in range(batch)]
+    for i, s in enumerate(srcs):
+        s.upload([np.roll(p, i * 17, axis=1) for p in base])
+
+    def step():
+        for s, d in zip(srcs, dsts):
+            ctx.submit(stream_id, fmt, W, H, s.c, d.c)   # the 32nd submit launches the batch
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    ctx.stats_reset()
+    ctx.set_profiling(True)
+
+    barrier(dist, device)
+    t_wall0 = time.time()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_end()
+    ctx.sync()
+    t_wall1 = time.time()
+    barrier(dist, device)
+    st = ctx.stats()
+    ctx.set_profiling(False)
+
+    # clocks: if the timed region was too short for nvidia-smi to sample, keep the same
+    # workload running (untimed) until there are samples
+    clocks = sampler.summary(t_wall0, t_wall1)
+    clocks["window"] = "timed region"
+    if clocks["samples"] < 3:
+        t0 = time.time()
+        while time.time() - t0 < 1.5:
+            for _ in range(50):
+                step()
+            ctx.sync()
+        clocks = sampler.summary(t0, time.time())
+        clocks["window"] = "same workload re-run for 1.5 s right after the timed region"
+
+    worst_ms = sh.reduce_max(ms, dist, device)
+    records = sh.gather_records((batch * args.steps, ms, st["kernel_ms"], st["kernel_ms_launches"]),
+                                dist, device)
+    value = sh.aggregate_fps(records)
+
+    # roofline of the dominant (only) kernel, this rank
+    peak, peak_src = load_peaks()
+    launch_ms = st["kernel_ms"] / max(1, st["kernel_ms_launches"])
+    achieved = (B * batch) / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "ttmlblend_blend_kernel<PLANE8>", "launch_ms": launch_ms,
+                "algorithmic_bytes_per_launch": B * batch, "peak_source": peak_src,
+                "frac_of_8000_nominal": achieved / 8000.0}
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:   # noqa: BLE001
+            pass
+
+    inplace = None
+    if args.inplace:
+        ctx.stats_reset()
+        ctx.timer_begin()
+        for _ in range(args.steps):
+            for s in srcs:
+                ctx.submit(stream_id, fmt, W, H, s.c, s.c)
+        ms_ip = ctx.timer_end()
+        st_ip = ctx.stats()
+        inplace = {"value": batch * args.steps / (ms_ip * 1e-3), "unit": UNIT,
+                   "algorithmic_gbs": st_ip["algorithmic_bytes"] / (ms_ip * 1e-3) / 1e9}
+
+    # e2e: pinned host frames through the drop-in call, PCIe copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        for f in dsts:
+            f.release()
+        hosts = [ctx.acquire(fmt, W, H, on_host=True) for _ in range(batch)]
+        for i, hf in enumerate(hosts):
+            for dstp, srcp in zip(hf.host_planes(), base):
+                dstp[...] = np.roll(srcp, i * 17, axis=1)
+        e2e_steps = max(3, min(args.steps, 100))
+
+        def e2e_step():
+            tickets = [ctx.blend_host_frame(stream_id, fmt, W, H, hf.c) for hf in hosts]
+            for t in tickets:
+                ctx.wait(t)
+
+        for _ in range(3):
+            e2e_step()
+        ctx.sync()
+        ctx.stats_reset()
+        barrier(dist, device)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        ctx.sync()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        barrier(dist, device)
+        st2 = ctx.stats()
+        rec2 = sh.gather_records((batch * e2e_steps, e2e_ms), dist, device)
+        e2e = {"value": sh.aggregate_fps(rec2), "unit": UNIT,
+               "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps,
+               "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
+               "steps": e2e_steps, "launches": st2["launches"],
+               "api": "fluc_ttmlblend_blend_host (pinned host frames, in place, rows under the cue regions only)"}
+    sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu_baseline(cfg, wl)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": worst_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": cfg.name, "format": fmt, "width": W, "height": H,
+                       "frames_per_launch": batch, "regions": wl.region_rects(cfg),
+                       "mode": "out-of-place (whole frame read + written)",
+                       "bytes_per_frame": B,
+                       "l2": "inputs larger than L2 (398 MB read + 398 MB written per step)",
+                       "parallelism": f"{world} x independent frame batches, no collective"},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": int(st["launches"]),
+            "per_rank": [{"frames": r[0], "ms": r[1], "kernel_ms": r[2]} for r in records],
+        }
+        if inplace:
+            line["inplace"] = inplace
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

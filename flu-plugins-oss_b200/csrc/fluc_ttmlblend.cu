@@ -154,7 +154,8 @@ struct TableSlot {
   PlaneJob *h_jobs = nullptr, *d_jobs = nullptr;
   uint32_t *h_begin = nullptr, *d_begin = nullptr;
   size_t cap = 0;
-  cudaEvent_t copied = nullptr;
+  cudaEvent_t copied = nullptr;        /* last kernel that read the slot has finished */
+  cudaEvent_t uploaded = nullptr;      /* table copy has landed */
 };
 
 struct PoolEntry {
@@ -171,7 +172,7 @@ struct Lane {
   bool busy = false;
   uint8_t *dev = nullptr;
   size_t dev_bytes = 0;
-  TableSlot table;
+  TableSlot table[2];
   std::shared_ptr<Overlay> keep;
 };
 
@@ -185,7 +186,7 @@ struct Ctx {
   int sticky = 0;
   std::string cuda_error;
 
-  cudaStream_t blend_stream = nullptr, up_stream = nullptr, reaper = nullptr;
+  cudaStream_t blend_stream = nullptr, up_stream = nullptr, reaper = nullptr, table_stream = nullptr;
   cudaEvent_t ev_fence[kLanes + 2] = {};
   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 
@@ -487,12 +488,6 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
 /* ---------------------------------------------------------------------- */
 /* plane jobs                                                             */
 
-bool
-spans_intersect (const RectRef &a, const RectRef &b)
-{
-  return a.v0 < b.v1 && b.v0 < a.v1 && a.y0 < b.y1 && b.y0 < a.y1;
-}
-
 void
 push_window (std::vector<PlaneJob> &jobs, PlaneJob base, int v0, int v1, int y0, int y1)
 {
@@ -518,7 +513,33 @@ push_window (std::vector<PlaneJob> &jobs, PlaneJob base, int v0, int v1, int y0,
   }
 }
 
-/* Builds the plane jobs of one frame. Returns algorithmic bytes moved. */
+/* A window goes to the fast kernel where whole 16-byte vectors can be moved
+ * (aligned frame, vector inside row_bytes); a ragged last vector column and
+ * unaligned frames go to the byte-granular variant. */
+void
+push_split (std::vector<PlaneJob> &jobs, PlaneJob b, bool aligned, int v0, int v1, int y0, int y1)
+{
+  const int nv_full = b.row_bytes / 16;
+  if (!aligned) {
+    b.flags &= ~(JF_VECTOR | JF_FAST);
+    push_window (jobs, b, v0, v1, y0, y1);
+    return;
+  }
+  PlaneJob f = b;
+  f.flags |= JF_VECTOR | JF_FAST;
+  push_window (jobs, f, v0, std::min (v1, nv_full), y0, y1);
+  if (v1 > nv_full) {
+    PlaneJob t = b;
+    t.flags = (t.flags | JF_VECTOR) & ~JF_FAST;
+    push_window (jobs, t, std::max (v0, nv_full), v1, y0, y1);
+  }
+}
+
+/* Builds the jobs of one frame: every plane is cut into bands of rows at the
+ * top and bottom edges of the prepared rectangles, so that each band sees a
+ * fixed set of rectangles and its class (copy / one rectangle / general) is
+ * decided here, once, instead of per vector on the GPU. Returns the
+ * algorithmic bytes moved. */
 uint64_t
 build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
     const FlucTtmlBlendFrame *dst, const Prepared *prep, std::vector<PlaneJob> &jobs)
@@ -526,6 +547,7 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
   const int n_planes = format_planes (format);
   const bool inplace = src->plane[0] == dst->plane[0];
   uint64_t bytes = 0;
+  std::vector<int> ys;
   for (int pl = 0; pl < n_planes; pl++) {
     PlaneJob b = {};
     b.src = static_cast<const uint8_t *> (src->plane[pl]);
@@ -537,44 +559,54 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
     const int rows = plane_rows (format, pl, H);
     const bool aligned = (((uintptr_t) b.src | (uintptr_t) b.dst | (uintptr_t) b.src_pitch |
             (uintptr_t) b.dst_pitch) & 15u) == 0;
-    b.flags = (aligned ? JF_VECTOR : 0) | (inplace ? JF_INPLACE : 0) |
+    b.flags = (inplace ? JF_INPLACE : 0) |
         ((frame_flags & FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA) ? JF_DST_PREMUL : 0);
-    const std::vector<RectRef> *rects = prep ? &prep->h_rects[pl] : nullptr;
+    static const std::vector<RectRef> none;
+    const std::vector<RectRef> &rects = prep ? prep->h_rects[pl] : none;
     b.rects = prep ? prep->d_rects[pl] : nullptr;
-    b.n_rects = rects ? (int32_t) rects->size () : 0;
     const int nv_row = ceil_div (b.row_bytes, 16);
-    if (!inplace) {
-      push_window (jobs, b, 0, nv_row, 0, rows);
-      bytes += 2ull * (uint64_t) b.row_bytes * (uint64_t) rows;
-      continue;
+
+    ys.clear ();
+    ys.push_back (0);
+    ys.push_back (rows);
+    for (const RectRef &r : rects) {
+      ys.push_back (std::max (0, std::min (rows, r.y0)));
+      ys.push_back (std::max (0, std::min (rows, r.y1)));
     }
-    if (b.n_rects == 0)
-      continue;
-    bool disjoint = true;
-    for (size_t i = 0; i < rects->size () && disjoint; i++)
-      for (size_t k = i + 1; k < rects->size (); k++)
-        if (spans_intersect ((*rects)[i], (*rects)[k])) {
-          disjoint = false;
-          break;
+    std::sort (ys.begin (), ys.end ());
+    ys.erase (std::unique (ys.begin (), ys.end ()), ys.end ());
+
+    for (size_t bi = 0; bi + 1 < ys.size (); bi++) {
+      const int ya = ys[bi], yb = ys[bi + 1];
+      unsigned long long mask = 0;
+      int count = 0, one = -1, minv = 1 << 30, maxv = 0;
+      for (size_t i = 0; i < rects.size (); i++) {
+        const RectRef &r = rects[i];
+        if (r.y0 <= ya && r.y1 >= yb && r.v0 < nv_row && r.v1 > 0) {
+          mask |= 1ull << i;
+          count++;
+          one = (int) i;
+          minv = std::min (minv, std::max (r.v0, 0));
+          maxv = std::max (maxv, std::min (r.v1, nv_row));
         }
-    if (disjoint) {
-      for (const RectRef &r : *rects) {
-        const int v1 = std::min (r.v1, nv_row), y1 = std::min (r.y1, rows);
-        push_window (jobs, b, r.v0, v1, r.y0, y1);
-        if (v1 > r.v0 && y1 > r.y0)
-          bytes += 2ull * (uint64_t) std::min ((v1 - r.v0) * 16, b.row_bytes - r.v0 * 16) * (uint64_t) (y1 - r.y0);
       }
-    } else {
-      int v0 = 1 << 30, v1 = 0, y0 = 1 << 30, y1 = 0;
-      for (const RectRef &r : *rects) {
-        v0 = std::min (v0, r.v0); v1 = std::max (v1, r.v1);
-        y0 = std::min (y0, r.y0); y1 = std::max (y1, r.y1);
+      PlaneJob j = b;
+      j.rect_mask = mask;
+      j.one_rect = one < 0 ? 0 : one;
+      int v0 = 0, v1 = nv_row;
+      if (count == 0) {
+        if (inplace)
+          continue;
+        j.cls = JC_COPY;
+      } else if (!inplace) {
+        j.cls = (count == 1 && rects[one].v0 <= 0 && rects[one].v1 >= nv_row) ? JC_ONE : JC_GENERAL;
+      } else {
+        j.cls = count == 1 ? JC_ONE : JC_GENERAL;
+        v0 = minv;
+        v1 = maxv;
       }
-      v1 = std::min (v1, nv_row);
-      y1 = std::min (y1, rows);
-      push_window (jobs, b, v0, v1, y0, y1);
-      if (v1 > v0 && y1 > y0)
-        bytes += 2ull * (uint64_t) std::min ((v1 - v0) * 16, b.row_bytes - v0 * 16) * (uint64_t) (y1 - y0);
+      push_split (jobs, j, aligned, v0, v1, ya, yb);
+      bytes += 2ull * (uint64_t) std::min ((v1 - v0) * 16, b.row_bytes - v0 * 16) * (uint64_t) (yb - ya);
     }
   }
   if (prep)
@@ -599,14 +631,16 @@ slot_reserve (Ctx *c, TableSlot &s, size_t n)
   CU (c, cudaMalloc ((void **) &s.d_begin, cap * sizeof (uint32_t)));
   if (!s.copied)
     CU (c, cudaEventCreateWithFlags (&s.copied, cudaEventDisableTiming));
+  if (!s.uploaded)
+    CU (c, cudaEventCreateWithFlags (&s.uploaded, cudaEventDisableTiming));
   s.cap = cap;
   return 0;
 }
 
 /* Copies `jobs` (one PlaneKind) into a table slot and launches the kernel. */
 int
-launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, cudaStream_t stream,
-    cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr)
+launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast,
+    cudaStream_t stream, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr)
 {
   if (n == 0)
     return 0;
@@ -621,14 +655,18 @@ launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, cud
     s.h_begin[i] = total;
     total += jobs[i].n_chunks;
   }
-  CU (c, cudaMemcpyAsync (s.d_jobs, s.h_jobs, n * sizeof (PlaneJob), cudaMemcpyHostToDevice, stream));
-  CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, n * sizeof (uint32_t), cudaMemcpyHostToDevice, stream));
-  CU (c, cudaEventRecord (s.copied, stream));
+  /* the table goes up on the copy stream, so that it overlaps the kernel still
+   * running on `stream`; the slot is free (its last kernel waited on above) */
+  CU (c, cudaMemcpyAsync (s.d_jobs, s.h_jobs, n * sizeof (PlaneJob), cudaMemcpyHostToDevice, c->table_stream));
+  CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, n * sizeof (uint32_t), cudaMemcpyHostToDevice, c->table_stream));
+  CU (c, cudaEventRecord (s.uploaded, c->table_stream));
+  CU (c, cudaStreamWaitEvent (stream, s.uploaded, 0));
   if (t0)
     CU (c, cudaEventRecord (t0, stream));
-  CU (c, launch_blend (s.d_jobs, s.d_begin, (int) n, total, kind, stream));
+  CU (c, launch_blend (s.d_jobs, s.d_begin, (int) n, total, kind, fast, stream));
   if (t1)
     CU (c, cudaEventRecord (t1, stream));
+  CU (c, cudaEventRecord (s.copied, stream));    /* slot busy until this kernel is done */
   c->stats.launches++;
   return 0;
 }
@@ -664,11 +702,11 @@ launch_pending (Ctx *c)
   reap_batches (c);
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
-  std::vector<PlaneJob> by_kind[3];
+  std::vector<PlaneJob> by_kind[6];     /* PlaneKind x {byte-granular, fast} */
   std::vector<Prepared *> waited;
   for (PendingFrame &f : c->pending) {
     for (const PlaneJob &j : f.jobs)
-      by_kind[f.kind].push_back (j);
+      by_kind[f.kind * 2 + ((j.flags & JF_FAST) ? 1 : 0)].push_back (j);
     if (f.overlay)
       b.keep.push_back (f.overlay);
     if (f.prep && std::find (waited.begin (), waited.end (), f.prep) == waited.end ()) {
@@ -680,18 +718,19 @@ launch_pending (Ctx *c)
   }
   c->pending.clear ();
   int n_kinds = 0;
-  for (int k = 0; k < 3; k++)
+  for (int k = 0; k < 6; k++)
     n_kinds += !by_kind[k].empty ();
   if (c->profiling && n_kinds == 1) {
     CU (c, cudaEventCreate (&b.t0));
     CU (c, cudaEventCreate (&b.t1));
   }
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < 6; k++) {
     if (by_kind[k].empty ())
       continue;
     TableSlot &s = c->slots[c->next_slot];
     c->next_slot = (c->next_slot + 1) % kTableSlots;
-    int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k, c->blend_stream, b.t0, b.t1);
+    int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0,
+        c->blend_stream, b.t0, b.t1);
     if (rc)
       return rc;
   }
@@ -911,6 +950,7 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   ok &= cudaStreamCreateWithFlags (&c->blend_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->up_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->reaper, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags (&c->table_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < kLanes + 2 && ok; i++)
     ok &= cudaEventCreateWithFlags (&c->ev_fence[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < kLanes && ok; i++) {
@@ -979,11 +1019,13 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
       if (s.d_jobs) cudaFree (s.d_jobs);
       if (s.d_begin) cudaFree (s.d_begin);
       if (s.copied) cudaEventDestroy (s.copied);
+      if (s.uploaded) cudaEventDestroy (s.uploaded);
     };
     for (auto &s : c->slots)
       free_slot (s);
     for (int i = 0; i < kLanes; i++) {
-      free_slot (c->lanes[i].table);
+      free_slot (c->lanes[i].table[0]);
+      free_slot (c->lanes[i].table[1]);
       if (c->lanes[i].dev) cudaFree (c->lanes[i].dev);
       if (c->lanes[i].done) cudaEventDestroy (c->lanes[i].done);
       if (c->lanes[i].stream) cudaStreamDestroy (c->lanes[i].stream);
@@ -1002,6 +1044,7 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
     cudaStreamDestroy (c->blend_stream);
     cudaStreamDestroy (c->up_stream);
     cudaStreamDestroy (c->reaper);
+    cudaStreamDestroy (c->table_stream);
   }
   delete thiz;
 }
@@ -1256,13 +1299,14 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
     return 0;
   CU (c, cudaStreamWaitEvent (l.stream, prep->ready, 0));
 
-  /* rows each window touches: host -> device */
+  /* rows each window touches: host -> device. Bands that are neighbours in y
+   * with the same byte range merge into one copy. */
   struct Span { int pl, b0, nb, y0, rows; };
   std::vector<Span> spans;
   for (const PlaneJob &j : jobs) {
     int pl = 0;
     for (int q = 0; q < n_planes; q++)
-      if (j.dst == df.plane[q])
+      if (j.dst >= static_cast<uint8_t *> (df.plane[q]))
         pl = q;
     Span s;
     s.pl = pl;
@@ -1270,22 +1314,48 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
     s.nb = std::min (j.win_nv * 16, j.row_bytes - s.b0);
     s.y0 = j.win_y0;
     s.rows = j.win_rows;
-    spans.push_back (s);
+    bool merged = false;
+    for (Span &o : spans)
+      if (o.pl == s.pl && o.b0 == s.b0 && o.nb == s.nb && o.y0 + o.rows == s.y0) {
+        o.rows += s.rows;
+        merged = true;
+        break;
+      }
+    if (!merged)
+      spans.push_back (s);
   }
-  for (const Span &s : spans) {
+  auto copy_span = [&](const Span &s, bool to_device) -> cudaError_t {
     uint8_t *d = static_cast<uint8_t *> (df.plane[s.pl]) + (size_t) s.y0 * df.stride[s.pl] + s.b0;
-    const uint8_t *h = static_cast<const uint8_t *> (hf->plane[s.pl]) + (size_t) s.y0 * hf->stride[s.pl] + s.b0;
-    CU (c, cudaMemcpy2DAsync (d, df.stride[s.pl], h, hf->stride[s.pl], s.nb, s.rows,
-            cudaMemcpyHostToDevice, l.stream));
+    uint8_t *h = static_cast<uint8_t *> (hf->plane[s.pl]) + (size_t) s.y0 * hf->stride[s.pl] + s.b0;
+    if (s.nb == df.stride[s.pl] && s.nb == hf->stride[s.pl]) {
+      /* full rows, equal strides: one linear copy */
+      return to_device ?
+          cudaMemcpyAsync (d, h, (size_t) s.nb * s.rows, cudaMemcpyHostToDevice, l.stream) :
+          cudaMemcpyAsync (h, d, (size_t) s.nb * s.rows, cudaMemcpyDeviceToHost, l.stream);
+    }
+    return to_device ?
+        cudaMemcpy2DAsync (d, df.stride[s.pl], h, hf->stride[s.pl], s.nb, s.rows,
+            cudaMemcpyHostToDevice, l.stream) :
+        cudaMemcpy2DAsync (h, hf->stride[s.pl], d, df.stride[s.pl], s.nb, s.rows,
+            cudaMemcpyDeviceToHost, l.stream);
+  };
+  for (const Span &s : spans) {
+    CU (c, copy_span (s, true));
     c->stats.h2d_bytes += (uint64_t) s.nb * s.rows;
   }
-  if ((rc = launch_jobs (c, l.table, jobs.data (), jobs.size (), plane_kind (fmt), l.stream)))
-    return rc;
+  {
+    std::vector<PlaneJob> grp[2];
+    for (const PlaneJob &j : jobs)
+      grp[(j.flags & JF_FAST) ? 1 : 0].push_back (j);
+    for (int g = 0; g < 2; g++)
+      if (!grp[g].empty ()) {
+        if ((rc = launch_jobs (c, l.table[g], grp[g].data (), grp[g].size (), plane_kind (fmt),
+                    g == 1, l.stream)))
+          return rc;
+      }
+  }
   for (const Span &s : spans) {
-    const uint8_t *d = static_cast<const uint8_t *> (df.plane[s.pl]) + (size_t) s.y0 * df.stride[s.pl] + s.b0;
-    uint8_t *h = static_cast<uint8_t *> (hf->plane[s.pl]) + (size_t) s.y0 * hf->stride[s.pl] + s.b0;
-    CU (c, cudaMemcpy2DAsync (h, hf->stride[s.pl], d, df.stride[s.pl], s.nb, s.rows,
-            cudaMemcpyDeviceToHost, l.stream));
+    CU (c, copy_span (s, false));
     c->stats.d2h_bytes += (uint64_t) s.nb * s.rows;
   }
   CU (c, cudaEventRecord (l.done, l.stream));

@@ -11,6 +11,8 @@
  */
 #include "ttmlblend_kernels.cuh"
 
+#include <cstdlib>
+
 namespace tb {
 
 /* ---------------------------------------------------------------------- */
@@ -180,12 +182,6 @@ rect_geom (const RectRef *r)
   return o;
 }
 
-__device__ __forceinline__ bool
-rect_hit (const RectGeom &g, int v, int y)
-{
-  return v >= g.v0 && v < g.v1 && y >= g.y0 && y < g.y1;
-}
-
 template <int KIND>
 __device__ __forceinline__ uint4
 blend_with_rect (uint4 f, const RectRef *r, const RectGeom &g, int v, int y,
@@ -204,75 +200,155 @@ blend_with_rect (uint4 f, const RectRef *r, const RectGeom &g, int v, int y,
   }
 }
 
-/* One CTA = one chunk of kItemsPerChunk 16-byte vectors of one plane window.
- * Thread t owns items t, t+256, t+512, t+768 of the chunk: four independent
- * 128-bit frame loads (and up to eight overlay loads) are in flight per
- * thread before the first one is consumed. */
-template <int KIND>
-__global__ void __launch_bounds__ (kThreads)
-ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
-    const uint32_t *__restrict__ chunk_begin, int n_jobs)
+/* Job fields a CTA keeps in registers while it works through the job. */
+struct JobRegs {
+  const PlaneJob *job;
+  const uint8_t *src;
+  uint8_t *dst;
+  int src_pitch, dst_pitch;
+  int win_v0, win_y0;
+  uint32_t win_nv, total_items, magic;
+  int cls;
+};
+
+__device__ __forceinline__ JobRegs
+load_job (const PlaneJob *job)
 {
-  const uint32_t chunk = blockIdx.x;
+  JobRegs J;
+  J.job = job;
+  J.src = ldg_ptr (&job->src);
+  J.dst = ldg_ptr (&job->dst);
+  J.src_pitch = __ldg (&job->src_pitch);
+  J.dst_pitch = __ldg (&job->dst_pitch);
+  J.win_v0 = __ldg (&job->win_v0);
+  J.win_nv = (uint32_t) __ldg (&job->win_nv);
+  J.win_y0 = __ldg (&job->win_y0);
+  J.total_items = J.win_nv * (uint32_t) __ldg (&job->win_rows);
+  J.magic = __ldg (&job->div_magic);
+  J.cls = __ldg (&job->cls);
+  return J;
+}
 
-  /* which plane job does this chunk belong to: count begins <= chunk */
-  int cnt = 0;
-  for (int base = 0; base < n_jobs; base += kThreads) {
-    const int j = base + (int) threadIdx.x;
-    const int pred = (j < n_jobs) && (__ldg (chunk_begin + j) <= chunk);
-    cnt += __syncthreads_count (pred);
-  }
-  const PlaneJob *job = jobs + (cnt - 1);
-  const uint32_t local_chunk = chunk - __ldg (chunk_begin + (cnt - 1));
-
-  const uint8_t *src = ldg_ptr (&job->src);
-  uint8_t *dst = ldg_ptr (&job->dst);
-  const RectRef *rects = ldg_ptr (&job->rects);
-  const int n_rects = __ldg (&job->n_rects);
-  const int src_pitch = __ldg (&job->src_pitch);
-  const int dst_pitch = __ldg (&job->dst_pitch);
-  const int row_bytes = __ldg (&job->row_bytes);
-  const int win_v0 = __ldg (&job->win_v0);
-  const uint32_t win_nv = (uint32_t) __ldg (&job->win_nv);
-  const int win_y0 = __ldg (&job->win_y0);
-  const uint32_t total_items = win_nv * (uint32_t) __ldg (&job->win_rows);
-  const uint32_t magic = __ldg (&job->div_magic);
-  const int flags = __ldg (&job->flags);
-  const bool vec_ok = (flags & JF_VECTOR) != 0;
-  const bool inplace = (flags & JF_INPLACE) != 0;
-  const bool dst_premul = (flags & JF_DST_PREMUL) != 0;
-
+/* One chunk = kItemsPerChunk consecutive 16-byte vectors of one job. A job is
+ * a window of one plane whose rows all see the same set of rectangles
+ * (rect_mask): the host cuts every plane at the rectangles' top and bottom
+ * edges, so the class of a chunk is known before launch and uniform per CTA:
+ *   JC_COPY     no rectangle: stream the rows through;
+ *   JC_ONE      exactly one rectangle covering the window's whole width:
+ *               every vector blends with it, no per-item tests;
+ *   JC_GENERAL  several rectangles and/or partial width: per-item column
+ *               tests, rectangles applied in order.
+ * Thread t owns items t, t+256, t+512, t+768 of the chunk, so four
+ * independent 128-bit frame loads (plus their overlay loads) are in flight
+ * per thread before the first is consumed. FAST = 16-byte aligned frame and
+ * no ragged vector; otherwise the byte-granular variant runs. */
+template <int KIND, bool FAST>
+__device__ __forceinline__ void
+process_chunk (const JobRegs &J, uint32_t local_chunk)
+{
+  const uint8_t *src = J.src;
+  uint8_t *dst = J.dst;
+  const int src_pitch = J.src_pitch, dst_pitch = J.dst_pitch;
   const uint32_t item0 = local_chunk * kItemsPerChunk + threadIdx.x;
 
-  int vv[kUnroll], yy[kUnroll], hit[kUnroll];
+  int vv[kUnroll], yy[kUnroll];
   bool act[kUnroll];
 #pragma unroll
   for (int k = 0; k < kUnroll; k++) {
     const uint32_t item = item0 + k * kThreads;
-    act[k] = item < total_items;
-    const uint32_t row = win_nv == 1u ? item : __umulhi (item, magic);
-    const uint32_t col = item - row * win_nv;
-    vv[k] = win_v0 + (int) col;
-    yy[k] = win_y0 + (int) row;
-    hit[k] = -1;
-  }
-
-  /* first rectangle (lowest index = first in blend order) covering each item */
-  for (int r = n_rects - 1; r >= 0; r--) {
-    const RectGeom g = rect_geom (rects + r);
-#pragma unroll
-    for (int k = 0; k < kUnroll; k++)
-      if (rect_hit (g, vv[k], yy[k]))
-        hit[k] = r;
+    act[k] = item < J.total_items;
+    const uint32_t row = J.win_nv == 1u ? item : __umulhi (item, J.magic);
+    const uint32_t col = item - row * J.win_nv;
+    vv[k] = J.win_v0 + (int) col;
+    yy[k] = J.win_y0 + (int) row;
   }
 
   uint4 f[kUnroll];
+
+  if (FAST) {
+    if (J.cls == JC_COPY) {
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++)
+        if (act[k])
+          f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++)
+        if (act[k])
+          st_frame16 (dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16, f[k]);
+      return;
+    }
+    if (J.cls == JC_ONE) {
+      const RectRef *r = ldg_ptr (&J.job->rects) + __ldg (&J.job->one_rect);
+      const RectGeom g = rect_geom (r);
+      const int32_t pitch = __ldg (&r->pitch);
+      const uint8_t *pa = ldg_ptr (&r->a);
+      uint4 oa[kUnroll], oc[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++)
+        if (act[k])
+          f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+      if (KIND == PK_PLANE8) {
+        const uint8_t *pc = ldg_ptr (&r->c);
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k]) {
+            const size_t off = (size_t) (yy[k] - g.y0) * pitch + (size_t) (vv[k] - g.v0) * 16;
+            oa[k] = ld_overlay16 (pa + off);
+            oc[k] = ld_overlay16 (pc + off);
+          }
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k])
+            st_frame16 (dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16,
+                blend16_plane8 (f[k], oa[k], oc[k]));
+      } else {
+        const uint32_t ga = (uint32_t) __ldg (&r->ga);
+        const bool sp = __ldg (&r->src_premul) != 0;
+        const bool dp = (__ldg (&J.job->flags) & JF_DST_PREMUL) != 0;
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k])
+            oa[k] = ld_overlay16 (pa + (size_t) (yy[k] - g.y0) * pitch + (size_t) (vv[k] - g.v0) * 16);
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k])
+            st_frame16 (dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16,
+                blend16_packed<KIND == PK_PACKED_A0 ? 0 : 3> (f[k], oa[k], ga, sp, dp));
+      }
+      return;
+    }
+  }
+
+  /* JC_GENERAL, and every class of the byte-granular variant */
+  const RectRef *rects = ldg_ptr (&J.job->rects);
+  const unsigned long long mask = __ldg (&J.job->rect_mask);
+  const int flags = __ldg (&J.job->flags);
+  const int row_bytes = __ldg (&J.job->row_bytes);
+  const bool inplace = (flags & JF_INPLACE) != 0;
+  const bool dst_premul = (flags & JF_DST_PREMUL) != 0;
+  const bool vec_ok = FAST || (flags & JF_VECTOR) != 0;
+
+  /* in place, vectors no rectangle covers are neither read nor written */
+  if (inplace) {
+    bool hit[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++)
+      hit[k] = false;
+    for (unsigned long long m = mask; m; m &= m - 1) {
+      const RectGeom g = rect_geom (rects + (__ffsll ((long long) m) - 1));
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++)
+        hit[k] = hit[k] || (vv[k] >= g.v0 && vv[k] < g.v1);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++)
+      act[k] = act[k] && hit[k];
+  }
+
   int nvalid[kUnroll];
 #pragma unroll
   for (int k = 0; k < kUnroll; k++) {
-    if (inplace && hit[k] < 0)
-      act[k] = false;
-    nvalid[k] = min (16, row_bytes - vv[k] * 16);
+    nvalid[k] = FAST ? 16 : min (16, row_bytes - vv[k] * 16);
     if (act[k]) {
       const uint8_t *p = src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16;
       if (vec_ok && nvalid[k] == 16)
@@ -282,19 +358,14 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
     }
   }
 
+  /* rectangles in blend order; the job's rows are inside every one of them */
+  for (unsigned long long m = mask; m; m &= m - 1) {
+    const RectRef *r = rects + (__ffsll ((long long) m) - 1);
+    const RectGeom g = rect_geom (r);
 #pragma unroll
-  for (int k = 0; k < kUnroll; k++) {
-    if (act[k] && hit[k] >= 0) {
-      const RectRef *r = rects + hit[k];
-      const RectGeom g = rect_geom (r);
-      f[k] = blend_with_rect<KIND> (f[k], r, g, vv[k], yy[k], dst_premul);
-      /* overlapping rectangles: the later ones blend on top, in order */
-      for (int r2 = hit[k] + 1; r2 < n_rects; r2++) {
-        const RectGeom g2 = rect_geom (rects + r2);
-        if (rect_hit (g2, vv[k], yy[k]))
-          f[k] = blend_with_rect<KIND> (f[k], rects + r2, g2, vv[k], yy[k], dst_premul);
-      }
-    }
+    for (int k = 0; k < kUnroll; k++)
+      if (act[k] && vv[k] >= g.v0 && vv[k] < g.v1)
+        f[k] = blend_with_rect<KIND> (f[k], r, g, vv[k], yy[k], dst_premul);
   }
 
 #pragma unroll
@@ -309,29 +380,99 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
   }
 }
 
+/* One CTA per chunk (a streaming copy on B200 is fastest as many short-lived
+ * CTAs: tools/copybench.cu). CTAs do NOT take chunks in list order:
+ * the flat chunk list is walked as `lanes` interleaved sequential streams
+ *     chunk = (cta % lanes) * per_lane + cta / lanes
+ * so that the CTAs resident at any moment are spread over all frames and
+ * bands of the launch. Blend chunks (ALU-heavy) and copy chunks (pure HBM
+ * streaming) then share every SM all the time and the integer work hides
+ * under the memory time, instead of the chip being compute-bound inside the
+ * cue bands and idle on the ALUs outside them. */
+#ifndef TTMLBLEND_MIN_CTAS
+#define TTMLBLEND_MIN_CTAS 4
+#endif
+
+template <int KIND, bool FAST>
+__global__ void __launch_bounds__ (kThreads, FAST ? TTMLBLEND_MIN_CTAS : 2)
+ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
+    const uint32_t *__restrict__ chunk_begin, int n_jobs, uint32_t total_chunks,
+    uint32_t lanes, uint32_t per_lane, uint32_t lanes_magic)
+{
+  const uint32_t q = lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, lanes_magic);
+  const uint32_t r = blockIdx.x - q * lanes;
+  const uint32_t chunk = r * per_lane + q;
+  /* uniform per CTA, so nobody is left waiting at the barrier below */
+  if (chunk >= total_chunks)
+    return;
+
+  /* which job: count begins <= chunk, cooperatively */
+  int cnt = 0;
+  for (int base = 0; base < n_jobs; base += kThreads) {
+    const int j = base + (int) threadIdx.x;
+    const int pred = (j < n_jobs) && (__ldg (chunk_begin + j) <= chunk);
+    cnt += __syncthreads_count (pred);
+  }
+  const JobRegs J = load_job (jobs + (cnt - 1));
+  process_chunk<KIND, FAST> (J, chunk - __ldg (chunk_begin + (cnt - 1)));
+}
+
+/* Number of interleaved streams the chunk list is walked in (env
+ * FLUC_TTMLBLEND_LANES, default 61: a prime, so that lane starts do not line
+ * up with the frame structure of a batch). 1 = list order. */
+static uint32_t
+interleave_lanes ()
+{
+  static uint32_t n = 0;
+  if (n == 0) {
+    const char *e = getenv ("FLUC_TTMLBLEND_LANES");
+    int v = e ? atoi (e) : 61;
+    if (v < 1) v = 1;
+    if (v > 4096) v = 4096;
+    n = (uint32_t) v;
+  }
+  return n;
+}
+
+template <int KIND>
+static cudaError_t
+launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_jobs,
+    uint32_t total_chunks, bool fast, cudaStream_t stream)
+{
+  uint32_t lanes = interleave_lanes ();
+  if (total_chunks < lanes * 8u)
+    lanes = 1;
+  const uint32_t per_lane = (total_chunks + lanes - 1) / lanes;
+  const uint32_t grid = lanes * per_lane;
+  /* umulhi (i, ceil (2^32 / lanes)) == i / lanes while i * lanes < 2^32 */
+  if ((unsigned long long) grid * lanes >= (1ull << 32))
+    return cudaErrorInvalidValue;
+  const uint32_t magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
+  if (fast)
+    ttmlblend_blend_kernel<KIND, true><<<grid, kThreads, 0, stream>>> (d_jobs,
+        d_chunk_begin, n_jobs, total_chunks, lanes, per_lane, magic);
+  else
+    ttmlblend_blend_kernel<KIND, false><<<grid, kThreads, 0, stream>>> (d_jobs,
+        d_chunk_begin, n_jobs, total_chunks, lanes, per_lane, magic);
+  return cudaGetLastError ();
+}
+
 cudaError_t
 launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_jobs,
-    uint32_t total_chunks, int kind, cudaStream_t stream)
+    uint32_t total_chunks, int kind, bool fast, cudaStream_t stream)
 {
   if (n_jobs <= 0 || total_chunks == 0)
     return cudaSuccess;
   switch (kind) {
     case PK_PLANE8:
-      ttmlblend_blend_kernel<PK_PLANE8><<<total_chunks, kThreads, 0, stream>>> (
-          d_jobs, d_chunk_begin, n_jobs);
-      break;
+      return launch_blend_kind<PK_PLANE8> (d_jobs, d_chunk_begin, n_jobs, total_chunks, fast, stream);
     case PK_PACKED_A0:
-      ttmlblend_blend_kernel<PK_PACKED_A0><<<total_chunks, kThreads, 0, stream>>> (
-          d_jobs, d_chunk_begin, n_jobs);
-      break;
+      return launch_blend_kind<PK_PACKED_A0> (d_jobs, d_chunk_begin, n_jobs, total_chunks, fast, stream);
     case PK_PACKED_A3:
-      ttmlblend_blend_kernel<PK_PACKED_A3><<<total_chunks, kThreads, 0, stream>>> (
-          d_jobs, d_chunk_begin, n_jobs);
-      break;
+      return launch_blend_kind<PK_PACKED_A3> (d_jobs, d_chunk_begin, n_jobs, total_chunks, fast, stream);
     default:
       return cudaErrorInvalidValue;
   }
-  return cudaGetLastError ();
 }
 
 /* ---------------------------------------------------------------------- */

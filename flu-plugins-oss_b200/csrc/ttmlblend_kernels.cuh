@@ -37,7 +37,8 @@ enum PlaneKind : int32_t {
 enum JobFlags : int32_t {
   JF_VECTOR = 1,        /* src, dst and both pitches are 16-byte aligned */
   JF_INPLACE = 2,       /* dst == src: bytes no rectangle covers are not touched */
-  JF_DST_PREMUL = 4     /* destination frame is premultiplied (packed kinds) */
+  JF_DST_PREMUL = 4,    /* destination frame is premultiplied (packed kinds) */
+  JF_FAST = 8           /* host-side: JF_VECTOR and no ragged last vector -> fast kernel */
 };
 
 /* One prepared rectangle as seen from one destination plane. */
@@ -52,26 +53,39 @@ struct alignas (16) RectRef {
   int32_t pad_;
 };
 
-/* One window of one plane of one frame. Items are 16-byte vectors, numbered
- * row-major inside the window; a chunk is kItemsPerChunk consecutive items. */
+enum JobClass : int32_t {
+  JC_COPY = 0,          /* no rectangle touches the window */
+  JC_ONE = 1,           /* one rectangle covers the whole window */
+  JC_GENERAL = 2        /* several rectangles and/or partial width */
+};
+
+/* One window of one plane of one frame: a band of rows that all see the same
+ * rectangles (rect_mask, bit i = rects[i]; every one of them spans all the
+ * band's rows). Items are 16-byte vectors, numbered row-major inside the
+ * window; a chunk is kItemsPerChunk consecutive items. */
 struct alignas (16) PlaneJob {
   const uint8_t *src;
   uint8_t *dst;
   const RectRef *rects;
-  int32_t n_rects;
+  unsigned long long rect_mask;
   int32_t src_pitch, dst_pitch;
   int32_t row_bytes;    /* valid bytes per plane row */
   int32_t win_v0, win_nv, win_y0, win_rows;
   uint32_t div_magic;   /* ceil (2^32 / win_nv): item / win_nv == umulhi (item, magic) */
   int32_t kind;         /* PlaneKind */
   int32_t flags;        /* JobFlags */
+  int32_t cls;          /* JobClass */
+  int32_t one_rect;     /* JC_ONE: index into rects */
   uint32_t n_chunks;
+  int32_t pad_;
 };
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
+#ifndef TTMLBLEND_UNROLL
+#define TTMLBLEND_UNROLL 4
+#endif
+constexpr int kUnroll = TTMLBLEND_UNROLL;
 constexpr int kItemsPerChunk = kThreads * kUnroll;
-constexpr int kSmemRects = 8;
 
 /* Parameters of the once-per-cue prepare kernels. Raw = device copy of the
  * rectangle's BGRA bytes whose pixel (0,0) sits at frame (fx, fy). */
@@ -102,9 +116,10 @@ enum PrepareMode : int32_t {
   PM_PACKED_BGRA = 8
 };
 
-/* All jobs of one launch share one PlaneKind. */
+/* All jobs of one launch share one PlaneKind and one variant: fast (every
+ * job 16-byte aligned with row_bytes % 16 == 0) or byte-granular. */
 cudaError_t launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin,
-    int n_jobs, uint32_t total_chunks, int kind, cudaStream_t stream);
+    int n_jobs, uint32_t total_chunks, int kind, bool fast, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);

@@ -117,7 +117,7 @@ def load_library(path: Optional[str] = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("FLUC_TTMLBLEND_LIB") or LIB_PATH   # env: kernel-variant experiments
     if not os.path.exists(p):
         raise FileNotFoundError(
             f"{p} is missing: build it with `make -C {os.path.dirname(p)}` "

@@ -1,0 +1,146 @@
+/*
+ * xcheck_gst.c -- pins the oracle against a REAL libgstvideo-1.0.
+ *
+ * TEST INFRASTRUCTURE. Cannot be built in the graft image (no GLib/GStreamer);
+ * `make -C oracle xcheck_gst` works wherever `pkg-config gstreamer-video-1.0`
+ * does. It runs gst_video_overlay_composition_blend () -- the call the
+ * reference pipeline ends up in for ttmlrender's BGRA buffers
+ * (/root/reference/plugins/ttml/gstttmlrender.c:78-84,1427-1478) -- and
+ * tbref_composition_blend () on the same seeded inputs for every supported
+ * destination format and prints the number of differing bytes. Record the
+ * printed GStreamer version in DESIGN.md next to the result; until someone
+ * has done that, parity is "unpinned".
+ */
+#include <gst/gst.h>
+#include <gst/video/video.h>
+#include <gst/video/video-overlay-composition.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ttmlblend_ref.h"
+
+static guint64 sm_state;
+
+static guint64
+splitmix64 (void)
+{
+  guint64 z = (sm_state += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+static const struct {
+  GstVideoFormat gst;
+  int ref;
+  const char *name;
+} formats[] = {
+  { GST_VIDEO_FORMAT_I420, TBREF_FORMAT_I420, "I420" },
+  { GST_VIDEO_FORMAT_YV12, TBREF_FORMAT_YV12, "YV12" },
+  { GST_VIDEO_FORMAT_NV12, TBREF_FORMAT_NV12, "NV12" },
+  { GST_VIDEO_FORMAT_NV21, TBREF_FORMAT_NV21, "NV21" },
+  { GST_VIDEO_FORMAT_AYUV, TBREF_FORMAT_AYUV, "AYUV" },
+  { GST_VIDEO_FORMAT_ARGB, TBREF_FORMAT_ARGB, "ARGB" },
+  { GST_VIDEO_FORMAT_ABGR, TBREF_FORMAT_ABGR, "ABGR" },
+  { GST_VIDEO_FORMAT_RGBA, TBREF_FORMAT_RGBA, "RGBA" },
+  { GST_VIDEO_FORMAT_BGRA, TBREF_FORMAT_BGRA, "BGRA" },
+};
+
+int
+main (int argc, char **argv)
+{
+  const int W = 321, H = 181, RW = 200, RH = 90, RX = 37, RY = 51;
+  guint f, total_bad = 0;
+  gst_init (&argc, &argv);
+  printf ("GStreamer %s\n", gst_version_string ());
+
+  for (f = 0; f < G_N_ELEMENTS (formats); f++) {
+    int opaque;
+    for (opaque = 1; opaque >= 0; opaque--) {
+      GstVideoInfo info, rinfo;
+      GstBuffer *fbuf, *rbuf;
+      GstVideoFrame frame;
+      GstVideoOverlayRectangle *rect;
+      GstVideoOverlayComposition *comp;
+      GstMapInfo map;
+      guint8 *copy, *rpix;
+      TbRefFrame rf;
+      TbRefRectangle rr;
+      gsize i, bad = 0;
+      guint p;
+
+      sm_state = 0x74746d6c + f * 2 + opaque;
+      gst_video_info_set_format (&info, formats[f].gst, W, H);
+      fbuf = gst_buffer_new_allocate (NULL, info.size, NULL);
+      gst_buffer_map (fbuf, &map, GST_MAP_WRITE);
+      for (i = 0; i < map.size; i++)
+        map.data[i] = (guint8) splitmix64 ();
+      if (opaque && GST_VIDEO_INFO_HAS_ALPHA (&info)) {
+        guint aoff = GST_VIDEO_INFO_COMP_POFFSET (&info, GST_VIDEO_COMP_A);
+        for (i = aoff; i < map.size; i += 4)
+          map.data[i] = 255;
+      }
+      copy = g_memdup2 (map.data, map.size);
+      gst_buffer_unmap (fbuf, &map);
+
+      /* premultiplied BGRA rectangle, like Cairo ARGB32 */
+      gst_video_info_set_format (&rinfo, GST_VIDEO_OVERLAY_COMPOSITION_FORMAT_RGB, RW, RH);
+      rpix = g_malloc (RW * RH * 4);
+      for (i = 0; i < (gsize) RW * RH; i++) {
+        guint a = splitmix64 () & 0xff, k;
+        if ((splitmix64 () & 7) == 0) a = 0;
+        if ((splitmix64 () & 7) == 1) a = 255;
+        for (k = 0; k < 3; k++)
+          rpix[4 * i + k] = (guint8) (((splitmix64 () & 0xff) * a + 127) / 255);
+        rpix[4 * i + 3] = (guint8) a;
+      }
+      rbuf = gst_buffer_new_wrapped (g_memdup2 (rpix, RW * RH * 4), RW * RH * 4);
+      gst_buffer_add_video_meta (rbuf, GST_VIDEO_FRAME_FLAG_NONE,
+          GST_VIDEO_OVERLAY_COMPOSITION_FORMAT_RGB, RW, RH);
+      rect = gst_video_overlay_rectangle_new_raw (rbuf, RX, RY, RW, RH,
+          GST_VIDEO_OVERLAY_FORMAT_FLAG_PREMULTIPLIED_ALPHA);
+      comp = gst_video_overlay_composition_new (rect);
+
+      gst_video_frame_map (&frame, &info, fbuf, GST_MAP_READWRITE);
+      gst_video_overlay_composition_blend (comp, &frame);
+      gst_video_frame_unmap (&frame);
+
+      memset (&rf, 0, sizeof rf);
+      rf.format = formats[f].ref;
+      rf.width = W;
+      rf.height = H;
+      for (p = 0; p < GST_VIDEO_INFO_N_PLANES (&info); p++) {
+        rf.data[p] = copy + GST_VIDEO_INFO_PLANE_OFFSET (&info, p);
+        rf.stride[p] = GST_VIDEO_INFO_PLANE_STRIDE (&info, p);
+      }
+      memset (&rr, 0, sizeof rr);
+      rr.pixels = rpix;
+      rr.width = RW;
+      rr.height = RH;
+      rr.stride = RW * 4;
+      rr.x = RX;
+      rr.y = RY;
+      rr.global_alpha = 1.0f;
+      rr.flags = TBREF_FLAG_PREMULTIPLIED_ALPHA;
+      tbref_composition_blend (&rf, &rr, 1);
+
+      gst_buffer_map (fbuf, &map, GST_MAP_READ);
+      for (i = 0; i < map.size; i++)
+        bad += map.data[i] != copy[i];
+      gst_buffer_unmap (fbuf, &map);
+      printf ("%-5s dest alpha %-7s: %" G_GSIZE_FORMAT " differing bytes of %" G_GSIZE_FORMAT "\n",
+          formats[f].name, opaque ? "opaque" : "random", bad, (gsize) info.size);
+      total_bad += bad;
+
+      gst_video_overlay_composition_unref (comp);
+      gst_video_overlay_rectangle_unref (rect);
+      gst_buffer_unref (rbuf);
+      gst_buffer_unref (fbuf);
+      g_free (copy);
+      g_free (rpix);
+    }
+  }
+  printf ("%s\n", total_bad ? "MISMATCH" : "oracle == libgstvideo on all vectors");
+  return total_bad ? 1 : 0;
+}
