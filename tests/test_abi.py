@@ -112,3 +112,34 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"ttmlblend_ref|tbref_|from oracle|import oracle|oracle/", txt):
                     bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_host_mirror_exports_its_header(lib):
+    """host/fluc_videooverlay.h (the C mirror of gst_video_overlay_composition_*)."""
+    vo = pkg.videooverlay
+    if not os.path.exists(vo.LIB_PATH):
+        graft.build()
+    src = open(os.path.join(graft.PKG_DIR, "host", "fluc_videooverlay.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = set(re.findall(r"FLUC_EXPORT[^;]*?\b(fluc_video_overlay_\w+)\s*\(", src))
+    out = subprocess.check_output(["nm", "-D", "--defined-only", vo.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (fluc_video_overlay_\w+)", out))
+    assert declared == exported == set(vo.PROTOTYPES)
+    vlib = vo.load_library()
+    # object model without a GPU: refcounts, n_rectangles, global alpha, NULL handling
+    import numpy as np
+    px = np.zeros((4, 6, 4), dtype=np.uint8)
+    r = vo.Rectangle(px, 1, 2)
+    assert r.get_global_alpha() == 1.0
+    r.set_global_alpha(0.5)
+    assert r.get_global_alpha() == 0.5
+    r.set_global_alpha(7.0)                      # out of range: ignored, like the g_return_if_fail
+    assert r.get_global_alpha() == 0.5
+    c = vo.Composition(r)
+    c.add_rectangle(r)
+    assert c.n_rectangles() == 2
+    assert vlib.fluc_video_overlay_rectangle_new_raw(None, 4, 4, 16, 0, 0, 0) is None
+    assert vlib.fluc_video_overlay_composition_blend(None, None) == 0
+    if lib.fluc_ttmlblend_device_count() == 0:
+        planes = [np.zeros((8, 8 * 4), dtype=np.uint8)]
+        assert c.blend("BGRA", 8, 8, planes) is False     # FALSE, not a CPU fallback
