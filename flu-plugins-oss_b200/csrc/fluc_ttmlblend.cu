@@ -176,6 +176,9 @@ struct Lane {
   std::shared_ptr<Overlay> keep;
 };
 
+/* How blend_host moves a device-accessible (pinned) host frame. */
+enum HostMode { HM_STAGED = 0, HM_ZEROCOPY = 1, HM_WRITEBACK = 2 };
+
 constexpr int kLanes = 4;
 constexpr int kTableSlots = 8;
 
@@ -201,6 +204,7 @@ struct Ctx {
   int next_slot = 0;
 
   uint32_t max_batch = 32, linger_us = 200;
+  int host_mode = HM_ZEROCOPY;
   bool profiling = false;
   std::thread sched;
   bool quit = false;
@@ -542,10 +546,12 @@ push_split (std::vector<PlaneJob> &jobs, PlaneJob b, bool aligned, int v0, int v
  * algorithmic bytes moved. */
 uint64_t
 build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
-    const FlucTtmlBlendFrame *dst, const Prepared *prep, std::vector<PlaneJob> &jobs)
+    const FlucTtmlBlendFrame *dst, const Prepared *prep, bool windowed, std::vector<PlaneJob> &jobs)
 {
   const int n_planes = format_planes (format);
-  const bool inplace = src->plane[0] == dst->plane[0];
+  /* windowed: only the vectors a rectangle covers are read and written (in
+   * place, or host frames where untouched bytes never cross PCIe) */
+  const bool inplace = windowed;
   uint64_t bytes = 0;
   std::vector<int> ys;
   for (int pl = 0; pl < n_planes; pl++) {
@@ -556,6 +562,7 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
     b.dst_pitch = dst->stride[pl];
     b.row_bytes = plane_row_bytes (format, pl, W);
     b.kind = plane_kind (format);
+    b.plane = pl;
     const int rows = plane_rows (format, pl, H);
     const bool aligned = (((uintptr_t) b.src | (uintptr_t) b.dst | (uintptr_t) b.src_pitch |
             (uintptr_t) b.dst_pitch) & 15u) == 0;
@@ -975,6 +982,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   const char *e;
   if ((e = getenv ("FLUC_TTMLBLEND_BATCH")))
     c->max_batch = (uint32_t) std::max (1, std::min (1024, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))
+    c->host_mode = std::max (0, std::min (2, atoi (e)));
   if ((e = getenv ("FLUC_TTMLBLEND_LINGER_US")))
     c->linger_us = (uint32_t) std::max (0, atoi (e));
   c->sched = std::thread (scheduler_main, c);
@@ -1138,7 +1147,8 @@ fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat
     if ((rc = prepare_overlay (c, f.overlay.get (), fmt, W, H, &f.prep)))
       return rc;
   }
-  f.algo_bytes = build_jobs (fmt, W, H, frame_flags, src, dst, f.prep, f.jobs);
+  f.algo_bytes = build_jobs (fmt, W, H, frame_flags, src, dst, f.prep,
+      src->plane[0] == dst->plane[0], f.jobs);
   f.ticket = ++c->next_ticket;
   if (ticket)
     *ticket = f.ticket;
@@ -1268,6 +1278,48 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
   if ((rc = prepare_overlay (c, ov.get (), fmt, W, H, &prep)))
     return rc;
 
+  /* Is the host frame device-accessible (pool frame / host_register)? Then the
+   * kernel can reach it over PCIe itself. */
+  const int n_planes = format_planes (fmt);
+  FlucTtmlBlendFrame zf = {};
+  bool mapped = c->host_mode != HM_STAGED;
+  for (int pl = 0; pl < n_planes && mapped; pl++) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes (&attr, hf->plane[pl]) != cudaSuccess ||
+        attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+      cudaGetLastError ();
+      mapped = false;
+    } else {
+      zf.plane[pl] = attr.devicePointer;
+      zf.stride[pl] = hf->stride[pl];
+    }
+  }
+
+  if (mapped && c->host_mode == HM_ZEROCOPY) {
+    /* zero copy: the frame joins the batch; the blend kernel reads the rows
+     * under the cue from host memory and writes them back, all over PCIe,
+     * one launch for every queued frame */
+    PendingFrame f;
+    f.kind = plane_kind (fmt);
+    f.overlay = ov;
+    f.prep = prep;
+    f.ticket = tk;
+    f.algo_bytes = build_jobs (fmt, W, H, frame_flags, &zf, &zf, prep, true, f.jobs);
+    for (const PlaneJob &j : f.jobs) {
+      const uint64_t nb = (uint64_t) std::min (j.win_nv * 16, j.row_bytes - j.win_v0 * 16) * j.win_rows;
+      c->stats.h2d_bytes += nb;
+      c->stats.d2h_bytes += nb;
+    }
+    if (c->pending.empty ())
+      c->oldest_pending = std::chrono::steady_clock::now ();
+    c->pending.push_back (std::move (f));
+    if (c->pending.size () >= c->max_batch)
+      return launch_pending (c);
+    if (c->linger_us)
+      c->cv.notify_all ();
+    return 0;
+  }
+
   Lane &l = c->lanes[c->next_lane];
   const int lane_idx = c->next_lane;
   c->next_lane = (c->next_lane + 1) % kLanes;
@@ -1279,7 +1331,6 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
   }
 
   /* device staging frame: same strides as a pool frame */
-  const int n_planes = format_planes (fmt);
   FlucTtmlBlendFrame df = {};
   size_t off = 0;
   size_t plane_off[3];
@@ -1293,8 +1344,11 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
   for (int pl = 0; pl < n_planes; pl++)
     df.plane[pl] = l.dev + plane_off[pl];
 
+  /* HM_WRITEBACK: the copy engine brings the rows in, the kernel stores the
+   * result straight into the host frame (posted PCIe writes), no copy back */
+  const bool writeback = mapped && c->host_mode == HM_WRITEBACK;
   std::vector<PlaneJob> jobs;
-  const uint64_t algo = build_jobs (fmt, W, H, frame_flags, &df, &df, prep, jobs);
+  const uint64_t algo = build_jobs (fmt, W, H, frame_flags, &df, writeback ? &zf : &df, prep, true, jobs);
   if (jobs.empty ())
     return 0;
   CU (c, cudaStreamWaitEvent (l.stream, prep->ready, 0));
@@ -1304,12 +1358,8 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
   struct Span { int pl, b0, nb, y0, rows; };
   std::vector<Span> spans;
   for (const PlaneJob &j : jobs) {
-    int pl = 0;
-    for (int q = 0; q < n_planes; q++)
-      if (j.dst >= static_cast<uint8_t *> (df.plane[q]))
-        pl = q;
     Span s;
-    s.pl = pl;
+    s.pl = j.plane;
     s.b0 = j.win_v0 * 16;
     s.nb = std::min (j.win_nv * 16, j.row_bytes - s.b0);
     s.y0 = j.win_y0;
@@ -1355,7 +1405,8 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
       }
   }
   for (const Span &s : spans) {
-    CU (c, copy_span (s, false));
+    if (!writeback)
+      CU (c, copy_span (s, false));
     c->stats.d2h_bytes += (uint64_t) s.nb * s.rows;
   }
   CU (c, cudaEventRecord (l.done, l.stream));

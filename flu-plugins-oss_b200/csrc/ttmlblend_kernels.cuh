@@ -77,7 +77,7 @@ struct alignas (16) PlaneJob {
   int32_t cls;          /* JobClass */
   int32_t one_rect;     /* JC_ONE: index into rects */
   uint32_t n_chunks;
-  int32_t pad_;
+  int32_t plane;        /* host-side bookkeeping: plane index of the frame */
 };
 
 constexpr int kThreads = 256;

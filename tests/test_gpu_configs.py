@@ -110,3 +110,45 @@ def test_256_streams_each_with_its_own_cue(ctx):
             ctx.overlay_clear(1000 + s)
     finally:
         ctx.set_batch(32, 200)
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("fmt,w,h", [("NV12", 1920, 1080), ("I420", 1279, 719), ("BGRA", 640, 360)])
+def test_host_modes_agree(monkeypatch, mode, fmt, w, h):
+    """FLUC_TTMLBLEND_HOST_MODE: 0 staged copies, 1 zero-copy (kernel reads/writes pinned host
+    memory over PCIe, batched), 2 copy in + kernel writes back. Same bytes in all three."""
+    from helpers import random_frame, random_overlay
+    monkeypatch.setenv("FLUC_TTMLBLEND_HOST_MODE", mode)
+    c = pkg.TtmlBlend(0)
+    try:
+        rects = [dict(pixels=random_overlay(w // 2, h // 4, 5), x=w // 4 + 1, y=h // 2 + 1),
+                 dict(pixels=random_overlay(w // 3, h // 5, 6), x=3, y=7, global_alpha=0.9)]
+        c.overlay_set_rectangles(2, rects)
+        frames = [random_frame(fmt, w, h, 40 + i) for i in range(6)]
+        want = [oracle_blend(fmt, w, h, copy_planes(f), rects) for f in frames]
+        pinned = [c.acquire(fmt, w, h, on_host=True) for _ in frames]
+        for p, f in zip(pinned, frames):
+            for dst, src in zip(p.host_planes(), f):
+                dst[...] = src
+        tickets = [c.blend_host_frame(2, fmt, w, h, p.c) for p in pinned]
+        for t in reversed(tickets):
+            c.wait(t)
+        for p, wnt in zip(pinned, want):
+            assert_planes_equal([np.array(x) for x in p.host_planes()], wnt, f"mode {mode}")
+        st = c.stats()
+        assert st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0
+        # registered (cudaHostRegister) numpy memory takes the same route as pool frames
+        buf = np.zeros(sum(r * cw for r, cw in wl.plane_shapes(fmt, w, h)) + 4096, dtype=np.uint8)
+        c.host_register(buf)
+        off, planes = 0, []
+        for (r, cw), src in zip(wl.plane_shapes(fmt, w, h), frames[0]):
+            v = buf[off:off + r * cw].reshape(r, cw)
+            v[...] = src
+            planes.append(v)
+            off += r * cw
+        c.wait(c.blend_host(2, fmt, w, h, planes))
+        assert_planes_equal(planes, want[0], f"registered, mode {mode}")
+        c.sync()
+        c.host_unregister(buf)
+    finally:
+        c.close()
