@@ -122,7 +122,10 @@ struct Prepared {
   int format = -1, W = 0, H = 0;
   std::vector<void *> allocs;
   std::vector<RectRef> h_rects[3];     /* per plane, host copy */
+  std::vector<RectRef> h_rects_all;
   RectRef *d_rects[3] = { nullptr, nullptr, nullptr };
+  RectRef *d_rects_all = nullptr;      /* the three tables, contiguous */
+  int32_t rect_off[3] = { 0, 0, 0 };   /* first entry of plane p in d_rects_all */
   uint64_t overlay_px = 0;             /* sum of clipped w*h */
   cudaEvent_t ready = nullptr;
 };
@@ -139,8 +142,21 @@ struct PendingFrame {
   std::shared_ptr<Overlay> overlay;
   Prepared *prep;
   int kind;
-  std::vector<PlaneJob> jobs;
+  std::vector<PlaneJob> jobs;          /* generic-kernel jobs (byte-granular parts, odd frames) */
   uint64_t algo_bytes;
+  /* group launch: the fast windows as a band list + this frame's pointers */
+  bool grouped = false;
+  std::vector<BandDesc> bands;
+  FramePtrs ptrs;
+  int32_t src_pitch[3], dst_pitch[3], rect_off[3], gflags;
+  uint32_t chunks_per_frame = 0;
+  const void *dst0 = nullptr;
+};
+
+/* frames that can share one launch: everything but the pointers is equal */
+struct Group {
+  int kind;
+  GroupParams P;
 };
 
 struct Batch {
@@ -196,6 +212,7 @@ struct Ctx {
   std::unordered_map<uint32_t, std::shared_ptr<Overlay>> overlays;
 
   std::vector<PendingFrame> pending;
+  std::vector<Group> groups;           /* scratch of launch_pending */
   std::chrono::steady_clock::time_point oldest_pending;
   uint64_t next_ticket = 0, launched_ticket = 0, done_ticket = 0;
   std::deque<Batch> batches;
@@ -205,6 +222,7 @@ struct Ctx {
 
   uint32_t max_batch = 32, linger_us = 200;
   int host_mode = HM_ZEROCOPY;
+  bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
   bool profiling = false;
   std::thread sched;
   bool quit = false;
@@ -467,20 +485,31 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
     }
   }
 
-  /* rectangle tables */
-  for (int pl = 0; pl < 3; pl++) {
-    if (P->h_rects[pl].empty ())
-      continue;
-    if (P->h_rects[pl].size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
-      return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-    uint8_t *d;
-    const size_t bytes = P->h_rects[pl].size () * sizeof (RectRef);
-    int rc;
-    if ((rc = dev_alloc (c, P.get (), bytes, &d)))
-      return rc;
-    /* pageable source: the copy has left the host buffer when this returns */
-    CU (c, cudaMemcpyAsync (d, P->h_rects[pl].data (), bytes, cudaMemcpyHostToDevice, c->up_stream));
-    P->d_rects[pl] = reinterpret_cast<RectRef *> (d);
+  /* rectangle tables: one contiguous device array, plane after plane */
+  {
+    size_t total = 0;
+    for (int pl = 0; pl < 3; pl++) {
+      if (P->h_rects[pl].size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+        return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+      P->rect_off[pl] = (int32_t) total;
+      total += P->h_rects[pl].size ();
+    }
+    if (total) {
+      P->h_rects_all.clear ();
+      for (int pl = 0; pl < 3; pl++)
+        P->h_rects_all.insert (P->h_rects_all.end (), P->h_rects[pl].begin (), P->h_rects[pl].end ());
+      uint8_t *d;
+      int rc;
+      if ((rc = dev_alloc (c, P.get (), total * sizeof (RectRef), &d)))
+        return rc;
+      /* h_rects_all lives as long as the Prepared: safe source for the async copy */
+      CU (c, cudaMemcpyAsync (d, P->h_rects_all.data (), total * sizeof (RectRef),
+              cudaMemcpyHostToDevice, c->up_stream));
+      P->d_rects_all = reinterpret_cast<RectRef *> (d);
+      for (int pl = 0; pl < 3; pl++)
+        if (!P->h_rects[pl].empty ())
+          P->d_rects[pl] = P->d_rects_all + P->rect_off[pl];
+    }
   }
   CU (c, cudaEventCreateWithFlags (&P->ready, cudaEventDisableTiming));
   CU (c, cudaEventRecord (P->ready, c->up_stream));
@@ -621,6 +650,90 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
   return bytes;
 }
 
+/* Moves the fast jobs of a frame into a band list for the group kernel. */
+void
+make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst)
+{
+  size_t n_fast = 0;
+  for (const PlaneJob &j : f.jobs)
+    n_fast += (j.flags & JF_FAST) ? 1 : 0;
+  if (n_fast == 0 || n_fast > (size_t) kMaxGroupBands)
+    return;
+  std::vector<PlaneJob> rest;
+  uint32_t total = 0;
+  int gflags = -1;
+  for (const PlaneJob &j : f.jobs) {
+    if (!(j.flags & JF_FAST)) {
+      rest.push_back (j);
+      continue;
+    }
+    BandDesc b = {};
+    b.chunk_begin = total;
+    b.plane = j.plane;
+    b.win_v0 = j.win_v0;
+    b.win_nv = j.win_nv;
+    b.win_y0 = j.win_y0;
+    b.win_rows = j.win_rows;
+    b.div_magic = j.div_magic;
+    b.cls = j.cls;
+    b.one_rect = j.one_rect;
+    b.rect_mask_lo = (uint32_t) j.rect_mask;
+    b.rect_mask_hi = (uint32_t) (j.rect_mask >> 32);
+    b.n_chunks = j.n_chunks;
+    total += j.n_chunks;
+    f.bands.push_back (b);
+    gflags = j.flags & (JF_INPLACE | JF_DST_PREMUL);
+  }
+  /* frame = umulhi (chunk, ceil (2^32 / cpf)) must be exact for every chunk of a full group */
+  const uint64_t magic = ((1ull << 32) + total - 1) / total;
+  const uint64_t e = magic * total - (1ull << 32);
+  if ((uint64_t) kMaxGroupFrames * total * e >= (1ull << 32) || (uint64_t) kMaxGroupFrames * total >= (1ull << 26)) {
+    f.bands.clear ();
+    return;
+  }
+  f.jobs.swap (rest);
+  f.grouped = true;
+  f.chunks_per_frame = total;
+  f.gflags = gflags;
+  for (int pl = 0; pl < 3; pl++) {
+    f.ptrs.src[pl] = static_cast<const uint8_t *> (src->plane[pl]);
+    f.ptrs.dst[pl] = static_cast<uint8_t *> (dst->plane[pl]);
+    f.src_pitch[pl] = src->stride[pl];
+    f.dst_pitch[pl] = dst->stride[pl];
+    f.rect_off[pl] = f.prep ? f.prep->rect_off[pl] : 0;
+  }
+  f.ptrs.rects = f.prep ? f.prep->d_rects_all : nullptr;
+  f.ptrs.pad_ = 0;
+}
+
+bool
+group_accepts (const Group &g, const PendingFrame &f)
+{
+  const GroupParams &P = g.P;
+  if (g.kind != f.kind || P.n_frames >= (uint32_t) kMaxGroupFrames || P.n_bands != f.bands.size () ||
+      P.chunks_per_frame != f.chunks_per_frame || P.flags != f.gflags)
+    return false;
+  if (memcmp (P.src_pitch, f.src_pitch, sizeof P.src_pitch) || memcmp (P.dst_pitch, f.dst_pitch, sizeof P.dst_pitch) ||
+      memcmp (P.rect_off, f.rect_off, sizeof P.rect_off))
+    return false;
+  return memcmp (P.bands, f.bands.data (), f.bands.size () * sizeof (BandDesc)) == 0;
+}
+
+void
+group_start (Group &g, const PendingFrame &f)
+{
+  memset (&g.P, 0, sizeof g.P);
+  g.kind = f.kind;
+  g.P.n_bands = (uint32_t) f.bands.size ();
+  g.P.chunks_per_frame = f.chunks_per_frame;
+  g.P.cpf_magic = (uint32_t) (((1ull << 32) + f.chunks_per_frame - 1) / f.chunks_per_frame);
+  g.P.flags = f.gflags;
+  memcpy (g.P.src_pitch, f.src_pitch, sizeof g.P.src_pitch);
+  memcpy (g.P.dst_pitch, f.dst_pitch, sizeof g.P.dst_pitch);
+  memcpy (g.P.rect_off, f.rect_off, sizeof g.P.rect_off);
+  memcpy (g.P.bands, f.bands.data (), f.bands.size () * sizeof (BandDesc));
+}
+
 int
 slot_reserve (Ctx *c, TableSlot &s, size_t n)
 {
@@ -710,10 +823,26 @@ launch_pending (Ctx *c)
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
   std::vector<PlaneJob> by_kind[6];     /* PlaneKind x {byte-granular, fast} */
+  std::vector<Group> &groups = c->groups;
+  groups.clear ();
   std::vector<Prepared *> waited;
   for (PendingFrame &f : c->pending) {
     for (const PlaneJob &j : f.jobs)
       by_kind[f.kind * 2 + ((j.flags & JF_FAST) ? 1 : 0)].push_back (j);
+    if (f.grouped) {
+      Group *g = nullptr;
+      for (Group &o : groups)
+        if (group_accepts (o, f)) {
+          g = &o;
+          break;
+        }
+      if (!g) {
+        groups.emplace_back ();
+        g = &groups.back ();
+        group_start (*g, f);
+      }
+      g->P.frames[g->P.n_frames++] = f.ptrs;
+    }
     if (f.overlay)
       b.keep.push_back (f.overlay);
     if (f.prep && std::find (waited.begin (), waited.end (), f.prep) == waited.end ()) {
@@ -724,12 +853,21 @@ launch_pending (Ctx *c)
     c->stats.algorithmic_bytes += f.algo_bytes;
   }
   c->pending.clear ();
-  int n_kinds = 0;
+  size_t n_launches = groups.size ();
   for (int k = 0; k < 6; k++)
-    n_kinds += !by_kind[k].empty ();
-  if (c->profiling && n_kinds == 1) {
+    n_launches += !by_kind[k].empty ();
+  if (c->profiling && n_launches == 1) {
     CU (c, cudaEventCreate (&b.t0));
     CU (c, cudaEventCreate (&b.t1));
+  }
+  for (Group &g : groups) {
+    if (b.t0)
+      CU (c, cudaEventRecord (b.t0, c->blend_stream));
+    CU (c, launch_group (g.P, g.kind, c->blend_stream));
+    if (b.t1)
+      CU (c, cudaEventRecord (b.t1, c->blend_stream));
+    c->stats.launches++;
+    c->stats.group_launches++;
   }
   for (int k = 0; k < 6; k++) {
     if (by_kind[k].empty ())
@@ -982,6 +1120,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   const char *e;
   if ((e = getenv ("FLUC_TTMLBLEND_BATCH")))
     c->max_batch = (uint32_t) std::max (1, std::min (1024, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_GROUPS")))
+    c->use_groups = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))
     c->host_mode = std::max (0, std::min (2, atoi (e)));
   if ((e = getenv ("FLUC_TTMLBLEND_LINGER_US")))
@@ -1147,8 +1287,18 @@ fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat
     if ((rc = prepare_overlay (c, f.overlay.get (), fmt, W, H, &f.prep)))
       return rc;
   }
+  /* a buffer written twice in one batch would race: launch what is queued first */
+  for (const PendingFrame &p : c->pending)
+    if (p.dst0 == dst->plane[0]) {
+      if ((rc = launch_pending (c)))
+        return rc;
+      break;
+    }
   f.algo_bytes = build_jobs (fmt, W, H, frame_flags, src, dst, f.prep,
       src->plane[0] == dst->plane[0], f.jobs);
+  f.dst0 = dst->plane[0];
+  if (c->use_groups)
+    make_groupable (f, src, dst);
   f.ticket = ++c->next_ticket;
   if (ticket)
     *ticket = f.ticket;
@@ -1304,12 +1454,21 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
     f.overlay = ov;
     f.prep = prep;
     f.ticket = tk;
+    for (const PendingFrame &p : c->pending)
+      if (p.dst0 == zf.plane[0]) {
+        if ((rc = launch_pending (c)))
+          return rc;
+        break;
+      }
     f.algo_bytes = build_jobs (fmt, W, H, frame_flags, &zf, &zf, prep, true, f.jobs);
+    f.dst0 = zf.plane[0];
     for (const PlaneJob &j : f.jobs) {
       const uint64_t nb = (uint64_t) std::min (j.win_nv * 16, j.row_bytes - j.win_v0 * 16) * j.win_rows;
       c->stats.h2d_bytes += nb;
       c->stats.d2h_bytes += nb;
     }
+    if (c->use_groups)
+      make_groupable (f, &zf, &zf);
     if (c->pending.empty ())
       c->oldest_pending = std::chrono::steady_clock::now ();
     c->pending.push_back (std::move (f));

@@ -202,20 +202,25 @@ blend_with_rect (uint4 f, const RectRef *r, const RectGeom &g, int v, int y,
 
 /* Job fields a CTA keeps in registers while it works through the job. */
 struct JobRegs {
-  const PlaneJob *job;
   const uint8_t *src;
   uint8_t *dst;
+  const RectRef *rects;
+  unsigned long long rect_mask;
   int src_pitch, dst_pitch;
   int win_v0, win_y0;
   uint32_t win_nv, total_items, magic;
-  int cls;
+  int cls, one_rect, flags, row_bytes;
 };
 
 __device__ __forceinline__ JobRegs
 load_job (const PlaneJob *job)
 {
   JobRegs J;
-  J.job = job;
+  J.rects = ldg_ptr (&job->rects);
+  J.rect_mask = __ldg (&job->rect_mask);
+  J.one_rect = __ldg (&job->one_rect);
+  J.flags = __ldg (&job->flags);
+  J.row_bytes = __ldg (&job->row_bytes);
   J.src = ldg_ptr (&job->src);
   J.dst = ldg_ptr (&job->dst);
   J.src_pitch = __ldg (&job->src_pitch);
@@ -278,7 +283,7 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
       return;
     }
     if (J.cls == JC_ONE) {
-      const RectRef *r = ldg_ptr (&J.job->rects) + __ldg (&J.job->one_rect);
+      const RectRef *r = J.rects + J.one_rect;
       const RectGeom g = rect_geom (r);
       const int32_t pitch = __ldg (&r->pitch);
       const uint8_t *pa = ldg_ptr (&r->a);
@@ -304,7 +309,7 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
       } else {
         const uint32_t ga = (uint32_t) __ldg (&r->ga);
         const bool sp = __ldg (&r->src_premul) != 0;
-        const bool dp = (__ldg (&J.job->flags) & JF_DST_PREMUL) != 0;
+        const bool dp = (J.flags & JF_DST_PREMUL) != 0;
 #pragma unroll
         for (int k = 0; k < kUnroll; k++)
           if (act[k])
@@ -320,10 +325,10 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
   }
 
   /* JC_GENERAL, and every class of the byte-granular variant */
-  const RectRef *rects = ldg_ptr (&J.job->rects);
-  const unsigned long long mask = __ldg (&J.job->rect_mask);
-  const int flags = __ldg (&J.job->flags);
-  const int row_bytes = __ldg (&J.job->row_bytes);
+  const RectRef *rects = J.rects;
+  const unsigned long long mask = J.rect_mask;
+  const int flags = J.flags;
+  const int row_bytes = J.row_bytes;
   const bool inplace = (flags & JF_INPLACE) != 0;
   const bool dst_premul = (flags & JF_DST_PREMUL) != 0;
   const bool vec_ok = FAST || (flags & JF_VECTOR) != 0;
@@ -417,6 +422,52 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
   process_chunk<KIND, FAST> (J, chunk - __ldg (chunk_begin + (cnt - 1)));
 }
 
+/* The common case -- a batch of frames that share format, size, strides and
+ * cue layout (consecutive frames of a stream, or many streams with the same
+ * region boxes) -- needs no table in global memory at all: the band list is
+ * the same for every frame and only the plane pointers differ, so both fit in
+ * the kernel parameters (constant bank). A CTA finds its frame with one
+ * multiply, its band with a short scan of uniform compares, and issues its
+ * first frame load without a single dependent global load or barrier in
+ * front of it (the table search of the generic kernel above costs ~8 % of a
+ * streaming copy: tools/copybench.cu "+prologue"). */
+template <int KIND>
+__global__ void __launch_bounds__ (kThreads, TTMLBLEND_MIN_CTAS)
+ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
+{
+  const uint32_t q = P.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, P.lanes_magic);
+  const uint32_t r = blockIdx.x - q * P.lanes;
+  const uint32_t chunk = r * P.per_lane + q;
+  if (chunk >= P.total_chunks)
+    return;
+  const uint32_t frame = P.n_frames == 1u ? 0u : __umulhi (chunk, P.cpf_magic);
+  const uint32_t cif = chunk - frame * P.chunks_per_frame;
+  uint32_t b = 0;
+  for (uint32_t i = 1; i < P.n_bands; i++)
+    b += cif >= P.bands[i].chunk_begin ? 1u : 0u;
+  const BandDesc &B = P.bands[b];
+  const FramePtrs &F = P.frames[frame];
+  const int pl = B.plane;
+
+  JobRegs J;
+  J.src = F.src[pl];
+  J.dst = F.dst[pl];
+  J.rects = F.rects + P.rect_off[pl];
+  J.rect_mask = ((unsigned long long) B.rect_mask_hi << 32) | B.rect_mask_lo;
+  J.src_pitch = P.src_pitch[pl];
+  J.dst_pitch = P.dst_pitch[pl];
+  J.win_v0 = B.win_v0;
+  J.win_y0 = B.win_y0;
+  J.win_nv = (uint32_t) B.win_nv;
+  J.total_items = (uint32_t) B.win_nv * (uint32_t) B.win_rows;
+  J.magic = B.div_magic;
+  J.cls = B.cls;
+  J.one_rect = B.one_rect;
+  J.flags = P.flags;
+  J.row_bytes = 0;              /* FAST: never read */
+  process_chunk<KIND, true> (J, cif - B.chunk_begin);
+}
+
 /* Number of interleaved streams the chunk list is walked in (env
  * FLUC_TTMLBLEND_LANES, default 61: a prime, so that lane starts do not line
  * up with the frame structure of a batch). 1 = list order. */
@@ -454,6 +505,37 @@ launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_
   else
     ttmlblend_blend_kernel<KIND, false><<<grid, kThreads, 0, stream>>> (d_jobs,
         d_chunk_begin, n_jobs, total_chunks, lanes, per_lane, magic);
+  return cudaGetLastError ();
+}
+
+cudaError_t
+launch_group (GroupParams &P, int kind, cudaStream_t stream)
+{
+  P.total_chunks = P.n_frames * P.chunks_per_frame;
+  if (P.total_chunks == 0)
+    return cudaSuccess;
+  uint32_t lanes = interleave_lanes ();
+  if (P.total_chunks < lanes * 8u)
+    lanes = 1;
+  P.lanes = lanes;
+  P.per_lane = (P.total_chunks + lanes - 1) / lanes;
+  const uint32_t grid = lanes * P.per_lane;
+  if ((unsigned long long) grid * lanes >= (1ull << 32))
+    return cudaErrorInvalidValue;
+  P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
+  switch (kind) {
+    case PK_PLANE8:
+      ttmlblend_group_kernel<PK_PLANE8><<<grid, kThreads, 0, stream>>> (P);
+      break;
+    case PK_PACKED_A0:
+      ttmlblend_group_kernel<PK_PACKED_A0><<<grid, kThreads, 0, stream>>> (P);
+      break;
+    case PK_PACKED_A3:
+      ttmlblend_group_kernel<PK_PACKED_A3><<<grid, kThreads, 0, stream>>> (P);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
   return cudaGetLastError ();
 }
 

@@ -80,6 +80,39 @@ struct alignas (16) PlaneJob {
   int32_t plane;        /* host-side bookkeeping: plane index of the frame */
 };
 
+/* ---- group launch: frames that share geometry, tables in kernel parameters ---- */
+constexpr int kMaxGroupFrames = 40;
+constexpr int kMaxGroupBands = 24;
+
+struct BandDesc {             /* one band of rows of one plane, same for every frame */
+  uint32_t chunk_begin;       /* first chunk of the band inside a frame's chunk list */
+  int32_t plane;
+  int32_t win_v0, win_nv, win_y0, win_rows;
+  uint32_t div_magic;
+  int32_t cls;                /* JobClass */
+  int32_t one_rect;           /* JC_ONE: index into the plane's rectangle table */
+  uint32_t rect_mask_lo, rect_mask_hi;
+  uint32_t n_chunks;
+};
+
+struct FramePtrs {
+  const uint8_t *src[3];
+  uint8_t *dst[3];
+  const RectRef *rects;       /* the frame's prepared overlay: all planes' tables, contiguous */
+  uint64_t pad_;
+};
+
+struct GroupParams {
+  uint32_t n_frames, n_bands, chunks_per_frame, cpf_magic;
+  uint32_t total_chunks, lanes, per_lane, lanes_magic;
+  int32_t src_pitch[3], dst_pitch[3];
+  int32_t rect_off[3];        /* first RectRef of plane p inside FramePtrs::rects */
+  int32_t flags;              /* JobFlags shared by the group */
+  BandDesc bands[kMaxGroupBands];
+  FramePtrs frames[kMaxGroupFrames];
+};
+static_assert (sizeof (GroupParams) <= 4096, "kernel parameters must stay within 4 KB");
+
 constexpr int kThreads = 256;
 #ifndef TTMLBLEND_UNROLL
 #define TTMLBLEND_UNROLL 4
@@ -120,6 +153,8 @@ enum PrepareMode : int32_t {
  * job 16-byte aligned with row_bytes % 16 == 0) or byte-granular. */
 cudaError_t launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin,
     int n_jobs, uint32_t total_chunks, int kind, bool fast, cudaStream_t stream);
+/* Fills in total_chunks and the interleave fields of P, then launches. */
+cudaError_t launch_group (GroupParams &P, int kind, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);

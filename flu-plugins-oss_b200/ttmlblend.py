@@ -54,7 +54,7 @@ class Frame(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("frames_blended", C.c_uint64), ("launches", C.c_uint64),
-                ("prepare_launches", C.c_uint64), ("overlays_set", C.c_uint64),
+                ("group_launches", C.c_uint64), ("prepare_launches", C.c_uint64), ("overlays_set", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("kernel_ms", C.c_double),
                 ("kernel_ms_launches", C.c_uint64)]

@@ -113,6 +113,7 @@ typedef struct {
 typedef struct {
   uint64_t frames_blended;      /* frames that went through a blend launch */
   uint64_t launches;            /* blend kernel launches */
+  uint64_t group_launches;      /* of which: group launches (tables in kernel parameters) */
   uint64_t prepare_launches;    /* overlay prepare kernel launches */
   uint64_t overlays_set;
   uint64_t algorithmic_bytes;   /* 2*frame bytes (or touched bytes in place) + 4*overlay px */

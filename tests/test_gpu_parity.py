@@ -211,7 +211,9 @@ def test_mixed_batch_many_streams_one_launch(ctx):
         tickets = [ctx.submit(100 + i, fmt, w, h, src.c, dst.c)
                    for i, (fmt, w, h, _, _, src, dst) in enumerate(jobs)]
         ctx.wait(tickets[-1])
-        assert 3 <= ctx.stats()["launches"] - before <= 6   # one per plane kind (x fast / byte variant)
+        st = ctx.stats()
+        assert st["launches"] - before >= 3     # at least one per plane kind
+        assert st["group_launches"] > 0         # same-geometry frames share a group launch
         for fmt, w, h, planes, rects, src, dst in jobs:
             assert_planes_equal(dst.download(), oracle_blend(fmt, w, h, copy_planes(planes), rects), fmt)
             src.release()

@@ -29,6 +29,40 @@ __global__ void __launch_bounds__(256) copy_chunk(const uint4* __restrict__ s, u
   for (int k = 0; k < U; k++) { size_t i = base + (size_t)k * 256; if (i < n) { if (MODE == 3) st_cs(d + i, v[k]); else if (MODE == 2) d[i] = v[k]; else st_na(d + i, v[k]); } }
 }
 
+// occupancy-limited copy: dynamic smem only there to cap CTAs/SM
+template <int U>
+__global__ void __launch_bounds__(256) copy_occ(const uint4* __restrict__ s, uint4* __restrict__ d, size_t n) {
+  extern __shared__ uint8_t dummy[];
+  size_t base = (size_t)blockIdx.x * (256 * U) + threadIdx.x;
+  uint4 v[U];
+#pragma unroll
+  for (int k = 0; k < U; k++) { size_t i = base + (size_t)k * 256; if (i < n) v[k] = ld_na(s + i); }
+#pragma unroll
+  for (int k = 0; k < U; k++) { size_t i = base + (size_t)k * 256; if (i < n) st_na(d + i, v[k]); }
+  if (n == 1) dummy[threadIdx.x] = 0;
+}
+
+// copy with the blend kernel's prologue: table search (barrier) + dependent job-field loads
+struct FakeJob { const uint4* s; uint4* d; unsigned begin; unsigned pad; };
+template <int U>
+__global__ void __launch_bounds__(256) copy_prologue(const FakeJob* __restrict__ jobs, const unsigned* __restrict__ begins, int n_jobs, size_t n) {
+  extern __shared__ uint8_t dummy[];
+  unsigned chunk = blockIdx.x;
+  int cnt = 0;
+  for (int b = 0; b < n_jobs; b += 256) { int j = b + threadIdx.x; cnt += __syncthreads_count(j < n_jobs && __ldg(begins + j) <= chunk); }
+  const FakeJob* job = jobs + (cnt - 1);
+  const uint4* s = (const uint4*)__ldg((const unsigned long long*)&job->s);
+  uint4* d = (uint4*)__ldg((const unsigned long long*)&job->d);
+  unsigned local = chunk - __ldg(&job->begin);
+  size_t base = (size_t)local * (256 * U) + threadIdx.x;
+  uint4 v[U];
+#pragma unroll
+  for (int k = 0; k < U; k++) { size_t i = base + (size_t)k * 256; v[k] = ld_na(s + i); }
+#pragma unroll
+  for (int k = 0; k < U; k++) { size_t i = base + (size_t)k * 256; st_na(d + i, v[k]); }
+  if (n == 1) dummy[threadIdx.x] = 0;
+}
+
 template <int U>
 __global__ void __launch_bounds__(256) copy_persist(const uint4* __restrict__ s, uint4* __restrict__ d, size_t n) {
   const size_t chunks = (n + 256 * U - 1) / (256 * U);
@@ -143,7 +177,31 @@ int main(int argc, char** argv) {
   rep("chunk U8 ld.na/st.na", timeit([&] { copy_chunk<8, 0><<<(n + 2047) / 2048, 256>>>((uint4*)s, (uint4*)d, n); }));
   rep("chunk U2 ld.na/st.na", timeit([&] { copy_chunk<2, 0><<<(n + 511) / 512, 256>>>((uint4*)s, (uint4*)d, n); }));
   rep("chunk U1 ld.na/st.na", timeit([&] { copy_chunk<1, 0><<<(n + 255) / 256, 256>>>((uint4*)s, (uint4*)d, n); }));
-  for (int per : {2, 4, 6, 8}) {
+  for (int occ : {2, 3, 4, 5, 6, 8}) {
+    int smem = 227 * 1024 / occ - 1024; smem = smem / 1024 * 1024;
+    CK(cudaFuncSetAttribute(copy_occ<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(copy_occ<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    char nm[64]; snprintf(nm, sizeof nm, "chunk U4 capped %d CTA/SM", occ);
+    rep(nm, timeit([&] { copy_occ<4><<<(n + 1023) / 1024, 256, smem>>>((uint4*)s, (uint4*)d, n); }));
+    snprintf(nm, sizeof nm, "chunk U2 capped %d CTA/SM", occ);
+    rep(nm, timeit([&] { copy_occ<2><<<(n + 511) / 512, 256, smem>>>((uint4*)s, (uint4*)d, n); }));
+  }
+  {
+    // 320 jobs of equal size, like 32 frames x 10 bands
+    int n_jobs = 320; size_t chunks = n / 1024, per = chunks / n_jobs;
+    std::vector<FakeJob> hj(n_jobs); std::vector<unsigned> hb(n_jobs);
+    for (int j = 0; j < n_jobs; j++) { hj[j].s = (const uint4*)s + (size_t)j * per * 1024; hj[j].d = (uint4*)d + (size_t)j * per * 1024; hj[j].begin = hb[j] = (unsigned)(j * per); }
+    FakeJob* dj; unsigned* db; CK(cudaMalloc(&dj, n_jobs * sizeof(FakeJob))); CK(cudaMalloc(&db, n_jobs * 4));
+    CK(cudaMemcpy(dj, hj.data(), n_jobs * sizeof(FakeJob), cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, hb.data(), n_jobs * 4, cudaMemcpyHostToDevice));
+    for (int occ : {4, 8}) {
+      int smem = 227 * 1024 / occ - 1024; smem = smem / 1024 * 1024;
+      CK(cudaFuncSetAttribute(copy_prologue<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      char nm[64]; snprintf(nm, sizeof nm, "chunk U4 +prologue %d CTA/SM", occ);
+      float ms = timeit([&] { copy_prologue<4><<<(unsigned)(per * n_jobs), 256, smem>>>(dj, db, n_jobs, n); });
+      printf("%-34s %8.4f ms  %8.1f GB/s (read+write)\n", nm, ms, 2.0 * per * n_jobs * 16384 / ms / 1e6);
+    }
+  }
+  for (int per : {2, 4}) {
     char nm[64]; snprintf(nm, sizeof nm, "persist U4 %d CTA/SM", per);
     rep(nm, timeit([&] { copy_persist<4><<<148 * per, 256>>>((uint4*)s, (uint4*)d, n); }));
     snprintf(nm, sizeof nm, "persist U8 %d CTA/SM", per);
