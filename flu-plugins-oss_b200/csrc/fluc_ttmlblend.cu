@@ -132,7 +132,9 @@ struct Prepared {
 
 struct Overlay {
   Ctx *ctx = nullptr;
-  std::vector<RawRect> rects;
+  std::vector<RawRect> rects;          /* what gets prepared: cropped to non-transparent pixels */
+  std::vector<void *> raw_allocs;      /* device copies the rects point into */
+  std::vector<FlucTtmlBlendRect> declared;   /* rectangles as handed in (algorithmic bytes) */
   std::vector<std::unique_ptr<Prepared>> prepared;
   ~Overlay ();
 };
@@ -222,6 +224,7 @@ struct Ctx {
 
   uint32_t max_batch = 32, linger_us = 200;
   int host_mode = HM_ZEROCOPY;
+  bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
   bool profiling = false;
   std::thread sched;
@@ -301,9 +304,8 @@ free_deferred (Ctx *c, const std::vector<void *> &ptrs)
 Overlay::~Overlay ()
 {
   std::vector<void *> ptrs;
-  for (auto &r : rects)
-    if (r.dev)
-      ptrs.push_back (r.dev);
+  for (void *a : raw_allocs)
+    ptrs.push_back (a);
   for (auto &p : prepared) {
     for (void *a : p->allocs)
       ptrs.push_back (a);
@@ -343,13 +345,17 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
   const int kind = plane_kind (format);
   const int n_planes = format_planes (format);
 
+  for (const FlucTtmlBlendRect &d : ov->declared) {
+    const int w = std::min (d.x + d.w, W) - d.x, h = std::min (d.y + d.h, H) - d.y;
+    if (w > 0 && h > 0)
+      P->overlay_px += (uint64_t) w * (uint64_t) h;
+  }
   for (const RawRect &rr : ov->rects) {
     /* gst_video_blend clipping: rr is already clipped at the left/top */
     const int cx0 = rr.x, cy0 = rr.y;
     const int cx1 = std::min (rr.x + rr.w, W), cy1 = std::min (rr.y + rr.h, H);
     if (cx1 <= cx0 || cy1 <= cy0)
       continue;
-    P->overlay_px += (uint64_t) (cx1 - cx0) * (uint64_t) (cy1 - cy0);
     if (rr.ga == 0)
       continue;                 /* asrc == 0 everywhere: blends nothing */
 
@@ -966,11 +972,50 @@ disjoint_cover (const std::vector<FlucTtmlBlendRect> &in)
   return out;
 }
 
+/* Cuts a rectangle down to where it is not transparent: runs of non-empty
+ * rows (text lines, boxes) become separate sub-rectangles, each as wide as its
+ * outermost non-transparent pixels. Pixels with alpha 0 never change the frame
+ * (BLENDSPEC section 2, `continue`), so dropping them is exact; what it buys is
+ * that ttmlrender's frame-sized, mostly empty image costs overlay reads, ALU
+ * work and -- for host frames -- PCIe traffic only where there is a cue. */
+void
+crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, std::vector<FlucTtmlBlendRect> &out)
+{
+  struct Run { int y0, y1, x0, x1; };
+  std::vector<Run> runs;
+  for (int y = 0; y < (int) spans.size (); y++) {
+    if (spans[y].y < spans[y].x)
+      continue;
+    if (!runs.empty () && y - runs.back ().y1 < min_gap) {
+      Run &r = runs.back ();
+      r.y1 = y + 1;
+      r.x0 = std::min (r.x0, spans[y].x);
+      r.x1 = std::max (r.x1, spans[y].y + 1);
+    } else {
+      runs.push_back ({ y, y + 1, spans[y].x, spans[y].y + 1 });
+    }
+  }
+  while (runs.size () > max_runs) {
+    size_t best = 0;
+    for (size_t i = 1; i + 1 < runs.size (); i++)
+      if (runs[i + 1].y0 - runs[i].y1 < runs[best + 1].y0 - runs[best].y1)
+        best = i;
+    runs[best].y1 = runs[best + 1].y1;
+    runs[best].x0 = std::min (runs[best].x0, runs[best + 1].x0);
+    runs[best].x1 = std::max (runs[best].x1, runs[best + 1].x1);
+    runs.erase (runs.begin () + best + 1);
+  }
+  for (const Run &r : runs)
+    out.push_back ({ r.x0, r.y0, r.x1 - r.x0, r.y1 - r.y0 });
+}
+
 int
 overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n)
 {
   std::shared_ptr<Overlay> ov (new Overlay ());
   ov->ctx = c;
+  struct Up { RawRect rr; int2 *d_spans; std::vector<int2> spans; };
+  std::vector<Up> ups;
   for (uint32_t i = 0; i < n; i++) {
     const FlucTtmlBlendRectangle &r = rects[i];
     if (!r.pixels || r.width <= 0 || r.height <= 0 || r.stride < r.width * 4)
@@ -979,7 +1024,8 @@ overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, u
     const int xoff = r.x < 0 ? -r.x : 0, yoff = r.y < 0 ? -r.y : 0;
     if (xoff >= r.width || yoff >= r.height)
       continue;
-    RawRect rr;
+    Up u;
+    RawRect &rr = u.rr;
     rr.w = r.width - xoff;
     rr.h = r.height - yoff;
     rr.x = r.x + xoff;
@@ -988,16 +1034,49 @@ overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, u
     rr.ga = std::max (0, std::min (255, rr.ga));
     rr.premul = (r.flags & FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA) != 0;
     rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
+    ov->declared.push_back ({ rr.x, rr.y, rr.w, rr.h });
     void *d = nullptr;
     CU (c, cudaMallocAsync (&d, (size_t) rr.pitch * rr.h, c->up_stream));
+    ov->raw_allocs.push_back (d);
     rr.dev = static_cast<uint8_t *> (d);
-    ov->rects.push_back (rr);
     CU (c, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
             r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
     c->stats.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+    u.d_spans = nullptr;
+    if (c->autocrop) {
+      void *sp = nullptr;
+      CU (c, cudaMallocAsync (&sp, (size_t) rr.h * sizeof (int2), c->up_stream));
+      u.d_spans = static_cast<int2 *> (sp);
+      u.spans.resize (rr.h);
+      CU (c, launch_rowspan (rr.dev, rr.pitch, rr.w, rr.h, u.d_spans, c->up_stream));
+      CU (c, cudaMemcpyAsync (u.spans.data (), u.d_spans, (size_t) rr.h * sizeof (int2),
+              cudaMemcpyDeviceToHost, c->up_stream));
+      CU (c, cudaFreeAsync (sp, c->up_stream));
+    }
+    ups.push_back (std::move (u));
   }
-  /* the caller's pixels must be consumed before we return */
+  /* the caller's pixels must be consumed (and the row spans back) before we return */
   CU (c, cudaStreamSynchronize (c->up_stream));
+  for (Up &u : ups) {
+    if (!c->autocrop) {
+      ov->rects.push_back (u.rr);
+      continue;
+    }
+    std::vector<FlucTtmlBlendRect> subs;
+    /* at most 8 runs per rectangle, and never more sub-rectangles than the 64-bit band masks hold */
+    crop_runs (u.spans, 16, std::max<size_t> (1, std::min<size_t> (8, FLUC_TTMLBLEND_MAX_RECTANGLES / ups.size ())), subs);
+    for (const FlucTtmlBlendRect &s : subs) {
+      RawRect q = u.rr;
+      q.dev = u.rr.dev + (size_t) s.y * u.rr.pitch + (size_t) s.x * 4;
+      q.x = u.rr.x + s.x;
+      q.y = u.rr.y + s.y;
+      q.w = s.w;
+      q.h = s.h;
+      ov->rects.push_back (q);
+    }
+  }
+  if (ov->rects.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
   c->overlays[stream] = ov;       /* frames already queued keep the old one */
   c->stats.overlays_set++;
   return 0;
@@ -1120,6 +1199,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   const char *e;
   if ((e = getenv ("FLUC_TTMLBLEND_BATCH")))
     c->max_batch = (uint32_t) std::max (1, std::min (1024, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_AUTOCROP")))
+    c->autocrop = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_GROUPS")))
     c->use_groups = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))

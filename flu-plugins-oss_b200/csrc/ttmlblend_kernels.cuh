@@ -81,8 +81,8 @@ struct alignas (16) PlaneJob {
 };
 
 /* ---- group launch: frames that share geometry, tables in kernel parameters ---- */
-constexpr int kMaxGroupFrames = 40;
-constexpr int kMaxGroupBands = 24;
+constexpr int kMaxGroupFrames = 64;
+constexpr int kMaxGroupBands = 64;
 
 struct BandDesc {             /* one band of rows of one plane, same for every frame */
   uint32_t chunk_begin;       /* first chunk of the band inside a frame's chunk list */
@@ -111,7 +111,9 @@ struct GroupParams {
   BandDesc bands[kMaxGroupBands];
   FramePtrs frames[kMaxGroupFrames];
 };
-static_assert (sizeof (GroupParams) <= 4096, "kernel parameters must stay within 4 KB");
+/* > 4 KB of kernel parameters needs CUDA >= 12.1 and driver >= R530 (limit 32764 B), which
+ * every sm_100a system has */
+static_assert (sizeof (GroupParams) <= 16384, "kernel parameters");
 
 constexpr int kThreads = 256;
 #ifndef TTMLBLEND_UNROLL
@@ -158,6 +160,8 @@ cudaError_t launch_group (GroupParams &P, int kind, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);
+/* spans[y] = first / last x of row y with alpha != 0, (w, -1) for an empty row. */
+cudaError_t launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaStream_t stream);
 
 }  // namespace tb
 #endif

@@ -307,3 +307,55 @@ def test_stats_count_algorithmic_bytes(ctx):
     assert st["algorithmic_bytes"] == wl.algorithmic_bytes(cfg) == 3207168
     src.release()
     dst.release()
+
+
+def _text_like_overlay(w, h, seed):
+    """Frame-sized image as ttmlrender emits it for transparent-background regions: a few
+    lines of glyph boxes, everything else alpha 0."""
+    r = np.random.default_rng(seed)
+    ov = np.zeros((h, w, 4), dtype=np.uint8)
+    for (y0, y1, x0, x1) in ((h // 8, h // 8 + 14, w // 4, w // 4 + w // 3),
+                             (h // 8 + 20, h // 8 + 34, w // 5, w // 5 + w // 2),
+                             (h - 60, h - 44, 17, w - 23), (h - 38, h - 22, w // 3, w - 101)):
+        a = r.integers(1, 256, size=(y1 - y0, x1 - x0), dtype=np.uint8)
+        a[r.random(a.shape) < 0.3] = 0
+        c = r.integers(0, 256, size=(y1 - y0, x1 - x0, 3), dtype=np.uint8)
+        ov[y0:y1, x0:x1, :3] = (c.astype(np.uint32) * a[:, :, None] // 255).astype(np.uint8)
+        ov[y0:y1, x0:x1, 3] = a
+    return ov
+
+
+@pytest.mark.parametrize("fmt", ("I420", "NV12", "RGBA", "AYUV"))
+def test_autocrop_of_sparse_frame_sized_overlay(ctx, fmt):
+    """The element hands over ttmlrender's whole W x H image (no region boxes). The overlay
+    cache crops it to the runs of non-transparent rows; results stay bit-exact and the
+    host-frame path moves only those rows over PCIe."""
+    w, h = 640, 360
+    ov = _text_like_overlay(w, h, 21)
+    planes = random_frame(fmt, w, h, 22)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), oracle.ttmlrender_rectangles(ov))
+    for mode in MODES:
+        got = gpu_blend(ctx, fmt, w, h, planes, overlay=ov, regions=(), mode=mode, stream=77)
+        assert_planes_equal(got, want, f"{fmt} autocrop {mode}")
+    pinned = ctx.acquire(fmt, w, h, on_host=True)
+    for d, s in zip(pinned.host_planes(), planes):
+        d[...] = s
+    ctx.sync()
+    ctx.stats_reset()
+    ctx.wait(ctx.blend_host_frame(77, fmt, w, h, pinned.c))
+    st = ctx.stats()
+    frame_bytes = sum(p.size for p in planes)
+    assert 0 < st["h2d_bytes"] < 0.35 * frame_bytes, (st["h2d_bytes"], frame_bytes)
+    assert st["h2d_bytes"] == st["d2h_bytes"]
+    assert_planes_equal([np.array(x) for x in pinned.host_planes()], want, "pinned autocrop")
+    pinned.release()
+
+
+def test_fully_transparent_overlay_moves_nothing(ctx):
+    w, h = 320, 180
+    ov = np.zeros((h, w, 4), dtype=np.uint8)
+    ov[:, :, :3] = 7                      # colour without alpha: still transparent
+    planes = random_frame("NV12", w, h, 23)
+    for mode in MODES:
+        got = gpu_blend(ctx, "NV12", w, h, planes, overlay=ov, mode=mode, stream=78)
+        assert_planes_equal(got, planes, f"transparent {mode}")
