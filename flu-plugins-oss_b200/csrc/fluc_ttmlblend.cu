@@ -31,6 +31,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 using namespace tb;
@@ -128,6 +129,7 @@ struct Prepared {
   int32_t rect_off[3] = { 0, 0, 0 };   /* first entry of plane p in d_rects_all */
   uint64_t overlay_px = 0;             /* sum of clipped w*h */
   cudaEvent_t ready = nullptr;
+  bool blend_waited = false;           /* blend stream already ordered after `ready` */
 };
 
 struct Overlay {
@@ -215,6 +217,8 @@ struct Ctx {
 
   std::vector<PendingFrame> pending;
   std::vector<Group> groups;           /* scratch of launch_pending */
+  std::unordered_set<const void *> pending_dst;   /* destination buffers queued in `pending` */
+  std::vector<cudaEvent_t> timing_pool;
   std::chrono::steady_clock::time_point oldest_pending;
   uint64_t next_ticket = 0, launched_ticket = 0, done_ticket = 0;
   std::deque<Batch> batches;
@@ -810,8 +814,8 @@ reap_batches (Ctx *c)
         c->stats.kernel_ms += ms;
         c->stats.kernel_ms_launches++;
       }
-      cudaEventDestroy (b.t0);
-      cudaEventDestroy (b.t1);
+      c->timing_pool.push_back (b.t0);
+      c->timing_pool.push_back (b.t1);
     }
     c->done_ticket = b.last_ticket;
     c->event_pool.push_back (b.done);
@@ -831,7 +835,6 @@ launch_pending (Ctx *c)
   std::vector<PlaneJob> by_kind[6];     /* PlaneKind x {byte-granular, fast} */
   std::vector<Group> &groups = c->groups;
   groups.clear ();
-  std::vector<Prepared *> waited;
   for (PendingFrame &f : c->pending) {
     for (const PlaneJob &j : f.jobs)
       by_kind[f.kind * 2 + ((j.flags & JF_FAST) ? 1 : 0)].push_back (j);
@@ -851,20 +854,28 @@ launch_pending (Ctx *c)
     }
     if (f.overlay)
       b.keep.push_back (f.overlay);
-    if (f.prep && std::find (waited.begin (), waited.end (), f.prep) == waited.end ()) {
-      waited.push_back (f.prep);
+    if (f.prep && !f.prep->blend_waited) {
+      /* once per prepared overlay: later launches follow in stream order */
+      f.prep->blend_waited = true;
       CU (c, cudaStreamWaitEvent (c->blend_stream, f.prep->ready, 0));
     }
     c->stats.frames_blended++;
     c->stats.algorithmic_bytes += f.algo_bytes;
   }
   c->pending.clear ();
+  c->pending_dst.clear ();
   size_t n_launches = groups.size ();
   for (int k = 0; k < 6; k++)
     n_launches += !by_kind[k].empty ();
   if (c->profiling && n_launches == 1) {
-    CU (c, cudaEventCreate (&b.t0));
-    CU (c, cudaEventCreate (&b.t1));
+    for (cudaEvent_t *e : { &b.t0, &b.t1 }) {
+      if (!c->timing_pool.empty ()) {
+        *e = c->timing_pool.back ();
+        c->timing_pool.pop_back ();
+      } else {
+        CU (c, cudaEventCreate (e));
+      }
+    }
   }
   for (Group &g : groups) {
     if (b.t0)
@@ -906,8 +917,10 @@ scheduler_main (Ctx *c)
     if (std::chrono::steady_clock::now () >= deadline) {
       if (!c->sticky)
         launch_pending (c);
-      else
+      else {
         c->pending.clear ();
+        c->pending_dst.clear ();
+      }
     } else {
       c->cv.wait_until (lk, deadline);
     }
@@ -1243,6 +1256,8 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
     cudaStreamSynchronize (c->reaper);
     for (auto e : c->event_pool)
       cudaEventDestroy (e);
+    for (auto e : c->timing_pool)
+      cudaEventDestroy (e);
     auto free_slot = [](TableSlot &s) {
       if (s.h_jobs) cudaFreeHost (s.h_jobs);
       if (s.h_begin) cudaFreeHost (s.h_begin);
@@ -1350,12 +1365,10 @@ fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream)
 
 /* ---- device-resident frames ------------------------------------------ */
 
-int
-fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
-    int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
-    const FlucTtmlBlendFrame *dst, uint64_t *ticket)
+static int
+submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst, uint64_t *ticket)
 {
-  ENTER (thiz);
   int rc;
   if ((rc = check_frame (fmt, W, H, src)) || (rc = check_frame (fmt, W, H, dst)))
     return rc;
@@ -1369,12 +1382,8 @@ fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat
       return rc;
   }
   /* a buffer written twice in one batch would race: launch what is queued first */
-  for (const PendingFrame &p : c->pending)
-    if (p.dst0 == dst->plane[0]) {
-      if ((rc = launch_pending (c)))
-        return rc;
-      break;
-    }
+  if (c->pending_dst.count (dst->plane[0]) && (rc = launch_pending (c)))
+    return rc;
   f.algo_bytes = build_jobs (fmt, W, H, frame_flags, src, dst, f.prep,
       src->plane[0] == dst->plane[0], f.jobs);
   f.dst0 = dst->plane[0];
@@ -1385,10 +1394,40 @@ fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat
     *ticket = f.ticket;
   if (c->pending.empty ())
     c->oldest_pending = std::chrono::steady_clock::now ();
+  c->pending_dst.insert (f.dst0);
   c->pending.push_back (std::move (f));
   if (c->pending.size () >= c->max_batch)
     return launch_pending (c);
-  if (c->linger_us)
+  return 0;
+}
+
+int
+fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
+    int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
+    const FlucTtmlBlendFrame *dst, uint64_t *ticket)
+{
+  ENTER (thiz);
+  int rc = submit_locked (c, stream, fmt, W, H, frame_flags, src, dst, ticket);
+  if (rc == 0 && c->linger_us && !c->pending.empty ())
+    c->cv.notify_all ();
+  return rc;
+}
+
+int
+fluc_ttmlblend_submit_many (FlucTtmlBlend *thiz, uint32_t n, const uint32_t *streams,
+    FlucTtmlBlendFormat fmt, int32_t W, int32_t H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *srcs, const FlucTtmlBlendFrame *dsts, uint64_t *tickets)
+{
+  ENTER (thiz);
+  if (n && (!streams || !srcs || !dsts))
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < n; i++) {
+    int rc = submit_locked (c, streams[i], fmt, W, H, frame_flags, &srcs[i], &dsts[i],
+        tickets ? &tickets[i] : nullptr);
+    if (rc)
+      return rc;
+  }
+  if (c->linger_us && !c->pending.empty ())
     c->cv.notify_all ();
   return 0;
 }
@@ -1535,14 +1574,11 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
     f.overlay = ov;
     f.prep = prep;
     f.ticket = tk;
-    for (const PendingFrame &p : c->pending)
-      if (p.dst0 == zf.plane[0]) {
-        if ((rc = launch_pending (c)))
-          return rc;
-        break;
-      }
+    if (c->pending_dst.count (zf.plane[0]) && (rc = launch_pending (c)))
+      return rc;
     f.algo_bytes = build_jobs (fmt, W, H, frame_flags, &zf, &zf, prep, true, f.jobs);
     f.dst0 = zf.plane[0];
+    c->pending_dst.insert (f.dst0);
     for (const PlaneJob &j : f.jobs) {
       const uint64_t nb = (uint64_t) std::min (j.win_nv * 16, j.row_bytes - j.win_v0 * 16) * j.win_rows;
       c->stats.h2d_bytes += nb;

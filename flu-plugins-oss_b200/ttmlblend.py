@@ -76,6 +76,9 @@ PROTOTYPES = {
     "fluc_ttmlblend_submit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
                                         C.c_uint32, C.POINTER(Frame), C.POINTER(Frame),
                                         C.POINTER(C.c_uint64)]),
+    "fluc_ttmlblend_submit_many": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_int,
+                                             C.c_int32, C.c_int32, C.c_uint32, C.POINTER(Frame),
+                                             C.POINTER(Frame), C.POINTER(C.c_uint64)]),
     "fluc_ttmlblend_flush": (C.c_int, [C.c_void_p]),
     "fluc_ttmlblend_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fluc_ttmlblend_sync": (C.c_int, [C.c_void_p]),
@@ -269,6 +272,24 @@ class TtmlBlend:
             self.h, stream, FORMATS[fmt], width, height, frame_flags, C.byref(src), C.byref(dst),
             C.byref(t)), "submit")
         return t.value
+
+    class Batch:
+        """Pre-marshalled arguments of submit_many (arrays of streams / frames / tickets)."""
+
+        def __init__(self, streams, fmt, width, height, srcs, dsts, frame_flags=0):
+            n = len(streams)
+            self.n, self.fmt, self.width, self.height, self.flags = n, FORMATS[fmt], width, height, frame_flags
+            self.streams = (C.c_uint32 * n)(*streams)
+            self.srcs = (Frame * n)(*srcs)
+            self.dsts = (Frame * n)(*dsts)
+            self.tickets = (C.c_uint64 * n)()
+
+    def submit_many(self, batch: "TtmlBlend.Batch"):
+        """One C call for a whole batch; returns the ticket array (ctypes)."""
+        self._check(self.lib.fluc_ttmlblend_submit_many(
+            self.h, batch.n, batch.streams, batch.fmt, batch.width, batch.height, batch.flags,
+            batch.srcs, batch.dsts, batch.tickets), "submit_many")
+        return batch.tickets
 
     def flush(self):
         self._check(self.lib.fluc_ttmlblend_flush(self.h), "flush")

@@ -157,6 +157,12 @@ FLUC_EXPORT int fluc_ttmlblend_submit (FlucTtmlBlend *thiz, uint32_t stream,
     FlucTtmlBlendFormat fmt, int32_t width, int32_t height, uint32_t frame_flags,
     const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst,
     uint64_t *ticket);
+/* The same for n frames of one geometry under a single lock (many streams, or
+ * consecutive frames of one): streams[i], srcs[i], dsts[i], tickets[i]. */
+FLUC_EXPORT int fluc_ttmlblend_submit_many (FlucTtmlBlend *thiz, uint32_t n,
+    const uint32_t *streams, FlucTtmlBlendFormat fmt, int32_t width, int32_t height,
+    uint32_t frame_flags, const FlucTtmlBlendFrame *srcs, const FlucTtmlBlendFrame *dsts,
+    uint64_t *tickets);
 FLUC_EXPORT int fluc_ttmlblend_flush (FlucTtmlBlend *thiz);
 FLUC_EXPORT int fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket);
 FLUC_EXPORT int fluc_ttmlblend_sync (FlucTtmlBlend *thiz);   /* flush + wait all */

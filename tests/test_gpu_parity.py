@@ -359,3 +359,37 @@ def test_fully_transparent_overlay_moves_nothing(ctx):
     for mode in MODES:
         got = gpu_blend(ctx, "NV12", w, h, planes, overlay=ov, mode=mode, stream=78)
         assert_planes_equal(got, planes, f"transparent {mode}")
+
+
+def test_submit_many_equals_submit(ctx):
+    """One call for a batch of frames of several streams == one submit per frame."""
+    w, h, fmt, n = 256, 144, "NV12", 12
+    ctx.set_batch(64, 0)
+    try:
+        rects = [[dict(pixels=random_overlay(128, 40, 800 + s), x=20 + 3 * s, y=60 + s)] for s in range(3)]
+        for s in range(3):
+            ctx.overlay_set_rectangles(600 + s, rects[s])
+        frames = [random_frame(fmt, w, h, 820 + i) for i in range(n)]
+        srcs = [ctx.acquire(fmt, w, h) for _ in range(n)]
+        dsts = [ctx.acquire(fmt, w, h) for _ in range(n)]
+        for s_, f in zip(srcs, frames):
+            s_.upload(f)
+        streams = [600 + (i % 3) for i in range(n)]
+        batch = ctx.Batch(streams, fmt, w, h, [s_.c for s_ in srcs], [d.c for d in dsts])
+        tickets = ctx.submit_many(batch)
+        assert len(set(tickets)) == n and all(t > 0 for t in tickets)
+        ctx.wait(max(tickets))
+        for i in range(n):
+            want = oracle_blend(fmt, w, h, copy_planes(frames[i]), rects[i % 3])
+            assert_planes_equal(dsts[i].download(), want, f"frame {i}")
+        # the same destination twice in one batch must not race: second one launches after the first
+        t0 = ctx.submit(600, fmt, w, h, srcs[0].c, dsts[0].c)
+        t1 = ctx.submit(601, fmt, w, h, dsts[0].c, dsts[0].c)     # in place on the first result
+        ctx.wait(t1)
+        step1 = oracle_blend(fmt, w, h, copy_planes(frames[0]), rects[0])
+        want = oracle_blend(fmt, w, h, step1, rects[1])
+        assert_planes_equal(dsts[0].download(), want, "same buffer twice")
+        for f in srcs + dsts:
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)
