@@ -145,7 +145,7 @@ def cpu_reference_setup(cfg, wl, n_frames):
     import ctypes as C
     arr = (oracle.RefFrame * n_frames)()
     for i in range(n_frames):
-        planes = [np.roll(p, i * 17, axis=1).copy() for p in base]
+        planes = [np.roll(p, i * 16, axis=1).copy() for p in base]
         keep.append(planes)
         arr[i] = oracle.make_frame(cfg.fmt, cfg.width, cfg.height, planes)
     rects = oracle.make_rectangles(oracle.ttmlrender_rectangles(ov))
@@ -258,7 +258,7 @@ def main():
     srcs = [ctx.acquire(fmt, W, H) for _ in range(batch)]
     dsts = [ctx.acquire(fmt, W, H) for _ in range(batch)]
     for i, s in enumerate(srcs):
-        s.upload([np.roll(p, i * 17, axis=1) for p in base])
+        s.upload([np.roll(p, i * 16, axis=1) for p in base])
     stream_id = stream_ids[0]
 
     tb_batch = ctx.Batch(stream_ids, fmt, W, H, [s.c for s in srcs], [d.c for d in dsts])
@@ -342,7 +342,7 @@ def main():
         hosts = [ctx.acquire(fmt, W, H, on_host=True) for _ in range(batch)]
         for i, hf in enumerate(hosts):
             for dstp, srcp in zip(hf.host_planes(), base):
-                dstp[...] = np.roll(srcp, i * 17, axis=1)
+                dstp[...] = np.roll(srcp, i * 16, axis=1)
         e2e_steps = max(3, min(args.steps, 100))
 
         def e2e_step():

@@ -83,19 +83,28 @@ div255 (uint32_t x)
 
 /* PLANE8: four destination bytes. Opaque destination, straight source:
  *   out = (Cs * asrc + Cd * (255 - asrc)) / 255        (OVER00, adst = 255)
- * asrc == 0 leaves Cd untouched by the same formula, like the `continue`. */
+ * asrc == 0 leaves Cd untouched by the same formula, like the `continue`.
+ * ~5.5 integer instructions per byte: the two products of a byte are one
+ * IDP.4A ((Cs, Cd, 0, 0) . (a, 255 - a, ., .)), and the truncating /255 runs
+ * on two 16-bit lanes at once, x / 255 == (x + 1 + (x >> 8)) >> 8 for
+ * x <= 65534 (numerators are <= 255 * 255). */
 __device__ __forceinline__ uint32_t
 blend4_plane8 (uint32_t f, uint32_t a, uint32_t c)
 {
-  uint32_t out = 0u;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const uint32_t ak = (a >> (8 * k)) & 0xffu;
-    const uint32_t ck = (c >> (8 * k)) & 0xffu;
-    const uint32_t fk = (f >> (8 * k)) & 0xffu;
-    out |= div255 (ck * ak + fk * (255u - ak)) << (8 * k);
-  }
-  return out;
+  const uint32_t na = ~a;                               /* 255 - a, bytewise */
+  const uint32_t cf01 = __byte_perm (c, f, 0x5140);     /* c0 f0 c1 f1 */
+  const uint32_t cf23 = __byte_perm (c, f, 0x7362);     /* c2 f2 c3 f3 */
+  const uint32_t an01 = __byte_perm (a, na, 0x5140);    /* a0 n0 a1 n1 */
+  const uint32_t an23 = __byte_perm (a, na, 0x7362);    /* a2 n2 a3 n3 */
+  const uint32_t n0 = __dp4a (cf01 & 0x0000ffffu, an01, 0u);
+  const uint32_t n1 = __dp4a (cf01 & 0xffff0000u, an01, 0u);
+  const uint32_t n2 = __dp4a (cf23 & 0x0000ffffu, an23, 0u);
+  const uint32_t n3 = __dp4a (cf23 & 0xffff0000u, an23, 0u);
+  uint32_t e = __byte_perm (n0, n2, 0x5410);            /* n0 | n2 << 16 */
+  uint32_t o = __byte_perm (n1, n3, 0x5410);            /* n1 | n3 << 16 */
+  e = e + ((e >> 8) & 0x00ff00ffu) + 0x00010001u;       /* quotients in bits 8-15, 24-31 */
+  o = o + ((o >> 8) & 0x00ff00ffu) + 0x00010001u;
+  return __byte_perm (e, o, 0x7351);                    /* q0 q1 q2 q3 */
 }
 
 __device__ __forceinline__ uint4
