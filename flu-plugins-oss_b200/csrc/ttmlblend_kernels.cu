@@ -477,22 +477,24 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   process_chunk<KIND, true> (J, cif - B.chunk_begin);
 }
 
-/* Number of interleaved streams the chunk list is walked in (env
- * FLUC_TTMLBLEND_LANES; 1 = list order, the default: the interleave bought
- * 3 % with the table kernel and costs 1 % with the group kernel; a prime such
- * as 61 keeps lane starts from lining up with the frame structure). */
+/* Number of interleaved streams the chunk list is walked in. Measured on the
+ * 4K configs: the packed kinds (more ALU work per blended vector) gain 3 %
+ * with 61 lanes, PLANE8 loses 2 % against list order, so the default follows
+ * the kind; FLUC_TTMLBLEND_LANES overrides both (1 = list order). A prime
+ * keeps lane starts from lining up with the frame structure of a batch. */
 static uint32_t
-interleave_lanes ()
+interleave_lanes (int kind)
 {
-  static uint32_t n = 0;
-  if (n == 0) {
+  static int env = -1;
+  if (env < 0) {
     const char *e = getenv ("FLUC_TTMLBLEND_LANES");
-    int v = e ? atoi (e) : 1;
-    if (v < 1) v = 1;
-    if (v > 4096) v = 4096;
-    n = (uint32_t) v;
+    env = e ? atoi (e) : 0;
+    if (env < 0) env = 0;
+    if (env > 4096) env = 4096;
   }
-  return n;
+  if (env)
+    return (uint32_t) env;
+  return kind == PK_PLANE8 ? 1u : 61u;
 }
 
 template <int KIND>
@@ -500,7 +502,7 @@ static cudaError_t
 launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_jobs,
     uint32_t total_chunks, bool fast, cudaStream_t stream)
 {
-  uint32_t lanes = interleave_lanes ();
+  uint32_t lanes = interleave_lanes (KIND);
   if (total_chunks < lanes * 8u)
     lanes = 1;
   const uint32_t per_lane = (total_chunks + lanes - 1) / lanes;
@@ -524,7 +526,7 @@ launch_group (GroupParams &P, int kind, cudaStream_t stream)
   P.total_chunks = P.n_frames * P.chunks_per_frame;
   if (P.total_chunks == 0)
     return cudaSuccess;
-  uint32_t lanes = interleave_lanes ();
+  uint32_t lanes = interleave_lanes (kind);
   if (P.total_chunks < lanes * 8u)
     lanes = 1;
   P.lanes = lanes;
