@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -1837,6 +1838,53 @@ fluc_ttmlblend_frame_download (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt, int
   if (rc)
     return rc;
   return frame_copy (c, fmt, W, H, dev_src, host_dst, cudaMemcpyDeviceToHost);
+}
+
+/* ---- outline blur (per cue, producer side) --------------------------- */
+
+int
+fluc_ttmlblend_blur_argb32 (FlucTtmlBlend *thiz, const uint8_t *src, int32_t w, int32_t h,
+    int32_t stride, int32_t radius, double sigma, uint8_t *dst, int32_t dst_stride)
+{
+  ENTER (thiz);
+  if (!src || !dst || w <= 0 || h <= 0 || stride < 4 * w || dst_stride < 4 * w || radius < 0 ||
+      radius > 64 || !(sigma > 0.0))
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  /* gst_ttml_blur_create_gaussian_kernel, /root/reference/plugins/ttml/gstttmlblur.c:28-67:
+   * G(x,y) = exp (-(x^2 + y^2) / (2 sigma^2)) / (2 pi sigma^2), normalised, 16.16 fixed */
+  const int size = 2 * radius + 1, n = size * size;
+  std::vector<double> tmp (n);
+  std::vector<int32_t> taps (n);
+  const double scale2 = 2.0 * sigma * sigma;
+  const double scale1 = 1.0 / (3.14159265358979323846 * scale2);
+  double sum = 0;
+  int i = 0;
+  for (int x = -radius; x <= radius; ++x)
+    for (int y = -radius; y <= radius; ++y, ++i) {
+      const double u = x * x, v = y * y;
+      tmp[i] = scale1 * exp (-(u + v) / scale2);
+      sum += tmp[i];
+    }
+  for (i = 0; i < n; ++i)
+    taps[i] = (int32_t) ((tmp[i] / sum) * 65536.0);       /* pixman_double_to_fixed */
+
+  const size_t pitch = align_up ((size_t) w * 4, 256);
+  void *d_src = nullptr, *d_dst = nullptr, *d_taps = nullptr;
+  CU (c, cudaMallocAsync (&d_src, pitch * h, c->up_stream));
+  CU (c, cudaMallocAsync (&d_dst, pitch * h, c->up_stream));
+  CU (c, cudaMallocAsync (&d_taps, (size_t) n * 4, c->up_stream));
+  CU (c, cudaMemcpy2DAsync (d_src, pitch, src, stride, (size_t) w * 4, h, cudaMemcpyHostToDevice, c->up_stream));
+  CU (c, cudaMemcpyAsync (d_taps, taps.data (), (size_t) n * 4, cudaMemcpyHostToDevice, c->up_stream));
+  CU (c, launch_blur (static_cast<uint8_t *> (d_src), w, h, (int) pitch, static_cast<int32_t *> (d_taps),
+          radius, static_cast<uint8_t *> (d_dst), (int) pitch, c->up_stream));
+  CU (c, cudaMemcpy2DAsync (dst, dst_stride, d_dst, pitch, (size_t) w * 4, h, cudaMemcpyDeviceToHost, c->up_stream));
+  CU (c, cudaFreeAsync (d_src, c->up_stream));
+  CU (c, cudaFreeAsync (d_dst, c->up_stream));
+  CU (c, cudaFreeAsync (d_taps, c->up_stream));
+  CU (c, cudaStreamSynchronize (c->up_stream));
+  c->stats.h2d_bytes += (uint64_t) w * 4 * h;
+  c->stats.d2h_bytes += (uint64_t) w * 4 * h;
+  return 0;
 }
 
 /* ---- observability --------------------------------------------------- */

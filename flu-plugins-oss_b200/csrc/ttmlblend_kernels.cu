@@ -759,6 +759,84 @@ launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaSt
 }
 
 /* ---------------------------------------------------------------------- */
+/* once per cue with a blurred textOutline: pixman-style 2-D convolution   */
+
+/* gst_ttml_blur_image_surface (/root/reference/plugins/ttml/gstttmlblur.c:72-110):
+ * a8r8g8b8 source with a (2r+1)^2 kernel of 16.16 fixed-point taps, pixels
+ * outside the image are transparent, result = CLIP ((sum + 0x8000) >> 16).
+ * 32 x 8 output pixels per CTA; the tile plus its halo and the taps sit in
+ * shared memory, one thread per output pixel, four channels per thread. */
+constexpr int kBlurTileW = 32, kBlurTileH = 8;
+
+__global__ void __launch_bounds__ (kBlurTileW * kBlurTileH)
+ttmlblend_blur_kernel (const uint8_t *__restrict__ src, int w, int h, int src_pitch,
+    const int32_t *__restrict__ taps, int radius, uint8_t *__restrict__ dst, int dst_pitch)
+{
+  extern __shared__ uint32_t blur_smem[];
+  const int size = 2 * radius + 1;
+  const int tw = kBlurTileW + 2 * radius, th = kBlurTileH + 2 * radius;
+  uint32_t *tile = blur_smem;
+  int32_t *s_taps = reinterpret_cast<int32_t *> (blur_smem + tw * th);
+  const int tid = threadIdx.y * kBlurTileW + threadIdx.x;
+  const int x0 = blockIdx.x * kBlurTileW - radius, y0 = blockIdx.y * kBlurTileH - radius;
+  for (int i = tid; i < tw * th; i += kBlurTileW * kBlurTileH) {
+    const int x = x0 + i % tw, y = y0 + i / tw;
+    uint32_t px = 0u;
+    if (x >= 0 && x < w && y >= 0 && y < h)
+      px = *reinterpret_cast<const uint32_t *> (src + (size_t) y * src_pitch + 4 * (size_t) x);
+    tile[i] = px;
+  }
+  for (int i = tid; i < size * size; i += kBlurTileW * kBlurTileH)
+    s_taps[i] = taps[i];
+  __syncthreads ();
+  const int ox = blockIdx.x * kBlurTileW + threadIdx.x, oy = blockIdx.y * kBlurTileH + threadIdx.y;
+  if (ox >= w || oy >= h)
+    return;
+  int t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  for (int i = 0; i < size; i++) {
+    const uint32_t *row = tile + (threadIdx.y + i) * tw + threadIdx.x;
+    const int32_t *tr = s_taps + i * size;
+    for (int j = 0; j < size; j++) {
+      const int32_t f = tr[j];
+      const uint32_t px = row[j];
+      t0 += (int) (px & 0xffu) * f;
+      t1 += (int) ((px >> 8) & 0xffu) * f;
+      t2 += (int) ((px >> 16) & 0xffu) * f;
+      t3 += (int) (px >> 24) * f;
+    }
+  }
+  t0 = min (max ((t0 + 0x8000) >> 16, 0), 255);
+  t1 = min (max ((t1 + 0x8000) >> 16, 0), 255);
+  t2 = min (max ((t2 + 0x8000) >> 16, 0), 255);
+  t3 = min (max ((t3 + 0x8000) >> 16, 0), 255);
+  *reinterpret_cast<uint32_t *> (dst + (size_t) oy * dst_pitch + 4 * (size_t) ox) =
+      (uint32_t) t0 | ((uint32_t) t1 << 8) | ((uint32_t) t2 << 16) | ((uint32_t) t3 << 24);
+}
+
+cudaError_t
+launch_blur (const uint8_t *src, int w, int h, int src_pitch, const int32_t *taps, int radius,
+    uint8_t *dst, int dst_pitch, cudaStream_t stream)
+{
+  if (w <= 0 || h <= 0)
+    return cudaSuccess;
+  const int size = 2 * radius + 1;
+  const size_t smem = ((size_t) (kBlurTileW + 2 * radius) * (kBlurTileH + 2 * radius) +
+      (size_t) size * size) * 4;
+  if (smem > 200 * 1024)
+    return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute (ttmlblend_blur_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess)
+      return e;
+  }
+  dim3 grid ((w + kBlurTileW - 1) / kBlurTileW, (h + kBlurTileH - 1) / kBlurTileH);
+  dim3 block (kBlurTileW, kBlurTileH);
+  ttmlblend_blur_kernel<<<grid, block, smem, stream>>> (src, w, h, src_pitch, taps, radius, dst, dst_pitch);
+  return cudaGetLastError ();
+}
+
+/* ---------------------------------------------------------------------- */
 
 __global__ void
 ttmlblend_scrub_kernel (uint4 *buf, size_t n_vec, uint32_t seed)

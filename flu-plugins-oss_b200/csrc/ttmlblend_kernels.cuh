@@ -160,6 +160,9 @@ cudaError_t launch_group (GroupParams &P, int kind, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);
+/* (2r+1)^2 16.16 taps; ARGB32 in, ARGB32 out (pixman convolution semantics). */
+cudaError_t launch_blur (const uint8_t *src, int w, int h, int src_pitch, const int32_t *taps, int radius,
+    uint8_t *dst, int dst_pitch, cudaStream_t stream);
 /* spans[y] = first / last x of row y with alpha != 0, (w, -1) for an empty row. */
 cudaError_t launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaStream_t stream);
 

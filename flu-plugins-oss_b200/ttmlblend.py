@@ -94,6 +94,8 @@ PROTOTYPES = {
                                               C.POINTER(Frame), C.POINTER(Frame)]),
     "fluc_ttmlblend_frame_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32,
                                                 C.POINTER(Frame), C.POINTER(Frame)]),
+    "fluc_ttmlblend_blur_argb32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_double, C.c_void_p, C.c_int32]),
     "fluc_ttmlblend_format_planes": (C.c_int, [C.c_int]),
     "fluc_ttmlblend_plane_row_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int32]),
     "fluc_ttmlblend_plane_rows": (C.c_int, [C.c_int, C.c_int, C.c_int32]),
@@ -323,6 +325,15 @@ class TtmlBlend:
 
     def host_unregister(self, arr: np.ndarray):
         self._check(self.lib.fluc_ttmlblend_host_unregister(self.h, arr.ctypes.data), "host_unregister")
+
+    def blur_argb32(self, img: np.ndarray, radius: int, sigma: float) -> np.ndarray:
+        """gst_ttml_blur_image_surface (surface, radius, sigma): h x w x 4 uint8 in and out."""
+        assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 4 and img.strides[2] == 1
+        out = np.zeros_like(img)
+        self._check(self.lib.fluc_ttmlblend_blur_argb32(
+            self.h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], radius, float(sigma),
+            out.ctypes.data, out.strides[0]), "blur_argb32")
+        return out
 
     # -- pool / stats ----------------------------------------------------
     def acquire(self, fmt: str, width: int, height: int, on_host: bool = False) -> DeviceFrame:

@@ -204,6 +204,16 @@ FLUC_EXPORT int fluc_ttmlblend_format_planes (FlucTtmlBlendFormat fmt);
 FLUC_EXPORT int fluc_ttmlblend_plane_row_bytes (FlucTtmlBlendFormat fmt, int plane, int32_t width);
 FLUC_EXPORT int fluc_ttmlblend_plane_rows (FlucTtmlBlendFormat fmt, int plane, int32_t height);
 
+/* ---- producer-side helper: textOutline blur (once per cue) ----------- */
+/* gst_ttml_blur_image_surface (surface, radius, sigma) of
+ * /root/reference/plugins/ttml/gstttmlblur.c:72-110 on the GPU: Gaussian
+ * kernel of (2*radius+1)^2 16.16 fixed-point taps, pixman convolution
+ * semantics (transparent outside the image, (sum + 0x8000) >> 16, clip).
+ * ARGB32 in host memory in, ARGB32 out; synchronous. radius 0..64. */
+FLUC_EXPORT int fluc_ttmlblend_blur_argb32 (FlucTtmlBlend *thiz, const uint8_t *src,
+    int32_t width, int32_t height, int32_t stride, int32_t radius, double sigma,
+    uint8_t *dst, int32_t dst_stride);
+
 /* ---- observability --------------------------------------------------- */
 FLUC_EXPORT void fluc_ttmlblend_stats_copy (FlucTtmlBlend *thiz, FlucTtmlBlendStats *out);
 FLUC_EXPORT void fluc_ttmlblend_stats_reset (FlucTtmlBlend *thiz);

@@ -41,7 +41,7 @@ def build(native: bool = False, out_dir: str = None) -> str:
     flags = ["-O3", "-fPIC", "-shared", "-std=c99", "-D_POSIX_C_SOURCE=200809L"]
     if native:
         flags.append("-march=native")
-    subprocess.check_call(["gcc", *flags, "-o", out, src, "-lpthread"])
+    subprocess.check_call(["gcc", *flags, "-o", out, src, "-lpthread", "-lm"])
     return out
 
 
@@ -60,6 +60,11 @@ def load(native: bool = False, out_dir: str = None):
     lib.tbref_blend_many.restype = C.c_double
     lib.tbref_blend_many.argtypes = [C.POINTER(RefFrame), C.c_uint32, C.POINTER(RefRectangle),
                                      C.c_uint32, C.c_uint32]
+    lib.tbref_gaussian_kernel.restype = C.c_int32
+    lib.tbref_gaussian_kernel.argtypes = [C.c_int32, C.c_double, C.POINTER(C.c_int32)]
+    lib.tbref_blur_argb32.restype = None
+    lib.tbref_blur_argb32.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_double, C.c_void_p, C.c_int32]
     for n in ("tbref_matrix_prea_rgb_to_yuv", "tbref_matrix_rgb_to_yuv", "tbref_matrix_yuv_to_rgb"):
         getattr(lib, n).restype = None
         getattr(lib, n).argtypes = [C.c_void_p, C.c_uint32]
@@ -110,3 +115,21 @@ def ttmlrender_rectangles(bgra: np.ndarray, rects: Sequence[Sequence[int]] = ())
     premultiplied rectangle at (0,0); `rects` is ignored on purpose (the region boxes only
     tell the GPU path where non-transparent pixels can be)."""
     return [dict(pixels=bgra, x=0, y=0, global_alpha=1.0, premultiplied=True)]
+
+
+def blur_argb32(img: np.ndarray, radius: int, sigma: float, lib=None) -> np.ndarray:
+    """gst_ttml_blur_image_surface (surface, radius, sigma) on an h x w x 4 uint8 image."""
+    lib = lib or load()
+    assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 4 and img.strides[2] == 1
+    out = np.zeros_like(img)
+    lib.tbref_blur_argb32(img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], radius,
+                          float(sigma), out.ctypes.data, out.strides[0])
+    return out
+
+
+def gaussian_kernel(radius: int, sigma: float, lib=None) -> np.ndarray:
+    lib = lib or load()
+    n = (2 * radius + 1) ** 2
+    taps = (C.c_int32 * n)()
+    lib.tbref_gaussian_kernel(radius, float(sigma), taps)
+    return np.array(taps, dtype=np.int32).reshape(2 * radius + 1, 2 * radius + 1)

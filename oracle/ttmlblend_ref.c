@@ -20,6 +20,7 @@
  */
 #include "ttmlblend_ref.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -464,6 +465,61 @@ tbref_composition_blend (TbRefFrame *dest, const TbRefRectangle *rects,
   for (n = 0; n < n_rects; n++)
     ret = tbref_video_blend (dest, &rects[n]);
   return ret;
+}
+
+/* ---------------------------------------------------------------------- */
+/* outline blur: gstttmlblur.c + pixman's convolution filter               */
+
+int32_t
+tbref_gaussian_kernel (int32_t radius, double sigma, int32_t *taps)
+{
+  /* gst_ttml_blur_create_gaussian_kernel, /root/reference/plugins/ttml/gstttmlblur.c:28-67 */
+  const double scale2 = 2.0 * sigma * sigma;
+  const double scale1 = 1.0 / (3.14159265358979323846 * scale2);
+  const int size = 2 * radius + 1;
+  const int n = size * size;
+  double *tmp = (double *) malloc (sizeof (double) * (size_t) n);
+  double sum = 0;
+  int x, y, i = 0;
+  for (x = -radius; x <= radius; ++x)
+    for (y = -radius; y <= radius; ++y, ++i) {
+      const double u = x * x, v = y * y;
+      tmp[i] = scale1 * exp (-(u + v) / scale2);
+      sum += tmp[i];
+    }
+  for (i = 0; i < n; ++i)
+    taps[i] = (int32_t) ((tmp[i] / sum) * 65536.0);      /* pixman_double_to_fixed */
+  free (tmp);
+  return n;
+}
+
+void
+tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
+    int32_t radius, double sigma, uint8_t *dst, int32_t dst_stride)
+{
+  /* bits_image_fetch_pixel_convolution: window [x-r, x+r] x [y-r, y+r], pixels outside the
+   * image are transparent black (REPEAT_NONE), 16.16 taps, (sum + 0x8000) >> 16, CLIP 0..255 */
+  const int size = 2 * radius + 1;
+  int32_t *taps = (int32_t *) malloc (sizeof (int32_t) * (size_t) size * size);
+  int x, y, i, j, c;
+  tbref_gaussian_kernel (radius, sigma, taps);
+  for (y = 0; y < height; y++)
+    for (x = 0; x < width; x++) {
+      int tot[4] = { 0, 0, 0, 0 };
+      const int32_t *t = taps;
+      for (i = y - radius; i <= y + radius; i++)
+        for (j = x - radius; j <= x + radius; j++, t++) {
+          if (!*t || i < 0 || i >= height || j < 0 || j >= width)
+            continue;
+          for (c = 0; c < 4; c++)
+            tot[c] += (int) src[(size_t) i * stride + 4 * (size_t) j + c] * *t;
+        }
+      for (c = 0; c < 4; c++) {
+        int v = (tot[c] + 0x8000) >> 16;
+        dst[(size_t) y * dst_stride + 4 * (size_t) x + c] = (uint8_t) TB_CLAMP (v, 0, 255);
+      }
+    }
+  free (taps);
 }
 
 /* ---------------------------------------------------------------------- */

@@ -74,6 +74,17 @@ void tbref_matrix_prea_rgb_to_yuv (uint8_t *line, uint32_t width);
 void tbref_matrix_rgb_to_yuv (uint8_t *line, uint32_t width);
 void tbref_matrix_yuv_to_rgb (uint8_t *line, uint32_t width);
 
+/* Outline blur. The Gaussian kernel is the
+ * reference's own gst_ttml_blur_create_gaussian_kernel
+ * (/root/reference/plugins/ttml/gstttmlblur.c:28-67) in pixman 16.16 fixed
+ * point; the convolution restates pixman's PIXMAN_FILTER_CONVOLUTION on an
+ * a8r8g8b8 image with PIXMAN_REPEAT_NONE, operator SRC (gstttmlblur.c:72-110;
+ * pixman is not installed here: parity unpinned for the convolution part).
+ * `taps` receives (2*radius+1)^2 values; returns that count. */
+int32_t tbref_gaussian_kernel (int32_t radius, double sigma, int32_t *taps);
+void tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
+    int32_t radius, double sigma, uint8_t *dst, int32_t dst_stride);
+
 /* Plane geometry helpers shared by the tests and the bench. */
 int32_t tbref_n_planes (int32_t format);
 int32_t tbref_plane_row_bytes (int32_t format, int32_t plane, int32_t width);

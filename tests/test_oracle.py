@@ -210,3 +210,35 @@ def test_workloads_are_deterministic_and_valid_premultiplied():
     assert (a[:, :, :3].max(axis=2) <= a[:, :, 3]).all()
     assert a[:576].max() == 0 and a[576:684, 128:1152, 3].max() == 255
     assert wl.splitmix64(0, 1)[0] == np.uint64(0xE220A8397B1DCDAF)   # published first output for seed 0
+
+
+def test_gaussian_kernel_is_the_references_formula():
+    """gst_ttml_blur_create_gaussian_kernel (gstttmlblur.c:28-67): normalised 2-D Gaussian in
+    16.16 fixed point (truncated), symmetric, sums to just under 1.0."""
+    import math
+    from oracle import oracle
+    for radius, sigma in ((1, 0.5), (2, 1.0), (5, 2.5)):
+        k = oracle.gaussian_kernel(radius, sigma)
+        size = 2 * radius + 1
+        g = np.array([[math.exp(-(x * x + y * y) / (2 * sigma * sigma)) for y in range(-radius, radius + 1)]
+                      for x in range(-radius, radius + 1)])
+        want = np.floor(g / g.sum() * 65536.0).astype(np.int64)
+        assert k.shape == (size, size)
+        assert np.abs(k.astype(np.int64) - want).max() <= 1     # same formula up to the last ulp of exp()
+        assert np.array_equal(k, k.T) and np.array_equal(k, k[::-1, ::-1])
+        assert 65536 - size * size <= k.sum() <= 65536
+
+
+def test_blur_known_answers():
+    from oracle import oracle
+    img = np.zeros((9, 9, 4), dtype=np.uint8)
+    img[4, 4] = 255
+    out = oracle.blur_argb32(img, 2, 1.0)
+    k = oracle.gaussian_kernel(2, 1.0).astype(np.int64)
+    want = np.clip((255 * k + 0x8000) >> 16, 0, 255)
+    assert np.array_equal(out[2:7, 2:7, 3], want)           # impulse response == the kernel
+    assert out[:2].max() == 0 and out[:, :2].max() == 0
+    flat = np.full((12, 12, 4), 200, dtype=np.uint8)
+    out = oracle.blur_argb32(flat, 2, 1.0)
+    assert abs(int(out[6, 6, 0]) - 200) <= 1                 # interior of a flat field stays flat
+    assert out[0, 0, 0] < 150                                # edges fade: outside is transparent
