@@ -393,3 +393,48 @@ def test_submit_many_equals_submit(ctx):
             f.release()
     finally:
         ctx.set_batch(32, 200)
+
+
+@pytest.mark.parametrize("fmt", ("NV12", "I420", "BGRA"))
+@pytest.mark.parametrize("xoff,w", [(64, 320), (4, 310), (32, 333)])
+def test_no_byte_outside_the_frame_is_written(ctx, fmt, xoff, w):
+    """Guard-band check (compute-sanitizer is not available on the pool): the destination is a
+    window inside a larger buffer; everything around it must keep its pattern, for aligned
+    windows (vector path), 4-byte aligned ones (byte path) and ragged widths."""
+    tb = pkg.ttmlblend
+    h, W2, H2, yoff = 90, 512, 128, 10
+    rects = [dict(pixels=random_overlay(w + 40, 50, 31), x=-20, y=30),
+             dict(pixels=random_overlay(60, 200, 32), x=w - 30, y=-50)]
+    ctx.overlay_set_rectangles(88, rects)
+    planes = random_frame(fmt, w, h, 33)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+    big_src, big_dst = ctx.acquire(fmt, W2, H2), ctx.acquire(fmt, W2, H2)
+    try:
+        pattern = [np.full((rows, rb), 0xA5, dtype=np.uint8) for rows, rb in wl.plane_shapes(fmt, W2, H2)]
+        big_dst.upload(pattern)
+        big_src.upload(pattern)
+        bpp = 4 if fmt == "BGRA" else 1
+        src_f, dst_f, views = tb.Frame(), tb.Frame(), []
+        for i, ((rows, rb), (_, rb_big)) in enumerate(zip(wl.plane_shapes(fmt, w, h), wl.plane_shapes(fmt, W2, H2))):
+            sub = 1 if i == 0 or fmt == "BGRA" else 2                 # chroma subsampling of the offsets
+            xo = (xoff // sub) * bpp if not (fmt == "NV12" and i == 1) else xoff     # NV12 UV: 2 bytes per 2 px
+            yo = yoff // sub
+            for f, pool in ((src_f, big_src), (dst_f, big_dst)):
+                f.plane[i] = pool.c.plane[i] + yo * pool.c.stride[i] + xo
+                f.stride[i] = pool.c.stride[i]
+            views.append((yo, xo, rows, rb))
+        host = tb._frame_from_arrays([np.ascontiguousarray(p) for p in planes])
+        ctx._check(ctx.lib.fluc_ttmlblend_frame_upload(ctx.h, tb.FORMATS[fmt], w, h, host, src_f), "up")
+        for s_frame, d_frame, what in ((src_f, dst_f, "out of place"), (dst_f, dst_f, "in place again")):
+            if what == "in place again":       # restore the unblended frame inside the window first
+                ctx._check(ctx.lib.fluc_ttmlblend_frame_upload(ctx.h, tb.FORMATS[fmt], w, h, host, dst_f), "up")
+            ctx.wait(ctx.submit(88, fmt, w, h, s_frame, d_frame))
+            got_big = big_dst.download()
+            for (yo, xo, rows, rb), g, wnt in zip(views, got_big, want):
+                assert np.array_equal(g[yo:yo + rows, xo:xo + rb], wnt), what
+                outside = g.copy()
+                outside[yo:yo + rows, xo:xo + rb] = 0xA5
+                assert (outside == 0xA5).all(), f"{what}: {int((outside != 0xA5).sum())} guard bytes overwritten"
+    finally:
+        big_src.release()
+        big_dst.release()
