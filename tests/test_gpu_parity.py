@@ -438,3 +438,48 @@ def test_no_byte_outside_the_frame_is_written(ctx, fmt, xoff, w):
     finally:
         big_src.release()
         big_dst.release()
+
+
+def test_stress_cue_changes_while_frames_flow(ctx):
+    """Subtitle threads replace cues while video threads submit device frames and host frames
+    of the same streams: every frame must equal the oracle for the cue that was current at
+    submit time (atomic replace), whatever batches the scheduler forms."""
+    w, h, fmt, n_streams, rounds = 192, 108, "NV12", 6, 12
+    ctx.set_batch(16, 100)
+    errors = []
+    cues = [[dict(pixels=random_overlay(120, 30, 7000 + 10 * s + k), x=10 + 5 * k, y=20 + 7 * k + s)]
+            for s in range(n_streams) for k in range(2)]
+
+    def stream_thread(s):
+        try:
+            src, dst = ctx.acquire(fmt, w, h), ctx.acquire(fmt, w, h)
+            pinned = ctx.acquire(fmt, w, h, on_host=True)
+            for r in range(rounds):
+                cue = cues[2 * s + (r & 1)]
+                ctx.overlay_set_rectangles(900 + s, cue)
+                planes = random_frame(fmt, w, h, 7100 + 100 * s + r)
+                want = oracle_blend(fmt, w, h, copy_planes(planes), cue)
+                src.upload(planes)
+                t_dev = ctx.submit(900 + s, fmt, w, h, src.c, dst.c)
+                for d, p in zip(pinned.host_planes(), planes):
+                    d[...] = p
+                t_host = ctx.blend_host_frame(900 + s, fmt, w, h, pinned.c)
+                if r % 3 == 0:
+                    ctx.overlay_clear(900 + s)          # must not affect the two frames above
+                ctx.wait(t_host)
+                ctx.wait(t_dev)
+                assert_planes_equal(dst.download(), want, f"stream {s} round {r} device")
+                assert_planes_equal([np.array(x) for x in pinned.host_planes()], want,
+                                    f"stream {s} round {r} host")
+            for f in (src, dst, pinned):
+                f.release()
+        except Exception as e:      # noqa: BLE001
+            errors.append((s, repr(e)))
+
+    ths = [threading.Thread(target=stream_thread, args=(s,)) for s in range(n_streams)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    ctx.set_batch(32, 200)
+    assert not errors, errors
