@@ -589,6 +589,7 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
     const FlucTtmlBlendFrame *dst, const Prepared *prep, bool windowed, std::vector<PlaneJob> &jobs)
 {
   const int n_planes = format_planes (format);
+  static const bool use_bulk = !getenv ("FLUC_TTMLBLEND_BULK") || atoi (getenv ("FLUC_TTMLBLEND_BULK")) != 0;
   /* windowed: only the vectors a rectangle covers are read and written (in
    * place, or host frames where untouched bytes never cross PCIe) */
   const bool inplace = windowed;
@@ -625,35 +626,51 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
 
     for (size_t bi = 0; bi + 1 < ys.size (); bi++) {
       const int ya = ys[bi], yb = ys[bi + 1];
-      unsigned long long mask = 0;
-      int count = 0, one = -1, minv = 1 << 30, maxv = 0;
+      /* rectangles over this band, by first column; then cut the band into
+       * windows left to right: gaps copy, a rectangle alone in its columns is
+       * JC_ONE (no per-vector tests), rectangles sharing columns form one
+       * JC_GENERAL window that applies them in blend order */
+      struct InBand { int idx, v0, v1; };
+      InBand in_band[FLUC_TTMLBLEND_MAX_RECTANGLES];
+      int n_in = 0;
       for (size_t i = 0; i < rects.size (); i++) {
         const RectRef &r = rects[i];
-        if (r.y0 <= ya && r.y1 >= yb && r.v0 < nv_row && r.v1 > 0) {
-          mask |= 1ull << i;
-          count++;
-          one = (int) i;
-          minv = std::min (minv, std::max (r.v0, 0));
-          maxv = std::max (maxv, std::min (r.v1, nv_row));
+        if (r.y0 <= ya && r.y1 >= yb && r.v0 < nv_row && r.v1 > 0)
+          in_band[n_in++] = { (int) i, std::max (r.v0, 0), std::min (r.v1, nv_row) };
+      }
+      std::sort (in_band, in_band + n_in, [](const InBand &a, const InBand &c) { return a.v0 < c.v0; });
+      auto emit = [&](int cls, unsigned long long mask, int one, int v0, int v1) {
+        if (v1 <= v0)
+          return;
+        PlaneJob j = b;
+        j.rect_mask = mask;
+        j.one_rect = one < 0 ? 0 : one;
+        j.cls = cls;
+        /* prepared rows packed over exactly the window's columns: the overlay bytes of any
+         * run of vectors of the band are contiguous -> TMA bulk staging in the group kernel */
+        if (cls == JC_ONE && use_bulk && rects[one].v0 == v0 && rects[one].v1 == v1 &&
+            rects[one].pitch == (v1 - v0) * 16 && (b.row_bytes & 15) == 0)
+          j.cls = JC_ONE_BULK;
+        push_split (jobs, j, aligned, v0, v1, ya, yb);
+        bytes += 2ull * (uint64_t) std::min ((v1 - v0) * 16, b.row_bytes - v0 * 16) * (uint64_t) (yb - ya);
+      };
+      int cursor = 0;
+      for (int i = 0; i < n_in;) {
+        unsigned long long mask = 1ull << in_band[i].idx;
+        int c0 = in_band[i].v0, c1 = in_band[i].v1, k = i + 1;
+        while (k < n_in && in_band[k].v0 < c1) {      /* shares columns with the cluster */
+          mask |= 1ull << in_band[k].idx;
+          c1 = std::max (c1, in_band[k].v1);
+          k++;
         }
+        if (!inplace)
+          emit (JC_COPY, 0, -1, cursor, c0);
+        emit (k - i == 1 ? JC_ONE : JC_GENERAL, mask, in_band[i].idx, c0, c1);
+        cursor = c1;
+        i = k;
       }
-      PlaneJob j = b;
-      j.rect_mask = mask;
-      j.one_rect = one < 0 ? 0 : one;
-      int v0 = 0, v1 = nv_row;
-      if (count == 0) {
-        if (inplace)
-          continue;
-        j.cls = JC_COPY;
-      } else if (!inplace) {
-        j.cls = (count == 1 && rects[one].v0 <= 0 && rects[one].v1 >= nv_row) ? JC_ONE : JC_GENERAL;
-      } else {
-        j.cls = count == 1 ? JC_ONE : JC_GENERAL;
-        v0 = minv;
-        v1 = maxv;
-      }
-      push_split (jobs, j, aligned, v0, v1, ya, yb);
-      bytes += 2ull * (uint64_t) std::min ((v1 - v0) * 16, b.row_bytes - v0 * 16) * (uint64_t) (yb - ya);
+      if (!inplace)
+        emit (JC_COPY, 0, -1, cursor, nv_row);
     }
   }
   if (prep)

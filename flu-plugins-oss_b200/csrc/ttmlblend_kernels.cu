@@ -250,13 +250,17 @@ load_job (const PlaneJob *job)
  *   JC_COPY     no rectangle: stream the rows through;
  *   JC_ONE      exactly one rectangle covering the window's whole width:
  *               every vector blends with it, no per-item tests;
+ *   JC_ONE_BULK the same, and the rectangle's prepared rows are packed
+ *               back to back over exactly the window's columns, so the
+ *               chunk's overlay bytes are contiguous: staged through shared
+ *               memory by the TMA (group kernel only);
  *   JC_GENERAL  several rectangles and/or partial width: per-item column
  *               tests, rectangles applied in order.
  * Thread t owns items t, t+256, t+512, t+768 of the chunk, so four
  * independent 128-bit frame loads (plus their overlay loads) are in flight
  * per thread before the first is consumed. FAST = 16-byte aligned frame and
  * no ragged vector; otherwise the byte-granular variant runs. */
-template <int KIND, bool FAST>
+template <int KIND, bool FAST, bool BULK>
 __device__ __forceinline__ void
 process_chunk (const JobRegs &J, uint32_t local_chunk)
 {
@@ -291,7 +295,65 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
           st_frame16 (dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16, f[k]);
       return;
     }
-    if (J.cls == JC_ONE) {
+    if (BULK && J.cls == JC_ONE_BULK) {
+      /* The chunk's slice of the prepared overlay is one contiguous run of
+       * bytes (the rectangle spans the window and its rows are packed), so a
+       * single thread hands it to the TMA: cp.async.bulk global -> shared,
+       * completion on an mbarrier. Meanwhile every thread has its four frame
+       * loads in flight; no register holds overlay data while it travels. */
+      extern __shared__ __align__ (128) uint8_t ov_smem[];
+      __shared__ __align__ (8) unsigned long long ov_bar;
+      const RectRef *r = J.rects + J.one_rect;
+      const RectGeom g = rect_geom (r);
+      const uint32_t first = local_chunk * kItemsPerChunk;
+      const uint32_t bytes = min ((uint32_t) kItemsPerChunk, J.total_items - first) * 16u;
+      const size_t off = ((size_t) (J.win_y0 - g.y0) * J.win_nv + first) * 16;
+      const uint32_t bar = (uint32_t) __cvta_generic_to_shared (&ov_bar);
+      const uint32_t sm_a = (uint32_t) __cvta_generic_to_shared (ov_smem);
+      if (threadIdx.x == 0) {
+        asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (bar));
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+            :: "r" (bar), "r" (KIND == PK_PLANE8 ? 2u * bytes : bytes) : "memory");
+        asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            :: "r" (sm_a), "l" (ldg_ptr (&r->a) + off), "r" (bytes), "r" (bar) : "memory");
+        if (KIND == PK_PLANE8)
+          asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              :: "r" (sm_a + kItemsPerChunk * 16), "l" (ldg_ptr (&r->c) + off), "r" (bytes), "r" (bar) : "memory");
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++)
+        if (act[k])
+          f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+      __syncthreads ();           /* the barrier is initialised for everybody */
+      asm volatile ("{\n"
+          ".reg .pred p;\n"
+          "OV_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+          "@p bra OV_DONE;\n"
+          "bra OV_WAIT;\n"
+          "OV_DONE:\n"
+          "}" :: "r" (bar) : "memory");
+      const uint32_t ga = KIND == PK_PLANE8 ? 255u : (uint32_t) __ldg (&r->ga);
+      const bool sp = KIND == PK_PLANE8 ? false : __ldg (&r->src_premul) != 0;
+      const bool dp = (J.flags & JF_DST_PREMUL) != 0;
+#pragma unroll
+      for (int k = 0; k < kUnroll; k++)
+        if (act[k]) {
+          const uint32_t so = (threadIdx.x + k * kThreads) * 16u;
+          const uint4 oa = *reinterpret_cast<const uint4 *> (ov_smem + so);
+          uint4 out;
+          if (KIND == PK_PLANE8) {
+            const uint4 oc = *reinterpret_cast<const uint4 *> (ov_smem + kItemsPerChunk * 16 + so);
+            out = blend16_plane8 (f[k], oa, oc);
+          } else {
+            out = blend16_packed<KIND == PK_PACKED_A0 ? 0 : 3> (f[k], oa, ga, sp, dp);
+          }
+          st_frame16 (dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16, out);
+        }
+      return;
+    }
+    if (J.cls == JC_ONE || (!BULK && J.cls == JC_ONE_BULK)) {
       const RectRef *r = J.rects + J.one_rect;
       const RectGeom g = rect_geom (r);
       const int32_t pitch = __ldg (&r->pitch);
@@ -428,7 +490,7 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
     cnt += __syncthreads_count (pred);
   }
   const JobRegs J = load_job (jobs + (cnt - 1));
-  process_chunk<KIND, FAST> (J, chunk - __ldg (chunk_begin + (cnt - 1)));
+  process_chunk<KIND, FAST, false> (J, chunk - __ldg (chunk_begin + (cnt - 1)));
 }
 
 /* The common case -- a batch of frames that share format, size, strides and
@@ -474,7 +536,7 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   J.one_rect = B.one_rect;
   J.flags = P.flags;
   J.row_bytes = 0;              /* FAST: never read */
-  process_chunk<KIND, true> (J, cif - B.chunk_begin);
+  process_chunk<KIND, true, true> (J, cif - B.chunk_begin);
 }
 
 /* Number of interleaved streams the chunk list is walked in. Measured on the
@@ -535,15 +597,17 @@ launch_group (GroupParams &P, int kind, cudaStream_t stream)
   if ((unsigned long long) grid * lanes >= (1ull << 32))
     return cudaErrorInvalidValue;
   P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
+  /* shared memory for the TMA-staged overlay slice of a JC_ONE_BULK chunk */
+  const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
   switch (kind) {
     case PK_PLANE8:
-      ttmlblend_group_kernel<PK_PLANE8><<<grid, kThreads, 0, stream>>> (P);
+      ttmlblend_group_kernel<PK_PLANE8><<<grid, kThreads, smem_plane8, stream>>> (P);
       break;
     case PK_PACKED_A0:
-      ttmlblend_group_kernel<PK_PACKED_A0><<<grid, kThreads, 0, stream>>> (P);
+      ttmlblend_group_kernel<PK_PACKED_A0><<<grid, kThreads, smem_packed, stream>>> (P);
       break;
     case PK_PACKED_A3:
-      ttmlblend_group_kernel<PK_PACKED_A3><<<grid, kThreads, 0, stream>>> (P);
+      ttmlblend_group_kernel<PK_PACKED_A3><<<grid, kThreads, smem_packed, stream>>> (P);
       break;
     default:
       return cudaErrorInvalidValue;

@@ -56,7 +56,8 @@ struct alignas (16) RectRef {
 enum JobClass : int32_t {
   JC_COPY = 0,          /* no rectangle touches the window */
   JC_ONE = 1,           /* one rectangle covers the whole window */
-  JC_GENERAL = 2        /* several rectangles and/or partial width */
+  JC_GENERAL = 2,       /* several rectangles and/or partial width */
+  JC_ONE_BULK = 3       /* JC_ONE whose overlay bytes per chunk are contiguous (TMA staging) */
 };
 
 /* One window of one plane of one frame: a band of rows that all see the same
