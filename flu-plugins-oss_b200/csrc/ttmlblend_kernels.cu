@@ -353,7 +353,9 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
         }
       return;
     }
-    if (J.cls == JC_ONE || (!BULK && J.cls == JC_ONE_BULK)) {
+    /* register-staged variant: table kernel only (the group kernel sends the rare JC_ONE
+     * that is not bulk-eligible through the general path and keeps its register budget) */
+    if (!BULK && (J.cls == JC_ONE || J.cls == JC_ONE_BULK)) {
       const RectRef *r = J.rects + J.one_rect;
       const RectGeom g = rect_geom (r);
       const int32_t pitch = __ldg (&r->pitch);
@@ -466,7 +468,7 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
  * under the memory time, instead of the chip being compute-bound inside the
  * cue bands and idle on the ALUs outside them. */
 #ifndef TTMLBLEND_MIN_CTAS
-#define TTMLBLEND_MIN_CTAS 4
+#define TTMLBLEND_MIN_CTAS 5
 #endif
 
 template <int KIND, bool FAST>
