@@ -221,7 +221,7 @@ struct Ctx {
   std::unordered_set<const void *> pending_dst;   /* destination buffers queued in `pending` */
   std::vector<cudaEvent_t> timing_pool;
   std::chrono::steady_clock::time_point oldest_pending;
-  uint64_t next_ticket = 0, launched_ticket = 0, done_ticket = 0;
+  uint64_t next_ticket = 0;
   std::deque<Batch> batches;
   std::vector<cudaEvent_t> event_pool;
   TableSlot slots[kTableSlots];
@@ -835,7 +835,6 @@ reap_batches (Ctx *c)
       c->timing_pool.push_back (b.t0);
       c->timing_pool.push_back (b.t1);
     }
-    c->done_ticket = b.last_ticket;
     c->event_pool.push_back (b.done);
     c->batches.pop_front ();
   }
@@ -916,7 +915,6 @@ launch_pending (Ctx *c)
   }
   b.done = event_get (c);
   CU (c, cudaEventRecord (b.done, c->blend_stream));
-  c->launched_ticket = b.last_ticket;
   c->batches.push_back (std::move (b));
   return 0;
 }
