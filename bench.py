@@ -28,6 +28,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -403,6 +404,8 @@ def main():
                                        if cfg.streams > 1 else
                                        f"{world} x independent frame batches, no collective")},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+            "gstreamer": ("present: " + shutil.which("gst-launch-1.0")) if shutil.which("gst-launch-1.0")
+            else "absent on this box (no gst-launch-1.0): the reference pipeline itself cannot be timed",
             "gpu_launches": int(st["launches"]),
             "per_rank": [{"frames": r[0], "ms": r[1], "kernel_ms": r[2]} for r in records],
         }

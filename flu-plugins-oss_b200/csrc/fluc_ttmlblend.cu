@@ -18,6 +18,8 @@
 #include "../../include/fluc_ttmlblend.h"
 #include "ttmlblend_kernels.cuh"
 
+#include <nvtx3/nvToolsExt.h>       /* header-only: ranges show up in nsys / ncu timelines */
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -267,6 +269,12 @@ log_level ()
   return lvl;
 }
 
+/* NVTX range for the current scope */
+struct NvtxRange {
+  explicit NvtxRange (const char *name) { nvtxRangePushA (name); }
+  ~NvtxRange () { nvtxRangePop (); }
+};
+
 #define TBLOG(n, ...) do { if (log_level () >= (n)) { fprintf (stderr, "ttmlblend: " __VA_ARGS__); fputc ('\n', stderr); } } while (0)
 
 cudaEvent_t
@@ -343,6 +351,8 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
       return 0;
     }
 
+  NvtxRange nvtx ("ttmlblend.prepare_overlay");
+  TBLOG (2, "prepare overlay: format %d, %dx%d, %zu rectangle(s)", format, W, H, ov->rects.size ());
   std::unique_ptr<Prepared> P (new Prepared ());
   P->format = format;
   P->W = W;
@@ -846,6 +856,7 @@ launch_pending (Ctx *c)
 {
   if (c->pending.empty ())
     return 0;
+  NvtxRange nvtx ("ttmlblend.launch_batch");
   reap_batches (c);
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
@@ -1041,6 +1052,7 @@ crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, std::ve
 int
 overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n)
 {
+  NvtxRange nvtx ("ttmlblend.overlay_set");
   std::shared_ptr<Overlay> ov (new Overlay ());
   ov->ctx = c;
   struct Up { RawRect rr; int2 *d_spans; std::vector<int2> spans; };
