@@ -234,6 +234,7 @@ struct Ctx {
   bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
   bool profiling = false;
+  uint32_t profile_every = 1, profile_seq = 0;   /* FLUC_TTMLBLEND_PROFILE_EVERY */
   std::thread sched;
   bool quit = false;
 
@@ -798,7 +799,7 @@ slot_reserve (Ctx *c, TableSlot &s, size_t n)
 /* Copies `jobs` (one PlaneKind) into a table slot and launches the kernel. */
 int
 launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast,
-    cudaStream_t stream, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr)
+    cudaStream_t stream)
 {
   if (n == 0)
     return 0;
@@ -819,11 +820,7 @@ launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, boo
   CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, n * sizeof (uint32_t), cudaMemcpyHostToDevice, c->table_stream));
   CU (c, cudaEventRecord (s.uploaded, c->table_stream));
   CU (c, cudaStreamWaitEvent (stream, s.uploaded, 0));
-  if (t0)
-    CU (c, cudaEventRecord (t0, stream));
   CU (c, launch_blend (s.d_jobs, s.d_begin, (int) n, total, kind, fast, stream));
-  if (t1)
-    CU (c, cudaEventRecord (t1, stream));
   CU (c, cudaEventRecord (s.copied, stream));    /* slot busy until this kernel is done */
   c->stats.launches++;
   return 0;
@@ -895,7 +892,10 @@ launch_pending (Ctx *c)
   size_t n_launches = groups.size ();
   for (int k = 0; k < 6; k++)
     n_launches += !by_kind[k].empty ();
-  if (c->profiling && n_launches == 1) {
+  /* an event pair keeps the batch from overlapping its neighbours (~2 us of stream time):
+   * sample every profile_every-th batch. A batch of several launches (several groups /
+   * kinds) is timed from before its first to after its last launch. */
+  if (c->profiling && n_launches >= 1 && (c->profile_seq++ % c->profile_every) == 0) {
     for (cudaEvent_t *e : { &b.t0, &b.t1 }) {
       if (!c->timing_pool.empty ()) {
         *e = c->timing_pool.back ();
@@ -905,12 +905,10 @@ launch_pending (Ctx *c)
       }
     }
   }
+  if (b.t0)
+    CU (c, cudaEventRecord (b.t0, c->blend_stream));
   for (Group &g : groups) {
-    if (b.t0)
-      CU (c, cudaEventRecord (b.t0, c->blend_stream));
     CU (c, launch_group (g.P, g.kind, c->blend_stream));
-    if (b.t1)
-      CU (c, cudaEventRecord (b.t1, c->blend_stream));
     c->stats.launches++;
     c->stats.group_launches++;
   }
@@ -920,10 +918,12 @@ launch_pending (Ctx *c)
     TableSlot &s = c->slots[c->next_slot];
     c->next_slot = (c->next_slot + 1) % kTableSlots;
     int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0,
-        c->blend_stream, b.t0, b.t1);
+        c->blend_stream);
     if (rc)
       return rc;
   }
+  if (b.t1)
+    CU (c, cudaEventRecord (b.t1, c->blend_stream));
   b.done = event_get (c);
   CU (c, cudaEventRecord (b.done, c->blend_stream));
   c->batches.push_back (std::move (b));
@@ -1240,6 +1240,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   const char *e;
   if ((e = getenv ("FLUC_TTMLBLEND_BATCH")))
     c->max_batch = (uint32_t) std::max (1, std::min (1024, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_PROFILE_EVERY")))
+    c->profile_every = (uint32_t) std::max (1, atoi (e));
   if ((e = getenv ("FLUC_TTMLBLEND_AUTOCROP")))
     c->autocrop = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_GROUPS")))
@@ -1943,6 +1945,9 @@ fluc_ttmlblend_set_profiling (FlucTtmlBlend *thiz, int enabled)
 {
   ENTER (thiz);
   c->profiling = enabled != 0;
+  if (enabled > 0)
+    c->profile_every = (uint32_t) enabled;
+  c->profile_seq = 0;
   return 0;
 }
 

@@ -347,8 +347,9 @@ class TtmlBlend:
     def stats_reset(self):
         self.lib.fluc_ttmlblend_stats_reset(self.h)
 
-    def set_profiling(self, on: bool):
-        self._check(self.lib.fluc_ttmlblend_set_profiling(self.h, 1 if on else 0), "set_profiling")
+    def set_profiling(self, every: int):
+        """0 / False: off; 1 / True: time every launch; n: time every n-th launch."""
+        self._check(self.lib.fluc_ttmlblend_set_profiling(self.h, int(every)), "set_profiling")
 
     def timer_begin(self):
         self._check(self.lib.fluc_ttmlblend_timer_begin(self.h), "timer_begin")
