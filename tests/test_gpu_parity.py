@@ -483,3 +483,34 @@ def test_stress_cue_changes_while_frames_flow(ctx):
         t.join()
     ctx.set_batch(32, 200)
     assert not errors, errors
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_random_geometry(ctx, seed):
+    """Seeded fuzz over everything the host-side job builder has to cut correctly: odd and
+    tiny frames, many rectangles hanging over every border or overlapping, sparse and dense
+    overlays, global alpha, straight / premultiplied sources, non-opaque and premultiplied
+    destinations, all formats and all three ways into the library."""
+    r = np.random.default_rng(9000 + seed)
+    fmt = ALL_FORMATS[seed % len(ALL_FORMATS)]
+    w = int(r.choice([r.integers(1, 40), r.integers(40, 400), 16 * r.integers(1, 30)]))
+    h = int(r.choice([r.integers(1, 30), r.integers(30, 200)]))
+    packed = fmt in PACKED
+    opaque = bool(r.random() < 0.7) or not packed
+    dprem = packed and bool(r.random() < 0.2)
+    rects = []
+    for i in range(int(r.integers(1, 7))):
+        rw, rh = int(r.integers(1, max(2, w + 20))), int(r.integers(1, max(2, h + 20)))
+        ov = random_overlay(rw, rh, int(r.integers(1 << 30)), premultiplied=bool(r.random() < 0.7),
+                            density=float(r.choice([0.05, 0.5, 1.0])))
+        if r.random() < 0.3:
+            ov[:, :, 3][r.random((rh, rw)) < 0.9] = 0          # mostly transparent: exercises the crop
+            ov[:, :, :3] = np.minimum(ov[:, :, :3], ov[:, :, 3:4])
+        rects.append(dict(pixels=ov, x=int(r.integers(-rw, w + 5)), y=int(r.integers(-rh, h + 5)),
+                          global_alpha=float(r.choice([1.0, 1.0, 0.5, 0.99, 0.0])),
+                          premultiplied=bool(r.random() < 0.7)))
+    planes = random_frame(fmt, w, h, int(r.integers(1 << 30)), opaque=opaque)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), rects, dprem)
+    for mode in MODES:
+        got = gpu_blend(ctx, fmt, w, h, planes, rects, mode=mode, dest_premul=dprem, stream=40 + seed)
+        assert_planes_equal(got, want, f"seed {seed} {fmt} {w}x{h} {mode}")

@@ -242,3 +242,26 @@ def test_blur_known_answers():
     out = oracle.blur_argb32(flat, 2, 1.0)
     assert abs(int(out[6, 6, 0]) - 200) <= 1                 # interior of a flat field stays flat
     assert out[0, 0, 0] < 150                                # edges fade: outside is transparent
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_fuzz_oracle_vs_model(seed):
+    """The line-structured oracle and the per-plane numpy model agree on random geometry."""
+    r = np.random.default_rng(5000 + seed)
+    fmt = ALL_FORMATS[seed % len(ALL_FORMATS)]
+    w, h = int(r.integers(1, 120)), int(r.integers(1, 80))
+    packed = fmt in PACKED
+    opaque = bool(r.random() < 0.6) or not packed
+    dprem = packed and bool(r.random() < 0.3)
+    rects = []
+    for i in range(int(r.integers(1, 6))):
+        rw, rh = int(r.integers(1, w + 20)), int(r.integers(1, h + 20))
+        pm = bool(r.random() < 0.7)
+        rects.append(dict(pixels=random_overlay(rw, rh, int(r.integers(1 << 30)), premultiplied=pm),
+                          x=int(r.integers(-rw, w + 5)), y=int(r.integers(-rh, h + 5)),
+                          global_alpha=float(r.choice([1.0, 0.5, 0.99, 0.0])), premultiplied=pm))
+    planes = random_frame(fmt, w, h, int(r.integers(1 << 30)), opaque=opaque)
+    a = oracle_blend(fmt, w, h, copy_planes(planes), rects, dprem)
+    b = model_blend(fmt, w, h, copy_planes(planes), rects, dprem)
+    for i, (p, q) in enumerate(zip(a, b)):
+        assert np.array_equal(p, q), (fmt, seed, i, int((p != q).sum()))
