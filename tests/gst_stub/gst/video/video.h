@@ -1,0 +1,35 @@
+/* stub: see ../../README.md */
+#ifndef GST_STUB_VIDEO_H
+#define GST_STUB_VIDEO_H
+#include <gst/gst.h>
+#define GST_VIDEO_MAX_PLANES 4
+typedef enum { GST_VIDEO_FORMAT_UNKNOWN, GST_VIDEO_FORMAT_I420, GST_VIDEO_FORMAT_YV12, GST_VIDEO_FORMAT_NV12,
+  GST_VIDEO_FORMAT_NV21, GST_VIDEO_FORMAT_AYUV, GST_VIDEO_FORMAT_ARGB, GST_VIDEO_FORMAT_ABGR,
+  GST_VIDEO_FORMAT_RGBA, GST_VIDEO_FORMAT_BGRA } GstVideoFormat;
+typedef enum { GST_VIDEO_FLAG_NONE = 0, GST_VIDEO_FLAG_PREMULTIPLIED_ALPHA = 2 } GstVideoFlags;
+typedef enum { GST_VIDEO_FRAME_FLAG_NONE = 0 } GstVideoFrameFlags;
+typedef enum { GST_VIDEO_COMP_A = 3 } GstVideoCompStub;
+typedef struct _GstVideoInfo { GstVideoFormat format; GstVideoFlags flags; gint width, height; gsize size;
+  gsize offset[GST_VIDEO_MAX_PLANES]; gint stride[GST_VIDEO_MAX_PLANES]; guint n_planes; gboolean has_alpha; gint a_poffset; } GstVideoInfo;
+#define GST_VIDEO_INFO_WIDTH(i) ((i)->width)
+#define GST_VIDEO_INFO_HEIGHT(i) ((i)->height)
+#define GST_VIDEO_INFO_FLAGS(i) ((i)->flags)
+#define GST_VIDEO_INFO_N_PLANES(i) ((i)->n_planes)
+#define GST_VIDEO_INFO_PLANE_OFFSET(i, p) ((i)->offset[p])
+#define GST_VIDEO_INFO_PLANE_STRIDE(i, p) ((i)->stride[p])
+#define GST_VIDEO_INFO_HAS_ALPHA(i) ((i)->has_alpha)
+#define GST_VIDEO_INFO_COMP_POFFSET(i, c) ((i)->a_poffset + 0 * (c))
+gboolean gst_video_info_from_caps (GstVideoInfo *, const GstCaps *);
+gboolean gst_video_info_set_format (GstVideoInfo *, GstVideoFormat, guint, guint);
+typedef struct _GstVideoFrame { GstVideoInfo info; gpointer data[GST_VIDEO_MAX_PLANES]; } GstVideoFrame;
+gboolean gst_video_frame_map (GstVideoFrame *, const GstVideoInfo *, GstBuffer *, GstMapFlags);
+void gst_video_frame_unmap (GstVideoFrame *);
+#define GST_VIDEO_FRAME_N_PLANES(f) ((f)->info.n_planes)
+#define GST_VIDEO_FRAME_PLANE_DATA(f, p) ((f)->data[p])
+#define GST_VIDEO_FRAME_PLANE_STRIDE(f, p) ((f)->info.stride[p])
+#define GST_VIDEO_FRAME_FORMAT(f) ((f)->info.format)
+#define GST_VIDEO_FRAME_WIDTH(f) ((f)->info.width)
+#define GST_VIDEO_FRAME_HEIGHT(f) ((f)->info.height)
+#define GST_VIDEO_CAPS_MAKE(fmts) "video/x-raw, format = (string) " fmts
+gpointer gst_buffer_add_video_meta (GstBuffer *, GstVideoFrameFlags, GstVideoFormat, guint, guint);
+#endif

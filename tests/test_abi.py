@@ -143,3 +143,16 @@ def test_host_mirror_exports_its_header(lib):
     if lib.fluc_ttmlblend_device_count() == 0:
         planes = [np.zeros((8, 8 * 4), dtype=np.uint8)]
         assert c.blend("BGRA", 8, 8, planes) is False     # FALSE, not a CPU fallback
+
+
+@pytest.mark.parametrize("src", ["flu-plugins-oss_b200/gst/gstttmlblend.c",
+                                 "flu-plugins-oss_b200/gst/gstflucallocator.c", "oracle/xcheck_gst.c"])
+def test_gstreamer_glue_is_syntactically_sound(src):
+    """GStreamer is not installed here, so the element / allocator / cross-check sources cannot
+    be built; they are at least parsed and type-checked against declaration-only stand-ins of
+    the GStreamer headers (tests/gst_stub/README.md). Proves nothing about linking."""
+    r = subprocess.run(["gcc", "-fsyntax-only", "-std=gnu99", "-Wall", "-Werror",
+                        "-I", os.path.join(graft.ROOT, "tests", "gst_stub"),
+                        "-I", os.path.join(graft.ROOT, "include"), "-I", os.path.join(graft.ROOT, "oracle"),
+                        os.path.join(graft.ROOT, src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
