@@ -521,7 +521,8 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   const uint32_t chunk = r * P.per_lane + q;
   if (chunk >= P.total_chunks)
     return;
-  const uint32_t frame = P.n_frames == 1u ? 0u : __umulhi (chunk, P.cpf_magic);
+  /* ceil (2^32 / 1) does not fit the magic: one chunk per frame is its own case */
+  const uint32_t frame = P.chunks_per_frame == 1u ? chunk : __umulhi (chunk, P.cpf_magic);
   const uint32_t cif = chunk - frame * P.chunks_per_frame;
   uint32_t b = 0;
   for (uint32_t i = 1; i < P.n_bands; i++)

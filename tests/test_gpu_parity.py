@@ -514,3 +514,35 @@ def test_fuzz_random_geometry(ctx, seed):
     for mode in MODES:
         got = gpu_blend(ctx, fmt, w, h, planes, rects, mode=mode, dest_premul=dprem, stream=40 + seed)
         assert_planes_equal(got, want, f"seed {seed} {fmt} {w}x{h} {mode}")
+
+
+@pytest.mark.parametrize("fmt,w,h,with_cue", [("BGRA", 32, 32, False), ("BGRA", 64, 64, True),
+                                               ("NV12", 64, 32, True), ("I420", 16, 16, False)])
+def test_many_tiny_frames_in_one_group(ctx, fmt, w, h, with_cue):
+    """Frames of one or a few chunks each, many per group launch (one chunk per frame is a
+    corner of the frame-index arithmetic)."""
+    n = 48
+    ctx.set_batch(64, 0)
+    try:
+        rects = [dict(pixels=random_overlay(w, h // 2, 77), x=0, y=h // 4)] if with_cue else []
+        if with_cue:
+            ctx.overlay_set_rectangles(66, rects)
+        else:
+            ctx.overlay_clear(66)
+        frames = [random_frame(fmt, w, h, 6000 + i) for i in range(n)]
+        srcs = [ctx.acquire(fmt, w, h) for _ in range(n)]
+        dsts = [ctx.acquire(fmt, w, h) for _ in range(n)]
+        for s_, f in zip(srcs, frames):
+            s_.upload(f)
+        before = ctx.stats()
+        tickets = ctx.submit_many(ctx.Batch([66] * n, fmt, w, h, [s_.c for s_ in srcs], [d.c for d in dsts]))
+        ctx.wait(max(tickets))
+        after = ctx.stats()
+        assert after["group_launches"] - before["group_launches"] == 1
+        for i in range(n):
+            want = oracle_blend(fmt, w, h, copy_planes(frames[i]), rects)
+            assert_planes_equal(dsts[i].download(), want, f"tiny frame {i}")
+        for f in srcs + dsts:
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)

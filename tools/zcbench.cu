@@ -107,6 +107,36 @@ int main() {
     cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     rep("DMA h->d || kernel STG d->h", ms / 10, 2);
   }
+  {
+    // the e2e pattern: per frame 4 pieces (rows under two cue regions, luma + chroma of 4K NV12),
+    // DMA host->device of batch i+1 while a kernel stores batch i device->host
+    const size_t piece[4] = {1382400, 552960, 691200, 276480};
+    const int frames = 32; size_t per_frame = 0; for (size_t p : piece) per_frame += p;
+    cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    auto go = [&]() {
+      size_t off = 0;
+      for (int f = 0; f < frames; f++) for (size_t p : piece) { cudaMemcpyAsync(d1 + off, h1 + off, p, cudaMemcpyHostToDevice, s1); off += p; }
+      size_t nn = per_frame * frames / 16;
+      zc_ldg<4><<<(nn + 1023) / 1024, 256, 0, s2>>>((uint4*)d2, (uint4*)h2, nn);
+    };
+    for (int w = 0; w < 2; w++) go();
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, s1); cudaStreamWaitEvent(s2, e0, 0);
+    for (int i = 0; i < 10; i++) go();
+    cudaEventRecord(e2, s2); cudaStreamWaitEvent(s1, e2, 0); cudaEventRecord(e1, s1);
+    cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %8.3f ms per 32 frames -> %.0f frames/s, %.1f GB/s per direction\n", "frame pieces: DMA h->d || kernel STG d->h", ms / 10, frames / (ms / 10) * 1e3, per_frame * frames / (ms / 10) / 1e6);
+    auto go2 = [&]() {   // zero-copy shape: one kernel reads and writes host
+      size_t nn = per_frame * frames / 16;
+      zc_ldg<4><<<(nn + 1023) / 1024, 256, 0, s2>>>((uint4*)h1, (uint4*)h1, nn);
+    };
+    for (int w = 0; w < 2; w++) go2();
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0, s2);
+    for (int i = 0; i < 10; i++) go2();
+    cudaEventRecord(e1, s2); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %8.3f ms per 32 frames -> %.0f frames/s, %.1f GB/s per direction\n", "frame pieces: one kernel LDG+STG host", ms / 10, frames / (ms / 10) * 1e3, per_frame * frames / (ms / 10) / 1e6);
+  }
   rep("DMA H2D + D2H concurrently", timeit([&] { cudaMemcpyAsync(d1, h1, bytes, cudaMemcpyHostToDevice, s1); cudaMemcpyAsync(h2, d2, bytes, cudaMemcpyDeviceToHost, s2); cudaStreamSynchronize(s1); cudaStreamSynchronize(s2); }, 5), 2);
   rep("DMA H2D only", timeit([&] { cudaMemcpyAsync(d1, h1, bytes, cudaMemcpyHostToDevice, 0); }, 5), 1);
   return 0;
