@@ -1592,6 +1592,10 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
     } else {
       zf.plane[pl] = attr.devicePointer;
       zf.stride[pl] = hf->stride[pl];
+      /* byte-granular accesses to host memory would each cross PCIe: frames that are not
+       * 16-byte aligned go through the staging lanes (DMA, then the vector kernel) instead */
+      if ((((uintptr_t) zf.plane[pl] | (uintptr_t) zf.stride[pl]) & 15u) != 0)
+        mapped = false;
     }
   }
 

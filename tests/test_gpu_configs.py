@@ -5,7 +5,7 @@ outside the regions, batch == one-by-one)."""
 import numpy as np
 import pytest
 
-from helpers import assert_planes_equal, copy_planes, oracle_blend, pkg, wl
+from helpers import assert_planes_equal, copy_planes, oracle_blend, pkg, random_frame, random_overlay, wl
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -117,7 +117,6 @@ def test_256_streams_each_with_its_own_cue(ctx):
 def test_host_modes_agree(monkeypatch, mode, fmt, w, h):
     """FLUC_TTMLBLEND_HOST_MODE: 0 staged copies, 1 zero-copy (kernel reads/writes pinned host
     memory over PCIe, batched), 2 copy in + kernel writes back. Same bytes in all three."""
-    from helpers import random_frame, random_overlay
     monkeypatch.setenv("FLUC_TTMLBLEND_HOST_MODE", mode)
     c = pkg.TtmlBlend(0)
     try:
@@ -152,3 +151,53 @@ def test_host_modes_agree(monkeypatch, mode, fmt, w, h):
         c.host_unregister(buf)
     finally:
         c.close()
+
+
+def test_very_wide_frame_splits_windows(ctx):
+    """A 32752-pixel-wide plane has 2047 vectors per row; the row/column division by
+    multiplication is only exact up to ~2050 rows there, so the host must cut the plane into
+    several windows (push_window). Checked against the oracle on the rows under the cue and
+    against the source everywhere else."""
+    fmt, w, h = "NV12", 32752, 2200
+    rects = [dict(pixels=np.ascontiguousarray(np.tile(random_overlay(256, 24, 3), (1, 100, 1))[:, :25000]),
+                  x=123, y=2100), dict(pixels=random_overlay(300, 40, 4), x=32600, y=7)]
+    planes = wl.make_frame(fmt, w, h, 99)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+    ctx.overlay_set_rectangles(31, rects)
+    src, dst = ctx.acquire(fmt, w, h), ctx.acquire(fmt, w, h)
+    try:
+        src.upload(planes)
+        ctx.wait(ctx.submit(31, fmt, w, h, src.c, dst.c))
+        assert_planes_equal(dst.download(), want, "wide out of place")
+        ctx.wait(ctx.submit(31, fmt, w, h, src.c, src.c))
+        assert_planes_equal(src.download(), want, "wide in place")
+    finally:
+        src.release()
+        dst.release()
+
+
+def test_unaligned_pinned_host_frame_uses_the_staging_lanes(ctx):
+    """Pinned host frames whose strides are not multiples of 16 must not be blended zero-copy
+    (byte accesses over PCIe); they take the DMA lanes and still come out right."""
+    fmt, w, h = "I420", 1000, 562          # chroma stride 500: 4-byte but not 16-byte aligned
+    rects = [dict(pixels=random_overlay(700, 120, 8), x=151, y=400)]
+    ctx.overlay_set_rectangles(32, rects)
+    planes = random_frame(fmt, w, h, 4242)
+    want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+    buf = np.zeros(sum(p.size for p in planes) + 64, dtype=np.uint8)
+    ctx.host_register(buf)
+    try:
+        off, views = 0, []
+        for p in planes:
+            v = buf[off:off + p.size].reshape(p.shape)
+            v[...] = p
+            views.append(v)
+            off += p.size
+        ctx.sync()
+        ctx.stats_reset()
+        ctx.wait(ctx.blend_host(32, fmt, w, h, views))
+        assert_planes_equal(views, want, "unaligned pinned")
+        assert ctx.stats()["group_launches"] == 0       # went through a lane (table kernel)
+    finally:
+        ctx.sync()
+        ctx.host_unregister(buf)
