@@ -1,0 +1,219 @@
+/*
+ * scheduler.cu -- the multi-stream batch scheduler: pending frames -> group launches and table
+ * launches, table slots uploaded on a copy stream, batch events / tickets, the linger thread.
+ * Shape after the reference's worker-thread-under-a-monitor
+ * (/root/reference/libs/flu/downloader/lib/fludownloader.c:490-532).
+ */
+#include "ttmlblend_internal.h"
+
+namespace tbh {
+
+cudaEvent_t
+event_get (Ctx *c)
+{
+  if (!c->event_pool.empty ()) {
+    cudaEvent_t e = c->event_pool.back ();
+    c->event_pool.pop_back ();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+  return e;
+}
+
+int
+slot_reserve (Ctx *c, TableSlot &s, size_t n)
+{
+  if (s.cap >= n)
+    return 0;
+  const size_t cap = std::max<size_t> (256, n * 2);
+  if (s.h_jobs) cudaFreeHost (s.h_jobs);
+  if (s.h_begin) cudaFreeHost (s.h_begin);
+  if (s.d_jobs) cudaFree (s.d_jobs);
+  if (s.d_begin) cudaFree (s.d_begin);
+  s.cap = 0;
+  CU (c, cudaHostAlloc ((void **) &s.h_jobs, cap * sizeof (PlaneJob), cudaHostAllocDefault));
+  CU (c, cudaHostAlloc ((void **) &s.h_begin, cap * sizeof (uint32_t), cudaHostAllocDefault));
+  CU (c, cudaMalloc ((void **) &s.d_jobs, cap * sizeof (PlaneJob)));
+  CU (c, cudaMalloc ((void **) &s.d_begin, cap * sizeof (uint32_t)));
+  if (!s.copied)
+    CU (c, cudaEventCreateWithFlags (&s.copied, cudaEventDisableTiming));
+  if (!s.uploaded)
+    CU (c, cudaEventCreateWithFlags (&s.uploaded, cudaEventDisableTiming));
+  s.cap = cap;
+  return 0;
+}
+
+/* Copies `jobs` (one PlaneKind) into a table slot and launches the kernel. */
+int
+launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast,
+    cudaStream_t stream)
+{
+  if (n == 0)
+    return 0;
+  if (s.copied && s.cap)
+    CU (c, cudaEventSynchronize (s.copied));
+  int rc = slot_reserve (c, s, n);
+  if (rc)
+    return rc;
+  uint32_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    s.h_jobs[i] = jobs[i];
+    s.h_begin[i] = total;
+    total += jobs[i].n_chunks;
+  }
+  /* the table goes up on the copy stream, so that it overlaps the kernel still
+   * running on `stream`; the slot is free (its last kernel waited on above) */
+  CU (c, cudaMemcpyAsync (s.d_jobs, s.h_jobs, n * sizeof (PlaneJob), cudaMemcpyHostToDevice, c->table_stream));
+  CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, n * sizeof (uint32_t), cudaMemcpyHostToDevice, c->table_stream));
+  CU (c, cudaEventRecord (s.uploaded, c->table_stream));
+  CU (c, cudaStreamWaitEvent (stream, s.uploaded, 0));
+  CU (c, launch_blend (s.d_jobs, s.d_begin, (int) n, total, kind, fast, stream));
+  CU (c, cudaEventRecord (s.copied, stream));    /* slot busy until this kernel is done */
+  c->stats.launches++;
+  return 0;
+}
+
+void
+reap_batches (Ctx *c)
+{
+  while (!c->batches.empty ()) {
+    Batch &b = c->batches.front ();
+    if (cudaEventQuery (b.done) != cudaSuccess)
+      break;
+    if (b.t0 && b.t1) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime (&ms, b.t0, b.t1) == cudaSuccess) {
+        c->stats.kernel_ms += ms;
+        c->stats.kernel_ms_launches++;
+      }
+      c->timing_pool.push_back (b.t0);
+      c->timing_pool.push_back (b.t1);
+    }
+    c->event_pool.push_back (b.done);
+    c->batches.pop_front ();
+  }
+}
+
+/* Launches everything pending as one batch (per plane kind). mu held. */
+int
+launch_pending (Ctx *c)
+{
+  if (c->pending.empty ())
+    return 0;
+  NvtxRange nvtx ("ttmlblend.launch_batch");
+  reap_batches (c);
+  Batch b = {};
+  b.last_ticket = c->pending.back ().ticket;
+  std::vector<PlaneJob> by_kind[6];     /* PlaneKind x {byte-granular, fast} */
+  std::vector<Group> &groups = c->groups;
+  groups.clear ();
+  for (PendingFrame &f : c->pending) {
+    for (const PlaneJob &j : f.jobs)
+      by_kind[f.kind * 2 + ((j.flags & JF_FAST) ? 1 : 0)].push_back (j);
+    if (f.grouped) {
+      Group *g = nullptr;
+      for (Group &o : groups)
+        if (group_accepts (o, f)) {
+          g = &o;
+          break;
+        }
+      if (!g) {
+        groups.emplace_back ();
+        g = &groups.back ();
+        group_start (*g, f);
+      }
+      g->P.frames[g->P.n_frames++] = f.ptrs;
+    }
+    if (f.overlay)
+      b.keep.push_back (f.overlay);
+    if (f.prep && !f.prep->blend_waited) {
+      /* once per prepared overlay: later launches follow in stream order */
+      f.prep->blend_waited = true;
+      CU (c, cudaStreamWaitEvent (c->blend_stream, f.prep->ready, 0));
+    }
+    c->stats.frames_blended++;
+    c->stats.algorithmic_bytes += f.algo_bytes;
+  }
+  c->pending.clear ();
+  c->pending_dst.clear ();
+  size_t n_launches = groups.size ();
+  for (int k = 0; k < 6; k++)
+    n_launches += !by_kind[k].empty ();
+  /* an event pair keeps the batch from overlapping its neighbours (~2 us of stream time):
+   * sample every profile_every-th batch. A batch of several launches (several groups /
+   * kinds) is timed from before its first to after its last launch. */
+  if (c->profiling && n_launches >= 1 && (c->profile_seq++ % c->profile_every) == 0) {
+    for (cudaEvent_t *e : { &b.t0, &b.t1 }) {
+      if (!c->timing_pool.empty ()) {
+        *e = c->timing_pool.back ();
+        c->timing_pool.pop_back ();
+      } else {
+        CU (c, cudaEventCreate (e));
+      }
+    }
+  }
+  if (b.t0)
+    CU (c, cudaEventRecord (b.t0, c->blend_stream));
+  for (Group &g : groups) {
+    CU (c, launch_group (g.P, g.kind, c->blend_stream));
+    c->stats.launches++;
+    c->stats.group_launches++;
+  }
+  for (int k = 0; k < 6; k++) {
+    if (by_kind[k].empty ())
+      continue;
+    TableSlot &s = c->slots[c->next_slot];
+    c->next_slot = (c->next_slot + 1) % kTableSlots;
+    int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0,
+        c->blend_stream);
+    if (rc)
+      return rc;
+  }
+  if (b.t1)
+    CU (c, cudaEventRecord (b.t1, c->blend_stream));
+  b.done = event_get (c);
+  CU (c, cudaEventRecord (b.done, c->blend_stream));
+  c->batches.push_back (std::move (b));
+  return 0;
+}
+
+void
+scheduler_main (Ctx *c)
+{
+  cudaSetDevice (c->device);
+  std::unique_lock<std::mutex> lk (c->mu);
+  while (!c->quit) {
+    if (c->pending.empty () || c->linger_us == 0) {
+      c->cv.wait (lk);
+      continue;
+    }
+    const auto deadline = c->oldest_pending + std::chrono::microseconds (c->linger_us);
+    if (std::chrono::steady_clock::now () >= deadline) {
+      if (!c->sticky)
+        launch_pending (c);
+      else {
+        c->pending.clear ();
+        c->pending_dst.clear ();
+      }
+    } else {
+      c->cv.wait_until (lk, deadline);
+    }
+  }
+}
+
+int
+lane_reserve (Ctx *c, Lane &l, size_t bytes)
+{
+  if (l.dev_bytes >= bytes)
+    return 0;
+  if (l.dev)
+    CU (c, cudaFree (l.dev));
+  l.dev = nullptr;
+  l.dev_bytes = 0;
+  CU (c, cudaMalloc ((void **) &l.dev, bytes));
+  l.dev_bytes = bytes;
+  return 0;
+}
+
+}  // namespace tbh

@@ -1,0 +1,298 @@
+/*
+ * ttmlblend_internal.h -- shared declarations of the host runtime behind the C ABI
+ * (include/fluc_ttmlblend.h). Private to csrc/. The runtime is split by concern:
+ *   overlay_cache.cu  upload, auto-crop, once-per-cue prepare, deferred frees
+ *   jobs.cu           frame -> bands / windows / job classes / groups
+ *   scheduler.cu      batches, table slots, launches, the scheduler thread
+ *   fluc_ttmlblend.cu the extern "C" entry points (context, submit, host frames, pool, stats)
+ */
+#ifndef TTMLBLEND_INTERNAL_H
+#define TTMLBLEND_INTERNAL_H
+
+#include "../../include/fluc_ttmlblend.h"
+#include "ttmlblend_kernels.cuh"
+
+#include <nvtx3/nvToolsExt.h>       /* header-only: ranges show up in nsys / ncu timelines */
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace tbh {
+
+using namespace tb;
+
+/* ---------------------------------------------------------------------- */
+/* format geometry                                                        */
+
+enum FormatClass { FC_I420, FC_YV12, FC_NV12, FC_NV21, FC_AYUV, FC_ARGB, FC_ABGR, FC_RGBA, FC_BGRA, FC_COUNT };
+
+inline bool
+format_valid (int f)
+{
+  return f >= 0 && f < FLUC_TTMLBLEND_FORMAT_COUNT;
+}
+
+inline int
+format_planes (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_I420:
+    case FLUC_TTMLBLEND_FORMAT_YV12:
+      return 3;
+    case FLUC_TTMLBLEND_FORMAT_NV12:
+    case FLUC_TTMLBLEND_FORMAT_NV21:
+      return 2;
+    default:
+      return 1;
+  }
+}
+
+inline int
+plane_row_bytes (int f, int plane, int w)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_I420:
+    case FLUC_TTMLBLEND_FORMAT_YV12:
+      return plane == 0 ? w : (w + 1) / 2;
+    case FLUC_TTMLBLEND_FORMAT_NV12:
+    case FLUC_TTMLBLEND_FORMAT_NV21:
+      return plane == 0 ? w : 2 * ((w + 1) / 2);
+    default:
+      return 4 * w;
+  }
+}
+
+inline int
+plane_rows (int f, int plane, int h)
+{
+  return (format_planes (f) > 1 && plane > 0) ? (h + 1) / 2 : h;
+}
+
+inline int
+plane_kind (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_AYUV:
+    case FLUC_TTMLBLEND_FORMAT_ARGB:
+    case FLUC_TTMLBLEND_FORMAT_ABGR:
+      return PK_PACKED_A0;
+    case FLUC_TTMLBLEND_FORMAT_RGBA:
+    case FLUC_TTMLBLEND_FORMAT_BGRA:
+      return PK_PACKED_A3;
+    default:
+      return PK_PLANE8;
+  }
+}
+
+inline int ceil_div (int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up (size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+/* ---------------------------------------------------------------------- */
+/* overlay cache                                                          */
+
+struct Ctx;
+
+/* device copy of one rectangle's BGRA pixels (left/top clipped at 0) */
+struct RawRect {
+  uint8_t *dev = nullptr;
+  int pitch = 0, w = 0, h = 0;
+  int x = 0, y = 0;
+  int ga = 255;
+  bool premul = true;
+};
+
+/* everything frame-independent, for one (format, W, H) */
+struct Prepared {
+  int format = -1, W = 0, H = 0;
+  std::vector<void *> allocs;
+  std::vector<RectRef> h_rects[3];     /* per plane, host copy */
+  std::vector<RectRef> h_rects_all;
+  RectRef *d_rects[3] = { nullptr, nullptr, nullptr };
+  RectRef *d_rects_all = nullptr;      /* the three tables, contiguous */
+  int32_t rect_off[3] = { 0, 0, 0 };   /* first entry of plane p in d_rects_all */
+  uint64_t overlay_px = 0;             /* sum of clipped w*h */
+  cudaEvent_t ready = nullptr;
+  bool blend_waited = false;           /* blend stream already ordered after `ready` */
+};
+
+struct Overlay {
+  Ctx *ctx = nullptr;
+  std::vector<RawRect> rects;          /* what gets prepared: cropped to non-transparent pixels */
+  std::vector<void *> raw_allocs;      /* device copies the rects point into */
+  std::vector<FlucTtmlBlendRect> declared;   /* rectangles as handed in (algorithmic bytes) */
+  std::vector<std::unique_ptr<Prepared>> prepared;
+  ~Overlay ();
+};
+
+struct PendingFrame {
+  uint64_t ticket;
+  std::shared_ptr<Overlay> overlay;
+  Prepared *prep;
+  int kind;
+  std::vector<PlaneJob> jobs;          /* generic-kernel jobs (byte-granular parts, odd frames) */
+  uint64_t algo_bytes;
+  /* group launch: the fast windows as a band list + this frame's pointers */
+  bool grouped = false;
+  std::vector<BandDesc> bands;
+  FramePtrs ptrs;
+  int32_t src_pitch[3], dst_pitch[3], rect_off[3], gflags;
+  uint32_t chunks_per_frame = 0;
+  const void *dst0 = nullptr;
+};
+
+/* frames that can share one launch: everything but the pointers is equal */
+struct Group {
+  int kind;
+  GroupParams P;
+};
+
+struct Batch {
+  uint64_t last_ticket;
+  cudaEvent_t done;
+  cudaEvent_t t0, t1;                  /* profiling pair (may be null) */
+  std::vector<std::shared_ptr<Overlay>> keep;
+};
+
+struct TableSlot {
+  PlaneJob *h_jobs = nullptr, *d_jobs = nullptr;
+  uint32_t *h_begin = nullptr, *d_begin = nullptr;
+  size_t cap = 0;
+  cudaEvent_t copied = nullptr;        /* last kernel that read the slot has finished */
+  cudaEvent_t uploaded = nullptr;      /* table copy has landed */
+};
+
+struct PoolEntry {
+  void *base;
+  size_t bytes;
+  int fmt, W, H, on_host;
+  FlucTtmlBlendFrame frame;
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint64_t ticket = 0;
+  bool busy = false;
+  uint8_t *dev = nullptr;
+  size_t dev_bytes = 0;
+  TableSlot table[2];
+  std::shared_ptr<Overlay> keep;
+};
+
+/* How blend_host moves a device-accessible (pinned) host frame. */
+enum HostMode { HM_STAGED = 0, HM_ZEROCOPY = 1, HM_WRITEBACK = 2 };
+
+constexpr int kLanes = 4;
+constexpr int kTableSlots = 8;
+
+struct Ctx {
+  int device = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int sticky = 0;
+  std::string cuda_error;
+
+  cudaStream_t blend_stream = nullptr, up_stream = nullptr, reaper = nullptr, table_stream = nullptr;
+  cudaEvent_t ev_fence[kLanes + 2] = {};
+  cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+
+  std::unordered_map<uint32_t, std::shared_ptr<Overlay>> overlays;
+
+  std::vector<PendingFrame> pending;
+  std::vector<Group> groups;           /* scratch of launch_pending */
+  std::unordered_set<const void *> pending_dst;   /* destination buffers queued in `pending` */
+  std::vector<cudaEvent_t> timing_pool;
+  std::chrono::steady_clock::time_point oldest_pending;
+  uint64_t next_ticket = 0;
+  std::deque<Batch> batches;
+  std::vector<cudaEvent_t> event_pool;
+  TableSlot slots[kTableSlots];
+  int next_slot = 0;
+
+  uint32_t max_batch = 32, linger_us = 200;
+  int host_mode = HM_ZEROCOPY;
+  bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
+  bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
+  bool profiling = false;
+  uint32_t profile_every = 1, profile_seq = 0;   /* FLUC_TTMLBLEND_PROFILE_EVERY */
+  std::thread sched;
+  bool quit = false;
+
+  Lane lanes[kLanes];
+  int next_lane = 0;
+  std::map<uint64_t, int> lane_tickets;
+
+  std::vector<PoolEntry> pool_free, pool_used;
+  uint8_t *scrub = nullptr;
+  size_t scrub_bytes = 0;
+
+  FlucTtmlBlendStats stats = {};
+};
+
+#define CU(ctx, call) do {                                                   \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) {                                                 \
+      (ctx)->sticky = FLUC_TTMLBLEND_ERROR_CUDA;                             \
+      (ctx)->cuda_error = std::string (#call) + ": " + cudaGetErrorString (e_); \
+      return e_ == cudaErrorMemoryAllocation ?                               \
+          FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY : FLUC_TTMLBLEND_ERROR_CUDA;    \
+    }                                                                        \
+  } while (0)
+
+inline int
+log_level ()
+{
+  static int lvl = -1;
+  if (lvl < 0) {
+    const char *e = getenv ("FLUC_TTMLBLEND_DEBUG");
+    lvl = e ? atoi (e) : 0;
+  }
+  return lvl;
+}
+
+/* NVTX range for the current scope */
+struct NvtxRange {
+  explicit NvtxRange (const char *name) { nvtxRangePushA (name); }
+  ~NvtxRange () { nvtxRangePop (); }
+};
+
+#define TBLOG(n, ...) do { if (log_level () >= (n)) { fprintf (stderr, "ttmlblend: " __VA_ARGS__); fputc ('\n', stderr); } } while (0)
+
+/* overlay_cache.cu */
+void free_deferred (Ctx *c, const std::vector<void *> &ptrs);
+int prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out);
+std::vector<FlucTtmlBlendRect> disjoint_cover (const std::vector<FlucTtmlBlendRect> &in);
+int overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n);
+
+/* jobs.cu */
+int check_frame (int fmt, int W, int H, const FlucTtmlBlendFrame *f);
+uint64_t build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
+    const FlucTtmlBlendFrame *dst, const Prepared *prep, bool windowed, std::vector<PlaneJob> &jobs);
+void make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst);
+bool group_accepts (const Group &g, const PendingFrame &f);
+void group_start (Group &g, const PendingFrame &f);
+
+/* scheduler.cu */
+cudaEvent_t event_get (Ctx *c);
+int launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast, cudaStream_t stream);
+void reap_batches (Ctx *c);
+int launch_pending (Ctx *c);
+void scheduler_main (Ctx *c);
+int lane_reserve (Ctx *c, Lane &l, size_t bytes);
+
+}  // namespace tbh
+#endif
