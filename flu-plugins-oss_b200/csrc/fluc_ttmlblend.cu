@@ -273,6 +273,16 @@ fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream)
   return 0;
 }
 
+int
+fluc_ttmlblend_set_chroma_mode (FlucTtmlBlend *thiz, int mode)
+{
+  ENTER (thiz);
+  if (mode != FLUC_TTMLBLEND_CHROMA_SITED && mode != FLUC_TTMLBLEND_CHROMA_AVERAGE)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  c->chroma_average = mode == FLUC_TTMLBLEND_CHROMA_AVERAGE;
+  return 0;
+}
+
 /* ---- device-resident frames ------------------------------------------ */
 
 static int

@@ -64,7 +64,7 @@ int
 prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
 {
   for (auto &p : ov->prepared)
-    if (p->format == format && p->W == W && p->H == H) {
+    if (p->format == format && p->W == W && p->H == H && p->chroma_average == c->chroma_average) {
       *out = p.get ();
       return 0;
     }
@@ -75,6 +75,7 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
   P->format = format;
   P->W = W;
   P->H = H;
+  P->chroma_average = c->chroma_average;
   const int kind = plane_kind (format);
   const int n_planes = format_planes (format);
 
@@ -130,9 +131,11 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
         c->stats.prepare_launches++;
         P->h_rects[0].push_back (ref);
       }
-      /* chroma: the samples sited on even x / even y */
-      const int bx0 = ceil_div (cx0, 2), bx1 = ceil_div (cx1, 2);
-      const int by0 = ceil_div (cy0, 2), by1 = ceil_div (cy1, 2);
+      /* chroma: the samples sited on even x / even y (parity); with the non-parity 2x2
+       * average every sample with at least one covered pixel */
+      pp.chroma_average = P->chroma_average ? 1 : 0;
+      const int bx0 = P->chroma_average ? cx0 / 2 : ceil_div (cx0, 2), bx1 = ceil_div (cx1, 2);
+      const int by0 = P->chroma_average ? cy0 / 2 : ceil_div (cy0, 2), by1 = ceil_div (cy1, 2);
       if (bx1 > bx0 && by1 > by0) {
         if (n_planes == 3) {
           RectRef ref = {};

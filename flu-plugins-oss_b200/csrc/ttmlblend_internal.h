@@ -118,6 +118,7 @@ struct RawRect {
 /* everything frame-independent, for one (format, W, H) */
 struct Prepared {
   int format = -1, W = 0, H = 0;
+  bool chroma_average = false;         /* prepared with the non-parity 2x2 chroma mean */
   std::vector<void *> allocs;
   std::vector<RectRef> h_rects[3];     /* per plane, host copy */
   std::vector<RectRef> h_rects_all;
@@ -225,6 +226,7 @@ struct Ctx {
 
   uint32_t max_batch = 32, linger_us = 200;
   int host_mode = HM_ZEROCOPY;
+  bool chroma_average = false;         /* fluc_ttmlblend_set_chroma_mode (1): NOT bit-exact */
   bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
   bool profiling = false;

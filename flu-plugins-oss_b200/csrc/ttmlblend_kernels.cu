@@ -773,11 +773,75 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
   }
 }
 
+/* NON-PARITY option (fluc_ttmlblend_set_chroma_mode): each 4:2:0 chroma sample takes the
+ * alpha-weighted mean colour and the mean alpha of its 2x2 luma pixels instead of the
+ * pixel sited at (even x, even y). GStreamer does not do this (BLENDSPEC section 4), so the
+ * result is no longer bit-exact with the reference; it removes the chroma fringes the
+ * point-sampled siting leaves under anti-aliased glyph edges. One thread per luma column of
+ * the 2x2 blocks: it sums its two rows, the horizontal neighbour's sums arrive by warp
+ * shuffle, the even lane writes the sample. */
+__global__ void __launch_bounds__ (256)
+ttmlblend_prepare_chroma_avg_kernel (const PrepareParams p, int n_cols)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      /* luma column inside the span */
+  const int r = blockIdx.y;
+  const bool semi = p.mode != PM_CHROMA_PLANAR;
+  const int x = 2 * (semi ? p.v0 * 8 : p.v0 * 16) + i;
+  int sa = 0, su = 0, sv = 0;
+  if (i < n_cols && x >= p.cx0 && x < p.cx1) {
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+      const int y = 2 * (p.row0 + r) + dy;
+      if (y >= p.cy0 && y < p.cy1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), p.premul != 0);
+        const int asrc = s.a * p.ga / 255;
+        sa += asrc;
+        su += asrc * s.u;
+        sv += asrc * s.v;
+      }
+    }
+  }
+  sa += __shfl_xor_sync (0xffffffffu, sa, 1);
+  su += __shfl_xor_sync (0xffffffffu, su, 1);
+  sv += __shfl_xor_sync (0xffffffffu, sv, 1);
+  if ((i & 1) || i >= n_cols)
+    return;
+  const uint8_t a = (uint8_t) ((sa + 2) >> 2);
+  const uint8_t u = sa && a ? (uint8_t) ((su + sa / 2) / sa) : 0;
+  const uint8_t v = sa && a ? (uint8_t) ((sv + sa / 2) / sa) : 0;
+  const size_t orow = (size_t) r * p.out_pitch;
+  const int k = i >> 1;                                      /* chroma sample inside the span */
+  if (!semi) {
+    p.out_a[orow + k] = a;
+    p.out_c[orow + k] = u;
+    p.out_c2[orow + k] = v;
+  } else {
+    p.out_a[orow + 2 * k] = a;
+    p.out_a[orow + 2 * k + 1] = a;
+    p.out_c[orow + 2 * k] = p.mode == PM_CHROMA_UV ? u : v;
+    p.out_c[orow + 2 * k + 1] = p.mode == PM_CHROMA_UV ? v : u;
+  }
+}
+
 cudaError_t
 launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream)
 {
   if (n_elems <= 0 || p.rows <= 0)
     return cudaSuccess;
+  if (p.chroma_average && p.mode >= PM_CHROMA_PLANAR && p.mode <= PM_CHROMA_VU) {
+    for (int r0 = 0; r0 < p.rows; r0 += 65535) {
+      PrepareParams q = p;
+      const int nr = min (65535, p.rows - r0);
+      q.row0 = p.row0 + r0;
+      q.rows = nr;
+      q.out_a = p.out_a + (size_t) r0 * p.out_pitch;
+      q.out_c = p.out_c + (size_t) r0 * p.out_pitch;
+      if (p.out_c2) q.out_c2 = p.out_c2 + (size_t) r0 * p.out_pitch;
+      dim3 grid ((2 * n_elems + 255) / 256, nr);
+      ttmlblend_prepare_chroma_avg_kernel<<<grid, 256, 0, stream>>> (q, 2 * n_elems);
+    }
+    return cudaGetLastError ();
+  }
   const int rows_per_launch = 65535;
   for (int r0 = 0; r0 < p.rows; r0 += rows_per_launch) {
     PrepareParams q = p;

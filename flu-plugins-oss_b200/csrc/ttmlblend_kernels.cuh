@@ -138,6 +138,7 @@ struct PrepareParams {
   int32_t v0;                   /* first vector column of the prepared span */
   int32_t row0, rows;           /* first plane row and number of prepared rows */
   int32_t mode;
+  int32_t chroma_average;       /* non-parity option: 2x2 alpha-weighted chroma instead of the sited pixel */
 };
 
 enum PrepareMode : int32_t {

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "fluc_ttmlblend_overlay_set_rectangles": (C.c_int, [C.c_void_p, C.c_uint32,
                                                         C.POINTER(Rectangle), C.c_uint32]),
     "fluc_ttmlblend_overlay_clear": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "fluc_ttmlblend_set_chroma_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "fluc_ttmlblend_submit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
                                         C.c_uint32, C.POINTER(Frame), C.POINTER(Frame),
                                         C.POINTER(C.c_uint64)]),
@@ -265,6 +266,10 @@ class TtmlBlend:
 
     def overlay_clear(self, stream: int):
         self._check(self.lib.fluc_ttmlblend_overlay_clear(self.h, stream), "overlay_clear")
+
+    def set_chroma_mode(self, average: bool):
+        """False (default): GStreamer's sited chroma, bit-exact. True: 2x2 mean, NOT bit-exact."""
+        self._check(self.lib.fluc_ttmlblend_set_chroma_mode(self.h, 1 if average else 0), "set_chroma_mode")
 
     # -- device-resident frames -----------------------------------------
     def submit(self, stream: int, fmt: str, width: int, height: int, src: Frame, dst: Frame,

@@ -146,6 +146,15 @@ FLUC_EXPORT int fluc_ttmlblend_overlay_set_rectangles (FlucTtmlBlend *thiz,
  * (/root/reference/plugins/ttml/gstttmlevent.c:221-224): frames pass through. */
 FLUC_EXPORT int fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream);
 
+/* How the overlay reaches the chroma planes of 4:2:0 frames. SITED (default) is what
+ * GStreamer does and the only bit-exact mode: a chroma sample takes the overlay pixel at
+ * (even x, even y). AVERAGE is an explicit NON-PARITY option: the alpha-weighted mean of
+ * the 2x2 pixels (no chroma fringes under anti-aliased glyph edges). Applies to overlays
+ * prepared after the call. */
+#define FLUC_TTMLBLEND_CHROMA_SITED 0
+#define FLUC_TTMLBLEND_CHROMA_AVERAGE 1
+FLUC_EXPORT int fluc_ttmlblend_set_chroma_mode (FlucTtmlBlend *thiz, int mode);
+
 /* ---- per frame, device-resident (batched) ---------------------------- */
 /* Queues one frame. src/dst hold DEVICE pointers; dst == src (same plane[0])
  * blends in place like gst_video_blend does, otherwise the whole frame is

@@ -82,8 +82,9 @@ def _over(cs, cd, asrc, adst, ga, sp, dp):
     return np.minimum(v, 255), fa
 
 
-def model_blend(fmt, w, h, planes, rectangles, dest_premul=False):
-    """Blends in place on `planes` and returns them."""
+def model_blend(fmt, w, h, planes, rectangles, dest_premul=False, chroma_average=False):
+    """Blends in place on `planes` and returns them. chroma_average=True models the library's
+    NON-PARITY 2x2 chroma option (fluc_ttmlblend_set_chroma_mode), not GStreamer."""
     fmt = fmt.upper()
     for rc in rectangles:
         px = rc["pixels"].astype(np.int64)
@@ -113,6 +114,34 @@ def model_blend(fmt, w, h, planes, rectangles, dest_premul=False):
             yd = Y[y0:y1, x0:x1].astype(np.int64)
             v, _ = _over(c1, yd, asrc, 255, ga, sp, dest_premul)
             Y[y0:y1, x0:x1] = np.where(m, v, yd).astype(np.uint8)
+            if chroma_average:
+                # every chroma sample with a covered pixel: alpha = mean of the 4 alphas (outside
+                # the rectangle counts as 0), colour = alpha-weighted mean
+                bx0, bx1, by0, by1 = x0 // 2, (x1 + 1) // 2, y0 // 2, (y1 + 1) // 2
+                pa = np.zeros((2 * (by1 - by0), 2 * (bx1 - bx0)), dtype=np.int64)
+                pu, pv = pa.copy(), pa.copy()
+                sl = (slice(y0 - 2 * by0, y0 - 2 * by0 + (y1 - y0)), slice(x0 - 2 * bx0, x0 - 2 * bx0 + (x1 - x0)))
+                pa[sl], pu[sl], pv[sl] = asrc, asrc * c2, asrc * c3
+                blk = lambda t: t[0::2, 0::2] + t[0::2, 1::2] + t[1::2, 0::2] + t[1::2, 1::2]
+                sa, su, sv = blk(pa), blk(pu), blk(pv)
+                ca = (sa + 2) >> 2
+                den = np.where(sa == 0, 1, sa)
+                cu, cv = (su + sa // 2) // den, (sv + sa // 2) // den
+                cm = ca > 0
+                nby, nbx = ca.shape
+                if fmt in ("I420", "YV12"):
+                    iu, iv = (1, 2) if fmt == "I420" else (2, 1)
+                    for plane, cc in ((planes[iu], cu), (planes[iv], cv)):
+                        d = plane[by0:by0 + nby, bx0:bx0 + nbx].astype(np.int64)
+                        plane[by0:by0 + nby, bx0:bx0 + nbx] = np.where(cm, (cc * ca + d * (255 - ca)) // 255, d).astype(np.uint8)
+                else:
+                    ou, ovv = (0, 1) if fmt == "NV12" else (1, 0)
+                    UV = planes[1]
+                    for off, cc in ((ou, cu), (ovv, cv)):
+                        view = UV[by0:by0 + nby, 2 * bx0 + off:2 * (bx0 + nbx):2]
+                        d = view.astype(np.int64)
+                        view[...] = np.where(cm, (cc * ca + d * (255 - ca)) // 255, d).astype(np.uint8)
+                continue
             # chroma sample (bx, by) <- overlay pixel at frame (2bx, 2by) only
             ex0, ey0 = x0 + (x0 & 1), y0 + (y0 & 1)
             if ex0 < x1 and ey0 < y1:

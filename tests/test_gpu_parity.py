@@ -546,3 +546,34 @@ def test_many_tiny_frames_in_one_group(ctx, fmt, w, h, with_cue):
             f.release()
     finally:
         ctx.set_batch(32, 200)
+
+
+@pytest.mark.parametrize("fmt", PLANAR_420)
+@pytest.mark.parametrize("w,h,rect", [(64, 48, (31, 15, 7, 9)), (63, 47, (40, 30, -10, -7)),
+                                      (200, 120, (150, 60, 33, 41)), (33, 21, (80, 60, -20, -20))])
+def test_chroma_average_option_is_what_it_says(fmt, w, h, rect):
+    """fluc_ttmlblend_set_chroma_mode (AVERAGE): an explicit NON-PARITY option (GStreamer sites
+    chroma on the even pixel). Checked against its own numpy model; luma stays bit-exact with
+    the oracle, and the default mode is untouched."""
+    from helpers import model_blend
+    rw, rh, x, y = rect
+    rects = [dict(pixels=random_overlay(rw, rh, 51), x=x, y=y),
+             dict(pixels=random_overlay(20, 10, 52, premultiplied=False), x=w // 2, y=h // 3,
+                  premultiplied=False, global_alpha=0.8)]
+    planes = random_frame(fmt, w, h, 53)
+    c = pkg.TtmlBlend(0)
+    try:
+        c.set_chroma_mode(True)
+        want = model_blend(fmt, w, h, copy_planes(planes), rects, chroma_average=True)
+        sited = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+        for mode in MODES:
+            got = gpu_blend(c, fmt, w, h, planes, rects, mode=mode)
+            assert_planes_equal(got, want, f"{fmt} average {mode}")
+            assert np.array_equal(got[0], sited[0])                 # luma is not affected
+        c.set_chroma_mode(False)
+        c.overlay_set_rectangles(1, rects)
+        got = gpu_blend(c, fmt, w, h, planes, rects, mode="out")
+        assert_planes_equal(got, sited, f"{fmt} back to sited")
+        assert c.lib.fluc_ttmlblend_set_chroma_mode(c.h, 7) == pkg.ttmlblend.ERROR_INVALID_ARGUMENT
+    finally:
+        c.close()
