@@ -22,6 +22,16 @@ def test_div255_magic_is_exact():
     x = np.arange(0, 66299, dtype=np.uint64)
     assert np.array_equal((x * 32897) >> 23, x // 255)
     assert ((66299 * 32897) >> 23) != 66299 // 255      # and the bound is tight
+    # the two-lane form the kernels use: (x + 1 + (x >> 8)) >> 8, exact up to 65534
+    x = np.arange(0, 65535, dtype=np.uint64)
+    assert np.array_equal((x + 1 + (x >> 8)) >> 8, x // 255)
+    assert ((65535 + 1 + (65535 >> 8)) >> 8) != 65535 // 255
+    # two lanes in one 32-bit register never carry into each other (lanes <= 255*255)
+    lo, hi = np.meshgrid(np.array([0, 1, 254, 255, 65024, 65025], dtype=np.uint64),
+                         np.array([0, 1, 254, 255, 65024, 65025], dtype=np.uint64))
+    e = (lo | (hi << 16)) & 0xFFFFFFFF
+    t = (e + ((e >> 8) & 0x00FF00FF) + 0x00010001) & 0xFFFFFFFF
+    assert np.array_equal((t >> 8) & 0xFF, lo // 255) and np.array_equal((t >> 24) & 0xFF, hi // 255)
 
 
 def test_magic_row_division_is_exact():
