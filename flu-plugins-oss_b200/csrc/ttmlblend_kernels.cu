@@ -74,13 +74,6 @@ st_frame_bytes (uint8_t *p, const uint4 &v, int nvalid)
 /* ---------------------------------------------------------------------- */
 /* arithmetic                                                             */
 
-/* x / 255 (truncating) for 0 <= x <= 66298; every caller stays <= 65025 */
-__device__ __forceinline__ uint32_t
-div255 (uint32_t x)
-{
-  return (x * 32897u) >> 23;
-}
-
 /* PLANE8: four destination bytes. Opaque destination, straight source:
  *   out = (Cs * asrc + Cd * (255 - asrc)) / 255        (OVER00, adst = 255)
  * asrc == 0 leaves Cd untouched by the same formula, like the `continue`.
