@@ -227,7 +227,9 @@ def main():
     ap.add_argument("--format", default=None, help="override the config's frame format (config 4: RGBA/BGRA/AYUV)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--inplace", action="store_true", help="also time the in-place variant")
+    ap.add_argument("--no-inplace", dest="inplace", action="store_false",
+                    help="skip the in-place variant (reported separately, SURVEY 8d: B_inplace)")
+    ap.add_argument("--inplace", dest="inplace", action="store_true", default=True)
     ap.add_argument("--profile-every", type=int, default=16,
                     help="CUDA-event pair around every n-th launch of the timed region (roofline)")
     args = ap.parse_args()
@@ -345,7 +347,10 @@ def main():
         ms_ip = ctx.timer_end()
         st_ip = ctx.stats()
         inplace = {"value": batch * args.steps / (ms_ip * 1e-3), "unit": UNIT,
-                   "algorithmic_gbs": st_ip["algorithmic_bytes"] / (ms_ip * 1e-3) / 1e9}
+                   "bytes_per_frame": st_ip["algorithmic_bytes"] // max(1, st_ip["frames_blended"]),
+                   "algorithmic_gbs": st_ip["algorithmic_bytes"] / (ms_ip * 1e-3) / 1e9,
+                   "note": "dst == src: only the rows under the cue regions are read and written "
+                           "(B_inplace = 2 x touched frame bytes + 4 B/px overlay); this rank only"}
 
     # e2e: pinned host frames through the drop-in call, PCIe copies inside the timed region
     e2e = None

@@ -275,3 +275,19 @@ def test_fuzz_oracle_vs_model(seed):
     b = model_blend(fmt, w, h, copy_planes(planes), rects, dprem)
     for i, (p, q) in enumerate(zip(a, b)):
         assert np.array_equal(p, q), (fmt, seed, i, int((p != q).sum()))
+
+
+def test_oracle_under_asan_ubsan(tmp_path):
+    """The C oracle over awkward geometry (1x1 frames, rectangles hanging over every border,
+    exact-size allocations) built with -fsanitize=address,undefined: no out-of-bounds access,
+    no signed overflow, no misaligned load."""
+    import subprocess
+    exe = str(tmp_path / "selftest")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-O1", "-g", "-std=c99", "-D_POSIX_C_SOURCE=200809L",
+                           "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                           "-o", exe, os.path.join(root, "oracle", "selftest.c"),
+                           os.path.join(root, "oracle", "ttmlblend_ref.c"), "-lpthread", "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failure(s)" in r.stdout
