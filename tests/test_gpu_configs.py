@@ -201,3 +201,48 @@ def test_unaligned_pinned_host_frame_uses_the_staging_lanes(ctx):
     finally:
         ctx.sync()
         ctx.host_unregister(buf)
+
+
+@pytest.mark.parametrize("fmt", ("NV12", "I420", "BGRA", "AYUV"))
+def test_full_size_properties_without_the_oracle(ctx, fmt):
+    """Size-independent properties at 4K, no oracle involved: (1) an overlay whose alphas are
+    only 0 or 255 is idempotent -- blending the result again changes nothing; (2) the same
+    frame blended alone, inside a batch of 16 and in place gives identical bytes; (3) bytes
+    under alpha 0 are the source bytes."""
+    cfg = wl.CONFIGS[3]
+    w, h = cfg.width, cfg.height
+    ov = wl.overlay_for(cfg).copy()
+    a = ov[:, :, 3]
+    hard = np.where(a >= 128, 255, 0).astype(np.uint8)
+    ov[:, :, 3] = hard
+    ov[:, :, :3][hard == 0] = 0                      # valid premultiplied: colour <= alpha
+    ctx.overlay_set(450, ov, wl.region_rects(cfg))
+    ctx.set_batch(32, 0)
+    try:
+        frames = [wl.frame_for(cfg, i, fmt) for i in range(2)]
+        srcs = [ctx.acquire(fmt, w, h) for _ in range(16)]
+        dsts = [ctx.acquire(fmt, w, h) for _ in range(16)]
+        for i, s in enumerate(srcs):
+            s.upload(frames[i % 2])
+        # alone
+        ctx.wait(ctx.submit(450, fmt, w, h, srcs[0].c, dsts[0].c))
+        alone = dsts[0].download()
+        # in a batch of 16
+        t = ctx.submit_many(ctx.Batch([450] * 16, fmt, w, h, [s.c for s in srcs], [d.c for d in dsts]))
+        ctx.wait(max(t))
+        for i in (0, 2, 14):
+            assert_planes_equal(dsts[i].download(), alone, f"batch member {i}")
+        # idempotence: blend the result once more, in place
+        ctx.wait(ctx.submit(450, fmt, w, h, dsts[0].c, dsts[0].c))
+        assert_planes_equal(dsts[0].download(), alone, "idempotent for alphas in {0, 255}")
+        # alpha 0 leaves the source (luma / packed plane, pixel-exact mask)
+        mask = hard == 0
+        if fmt in ("NV12", "I420"):
+            assert np.array_equal(alone[0][mask], frames[0][0][mask])
+        else:
+            px = alone[0].reshape(h, w, 4)
+            assert np.array_equal(px[mask], frames[0][0].reshape(h, w, 4)[mask])
+        for f in srcs + dsts:
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)
