@@ -6,8 +6,17 @@
  * video-format.c as named by BASELINE.json's north_star).
  * Every formula below is the integer formula of that spec; nothing is
  * approximated. The kernels are HBM-bound byte work: 128-bit coalesced
- * loads/stores of the frame rows, overlay vectors from the prepared cache
- * (L2-resident across the frames of a batch), no tensor cores.
+ * loads/stores of the frame rows, overlay slices from the prepared cache
+ * (L2-resident across the frames of a batch) staged through shared memory by
+ * the TMA (cp.async.bulk + mbarrier), tables in kernel parameters, IDP.4A and
+ * two-lane SIMD arithmetic for the blend itself, no tensor cores.
+ *
+ *   ttmlblend_group_kernel      frames of equal geometry, band list in parameters
+ *   ttmlblend_blend_kernel      everything else (table in global memory, byte path)
+ *   ttmlblend_prepare_kernel    once per cue: unpack, un-premultiply, BT.709, siting
+ *   ttmlblend_prepare_chroma_avg_kernel   opt-in, non-parity 2x2 chroma mean
+ *   ttmlblend_rowspan_kernel    once per cue: non-transparent span of every row
+ *   ttmlblend_blur_kernel       textOutline blur (pixman convolution semantics)
  */
 #include "ttmlblend_kernels.cuh"
 

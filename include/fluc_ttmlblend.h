@@ -183,10 +183,13 @@ FLUC_EXPORT int fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_fram
 
 /* ---- per frame, host-resident: the drop-in for -----------------------
  * gst_video_overlay_composition_blend (comp, frame). The frame is in HOST
- * memory and is modified in place; only the rows the overlay can touch cross
- * PCIe (host -> device, blend, device -> host). Asynchronous: the copy back
- * has finished once wait(ticket) returns. Pinned memory (pool frames or
- * host_register) keeps the copies asynchronous. */
+ * memory and is modified in place; only the rows (and columns) the cue covers
+ * cross PCIe. Device-accessible frames -- pool frames acquired with on_host=1,
+ * or memory passed to host_register, 16-byte aligned -- are blended zero copy:
+ * they join the batch like submit() frames and the kernel reads and writes
+ * them over PCIe itself. Anything else (pageable or unaligned memory) is
+ * staged through copy lanes: host -> device, blend, device -> host.
+ * Asynchronous either way: the frame is complete once wait(ticket) returns. */
 FLUC_EXPORT int fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream,
     FlucTtmlBlendFormat fmt, int32_t width, int32_t height, uint32_t frame_flags,
     const FlucTtmlBlendFrame *host_frame, uint64_t *ticket);
