@@ -266,6 +266,18 @@ fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream, const uint8_t 
 }
 
 int
+fluc_ttmlblend_overlay_set_regions (FlucTtmlBlend *thiz, uint32_t stream, int32_t W, int32_t H,
+    const FlucTtmlBlendRegion *regions, uint32_t n_regions)
+{
+  ENTER (thiz);
+  if (W <= 0 || H <= 0 || W > 32768 || H > 32768 || (n_regions && !regions))
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  if (n_regions > FLUC_TTMLBLEND_MAX_RECTANGLES)
+    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+  return overlay_install_regions (c, stream, W, H, regions, n_regions);
+}
+
+int
 fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream)
 {
   ENTER (thiz);

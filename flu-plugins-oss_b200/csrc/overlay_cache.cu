@@ -343,13 +343,66 @@ crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, std::ve
     out.push_back ({ r.x0, r.y0, r.x1 - r.x0, r.y1 - r.y0 });
 }
 
+/* A rectangle whose pixels already sit in device memory, on its way into an overlay. */
+struct Up {
+  RawRect rr;
+  std::vector<int2> spans;
+};
+
+/* Queues the row-span scan of one device-resident rectangle on the upload stream. */
+static int
+scan_rows (Ctx *c, Up &u)
+{
+  if (!c->autocrop)
+    return 0;
+  void *sp = nullptr;
+  CU (c, cudaMallocAsync (&sp, (size_t) u.rr.h * sizeof (int2), c->up_stream));
+  u.spans.resize (u.rr.h);
+  CU (c, launch_rowspan (u.rr.dev, u.rr.pitch, u.rr.w, u.rr.h, static_cast<int2 *> (sp), c->up_stream));
+  CU (c, cudaMemcpyAsync (u.spans.data (), sp, (size_t) u.rr.h * sizeof (int2), cudaMemcpyDeviceToHost,
+          c->up_stream));
+  CU (c, cudaFreeAsync (sp, c->up_stream));
+  return 0;
+}
+
+/* Waits for uploads and scans, crops every rectangle to its non-transparent row runs and
+ * swaps the stream's overlay. */
+static int
+finish_install (Ctx *c, uint32_t stream, std::shared_ptr<Overlay> ov, std::vector<Up> &ups)
+{
+  /* the caller's pixels must be consumed (and the row spans back) before we return */
+  CU (c, cudaStreamSynchronize (c->up_stream));
+  for (Up &u : ups) {
+    if (!c->autocrop) {
+      ov->rects.push_back (u.rr);
+      continue;
+    }
+    std::vector<FlucTtmlBlendRect> subs;
+    /* at most 8 runs per rectangle, and never more sub-rectangles than the 64-bit band masks hold */
+    crop_runs (u.spans, 16, std::max<size_t> (1, std::min<size_t> (8, FLUC_TTMLBLEND_MAX_RECTANGLES / ups.size ())), subs);
+    for (const FlucTtmlBlendRect &s : subs) {
+      RawRect q = u.rr;
+      q.dev = u.rr.dev + (size_t) s.y * u.rr.pitch + (size_t) s.x * 4;
+      q.x = u.rr.x + s.x;
+      q.y = u.rr.y + s.y;
+      q.w = s.w;
+      q.h = s.h;
+      ov->rects.push_back (q);
+    }
+  }
+  if (ov->rects.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+  c->overlays[stream] = ov;       /* frames already queued keep the old one */
+  c->stats.overlays_set++;
+  return 0;
+}
+
 int
 overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n)
 {
   NvtxRange nvtx ("ttmlblend.overlay_set");
   std::shared_ptr<Overlay> ov (new Overlay ());
   ov->ctx = c;
-  struct Up { RawRect rr; int2 *d_spans; std::vector<int2> spans; };
   std::vector<Up> ups;
   for (uint32_t i = 0; i < n; i++) {
     const FlucTtmlBlendRectangle &r = rects[i];
@@ -377,44 +430,96 @@ overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, u
     CU (c, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
             r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
     c->stats.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
-    u.d_spans = nullptr;
-    if (c->autocrop) {
-      void *sp = nullptr;
-      CU (c, cudaMallocAsync (&sp, (size_t) rr.h * sizeof (int2), c->up_stream));
-      u.d_spans = static_cast<int2 *> (sp);
-      u.spans.resize (rr.h);
-      CU (c, launch_rowspan (rr.dev, rr.pitch, rr.w, rr.h, u.d_spans, c->up_stream));
-      CU (c, cudaMemcpyAsync (u.spans.data (), u.d_spans, (size_t) rr.h * sizeof (int2),
-              cudaMemcpyDeviceToHost, c->up_stream));
-      CU (c, cudaFreeAsync (sp, c->up_stream));
-    }
+    int rc = scan_rows (c, u);
+    if (rc)
+      return rc;
     ups.push_back (std::move (u));
   }
-  /* the caller's pixels must be consumed (and the row spans back) before we return */
-  CU (c, cudaStreamSynchronize (c->up_stream));
-  for (Up &u : ups) {
-    if (!c->autocrop) {
-      ov->rects.push_back (u.rr);
+  return finish_install (c, stream, ov, ups);
+}
+
+/* Cairo's colour conversion: double components -> premultiplied 16-bit shorts
+ * (_cairo_color_compute_shorts: d * 65535.0 + 0.5) -> pixman a8r8g8b8 (short >> 8). */
+static uint32_t
+cairo_solid_pixel (uint32_t rgba8888)
+{
+  /* GET_CAIRO_COMP, /root/reference/plugins/ttml/gstttmlrender.c:1178 */
+  const double r = ((rgba8888 >> 24) & 255) / 255.0, g = ((rgba8888 >> 16) & 255) / 255.0;
+  const double b = ((rgba8888 >> 8) & 255) / 255.0, a = (rgba8888 & 255) / 255.0;
+  const uint32_t as = (uint16_t) (a * 65535.0 + 0.5), rs = (uint16_t) (r * a * 65535.0 + 0.5);
+  const uint32_t gs = (uint16_t) (g * a * 65535.0 + 0.5), bs = (uint16_t) (b * a * 65535.0 + 0.5);
+  return ((as >> 8) << 24) | ((rs >> 8) << 16) | ((gs >> 8) << 8) | (bs >> 8);
+}
+
+/* The overlay composed on the GPU from region descriptors:
+ * a cleared frame-sized canvas, every region drawn onto it in list order by
+ * ttmlblend_region_kernel, then installed like an uploaded image cropped to the boxes. */
+int
+overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTtmlBlendRegion *regions, uint32_t n)
+{
+  NvtxRange nvtx ("ttmlblend.overlay_set_regions");
+  std::shared_ptr<Overlay> ov (new Overlay ());
+  ov->ctx = c;
+  const int pitch = (int) align_up ((size_t) W * 4, 256);
+  void *canvas = nullptr;
+  CU (c, cudaMallocAsync (&canvas, (size_t) pitch * H, c->up_stream));
+  ov->raw_allocs.push_back (canvas);
+  CU (c, cudaMemsetAsync (canvas, 0, (size_t) pitch * H, c->up_stream));   /* CAIRO_OPERATOR_CLEAR */
+  std::vector<void *> layers;
+  std::vector<FlucTtmlBlendRect> boxes;
+  for (uint32_t i = 0; i < n; i++)
+    if (regions[i].w <= 0 || regions[i].h <= 0 || !(regions[i].opacity >= 0.0 && regions[i].opacity <= 1.0) ||
+        (regions[i].layer && regions[i].layer_stride < 4 * regions[i].w))
+      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < n; i++) {
+    const FlucTtmlBlendRegion &r = regions[i];
+    const int x0 = std::max (r.x, 0), y0 = std::max (r.y, 0);
+    const int x1 = std::min (r.x + r.w, W), y1 = std::min (r.y + r.h, H);
+    if (x1 <= x0 || y1 <= y0)
       continue;
+    RegionParams p = {};
+    p.canvas = static_cast<uint8_t *> (canvas);
+    p.canvas_pitch = pitch;
+    p.x = x0; p.y = y0; p.w = x1 - x0; p.h = y1 - y0;
+    p.lx = x0 - r.x; p.ly = y0 - r.y;
+    p.bg = r.background_color ? cairo_solid_pixel (r.background_color) : 0u;
+    p.m8 = r.opacity < 1.0 ? ((uint32_t) (uint16_t) (r.opacity * 65535.0 + 0.5)) >> 8 : 255u;
+    if (r.layer) {
+      const int lp = (int) align_up ((size_t) r.w * 4, 256);
+      void *d = nullptr;
+      CU (c, cudaMallocAsync (&d, (size_t) lp * r.h, c->up_stream));
+      layers.push_back (d);
+      CU (c, cudaMemcpy2DAsync (d, lp, r.layer, r.layer_stride, (size_t) r.w * 4, r.h,
+              cudaMemcpyHostToDevice, c->up_stream));
+      c->stats.h2d_bytes += (uint64_t) r.w * 4 * r.h;
+      p.layer = static_cast<uint8_t *> (d);
+      p.layer_pitch = lp;
     }
-    std::vector<FlucTtmlBlendRect> subs;
-    /* at most 8 runs per rectangle, and never more sub-rectangles than the 64-bit band masks hold */
-    crop_runs (u.spans, 16, std::max<size_t> (1, std::min<size_t> (8, FLUC_TTMLBLEND_MAX_RECTANGLES / ups.size ())), subs);
-    for (const FlucTtmlBlendRect &s : subs) {
-      RawRect q = u.rr;
-      q.dev = u.rr.dev + (size_t) s.y * u.rr.pitch + (size_t) s.x * 4;
-      q.x = u.rr.x + s.x;
-      q.y = u.rr.y + s.y;
-      q.w = s.w;
-      q.h = s.h;
-      ov->rects.push_back (q);
-    }
+    if (!p.bg && !p.layer)
+      continue;                 /* nothing to draw */
+    CU (c, launch_region (p, c->up_stream));
+    c->stats.prepare_launches++;
+    boxes.push_back ({ x0, y0, x1 - x0, y1 - y0 });
   }
-  if (ov->rects.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+  for (void *d : layers)
+    CU (c, cudaFreeAsync (d, c->up_stream));
+  std::vector<Up> ups;
+  for (const FlucTtmlBlendRect &b : disjoint_cover (boxes)) {
+    Up u;
+    u.rr.dev = static_cast<uint8_t *> (canvas) + (size_t) b.y * pitch + (size_t) b.x * 4;
+    u.rr.pitch = pitch;
+    u.rr.w = b.w; u.rr.h = b.h; u.rr.x = b.x; u.rr.y = b.y;
+    u.rr.ga = 255;
+    u.rr.premul = true;
+    ov->declared.push_back (b);
+    int rc = scan_rows (c, u);
+    if (rc)
+      return rc;
+    ups.push_back (std::move (u));
+  }
+  if (ups.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
     return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-  c->overlays[stream] = ov;       /* frames already queued keep the old one */
-  c->stats.overlays_set++;
-  return 0;
+  return finish_install (c, stream, ov, ups);
 }
 
 }  // namespace tbh

@@ -900,6 +900,86 @@ launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaSt
 }
 
 /* ---------------------------------------------------------------------- */
+/* once per cue: region background / opacity composition (pixman 8-bit)    */
+
+/* pixman MUL_UN8: (a * b) / 255, rounded */
+__device__ __forceinline__ uint32_t
+mul_un8 (uint32_t a, uint32_t b)
+{
+  const uint32_t t = a * b + 0x80u;
+  return ((t >> 8) + t) >> 8;
+}
+
+/* premultiplied a8r8g8b8: s OVER d, per channel d = sat (s + d * (255 - s.a) / 255) */
+__device__ __forceinline__ uint32_t
+over_un8x4 (uint32_t s, uint32_t d)
+{
+  const uint32_t ia = 255u - (s >> 24);
+  uint32_t out = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t v = ((s >> (8 * k)) & 0xffu) + mul_un8 ((d >> (8 * k)) & 0xffu, ia);
+    out |= min (v, 255u) << (8 * k);
+  }
+  return out;
+}
+
+__device__ __forceinline__ uint32_t
+in_un8x4 (uint32_t s, uint32_t m)
+{
+  uint32_t out = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    out |= mul_un8 ((s >> (8 * k)) & 0xffu, m) << (8 * k);
+  return out;
+}
+
+/* gst_ttmlrender_show_regions without the text rasterisation
+ * (/root/reference/plugins/ttml/gstttmlrender.c:1250-1268,1375-1381): opacity 1 draws
+ * straight onto the canvas, opacity < 1 goes through a cleared group surface that is then
+ * painted with the opacity as mask. One thread per pixel of the (clipped) region box. */
+__global__ void __launch_bounds__ (256)
+ttmlblend_region_kernel (const RegionParams p)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= p.w || j >= p.h)
+    return;
+  uint32_t *dst = reinterpret_cast<uint32_t *> (p.canvas + (size_t) (p.y + j) * p.canvas_pitch) + (p.x + i);
+  const uint32_t layer = p.layer ?
+      *reinterpret_cast<const uint32_t *> (p.layer + (size_t) (p.ly + j) * p.layer_pitch + 4 * (size_t) (p.lx + i)) : 0u;
+  uint32_t d = *dst;
+  if (p.m8 == 255u) {
+    if (p.bg)
+      d = over_un8x4 (p.bg, d);
+    if (p.layer)
+      d = over_un8x4 (layer, d);
+  } else {
+    uint32_t g = p.bg;                      /* bg OVER cleared group surface */
+    if (p.layer)
+      g = over_un8x4 (layer, g);
+    d = over_un8x4 (in_un8x4 (g, p.m8), d); /* cairo_paint_with_alpha */
+  }
+  *dst = d;
+}
+
+cudaError_t
+launch_region (const RegionParams &p, cudaStream_t stream)
+{
+  if (p.w <= 0 || p.h <= 0)
+    return cudaSuccess;
+  for (int r0 = 0; r0 < p.h; r0 += 65535) {
+    RegionParams q = p;
+    q.y = p.y + r0;
+    q.ly = p.ly + r0;
+    q.h = min (65535, p.h - r0);
+    dim3 grid ((p.w + 255) / 256, q.h);
+    ttmlblend_region_kernel<<<grid, 256, 0, stream>>> (q);
+  }
+  return cudaGetLastError ();
+}
+
+/* ---------------------------------------------------------------------- */
 /* once per cue with a blurred textOutline: pixman-style 2-D convolution   */
 
 /* gst_ttml_blur_image_surface (/root/reference/plugins/ttml/gstttmlblur.c:72-110):

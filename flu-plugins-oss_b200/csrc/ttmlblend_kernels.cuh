@@ -162,6 +162,20 @@ cudaError_t launch_group (GroupParams &P, int kind, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);
+/* One TTML region composed onto the frame-sized premultiplied BGRA canvas (pixman 8-bit
+ * arithmetic): background colour `bg` (premultiplied pixel, 0 = none), optional text layer,
+ * group opacity mask `m8` (255 = none). Box already clipped to the canvas. */
+struct RegionParams {
+  uint8_t *canvas;
+  int32_t canvas_pitch;
+  int32_t x, y, w, h;           /* clipped box on the canvas */
+  int32_t lx, ly;               /* canvas (x, y) is layer pixel (lx, ly) */
+  const uint8_t *layer;         /* device copy or nullptr */
+  int32_t layer_pitch;
+  uint32_t bg;                  /* premultiplied a8r8g8b8 */
+  uint32_t m8;
+};
+cudaError_t launch_region (const RegionParams &p, cudaStream_t stream);
 /* (2r+1)^2 16.16 taps; ARGB32 in, ARGB32 out (pixman convolution semantics). */
 cudaError_t launch_blur (const uint8_t *src, int w, int h, int src_pitch, const int32_t *taps, int radius,
     uint8_t *dst, int dst_pitch, cudaStream_t stream);

@@ -48,6 +48,12 @@ class Rectangle(C.Structure):
                 ("global_alpha", C.c_float), ("flags", C.c_uint32)]
 
 
+class Region(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("background_color", C.c_uint32), ("opacity", C.c_double),
+                ("layer", C.c_void_p), ("layer_stride", C.c_int32)]
+
+
 class Frame(C.Structure):
     _fields_ = [("plane", C.c_void_p * 3), ("stride", C.c_int32 * 3)]
 
@@ -72,6 +78,8 @@ PROTOTYPES = {
                                              C.c_int32, C.c_int32, C.POINTER(Rect), C.c_uint32]),
     "fluc_ttmlblend_overlay_set_rectangles": (C.c_int, [C.c_void_p, C.c_uint32,
                                                         C.POINTER(Rectangle), C.c_uint32]),
+    "fluc_ttmlblend_overlay_set_regions": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32,
+                                                     C.POINTER(Region), C.c_uint32]),
     "fluc_ttmlblend_overlay_clear": (C.c_int, [C.c_void_p, C.c_uint32]),
     "fluc_ttmlblend_set_chroma_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "fluc_ttmlblend_submit": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
@@ -263,6 +271,22 @@ class TtmlBlend:
                                FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0)
         self._check(self.lib.fluc_ttmlblend_overlay_set_rectangles(self.h, stream, arr, n),
                     "overlay_set_rectangles")
+
+    def overlay_set_regions(self, stream: int, width: int, height: int, regions: Sequence[dict]):
+        """Region form: the overlay is composed on the GPU. Each dict: x, y, w, h,
+        background_color (0xRRGGBBAA), opacity, layer (h x w x 4 uint8 premultiplied BGRA or None)."""
+        n = len(regions)
+        arr = (Region * max(1, n))()
+        for i, r in enumerate(regions):
+            layer = r.get("layer")
+            if layer is not None:
+                assert layer.dtype == np.uint8 and layer.shape == (r["h"], r["w"], 4) and layer.strides[2] == 1
+            arr[i] = Region(r["x"], r["y"], r["w"], r["h"], r.get("background_color", 0),
+                            float(r.get("opacity", 1.0)),
+                            layer.ctypes.data if layer is not None else None,
+                            layer.strides[0] if layer is not None else 0)
+        self._check(self.lib.fluc_ttmlblend_overlay_set_regions(self.h, stream, width, height, arr, n),
+                    "overlay_set_regions")
 
     def overlay_clear(self, stream: int):
         self._check(self.lib.fluc_ttmlblend_overlay_clear(self.h, stream), "overlay_clear")

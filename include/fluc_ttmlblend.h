@@ -142,6 +142,25 @@ FLUC_EXPORT int fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream
 /* GstVideoOverlayComposition form: independent rectangles, blended in order. */
 FLUC_EXPORT int fluc_ttmlblend_overlay_set_rectangles (FlucTtmlBlend *thiz,
     uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n_rects);
+/* Region form: the overlay is composed on the GPU from region
+ * descriptors instead of being drawn by Cairo on the host -- what
+ * gst_ttmlrender_show_regions does around the text
+ * (/root/reference/plugins/ttml/gstttmlrender.c:1250-1268,1375-1381): background fill,
+ * group opacity, regions in list (z-index) order. `layer`, if not NULL, is what the host
+ * rasterised for the region's text/outline on a CLEARED w*h surface (premultiplied BGRA);
+ * it is composited OVER the background. Arithmetic: Cairo's colour conversion and
+ * pixman's 8-bit premultiplied OVER / IN (docs/BLENDSPEC.md section 9); parity with a real
+ * Cairo is unpinned, and a layer is only equivalent to Cairo drawing the glyphs one by one
+ * where anti-aliased glyph edges do not overlap. */
+typedef struct {
+  int32_t x, y, w, h;            /* GstTTMLRegion originx/y, extentx/y (gstttmlrender.c:44-76) */
+  uint32_t background_color;     /* 0xRRGGBBAA (gstttmlattribute.c:22); 0 = none */
+  double opacity;                /* tts:opacity, 1.0 = none */
+  const uint8_t *layer;          /* optional, host memory, read before the call returns */
+  int32_t layer_stride;
+} FlucTtmlBlendRegion;
+FLUC_EXPORT int fluc_ttmlblend_overlay_set_regions (FlucTtmlBlend *thiz, uint32_t stream,
+    int32_t frame_width, int32_t frame_height, const FlucTtmlBlendRegion *regions, uint32_t n_regions);
 /* The "clear" buffer ttmlrender pushes for timeline gaps
  * (/root/reference/plugins/ttml/gstttmlevent.c:221-224): frames pass through. */
 FLUC_EXPORT int fluc_ttmlblend_overlay_clear (FlucTtmlBlend *thiz, uint32_t stream);

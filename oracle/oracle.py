@@ -30,6 +30,12 @@ class RefRectangle(C.Structure):
                 ("global_alpha", C.c_float), ("flags", C.c_uint32)]
 
 
+class RefRegion(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("background_color", C.c_uint32), ("opacity", C.c_double),
+                ("layer", C.c_void_p), ("layer_stride", C.c_int32)]
+
+
 def build(native: bool = False, out_dir: str = None) -> str:
     """Compiles the oracle. native=True adds -march=native (CPU baseline on the box it runs on)."""
     out_dir = out_dir or _HERE
@@ -133,3 +139,23 @@ def gaussian_kernel(radius: int, sigma: float, lib=None) -> np.ndarray:
     taps = (C.c_int32 * n)()
     lib.tbref_gaussian_kernel(radius, float(sigma), taps)
     return np.array(taps, dtype=np.int32).reshape(2 * radius + 1, 2 * radius + 1)
+
+
+def compose_regions(regions: Sequence[dict], width: int, height: int, lib=None) -> np.ndarray:
+    """gst_ttmlrender_show_regions without the text rasterisation. Each dict: x, y, w, h,
+    background_color (0xRRGGBBAA), opacity, layer (h x w x 4 uint8 premultiplied BGRA or None).
+    Returns the frame-sized premultiplied BGRA overlay."""
+    lib = lib or load()
+    lib.tbref_compose_regions.restype = None
+    lib.tbref_compose_regions.argtypes = [C.POINTER(RefRegion), C.c_uint32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_int32]
+    arr = (RefRegion * max(1, len(regions)))()
+    for i, r in enumerate(regions):
+        layer = r.get("layer")
+        arr[i] = RefRegion(r["x"], r["y"], r["w"], r["h"], r.get("background_color", 0),
+                           float(r.get("opacity", 1.0)),
+                           layer.ctypes.data if layer is not None else None,
+                           layer.strides[0] if layer is not None else 0)
+    out = np.zeros((height, width, 4), dtype=np.uint8)
+    lib.tbref_compose_regions(arr, len(regions), width, height, out.ctypes.data, out.strides[0])
+    return out

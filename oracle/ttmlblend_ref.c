@@ -523,6 +523,107 @@ tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t st
 }
 
 /* ---------------------------------------------------------------------- */
+/* region composition: Cairo colour conversion + pixman 8-bit OVER / IN    */
+
+static uint32_t
+mul_un8 (uint32_t a, uint32_t b)
+{
+  /* pixman-combine32.h MUL_UN8 */
+  uint32_t t = a * b + 0x80;
+  return ((t >> 8) + t) >> 8;
+}
+
+static uint32_t
+over_px (uint32_t s, uint32_t d)
+{
+  /* combine_over_u: d = s + d * (255 - alpha (s)) / 255, saturating per channel */
+  uint32_t ia = 255 - (s >> 24), out = 0;
+  int k;
+  for (k = 0; k < 4; k++) {
+    uint32_t v = ((s >> (8 * k)) & 0xff) + mul_un8 ((d >> (8 * k)) & 0xff, ia);
+    out |= TB_MIN (v, 255u) << (8 * k);
+  }
+  return out;
+}
+
+static uint32_t
+in_px (uint32_t s, uint32_t m)
+{
+  uint32_t out = 0;
+  int k;
+  for (k = 0; k < 4; k++)
+    out |= mul_un8 ((s >> (8 * k)) & 0xff, m) << (8 * k);
+  return out;
+}
+
+static uint32_t
+solid_px (uint32_t c)
+{
+  /* GET_CAIRO_COMP (gstttmlrender.c:1178) -> cairo_set_source_rgba ->
+   * _cairo_color_compute_shorts (d * 65535.0 + 0.5, colour premultiplied) ->
+   * pixman solid fill (short >> 8) */
+  double r = ((c >> 24) & 255) / 255.0, g = ((c >> 16) & 255) / 255.0;
+  double b = ((c >> 8) & 255) / 255.0, a = (c & 255) / 255.0;
+  uint32_t as = (uint16_t) (a * 65535.0 + 0.5), rs = (uint16_t) (r * a * 65535.0 + 0.5);
+  uint32_t gs = (uint16_t) (g * a * 65535.0 + 0.5), bs = (uint16_t) (b * a * 65535.0 + 0.5);
+  return ((as >> 8) << 24) | ((rs >> 8) << 16) | ((gs >> 8) << 8) | (bs >> 8);
+}
+
+static uint32_t
+load32 (const uint8_t *p)
+{
+  return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+}
+
+void
+tbref_compose_regions (const TbRefRegion *regions, uint32_t n, int32_t W, int32_t H,
+    uint8_t *out, int32_t out_stride)
+{
+  uint32_t i;
+  int x, y;
+  for (y = 0; y < H; y++)
+    memset (out + (size_t) y * out_stride, 0, (size_t) W * 4);     /* CAIRO_OPERATOR_CLEAR */
+  for (i = 0; i < n; i++) {
+    const TbRefRegion *r = &regions[i];
+    uint32_t bg = r->background_color ? solid_px (r->background_color) : 0;
+    uint32_t m8 = r->opacity < 1.0 ? ((uint32_t) (uint16_t) (r->opacity * 65535.0 + 0.5)) >> 8 : 255;
+    if (!bg && !r->layer)
+      continue;
+    for (y = r->y; y < r->y + r->h; y++) {
+      if (y < 0 || y >= H)
+        continue;
+      for (x = r->x; x < r->x + r->w; x++) {
+        uint8_t *p;
+        uint32_t d, layer = 0;
+        if (x < 0 || x >= W)
+          continue;
+        p = out + (size_t) y * out_stride + 4 * (size_t) x;
+        d = load32 (p);
+        if (r->layer)
+          layer = load32 (r->layer + (size_t) (y - r->y) * r->layer_stride + 4 * (size_t) (x - r->x));
+        if (m8 == 255) {
+          /* drawn straight onto the frame-sized surface */
+          if (bg)
+            d = over_px (bg, d);
+          if (r->layer)
+            d = over_px (layer, d);
+        } else {
+          /* group surface, then cairo_paint_with_alpha (opacity) */
+          uint32_t g = bg;
+          if (r->layer)
+            g = over_px (layer, g);
+          d = over_px (in_px (g, m8), d);
+        }
+        p[0] = d & 0xff;
+        p[1] = (d >> 8) & 0xff;
+        p[2] = (d >> 16) & 0xff;
+        p[3] = d >> 24;
+      }
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------- */
 /* CPU baseline driver (bench.py cpu_baseline / --impl reference)         */
 
 typedef struct {

@@ -85,6 +85,21 @@ int32_t tbref_gaussian_kernel (int32_t radius, double sigma, int32_t *taps);
 void tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
     int32_t radius, double sigma, uint8_t *dst, int32_t dst_stride);
 
+/* Region composition: what gst_ttmlrender_show_regions does
+ * around the text (/root/reference/plugins/ttml/gstttmlrender.c:1250-1268,1375-1381) with
+ * Cairo's colour conversion and pixman's 8-bit premultiplied OVER / IN restated
+ * (docs/BLENDSPEC.md section 9; neither library is installed: parity unpinned). `out` is a
+ * cleared-then-drawn frame_w * frame_h premultiplied BGRA image. */
+typedef struct {
+  int32_t x, y, w, h;
+  uint32_t background_color;   /* 0xRRGGBBAA */
+  double opacity;
+  const uint8_t *layer;        /* optional premultiplied BGRA, w*h */
+  int32_t layer_stride;
+} TbRefRegion;
+void tbref_compose_regions (const TbRefRegion *regions, uint32_t n, int32_t frame_w, int32_t frame_h,
+    uint8_t *out, int32_t out_stride);
+
 /* Plane geometry helpers shared by the tests and the bench. */
 int32_t tbref_n_planes (int32_t format);
 int32_t tbref_plane_row_bytes (int32_t format, int32_t plane, int32_t width);

@@ -291,3 +291,25 @@ def test_oracle_under_asan_ubsan(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failure(s)" in r.stdout
+
+
+def test_region_composition_known_answers():
+    """pixman MUL_UN8 ((a*b + 0x80 + ((a*b + 0x80) >> 8)) >> 8) and Cairo's colour conversion,
+    hand-computed."""
+    from oracle import oracle
+    regions = [dict(x=0, y=0, w=2, h=1, background_color=0xFFFFFFFF, opacity=1.0),     # opaque white
+               dict(x=1, y=0, w=2, h=1, background_color=0x336699CC, opacity=1.0)]
+    ov = oracle.compose_regions(regions, 4, 1)
+    assert list(ov[0, 0]) == [255, 255, 255, 255]
+    # 0x336699CC: a = 0xCC = 204; premultiplied shorts r = 0x33*204*257/255 + .5 -> >> 8
+    a = 204
+    want = [int((c / 255.0) * (a / 255.0) * 65535.0 + 0.5) >> 8 for c in (0x99, 0x66, 0x33)] + [a]
+    assert list(ov[0, 2]) == want                                    # on the cleared canvas: src itself
+    mul = lambda x, y: (((x * y + 0x80) >> 8) + (x * y + 0x80)) >> 8
+    over_white = [min(255, s + mul(255, 255 - a)) for s in want]
+    assert list(ov[0, 1]) == over_white
+    assert ov[0, 3].max() == 0
+    # opacity goes through a group: IN with (opacity * 65535 + 0.5) >> 8
+    ov = oracle.compose_regions([dict(x=0, y=0, w=1, h=1, background_color=0xFF0000FF, opacity=0.25)], 1, 1)
+    m8 = int(0.25 * 65535.0 + 0.5) >> 8
+    assert list(ov[0, 0]) == [0, 0, mul(255, m8), mul(255, m8)]
