@@ -126,6 +126,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->autocrop = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_GROUPS")))
     c->use_groups = atoi (e) != 0;
+  if ((e = getenv ("FLUC_TTMLBLEND_AUTO_REGISTER")))
+    c->auto_register = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))
     c->host_mode = std::max (0, std::min (2, atoi (e)));
   if ((e = getenv ("FLUC_TTMLBLEND_LINGER_US")))
@@ -191,6 +193,9 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
     for (auto &p : c->pool_used) {
       if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
     }
+    for (auto &r : c->auto_regs)
+      cudaHostUnregister ((void *) r.first);
+    c->auto_regs.clear ();
     if (c->scrub) cudaFree (c->scrub);
     for (auto e : c->ev_fence)
       if (e) cudaEventDestroy (e);
@@ -461,6 +466,53 @@ fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_frames, uint32_t lin
 
 /* ---- host-resident frames -------------------------------------------- */
 
+/* Opt-in (fluc_ttmlblend_set_auto_register): pin the memory of pageable host frames the
+ * first time they are seen, so that later frames from the same buffers -- GStreamer buffer
+ * pools recycle them -- take the zero-copy path (10.7 k instead of 1.7 k 4K frames/s,
+ * tools/pageable_probe.py). Least recently used plane registrations are dropped beyond 192. The
+ * caller promises not to free registered memory without host_unregister / context free. */
+static void
+auto_register_frame (Ctx *c, int fmt, int H, const FlucTtmlBlendFrame *hf)
+{
+  /* plane by plane: the planes of a frame need not be neighbours in memory */
+  for (int pl = 0; pl < format_planes (fmt); pl++) {
+    const uintptr_t lo = (uintptr_t) hf->plane[pl];
+    const uintptr_t hi = lo + (uintptr_t) hf->stride[pl] * plane_rows (fmt, pl, H);
+    bool known = false;
+    for (size_t i = 0; i < c->auto_regs.size () && !known; i++)
+      if (c->auto_regs[i].first <= lo && hi <= c->auto_regs[i].second) {
+        std::rotate (c->auto_regs.begin (), c->auto_regs.begin () + i, c->auto_regs.begin () + i + 1);
+        known = true;           /* now most recently used */
+      }
+    if (known)
+      continue;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes (&attr, (void *) lo) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+      continue;                 /* already pinned by someone else */
+    cudaGetLastError ();
+    if (c->auto_regs.size () >= 192) {
+      /* nothing queued may still read the oldest one */
+      launch_pending (c);
+      cudaStreamSynchronize (c->blend_stream);
+      cudaHostUnregister ((void *) c->auto_regs.back ().first);
+      c->auto_regs.pop_back ();
+    }
+    if (cudaHostRegister ((void *) lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess)
+      c->auto_regs.insert (c->auto_regs.begin (), { lo, hi });
+    else
+      cudaGetLastError ();      /* cannot pin (memlock limit, odd mapping): staged copies it is */
+  }
+}
+
+int
+fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled)
+{
+  ENTER (thiz);
+  c->auto_register = enabled != 0;
+  return 0;
+}
+
+
 int
 fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
     int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *hf, uint64_t *ticket)
@@ -483,6 +535,8 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
   /* Is the host frame device-accessible (pool frame / host_register)? Then the
    * kernel can reach it over PCIe itself. */
   const int n_planes = format_planes (fmt);
+  if (c->auto_register && c->host_mode != HM_STAGED)
+    auto_register_frame (c, fmt, H, hf);
   FlucTtmlBlendFrame zf = {};
   bool mapped = c->host_mode != HM_STAGED;
   for (int pl = 0; pl < n_planes && mapped; pl++) {
@@ -649,6 +703,11 @@ int
 fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr)
 {
   ENTER (thiz);
+  for (size_t i = 0; i < c->auto_regs.size (); i++)
+    if (c->auto_regs[i].first == (uintptr_t) ptr) {
+      c->auto_regs.erase (c->auto_regs.begin () + i);
+      break;
+    }
   cudaError_t e = cudaHostUnregister (ptr);
   if (e != cudaSuccess) {
     cudaGetLastError ();

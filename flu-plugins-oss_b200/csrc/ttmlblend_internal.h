@@ -226,6 +226,8 @@ struct Ctx {
 
   uint32_t max_batch = 32, linger_us = 200;
   int host_mode = HM_ZEROCOPY;
+  bool auto_register = false;          /* pin pageable host frames on first sight (opt-in) */
+  std::vector<std::pair<uintptr_t, uintptr_t>> auto_regs;   /* [lo, hi), most recently used first */
   bool chroma_average = false;         /* fluc_ttmlblend_set_chroma_mode (1): NOT bit-exact */
   bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */

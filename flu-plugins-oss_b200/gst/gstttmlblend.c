@@ -220,6 +220,9 @@ gst_ttmlblend_start (GstBaseTransform * trans)
         ("%s", fluc_ttmlblend_strerror (rc)));
     return FALSE;
   }
+  /* frames that do not come from gstflucallocator.c are pageable: pin the buffers of the
+   * upstream pool as they show up, so that they are blended zero-copy from then on */
+  fluc_ttmlblend_set_auto_register (self->ctx, 1);
   self->have_overlay = FALSE;
   return TRUE;
 }

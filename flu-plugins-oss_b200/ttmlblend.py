@@ -94,6 +94,7 @@ PROTOTYPES = {
     "fluc_ttmlblend_set_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "fluc_ttmlblend_blend_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
                                             C.c_uint32, C.POINTER(Frame), C.POINTER(C.c_uint64)]),
+    "fluc_ttmlblend_set_auto_register": (C.c_int, [C.c_void_p, C.c_int]),
     "fluc_ttmlblend_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fluc_ttmlblend_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fluc_ttmlblend_frame_pool_acquire": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32,
@@ -347,6 +348,9 @@ class TtmlBlend:
             self.h, stream, FORMATS[fmt], width, height, frame_flags, C.byref(frame), C.byref(t)),
             "blend_host")
         return t.value
+
+    def set_auto_register(self, on: bool):
+        self._check(self.lib.fluc_ttmlblend_set_auto_register(self.h, 1 if on else 0), "set_auto_register")
 
     def host_register(self, arr: np.ndarray):
         self._check(self.lib.fluc_ttmlblend_host_register(self.h, arr.ctypes.data, arr.nbytes),

@@ -212,6 +212,10 @@ FLUC_EXPORT int fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_fram
 FLUC_EXPORT int fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream,
     FlucTtmlBlendFormat fmt, int32_t width, int32_t height, uint32_t frame_flags,
     const FlucTtmlBlendFrame *host_frame, uint64_t *ticket);
+/* Opt-in: pin pageable host frames the first time blend_host sees them (up to 192 planes,
+ * least recently used dropped), so that recycled buffers of a pool take the zero-copy path.
+ * The caller must not free such memory while the context lives without host_unregister. */
+FLUC_EXPORT int fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled);
 FLUC_EXPORT int fluc_ttmlblend_host_register (FlucTtmlBlend *thiz, void *ptr, size_t bytes);
 FLUC_EXPORT int fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr);
 

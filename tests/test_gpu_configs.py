@@ -246,3 +246,33 @@ def test_full_size_properties_without_the_oracle(ctx, fmt):
             f.release()
     finally:
         ctx.set_batch(32, 200)
+
+
+def test_auto_register_moves_pageable_frames_to_zero_copy():
+    """Opt-in auto registration: pageable frames are pinned on first sight and from then on
+    blended zero-copy (group launches), with identical results."""
+    fmt, w, h = "NV12", 640, 360
+    c = pkg.TtmlBlend(0)
+    try:
+        rects = [dict(pixels=random_overlay(400, 60, 3), x=100, y=250)]
+        c.overlay_set_rectangles(1, rects)
+        frames = [random_frame(fmt, w, h, 70 + i) for i in range(4)]
+        bufs = [copy_planes(f) for f in frames]
+        want = [oracle_blend(fmt, w, h, copy_planes(f), rects) for f in frames]
+        for b in bufs:                                  # default: staged lanes (table kernel)
+            c.wait(c.blend_host(1, fmt, w, h, b))
+        assert c.stats()["group_launches"] == 0
+        for b, wnt in zip(bufs, want):
+            assert_planes_equal(b, wnt, "staged")
+        c.set_auto_register(True)
+        bufs = [copy_planes(f) for f in frames]
+        c.stats_reset()
+        tickets = [c.blend_host(1, fmt, w, h, b) for b in bufs]
+        for t in tickets:
+            c.wait(t)
+        assert c.stats()["group_launches"] >= 1         # zero copy now
+        for b, wnt in zip(bufs, want):
+            assert_planes_equal(b, wnt, "auto-registered")
+        c.sync()
+    finally:
+        c.close()                                       # unregisters what it pinned
