@@ -892,6 +892,14 @@ fluc_ttmlblend_stats_copy (FlucTtmlBlend *thiz, FlucTtmlBlendStats *out)
   cudaSetDevice (thiz->c.device);
   reap_batches (&thiz->c);
   *out = thiz->c.stats;
+  /* what the overlay caches hold: everything they allocate is stream-ordered pool memory */
+  cudaMemPool_t pool;
+  uint64_t used = 0;
+  if (cudaDeviceGetDefaultMemPool (&pool, thiz->c.device) == cudaSuccess &&
+      cudaMemPoolGetAttribute (pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess)
+    out->cache_bytes = used;
+  else
+    cudaGetLastError ();
 }
 
 void

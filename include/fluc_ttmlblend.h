@@ -120,6 +120,7 @@ typedef struct {
   uint64_t h2d_bytes, d2h_bytes;
   double kernel_ms;             /* sum of the CUDA-event times of the timed batches (profiling on) */
   uint64_t kernel_ms_launches;  /* batches included in kernel_ms (one launch each unless mixed) */
+  uint64_t cache_bytes;         /* device memory held by overlay caches right now (stream-ordered pool) */
 } FlucTtmlBlendStats;
 
 /* ---- lifetime -------------------------------------------------------- */

@@ -577,3 +577,47 @@ def test_chroma_average_option_is_what_it_says(fmt, w, h, rect):
         assert c.lib.fluc_ttmlblend_set_chroma_mode(c.h, 7) == pkg.ttmlblend.ERROR_INVALID_ARGUMENT
     finally:
         c.close()
+
+
+def test_overlay_cache_does_not_leak():
+    """Hundreds of cue changes in every form (images, rectangles, regions, several formats and
+    sizes, clears) with frames in between: the device memory held by the overlay caches goes
+    back to zero once the cues are cleared and the work has drained."""
+    c = pkg.TtmlBlend(0)
+    try:
+        c.sync()
+        base = c.stats()["cache_bytes"]
+        w, h = 320, 180
+        frames = {fmt: (c.acquire(fmt, w, h), c.acquire(fmt, w, h)) for fmt in ("NV12", "I420", "BGRA", "AYUV")}
+        peak = 0
+        for i in range(150):
+            s_id = i % 5
+            if i % 3 == 0:
+                c.overlay_set(s_id, random_overlay(w, h, 100 + i), [(10, 20 + i % 30, 200, 60)])
+            elif i % 3 == 1:
+                c.overlay_set_rectangles(s_id, [dict(pixels=random_overlay(100, 40, 200 + i), x=i % 50, y=i % 90),
+                                                dict(pixels=random_overlay(60, 60, 300 + i), x=150, y=40)])
+            else:
+                c.overlay_set_regions(s_id, w, h, [dict(x=5, y=5 + i % 20, w=200, h=50,
+                                                       background_color=0x102030C0, opacity=0.5,
+                                                       layer=random_overlay(200, 50, 400 + i))])
+            for fmt, (src, dst) in frames.items():
+                if (i + len(fmt)) % 2:
+                    c.submit(s_id, fmt, w, h, src.c, dst.c)
+            if i % 7 == 0:
+                c.overlay_clear((i + 2) % 5)
+            if i % 10 == 0:
+                peak = max(peak, c.stats()["cache_bytes"])
+        c.sync()
+        assert peak > base
+        for s_id in range(5):
+            c.overlay_clear(s_id)
+        c.sync()
+        c.sync()        # deferred frees run on the reaper stream after the fences
+        import time
+        deadline = time.time() + 5
+        while c.stats()["cache_bytes"] > base and time.time() < deadline:
+            time.sleep(0.01)
+        assert c.stats()["cache_bytes"] == base, (c.stats()["cache_bytes"], base, peak)
+    finally:
+        c.close()
