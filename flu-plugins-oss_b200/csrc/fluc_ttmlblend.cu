@@ -307,6 +307,7 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
     const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst, uint64_t *ticket)
 {
   int rc;
+  fmt = format_canon (fmt);
   if ((rc = check_frame (fmt, W, H, src)) || (rc = check_frame (fmt, W, H, dst)))
     return rc;
   PendingFrame f;
@@ -519,6 +520,7 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
 {
   ENTER (thiz);
   int rc;
+  fmt = (FlucTtmlBlendFormat) format_canon (fmt);
   if ((rc = check_frame (fmt, W, H, hf)))
     return rc;
   const uint64_t tk = ++c->next_ticket;
@@ -721,12 +723,14 @@ fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr)
 int
 fluc_ttmlblend_format_planes (FlucTtmlBlendFormat fmt)
 {
+  fmt = (FlucTtmlBlendFormat) format_canon (fmt);
   return format_valid (fmt) ? format_planes (fmt) : 0;
 }
 
 int
 fluc_ttmlblend_plane_row_bytes (FlucTtmlBlendFormat fmt, int plane, int32_t width)
 {
+  fmt = (FlucTtmlBlendFormat) format_canon (fmt);
   if (!format_valid (fmt) || plane < 0 || plane >= format_planes (fmt))
     return 0;
   return plane_row_bytes (fmt, plane, width);
@@ -735,6 +739,7 @@ fluc_ttmlblend_plane_row_bytes (FlucTtmlBlendFormat fmt, int plane, int32_t widt
 int
 fluc_ttmlblend_plane_rows (FlucTtmlBlendFormat fmt, int plane, int32_t height)
 {
+  fmt = (FlucTtmlBlendFormat) format_canon (fmt);
   if (!format_valid (fmt) || plane < 0 || plane >= format_planes (fmt))
     return 0;
   return plane_rows (fmt, plane, height);
@@ -745,6 +750,7 @@ fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt,
     int32_t H, int on_host, FlucTtmlBlendFrame *out)
 {
   ENTER (thiz);
+  fmt = (FlucTtmlBlendFormat) format_canon (fmt);
   if (!out || W <= 0 || H <= 0)
     return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   if (!format_valid (fmt))
@@ -800,6 +806,7 @@ frame_copy (Ctx *c, int fmt, int W, int H, const FlucTtmlBlendFrame *s, const Fl
     cudaMemcpyKind kind)
 {
   int rc;
+  fmt = format_canon (fmt);
   if ((rc = check_frame (fmt, W, H, s)) || (rc = check_frame (fmt, W, H, d)))
     return rc;
   for (int pl = 0; pl < format_planes (fmt); pl++) {

@@ -40,6 +40,19 @@ using namespace tb;
 
 enum FormatClass { FC_I420, FC_YV12, FC_NV12, FC_NV21, FC_AYUV, FC_ARGB, FC_ABGR, FC_RGBA, FC_BGRA, FC_COUNT };
 
+/* RGBx / BGRx / xRGB / xBGR -> RGBA / BGRA / ARGB / ABGR (same pack/unpack in GStreamer) */
+inline int
+format_canon (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_RGBx: return FLUC_TTMLBLEND_FORMAT_RGBA;
+    case FLUC_TTMLBLEND_FORMAT_BGRx: return FLUC_TTMLBLEND_FORMAT_BGRA;
+    case FLUC_TTMLBLEND_FORMAT_xRGB: return FLUC_TTMLBLEND_FORMAT_ARGB;
+    case FLUC_TTMLBLEND_FORMAT_xBGR: return FLUC_TTMLBLEND_FORMAT_ABGR;
+    default: return f;
+  }
+}
+
 inline bool
 format_valid (int f)
 {

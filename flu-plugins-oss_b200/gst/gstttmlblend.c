@@ -62,7 +62,7 @@ enum
   PROP_DEVICE
 };
 
-#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA }"
+#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR }"
 
 static GstStaticPadTemplate video_sink_template = GST_STATIC_PAD_TEMPLATE ("sink",
     GST_PAD_SINK, GST_PAD_ALWAYS,
@@ -92,6 +92,10 @@ to_fluc_format (GstVideoFormat f)
     case GST_VIDEO_FORMAT_ABGR: return FLUC_TTMLBLEND_FORMAT_ABGR;
     case GST_VIDEO_FORMAT_RGBA: return FLUC_TTMLBLEND_FORMAT_RGBA;
     case GST_VIDEO_FORMAT_BGRA: return FLUC_TTMLBLEND_FORMAT_BGRA;
+    case GST_VIDEO_FORMAT_RGBx: return FLUC_TTMLBLEND_FORMAT_RGBx;
+    case GST_VIDEO_FORMAT_BGRx: return FLUC_TTMLBLEND_FORMAT_BGRx;
+    case GST_VIDEO_FORMAT_xRGB: return FLUC_TTMLBLEND_FORMAT_xRGB;
+    case GST_VIDEO_FORMAT_xBGR: return FLUC_TTMLBLEND_FORMAT_xBGR;
     default: return FLUC_TTMLBLEND_FORMAT_COUNT;
   }
 }

@@ -24,6 +24,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libfluc_ttmlblend.so")
 FORMATS = {
     "I420": 0, "NV12": 1, "AYUV": 2, "RGBA": 3, "BGRA": 4,
     "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8,
+    "RGBx": 9, "BGRx": 10, "xRGB": 11, "xBGR": 12,       # same paths as RGBA / BGRA / ARGB / ABGR
 }
 FLAG_PREMULTIPLIED_ALPHA = 1
 MAX_RECTANGLES = 64

@@ -98,9 +98,9 @@ def plane_shapes(fmt: str, width: int, height: int):
 
 def alpha_byte_index(fmt: str):
     f = fmt.upper()
-    if f in ("AYUV", "ARGB", "ABGR"):
+    if f in ("AYUV", "ARGB", "ABGR", "XRGB", "XBGR"):
         return 0
-    if f in ("RGBA", "BGRA"):
+    if f in ("RGBA", "BGRA", "RGBX", "BGRX"):
         return 3
     return None
 

@@ -62,6 +62,13 @@ typedef enum {
   FLUC_TTMLBLEND_FORMAT_NV21 = 6,
   FLUC_TTMLBLEND_FORMAT_ARGB = 7,
   FLUC_TTMLBLEND_FORMAT_ABGR = 8,
+  /* the padded RGB formats share pack/unpack with their alpha twins in GStreamer's format
+   * table (PACK_RGBA / PACK_BGRA / PACK_ARGB / PACK_ABGR): the padding byte IS the alpha
+   * byte as far as gst_video_blend is concerned, so these are the same code paths */
+  FLUC_TTMLBLEND_FORMAT_RGBx = 9,
+  FLUC_TTMLBLEND_FORMAT_BGRx = 10,
+  FLUC_TTMLBLEND_FORMAT_xRGB = 11,
+  FLUC_TTMLBLEND_FORMAT_xBGR = 12,
   FLUC_TTMLBLEND_FORMAT_COUNT
 } FlucTtmlBlendFormat;
 

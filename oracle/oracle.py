@@ -15,7 +15,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FORMATS = {"I420": 0, "NV12": 1, "AYUV": 2, "RGBA": 3, "BGRA": 4,
-           "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8}
+           "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8,
+           # x formats use their alpha twins' pack/unpack in GStreamer (PACK_RGBA ...)
+           "RGBx": 3, "BGRx": 4, "xRGB": 7, "xBGR": 8}
 FLAG_PREMULTIPLIED_ALPHA = 1
 
 

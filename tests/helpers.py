@@ -17,7 +17,8 @@ ALL_FORMATS = PLANAR_420 + PACKED
 
 # byte positions of (A, c1, c2, c3) inside a packed pixel, c = (Y,U,V) or (R,G,B)
 PACKED_ORDER = {"AYUV": (0, 1, 2, 3), "ARGB": (0, 1, 2, 3), "ABGR": (0, 3, 2, 1),
-                "RGBA": (3, 0, 1, 2), "BGRA": (3, 2, 1, 0)}
+                "RGBA": (3, 0, 1, 2), "BGRA": (3, 2, 1, 0),
+                "xRGB": (0, 1, 2, 3), "xBGR": (0, 3, 2, 1), "RGBx": (3, 0, 1, 2), "BGRx": (3, 2, 1, 0)}
 
 
 def rng(seed):

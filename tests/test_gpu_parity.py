@@ -621,3 +621,19 @@ def test_overlay_cache_does_not_leak():
         assert c.stats()["cache_bytes"] == base, (c.stats()["cache_bytes"], base, peak)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("fmt,twin", [("RGBx", "RGBA"), ("BGRx", "BGRA"), ("xRGB", "ARGB"), ("xBGR", "ABGR")])
+def test_padded_rgb_formats_are_their_alpha_twins(ctx, fmt, twin):
+    """RGBx / BGRx / xRGB / xBGR share pack/unpack with RGBA / BGRA / ARGB / ABGR in GStreamer's
+    format table, so gst_video_blend treats the padding byte as destination alpha: same bytes
+    out, also when the padding is not 255."""
+    w, h = 200, 90
+    rects = [dict(pixels=random_overlay(120, 50, 17), x=33, y=21)]
+    for opaque in (True, False):
+        planes = random_frame(twin, w, h, 18, opaque=opaque)
+        want = oracle_blend(twin, w, h, copy_planes(planes), rects)
+        assert_planes_equal(oracle_blend(fmt, w, h, copy_planes(planes), rects), want, "oracle alias")
+        for mode in MODES:
+            got = gpu_blend(ctx, fmt, w, h, planes, rects, mode=mode, stream=44)
+            assert_planes_equal(got, want, f"{fmt} {mode} opaque={opaque}")
