@@ -381,7 +381,29 @@ def main():
         barrier(dist, device)
         st2 = ctx.stats()
         rec2 = sh.gather_records((batch * e2e_steps, e2e_ms), dist, device)
+        # the same frames, one synchronous call per frame through the C mirror of the GStreamer
+        # call (fluc_video_overlay_composition_blend == gst_video_overlay_composition_blend):
+        # what a single streaming thread sees; not batched, so latency-bound
+        sync_fps = None
+        if cfg.streams == 1:
+            try:
+                vo = pkg.videooverlay
+                if vo.load_library().fluc_video_overlay_set_device(local) == 0:
+                    comp = vo.Composition(vo.Rectangle(ov, 0, 0, vo.FLAG_PREMULTIPLIED_ALPHA))
+                    views = [hf.host_planes() for hf in hosts]
+                    for v in views[:4]:
+                        comp.blend(fmt, W, H, v)
+                    n_sync = 0
+                    t0 = time.perf_counter()
+                    while time.perf_counter() - t0 < 1.0:
+                        comp.blend(fmt, W, H, views[n_sync % len(views)])
+                        n_sync += 1
+                    sync_fps = n_sync / (time.perf_counter() - t0)
+                    del comp
+            except Exception as e:      # noqa: BLE001
+                sync_fps = f"failed: {e!r}"
         e2e = {"value": sh.aggregate_fps(rec2), "unit": UNIT,
+               "one_synchronous_call_per_frame": sync_fps,
                "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps,
                "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
                "steps": e2e_steps, "launches": st2["launches"],
