@@ -47,15 +47,35 @@ static const struct {
   { GST_VIDEO_FORMAT_BGRA, TBREF_FORMAT_BGRA, "BGRA" },
 };
 
+/* geometry / flag cases: frame size, rectangle size and position (hanging over every
+ * border, odd origins and sizes), premultiplied or straight source, global alpha */
+static const struct {
+  int W, H, RW, RH, RX, RY;
+  gboolean premul;
+  gfloat ga;
+} cases[] = {
+  { 321, 181, 200, 90, 37, 51, TRUE, 1.0f },
+  { 321, 181, 200, 90, -33, -17, TRUE, 1.0f },
+  { 321, 181, 200, 90, 250, 150, TRUE, 1.0f },
+  { 320, 180, 320, 180, 0, 0, TRUE, 1.0f },       /* ttmlrender: frame-sized image at (0,0) */
+  { 63, 47, 31, 15, 7, 9, TRUE, 1.0f },
+  { 64, 48, 1, 1, 5, 5, TRUE, 1.0f },
+  { 321, 181, 200, 90, 37, 51, FALSE, 1.0f },
+  { 321, 181, 200, 90, 36, 50, TRUE, 0.5f },
+  { 321, 181, 200, 90, 37, 51, FALSE, 0.8f },
+};
+
 int
 main (int argc, char **argv)
 {
-  const int W = 321, H = 181, RW = 200, RH = 90, RX = 37, RY = 51;
-  guint f, total_bad = 0;
+  guint f, k, total_bad = 0;
   gst_init (&argc, &argv);
   printf ("GStreamer %s\n", gst_version_string ());
 
+  for (k = 0; k < G_N_ELEMENTS (cases); k++)
   for (f = 0; f < G_N_ELEMENTS (formats); f++) {
+    const int W = cases[k].W, H = cases[k].H, RW = cases[k].RW, RH = cases[k].RH;
+    const int RX = cases[k].RX, RY = cases[k].RY;
     int opaque;
     for (opaque = 1; opaque >= 0; opaque--) {
       GstVideoInfo info, rinfo;
@@ -70,7 +90,7 @@ main (int argc, char **argv)
       gsize i, bad = 0;
       guint p;
 
-      sm_state = 0x74746d6c + f * 2 + opaque;
+      sm_state = 0x74746d6c + (k * 64 + f) * 2 + opaque;
       gst_video_info_set_format (&info, formats[f].gst, W, H);
       fbuf = gst_buffer_new_allocate (NULL, info.size, NULL);
       gst_buffer_map (fbuf, &map, GST_MAP_WRITE);
@@ -84,22 +104,26 @@ main (int argc, char **argv)
       copy = g_memdup2 (map.data, map.size);
       gst_buffer_unmap (fbuf, &map);
 
-      /* premultiplied BGRA rectangle, like Cairo ARGB32 */
+      /* BGRA rectangle; premultiplied like Cairo ARGB32, or straight */
       gst_video_info_set_format (&rinfo, GST_VIDEO_OVERLAY_COMPOSITION_FORMAT_RGB, RW, RH);
       rpix = g_malloc (RW * RH * 4);
       for (i = 0; i < (gsize) RW * RH; i++) {
-        guint a = splitmix64 () & 0xff, k;
+        guint a = splitmix64 () & 0xff, c;
         if ((splitmix64 () & 7) == 0) a = 0;
         if ((splitmix64 () & 7) == 1) a = 255;
-        for (k = 0; k < 3; k++)
-          rpix[4 * i + k] = (guint8) (((splitmix64 () & 0xff) * a + 127) / 255);
+        for (c = 0; c < 3; c++) {
+          guint v = splitmix64 () & 0xff;
+          rpix[4 * i + c] = (guint8) (cases[k].premul ? (v * a + 127) / 255 : v);
+        }
         rpix[4 * i + 3] = (guint8) a;
       }
       rbuf = gst_buffer_new_wrapped (g_memdup2 (rpix, RW * RH * 4), RW * RH * 4);
       gst_buffer_add_video_meta (rbuf, GST_VIDEO_FRAME_FLAG_NONE,
           GST_VIDEO_OVERLAY_COMPOSITION_FORMAT_RGB, RW, RH);
       rect = gst_video_overlay_rectangle_new_raw (rbuf, RX, RY, RW, RH,
-          GST_VIDEO_OVERLAY_FORMAT_FLAG_PREMULTIPLIED_ALPHA);
+          cases[k].premul ? GST_VIDEO_OVERLAY_FORMAT_FLAG_PREMULTIPLIED_ALPHA :
+          GST_VIDEO_OVERLAY_FORMAT_FLAG_NONE);
+      gst_video_overlay_rectangle_set_global_alpha (rect, cases[k].ga);
       comp = gst_video_overlay_composition_new (rect);
 
       gst_video_frame_map (&frame, &info, fbuf, GST_MAP_READWRITE);
@@ -121,16 +145,16 @@ main (int argc, char **argv)
       rr.stride = RW * 4;
       rr.x = RX;
       rr.y = RY;
-      rr.global_alpha = 1.0f;
-      rr.flags = TBREF_FLAG_PREMULTIPLIED_ALPHA;
+      rr.global_alpha = cases[k].ga;
+      rr.flags = cases[k].premul ? TBREF_FLAG_PREMULTIPLIED_ALPHA : 0;
       tbref_composition_blend (&rf, &rr, 1);
 
       gst_buffer_map (fbuf, &map, GST_MAP_READ);
       for (i = 0; i < map.size; i++)
         bad += map.data[i] != copy[i];
       gst_buffer_unmap (fbuf, &map);
-      printf ("%-5s dest alpha %-7s: %" G_GSIZE_FORMAT " differing bytes of %" G_GSIZE_FORMAT "\n",
-          formats[f].name, opaque ? "opaque" : "random", bad, (gsize) info.size);
+      printf ("case %u %-5s dest alpha %-7s: %" G_GSIZE_FORMAT " differing bytes of %" G_GSIZE_FORMAT "\n",
+          k, formats[f].name, opaque ? "opaque" : "random", bad, (gsize) info.size);
       total_bad += bad;
 
       gst_video_overlay_composition_unref (comp);

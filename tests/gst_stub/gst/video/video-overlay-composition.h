@@ -9,6 +9,7 @@ typedef struct _GstVideoOverlayRectangle GstVideoOverlayRectangle;
 typedef struct _GstVideoOverlayComposition GstVideoOverlayComposition;
 GstVideoOverlayRectangle *gst_video_overlay_rectangle_new_raw (GstBuffer *, gint, gint, guint, guint, GstVideoOverlayFormatFlags);
 void gst_video_overlay_rectangle_unref (GstVideoOverlayRectangle *);
+void gst_video_overlay_rectangle_set_global_alpha (GstVideoOverlayRectangle *, gfloat);
 GstVideoOverlayComposition *gst_video_overlay_composition_new (GstVideoOverlayRectangle *);
 void gst_video_overlay_composition_unref (GstVideoOverlayComposition *);
 gboolean gst_video_overlay_composition_blend (GstVideoOverlayComposition *, GstVideoFrame *);
