@@ -38,8 +38,6 @@ using namespace tb;
 /* ---------------------------------------------------------------------- */
 /* format geometry                                                        */
 
-enum FormatClass { FC_I420, FC_YV12, FC_NV12, FC_NV21, FC_AYUV, FC_ARGB, FC_ABGR, FC_RGBA, FC_BGRA, FC_COUNT };
-
 /* RGBx / BGRx / xRGB / xBGR -> RGBA / BGRA / ARGB / ABGR (same pack/unpack in GStreamer) */
 inline int
 format_canon (int f)
