@@ -104,7 +104,34 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
     pp.ga = rr.ga;
     pp.premul = rr.premul ? 1 : 0;
 
-    if (kind == PK_PLANE8) {
+    pp.sub_x = format_sub_x (format);
+    pp.sub_y = format_sub_y (format);
+    if (kind == PK_PLANE8 && format_packed_422 (format)) {
+      /* YUY2 / UYVY: one plane of macropixels, every byte gets its own alpha + colour */
+      RectRef ref = {};
+      ref.v0 = (4 * (cx0 / 2)) / 16;
+      ref.v1 = ceil_div (4 * ceil_div (cx1, 2), 16);
+      ref.y0 = cy0;
+      ref.y1 = cy1;
+      ref.pitch = (ref.v1 - ref.v0) * 16;
+      ref.ga = 255;
+      const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+      uint8_t *a, *col;
+      int rc;
+      if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &col)))
+        return rc;
+      ref.a = a;
+      ref.c = col;
+      pp.mode = format == FLUC_TTMLBLEND_FORMAT_YUY2 ? PM_YUY2 : PM_UYVY;
+      pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
+      pp.out_pitch = ref.pitch;
+      pp.v0 = ref.v0;
+      pp.row0 = cy0;
+      pp.rows = cy1 - cy0;
+      CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
+      c->stats.prepare_launches++;
+      P->h_rects[0].push_back (ref);
+    } else if (kind == PK_PLANE8) {
       /* luma plane: byte == pixel */
       {
         RectRef ref = {};
@@ -131,12 +158,15 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
         c->stats.prepare_launches++;
         P->h_rects[0].push_back (ref);
       }
-      /* chroma: the samples sited on even x / even y (parity); with the non-parity 2x2
-       * average every sample with at least one covered pixel */
-      pp.chroma_average = P->chroma_average ? 1 : 0;
-      const int bx0 = P->chroma_average ? cx0 / 2 : ceil_div (cx0, 2), bx1 = ceil_div (cx1, 2);
-      const int by0 = P->chroma_average ? cy0 / 2 : ceil_div (cy0, 2), by1 = ceil_div (cy1, 2);
-      if (bx1 > bx0 && by1 > by0) {
+      /* chroma: the samples sited on the even pixel of each pair / the even line of each
+       * line pair, as far as the format subsamples (parity); with the non-parity 2x2 average
+       * of 4:2:0 every sample with at least one covered pixel */
+      const int sx = pp.sub_x, sy = pp.sub_y;
+      const bool avg = P->chroma_average && sx == 2 && sy == 2;
+      pp.chroma_average = avg ? 1 : 0;
+      const int bx0 = avg ? cx0 / 2 : ceil_div (cx0, sx), bx1 = ceil_div (cx1, sx);
+      const int by0 = avg ? cy0 / 2 : ceil_div (cy0, sy), by1 = ceil_div (cy1, sy);
+      if (n_planes >= 2 && bx1 > bx0 && by1 > by0) {
         if (n_planes == 3) {
           RectRef ref = {};
           ref.v0 = bx0 / 16;
@@ -159,7 +189,7 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
           pp.rows = by1 - by0;
           CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
           c->stats.prepare_launches++;
-          const int pu = format == FLUC_TTMLBLEND_FORMAT_I420 ? 1 : 2;
+          const int pu = format == FLUC_TTMLBLEND_FORMAT_YV12 ? 2 : 1;
           const int pv = 3 - pu;
           ref.a = a;
           ref.c = u;

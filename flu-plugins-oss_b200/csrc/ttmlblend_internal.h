@@ -57,12 +57,50 @@ format_valid (int f)
   return f >= 0 && f < FLUC_TTMLBLEND_FORMAT_COUNT;
 }
 
+/* chroma subsampling of the planar / semi-planar YUV formats (1 = none) */
+inline int
+format_sub_x (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_I420:
+    case FLUC_TTMLBLEND_FORMAT_YV12:
+    case FLUC_TTMLBLEND_FORMAT_NV12:
+    case FLUC_TTMLBLEND_FORMAT_NV21:
+    case FLUC_TTMLBLEND_FORMAT_Y42B:
+      return 2;
+    default:
+      return 1;
+  }
+}
+
+inline int
+format_sub_y (int f)
+{
+  switch (f) {
+    case FLUC_TTMLBLEND_FORMAT_I420:
+    case FLUC_TTMLBLEND_FORMAT_YV12:
+    case FLUC_TTMLBLEND_FORMAT_NV12:
+    case FLUC_TTMLBLEND_FORMAT_NV21:
+      return 2;
+    default:
+      return 1;
+  }
+}
+
+inline bool
+format_packed_422 (int f)
+{
+  return f == FLUC_TTMLBLEND_FORMAT_YUY2 || f == FLUC_TTMLBLEND_FORMAT_UYVY;
+}
+
 inline int
 format_planes (int f)
 {
   switch (f) {
     case FLUC_TTMLBLEND_FORMAT_I420:
     case FLUC_TTMLBLEND_FORMAT_YV12:
+    case FLUC_TTMLBLEND_FORMAT_Y42B:
+    case FLUC_TTMLBLEND_FORMAT_Y444:
       return 3;
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
@@ -78,10 +116,17 @@ plane_row_bytes (int f, int plane, int w)
   switch (f) {
     case FLUC_TTMLBLEND_FORMAT_I420:
     case FLUC_TTMLBLEND_FORMAT_YV12:
+    case FLUC_TTMLBLEND_FORMAT_Y42B:
       return plane == 0 ? w : (w + 1) / 2;
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
       return plane == 0 ? w : 2 * ((w + 1) / 2);
+    case FLUC_TTMLBLEND_FORMAT_Y444:
+    case FLUC_TTMLBLEND_FORMAT_GRAY8:
+      return w;
+    case FLUC_TTMLBLEND_FORMAT_YUY2:
+    case FLUC_TTMLBLEND_FORMAT_UYVY:
+      return 4 * ((w + 1) / 2);     /* whole macropixels */
     default:
       return 4 * w;
   }
@@ -90,7 +135,7 @@ plane_row_bytes (int f, int plane, int w)
 inline int
 plane_rows (int f, int plane, int h)
 {
-  return (format_planes (f) > 1 && plane > 0) ? (h + 1) / 2 : h;
+  return (plane > 0 && format_sub_y (f) == 2) ? (h + 1) / 2 : h;
 }
 
 inline int

@@ -706,7 +706,7 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
       break;
     }
     case PM_CHROMA_PLANAR:{
-      const int bx = p.v0 * 16 + i, x = 2 * bx, y = 2 * (p.row0 + r);
+      const int bx = p.v0 * 16 + i, x = p.sub_x * bx, y = p.sub_y * (p.row0 + r);
       uint8_t a = 0, u = 0, v = 0;
       if (x >= p.cx0 && x < p.cx1) {
         const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), premul);
@@ -724,7 +724,7 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
     }
     case PM_CHROMA_UV:
     case PM_CHROMA_VU:{
-      const int bx = p.v0 * 8 + i, x = 2 * bx, y = 2 * (p.row0 + r);
+      const int bx = p.v0 * 8 + i, x = p.sub_x * bx, y = p.sub_y * (p.row0 + r);
       uint8_t a = 0, u = 0, v = 0;
       if (x >= p.cx0 && x < p.cx1) {
         const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), premul);
@@ -739,6 +739,41 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
       p.out_a[orow + 2 * i + 1] = a;
       p.out_c[orow + 2 * i] = p.mode == PM_CHROMA_UV ? u : v;
       p.out_c[orow + 2 * i + 1] = p.mode == PM_CHROMA_UV ? v : u;
+      break;
+    }
+    case PM_YUY2:
+    case PM_UYVY:{
+      /* packed 4:2:2: thread = macropixel; both lumas, chroma from the even pixel */
+      const int x0 = 2 * (p.v0 * 4 + i), y = p.row0 + r;
+      uint8_t a0 = 0, a1 = 0, y0 = 0, y1 = 0, u = 0, v = 0;
+      if (x0 >= p.cx0 && x0 < p.cx1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x0, y), premul);
+        const int asrc = s.a * p.ga / 255;
+        if (asrc) {
+          a0 = (uint8_t) asrc;
+          y0 = (uint8_t) s.y;
+          u = (uint8_t) s.u;
+          v = (uint8_t) s.v;
+        }
+      }
+      if (x0 + 1 >= p.cx0 && x0 + 1 < p.cx1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x0 + 1, y), premul);
+        const int asrc = s.a * p.ga / 255;
+        if (asrc) {
+          a1 = (uint8_t) asrc;
+          y1 = (uint8_t) s.y;
+        }
+      }
+      uchar4 al, co;
+      if (p.mode == PM_YUY2) {
+        al = make_uchar4 (a0, a0, a1, a0);
+        co = make_uchar4 (y0, u, y1, v);
+      } else {
+        al = make_uchar4 (a0, a0, a0, a1);
+        co = make_uchar4 (u, y0, v, y1);
+      }
+      reinterpret_cast<uchar4 *> (p.out_a + orow)[i] = al;
+      reinterpret_cast<uchar4 *> (p.out_c + orow)[i] = co;
       break;
     }
     default:{
@@ -830,7 +865,7 @@ launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream)
 {
   if (n_elems <= 0 || p.rows <= 0)
     return cudaSuccess;
-  if (p.chroma_average && p.mode >= PM_CHROMA_PLANAR && p.mode <= PM_CHROMA_VU) {
+  if (p.chroma_average && p.sub_x == 2 && p.sub_y == 2 && p.mode >= PM_CHROMA_PLANAR && p.mode <= PM_CHROMA_VU) {
     for (int r0 = 0; r0 < p.rows; r0 += 65535) {
       PrepareParams q = p;
       const int nr = min (65535, p.rows - r0);

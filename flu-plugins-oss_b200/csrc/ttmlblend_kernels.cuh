@@ -139,6 +139,7 @@ struct PrepareParams {
   int32_t row0, rows;           /* first plane row and number of prepared rows */
   int32_t mode;
   int32_t chroma_average;       /* non-parity option: 2x2 alpha-weighted chroma instead of the sited pixel */
+  int32_t sub_x, sub_y;         /* chroma subsampling of the destination (2,2 / 2,1 / 1,1) */
 };
 
 enum PrepareMode : int32_t {
@@ -150,7 +151,9 @@ enum PrepareMode : int32_t {
   PM_PACKED_ARGB = 5,
   PM_PACKED_ABGR = 6,
   PM_PACKED_RGBA = 7,
-  PM_PACKED_BGRA = 8
+  PM_PACKED_BGRA = 8,
+  PM_YUY2 = 9,          /* one plane, macropixels Y0 U Y1 V: out_a / out_c per byte */
+  PM_UYVY = 10          /* macropixels U Y0 V Y1 */
 };
 
 /* All jobs of one launch share one PlaneKind and one variant: fast (every

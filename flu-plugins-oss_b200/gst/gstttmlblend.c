@@ -16,7 +16,8 @@
  * replaces the README pipeline's `compositor`
  * (/root/reference/plugins/ttml/README.md:45-48).
  *
- * Pads:  sink / src   video/x-raw { I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA }
+ * Pads:  sink / src   video/x-raw { I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA,
+ *                                   RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8 }
  *        subtitle_sink  video/x-raw, format=BGRA   (= GST_TTMLRENDER_SRC_CAPS)
  * Each subtitle buffer is valid for [PTS, PTS+duration) (gst_ttmlbase_gen_buffer,
  * /root/reference/plugins/ttml/gstttmlbase.c:180-181); an all-zero "clear"
@@ -62,7 +63,7 @@ enum
   PROP_DEVICE
 };
 
-#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR }"
+#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8 }"
 
 static GstStaticPadTemplate video_sink_template = GST_STATIC_PAD_TEMPLATE ("sink",
     GST_PAD_SINK, GST_PAD_ALWAYS,
@@ -96,6 +97,11 @@ to_fluc_format (GstVideoFormat f)
     case GST_VIDEO_FORMAT_BGRx: return FLUC_TTMLBLEND_FORMAT_BGRx;
     case GST_VIDEO_FORMAT_xRGB: return FLUC_TTMLBLEND_FORMAT_xRGB;
     case GST_VIDEO_FORMAT_xBGR: return FLUC_TTMLBLEND_FORMAT_xBGR;
+    case GST_VIDEO_FORMAT_Y42B: return FLUC_TTMLBLEND_FORMAT_Y42B;
+    case GST_VIDEO_FORMAT_Y444: return FLUC_TTMLBLEND_FORMAT_Y444;
+    case GST_VIDEO_FORMAT_YUY2: return FLUC_TTMLBLEND_FORMAT_YUY2;
+    case GST_VIDEO_FORMAT_UYVY: return FLUC_TTMLBLEND_FORMAT_UYVY;
+    case GST_VIDEO_FORMAT_GRAY8: return FLUC_TTMLBLEND_FORMAT_GRAY8;
     default: return FLUC_TTMLBLEND_FORMAT_COUNT;
   }
 }

@@ -93,6 +93,14 @@ def plane_shapes(fmt: str, width: int, height: int):
         return [(height, width), (ch, cw), (ch, cw)]
     if f in ("NV12", "NV21"):
         return [(height, width), (ch, 2 * cw)]
+    if f == "Y42B":
+        return [(height, width), (height, cw), (height, cw)]
+    if f == "Y444":
+        return [(height, width)] * 3
+    if f in ("YUY2", "UYVY"):
+        return [(height, 4 * cw)]
+    if f == "GRAY8":
+        return [(height, width)]
     return [(height, 4 * width)]
 
 

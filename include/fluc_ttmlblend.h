@@ -69,6 +69,13 @@ typedef enum {
   FLUC_TTMLBLEND_FORMAT_BGRx = 10,
   FLUC_TTMLBLEND_FORMAT_xRGB = 11,
   FLUC_TTMLBLEND_FORMAT_xBGR = 12,
+  /* further 8-bit YUV layouts GStreamer blends onto through the same AYUV lines: planar
+   * 4:2:2 / 4:4:4, packed 4:2:2, grey. Chroma of a pixel pair comes from its even pixel. */
+  FLUC_TTMLBLEND_FORMAT_Y42B = 13,
+  FLUC_TTMLBLEND_FORMAT_Y444 = 14,
+  FLUC_TTMLBLEND_FORMAT_YUY2 = 15,
+  FLUC_TTMLBLEND_FORMAT_UYVY = 16,
+  FLUC_TTMLBLEND_FORMAT_GRAY8 = 17,
   FLUC_TTMLBLEND_FORMAT_COUNT
 } FlucTtmlBlendFormat;
 
@@ -109,7 +116,7 @@ typedef struct {
 } FlucTtmlBlendRectangle;
 
 /* Plane pointers + strides of one frame (GstVideoFrame data[]/stride[]).
- * I420: Y,U,V. YV12: Y,V,U. NV12/NV21: Y,UV. Packed formats: plane[0]. */
+ * I420 / Y42B / Y444: Y,U,V. YV12: Y,V,U. NV12/NV21: Y,UV. Packed formats, GRAY8: plane[0]. */
 typedef struct {
   void *plane[3];
   int32_t stride[3];

@@ -37,7 +37,9 @@ is_yuv (int32_t f)
 {
   return f == TBREF_FORMAT_I420 || f == TBREF_FORMAT_NV12 ||
       f == TBREF_FORMAT_AYUV || f == TBREF_FORMAT_YV12 ||
-      f == TBREF_FORMAT_NV21;
+      f == TBREF_FORMAT_NV21 || f == TBREF_FORMAT_Y42B ||
+      f == TBREF_FORMAT_Y444 || f == TBREF_FORMAT_YUY2 ||
+      f == TBREF_FORMAT_UYVY || f == TBREF_FORMAT_GRAY8;
 }
 
 int32_t
@@ -46,6 +48,8 @@ tbref_n_planes (int32_t f)
   switch (f) {
     case TBREF_FORMAT_I420:
     case TBREF_FORMAT_YV12:
+    case TBREF_FORMAT_Y42B:
+    case TBREF_FORMAT_Y444:
       return 3;
     case TBREF_FORMAT_NV12:
     case TBREF_FORMAT_NV21:
@@ -61,10 +65,17 @@ tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
   switch (f) {
     case TBREF_FORMAT_I420:
     case TBREF_FORMAT_YV12:
+    case TBREF_FORMAT_Y42B:
       return plane == 0 ? w : (w + 1) / 2;
     case TBREF_FORMAT_NV12:
     case TBREF_FORMAT_NV21:
       return plane == 0 ? w : 2 * ((w + 1) / 2);
+    case TBREF_FORMAT_Y444:
+    case TBREF_FORMAT_GRAY8:
+      return w;
+    case TBREF_FORMAT_YUY2:
+    case TBREF_FORMAT_UYVY:
+      return 4 * ((w + 1) / 2);
     default:
       return 4 * w;
   }
@@ -73,7 +84,8 @@ tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
 int32_t
 tbref_plane_rows (int32_t f, int32_t plane, int32_t h)
 {
-  if (tbref_n_planes (f) > 1 && plane > 0)
+  if (plane > 0 && (f == TBREF_FORMAT_I420 || f == TBREF_FORMAT_YV12 ||
+          f == TBREF_FORMAT_NV12 || f == TBREF_FORMAT_NV21))
     return (h + 1) / 2;
   return h;
 }
@@ -113,6 +125,54 @@ unpack_line (const TbRefFrame *f, int y, uint8_t *d, int width)
         d[4 * x + 1] = sy[x];
         d[4 * x + 2] = suv[(x >> 1) * 2 + ou];
         d[4 * x + 3] = suv[(x >> 1) * 2 + (1 - ou)];
+      }
+      break;
+    }
+    case TBREF_FORMAT_Y42B:{       /* unpack_Y42B: chroma of the pair, same line */
+      const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
+      const uint8_t *su = f->data[1] + (size_t) f->stride[1] * y;
+      const uint8_t *sv = f->data[2] + (size_t) f->stride[2] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = sy[x];
+        d[4 * x + 2] = su[x >> 1];
+        d[4 * x + 3] = sv[x >> 1];
+      }
+      break;
+    }
+    case TBREF_FORMAT_Y444:{
+      const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
+      const uint8_t *su = f->data[1] + (size_t) f->stride[1] * y;
+      const uint8_t *sv = f->data[2] + (size_t) f->stride[2] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = sy[x];
+        d[4 * x + 2] = su[x];
+        d[4 * x + 3] = sv[x];
+      }
+      break;
+    }
+    case TBREF_FORMAT_YUY2:
+    case TBREF_FORMAT_UYVY:{       /* unpack_YUY2 / unpack_UYVY: macropixels of two pixels */
+      const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
+      const int oy = f->format == TBREF_FORMAT_YUY2 ? 0 : 1;   /* Y at 0,2 or 1,3 */
+      const int ou = f->format == TBREF_FORMAT_YUY2 ? 1 : 0, ov = f->format == TBREF_FORMAT_YUY2 ? 3 : 2;
+      for (x = 0; x < width; x++) {
+        const uint8_t *m = s + 4 * (x >> 1);
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = m[oy + 2 * (x & 1)];
+        d[4 * x + 2] = m[ou];
+        d[4 * x + 3] = m[ov];
+      }
+      break;
+    }
+    case TBREF_FORMAT_GRAY8:{      /* unpack_GRAY8: U = V = 0x80 */
+      const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = sy[x];
+        d[4 * x + 2] = 0x80;
+        d[4 * x + 3] = 0x80;
       }
       break;
     }
@@ -211,6 +271,61 @@ pack_line (TbRefFrame *f, int y, const uint8_t *s, int width)
         for (x = 0; x < width; x++)
           dy[x] = s[4 * x + 1];
       }
+      break;
+    }
+    case TBREF_FORMAT_Y42B:{       /* pack_Y42B: every line, chroma from the even pixel */
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      uint8_t *du = f->data[1] + (size_t) f->stride[1] * y;
+      uint8_t *dv = f->data[2] + (size_t) f->stride[2] * y;
+      for (i = 0; i < width / 2; i++) {
+        dy[i * 2 + 0] = s[i * 8 + 1];
+        dy[i * 2 + 1] = s[i * 8 + 5];
+        du[i] = s[i * 8 + 2];
+        dv[i] = s[i * 8 + 3];
+      }
+      if (width & 1) {
+        i = width - 1;
+        dy[i] = s[i * 4 + 1];
+        du[i >> 1] = s[i * 4 + 2];
+        dv[i >> 1] = s[i * 4 + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_Y444:{
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      uint8_t *du = f->data[1] + (size_t) f->stride[1] * y;
+      uint8_t *dv = f->data[2] + (size_t) f->stride[2] * y;
+      for (x = 0; x < width; x++) {
+        dy[x] = s[4 * x + 1];
+        du[x] = s[4 * x + 2];
+        dv[x] = s[4 * x + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_YUY2:
+    case TBREF_FORMAT_UYVY:{       /* pack_YUY2 / pack_UYVY: chroma from the even pixel; an odd
+                                    * last pixel writes its Y, U and V, not the second luma */
+      uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
+      const int oy = f->format == TBREF_FORMAT_YUY2 ? 0 : 1;
+      const int ou = f->format == TBREF_FORMAT_YUY2 ? 1 : 0, ov = f->format == TBREF_FORMAT_YUY2 ? 3 : 2;
+      for (i = 0; i < width / 2; i++) {
+        d[i * 4 + oy] = s[i * 8 + 1];
+        d[i * 4 + oy + 2] = s[i * 8 + 5];
+        d[i * 4 + ou] = s[i * 8 + 2];
+        d[i * 4 + ov] = s[i * 8 + 3];
+      }
+      if (width & 1) {
+        i = width - 1;
+        d[i * 2 + oy] = s[i * 4 + 1];
+        d[i * 2 + ou] = s[i * 4 + 2];
+        d[i * 2 + ov] = s[i * 4 + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_GRAY8:{
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      for (x = 0; x < width; x++)
+        dy[x] = s[4 * x + 1];
       break;
     }
     case TBREF_FORMAT_AYUV:
@@ -377,7 +492,8 @@ tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src)
 
   if (!dest || !src || !src->pixels)
     return 0;
-  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_ABGR)
+  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_GRAY8 ||
+      (dest->format > TBREF_FORMAT_ABGR && dest->format < TBREF_FORMAT_Y42B))
     return 0;
 
   ga = (int) (255.0 * src->global_alpha);

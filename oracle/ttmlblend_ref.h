@@ -39,7 +39,13 @@ enum {
   TBREF_FORMAT_YV12 = 5,
   TBREF_FORMAT_NV21 = 6,
   TBREF_FORMAT_ARGB = 7,
-  TBREF_FORMAT_ABGR = 8
+  TBREF_FORMAT_ABGR = 8,
+  /* 9..12 (RGBx, BGRx, xRGB, xBGR) are aliases of 3, 4, 7, 8 and are mapped by the caller */
+  TBREF_FORMAT_Y42B = 13,
+  TBREF_FORMAT_Y444 = 14,
+  TBREF_FORMAT_YUY2 = 15,
+  TBREF_FORMAT_UYVY = 16,
+  TBREF_FORMAT_GRAY8 = 17
 };
 
 #define TBREF_FLAG_PREMULTIPLIED_ALPHA 1u

@@ -45,6 +45,16 @@ static const struct {
   { GST_VIDEO_FORMAT_ABGR, TBREF_FORMAT_ABGR, "ABGR" },
   { GST_VIDEO_FORMAT_RGBA, TBREF_FORMAT_RGBA, "RGBA" },
   { GST_VIDEO_FORMAT_BGRA, TBREF_FORMAT_BGRA, "BGRA" },
+  /* padded RGB: expected to behave like their alpha twins (same pack/unpack) */
+  { GST_VIDEO_FORMAT_RGBx, TBREF_FORMAT_RGBA, "RGBx" },
+  { GST_VIDEO_FORMAT_BGRx, TBREF_FORMAT_BGRA, "BGRx" },
+  { GST_VIDEO_FORMAT_xRGB, TBREF_FORMAT_ARGB, "xRGB" },
+  { GST_VIDEO_FORMAT_xBGR, TBREF_FORMAT_ABGR, "xBGR" },
+  { GST_VIDEO_FORMAT_Y42B, TBREF_FORMAT_Y42B, "Y42B" },
+  { GST_VIDEO_FORMAT_Y444, TBREF_FORMAT_Y444, "Y444" },
+  { GST_VIDEO_FORMAT_YUY2, TBREF_FORMAT_YUY2, "YUY2" },
+  { GST_VIDEO_FORMAT_UYVY, TBREF_FORMAT_UYVY, "UYVY" },
+  { GST_VIDEO_FORMAT_GRAY8, TBREF_FORMAT_GRAY8, "GRAY8" },
 };
 
 /* geometry / flag cases: frame size, rectangle size and position (hanging over every

@@ -33,6 +33,15 @@ VECTORS = [
     ("bgra_alpha_dest", "BGRA", 80, 48, [(60, 20, 10, 20, 0.6, True), (30, 30, 40, 10, 1.0, False)], False, False),
     ("argb_premul_dest", "ARGB", 80, 48, [(60, 20, 10, 20, 1.0, True)], False, True),
     ("abgr", "ABGR", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
+    ("y42b", "Y42B", 63, 40, [(40, 20, 11, 13, 1.0, True), (9, 9, 57, 35, 1.0, True)], True, False),
+    ("y444", "Y444", 64, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
+    ("yuy2", "YUY2", 63, 40, [(40, 20, 11, 13, 1.0, True), (9, 9, 57, 35, 1.0, False)], True, False),
+    ("uyvy", "UYVY", 64, 40, [(41, 20, 10, 13, 1.0, True)], True, False),
+    ("gray8", "GRAY8", 50, 30, [(30, 10, 7, 9, 1.0, True)], True, False),
+    ("rgbx", "RGBx", 40, 24, [(20, 10, 3, 5, 1.0, True)], False, False),
+    ("bgrx", "BGRx", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
+    ("xrgb", "xRGB", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
+    ("xbgr", "xBGR", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
 ]
 
 

@@ -10,10 +10,31 @@ import __graft_entry__ as graft
 pkg = graft.load_package()
 wl = pkg.workloads
 
-YUV_FORMATS = ("I420", "YV12", "NV12", "NV21", "AYUV")
+YUV_FORMATS = ("I420", "YV12", "NV12", "NV21", "AYUV", "Y42B", "Y444", "YUY2", "UYVY", "GRAY8")
 PLANAR_420 = ("I420", "YV12", "NV12", "NV21")
+MORE_YUV = ("Y42B", "Y444", "YUY2", "UYVY", "GRAY8")       # byte-plane formats beyond 4:2:0
 PACKED = ("AYUV", "ARGB", "ABGR", "RGBA", "BGRA")
-ALL_FORMATS = PLANAR_420 + PACKED
+ALL_FORMATS = PLANAR_420 + PACKED + MORE_YUV
+
+
+def yuv_views(fmt, planes, w):
+    """(Y, U, V, sub_x, sub_y): writable strided views of the luma / chroma samples of a
+    byte-plane YUV frame (U, V None for GRAY8)."""
+    if fmt in ("I420", "Y42B", "Y444"):
+        return planes[0], planes[1], planes[2], (1 if fmt == "Y444" else 2), (2 if fmt == "I420" else 1)
+    if fmt == "YV12":
+        return planes[0], planes[2], planes[1], 2, 2
+    if fmt == "NV12":
+        return planes[0], planes[1][:, 0::2], planes[1][:, 1::2], 2, 2
+    if fmt == "NV21":
+        return planes[0], planes[1][:, 1::2], planes[1][:, 0::2], 2, 2
+    if fmt == "YUY2":
+        return planes[0][:, 0::2][:, :w], planes[0][:, 1::4], planes[0][:, 3::4], 2, 1
+    if fmt == "UYVY":
+        return planes[0][:, 1::2][:, :w], planes[0][:, 0::4], planes[0][:, 2::4], 2, 1
+    if fmt == "GRAY8":
+        return planes[0], None, None, 1, 1
+    raise KeyError(fmt)
 
 # byte positions of (A, c1, c2, c3) inside a packed pixel, c = (Y,U,V) or (R,G,B)
 PACKED_ORDER = {"AYUV": (0, 1, 2, 3), "ARGB": (0, 1, 2, 3), "ABGR": (0, 3, 2, 1),
@@ -110,12 +131,14 @@ def model_blend(fmt, w, h, planes, rectangles, dest_premul=False, chroma_average
             c1, c2, c3 = r, g, b
         asrc = a * ga // 255
         m = asrc > 0
-        if fmt in PLANAR_420:
-            Y = planes[0]
+        if fmt not in PACKED_ORDER:
+            Y, U, V, sx, sy = yuv_views(fmt, planes, w)
             yd = Y[y0:y1, x0:x1].astype(np.int64)
             v, _ = _over(c1, yd, asrc, 255, ga, sp, dest_premul)
             Y[y0:y1, x0:x1] = np.where(m, v, yd).astype(np.uint8)
-            if chroma_average:
+            if U is None:
+                continue
+            if chroma_average and sx == 2 and sy == 2:
                 # every chroma sample with a covered pixel: alpha = mean of the 4 alphas (outside
                 # the rectangle counts as 0), colour = alpha-weighted mean
                 bx0, bx1, by0, by1 = x0 // 2, (x1 + 1) // 2, y0 // 2, (y1 + 1) // 2
@@ -130,40 +153,23 @@ def model_blend(fmt, w, h, planes, rectangles, dest_premul=False, chroma_average
                 cu, cv = (su + sa // 2) // den, (sv + sa // 2) // den
                 cm = ca > 0
                 nby, nbx = ca.shape
-                if fmt in ("I420", "YV12"):
-                    iu, iv = (1, 2) if fmt == "I420" else (2, 1)
-                    for plane, cc in ((planes[iu], cu), (planes[iv], cv)):
-                        d = plane[by0:by0 + nby, bx0:bx0 + nbx].astype(np.int64)
-                        plane[by0:by0 + nby, bx0:bx0 + nbx] = np.where(cm, (cc * ca + d * (255 - ca)) // 255, d).astype(np.uint8)
-                else:
-                    ou, ovv = (0, 1) if fmt == "NV12" else (1, 0)
-                    UV = planes[1]
-                    for off, cc in ((ou, cu), (ovv, cv)):
-                        view = UV[by0:by0 + nby, 2 * bx0 + off:2 * (bx0 + nbx):2]
-                        d = view.astype(np.int64)
-                        view[...] = np.where(cm, (cc * ca + d * (255 - ca)) // 255, d).astype(np.uint8)
+                for plane, cc in ((U, cu), (V, cv)):
+                    view = plane[by0:by0 + nby, bx0:bx0 + nbx]
+                    d = view.astype(np.int64)
+                    view[...] = np.where(cm, (cc * ca + d * (255 - ca)) // 255, d).astype(np.uint8)
                 continue
-            # chroma sample (bx, by) <- overlay pixel at frame (2bx, 2by) only
-            ex0, ey0 = x0 + (x0 & 1), y0 + (y0 & 1)
+            # chroma sample (bx, by) <- overlay pixel at frame (sx*bx, sy*by) only
+            ex0, ey0 = -(-x0 // sx) * sx, -(-y0 // sy) * sy
             if ex0 < x1 and ey0 < y1:
-                sl = (slice(ey0 - y0, None, 2), slice(ex0 - x0, None, 2))
+                sl = (slice(ey0 - y0, None, sy), slice(ex0 - x0, None, sx))
                 cu, cv, ca, cm = c2[sl], c3[sl], asrc[sl], m[sl]
-                by0, bx0 = ey0 // 2, ex0 // 2
+                by0, bx0 = ey0 // sy, ex0 // sx
                 nby, nbx = cu.shape
-                if fmt in ("I420", "YV12"):
-                    pu, pv = (1, 2) if fmt == "I420" else (2, 1)
-                    for plane, cc in ((planes[pu], cu), (planes[pv], cv)):
-                        d = plane[by0:by0 + nby, bx0:bx0 + nbx].astype(np.int64)
-                        vv, _ = _over(cc, d, ca, 255, ga, sp, dest_premul)
-                        plane[by0:by0 + nby, bx0:bx0 + nbx] = np.where(cm, vv, d).astype(np.uint8)
-                else:
-                    ou, ov = (0, 1) if fmt == "NV12" else (1, 0)
-                    UV = planes[1]
-                    for off, cc in ((ou, cu), (ov, cv)):
-                        view = UV[by0:by0 + nby, 2 * bx0 + off:2 * (bx0 + nbx):2]
-                        d = view.astype(np.int64)
-                        vv, _ = _over(cc, d, ca, 255, ga, sp, dest_premul)
-                        view[...] = np.where(cm, vv, d).astype(np.uint8)
+                for plane, cc in ((U, cu), (V, cv)):
+                    view = plane[by0:by0 + nby, bx0:bx0 + nbx]
+                    d = view.astype(np.int64)
+                    vv, _ = _over(cc, d, ca, 255, ga, sp, dest_premul)
+                    view[...] = np.where(cm, vv, d).astype(np.uint8)
         else:
             ia, i1, i2, i3 = PACKED_ORDER[fmt]
             P = planes[0]

@@ -55,7 +55,7 @@ def test_rectangles_match_oracle(ctx, fmt, case, mode):
     assert_planes_equal(got, want, f"{fmt} case {case} {mode}")
 
 
-@pytest.mark.parametrize("fmt", ALL_FORMATS)
+@pytest.mark.parametrize("fmt", ALL_FORMATS + ("RGBx", "BGRx", "xRGB", "xBGR"))
 def test_golden_fixtures(ctx, fmt):
     with open(os.path.join(GOLDEN, "manifest.json")) as f:
         manifest = json.load(f)
