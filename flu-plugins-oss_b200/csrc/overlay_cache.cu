@@ -209,7 +209,7 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
           int rc;
           if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &uv)))
             return rc;
-          pp.mode = format == FLUC_TTMLBLEND_FORMAT_NV12 ? PM_CHROMA_UV : PM_CHROMA_VU;
+          pp.mode = format == FLUC_TTMLBLEND_FORMAT_NV21 ? PM_CHROMA_VU : PM_CHROMA_UV;
           pp.out_a = a; pp.out_c = uv; pp.out_c2 = nullptr;
           pp.out_pitch = ref.pitch;
           pp.v0 = ref.v0;

@@ -67,6 +67,7 @@ format_sub_x (int f)
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
     case FLUC_TTMLBLEND_FORMAT_Y42B:
+    case FLUC_TTMLBLEND_FORMAT_NV16:
       return 2;
     default:
       return 1;
@@ -104,6 +105,8 @@ format_planes (int f)
       return 3;
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
+    case FLUC_TTMLBLEND_FORMAT_NV16:
+    case FLUC_TTMLBLEND_FORMAT_NV24:
       return 2;
     default:
       return 1;
@@ -120,7 +123,10 @@ plane_row_bytes (int f, int plane, int w)
       return plane == 0 ? w : (w + 1) / 2;
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
+    case FLUC_TTMLBLEND_FORMAT_NV16:
       return plane == 0 ? w : 2 * ((w + 1) / 2);
+    case FLUC_TTMLBLEND_FORMAT_NV24:
+      return plane == 0 ? w : 2 * w;
     case FLUC_TTMLBLEND_FORMAT_Y444:
     case FLUC_TTMLBLEND_FORMAT_GRAY8:
       return w;

@@ -17,7 +17,8 @@
  * (/root/reference/plugins/ttml/README.md:45-48).
  *
  * Pads:  sink / src   video/x-raw { I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA,
- *                                   RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8 }
+ *                                   RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8,
+ *                                   NV16, NV24 }
  *        subtitle_sink  video/x-raw, format=BGRA   (= GST_TTMLRENDER_SRC_CAPS)
  * Each subtitle buffer is valid for [PTS, PTS+duration) (gst_ttmlbase_gen_buffer,
  * /root/reference/plugins/ttml/gstttmlbase.c:180-181); an all-zero "clear"
@@ -63,7 +64,7 @@ enum
   PROP_DEVICE
 };
 
-#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8 }"
+#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8, NV16, NV24 }"
 
 static GstStaticPadTemplate video_sink_template = GST_STATIC_PAD_TEMPLATE ("sink",
     GST_PAD_SINK, GST_PAD_ALWAYS,
@@ -102,6 +103,8 @@ to_fluc_format (GstVideoFormat f)
     case GST_VIDEO_FORMAT_YUY2: return FLUC_TTMLBLEND_FORMAT_YUY2;
     case GST_VIDEO_FORMAT_UYVY: return FLUC_TTMLBLEND_FORMAT_UYVY;
     case GST_VIDEO_FORMAT_GRAY8: return FLUC_TTMLBLEND_FORMAT_GRAY8;
+    case GST_VIDEO_FORMAT_NV16: return FLUC_TTMLBLEND_FORMAT_NV16;
+    case GST_VIDEO_FORMAT_NV24: return FLUC_TTMLBLEND_FORMAT_NV24;
     default: return FLUC_TTMLBLEND_FORMAT_COUNT;
   }
 }

@@ -25,7 +25,7 @@ FORMATS = {
     "I420": 0, "NV12": 1, "AYUV": 2, "RGBA": 3, "BGRA": 4,
     "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8,
     "RGBx": 9, "BGRx": 10, "xRGB": 11, "xBGR": 12,       # same paths as RGBA / BGRA / ARGB / ABGR
-    "Y42B": 13, "Y444": 14, "YUY2": 15, "UYVY": 16, "GRAY8": 17,
+    "Y42B": 13, "Y444": 14, "YUY2": 15, "UYVY": 16, "GRAY8": 17, "NV16": 18, "NV24": 19,
 }
 FLAG_PREMULTIPLIED_ALPHA = 1
 MAX_RECTANGLES = 64
@@ -158,6 +158,10 @@ def plane_layout(fmt: str, width: int, height: int):
     if f in ("NV12", "NV21"):
         cw, ch = (width + 1) // 2, (height + 1) // 2
         return [(width, height), (2 * cw, ch)]
+    if f == "NV16":
+        return [(width, height), (2 * ((width + 1) // 2), height)]
+    if f == "NV24":
+        return [(width, height), (2 * width, height)]
     if f == "Y42B":
         return [(width, height), ((width + 1) // 2, height), ((width + 1) // 2, height)]
     if f == "Y444":

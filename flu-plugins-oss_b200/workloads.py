@@ -93,6 +93,10 @@ def plane_shapes(fmt: str, width: int, height: int):
         return [(height, width), (ch, cw), (ch, cw)]
     if f in ("NV12", "NV21"):
         return [(height, width), (ch, 2 * cw)]
+    if f == "NV16":
+        return [(height, width), (height, 2 * cw)]
+    if f == "NV24":
+        return [(height, width), (height, 2 * width)]
     if f == "Y42B":
         return [(height, width), (height, cw), (height, cw)]
     if f == "Y444":

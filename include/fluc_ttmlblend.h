@@ -76,6 +76,8 @@ typedef enum {
   FLUC_TTMLBLEND_FORMAT_YUY2 = 15,
   FLUC_TTMLBLEND_FORMAT_UYVY = 16,
   FLUC_TTMLBLEND_FORMAT_GRAY8 = 17,
+  FLUC_TTMLBLEND_FORMAT_NV16 = 18,      /* semi-planar 4:2:2 */
+  FLUC_TTMLBLEND_FORMAT_NV24 = 19,      /* semi-planar 4:4:4 */
   FLUC_TTMLBLEND_FORMAT_COUNT
 } FlucTtmlBlendFormat;
 
@@ -116,7 +118,7 @@ typedef struct {
 } FlucTtmlBlendRectangle;
 
 /* Plane pointers + strides of one frame (GstVideoFrame data[]/stride[]).
- * I420 / Y42B / Y444: Y,U,V. YV12: Y,V,U. NV12/NV21: Y,UV. Packed formats, GRAY8: plane[0]. */
+ * I420 / Y42B / Y444: Y,U,V. YV12: Y,V,U. NV12/NV21/NV16/NV24: Y,UV. Packed formats, GRAY8: plane[0]. */
 typedef struct {
   void *plane[3];
   int32_t stride[3];

@@ -25,7 +25,7 @@ main (void)
 {
   static const int sizes[][2] = { {1, 1}, {2, 2}, {3, 5}, {17, 9}, {64, 48}, {63, 47}, {129, 3} };
   int fmt, s, k, fails = 0;
-  for (fmt = TBREF_FORMAT_I420; fmt <= TBREF_FORMAT_GRAY8; fmt++) {
+  for (fmt = TBREF_FORMAT_I420; fmt <= TBREF_FORMAT_NV24; fmt++) {
     if (fmt > TBREF_FORMAT_ABGR && fmt < TBREF_FORMAT_Y42B)
       continue;
     for (s = 0; s < (int) (sizeof sizes / sizeof sizes[0]); s++) {

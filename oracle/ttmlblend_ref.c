@@ -39,7 +39,8 @@ is_yuv (int32_t f)
       f == TBREF_FORMAT_AYUV || f == TBREF_FORMAT_YV12 ||
       f == TBREF_FORMAT_NV21 || f == TBREF_FORMAT_Y42B ||
       f == TBREF_FORMAT_Y444 || f == TBREF_FORMAT_YUY2 ||
-      f == TBREF_FORMAT_UYVY || f == TBREF_FORMAT_GRAY8;
+      f == TBREF_FORMAT_UYVY || f == TBREF_FORMAT_GRAY8 ||
+      f == TBREF_FORMAT_NV16 || f == TBREF_FORMAT_NV24;
 }
 
 int32_t
@@ -53,6 +54,8 @@ tbref_n_planes (int32_t f)
       return 3;
     case TBREF_FORMAT_NV12:
     case TBREF_FORMAT_NV21:
+    case TBREF_FORMAT_NV16:
+    case TBREF_FORMAT_NV24:
       return 2;
     default:
       return 1;
@@ -69,7 +72,10 @@ tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
       return plane == 0 ? w : (w + 1) / 2;
     case TBREF_FORMAT_NV12:
     case TBREF_FORMAT_NV21:
+    case TBREF_FORMAT_NV16:
       return plane == 0 ? w : 2 * ((w + 1) / 2);
+    case TBREF_FORMAT_NV24:
+      return plane == 0 ? w : 2 * w;
     case TBREF_FORMAT_Y444:
     case TBREF_FORMAT_GRAY8:
       return w;
@@ -125,6 +131,19 @@ unpack_line (const TbRefFrame *f, int y, uint8_t *d, int width)
         d[4 * x + 1] = sy[x];
         d[4 * x + 2] = suv[(x >> 1) * 2 + ou];
         d[4 * x + 3] = suv[(x >> 1) * 2 + (1 - ou)];
+      }
+      break;
+    }
+    case TBREF_FORMAT_NV16:
+    case TBREF_FORMAT_NV24:{       /* unpack_NV16 / unpack_NV24: UV interleaved, same line */
+      const int sh = f->format == TBREF_FORMAT_NV16 ? 1 : 0;
+      const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
+      const uint8_t *suv = f->data[1] + (size_t) f->stride[1] * y;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = sy[x];
+        d[4 * x + 2] = suv[(x >> sh) * 2 + 0];
+        d[4 * x + 3] = suv[(x >> sh) * 2 + 1];
       }
       break;
     }
@@ -270,6 +289,33 @@ pack_line (TbRefFrame *f, int y, const uint8_t *s, int width)
       } else {
         for (x = 0; x < width; x++)
           dy[x] = s[4 * x + 1];
+      }
+      break;
+    }
+    case TBREF_FORMAT_NV16:{       /* pack_NV16: every line, UV from the even pixel */
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      uint8_t *duv = f->data[1] + (size_t) f->stride[1] * y;
+      for (i = 0; i < width / 2; i++) {
+        dy[i * 2 + 0] = s[i * 8 + 1];
+        dy[i * 2 + 1] = s[i * 8 + 5];
+        duv[i * 2 + 0] = s[i * 8 + 2];
+        duv[i * 2 + 1] = s[i * 8 + 3];
+      }
+      if (width & 1) {
+        i = width - 1;
+        dy[i] = s[i * 4 + 1];
+        duv[i + 0] = s[i * 4 + 2];
+        duv[i + 1] = s[i * 4 + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_NV24:{
+      uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
+      uint8_t *duv = f->data[1] + (size_t) f->stride[1] * y;
+      for (x = 0; x < width; x++) {
+        dy[x] = s[4 * x + 1];
+        duv[2 * x + 0] = s[4 * x + 2];
+        duv[2 * x + 1] = s[4 * x + 3];
       }
       break;
     }
@@ -492,7 +538,7 @@ tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src)
 
   if (!dest || !src || !src->pixels)
     return 0;
-  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_GRAY8 ||
+  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_NV24 ||
       (dest->format > TBREF_FORMAT_ABGR && dest->format < TBREF_FORMAT_Y42B))
     return 0;
 

@@ -45,7 +45,9 @@ enum {
   TBREF_FORMAT_Y444 = 14,
   TBREF_FORMAT_YUY2 = 15,
   TBREF_FORMAT_UYVY = 16,
-  TBREF_FORMAT_GRAY8 = 17
+  TBREF_FORMAT_GRAY8 = 17,
+  TBREF_FORMAT_NV16 = 18,
+  TBREF_FORMAT_NV24 = 19
 };
 
 #define TBREF_FLAG_PREMULTIPLIED_ALPHA 1u

@@ -55,6 +55,8 @@ static const struct {
   { GST_VIDEO_FORMAT_YUY2, TBREF_FORMAT_YUY2, "YUY2" },
   { GST_VIDEO_FORMAT_UYVY, TBREF_FORMAT_UYVY, "UYVY" },
   { GST_VIDEO_FORMAT_GRAY8, TBREF_FORMAT_GRAY8, "GRAY8" },
+  { GST_VIDEO_FORMAT_NV16, TBREF_FORMAT_NV16, "NV16" },
+  { GST_VIDEO_FORMAT_NV24, TBREF_FORMAT_NV24, "NV24" },
 };
 
 /* geometry / flag cases: frame size, rectangle size and position (hanging over every

@@ -42,6 +42,9 @@ VECTORS = [
     ("bgrx", "BGRx", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
     ("xrgb", "xRGB", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
     ("xbgr", "xBGR", 40, 24, [(20, 10, 3, 5, 1.0, True)], True, False),
+    # append only: a vector's seed is its position in this list
+    ("nv16", "NV16", 63, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
+    ("nv24", "NV24", 61, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
 ]
 
 

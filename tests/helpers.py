@@ -10,9 +10,9 @@ import __graft_entry__ as graft
 pkg = graft.load_package()
 wl = pkg.workloads
 
-YUV_FORMATS = ("I420", "YV12", "NV12", "NV21", "AYUV", "Y42B", "Y444", "YUY2", "UYVY", "GRAY8")
+YUV_FORMATS = ("I420", "YV12", "NV12", "NV21", "AYUV", "Y42B", "Y444", "YUY2", "UYVY", "GRAY8", "NV16", "NV24")
 PLANAR_420 = ("I420", "YV12", "NV12", "NV21")
-MORE_YUV = ("Y42B", "Y444", "YUY2", "UYVY", "GRAY8")       # byte-plane formats beyond 4:2:0
+MORE_YUV = ("Y42B", "Y444", "YUY2", "UYVY", "GRAY8", "NV16", "NV24")       # byte-plane formats beyond 4:2:0
 PACKED = ("AYUV", "ARGB", "ABGR", "RGBA", "BGRA")
 ALL_FORMATS = PLANAR_420 + PACKED + MORE_YUV
 
@@ -28,6 +28,10 @@ def yuv_views(fmt, planes, w):
         return planes[0], planes[1][:, 0::2], planes[1][:, 1::2], 2, 2
     if fmt == "NV21":
         return planes[0], planes[1][:, 1::2], planes[1][:, 0::2], 2, 2
+    if fmt == "NV16":
+        return planes[0], planes[1][:, 0::2], planes[1][:, 1::2], 2, 1
+    if fmt == "NV24":
+        return planes[0], planes[1][:, 0::2], planes[1][:, 1::2], 1, 1
     if fmt == "YUY2":
         return planes[0][:, 0::2][:, :w], planes[0][:, 1::4], planes[0][:, 3::4], 2, 1
     if fmt == "UYVY":
