@@ -1,0 +1,119 @@
+/*
+ * test_hooks.cu -- C entry points into the HOST logic of the runtime (no GPU work), built
+ * into a separate libfluc_ttmlblend_testhooks.so for the CPU test-suite only: the job
+ * builder (bands, windows, classes, groups), the region-box decomposition and the
+ * row-run crop. Never linked into libfluc_ttmlblend.so.
+ */
+#include "ttmlblend_internal.h"
+
+using namespace tbh;
+
+extern "C" {
+
+/* One prepared rectangle as the job builder sees it on one plane. */
+struct TbHookRect { int32_t v0, v1, y0, y1; };
+
+/* One job back: window, class, mask and flags. */
+struct TbHookJob {
+  int32_t plane, cls, flags;
+  int32_t win_v0, win_nv, win_y0, win_rows;
+  uint32_t n_chunks, div_magic;
+  uint64_t rect_mask;
+  int32_t one_rect;
+  int32_t grouped;              /* ended up in the band list of a group launch */
+};
+
+/* Runs build_jobs (+ make_groupable) for a frame whose planes sit at fake, 16-byte aligned
+ * (or, with `misalign`, odd) addresses. rects[p] / n_rects[p]: prepared rectangles of plane p.
+ * Returns the number of jobs written (<= max_jobs), or -1. *algo_bytes gets the byte count. */
+__attribute__ ((visibility ("default"))) int
+tb_hook_build_jobs (int format, int W, int H, int windowed, int misalign,
+    const TbHookRect *rects0, int n0, const TbHookRect *rects1, int n1, const TbHookRect *rects2, int n2,
+    TbHookJob *out, int max_jobs, uint64_t *algo_bytes, uint32_t *chunks_per_frame)
+{
+  if (!format_valid (format))
+    return -1;
+  format = format_canon (format);
+  Prepared prep;
+  prep.format = format;
+  prep.W = W;
+  prep.H = H;
+  const TbHookRect *rr[3] = { rects0, rects1, rects2 };
+  const int nn[3] = { n0, n1, n2 };
+  static RectRef fake_table[3 * 64];
+  for (int pl = 0; pl < 3; pl++) {
+    for (int i = 0; i < nn[pl]; i++) {
+      RectRef r = {};
+      r.v0 = rr[pl][i].v0; r.v1 = rr[pl][i].v1; r.y0 = rr[pl][i].y0; r.y1 = rr[pl][i].y1;
+      r.pitch = (r.v1 - r.v0) * 16;
+      r.ga = 255;
+      prep.h_rects[pl].push_back (r);
+    }
+    prep.d_rects[pl] = fake_table + 64 * pl;
+    prep.rect_off[pl] = 64 * pl;
+  }
+  prep.d_rects_all = fake_table;
+  FlucTtmlBlendFrame src = {}, dst = {};
+  uintptr_t base = 0x10000000u + (misalign ? 4 : 0);
+  for (int pl = 0; pl < format_planes (format); pl++) {
+    const int stride = (int) align_up ((size_t) plane_row_bytes (format, pl, W), 256) + (misalign ? 4 : 0);
+    src.plane[pl] = (void *) base;
+    src.stride[pl] = stride;
+    dst.plane[pl] = (void *) (windowed ? base : base + 0x40000000u);
+    dst.stride[pl] = stride;
+    base += (uintptr_t) stride * plane_rows (format, pl, H) + 4096;
+  }
+  PendingFrame f;
+  f.kind = plane_kind (format);
+  f.prep = &prep;
+  f.algo_bytes = build_jobs (format, W, H, 0, &src, &dst, &prep, windowed != 0, f.jobs);
+  std::vector<PlaneJob> all = f.jobs;
+  make_groupable (f, &src, &dst);
+  if (algo_bytes)
+    *algo_bytes = f.algo_bytes;
+  if (chunks_per_frame)
+    *chunks_per_frame = f.grouped ? f.chunks_per_frame : 0;
+  int n = 0;
+  for (const PlaneJob &j : all) {
+    if (n >= max_jobs)
+      return -1;
+    TbHookJob &o = out[n++];
+    o.plane = j.plane; o.cls = j.cls; o.flags = j.flags;
+    o.win_v0 = j.win_v0; o.win_nv = j.win_nv; o.win_y0 = j.win_y0; o.win_rows = j.win_rows;
+    o.n_chunks = j.n_chunks; o.div_magic = j.div_magic;
+    o.rect_mask = j.rect_mask; o.one_rect = j.one_rect;
+    o.grouped = (f.grouped && (j.flags & JF_FAST)) ? 1 : 0;
+  }
+  return n;
+}
+
+__attribute__ ((visibility ("default"))) int
+tb_hook_disjoint_cover (const FlucTtmlBlendRect *in, int n, FlucTtmlBlendRect *out, int max_out)
+{
+  std::vector<FlucTtmlBlendRect> v (in, in + n);
+  std::vector<FlucTtmlBlendRect> r = disjoint_cover (v);
+  if ((int) r.size () > max_out)
+    return -1;
+  for (size_t i = 0; i < r.size (); i++)
+    out[i] = r[i];
+  return (int) r.size ();
+}
+
+/* spans: (first, last) non-transparent x per row, (w, -1) for an empty row */
+__attribute__ ((visibility ("default"))) int
+tb_hook_crop_runs (const int32_t *first, const int32_t *last, int rows, int min_gap, int max_runs,
+    FlucTtmlBlendRect *out, int max_out)
+{
+  std::vector<int2> spans (rows);
+  for (int i = 0; i < rows; i++)
+    spans[i] = make_int2 (first[i], last[i]);
+  std::vector<FlucTtmlBlendRect> r;
+  crop_runs (spans, min_gap, (size_t) max_runs, r);
+  if ((int) r.size () > max_out)
+    return -1;
+  for (size_t i = 0; i < r.size (); i++)
+    out[i] = r[i];
+  return (int) r.size ();
+}
+
+}  /* extern "C" */
