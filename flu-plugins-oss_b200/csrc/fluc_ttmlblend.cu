@@ -256,7 +256,7 @@ fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream, const uint8_t 
     return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
   std::vector<FlucTtmlBlendRectangle> rr;
   for (auto &r : in) {
-    FlucTtmlBlendRectangle q;
+    FlucTtmlBlendRectangle q = {};
     q.pixels = bgra + (size_t) r.y * stride + (size_t) r.x * 4;
     q.width = r.w;
     q.height = r.h;

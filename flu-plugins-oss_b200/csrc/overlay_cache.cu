@@ -427,6 +427,39 @@ finish_install (Ctx *c, uint32_t stream, std::shared_ptr<Overlay> ov, std::vecto
   return 0;
 }
 
+/* gst_video_blend_scale_linear_RGBA's vertical pass, row by row: upstream keeps the
+ * horizontally resampled source lines in a two-line cache (slot = row & 1) and tracks with
+ * `y1` how far it has resampled. Simulating that bookkeeping here gives, for every
+ * destination row, the two source rows and the 8-bit weight the kernel merges -- including
+ * the rows where the cache holds something else than rows j and j+1 (docs/BLENDSPEC.md
+ * section 10). */
+std::vector<int4>
+scale_row_plan (int src_h, int dst_h)
+{
+  const int y_inc = dst_h == 1 ? 0 : ((src_h - 1) << 16) / (dst_h - 1) - 1;
+  int slot[2] = { 0, 0 };
+  int y1 = 0, acc = 0;
+  std::vector<int4> plan ((size_t) dst_h);
+  for (int i = 0; i < dst_h; i++) {
+    const int j = acc >> 16, x = acc & 0xffff;
+    if (x == 0) {
+      plan[i] = make_int4 (slot[j & 1], slot[j & 1], 0, 0);       /* memcpy of LINE (j) */
+    } else {
+      if (j > y1) {
+        slot[j & 1] = j;
+        y1++;
+      }
+      if (j >= y1) {
+        slot[(j + 1) & 1] = j + 1;
+        y1++;
+      }
+      plan[i] = make_int4 (slot[j & 1], slot[(j + 1) & 1], x >> 8, 0);
+    }
+    acc += y_inc;
+  }
+  return plan;
+}
+
 int
 overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n)
 {
@@ -434,32 +467,64 @@ overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, u
   std::shared_ptr<Overlay> ov (new Overlay ());
   ov->ctx = c;
   std::vector<Up> ups;
+  std::vector<std::vector<int4>> plans;     /* host side of async uploads: alive until finish_install */
   for (uint32_t i = 0; i < n; i++) {
     const FlucTtmlBlendRectangle &r = rects[i];
-    if (!r.pixels || r.width <= 0 || r.height <= 0 || r.stride < r.width * 4)
+    if (!r.pixels || r.width <= 0 || r.height <= 0 || r.stride < r.width * 4 || r.render_width < 0 ||
+        r.render_height < 0 || r.render_width > 32768 || r.render_height > 32768)
       return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+    /* gst_video_overlay_rectangle_needs_scaling: render size != pixel size */
+    const int rw = r.render_width ? r.render_width : r.width, rh = r.render_height ? r.render_height : r.height;
+    const bool scaled = rw != r.width || rh != r.height;
+    if (scaled && (r.width < 2 || r.height < 2))
+      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;   /* upstream reads outside the image here */
     /* gst_video_blend: negative offsets skip source columns / rows */
     const int xoff = r.x < 0 ? -r.x : 0, yoff = r.y < 0 ? -r.y : 0;
-    if (xoff >= r.width || yoff >= r.height)
+    if (xoff >= rw || yoff >= rh)
       continue;
     Up u;
     RawRect &rr = u.rr;
-    rr.w = r.width - xoff;
-    rr.h = r.height - yoff;
+    rr.w = rw - xoff;
+    rr.h = rh - yoff;
     rr.x = r.x + xoff;
     rr.y = r.y + yoff;
     rr.ga = (int) (255.0 * r.global_alpha);
     rr.ga = std::max (0, std::min (255, rr.ga));
     rr.premul = (r.flags & FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA) != 0;
-    rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
     ov->declared.push_back ({ rr.x, rr.y, rr.w, rr.h });
-    void *d = nullptr;
-    CU (c, cudaMallocAsync (&d, (size_t) rr.pitch * rr.h, c->up_stream));
-    ov->raw_allocs.push_back (d);
-    rr.dev = static_cast<uint8_t *> (d);
-    CU (c, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
-            r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
-    c->stats.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+    if (!scaled) {
+      rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
+      void *d = nullptr;
+      CU (c, cudaMallocAsync (&d, (size_t) rr.pitch * rr.h, c->up_stream));
+      ov->raw_allocs.push_back (d);
+      rr.dev = static_cast<uint8_t *> (d);
+      CU (c, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
+              r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
+      c->stats.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+    } else {
+      /* the whole source goes up, is scaled to the render size on the GPU, and the clipped
+       * part of the scaled image is what gets blended */
+      const int sp = (int) align_up ((size_t) r.width * 4, 256);
+      void *s = nullptr, *d = nullptr, *p = nullptr;
+      CU (c, cudaMallocAsync (&s, (size_t) sp * r.height, c->up_stream));
+      CU (c, cudaMemcpy2DAsync (s, sp, r.pixels, r.stride, (size_t) r.width * 4, r.height,
+              cudaMemcpyHostToDevice, c->up_stream));
+      c->stats.h2d_bytes += (uint64_t) r.width * 4 * r.height;
+      plans.push_back (scale_row_plan (r.height, rh));
+      CU (c, cudaMallocAsync (&p, (size_t) rh * sizeof (int4), c->up_stream));
+      CU (c, cudaMemcpyAsync (p, plans.back ().data (), (size_t) rh * sizeof (int4), cudaMemcpyHostToDevice,
+              c->up_stream));
+      rr.pitch = (int) align_up ((size_t) rw * 4, 256);
+      CU (c, cudaMallocAsync (&d, (size_t) rr.pitch * rh, c->up_stream));
+      ov->raw_allocs.push_back (d);
+      const int x_inc = rw == 1 ? 0 : ((r.width - 1) << 16) / (rw - 1) - 1;
+      CU (c, launch_scale (static_cast<const uint8_t *> (s), sp, static_cast<const int4 *> (p), x_inc,
+              static_cast<uint8_t *> (d), rr.pitch, rw, rh, c->up_stream));
+      c->stats.prepare_launches++;
+      CU (c, cudaFreeAsync (s, c->up_stream));
+      CU (c, cudaFreeAsync (p, c->up_stream));
+      rr.dev = static_cast<uint8_t *> (d) + (size_t) yoff * rr.pitch + (size_t) xoff * 4;
+    }
     int rc = scan_rows (c, u);
     if (rc)
       return rc;

@@ -1,8 +1,8 @@
 /*
  * test_hooks.cu -- C entry points into the HOST logic of the runtime (no GPU work), built
  * into a separate libfluc_ttmlblend_testhooks.so for the CPU test-suite only: the job
- * builder (bands, windows, classes, groups), the region-box decomposition and the
- * row-run crop. Never linked into libfluc_ttmlblend.so.
+ * builder (bands, windows, classes, groups), the region-box decomposition, the
+ * row-run crop and the row plan of the rectangle scaler. Never linked into libfluc_ttmlblend.so.
  */
 #include "ttmlblend_internal.h"
 
@@ -114,6 +114,21 @@ tb_hook_crop_runs (const int32_t *first, const int32_t *last, int rows, int min_
   for (size_t i = 0; i < r.size (); i++)
     out[i] = r[i];
   return (int) r.size ();
+}
+
+/* rows[3*i..] = (source row a, source row b, weight) of destination row i */
+__attribute__ ((visibility ("default"))) int
+tb_hook_scale_row_plan (int src_h, int dst_h, int32_t *rows)
+{
+  if (src_h < 2 || dst_h < 1)
+    return -1;
+  const std::vector<int4> plan = scale_row_plan (src_h, dst_h);
+  for (size_t i = 0; i < plan.size (); i++) {
+    rows[3 * i] = plan[i].x;
+    rows[3 * i + 1] = plan[i].y;
+    rows[3 * i + 2] = plan[i].z;
+  }
+  return (int) plan.size ();
 }
 
 }  /* extern "C" */

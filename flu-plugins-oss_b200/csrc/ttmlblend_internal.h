@@ -342,6 +342,7 @@ struct NvtxRange {
 void free_deferred (Ctx *c, const std::vector<void *> &ptrs);
 int prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out);
 std::vector<FlucTtmlBlendRect> disjoint_cover (const std::vector<FlucTtmlBlendRect> &in);
+std::vector<int4> scale_row_plan (int src_h, int dst_h);
 void crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, std::vector<FlucTtmlBlendRect> &out);
 int overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n);
 int overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTtmlBlendRegion *regions, uint32_t n);

@@ -1093,6 +1093,58 @@ launch_blur (const uint8_t *src, int w, int h, int src_pitch, const int32_t *tap
 }
 
 /* ---------------------------------------------------------------------- */
+/* Rectangle scaling, once per cue: gst_video_blend_scale_linear_RGBA (docs/BLENDSPEC.md
+ * section 10). One thread per destination pixel. Horizontally, ORC's bilinear resample of
+ * the two source pixels under 16.16 position x * x_inc with an 8-bit fraction,
+ * (a*(256-f) + b*f) >> 8 per byte; vertically, ORC's merge of two such lines,
+ * a + (((b-a)*w + 128) >> 8). Which two source rows and which weight a destination row
+ * uses comes from the host (`rows`: upstream's two-line cache simulated row by row), so the
+ * kernel is stateless. */
+
+__device__ __forceinline__ uint32_t
+scale_mix_h (uint32_t a, uint32_t b, uint32_t f)
+{
+  /* two bytes per multiply: (a & 0x00ff00ff) * (256-f) stays below 2^16 per lane */
+  const uint32_t g = 256u - f;
+  const uint32_t lo = ((a & 0x00ff00ffu) * g + (b & 0x00ff00ffu) * f) >> 8;
+  const uint32_t hi = (((a >> 8) & 0x00ff00ffu) * g + ((b >> 8) & 0x00ff00ffu) * f) >> 8;
+  return (lo & 0x00ff00ffu) | ((hi & 0x00ff00ffu) << 8);
+}
+
+__global__ void __launch_bounds__ (256)
+ttmlblend_scale_kernel (const uint8_t *__restrict__ src, int src_pitch, const int4 *__restrict__ rows,
+    int x_inc, uint8_t *__restrict__ dst, int dst_pitch, int dw, int dh)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw || y >= dh)
+    return;
+  const int4 r = __ldg (&rows[y]);                /* row a, row b, weight */
+  const int tmp = x * x_inc;
+  const int sx = tmp >> 16;
+  const uint32_t f = (uint32_t) (tmp >> 8) & 0xffu;
+  const uint32_t *ra = reinterpret_cast<const uint32_t *> (src + (size_t) r.x * src_pitch) + sx;
+  const uint32_t *rb = reinterpret_cast<const uint32_t *> (src + (size_t) r.y * src_pitch) + sx;
+  const uint32_t a = scale_mix_h (__ldg (ra), __ldg (ra + 1), f);
+  const uint32_t b = scale_mix_h (__ldg (rb), __ldg (rb + 1), f);
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int ca = (int) ((a >> k) & 0xffu), cb = (int) ((b >> k) & 0xffu);
+    out |= (uint32_t) ((ca + (((cb - ca) * r.z + 128) >> 8)) & 0xff) << k;
+  }
+  reinterpret_cast<uint32_t *> (dst + (size_t) y * dst_pitch)[x] = out;
+}
+
+cudaError_t
+launch_scale (const uint8_t *src, int src_pitch, const int4 *rows, int x_inc, uint8_t *dst, int dst_pitch,
+    int dw, int dh, cudaStream_t stream)
+{
+  dim3 grid ((unsigned) ((dw + 255) / 256), (unsigned) dh);
+  ttmlblend_scale_kernel<<<grid, 256, 0, stream>>> (src, src_pitch, rows, x_inc, dst, dst_pitch, dw, dh);
+  return cudaGetLastError ();
+}
+
+/* ---------------------------------------------------------------------- */
 
 __global__ void
 ttmlblend_scrub_kernel (uint4 *buf, size_t n_vec, uint32_t seed)

@@ -184,6 +184,10 @@ cudaError_t launch_blur (const uint8_t *src, int w, int h, int src_pitch, const 
     uint8_t *dst, int dst_pitch, cudaStream_t stream);
 /* spans[y] = first / last x of row y with alpha != 0, (w, -1) for an empty row. */
 cudaError_t launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaStream_t stream);
+/* gst_video_blend_scale_linear_RGBA: rows[y] = (source row a, source row b, 8-bit weight, 0),
+ * x_inc = the 16.16 horizontal increment; src needs dw's last position + 1 < its width. */
+cudaError_t launch_scale (const uint8_t *src, int src_pitch, const int4 *rows, int x_inc, uint8_t *dst,
+    int dst_pitch, int dw, int dh, cudaStream_t stream);
 
 }  // namespace tb
 #endif

@@ -16,6 +16,7 @@ struct _FlucVideoOverlayRectangle {
   uint8_t *pixels;
   int32_t width, height, stride;
   int32_t x, y;
+  int32_t render_width, render_height;
   float global_alpha;
   uint32_t flags;
 };
@@ -78,11 +79,13 @@ fluc_video_overlay_deinit (void)
 
 FlucVideoOverlayRectangle *
 fluc_video_overlay_rectangle_new_raw (const uint8_t *pixels, int32_t width, int32_t height,
-    int32_t stride, int32_t render_x, int32_t render_y, uint32_t flags)
+    int32_t stride, int32_t render_x, int32_t render_y, uint32_t render_width, uint32_t render_height,
+    uint32_t flags)
 {
   FlucVideoOverlayRectangle *r;
   int32_t y;
-  if (!pixels || width <= 0 || height <= 0 || stride < width * 4)
+  if (!pixels || width <= 0 || height <= 0 || stride < width * 4 || render_width > 32768 ||
+      render_height > 32768)
     return NULL;
   r = (FlucVideoOverlayRectangle *) calloc (1, sizeof (*r));
   if (!r)
@@ -100,6 +103,8 @@ fluc_video_overlay_rectangle_new_raw (const uint8_t *pixels, int32_t width, int3
   r->stride = width * 4;
   r->x = render_x;
   r->y = render_y;
+  r->render_width = render_width ? (int32_t) render_width : width;
+  r->render_height = render_height ? (int32_t) render_height : height;
   r->global_alpha = 1.0f;
   r->flags = flags;
   return r;
@@ -137,11 +142,13 @@ fluc_video_overlay_rectangle_get_global_alpha (FlucVideoOverlayRectangle *rect)
 
 void
 fluc_video_overlay_rectangle_set_render_rectangle (FlucVideoOverlayRectangle *rect, int32_t render_x,
-    int32_t render_y)
+    int32_t render_y, uint32_t render_width, uint32_t render_height)
 {
-  if (rect) {
+  if (rect && render_width <= 32768 && render_height <= 32768) {
     rect->x = render_x;
     rect->y = render_y;
+    rect->render_width = render_width ? (int32_t) render_width : rect->width;
+    rect->render_height = render_height ? (int32_t) render_height : rect->height;
   }
 }
 
@@ -228,6 +235,8 @@ fluc_video_overlay_composition_blend (FlucVideoOverlayComposition *comp, FlucVid
       rr[n].stride = r->stride;
       rr[n].x = r->x;
       rr[n].y = r->y;
+      rr[n].render_width = r->render_width;      /* != pixel size: scaled on the GPU first */
+      rr[n].render_height = r->render_height;
       rr[n].global_alpha = r->global_alpha;
       rr[n].flags = (r->flags & FLUC_VIDEO_OVERLAY_FORMAT_FLAG_PREMULTIPLIED_ALPHA) ?
           FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA : 0;

@@ -45,16 +45,19 @@ typedef struct {
   int32_t stride[3];
 } FlucVideoFrame;
 
-/* The pixels are copied; render size == pixel size (no scaling). */
+/* The pixels are copied (GStreamer takes a GstBuffer + video meta: pixels, width, height,
+ * stride stand in for it). render_width / render_height as in GStreamer; 0 = pixel size.
+ * A render size that differs from the pixel size makes the composition scale the rectangle
+ * (gst_video_blend_scale_linear_RGBA semantics, on the GPU, once). */
 FLUC_EXPORT FlucVideoOverlayRectangle *fluc_video_overlay_rectangle_new_raw (
     const uint8_t *bgra_pixels, int32_t width, int32_t height, int32_t stride,
-    int32_t render_x, int32_t render_y, uint32_t flags);
+    int32_t render_x, int32_t render_y, uint32_t render_width, uint32_t render_height, uint32_t flags);
 FLUC_EXPORT FlucVideoOverlayRectangle *fluc_video_overlay_rectangle_ref (FlucVideoOverlayRectangle *rect);
 FLUC_EXPORT void fluc_video_overlay_rectangle_unref (FlucVideoOverlayRectangle *rect);
 FLUC_EXPORT void fluc_video_overlay_rectangle_set_global_alpha (FlucVideoOverlayRectangle *rect, float global_alpha);
 FLUC_EXPORT float fluc_video_overlay_rectangle_get_global_alpha (FlucVideoOverlayRectangle *rect);
 FLUC_EXPORT void fluc_video_overlay_rectangle_set_render_rectangle (FlucVideoOverlayRectangle *rect,
-    int32_t render_x, int32_t render_y);
+    int32_t render_x, int32_t render_y, uint32_t render_width, uint32_t render_height);
 
 FLUC_EXPORT FlucVideoOverlayComposition *fluc_video_overlay_composition_new (FlucVideoOverlayRectangle *rect);
 FLUC_EXPORT void fluc_video_overlay_composition_add_rectangle (FlucVideoOverlayComposition *comp,

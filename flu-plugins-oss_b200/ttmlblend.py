@@ -47,7 +47,8 @@ class Rect(C.Structure):
 class Rectangle(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32),
                 ("stride", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
-                ("global_alpha", C.c_float), ("flags", C.c_uint32)]
+                ("global_alpha", C.c_float), ("flags", C.c_uint32),
+                ("render_width", C.c_int32), ("render_height", C.c_int32)]
 
 
 class Region(C.Structure):
@@ -274,7 +275,8 @@ class TtmlBlend:
 
     def overlay_set_rectangles(self, stream: int, rectangles: Sequence[dict]):
         """GstVideoOverlayComposition form. Each dict: pixels (h x w x 4 uint8 BGRA), x, y,
-        global_alpha (default 1.0), premultiplied (default True)."""
+        global_alpha (default 1.0), premultiplied (default True), render_width / render_height
+        (default: the pixel size; anything else is scaled like GStreamer does before blending)."""
         n = len(rectangles)
         arr = (Rectangle * max(1, n))()
         for i, r in enumerate(rectangles):
@@ -283,7 +285,8 @@ class TtmlBlend:
             arr[i] = Rectangle(px.ctypes.data, px.shape[1], px.shape[0], px.strides[0],
                                int(r.get("x", 0)), int(r.get("y", 0)),
                                float(r.get("global_alpha", 1.0)),
-                               FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0)
+                               FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0,
+                               int(r.get("render_width", 0)), int(r.get("render_height", 0)))
         self._check(self.lib.fluc_ttmlblend_overlay_set_rectangles(self.h, stream, arr, n),
                     "overlay_set_rectangles")
 

@@ -26,12 +26,14 @@ class VideoFrame(C.Structure):
 
 PROTOTYPES = {
     "fluc_video_overlay_rectangle_new_raw": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                                          C.c_int32, C.c_int32, C.c_uint32]),
+                                                          C.c_int32, C.c_int32, C.c_uint32, C.c_uint32,
+                                                          C.c_uint32]),
     "fluc_video_overlay_rectangle_ref": (C.c_void_p, [C.c_void_p]),
     "fluc_video_overlay_rectangle_unref": (None, [C.c_void_p]),
     "fluc_video_overlay_rectangle_set_global_alpha": (None, [C.c_void_p, C.c_float]),
     "fluc_video_overlay_rectangle_get_global_alpha": (C.c_float, [C.c_void_p]),
-    "fluc_video_overlay_rectangle_set_render_rectangle": (None, [C.c_void_p, C.c_int32, C.c_int32]),
+    "fluc_video_overlay_rectangle_set_render_rectangle": (None, [C.c_void_p, C.c_int32, C.c_int32,
+                                                                 C.c_uint32, C.c_uint32]),
     "fluc_video_overlay_composition_new": (C.c_void_p, [C.c_void_p]),
     "fluc_video_overlay_composition_add_rectangle": (None, [C.c_void_p, C.c_void_p]),
     "fluc_video_overlay_composition_n_rectangles": (C.c_uint32, [C.c_void_p]),
@@ -61,11 +63,13 @@ def load_library():
 
 
 class Rectangle:
-    def __init__(self, pixels: np.ndarray, x: int, y: int, flags: int = FLAG_PREMULTIPLIED_ALPHA):
+    def __init__(self, pixels: np.ndarray, x: int, y: int, flags: int = FLAG_PREMULTIPLIED_ALPHA,
+                 render_width: int = 0, render_height: int = 0):
         assert pixels.dtype == np.uint8 and pixels.ndim == 3 and pixels.shape[2] == 4
         self.lib = load_library()
         self.h = self.lib.fluc_video_overlay_rectangle_new_raw(
-            pixels.ctypes.data, pixels.shape[1], pixels.shape[0], pixels.strides[0], x, y, flags)
+            pixels.ctypes.data, pixels.shape[1], pixels.shape[0], pixels.strides[0], x, y,
+            render_width, render_height, flags)
         if not self.h:
             raise ValueError("fluc_video_overlay_rectangle_new_raw returned NULL")
 
@@ -74,6 +78,9 @@ class Rectangle:
 
     def get_global_alpha(self) -> float:
         return self.lib.fluc_video_overlay_rectangle_get_global_alpha(self.h)
+
+    def set_render_rectangle(self, x: int, y: int, render_width: int = 0, render_height: int = 0):
+        self.lib.fluc_video_overlay_rectangle_set_render_rectangle(self.h, x, y, render_width, render_height)
 
     def __del__(self):
         if getattr(self, "h", None):

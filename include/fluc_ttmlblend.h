@@ -106,15 +106,19 @@ typedef struct {
   int32_t x, y, w, h;
 } FlucTtmlBlendRect;
 
-/* One overlay rectangle = GstVideoOverlayRectangle with render size equal to
- * its pixel size: BGRA bytes (ARGB32 little endian), position, global alpha,
- * premultiplied flag. */
+/* One overlay rectangle = GstVideoOverlayRectangle: BGRA bytes (ARGB32 little
+ * endian), position, global alpha, premultiplied flag, render size. ttmlrender's
+ * image is rendered at its pixel size (render_width = render_height = 0); a
+ * rectangle with another render size is first scaled on the GPU exactly as
+ * gst_video_overlay_composition_blend does with gst_video_blend_scale_linear_RGBA
+ * (once per cue, cached like everything else); its pixel size must then be >= 2x2. */
 typedef struct {
   const uint8_t *pixels;   /* host memory, read before the call returns */
   int32_t width, height, stride;
   int32_t x, y;
   float global_alpha;      /* 1.0f for ttmlrender */
   uint32_t flags;          /* FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA */
+  int32_t render_width, render_height;   /* 0 = width / height (no scaling) */
 } FlucTtmlBlendRectangle;
 
 /* Plane pointers + strides of one frame (GstVideoFrame data[]/stride[]).

@@ -30,7 +30,8 @@ class RefFrame(C.Structure):
 class RefRectangle(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32),
                 ("stride", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
-                ("global_alpha", C.c_float), ("flags", C.c_uint32)]
+                ("global_alpha", C.c_float), ("flags", C.c_uint32),
+                ("render_width", C.c_int32), ("render_height", C.c_int32)]
 
 
 class RefRegion(C.Structure):
@@ -74,6 +75,9 @@ def load(native: bool = False, out_dir: str = None):
     lib.tbref_blur_argb32.restype = None
     lib.tbref_blur_argb32.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_void_p, C.c_int32]
+    lib.tbref_scale_linear_rgba.restype = None
+    lib.tbref_scale_linear_rgba.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p]
     for n in ("tbref_matrix_prea_rgb_to_yuv", "tbref_matrix_rgb_to_yuv", "tbref_matrix_yuv_to_rgb"):
         getattr(lib, n).restype = None
         getattr(lib, n).argtypes = [C.c_void_p, C.c_uint32]
@@ -103,7 +107,8 @@ def make_rectangles(rectangles: Sequence[dict]):
         arr[i] = RefRectangle(px.ctypes.data, px.shape[1], px.shape[0], px.strides[0],
                               int(r.get("x", 0)), int(r.get("y", 0)),
                               float(r.get("global_alpha", 1.0)),
-                              FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0)
+                              FLAG_PREMULTIPLIED_ALPHA if r.get("premultiplied", True) else 0,
+                              int(r.get("render_width", 0)), int(r.get("render_height", 0)))
     return arr
 
 
@@ -124,6 +129,17 @@ def ttmlrender_rectangles(bgra: np.ndarray, rects: Sequence[Sequence[int]] = ())
     premultiplied rectangle at (0,0); `rects` is ignored on purpose (the region boxes only
     tell the GPU path where non-transparent pixels can be)."""
     return [dict(pixels=bgra, x=0, y=0, global_alpha=1.0, premultiplied=True)]
+
+
+def scale_linear_rgba(img: np.ndarray, dest_width: int, dest_height: int, lib=None) -> np.ndarray:
+    """gst_video_blend_scale_linear_RGBA on an h x w x 4 uint8 image (h, w >= 2)."""
+    lib = lib or load()
+    assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 4 and img.strides[2] == 1
+    assert img.shape[0] >= 2 and img.shape[1] >= 2
+    out = np.empty((dest_height, dest_width, 4), np.uint8)
+    lib.tbref_scale_linear_rgba(img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                dest_width, dest_height, out.ctypes.data)
+    return out
 
 
 def blur_argb32(img: np.ndarray, radius: int, sigma: float, lib=None) -> np.ndarray:

@@ -618,14 +618,111 @@ tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src)
   return 1;
 }
 
+/* ---------------------------------------------------------------------- */
+/* rectangle scaling: gst_video_blend_scale_linear_RGBA (video-blend.c) with
+ * the two ORC programs it calls (video-orc.orc) [UPSTREAM-RECALL]            */
+
+/* video_orc_resample_bilinear_u32 (d, s, p1, p2, n) = ORC `ldreslinl`: for every
+ * destination pixel tmp = p1 + i*p2; the two source pixels tmp>>16 and (tmp>>16)+1 are
+ * mixed per byte with the 8-bit fraction (tmp>>8)&255: (a*(256-f) + b*f) >> 8. The second
+ * pixel is read even when f == 0. */
+static void
+orc_resample_bilinear_u32 (uint8_t *d, const uint8_t *s, int p1, int p2, int n)
+{
+  int i, k;
+  for (i = 0; i < n; i++) {
+    const int tmp = p1 + i * p2;
+    const uint8_t *a = s + 4 * (tmp >> 16), *b = a + 4;
+    const int f = (tmp >> 8) & 0xff;
+    for (k = 0; k < 4; k++)
+      d[4 * i + k] = (uint8_t) ((a[k] * (256 - f) + b[k] * f) >> 8);
+  }
+}
+
+/* video_orc_merge_linear_u8 (d, s1, s2, p1, n): convubw both, subw, mullw by p1, addw 128,
+ * convhwb (high byte of the 16-bit word), addb s1 -- all wrapping, which for 8-bit inputs
+ * equals s1 + floor (((s2 - s1)*p1 + 128) / 256). */
+static void
+orc_merge_linear_u8 (uint8_t *d, const uint8_t *s1, const uint8_t *s2, int p1, int n)
+{
+  int i;
+  for (i = 0; i < n; i++) {
+    const uint16_t t = (uint16_t) ((uint16_t) ((uint16_t) s2[i] - (uint16_t) s1[i]) * (uint16_t) p1 + 128u);
+    d[i] = (uint8_t) (s1[i] + (uint8_t) (t >> 8));
+  }
+}
+
+/* gst_video_blend_scale_linear_RGBA: horizontally resampled source lines are kept in a
+ * two-line cache (LINE (n) = slot n & 1) and merged vertically. The cache bookkeeping (y1)
+ * is restated as upstream has it, including what it does when the row index jumps. A
+ * source that is 1 pixel wide or high makes upstream read outside the image (increment -1);
+ * the callers here reject that case. dst is tightly packed (stride dest_width*4). */
+void
+tbref_scale_linear_rgba (const uint8_t *src_pixels, int32_t src_width, int32_t src_height,
+    int32_t src_stride, int32_t dest_width, int32_t dest_height, uint8_t *dest_pixels)
+{
+  int acc = 0, y_increment, x_increment, y1 = 0, i, j, x;
+  const int dest_size = dest_width * 4, dest_stride = dest_width * 4;
+  uint8_t *tmpbuf = (uint8_t *) malloc ((size_t) dest_width * 8 * 4);
+#define LINE(n) (tmpbuf + (size_t) dest_size * ((n) & 1))
+
+  y_increment = dest_height == 1 ? 0 : ((src_height - 1) << 16) / (dest_height - 1) - 1;
+  x_increment = dest_width == 1 ? 0 : ((src_width - 1) << 16) / (dest_width - 1) - 1;
+
+  orc_resample_bilinear_u32 (LINE (0), src_pixels, 0, x_increment, dest_width);
+  for (i = 0; i < dest_height; i++) {
+    j = acc >> 16;
+    x = acc & 0xffff;
+    if (x == 0) {
+      memcpy (dest_pixels + (size_t) i * dest_stride, LINE (j), (size_t) dest_size);
+    } else {
+      if (j > y1) {
+        orc_resample_bilinear_u32 (LINE (j), src_pixels + (size_t) j * src_stride, 0, x_increment, dest_width);
+        y1++;
+      }
+      if (j >= y1) {
+        orc_resample_bilinear_u32 (LINE (j + 1), src_pixels + (size_t) (j + 1) * src_stride, 0, x_increment,
+            dest_width);
+        y1++;
+      }
+      orc_merge_linear_u8 (dest_pixels + (size_t) i * dest_stride, LINE (j), LINE (j + 1), x >> 8, dest_width * 4);
+    }
+    acc += y_increment;
+  }
+#undef LINE
+  free (tmpbuf);
+}
+
+/* gst_video_overlay_composition_blend: rectangles in list order; one whose render size
+ * differs from its pixel size (gst_video_overlay_rectangle_needs_scaling) is scaled first. */
 int
 tbref_composition_blend (TbRefFrame *dest, const TbRefRectangle *rects,
     uint32_t n_rects)
 {
   uint32_t n;
   int ret = 1;
-  for (n = 0; n < n_rects; n++)
-    ret = tbref_video_blend (dest, &rects[n]);
+  for (n = 0; n < n_rects; n++) {
+    const TbRefRectangle *r = &rects[n];
+    const int32_t rw = r->render_width > 0 ? r->render_width : r->width;
+    const int32_t rh = r->render_height > 0 ? r->render_height : r->height;
+    if (rw != r->width || rh != r->height) {
+      TbRefRectangle scaled = *r;
+      uint8_t *px;
+      if (r->width < 2 || r->height < 2)
+        return 0;                   /* upstream reads out of bounds here */
+      px = (uint8_t *) malloc ((size_t) rw * 4 * (size_t) rh);
+      tbref_scale_linear_rgba (r->pixels, r->width, r->height, r->stride, rw, rh, px);
+      scaled.pixels = px;
+      scaled.width = rw;
+      scaled.height = rh;
+      scaled.stride = rw * 4;
+      scaled.render_width = scaled.render_height = 0;
+      ret = tbref_video_blend (dest, &scaled);
+      free (px);
+    } else {
+      ret = tbref_video_blend (dest, r);
+    }
+  }
   return ret;
 }
 

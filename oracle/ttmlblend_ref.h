@@ -61,13 +61,14 @@ typedef struct {
   int32_t stride[3];
 } TbRefFrame;
 
-/* Shape of a GstVideoOverlayRectangle with render size == pixel size. */
+/* Shape of a GstVideoOverlayRectangle. */
 typedef struct {
   const uint8_t *pixels;   /* BGRA byte order (ARGB32 little endian) */
   int32_t width, height, stride;
   int32_t x, y;            /* position in the frame; may be negative */
   float global_alpha;      /* 1.0 in every ttmlrender use */
   uint32_t flags;          /* TBREF_FLAG_PREMULTIPLIED_ALPHA: Cairo data */
+  int32_t render_width, render_height;   /* 0 = pixel size (ttmlrender); else scaled first */
 } TbRefRectangle;
 
 /* gst_video_blend (dest, src, x, y, global_alpha): 1 = TRUE, 0 = FALSE. */
@@ -76,6 +77,11 @@ int tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src);
 /* gst_video_overlay_composition_blend (comp, frame): rectangles in order. */
 int tbref_composition_blend (TbRefFrame *dest, const TbRefRectangle *rects,
     uint32_t n_rects);
+
+/* gst_video_blend_scale_linear_RGBA: src (>= 2x2) to a tightly packed dest_width x
+ * dest_height BGRA image; what composition_blend applies when render size != pixel size. */
+void tbref_scale_linear_rgba (const uint8_t *src_pixels, int32_t src_width, int32_t src_height,
+    int32_t src_stride, int32_t dest_width, int32_t dest_height, uint8_t *dest_pixels);
 
 /* The three colour matrices of video-blend.c, on an (A,c1,c2,c3) line. */
 void tbref_matrix_prea_rgb_to_yuv (uint8_t *line, uint32_t width);

@@ -65,6 +65,7 @@ static const struct {
   int W, H, RW, RH, RX, RY;
   gboolean premul;
   gfloat ga;
+  int render_w, render_h;       /* 0 = pixel size; else the composition scales the rectangle first */
 } cases[] = {
   { 321, 181, 200, 90, 37, 51, TRUE, 1.0f },
   { 321, 181, 200, 90, -33, -17, TRUE, 1.0f },
@@ -75,6 +76,11 @@ static const struct {
   { 321, 181, 200, 90, 37, 51, FALSE, 1.0f },
   { 321, 181, 200, 90, 36, 50, TRUE, 0.5f },
   { 321, 181, 200, 90, 37, 51, FALSE, 0.8f },
+  /* gst_video_blend_scale_linear_RGBA: up, down (> 2x: the line cache jumps), mixed */
+  { 321, 181, 100, 45, 37, 51, TRUE, 1.0f, 200, 90 },
+  { 321, 181, 200, 90, 37, 51, TRUE, 1.0f, 61, 29 },
+  { 321, 181, 64, 64, -9, 100, TRUE, 1.0f, 257, 33 },
+  { 321, 181, 97, 53, 10, 10, FALSE, 0.5f, 150, 70 },
 };
 
 int
@@ -132,7 +138,8 @@ main (int argc, char **argv)
       rbuf = gst_buffer_new_wrapped (g_memdup2 (rpix, RW * RH * 4), RW * RH * 4);
       gst_buffer_add_video_meta (rbuf, GST_VIDEO_FRAME_FLAG_NONE,
           GST_VIDEO_OVERLAY_COMPOSITION_FORMAT_RGB, RW, RH);
-      rect = gst_video_overlay_rectangle_new_raw (rbuf, RX, RY, RW, RH,
+      rect = gst_video_overlay_rectangle_new_raw (rbuf, RX, RY,
+          cases[k].render_w ? cases[k].render_w : RW, cases[k].render_h ? cases[k].render_h : RH,
           cases[k].premul ? GST_VIDEO_OVERLAY_FORMAT_FLAG_PREMULTIPLIED_ALPHA :
           GST_VIDEO_OVERLAY_FORMAT_FLAG_NONE);
       gst_video_overlay_rectangle_set_global_alpha (rect, cases[k].ga);
@@ -159,6 +166,8 @@ main (int argc, char **argv)
       rr.y = RY;
       rr.global_alpha = cases[k].ga;
       rr.flags = cases[k].premul ? TBREF_FLAG_PREMULTIPLIED_ALPHA : 0;
+      rr.render_width = cases[k].render_w;
+      rr.render_height = cases[k].render_h;
       tbref_composition_blend (&rf, &rr, 1);
 
       gst_buffer_map (fbuf, &map, GST_MAP_READ);

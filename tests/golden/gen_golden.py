@@ -45,6 +45,11 @@ VECTORS = [
     # append only: a vector's seed is its position in this list
     ("nv16", "NV16", 63, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
     ("nv24", "NV24", 61, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
+    # rectangles with a render size (.., render_w, render_h): scaled before the blend
+    ("nv12_scaled", "NV12", 96, 64, [(30, 10, 8, 40, 1.0, True, 80, 21), (40, 40, -6, -4, 1.0, True, 17, 23)],
+     True, False),
+    ("bgra_scaled", "BGRA", 80, 48, [(25, 12, 10, 20, 0.7, False, 60, 20), (50, 40, 50, 30, 1.0, True, 45, 13)],
+     False, False),
 ]
 
 
@@ -56,14 +61,17 @@ def main():
         planes = random_frame(fmt, w, h, 7000 + k, opaque=opaque)
         planes = copy_planes(planes)
         rectangles = [dict(pixels=random_overlay(rw, rh, 7100 + 10 * k + i, premultiplied=pm),
-                           x=x, y=y, global_alpha=ga, premultiplied=pm)
-                      for i, (rw, rh, x, y, ga, pm) in enumerate(rects)]
+                           x=x, y=y, global_alpha=ga, premultiplied=pm,
+                           render_width=(rs + [0, 0])[0], render_height=(rs + [0, 0])[1])
+                      for i, (rw, rh, x, y, ga, pm, *rs) in enumerate(rects)]
         out = oracle_blend(fmt, w, h, copy_planes(planes), rectangles, dprem)
         data = {"width": w, "height": h, "n_planes": len(planes), "n_rects": len(rectangles),
                 "dest_premul": dprem,
                 "pos": np.array([[r["x"], r["y"]] for r in rectangles], dtype=np.int32),
                 "ga": np.array([r["global_alpha"] for r in rectangles], dtype=np.float32),
                 "premul": np.array([r["premultiplied"] for r in rectangles], dtype=np.bool_)}
+        if any(r["render_width"] for r in rectangles):
+            data["render"] = np.array([[r["render_width"], r["render_height"]] for r in rectangles], dtype=np.int32)
         for i, p in enumerate(planes):
             data[f"in{i}"] = p
             data[f"out{i}"] = out[i]

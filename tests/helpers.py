@@ -108,12 +108,52 @@ def _over(cs, cd, asrc, adst, ga, sp, dp):
     return np.minimum(v, 255), fa
 
 
+def model_scale_rows(sh, dh):
+    """Which two horizontally resampled source rows, and which 8-bit weight, each destination
+    row of gst_video_blend_scale_linear_RGBA ends up merging: a simulation of its two-line
+    cache (slot = row & 1, `y1` bookkeeping) -- docs/BLENDSPEC.md section 10."""
+    y_inc = 0 if dh == 1 else ((sh - 1) << 16) // (dh - 1) - 1
+    slot = {0: 0}
+    y1, acc, plan = 0, 0, []
+    for _ in range(dh):
+        j, x = acc >> 16, acc & 0xffff
+        if x == 0:
+            plan.append((slot[j & 1], slot[j & 1], 0))
+        else:
+            if j > y1:
+                slot[j & 1] = j
+                y1 += 1
+            if j >= y1:
+                slot[(j + 1) & 1] = j + 1
+                y1 += 1
+            plan.append((slot[j & 1], slot[(j + 1) & 1], x >> 8))
+        acc += y_inc
+    return plan
+
+
+def model_scale(img, dw, dh):
+    """Independent numpy model of gst_video_blend_scale_linear_RGBA (h x w x 4 uint8 in/out)."""
+    sh, sw = img.shape[:2]
+    x_inc = 0 if dw == 1 else ((sw - 1) << 16) // (dw - 1) - 1
+    tmp = np.arange(dw, dtype=np.int64) * x_inc
+    sx, f = tmp >> 16, ((tmp >> 8) & 0xff)[None, :, None]
+    src = img.astype(np.int64)
+    lines = (src[:, sx] * (256 - f) + src[:, sx + 1] * f) >> 8          # every source row resampled
+    plan = np.array(model_scale_rows(sh, dh), dtype=np.int64)
+    a, b, p = lines[plan[:, 0]], lines[plan[:, 1]], plan[:, 2][:, None, None]
+    return (a + (((b - a) * p + 128) >> 8)).astype(np.uint8)
+
+
 def model_blend(fmt, w, h, planes, rectangles, dest_premul=False, chroma_average=False):
     """Blends in place on `planes` and returns them. chroma_average=True models the library's
     NON-PARITY 2x2 chroma option (fluc_ttmlblend_set_chroma_mode), not GStreamer."""
     fmt = fmt.upper()
     for rc in rectangles:
-        px = rc["pixels"].astype(np.int64)
+        px = rc["pixels"]
+        rw_, rh_ = int(rc.get("render_width", 0)) or px.shape[1], int(rc.get("render_height", 0)) or px.shape[0]
+        if (rw_, rh_) != (px.shape[1], px.shape[0]):
+            px = model_scale(px, rw_, rh_)
+        px = px.astype(np.int64)
         ga = int(255.0 * float(np.float32(rc.get("global_alpha", 1.0))))
         sp = bool(rc.get("premultiplied", True))
         x, y = int(rc.get("x", 0)), int(rc.get("y", 0))

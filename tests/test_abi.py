@@ -138,7 +138,7 @@ def test_host_mirror_exports_its_header(lib):
     c = vo.Composition(r)
     c.add_rectangle(r)
     assert c.n_rectangles() == 2
-    assert vlib.fluc_video_overlay_rectangle_new_raw(None, 4, 4, 16, 0, 0, 0) is None
+    assert vlib.fluc_video_overlay_rectangle_new_raw(None, 4, 4, 16, 0, 0, 4, 4, 0) is None
     assert vlib.fluc_video_overlay_composition_blend(None, None) == 0
     if lib.fluc_ttmlblend_device_count() == 0:
         planes = [np.zeros((8, 8 * 4), dtype=np.uint8)]

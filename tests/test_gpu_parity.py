@@ -66,7 +66,9 @@ def test_golden_fixtures(ctx, fmt):
         n = int(z["n_planes"])
         planes = [z[f"in{i}"] for i in range(n)]
         rects = [dict(pixels=z[f"rect{i}"], x=int(z["pos"][i][0]), y=int(z["pos"][i][1]),
-                      global_alpha=float(z["ga"][i]), premultiplied=bool(z["premul"][i]))
+                      global_alpha=float(z["ga"][i]), premultiplied=bool(z["premul"][i]),
+                      render_width=int(z["render"][i][0]) if "render" in z else 0,
+                      render_height=int(z["render"][i][1]) if "render" in z else 0)
                  for i in range(int(z["n_rects"]))]
         for mode in MODES:
             got = gpu_blend(ctx, fmt, int(z["width"]), int(z["height"]), planes, rects, mode=mode,

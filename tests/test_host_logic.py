@@ -50,6 +50,8 @@ def hooks():
     lib.tb_hook_crop_runs.restype = C.c_int
     lib.tb_hook_crop_runs.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int,
                                       C.c_int, C.POINTER(Rect), C.c_int]
+    lib.tb_hook_scale_row_plan.restype = C.c_int
+    lib.tb_hook_scale_row_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
     return lib
 
 
@@ -335,3 +337,25 @@ def test_crop_runs_keeps_every_non_transparent_pixel(hooks, seed):
         if last[y] >= first[y]:
             assert m[y, first[y]:last[y] + 1].all()
     assert runs == sorted(runs, key=lambda r: r[1])
+
+
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("sh,dh", [(2, 3), (2, 1), (90, 29), (45, 90), (64, 33), (53, 70), (1080, 2160),
+                                   (2160, 1080), (4377, 3340), (4324, 1397), (3908, 2787)])
+def test_scale_row_plan_is_the_simulated_line_cache(hooks, sh, dh):
+    """The runtime's row plan for gst_video_blend_scale_linear_RGBA equals the independent
+    simulation in tests/helpers.py; the last three sizes contain rows where upstream's
+    two-line cache holds other rows than (j, j+1)."""
+    from helpers import model_scale_rows
+    out = (C.c_int32 * (3 * dh))()
+    assert hooks.tb_hook_scale_row_plan(sh, dh, out) == dh
+    got = [tuple(out[3 * i:3 * i + 3]) for i in range(dh)]
+    want = model_scale_rows(sh, dh)
+    assert got == want
+    assert all(0 <= a < sh and 0 <= b < sh and 0 <= p <= 255 for a, b, p in got)
+    if sh >= 3000:
+        y_inc = ((sh - 1) << 16) // (dh - 1) - 1
+        naive = [((i * y_inc) >> 16, (i * y_inc) >> 16, 0) if (i * y_inc) & 0xffff == 0 else
+                 ((i * y_inc) >> 16, ((i * y_inc) >> 16) + 1, ((i * y_inc) & 0xffff) >> 8) for i in range(dh)]
+        assert naive != got          # the quirk is really exercised

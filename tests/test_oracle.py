@@ -13,6 +13,7 @@ import pytest
 
 from helpers import (ALL_FORMATS, PACKED, PACKED_ORDER, PLANAR_420, copy_planes, model_blend,
                      oracle_blend, random_frame, random_overlay, wl)
+from oracle import oracle
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -194,7 +195,9 @@ def test_golden_fixtures_match_oracle():
         n = int(z["n_planes"])
         planes = [z[f"in{i}"].copy() for i in range(n)]
         rects = [dict(pixels=z[f"rect{i}"], x=int(z["pos"][i][0]), y=int(z["pos"][i][1]),
-                      global_alpha=float(z["ga"][i]), premultiplied=bool(z["premul"][i]))
+                      global_alpha=float(z["ga"][i]), premultiplied=bool(z["premul"][i]),
+                      render_width=int(z["render"][i][0]) if "render" in z else 0,
+                      render_height=int(z["render"][i][1]) if "render" in z else 0)
                  for i in range(int(z["n_rects"]))]
         out = oracle_blend(v["format"], int(z["width"]), int(z["height"]), planes, rects,
                            bool(z["dest_premul"]))
@@ -313,3 +316,69 @@ def test_region_composition_known_answers():
     ov = oracle.compose_regions([dict(x=0, y=0, w=1, h=1, background_color=0xFF0000FF, opacity=0.25)], 1, 1)
     m8 = int(0.25 * 65535.0 + 0.5) >> 8
     assert list(ov[0, 0]) == [0, 0, mul(255, m8), mul(255, m8)]
+
+
+# ---------------------------------------------------------------------------------------------
+# rectangle scaling (gst_video_blend_scale_linear_RGBA, docs/BLENDSPEC.md section 10)
+
+def test_scale_known_answers():
+    """Hand-computed from the two ORC formulas. 2x2 -> 3x3: both increments are
+    (1 << 16)/2 - 1 = 32767, so the positions are 0, 32767 (fraction 127), 65534 (still pixel
+    0, fraction 255): the last source pixel is never reached exactly (254, not 255)."""
+    from helpers import model_scale
+    img = np.zeros((2, 2, 4), np.uint8)
+    img[:, 1] = 255                                   # left column 0, right column 255
+    out = oracle.scale_linear_rgba(img, 3, 3)
+    assert out[..., 0].tolist() == [[0, (255 * 127) >> 8, (255 * 255) >> 8]] * 3 == [[0, 126, 254]] * 3
+    img = np.zeros((2, 2, 4), np.uint8)
+    img[1] = 255                                      # top row 0, bottom row 255
+    out = oracle.scale_linear_rgba(img, 3, 3)
+    col = [0, (255 * 127 + 128) >> 8, (255 * 255 + 128) >> 8]
+    assert col == [0, 127, 254] and out[:, :, 2].T.tolist() == [col] * 3
+    # a constant image stays constant, whatever the size
+    img = np.full((5, 7, 4), 93, np.uint8)
+    assert (oracle.scale_linear_rgba(img, 40, 3) == 93).all() and (model_scale(img, 40, 3) == 93).all()
+    # one destination row / column: increments 0 -> first source row / column
+    img = np.arange(3 * 4 * 4, dtype=np.uint8).reshape(3, 4, 4)
+    assert np.array_equal(oracle.scale_linear_rgba(img, 1, 1)[0, 0], img[0, 0])
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_scale_oracle_equals_numpy_model(seed):
+    from helpers import model_scale
+    r = np.random.default_rng(4000 + seed)
+    sw, sh = (int(v) for v in r.integers(2, 90, 2))
+    dw, dh = (int(v) for v in r.integers(1, 260, 2))
+    img = r.integers(0, 256, (sh, sw, 4), dtype=np.uint8)
+    assert np.array_equal(oracle.scale_linear_rgba(img, dw, dh), model_scale(img, dw, dh)), (sw, sh, dw, dh)
+
+
+def test_scale_line_cache_quirk_sizes():
+    """Tall sources scaled down: destination rows whose 16.16 position has a zero fraction copy
+    whatever the two-line cache holds (not row j). Oracle (literal loop) == model (simulation)."""
+    from helpers import model_scale
+    r = np.random.default_rng(7)
+    for sh, dh in ((4377, 3340), (4324, 1397)):
+        img = r.integers(0, 256, (sh, 3, 4), dtype=np.uint8)
+        assert np.array_equal(oracle.scale_linear_rgba(img, 5, dh), model_scale(img, 5, dh))
+
+
+@pytest.mark.parametrize("fmt", ("I420", "NV12", "AYUV", "BGRA", "YUY2"))
+def test_scaled_rectangles_in_a_composition(fmt):
+    w, h = 160, 90
+    rects = [dict(pixels=random_overlay(50, 20, 31), x=10, y=50, render_width=120, render_height=33),
+             dict(pixels=random_overlay(90, 60, 32, premultiplied=False), x=-7, y=-5, premultiplied=False,
+                  global_alpha=0.6, render_width=40, render_height=25),
+             dict(pixels=random_overlay(30, 30, 33), x=140, y=70, render_width=61, render_height=30)]
+    planes = random_frame(fmt, w, h, 77)
+    want = model_blend(fmt, w, h, copy_planes(planes), rects)
+    got = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # scaling first and blending the result at pixel size is the same thing
+    pre = [dict(r, pixels=oracle.scale_linear_rgba(r["pixels"], r["render_width"], r["render_height"]),
+                render_width=0, render_height=0) for r in rects]
+    again = oracle_blend(fmt, w, h, copy_planes(planes), pre)
+    for a, b in zip(got, again):
+        assert np.array_equal(a, b)
+    assert any(not np.array_equal(a, b) for a, b in zip(got, planes))
