@@ -65,6 +65,25 @@ fluc_ttmlblend_device_count (void)
   return n;
 }
 
+/* Streams, events and the memory pool fluc_ttmlblend_new creates (also its failure path). */
+static void
+destroy_cuda_objects (Ctx *c)
+{
+  for (cudaEvent_t &e : c->ev_fence)
+    if (e) { cudaEventDestroy (e); e = nullptr; }
+  for (cudaEvent_t *e : { &c->timer0, &c->timer1 })
+    if (*e) { cudaEventDestroy (*e); *e = nullptr; }
+  for (int i = 0; i < kLanes; i++) {
+    if (c->lanes[i].done) cudaEventDestroy (c->lanes[i].done);
+    if (c->lanes[i].stream) cudaStreamDestroy (c->lanes[i].stream);
+    c->lanes[i].done = nullptr;
+    c->lanes[i].stream = nullptr;
+  }
+  for (cudaStream_t *st : { &c->blend_stream, &c->up_stream, &c->reaper, &c->table_stream })
+    if (*st) { cudaStreamDestroy (*st); *st = nullptr; }
+  if (c->mem_pool) { cudaMemPoolDestroy (c->mem_pool); c->mem_pool = nullptr; }
+}
+
 int
 fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
 {
@@ -105,15 +124,23 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   ok &= cudaEventCreate (&c->timer0) == cudaSuccess;
   ok &= cudaEventCreate (&c->timer1) == cudaSuccess;
   if (ok) {
-    /* keep freed overlay memory in the pool instead of returning it to the OS */
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool (&pool, device) == cudaSuccess) {
+    /* a memory pool of our own for the stream-ordered overlay allocations: freed overlay
+     * memory stays in it instead of going back to the OS, and nothing process-wide (the
+     * device's default pool, which other libraries may use) is reconfigured */
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    ok &= cudaMemPoolCreate (&c->mem_pool, &props) == cudaSuccess;
+    if (ok) {
       uint64_t thr = ~0ull;
-      cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      cudaMemPoolSetAttribute (c->mem_pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
   }
   if (!ok) {
     cudaGetLastError ();
+    destroy_cuda_objects (c);
     delete t;
     return FLUC_TTMLBLEND_ERROR_NO_DEVICE;
   }
@@ -152,7 +179,11 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
   if (c->sched.joinable ())
     c->sched.join ();
   cudaSetDevice (c->device);
-  cudaDeviceSynchronize ();
+  /* our own streams only: other users of the device are none of our business */
+  for (cudaStream_t st : { c->blend_stream, c->up_stream, c->table_stream })
+    cudaStreamSynchronize (st);
+  for (int i = 0; i < kLanes; i++)
+    cudaStreamSynchronize (c->lanes[i].stream);
   {
     std::unique_lock<std::mutex> lk (c->mu);
     c->pending.clear ();
@@ -184,8 +215,6 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
       free_slot (c->lanes[i].table[0]);
       free_slot (c->lanes[i].table[1]);
       if (c->lanes[i].dev) cudaFree (c->lanes[i].dev);
-      if (c->lanes[i].done) cudaEventDestroy (c->lanes[i].done);
-      if (c->lanes[i].stream) cudaStreamDestroy (c->lanes[i].stream);
     }
     for (auto &p : c->pool_free) {
       if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
@@ -197,14 +226,7 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
       cudaHostUnregister ((void *) r.first);
     c->auto_regs.clear ();
     if (c->scrub) cudaFree (c->scrub);
-    for (auto e : c->ev_fence)
-      if (e) cudaEventDestroy (e);
-    if (c->timer0) cudaEventDestroy (c->timer0);
-    if (c->timer1) cudaEventDestroy (c->timer1);
-    cudaStreamDestroy (c->blend_stream);
-    cudaStreamDestroy (c->up_stream);
-    cudaStreamDestroy (c->reaper);
-    cudaStreamDestroy (c->table_stream);
+    destroy_cuda_objects (c);
   }
   delete thiz;
 }
@@ -871,9 +893,9 @@ fluc_ttmlblend_blur_argb32 (FlucTtmlBlend *thiz, const uint8_t *src, int32_t w, 
 
   const size_t pitch = align_up ((size_t) w * 4, 256);
   void *d_src = nullptr, *d_dst = nullptr, *d_taps = nullptr;
-  CU (c, cudaMallocAsync (&d_src, pitch * h, c->up_stream));
-  CU (c, cudaMallocAsync (&d_dst, pitch * h, c->up_stream));
-  CU (c, cudaMallocAsync (&d_taps, (size_t) n * 4, c->up_stream));
+  CU (c, cudaMallocFromPoolAsync (&d_src, pitch * h, c->mem_pool, c->up_stream));
+  CU (c, cudaMallocFromPoolAsync (&d_dst, pitch * h, c->mem_pool, c->up_stream));
+  CU (c, cudaMallocFromPoolAsync (&d_taps, (size_t) n * 4, c->mem_pool, c->up_stream));
   CU (c, cudaMemcpy2DAsync (d_src, pitch, src, stride, (size_t) w * 4, h, cudaMemcpyHostToDevice, c->up_stream));
   CU (c, cudaMemcpyAsync (d_taps, taps.data (), (size_t) n * 4, cudaMemcpyHostToDevice, c->up_stream));
   CU (c, launch_blur (static_cast<uint8_t *> (d_src), w, h, (int) pitch, static_cast<int32_t *> (d_taps),
@@ -900,10 +922,8 @@ fluc_ttmlblend_stats_copy (FlucTtmlBlend *thiz, FlucTtmlBlendStats *out)
   reap_batches (&thiz->c);
   *out = thiz->c.stats;
   /* what the overlay caches hold: everything they allocate is stream-ordered pool memory */
-  cudaMemPool_t pool;
   uint64_t used = 0;
-  if (cudaDeviceGetDefaultMemPool (&pool, thiz->c.device) == cudaSuccess &&
-      cudaMemPoolGetAttribute (pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess)
+  if (cudaMemPoolGetAttribute (thiz->c.mem_pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess)
     out->cache_bytes = used;
   else
     cudaGetLastError ();

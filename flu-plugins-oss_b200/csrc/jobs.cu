@@ -209,6 +209,8 @@ make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBl
     f.bands.clear ();
     return;
   }
+  if ((gflags & JF_INPLACE) && f.overlay && f.overlay->lazy_inplace)
+    gflags |= JF_LAZY;
   f.jobs.swap (rest);
   f.grouped = true;
   f.chunks_per_frame = total;

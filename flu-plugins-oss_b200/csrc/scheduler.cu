@@ -159,6 +159,8 @@ launch_pending (Ctx *c)
     CU (c, launch_group (g.P, g.kind, c->blend_stream));
     c->stats.launches++;
     c->stats.group_launches++;
+    if (g.P.flags & JF_LAZY)
+      c->stats.lazy_launches++;
   }
   for (int k = 0; k < 6; k++) {
     if (by_kind[k].empty ())

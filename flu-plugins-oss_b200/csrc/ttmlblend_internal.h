@@ -198,6 +198,8 @@ struct Overlay {
   std::vector<void *> raw_allocs;      /* device copies the rects point into */
   std::vector<FlucTtmlBlendRect> declared;   /* rectangles as handed in (algorithmic bytes) */
   std::vector<std::unique_ptr<Prepared>> prepared;
+  double transparent_fraction = 0.0;   /* of the 16-pixel groups under the kept rectangles */
+  bool lazy_inplace = false;           /* in-place group launches look at the overlay first */
   ~Overlay ();
 };
 
@@ -270,6 +272,7 @@ struct Ctx {
   std::string cuda_error;
 
   cudaStream_t blend_stream = nullptr, up_stream = nullptr, reaper = nullptr, table_stream = nullptr;
+  cudaMemPool_t mem_pool = nullptr;    /* stream-ordered allocations of the overlay cache */
   cudaEvent_t ev_fence[kLanes + 2] = {};
   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 
@@ -309,13 +312,18 @@ struct Ctx {
   FlucTtmlBlendStats stats = {};
 };
 
+/* A failed allocation is reported and forgotten (the context stays usable); any other CUDA
+ * error is sticky. */
 #define CU(ctx, call) do {                                                   \
     cudaError_t e_ = (call);                                                 \
     if (e_ != cudaSuccess) {                                                 \
-      (ctx)->sticky = FLUC_TTMLBLEND_ERROR_CUDA;                             \
       (ctx)->cuda_error = std::string (#call) + ": " + cudaGetErrorString (e_); \
-      return e_ == cudaErrorMemoryAllocation ?                               \
-          FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY : FLUC_TTMLBLEND_ERROR_CUDA;    \
+      if (e_ == cudaErrorMemoryAllocation) {                                 \
+        cudaGetLastError ();                                                 \
+        return FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY;                           \
+      }                                                                      \
+      (ctx)->sticky = FLUC_TTMLBLEND_ERROR_CUDA;                             \
+      return FLUC_TTMLBLEND_ERROR_CUDA;                                      \
     }                                                                        \
   } while (0)
 

@@ -253,6 +253,18 @@ load_job (const PlaneJob *job)
   return J;
 }
 
+/* Does this 16-byte vector of prepared overlay hold any alpha != 0? PLANE8: an alpha byte
+ * per destination byte; packed: the alpha byte of each of the four pixel words. Alpha 0
+ * leaves the destination untouched (BLENDSPEC section 2, `continue`), so an in-place blend
+ * needs neither read nor write such a vector. */
+template <int KIND>
+__device__ __forceinline__ bool
+any_alpha (const uint4 &oa)
+{
+  const uint32_t m = oa.x | oa.y | oa.z | oa.w;
+  return KIND == PK_PLANE8 ? m != 0u : ((m >> (KIND == PK_PACKED_A0 ? 0 : 24)) & 0xffu) != 0u;
+}
+
 /* One chunk = kItemsPerChunk consecutive 16-byte vectors of one job. A job is
  * a window of one plane whose rows all see the same set of rectangles
  * (rect_mask): the host cuts every plane at the rectangles' top and bottom
@@ -269,8 +281,12 @@ load_job (const PlaneJob *job)
  * Thread t owns items t, t+256, t+512, t+768 of the chunk, so four
  * independent 128-bit frame loads (plus their overlay loads) are in flight
  * per thread before the first is consumed. FAST = 16-byte aligned frame and
- * no ragged vector; otherwise the byte-granular variant runs. */
-template <int KIND, bool FAST, bool BULK>
+ * no ragged vector; otherwise the byte-granular variant runs. LAZY (in-place
+ * group launches: dst == src, or host frames blended over PCIe) looks at the
+ * overlay first and touches only the vectors it will change: a vector whose
+ * alpha is zero everywhere is neither loaded nor stored -- for cues without a
+ * background box most of the region never crosses the bus. */
+template <int KIND, bool FAST, bool BULK, bool LAZY = false>
 __device__ __forceinline__ void
 process_chunk (const JobRegs &J, uint32_t local_chunk)
 {
@@ -331,10 +347,12 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
           asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
               :: "r" (sm_a + kItemsPerChunk * 16), "l" (ldg_ptr (&r->c) + off), "r" (bytes), "r" (bar) : "memory");
       }
+      if (!LAZY) {
 #pragma unroll
-      for (int k = 0; k < kUnroll; k++)
-        if (act[k])
-          f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k])
+            f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+      }
       __syncthreads ();           /* the barrier is initialised for everybody */
       asm volatile ("{\n"
           ".reg .pred p;\n"
@@ -344,6 +362,18 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
           "bra OV_WAIT;\n"
           "OV_DONE:\n"
           "}" :: "r" (bar) : "memory");
+      if (LAZY) {
+        /* overlay first: only vectors with some alpha are fetched (all of them in flight
+         * together) and written back */
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          act[k] = act[k] && any_alpha<KIND> (*reinterpret_cast<const uint4 *> (ov_smem +
+                  (threadIdx.x + k * kThreads) * 16u));
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k])
+            f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+      }
       const uint32_t ga = KIND == PK_PLANE8 ? 255u : (uint32_t) __ldg (&r->ga);
       const bool sp = KIND == PK_PLANE8 ? false : __ldg (&r->src_premul) != 0;
       const bool dp = (J.flags & JF_DST_PREMUL) != 0;
@@ -423,10 +453,21 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
     for (int k = 0; k < kUnroll; k++)
       hit[k] = false;
     for (unsigned long long m = mask; m; m &= m - 1) {
-      const RectGeom g = rect_geom (rects + (__ffsll ((long long) m) - 1));
+      const RectRef *r = rects + (__ffsll ((long long) m) - 1);
+      const RectGeom g = rect_geom (r);
+      if (LAZY) {
+        const int32_t pitch = __ldg (&r->pitch);
+        const uint8_t *pa = ldg_ptr (&r->a);
 #pragma unroll
-      for (int k = 0; k < kUnroll; k++)
-        hit[k] = hit[k] || (vv[k] >= g.v0 && vv[k] < g.v1);
+        for (int k = 0; k < kUnroll; k++)
+          if (act[k] && !hit[k] && vv[k] >= g.v0 && vv[k] < g.v1)
+            hit[k] = any_alpha<KIND> (ld_overlay16 (pa + (size_t) (yy[k] - g.y0) * pitch +
+                    (size_t) (vv[k] - g.v0) * 16));
+      } else {
+#pragma unroll
+        for (int k = 0; k < kUnroll; k++)
+          hit[k] = hit[k] || (vv[k] >= g.v0 && vv[k] < g.v1);
+      }
     }
 #pragma unroll
     for (int k = 0; k < kUnroll; k++)
@@ -514,7 +555,7 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
  * first frame load without a single dependent global load or barrier in
  * front of it (the table search of the generic kernel above costs ~8 % of a
  * streaming copy: tools/copybench.cu "+prologue"). */
-template <int KIND>
+template <int KIND, bool LAZY>
 __global__ void __launch_bounds__ (kThreads, TTMLBLEND_MIN_CTAS)
 ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
 {
@@ -549,7 +590,7 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   J.one_rect = B.one_rect;
   J.flags = P.flags;
   J.row_bytes = 0;              /* FAST: never read */
-  process_chunk<KIND, true, true> (J, cif - B.chunk_begin);
+  process_chunk<KIND, true, true, LAZY> (J, cif - B.chunk_begin);
 }
 
 /* Number of interleaved streams the chunk list is walked in. Measured on the
@@ -612,15 +653,27 @@ launch_group (GroupParams &P, int kind, cudaStream_t stream)
   P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
   /* shared memory for the TMA-staged overlay slice of a JC_ONE_BULK chunk */
   const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
+  /* in place (dst == src, host frames over PCIe) under a sparse cue: the variant that reads
+   * the overlay first and skips the vectors it would not change */
+  const bool lazy = (P.flags & JF_LAZY) != 0;
   switch (kind) {
     case PK_PLANE8:
-      ttmlblend_group_kernel<PK_PLANE8><<<grid, kThreads, smem_plane8, stream>>> (P);
+      if (lazy)
+        ttmlblend_group_kernel<PK_PLANE8, true><<<grid, kThreads, smem_plane8, stream>>> (P);
+      else
+        ttmlblend_group_kernel<PK_PLANE8, false><<<grid, kThreads, smem_plane8, stream>>> (P);
       break;
     case PK_PACKED_A0:
-      ttmlblend_group_kernel<PK_PACKED_A0><<<grid, kThreads, smem_packed, stream>>> (P);
+      if (lazy)
+        ttmlblend_group_kernel<PK_PACKED_A0, true><<<grid, kThreads, smem_packed, stream>>> (P);
+      else
+        ttmlblend_group_kernel<PK_PACKED_A0, false><<<grid, kThreads, smem_packed, stream>>> (P);
       break;
     case PK_PACKED_A3:
-      ttmlblend_group_kernel<PK_PACKED_A3><<<grid, kThreads, smem_packed, stream>>> (P);
+      if (lazy)
+        ttmlblend_group_kernel<PK_PACKED_A3, true><<<grid, kThreads, smem_packed, stream>>> (P);
+      else
+        ttmlblend_group_kernel<PK_PACKED_A3, false><<<grid, kThreads, smem_packed, stream>>> (P);
       break;
     default:
       return cudaErrorInvalidValue;
@@ -897,40 +950,51 @@ launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream)
 /* ---------------------------------------------------------------------- */
 /* once per cue: where is the rectangle not transparent?                   */
 
-/* One CTA per row: span[y] = (first x, last x) with alpha != 0, or (w, -1). */
+/* One CTA per row: span[y] = (first x, last x) with alpha != 0, or (w, -1); groups[y] = how
+ * many of the row's 16-pixel groups hold any alpha != 0 (how sparse the cue is: decides
+ * whether in-place launches look at the overlay before touching the frame). */
 __global__ void __launch_bounds__ (128)
-ttmlblend_rowspan_kernel (const uint8_t *__restrict__ raw, int pitch, int w, int2 *__restrict__ spans)
+ttmlblend_rowspan_kernel (const uint8_t *__restrict__ raw, int pitch, int w, int2 *__restrict__ spans,
+    int *__restrict__ groups)
 {
   const int y = blockIdx.x;
   const uint32_t *row = reinterpret_cast<const uint32_t *> (raw + (size_t) y * pitch);
-  int lo = w, hi = -1;
-  for (int x = threadIdx.x; x < w; x += blockDim.x)
-    if (row[x] >> 24) {
+  int lo = w, hi = -1, ng = 0;
+  for (int base = 0; base < w; base += blockDim.x) {
+    const int x = base + (int) threadIdx.x;
+    const bool on = x < w && (row[x] >> 24) != 0;
+    if (on) {
       lo = min (lo, x);
       hi = max (hi, x);
     }
+    const uint32_t b = __ballot_sync (0xffffffffu, on);      /* two groups of 16 pixels per warp */
+    ng += ((b & 0xffffu) ? 1 : 0) + ((b >> 16) ? 1 : 0);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = min (lo, __shfl_xor_sync (0xffffffffu, lo, o));
     hi = max (hi, __shfl_xor_sync (0xffffffffu, hi, o));
   }
-  __shared__ int s_lo[4], s_hi[4];
+  __shared__ int s_lo[4], s_hi[4], s_ng[4];
   if ((threadIdx.x & 31) == 0) {
     s_lo[threadIdx.x >> 5] = lo;
     s_hi[threadIdx.x >> 5] = hi;
+    s_ng[threadIdx.x >> 5] = ng;        /* the same in every lane of a warp */
   }
   __syncthreads ();
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     spans[y] = make_int2 (min (min (s_lo[0], s_lo[1]), min (s_lo[2], s_lo[3])),
         max (max (s_hi[0], s_hi[1]), max (s_hi[2], s_hi[3])));
+    groups[y] = s_ng[0] + s_ng[1] + s_ng[2] + s_ng[3];
+  }
 }
 
 cudaError_t
-launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaStream_t stream)
+launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, int *groups, cudaStream_t stream)
 {
   if (w <= 0 || h <= 0)
     return cudaSuccess;
-  ttmlblend_rowspan_kernel<<<h, 128, 0, stream>>> (raw, pitch, w, spans);
+  ttmlblend_rowspan_kernel<<<h, 128, 0, stream>>> (raw, pitch, w, spans, groups);
   return cudaGetLastError ();
 }
 

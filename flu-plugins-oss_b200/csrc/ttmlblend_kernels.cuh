@@ -38,7 +38,8 @@ enum JobFlags : int32_t {
   JF_VECTOR = 1,        /* src, dst and both pitches are 16-byte aligned */
   JF_INPLACE = 2,       /* dst == src: bytes no rectangle covers are not touched */
   JF_DST_PREMUL = 4,    /* destination frame is premultiplied (packed kinds) */
-  JF_FAST = 8           /* host-side: JF_VECTOR and no ragged last vector -> fast kernel */
+  JF_FAST = 8,          /* host-side: JF_VECTOR and no ragged last vector -> fast kernel */
+  JF_LAZY = 16          /* host-side, group launches in place: overlay first, skip transparent vectors */
 };
 
 /* One prepared rectangle as seen from one destination plane. */
@@ -182,8 +183,10 @@ cudaError_t launch_region (const RegionParams &p, cudaStream_t stream);
 /* (2r+1)^2 16.16 taps; ARGB32 in, ARGB32 out (pixman convolution semantics). */
 cudaError_t launch_blur (const uint8_t *src, int w, int h, int src_pitch, const int32_t *taps, int radius,
     uint8_t *dst, int dst_pitch, cudaStream_t stream);
-/* spans[y] = first / last x of row y with alpha != 0, (w, -1) for an empty row. */
-cudaError_t launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, cudaStream_t stream);
+/* spans[y] = first / last x of row y with alpha != 0, (w, -1) for an empty row;
+ * groups[y] = number of 16-pixel groups of the row with any alpha != 0. */
+cudaError_t launch_rowspan (const uint8_t *raw, int pitch, int w, int h, int2 *spans, int *groups,
+    cudaStream_t stream);
 /* gst_video_blend_scale_linear_RGBA: rows[y] = (source row a, source row b, 8-bit weight, 0),
  * x_inc = the 16.16 horizontal increment; src needs dw's last position + 1 < its width. */
 cudaError_t launch_scale (const uint8_t *src, int src_pitch, const int4 *rows, int x_inc, uint8_t *dst,

@@ -137,10 +137,13 @@ typedef struct {
   uint64_t prepare_launches;    /* overlay prepare kernel launches */
   uint64_t overlays_set;
   uint64_t algorithmic_bytes;   /* 2*frame bytes (or touched bytes in place) + 4*overlay px */
-  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t h2d_bytes, d2h_bytes;   /* zero-copy host frames: bytes of the windows under the cue
+                                    * (an upper bound when a lazy launch skips transparent vectors) */
   double kernel_ms;             /* sum of the CUDA-event times of the timed batches (profiling on) */
   uint64_t kernel_ms_launches;  /* batches included in kernel_ms (one launch each unless mixed) */
   uint64_t cache_bytes;         /* device memory held by overlay caches right now (stream-ordered pool) */
+  uint64_t lazy_launches;       /* group launches in place that read the overlay first and skipped
+                                 * the vectors it leaves untouched (sparse cues; exact either way) */
 } FlucTtmlBlendStats;
 
 /* ---- lifetime -------------------------------------------------------- */

@@ -639,3 +639,46 @@ def test_padded_rgb_formats_are_their_alpha_twins(ctx, fmt, twin):
         for mode in MODES:
             got = gpu_blend(ctx, fmt, w, h, planes, rects, mode=mode, stream=44)
             assert_planes_equal(got, want, f"{fmt} {mode} opaque={opaque}")
+
+
+@pytest.mark.parametrize("fmt", ("NV12", "I420", "BGRA", "AYUV", "YUY2"))
+def test_sparse_cues_take_the_overlay_first_path_in_place(ctx, fmt):
+    """In place (device frames with dst == src, pinned host frames) under a cue without a
+    background box the group kernel reads the overlay first and neither loads nor stores the
+    vectors whose alpha is zero everywhere. Same bytes as the oracle; a cue with a filled box
+    keeps the eager variant."""
+    cfg = wl.CONFIGS[1]                            # 720p, one cue, transparent background
+    w, h = cfg.width, cfg.height
+    sparse = wl.overlay_for(cfg)
+    boxed = sparse.copy()
+    r = cfg.regions[0]
+    box = boxed[r.y:r.y + r.h, r.x:r.x + r.w]
+    box[box[..., 3] == 0] = (0, 0, 0, 96)          # a translucent black box behind the glyphs
+    planes = random_frame(fmt, w, h, 3)
+    for name, ov, lazy in (("sparse", sparse, True), ("boxed", boxed, False)):
+        want = oracle_blend(fmt, w, h, copy_planes(planes), oracle.ttmlrender_rectangles(ov))
+        ctx.overlay_set(5, ov, wl.region_rects(cfg))
+        for on_host in (False, True):
+            fr = ctx.acquire(fmt, w, h, on_host=on_host)
+            if on_host:
+                for d, s in zip(fr.host_planes(), planes):
+                    d[...] = s
+            else:
+                fr.upload(planes)
+            ctx.sync()
+            ctx.stats_reset()
+            if on_host:
+                ctx.wait(ctx.blend_host_frame(5, fmt, w, h, fr.c))
+                got = [np.array(p) for p in fr.host_planes()]
+            else:
+                ctx.wait(ctx.submit(5, fmt, w, h, fr.c, fr.c))
+                got = fr.download()
+            st = ctx.stats()
+            assert (st["lazy_launches"] > 0) == lazy, (name, on_host, st)
+            assert st["lazy_launches"] <= st["group_launches"]
+            assert_planes_equal(got, want, f"{fmt} {name} host={on_host}")
+            fr.release()
+        # out of place never skips: every byte of dst must be written
+        got = gpu_blend(ctx, fmt, w, h, planes, mode="out", stream=5, set_overlay=False)
+        assert ctx.stats()["lazy_launches"] == (st["lazy_launches"])
+        assert_planes_equal(got, want, f"{fmt} {name} out of place")
