@@ -153,6 +153,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->autocrop = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_GROUPS")))
     c->use_groups = atoi (e) != 0;
+  if ((e = getenv ("FLUC_TTMLBLEND_MULTI")))
+    c->use_multi = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_AUTO_REGISTER")))
     c->auto_register = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))

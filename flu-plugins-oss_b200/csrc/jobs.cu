@@ -211,6 +211,9 @@ make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBl
   }
   if ((gflags & JF_INPLACE) && f.overlay && f.overlay->lazy_inplace)
     gflags |= JF_LAZY;
+  for (const PlaneJob &j : f.jobs)
+    if (j.flags & JF_FAST)
+      f.gjobs.push_back (j);
   f.jobs.swap (rest);
   f.grouped = true;
   f.chunks_per_frame = total;
@@ -252,6 +255,58 @@ group_start (Group &g, const PendingFrame &f)
   memcpy (g.P.dst_pitch, f.dst_pitch, sizeof g.P.dst_pitch);
   memcpy (g.P.rect_off, f.rect_off, sizeof g.P.rect_off);
   memcpy (g.P.bands, f.bands.data (), f.bands.size () * sizeof (BandDesc));
+}
+
+void
+multi_start (MultiGroup &m, const PendingFrame &f)
+{
+  m.kind = f.kind;
+  m.n_bands = 0;
+  m.layouts.clear ();
+  /* only the header: frames and bands are written as they are added */
+  m.P.n_frames = 0;
+  m.P.flags = f.gflags;
+  memcpy (m.P.src_pitch, f.src_pitch, sizeof m.P.src_pitch);
+  memcpy (m.P.dst_pitch, f.dst_pitch, sizeof m.P.dst_pitch);
+  m.P.frame_begin[0] = 0;
+}
+
+/* Adds a groupable frame to a multi-layout launch if it fits: same kind, pitches and flags,
+ * room for the frame and -- unless an equal band list is already there -- for its bands. */
+bool
+multi_add (MultiGroup &m, const PendingFrame &f)
+{
+  MultiParams &P = m.P;
+  if (m.kind != f.kind || P.flags != f.gflags || P.n_frames >= (uint32_t) kMaxGroupFrames ||
+      memcmp (P.src_pitch, f.src_pitch, sizeof P.src_pitch) || memcmp (P.dst_pitch, f.dst_pitch, sizeof P.dst_pitch))
+    return false;
+  if ((uint64_t) P.frame_begin[P.n_frames] + f.chunks_per_frame >= (1ull << 26))
+    return false;
+  for (int pl = 0; pl < 3; pl++)
+    if (f.rect_off[pl] < 0 || f.rect_off[pl] > 0xffff)
+      return false;
+  const size_t nb = f.bands.size ();
+  int layout = -1;
+  for (size_t i = 0; i < m.layouts.size (); i++)
+    if (m.layouts[i].second == nb && memcmp (&P.bands[m.layouts[i].first], f.bands.data (), nb * sizeof (BandDesc)) == 0) {
+      layout = (int) i;
+      break;
+    }
+  if (layout < 0) {
+    if (m.n_bands + nb > (size_t) kMaxMultiBands)
+      return false;
+    memcpy (&P.bands[m.n_bands], f.bands.data (), nb * sizeof (BandDesc));
+    m.layouts.push_back ({ (uint16_t) m.n_bands, (uint16_t) nb });
+    layout = (int) m.layouts.size () - 1;
+    m.n_bands += (uint32_t) nb;
+  }
+  const uint32_t k = P.n_frames++;
+  P.frame_band0[k] = m.layouts[layout].first;
+  P.frame_nbands[k] = m.layouts[layout].second;
+  P.frames[k] = f.ptrs;
+  P.frames[k].pad_ = (uint64_t) f.rect_off[0] | ((uint64_t) f.rect_off[1] << 16) | ((uint64_t) f.rect_off[2] << 32);
+  P.frame_begin[k + 1] = P.frame_begin[k] + f.chunks_per_frame;
+  return true;
 }
 
 }  // namespace tbh

@@ -22,29 +22,33 @@ event_get (Ctx *c)
 }
 
 int
-slot_reserve (Ctx *c, TableSlot &s, size_t n)
+slot_reserve (Ctx *c, TableSlot &s, size_t n, size_t words)
 {
-  if (s.cap >= n)
+  if (s.cap >= n && s.cap_words >= words)
     return 0;
-  const size_t cap = std::max<size_t> (256, n * 2);
+  const size_t cap = std::max<size_t> (256, n * 2), cap_words = std::max<size_t> (4096, words * 2);
   if (s.h_jobs) cudaFreeHost (s.h_jobs);
   if (s.h_begin) cudaFreeHost (s.h_begin);
   if (s.d_jobs) cudaFree (s.d_jobs);
   if (s.d_begin) cudaFree (s.d_begin);
-  s.cap = 0;
+  s.h_jobs = nullptr; s.h_begin = nullptr; s.d_jobs = nullptr; s.d_begin = nullptr;
+  s.cap = s.cap_words = 0;
   CU (c, cudaHostAlloc ((void **) &s.h_jobs, cap * sizeof (PlaneJob), cudaHostAllocDefault));
-  CU (c, cudaHostAlloc ((void **) &s.h_begin, cap * sizeof (uint32_t), cudaHostAllocDefault));
+  CU (c, cudaHostAlloc ((void **) &s.h_begin, cap_words * sizeof (uint32_t), cudaHostAllocDefault));
   CU (c, cudaMalloc ((void **) &s.d_jobs, cap * sizeof (PlaneJob)));
-  CU (c, cudaMalloc ((void **) &s.d_begin, cap * sizeof (uint32_t)));
+  CU (c, cudaMalloc ((void **) &s.d_begin, cap_words * sizeof (uint32_t)));
   if (!s.copied)
     CU (c, cudaEventCreateWithFlags (&s.copied, cudaEventDisableTiming));
   if (!s.uploaded)
     CU (c, cudaEventCreateWithFlags (&s.uploaded, cudaEventDisableTiming));
   s.cap = cap;
+  s.cap_words = cap_words;
   return 0;
 }
 
-/* Copies `jobs` (one PlaneKind) into a table slot and launches the kernel. */
+/* Copies `jobs` (one PlaneKind) into a table slot and launches the kernel. The slot's word
+ * array holds the first chunk of every job, then the coarse index (job of every
+ * 2^kCoarseShift-th chunk) the kernel starts its search from. */
 int
 launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast,
     cudaStream_t stream)
@@ -53,22 +57,33 @@ launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, boo
     return 0;
   if (s.copied && s.cap)
     CU (c, cudaEventSynchronize (s.copied));
-  int rc = slot_reserve (c, s, n);
+  uint64_t total64 = 0;
+  for (size_t i = 0; i < n; i++)
+    total64 += jobs[i].n_chunks;
+  if (total64 >= (1ull << 31))
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  const size_t n_coarse = (size_t) ((total64 + (1u << kCoarseShift) - 1) >> kCoarseShift);
+  int rc = slot_reserve (c, s, n, n + n_coarse);
   if (rc)
     return rc;
   uint32_t total = 0;
+  uint32_t *coarse = s.h_begin + n;
+  size_t next = 0;
   for (size_t i = 0; i < n; i++) {
     s.h_jobs[i] = jobs[i];
     s.h_begin[i] = total;
     total += jobs[i].n_chunks;
+    for (; next < n_coarse && ((uint32_t) next << kCoarseShift) < total; next++)
+      coarse[next] = (uint32_t) i;
   }
   /* the table goes up on the copy stream, so that it overlaps the kernel still
    * running on `stream`; the slot is free (its last kernel waited on above) */
   CU (c, cudaMemcpyAsync (s.d_jobs, s.h_jobs, n * sizeof (PlaneJob), cudaMemcpyHostToDevice, c->table_stream));
-  CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, n * sizeof (uint32_t), cudaMemcpyHostToDevice, c->table_stream));
+  CU (c, cudaMemcpyAsync (s.d_begin, s.h_begin, (n + n_coarse) * sizeof (uint32_t), cudaMemcpyHostToDevice,
+          c->table_stream));
   CU (c, cudaEventRecord (s.uploaded, c->table_stream));
   CU (c, cudaStreamWaitEvent (stream, s.uploaded, 0));
-  CU (c, launch_blend (s.d_jobs, s.d_begin, (int) n, total, kind, fast, stream));
+  CU (c, launch_blend (s.d_jobs, s.d_begin, s.d_begin + n, (int) n, total, kind, fast, stream));
   CU (c, cudaEventRecord (s.copied, stream));    /* slot busy until this kernel is done */
   c->stats.launches++;
   return 0;
@@ -108,23 +123,30 @@ launch_pending (Ctx *c)
   std::vector<PlaneJob> by_kind[6];     /* PlaneKind x {byte-granular, fast} */
   std::vector<Group> &groups = c->groups;
   groups.clear ();
+  size_t n_multis = 0;
+  std::vector<int> &frame_group = c->frame_group;
+  frame_group.assign (c->pending.size (), -1);
+  size_t fi = 0;
   for (PendingFrame &f : c->pending) {
     for (const PlaneJob &j : f.jobs)
       by_kind[f.kind * 2 + ((j.flags & JF_FAST) ? 1 : 0)].push_back (j);
     if (f.grouped) {
-      Group *g = nullptr;
-      for (Group &o : groups)
-        if (group_accepts (o, f)) {
-          g = &o;
+      int gi = -1;
+      for (size_t k = 0; k < groups.size (); k++)
+        if (group_accepts (groups[k], f)) {
+          gi = (int) k;
           break;
         }
-      if (!g) {
+      if (gi < 0) {
         groups.emplace_back ();
-        g = &groups.back ();
-        group_start (*g, f);
+        gi = (int) groups.size () - 1;
+        group_start (groups[gi], f);
       }
-      g->P.frames[g->P.n_frames++] = f.ptrs;
+      Group &g = groups[gi];
+      g.P.frames[g.P.n_frames++] = f.ptrs;
+      frame_group[fi] = gi;
     }
+    fi++;
     if (f.overlay)
       b.keep.push_back (f.overlay);
     if (f.prep && !f.prep->blend_waited) {
@@ -135,9 +157,51 @@ launch_pending (Ctx *c)
     c->stats.frames_blended++;
     c->stats.algorithmic_bytes += f.algo_bytes;
   }
+  /* Many streams with different cue layouts give many groups of a frame or two, and a launch
+   * of a few hundred chunks leaves most of the chip idle (tools/many_cues_probe.py: 61 group
+   * launches for 256 1080p frames ran at half the rate of 4). Small groups are dissolved --
+   * when that saves a launch, i.e. there are at least two of them or a table launch of
+   * whole-vector windows is going out anyway. */
+  {
+    size_t n_small = 0, n_table = 0;
+    for (int k = 1; k < 6; k += 2)
+      n_table += by_kind[k].size ();
+    for (Group &g : groups) {
+      g.dissolved = (uint64_t) g.P.n_frames * g.P.chunks_per_frame < (uint64_t) kMinGroupChunks;
+      n_small += g.dissolved ? 1 : 0;
+    }
+    if (n_small < 2 && n_table == 0)
+      for (Group &g : groups)
+        g.dissolved = false;
+    /* their frames are packed into multi-layout launches (band lists in the parameters,
+     * up to 64 frames and kMaxMultiBands bands each); what does not fit goes to the table */
+    fi = 0;
+    for (PendingFrame &f : c->pending) {
+      const int gi = frame_group[fi++];
+      if (gi < 0 || !groups[gi].dissolved)
+        continue;
+      bool placed = false;
+      if (c->use_multi) {
+        for (size_t k = 0; k < n_multis && !placed; k++)
+          placed = multi_add (*c->multis[k], f);
+        if (!placed) {
+          if (n_multis == c->multis.size ())
+            c->multis.emplace_back (new MultiGroup ());
+          multi_start (*c->multis[n_multis], f);
+          placed = multi_add (*c->multis[n_multis], f);
+          n_multis += placed ? 1 : 0;
+        }
+      }
+      if (!placed)
+        for (const PlaneJob &j : f.gjobs)
+          by_kind[f.kind * 2 + 1].push_back (j);
+    }
+  }
   c->pending.clear ();
   c->pending_dst.clear ();
-  size_t n_launches = groups.size ();
+  size_t n_launches = n_multis;
+  for (Group &g : groups)
+    n_launches += g.dissolved ? 0 : 1;
   for (int k = 0; k < 6; k++)
     n_launches += !by_kind[k].empty ();
   /* an event pair keeps the batch from overlapping its neighbours (~2 us of stream time):
@@ -156,10 +220,20 @@ launch_pending (Ctx *c)
   if (b.t0)
     CU (c, cudaEventRecord (b.t0, c->blend_stream));
   for (Group &g : groups) {
+    if (g.dissolved)
+      continue;
     CU (c, launch_group (g.P, g.kind, c->blend_stream));
     c->stats.launches++;
     c->stats.group_launches++;
     if (g.P.flags & JF_LAZY)
+      c->stats.lazy_launches++;
+  }
+  for (size_t k = 0; k < n_multis; k++) {
+    MultiGroup &m = *c->multis[k];
+    CU (c, launch_multi (m.P, m.kind, c->blend_stream));
+    c->stats.launches++;
+    c->stats.multi_launches++;
+    if (m.P.flags & JF_LAZY)
       c->stats.lazy_launches++;
   }
   for (int k = 0; k < 6; k++) {

@@ -209,6 +209,7 @@ struct PendingFrame {
   Prepared *prep;
   int kind;
   std::vector<PlaneJob> jobs;          /* generic-kernel jobs (byte-granular parts, odd frames) */
+  std::vector<PlaneJob> gjobs;         /* the fast windows as table jobs, should the group be dissolved */
   uint64_t algo_bytes;
   /* group launch: the fast windows as a band list + this frame's pointers */
   bool grouped = false;
@@ -222,8 +223,22 @@ struct PendingFrame {
 /* frames that can share one launch: everything but the pointers is equal */
 struct Group {
   int kind;
+  bool dissolved = false;              /* too small to be worth a launch: frames go to the table kernel */
   GroupParams P;
 };
+
+/* frames of one kind / pitch set / flag set with different band lists, packed into one
+ * multi-layout launch; layouts = (first band, number of bands) of the distinct lists so far */
+struct MultiGroup {
+  int kind = 0;
+  uint32_t n_bands = 0;
+  std::vector<std::pair<uint16_t, uint16_t>> layouts;
+  MultiParams P;
+};
+
+/* a group launch below this many chunks (16 KB each; 4096 = 64 MB, ~10 us of HBM time) is
+ * dissolved when there is a table launch to join */
+constexpr uint32_t kMinGroupChunks = 4096;
 
 struct Batch {
   uint64_t last_ticket;
@@ -235,7 +250,7 @@ struct Batch {
 struct TableSlot {
   PlaneJob *h_jobs = nullptr, *d_jobs = nullptr;
   uint32_t *h_begin = nullptr, *d_begin = nullptr;
-  size_t cap = 0;
+  size_t cap = 0, cap_words = 0;       /* jobs / words (job begins + coarse index) */
   cudaEvent_t copied = nullptr;        /* last kernel that read the slot has finished */
   cudaEvent_t uploaded = nullptr;      /* table copy has landed */
 };
@@ -280,6 +295,8 @@ struct Ctx {
 
   std::vector<PendingFrame> pending;
   std::vector<Group> groups;           /* scratch of launch_pending */
+  std::vector<int> frame_group;        /* scratch: pending frame -> index into groups */
+  std::vector<std::unique_ptr<MultiGroup>> multis;   /* scratch: multi-layout launches (reused) */
   std::unordered_set<const void *> pending_dst;   /* destination buffers queued in `pending` */
   std::vector<cudaEvent_t> timing_pool;
   std::chrono::steady_clock::time_point oldest_pending;
@@ -296,6 +313,7 @@ struct Ctx {
   bool chroma_average = false;         /* fluc_ttmlblend_set_chroma_mode (1): NOT bit-exact */
   bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
+  bool use_multi = true;               /* FLUC_TTMLBLEND_MULTI=0: dissolved groups go to the table kernel */
   bool profiling = false;
   uint32_t profile_every = 1, profile_seq = 0;   /* FLUC_TTMLBLEND_PROFILE_EVERY */
   std::thread sched;
@@ -362,6 +380,8 @@ uint64_t build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucT
 void make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst);
 bool group_accepts (const Group &g, const PendingFrame &f);
 void group_start (Group &g, const PendingFrame &f);
+void multi_start (MultiGroup &m, const PendingFrame &f);
+bool multi_add (MultiGroup &m, const PendingFrame &f);
 
 /* scheduler.cu */
 cudaEvent_t event_get (Ctx *c);

@@ -525,25 +525,25 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
 template <int KIND, bool FAST>
 __global__ void __launch_bounds__ (kThreads, FAST ? 4 : 2)
 ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
-    const uint32_t *__restrict__ chunk_begin, int n_jobs, uint32_t total_chunks,
-    uint32_t lanes, uint32_t per_lane, uint32_t lanes_magic)
+    const uint32_t *__restrict__ chunk_begin, const uint32_t *__restrict__ coarse, int n_jobs,
+    uint32_t total_chunks, uint32_t lanes, uint32_t per_lane, uint32_t lanes_magic)
 {
   const uint32_t q = lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, lanes_magic);
   const uint32_t r = blockIdx.x - q * lanes;
   const uint32_t chunk = r * per_lane + q;
-  /* uniform per CTA, so nobody is left waiting at the barrier below */
   if (chunk >= total_chunks)
     return;
 
-  /* which job: count begins <= chunk, cooperatively */
-  int cnt = 0;
-  for (int base = 0; base < n_jobs; base += kThreads) {
-    const int j = base + (int) threadIdx.x;
-    const int pred = (j < n_jobs) && (__ldg (chunk_begin + j) <= chunk);
-    cnt += __syncthreads_count (pred);
-  }
-  const JobRegs J = load_job (jobs + (cnt - 1));
-  process_chunk<KIND, FAST, false> (J, chunk - __ldg (chunk_begin + (cnt - 1)));
+  /* which job: the host's coarse index names the job that holds the first chunk of this
+   * chunk's block of kCoarseChunks; from there a short walk over the begins. Every thread does
+   * the same (broadcast) loads, so there is no barrier and the cost does not grow with the
+   * number of jobs -- a launch may carry the windows of hundreds of frames with different
+   * cue layouts. */
+  uint32_t j = __ldg (coarse + (chunk >> kCoarseShift));
+  while (j + 1u < (uint32_t) n_jobs && __ldg (chunk_begin + j + 1u) <= chunk)
+    j++;
+  const JobRegs J = load_job (jobs + j);
+  process_chunk<KIND, FAST, false> (J, chunk - __ldg (chunk_begin + j));
 }
 
 /* The common case -- a batch of frames that share format, size, strides and
@@ -593,6 +593,55 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   process_chunk<KIND, true, true, LAZY> (J, cif - B.chunk_begin);
 }
 
+/* The same for frames whose band lists differ (many streams, each with its own cue): the
+ * distinct band lists sit back to back in the parameters and every frame names the one it
+ * uses. A CTA finds its frame by bisecting the frames' first chunks (six uniform
+ * constant-bank reads), then its band as above -- still no global load and no barrier before
+ * the first frame load. */
+template <int KIND, bool LAZY>
+__global__ void __launch_bounds__ (kThreads, TTMLBLEND_MIN_CTAS)
+ttmlblend_multi_kernel (const __grid_constant__ MultiParams P)
+{
+  const uint32_t q = P.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, P.lanes_magic);
+  const uint32_t r = blockIdx.x - q * P.lanes;
+  const uint32_t chunk = r * P.per_lane + q;
+  if (chunk >= P.total_chunks)
+    return;
+  uint32_t frame = 0;
+#pragma unroll
+  for (uint32_t step = kMaxGroupFrames / 2; step > 0; step >>= 1) {
+    const uint32_t t = frame + step;
+    if (t < P.n_frames && P.frame_begin[t] <= chunk)
+      frame = t;
+  }
+  const uint32_t cif = chunk - P.frame_begin[frame];
+  const uint32_t b0 = P.frame_band0[frame], nb = P.frame_nbands[frame];
+  uint32_t b = b0;
+  for (uint32_t i = 1; i < nb; i++)
+    b += cif >= P.bands[b0 + i].chunk_begin ? 1u : 0u;
+  const BandDesc &B = P.bands[b];
+  const FramePtrs &F = P.frames[frame];
+  const int pl = B.plane;
+
+  JobRegs J;
+  J.src = F.src[pl];
+  J.dst = F.dst[pl];
+  J.rects = F.rects + ((F.pad_ >> (16 * pl)) & 0xffffu);
+  J.rect_mask = ((unsigned long long) B.rect_mask_hi << 32) | B.rect_mask_lo;
+  J.src_pitch = P.src_pitch[pl];
+  J.dst_pitch = P.dst_pitch[pl];
+  J.win_v0 = B.win_v0;
+  J.win_y0 = B.win_y0;
+  J.win_nv = (uint32_t) B.win_nv;
+  J.total_items = (uint32_t) B.win_nv * (uint32_t) B.win_rows;
+  J.magic = B.div_magic;
+  J.cls = B.cls;
+  J.one_rect = B.one_rect;
+  J.flags = P.flags;
+  J.row_bytes = 0;              /* FAST: never read */
+  process_chunk<KIND, true, true, LAZY> (J, cif - B.chunk_begin);
+}
+
 /* Number of interleaved streams the chunk list is walked in. Measured on the
  * 4K configs: the packed kinds (more ALU work per blended vector) gain 3 %
  * with 61 lanes, PLANE8 loses 2 % against list order, so the default follows
@@ -615,7 +664,7 @@ interleave_lanes (int kind)
 
 template <int KIND>
 static cudaError_t
-launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_jobs,
+launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint32_t *d_coarse, int n_jobs,
     uint32_t total_chunks, bool fast, cudaStream_t stream)
 {
   uint32_t lanes = interleave_lanes (KIND);
@@ -629,10 +678,10 @@ launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_
   const uint32_t magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
   if (fast)
     ttmlblend_blend_kernel<KIND, true><<<grid, kThreads, 0, stream>>> (d_jobs,
-        d_chunk_begin, n_jobs, total_chunks, lanes, per_lane, magic);
+        d_chunk_begin, d_coarse, n_jobs, total_chunks, lanes, per_lane, magic);
   else
     ttmlblend_blend_kernel<KIND, false><<<grid, kThreads, 0, stream>>> (d_jobs,
-        d_chunk_begin, n_jobs, total_chunks, lanes, per_lane, magic);
+        d_chunk_begin, d_coarse, n_jobs, total_chunks, lanes, per_lane, magic);
   return cudaGetLastError ();
 }
 
@@ -682,18 +731,60 @@ launch_group (GroupParams &P, int kind, cudaStream_t stream)
 }
 
 cudaError_t
-launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, int n_jobs,
+launch_multi (MultiParams &P, int kind, cudaStream_t stream)
+{
+  P.total_chunks = P.frame_begin[P.n_frames];
+  if (P.total_chunks == 0)
+    return cudaSuccess;
+  uint32_t lanes = interleave_lanes (kind);
+  if (P.total_chunks < lanes * 8u)
+    lanes = 1;
+  P.lanes = lanes;
+  P.per_lane = (P.total_chunks + lanes - 1) / lanes;
+  const uint32_t grid = lanes * P.per_lane;
+  if ((unsigned long long) grid * lanes >= (1ull << 32))
+    return cudaErrorInvalidValue;
+  P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
+  const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
+  const bool lazy = (P.flags & JF_LAZY) != 0;
+  switch (kind) {
+    case PK_PLANE8:
+      if (lazy)
+        ttmlblend_multi_kernel<PK_PLANE8, true><<<grid, kThreads, smem_plane8, stream>>> (P);
+      else
+        ttmlblend_multi_kernel<PK_PLANE8, false><<<grid, kThreads, smem_plane8, stream>>> (P);
+      break;
+    case PK_PACKED_A0:
+      if (lazy)
+        ttmlblend_multi_kernel<PK_PACKED_A0, true><<<grid, kThreads, smem_packed, stream>>> (P);
+      else
+        ttmlblend_multi_kernel<PK_PACKED_A0, false><<<grid, kThreads, smem_packed, stream>>> (P);
+      break;
+    case PK_PACKED_A3:
+      if (lazy)
+        ttmlblend_multi_kernel<PK_PACKED_A3, true><<<grid, kThreads, smem_packed, stream>>> (P);
+      else
+        ttmlblend_multi_kernel<PK_PACKED_A3, false><<<grid, kThreads, smem_packed, stream>>> (P);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError ();
+}
+
+cudaError_t
+launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint32_t *d_coarse, int n_jobs,
     uint32_t total_chunks, int kind, bool fast, cudaStream_t stream)
 {
   if (n_jobs <= 0 || total_chunks == 0)
     return cudaSuccess;
   switch (kind) {
     case PK_PLANE8:
-      return launch_blend_kind<PK_PLANE8> (d_jobs, d_chunk_begin, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PLANE8> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
     case PK_PACKED_A0:
-      return launch_blend_kind<PK_PACKED_A0> (d_jobs, d_chunk_begin, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PACKED_A0> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
     case PK_PACKED_A3:
-      return launch_blend_kind<PK_PACKED_A3> (d_jobs, d_chunk_begin, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PACKED_A3> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
     default:
       return cudaErrorInvalidValue;
   }

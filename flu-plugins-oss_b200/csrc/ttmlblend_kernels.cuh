@@ -117,6 +117,23 @@ struct GroupParams {
  * every sm_100a system has */
 static_assert (sizeof (GroupParams) <= 16384, "kernel parameters");
 
+/* ---- multi-layout group launch: frames of one format / size / pitch set whose cue layouts
+ * (band lists) differ -- many streams, each showing its own text. Still everything in kernel
+ * parameters: the distinct band lists back to back, and per frame its pointers, which band
+ * list it uses and where its chunks start. */
+constexpr int kMaxMultiBands = 576;
+
+struct MultiParams {
+  uint32_t n_frames, total_chunks, lanes, per_lane, lanes_magic;
+  int32_t flags;
+  int32_t src_pitch[3], dst_pitch[3];
+  uint32_t frame_begin[kMaxGroupFrames + 1];      /* first chunk of every frame, then the total */
+  uint16_t frame_band0[kMaxGroupFrames], frame_nbands[kMaxGroupFrames];
+  FramePtrs frames[kMaxGroupFrames];              /* pad_ = rect_off of planes 0,1,2 in 16-bit fields */
+  BandDesc bands[kMaxMultiBands];                 /* chunk_begin relative to the frame */
+};
+static_assert (sizeof (MultiParams) <= 32764, "kernel parameters");
+
 constexpr int kThreads = 256;
 #ifndef TTMLBLEND_UNROLL
 #define TTMLBLEND_UNROLL 4
@@ -159,10 +176,14 @@ enum PrepareMode : int32_t {
 
 /* All jobs of one launch share one PlaneKind and one variant: fast (every
  * job 16-byte aligned with row_bytes % 16 == 0) or byte-granular. */
-cudaError_t launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin,
+/* d_coarse[i] = index of the job that holds chunk i << kCoarseShift. */
+constexpr int kCoarseShift = 4;
+cudaError_t launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint32_t *d_coarse,
     int n_jobs, uint32_t total_chunks, int kind, bool fast, cudaStream_t stream);
 /* Fills in total_chunks and the interleave fields of P, then launches. */
 cudaError_t launch_group (GroupParams &P, int kind, cudaStream_t stream);
+/* Fills in total_chunks (from frame_begin[n_frames]) and the interleave fields, then launches. */
+cudaError_t launch_multi (MultiParams &P, int kind, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);

@@ -67,7 +67,7 @@ class Stats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("kernel_ms", C.c_double),
                 ("kernel_ms_launches", C.c_uint64), ("cache_bytes", C.c_uint64),
-                ("lazy_launches", C.c_uint64)]
+                ("multi_launches", C.c_uint64), ("lazy_launches", C.c_uint64)]
 
 
 # name -> (restype, argtypes); also the list tests check against the header

@@ -142,6 +142,8 @@ typedef struct {
   double kernel_ms;             /* sum of the CUDA-event times of the timed batches (profiling on) */
   uint64_t kernel_ms_launches;  /* batches included in kernel_ms (one launch each unless mixed) */
   uint64_t cache_bytes;         /* device memory held by overlay caches right now (stream-ordered pool) */
+  uint64_t multi_launches;      /* launches that carried frames with different cue layouts (band
+                                 * lists of up to 64 frames in the kernel parameters) */
   uint64_t lazy_launches;       /* group launches in place that read the overlay first and skipped
                                  * the vectors it leaves untouched (sparse cues; exact either way) */
 } FlucTtmlBlendStats;

@@ -682,3 +682,53 @@ def test_sparse_cues_take_the_overlay_first_path_in_place(ctx, fmt):
         got = gpu_blend(ctx, fmt, w, h, planes, mode="out", stream=5, set_overlay=False)
         assert ctx.stats()["lazy_launches"] == (st["lazy_launches"])
         assert_planes_equal(got, want, f"{fmt} {name} out of place")
+
+
+@pytest.mark.parametrize("fmt,mode", [("I420", "out"), ("NV12", "inplace"), ("BGRA", "out"), ("AYUV", "host")])
+def test_streams_with_different_cue_layouts_share_one_launch(ctx, fmt, mode):
+    """Many streams of one frame geometry, each showing its own cue (other rows, other widths):
+    their band lists differ, so they cannot share a plain group launch; they travel as one
+    multi-layout launch (distinct band lists + per-frame layout index in the kernel parameters).
+    Streams 2k and 2k+1 show the same cue and must share a band list."""
+    w, h, n = 256, 144, 40
+    ctx.set_batch(64, 0)
+    try:
+        frames, rects_of = [], []
+        for i in range(n):
+            k = i // 2
+            rects = [dict(pixels=random_overlay(64 + 16 * (k % 9), 10 + k, 3000 + k), x=16 * (k % 5), y=8 + 3 * k)]
+            if k % 3 == 0:
+                rects.append(dict(pixels=random_overlay(48, 12, 3100 + k, premultiplied=False), x=100 + k, y=4,
+                                  premultiplied=False, global_alpha=0.5))
+            ctx.overlay_set_rectangles(500 + i, rects)
+            rects_of.append(rects)
+            frames.append(random_frame(fmt, w, h, 4000 + i))
+        on_host = mode == "host"
+        srcs = [ctx.acquire(fmt, w, h, on_host=on_host) for _ in range(n)]
+        dsts = srcs if mode != "out" else [ctx.acquire(fmt, w, h) for _ in range(n)]
+        for s_, f in zip(srcs, frames):
+            if on_host:
+                for d, p in zip(s_.host_planes(), f):
+                    d[...] = p
+            else:
+                s_.upload(f)
+        ctx.sync()
+        ctx.stats_reset()
+        if on_host:
+            tickets = [ctx.blend_host_frame(500 + i, fmt, w, h, srcs[i].c) for i in range(n)]
+        else:
+            tickets = ctx.submit_many(ctx.Batch([500 + i for i in range(n)], fmt, w, h,
+                                                [s_.c for s_ in srcs], [d.c for d in dsts]))
+        ctx.wait(max(tickets))
+        st = ctx.stats()
+        assert st["multi_launches"] == 1 and st["launches"] == 1, st
+        for i in range(n):
+            want = oracle_blend(fmt, w, h, copy_planes(frames[i]), rects_of[i])
+            got = [np.array(p) for p in dsts[i].host_planes()] if on_host else dsts[i].download()
+            assert_planes_equal(got, want, f"{fmt} {mode} stream {i}")
+        for f in set(srcs + dsts):
+            f.release()
+        for i in range(n):
+            ctx.overlay_clear(500 + i)
+    finally:
+        ctx.set_batch(32, 200)
