@@ -335,7 +335,6 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
   if ((rc = check_frame (fmt, W, H, src)) || (rc = check_frame (fmt, W, H, dst)))
     return rc;
   PendingFrame f;
-  f.kind = plane_kind (fmt);
   f.prep = nullptr;
   auto it = c->overlays.find (stream);
   if (it != c->overlays.end ()) {
@@ -346,17 +345,18 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
   /* a buffer written twice in one batch would race: launch what is queued first */
   if (c->pending_dst.count (dst->plane[0]) && (rc = launch_pending (c)))
     return rc;
-  f.algo_bytes = build_jobs (fmt, W, H, frame_flags, src, dst, f.prep,
-      src->plane[0] == dst->plane[0], f.jobs);
-  f.dst0 = dst->plane[0];
-  if (c->use_groups)
-    make_groupable (f, src, dst);
+  f.layout = find_layout (c, f.prep, f.overlay && f.overlay->lazy_inplace, fmt, W, H, frame_flags, src, dst,
+      src->plane[0] == dst->plane[0]);
+  for (int pl = 0; pl < 3; pl++) {
+    f.src[pl] = static_cast<const uint8_t *> (src->plane[pl]);
+    f.dst[pl] = static_cast<uint8_t *> (dst->plane[pl]);
+  }
   f.ticket = ++c->next_ticket;
   if (ticket)
     *ticket = f.ticket;
   if (c->pending.empty ())
     c->oldest_pending = std::chrono::steady_clock::now ();
-  c->pending_dst.insert (f.dst0);
+  c->pending_dst.insert (dst->plane[0]);
   c->pending.push_back (std::move (f));
   if (c->pending.size () >= c->max_batch)
     return launch_pending (c);
@@ -586,22 +586,19 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
      * under the cue from host memory and writes them back, all over PCIe,
      * one launch for every queued frame */
     PendingFrame f;
-    f.kind = plane_kind (fmt);
     f.overlay = ov;
     f.prep = prep;
     f.ticket = tk;
     if (c->pending_dst.count (zf.plane[0]) && (rc = launch_pending (c)))
       return rc;
-    f.algo_bytes = build_jobs (fmt, W, H, frame_flags, &zf, &zf, prep, true, f.jobs);
-    f.dst0 = zf.plane[0];
-    c->pending_dst.insert (f.dst0);
-    for (const PlaneJob &j : f.jobs) {
-      const uint64_t nb = (uint64_t) std::min (j.win_nv * 16, j.row_bytes - j.win_v0 * 16) * j.win_rows;
-      c->stats.h2d_bytes += nb;
-      c->stats.d2h_bytes += nb;
+    f.layout = find_layout (c, prep, ov->lazy_inplace, fmt, W, H, frame_flags, &zf, &zf, true);
+    for (int pl = 0; pl < 3; pl++) {
+      f.src[pl] = static_cast<const uint8_t *> (zf.plane[pl]);
+      f.dst[pl] = static_cast<uint8_t *> (zf.plane[pl]);
     }
-    if (c->use_groups)
-      make_groupable (f, &zf, &zf);
+    c->pending_dst.insert (zf.plane[0]);
+    c->stats.h2d_bytes += f.layout->window_bytes;
+    c->stats.d2h_bytes += f.layout->window_bytes;
     if (c->pending.empty ())
       c->oldest_pending = std::chrono::steady_clock::now ();
     c->pending.push_back (std::move (f));

@@ -168,19 +168,19 @@ build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendF
   return bytes;
 }
 
-/* Moves the fast jobs of a frame into a band list for the group kernel. */
+/* Turns the fast jobs of a layout into a band list for the group kernels. */
 void
-make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst)
+make_groupable (Layout &L, bool lazy_inplace)
 {
   size_t n_fast = 0;
-  for (const PlaneJob &j : f.jobs)
+  for (const PlaneJob &j : L.jobs)
     n_fast += (j.flags & JF_FAST) ? 1 : 0;
   if (n_fast == 0 || n_fast > (size_t) kMaxGroupBands)
     return;
   std::vector<PlaneJob> rest;
   uint32_t total = 0;
   int gflags = -1;
-  for (const PlaneJob &j : f.jobs) {
+  for (const PlaneJob &j : L.jobs) {
     if (!(j.flags & JF_FAST)) {
       rest.push_back (j);
       continue;
@@ -199,113 +199,249 @@ make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBl
     b.rect_mask_hi = (uint32_t) (j.rect_mask >> 32);
     b.n_chunks = j.n_chunks;
     total += j.n_chunks;
-    f.bands.push_back (b);
+    L.bands.push_back (b);
     gflags = j.flags & (JF_INPLACE | JF_DST_PREMUL);
   }
   /* frame = umulhi (chunk, ceil (2^32 / cpf)) must be exact for every chunk of a full group */
   const uint64_t magic = ((1ull << 32) + total - 1) / total;
   const uint64_t e = magic * total - (1ull << 32);
   if ((uint64_t) kMaxGroupFrames * total * e >= (1ull << 32) || (uint64_t) kMaxGroupFrames * total >= (1ull << 26)) {
-    f.bands.clear ();
+    L.bands.clear ();
     return;
   }
-  if ((gflags & JF_INPLACE) && f.overlay && f.overlay->lazy_inplace)
+  if ((gflags & JF_INPLACE) && lazy_inplace)
     gflags |= JF_LAZY;
-  for (const PlaneJob &j : f.jobs)
+  for (const PlaneJob &j : L.jobs)
     if (j.flags & JF_FAST)
-      f.gjobs.push_back (j);
-  f.jobs.swap (rest);
-  f.grouped = true;
-  f.chunks_per_frame = total;
-  f.gflags = gflags;
-  for (int pl = 0; pl < 3; pl++) {
-    f.ptrs.src[pl] = static_cast<const uint8_t *> (src->plane[pl]);
-    f.ptrs.dst[pl] = static_cast<uint8_t *> (dst->plane[pl]);
-    f.src_pitch[pl] = src->stride[pl];
-    f.dst_pitch[pl] = dst->stride[pl];
-    f.rect_off[pl] = f.prep ? f.prep->rect_off[pl] : 0;
+      L.gjobs.push_back (j);
+  L.jobs.swap (rest);
+  L.grouped = true;
+  L.chunks_per_frame = total;
+  L.gflags = gflags;
+}
+
+static uint32_t
+aligned_mask_of (int format, const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst)
+{
+  uint32_t m = 0;
+  for (int pl = 0; pl < format_planes (format); pl++)
+    if ((((uintptr_t) src->plane[pl] | (uintptr_t) dst->plane[pl] | (uintptr_t) src->stride[pl] |
+                (uintptr_t) dst->stride[pl]) & 15u) == 0)
+      m |= 1u << pl;
+  return m;
+}
+
+/* Layouts built for different overlays are different objects, but when every stream shows
+ * the same kind of cue (same region box, filled background) their band lists are equal byte
+ * for byte. Those get one id, found through a hash of the band list and confirmed by
+ * comparing it, so that their frames share plain group launches. */
+static uint64_t
+canonical_layout_id (Ctx *c, const Layout &L)
+{
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](const void *p, size_t n) {
+    const uint8_t *b = static_cast<const uint8_t *> (p);
+    for (size_t i = 0; i < n; i++)
+      h = (h ^ b[i]) * 1099511628211ull;
+  };
+  mix (L.bands.data (), L.bands.size () * sizeof (BandDesc));
+  mix (L.src_pitch, sizeof L.src_pitch);
+  mix (L.dst_pitch, sizeof L.dst_pitch);
+  mix (L.rect_off, sizeof L.rect_off);
+  mix (&L.gflags, sizeof L.gflags);
+  mix (&L.kind, sizeof L.kind);
+  std::vector<Ctx::LayoutSig> &bucket = c->layout_sigs[h];
+  for (const Ctx::LayoutSig &s : bucket)
+    if (s.kind == L.kind && s.gflags == L.gflags && s.bands.size () == L.bands.size () &&
+        memcmp (s.pitch, L.src_pitch, sizeof L.src_pitch) == 0 &&
+        memcmp (s.pitch + 3, L.dst_pitch, sizeof L.dst_pitch) == 0 &&
+        memcmp (s.rect_off, L.rect_off, sizeof L.rect_off) == 0 &&
+        memcmp (s.bands.data (), L.bands.data (), L.bands.size () * sizeof (BandDesc)) == 0)
+      return s.id;
+  if (c->n_layout_sigs >= 4096) {       /* ids stay unique; equal layouts built later just get a new one */
+    c->layout_sigs.clear ();
+    c->n_layout_sigs = 0;
   }
-  f.ptrs.rects = f.prep ? f.prep->d_rects_all : nullptr;
-  f.ptrs.pad_ = 0;
+  Ctx::LayoutSig s;
+  s.id = L.id;
+  s.kind = L.kind;
+  s.gflags = L.gflags;
+  memcpy (s.pitch, L.src_pitch, sizeof L.src_pitch);
+  memcpy (s.pitch + 3, L.dst_pitch, sizeof L.dst_pitch);
+  memcpy (s.rect_off, L.rect_off, sizeof L.rect_off);
+  s.bands = L.bands;
+  c->layout_sigs[h].push_back (std::move (s));
+  c->n_layout_sigs++;
+  return L.id;
+}
+
+/* The layout for this frame: found among those already built for the prepared overlay (or,
+ * without an overlay, for the format and size), else built now. */
+const Layout *
+find_layout (Ctx *c, Prepared *prep, bool lazy_inplace, int format, int W, int H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst, bool windowed)
+{
+  std::vector<std::unique_ptr<Layout>> *list = nullptr;
+  if (prep) {
+    list = &prep->layouts;
+  } else {
+    for (auto &b : c->bare_layouts)
+      if (b.format == format && b.W == W && b.H == H)
+        list = &b.layouts;
+    if (!list) {
+      if (c->bare_layouts.size () >= 16) {
+        launch_pending (c);               /* queued frames may point into what is dropped */
+        c->bare_layouts.erase (c->bare_layouts.begin ());
+      }
+      c->bare_layouts.push_back ({ format, W, H, {} });
+      list = &c->bare_layouts.back ().layouts;
+    }
+  }
+  const uint32_t am = aligned_mask_of (format, src, dst);
+  const uint32_t ff = frame_flags & FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA;
+  const int n_planes = format_planes (format);
+  for (auto &l : *list) {
+    if (l->aligned_mask != am || l->windowed != windowed || l->frame_flags != ff)
+      continue;
+    bool same = true;
+    for (int pl = 0; pl < n_planes; pl++)
+      same = same && l->src_pitch[pl] == src->stride[pl] && l->dst_pitch[pl] == dst->stride[pl];
+    if (same)
+      return l.get ();
+  }
+  if (list->size () >= 8) {
+    launch_pending (c);                   /* queued frames may point into what is dropped */
+    list->erase (list->begin ());
+  }
+  std::unique_ptr<Layout> L (new Layout ());
+  L->id = ++c->next_layout_id;
+  L->kind = plane_kind (format);
+  for (int pl = 0; pl < n_planes; pl++) {
+    L->src_pitch[pl] = src->stride[pl];
+    L->dst_pitch[pl] = dst->stride[pl];
+  }
+  L->aligned_mask = am;
+  L->windowed = windowed;
+  L->frame_flags = ff;
+  L->algo_bytes = build_jobs (format, W, H, frame_flags, src, dst, prep, windowed, L->jobs);
+  for (const PlaneJob &j : L->jobs)
+    L->window_bytes += (uint64_t) std::min (j.win_nv * 16, j.row_bytes - j.win_v0 * 16) * (uint64_t) j.win_rows;
+  for (int pl = 0; pl < 3; pl++)
+    L->rect_off[pl] = prep ? prep->rect_off[pl] : 0;
+  L->rects_all = prep ? prep->d_rects_all : nullptr;
+  if (c->use_groups)
+    make_groupable (*L, lazy_inplace);
+  if (L->grouped)
+    L->id = canonical_layout_id (c, *L);
+  list->push_back (std::move (L));
+  return list->back ().get ();
+}
+
+static FramePtrs
+frame_ptrs (const PendingFrame &f)
+{
+  FramePtrs p = {};
+  for (int pl = 0; pl < 3; pl++) {
+    p.src[pl] = f.src[pl];
+    p.dst[pl] = f.dst[pl];
+  }
+  p.rects = f.layout->rects_all;
+  return p;
+}
+
+/* The layout's table jobs with this frame's pointers, appended per (kind, fast). */
+void
+emit_table_jobs (const std::vector<PlaneJob> &tmpl, const PendingFrame &f, std::vector<PlaneJob> *by_kind)
+{
+  for (const PlaneJob &t : tmpl) {
+    std::vector<PlaneJob> &v = by_kind[f.layout->kind * 2 + ((t.flags & JF_FAST) ? 1 : 0)];
+    v.push_back (t);
+    v.back ().src = f.src[t.plane];
+    v.back ().dst = f.dst[t.plane];
+  }
 }
 
 bool
 group_accepts (const Group &g, const PendingFrame &f)
 {
-  const GroupParams &P = g.P;
-  if (g.kind != f.kind || P.n_frames >= (uint32_t) kMaxGroupFrames || P.n_bands != f.bands.size () ||
-      P.chunks_per_frame != f.chunks_per_frame || P.flags != f.gflags)
-    return false;
-  if (memcmp (P.src_pitch, f.src_pitch, sizeof P.src_pitch) || memcmp (P.dst_pitch, f.dst_pitch, sizeof P.dst_pitch) ||
-      memcmp (P.rect_off, f.rect_off, sizeof P.rect_off))
-    return false;
-  return memcmp (P.bands, f.bands.data (), f.bands.size () * sizeof (BandDesc)) == 0;
+  return g.layout_id == f.layout->id && g.P.n_frames < (uint32_t) kMaxGroupFrames;
 }
 
 void
 group_start (Group &g, const PendingFrame &f)
 {
-  memset (&g.P, 0, sizeof g.P);
-  g.kind = f.kind;
-  g.P.n_bands = (uint32_t) f.bands.size ();
-  g.P.chunks_per_frame = f.chunks_per_frame;
-  g.P.cpf_magic = (uint32_t) (((1ull << 32) + f.chunks_per_frame - 1) / f.chunks_per_frame);
-  g.P.flags = f.gflags;
-  memcpy (g.P.src_pitch, f.src_pitch, sizeof g.P.src_pitch);
-  memcpy (g.P.dst_pitch, f.dst_pitch, sizeof g.P.dst_pitch);
-  memcpy (g.P.rect_off, f.rect_off, sizeof g.P.rect_off);
-  memcpy (g.P.bands, f.bands.data (), f.bands.size () * sizeof (BandDesc));
+  const Layout &L = *f.layout;
+  memset (&g.P, 0, offsetof (GroupParams, bands));
+  g.kind = L.kind;
+  g.layout_id = L.id;
+  g.dissolved = false;
+  g.P.n_bands = (uint32_t) L.bands.size ();
+  g.P.chunks_per_frame = L.chunks_per_frame;
+  g.P.cpf_magic = (uint32_t) (((1ull << 32) + L.chunks_per_frame - 1) / L.chunks_per_frame);
+  g.P.flags = L.gflags;
+  memcpy (g.P.src_pitch, L.src_pitch, sizeof g.P.src_pitch);
+  memcpy (g.P.dst_pitch, L.dst_pitch, sizeof g.P.dst_pitch);
+  memcpy (g.P.rect_off, L.rect_off, sizeof g.P.rect_off);
+  memcpy (g.P.bands, L.bands.data (), L.bands.size () * sizeof (BandDesc));
+}
+
+void
+group_add (Group &g, const PendingFrame &f)
+{
+  g.P.frames[g.P.n_frames++] = frame_ptrs (f);
 }
 
 void
 multi_start (MultiGroup &m, const PendingFrame &f)
 {
-  m.kind = f.kind;
+  const Layout &L = *f.layout;
+  m.kind = L.kind;
   m.n_bands = 0;
   m.layouts.clear ();
   /* only the header: frames and bands are written as they are added */
   m.P.n_frames = 0;
-  m.P.flags = f.gflags;
-  memcpy (m.P.src_pitch, f.src_pitch, sizeof m.P.src_pitch);
-  memcpy (m.P.dst_pitch, f.dst_pitch, sizeof m.P.dst_pitch);
+  m.P.flags = L.gflags;
+  memcpy (m.P.src_pitch, L.src_pitch, sizeof m.P.src_pitch);
+  memcpy (m.P.dst_pitch, L.dst_pitch, sizeof m.P.dst_pitch);
   m.P.frame_begin[0] = 0;
 }
 
 /* Adds a groupable frame to a multi-layout launch if it fits: same kind, pitches and flags,
- * room for the frame and -- unless an equal band list is already there -- for its bands. */
+ * room for the frame and -- unless its band list is already there -- for its bands. */
 bool
 multi_add (MultiGroup &m, const PendingFrame &f)
 {
+  const Layout &L = *f.layout;
   MultiParams &P = m.P;
-  if (m.kind != f.kind || P.flags != f.gflags || P.n_frames >= (uint32_t) kMaxGroupFrames ||
-      memcmp (P.src_pitch, f.src_pitch, sizeof P.src_pitch) || memcmp (P.dst_pitch, f.dst_pitch, sizeof P.dst_pitch))
+  if (m.kind != L.kind || P.flags != L.gflags || P.n_frames >= (uint32_t) kMaxGroupFrames ||
+      memcmp (P.src_pitch, L.src_pitch, sizeof P.src_pitch) || memcmp (P.dst_pitch, L.dst_pitch, sizeof P.dst_pitch))
     return false;
-  if ((uint64_t) P.frame_begin[P.n_frames] + f.chunks_per_frame >= (1ull << 26))
+  if ((uint64_t) P.frame_begin[P.n_frames] + L.chunks_per_frame >= (1ull << 26))
     return false;
   for (int pl = 0; pl < 3; pl++)
-    if (f.rect_off[pl] < 0 || f.rect_off[pl] > 0xffff)
+    if (L.rect_off[pl] < 0 || L.rect_off[pl] > 0xffff)
       return false;
-  const size_t nb = f.bands.size ();
-  int layout = -1;
+  const size_t nb = L.bands.size ();
+  int slot = -1;
   for (size_t i = 0; i < m.layouts.size (); i++)
-    if (m.layouts[i].second == nb && memcmp (&P.bands[m.layouts[i].first], f.bands.data (), nb * sizeof (BandDesc)) == 0) {
-      layout = (int) i;
+    if (m.layouts[i].id == L.id) {
+      slot = (int) i;
       break;
     }
-  if (layout < 0) {
+  if (slot < 0) {
     if (m.n_bands + nb > (size_t) kMaxMultiBands)
       return false;
-    memcpy (&P.bands[m.n_bands], f.bands.data (), nb * sizeof (BandDesc));
-    m.layouts.push_back ({ (uint16_t) m.n_bands, (uint16_t) nb });
-    layout = (int) m.layouts.size () - 1;
+    memcpy (&P.bands[m.n_bands], L.bands.data (), nb * sizeof (BandDesc));
+    m.layouts.push_back ({ L.id, (uint16_t) m.n_bands, (uint16_t) nb });
+    slot = (int) m.layouts.size () - 1;
     m.n_bands += (uint32_t) nb;
   }
   const uint32_t k = P.n_frames++;
-  P.frame_band0[k] = m.layouts[layout].first;
-  P.frame_nbands[k] = m.layouts[layout].second;
-  P.frames[k] = f.ptrs;
-  P.frames[k].pad_ = (uint64_t) f.rect_off[0] | ((uint64_t) f.rect_off[1] << 16) | ((uint64_t) f.rect_off[2] << 32);
-  P.frame_begin[k + 1] = P.frame_begin[k] + f.chunks_per_frame;
+  P.frame_band0[k] = m.layouts[slot].band0;
+  P.frame_nbands[k] = m.layouts[slot].n_bands;
+  P.frames[k] = frame_ptrs (f);
+  P.frames[k].pad_ = (uint64_t) L.rect_off[0] | ((uint64_t) L.rect_off[1] << 16) | ((uint64_t) L.rect_off[2] << 32);
+  P.frame_begin[k + 1] = P.frame_begin[k] + L.chunks_per_frame;
   return true;
 }
 

@@ -128,9 +128,8 @@ launch_pending (Ctx *c)
   frame_group.assign (c->pending.size (), -1);
   size_t fi = 0;
   for (PendingFrame &f : c->pending) {
-    for (const PlaneJob &j : f.jobs)
-      by_kind[f.kind * 2 + ((j.flags & JF_FAST) ? 1 : 0)].push_back (j);
-    if (f.grouped) {
+    emit_table_jobs (f.layout->jobs, f, by_kind);
+    if (f.layout->grouped) {
       int gi = -1;
       for (size_t k = 0; k < groups.size (); k++)
         if (group_accepts (groups[k], f)) {
@@ -142,8 +141,7 @@ launch_pending (Ctx *c)
         gi = (int) groups.size () - 1;
         group_start (groups[gi], f);
       }
-      Group &g = groups[gi];
-      g.P.frames[g.P.n_frames++] = f.ptrs;
+      group_add (groups[gi], f);
       frame_group[fi] = gi;
     }
     fi++;
@@ -155,7 +153,7 @@ launch_pending (Ctx *c)
       CU (c, cudaStreamWaitEvent (c->blend_stream, f.prep->ready, 0));
     }
     c->stats.frames_blended++;
-    c->stats.algorithmic_bytes += f.algo_bytes;
+    c->stats.algorithmic_bytes += f.layout->algo_bytes;
   }
   /* Many streams with different cue layouts give many groups of a frame or two, and a launch
    * of a few hundred chunks leaves most of the chip idle (tools/many_cues_probe.py: 61 group
@@ -193,8 +191,7 @@ launch_pending (Ctx *c)
         }
       }
       if (!placed)
-        for (const PlaneJob &j : f.gjobs)
-          by_kind[f.kind * 2 + 1].push_back (j);
+        emit_table_jobs (f.layout->gjobs, f, by_kind);
     }
   }
   c->pending.clear ();

@@ -63,16 +63,15 @@ tb_hook_build_jobs (int format, int W, int H, int windowed, int misalign,
     dst.stride[pl] = stride;
     base += (uintptr_t) stride * plane_rows (format, pl, H) + 4096;
   }
-  PendingFrame f;
-  f.kind = plane_kind (format);
-  f.prep = &prep;
-  f.algo_bytes = build_jobs (format, W, H, 0, &src, &dst, &prep, windowed != 0, f.jobs);
-  std::vector<PlaneJob> all = f.jobs;
-  make_groupable (f, &src, &dst);
+  Layout L;
+  L.kind = plane_kind (format);
+  L.algo_bytes = build_jobs (format, W, H, 0, &src, &dst, &prep, windowed != 0, L.jobs);
+  std::vector<PlaneJob> all = L.jobs;
+  make_groupable (L, false);
   if (algo_bytes)
-    *algo_bytes = f.algo_bytes;
+    *algo_bytes = L.algo_bytes;
   if (chunks_per_frame)
-    *chunks_per_frame = f.grouped ? f.chunks_per_frame : 0;
+    *chunks_per_frame = L.grouped ? L.chunks_per_frame : 0;
   int n = 0;
   for (const PlaneJob &j : all) {
     if (n >= max_jobs)
@@ -82,7 +81,7 @@ tb_hook_build_jobs (int format, int W, int H, int windowed, int misalign,
     o.win_v0 = j.win_v0; o.win_nv = j.win_nv; o.win_y0 = j.win_y0; o.win_rows = j.win_rows;
     o.n_chunks = j.n_chunks; o.div_magic = j.div_magic;
     o.rect_mask = j.rect_mask; o.one_rect = j.one_rect;
-    o.grouped = (f.grouped && (j.flags & JF_FAST)) ? 1 : 0;
+    o.grouped = (L.grouped && (j.flags & JF_FAST)) ? 1 : 0;
   }
   return n;
 }

@@ -177,6 +177,32 @@ struct RawRect {
   bool premul = true;
 };
 
+/* The work of one frame minus its pointers: windows, classes, band list. It depends on the
+ * prepared overlay, the strides, the alignment of the planes, in place or not and the frame
+ * flags -- not on which buffer the frame is in -- so it is built once and shared by every
+ * frame that matches (consecutive frames of a stream, pool buffers). `id` is unique per
+ * context: equal id == equal band list, which is what grouping compares. */
+struct Layout {
+  uint64_t id = 0;
+  int kind = 0;
+  /* key */
+  int32_t src_pitch[3] = { 0, 0, 0 }, dst_pitch[3] = { 0, 0, 0 };
+  uint32_t aligned_mask = 0;           /* bit p: plane p's pointers and strides are 16-byte aligned */
+  bool windowed = false;
+  uint32_t frame_flags = 0;
+  /* value */
+  std::vector<PlaneJob> jobs;          /* table-kernel jobs, src / dst patched per frame */
+  std::vector<PlaneJob> gjobs;         /* the band list's windows as table jobs (group dissolved, no room) */
+  bool grouped = false;
+  std::vector<BandDesc> bands;
+  uint32_t chunks_per_frame = 0;
+  int32_t rect_off[3] = { 0, 0, 0 };
+  int32_t gflags = 0;
+  const RectRef *rects_all = nullptr;
+  uint64_t algo_bytes = 0;
+  uint64_t window_bytes = 0;           /* bytes of all windows (what a zero-copy host frame moves each way) */
+};
+
 /* everything frame-independent, for one (format, W, H) */
 struct Prepared {
   int format = -1, W = 0, H = 0;
@@ -190,6 +216,7 @@ struct Prepared {
   uint64_t overlay_px = 0;             /* sum of clipped w*h */
   cudaEvent_t ready = nullptr;
   bool blend_waited = false;           /* blend stream already ordered after `ready` */
+  std::vector<std::unique_ptr<Layout>> layouts;
 };
 
 struct Overlay {
@@ -205,24 +232,17 @@ struct Overlay {
 
 struct PendingFrame {
   uint64_t ticket;
-  std::shared_ptr<Overlay> overlay;
+  std::shared_ptr<Overlay> overlay;    /* keeps prep and layout alive */
   Prepared *prep;
-  int kind;
-  std::vector<PlaneJob> jobs;          /* generic-kernel jobs (byte-granular parts, odd frames) */
-  std::vector<PlaneJob> gjobs;         /* the fast windows as table jobs, should the group be dissolved */
-  uint64_t algo_bytes;
-  /* group launch: the fast windows as a band list + this frame's pointers */
-  bool grouped = false;
-  std::vector<BandDesc> bands;
-  FramePtrs ptrs;
-  int32_t src_pitch[3], dst_pitch[3], rect_off[3], gflags;
-  uint32_t chunks_per_frame = 0;
-  const void *dst0 = nullptr;
+  const Layout *layout;
+  const uint8_t *src[3];
+  uint8_t *dst[3];
 };
 
 /* frames that can share one launch: everything but the pointers is equal */
 struct Group {
   int kind;
+  uint64_t layout_id;
   bool dissolved = false;              /* too small to be worth a launch: frames go to the table kernel */
   GroupParams P;
 };
@@ -232,7 +252,8 @@ struct Group {
 struct MultiGroup {
   int kind = 0;
   uint32_t n_bands = 0;
-  std::vector<std::pair<uint16_t, uint16_t>> layouts;
+  struct Slot { uint64_t id; uint16_t band0, n_bands; };
+  std::vector<Slot> layouts;
   MultiParams P;
 };
 
@@ -292,6 +313,15 @@ struct Ctx {
   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 
   std::unordered_map<uint32_t, std::shared_ptr<Overlay>> overlays;
+  /* layouts of frames without an overlay (pass-through copies), by format / size */
+  struct BareLayouts { int format, W, H; std::vector<std::unique_ptr<Layout>> layouts; };
+  std::vector<BareLayouts> bare_layouts;
+  uint64_t next_layout_id = 0;
+  /* band lists seen so far, by hash: layouts of different overlays (streams) with the same
+   * bands, strides and flags get the same id and so share group launches */
+  struct LayoutSig { uint64_t id; int kind; int32_t gflags; int32_t pitch[6], rect_off[3]; std::vector<BandDesc> bands; };
+  std::unordered_map<uint64_t, std::vector<LayoutSig>> layout_sigs;
+  size_t n_layout_sigs = 0;
 
   std::vector<PendingFrame> pending;
   std::vector<Group> groups;           /* scratch of launch_pending */
@@ -377,11 +407,15 @@ int overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTt
 int check_frame (int fmt, int W, int H, const FlucTtmlBlendFrame *f);
 uint64_t build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
     const FlucTtmlBlendFrame *dst, const Prepared *prep, bool windowed, std::vector<PlaneJob> &jobs);
-void make_groupable (PendingFrame &f, const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst);
+void make_groupable (Layout &L, bool lazy_inplace);
+const Layout *find_layout (Ctx *c, Prepared *prep, bool lazy_inplace, int format, int W, int H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst, bool windowed);
 bool group_accepts (const Group &g, const PendingFrame &f);
 void group_start (Group &g, const PendingFrame &f);
+void group_add (Group &g, const PendingFrame &f);
 void multi_start (MultiGroup &m, const PendingFrame &f);
 bool multi_add (MultiGroup &m, const PendingFrame &f);
+void emit_table_jobs (const std::vector<PlaneJob> &tmpl, const PendingFrame &f, std::vector<PlaneJob> *by_kind);
 
 /* scheduler.cu */
 cudaEvent_t event_get (Ctx *c);
