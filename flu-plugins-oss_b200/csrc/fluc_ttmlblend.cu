@@ -538,13 +538,12 @@ fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled)
 }
 
 
-int
-fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
-    int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *hf, uint64_t *ticket)
+static int
+blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *hf, uint64_t *ticket)
 {
-  ENTER (thiz);
   int rc;
-  fmt = (FlucTtmlBlendFormat) format_canon (fmt);
+  fmt = format_canon (fmt);
   if ((rc = check_frame (fmt, W, H, hf)))
     return rc;
   const uint64_t tk = ++c->next_ticket;
@@ -566,6 +565,15 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
   FlucTtmlBlendFrame zf = {};
   bool mapped = c->host_mode != HM_STAGED;
   for (int pl = 0; pl < n_planes && mapped; pl++) {
+    /* pinned pool frames are known (cudaHostAlloc under UVA: device pointer == host pointer):
+     * no driver call per plane per frame for them */
+    if (c->pinned_planes.count (hf->plane[pl])) {
+      zf.plane[pl] = hf->plane[pl];
+      zf.stride[pl] = hf->stride[pl];
+      if ((zf.stride[pl] & 15) != 0)
+        mapped = false;
+      continue;
+    }
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes (&attr, hf->plane[pl]) != cudaSuccess ||
         attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
@@ -709,6 +717,31 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
 }
 
 int
+fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFormat fmt,
+    int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *hf, uint64_t *ticket)
+{
+  ENTER (thiz);
+  return blend_host_locked (c, stream, fmt, W, H, frame_flags, hf, ticket);
+}
+
+int
+fluc_ttmlblend_blend_host_many (FlucTtmlBlend *thiz, uint32_t n, const uint32_t *streams,
+    FlucTtmlBlendFormat fmt, int32_t W, int32_t H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *host_frames, uint64_t *tickets)
+{
+  ENTER (thiz);
+  if (n && (!streams || !host_frames))
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < n; i++) {
+    int rc = blend_host_locked (c, streams[i], fmt, W, H, frame_flags, &host_frames[i],
+        tickets ? &tickets[i] : nullptr);
+    if (rc)
+      return rc;
+  }
+  return 0;
+}
+
+int
 fluc_ttmlblend_host_register (FlucTtmlBlend *thiz, void *ptr, size_t bytes)
 {
   ENTER (thiz);
@@ -800,8 +833,11 @@ fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt,
     CU (c, cudaHostAlloc (&p.base, off, cudaHostAllocDefault));
   else
     CU (c, cudaMalloc (&p.base, off));
-  for (int pl = 0; pl < n_planes; pl++)
+  for (int pl = 0; pl < n_planes; pl++) {
     p.frame.plane[pl] = static_cast<uint8_t *> (p.base) + plane_off[pl];
+    if (on_host)
+      c->pinned_planes.insert (p.frame.plane[pl]);
+  }
   *out = p.frame;
   c->pool_used.push_back (p);
   return 0;

@@ -354,6 +354,7 @@ struct Ctx {
   std::map<uint64_t, int> lane_tickets;
 
   std::vector<PoolEntry> pool_free, pool_used;
+  std::unordered_set<const void *> pinned_planes;   /* plane pointers of the pinned host pool frames */
   uint8_t *scrub = nullptr;
   size_t scrub_bytes = 0;
 

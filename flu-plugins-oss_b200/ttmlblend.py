@@ -98,6 +98,9 @@ PROTOTYPES = {
     "fluc_ttmlblend_set_batch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "fluc_ttmlblend_blend_host": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int32, C.c_int32,
                                             C.c_uint32, C.POINTER(Frame), C.POINTER(C.c_uint64)]),
+    "fluc_ttmlblend_blend_host_many": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_int,
+                                                 C.c_int32, C.c_int32, C.c_uint32, C.POINTER(Frame),
+                                                 C.POINTER(C.c_uint64)]),
     "fluc_ttmlblend_set_auto_register": (C.c_int, [C.c_void_p, C.c_int]),
     "fluc_ttmlblend_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fluc_ttmlblend_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -366,6 +369,14 @@ class TtmlBlend:
             self.h, stream, FORMATS[fmt], width, height, frame_flags, C.byref(frame), C.byref(t)),
             "blend_host")
         return t.value
+
+    def blend_host_many(self, batch: "TtmlBlend.Batch"):
+        """One C call for a batch of host frames (batch.dsts; modified in place); returns the
+        ticket array."""
+        self._check(self.lib.fluc_ttmlblend_blend_host_many(
+            self.h, batch.n, batch.streams, batch.fmt, batch.width, batch.height, batch.flags,
+            batch.dsts, batch.tickets), "blend_host_many")
+        return batch.tickets
 
     def set_auto_register(self, on: bool):
         self._check(self.lib.fluc_ttmlblend_set_auto_register(self.h, 1 if on else 0), "set_auto_register")

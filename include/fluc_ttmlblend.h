@@ -238,6 +238,12 @@ FLUC_EXPORT int fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_fram
 FLUC_EXPORT int fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream,
     FlucTtmlBlendFormat fmt, int32_t width, int32_t height, uint32_t frame_flags,
     const FlucTtmlBlendFrame *host_frame, uint64_t *ticket);
+/* The same for n host frames of one geometry under a single lock (many streams, or a run of
+ * frames of one): streams[i], host_frames[i], tickets[i]. Waiting for the last ticket waits
+ * for all of them when every frame took the zero-copy path. */
+FLUC_EXPORT int fluc_ttmlblend_blend_host_many (FlucTtmlBlend *thiz, uint32_t n,
+    const uint32_t *streams, FlucTtmlBlendFormat fmt, int32_t width, int32_t height,
+    uint32_t frame_flags, const FlucTtmlBlendFrame *host_frames, uint64_t *tickets);
 /* Opt-in: pin pageable host frames the first time blend_host sees them (up to 192 planes,
  * least recently used dropped), so that recycled buffers of a pool take the zero-copy path.
  * The caller must not free such memory while the context lives without host_unregister. */

@@ -732,3 +732,31 @@ def test_streams_with_different_cue_layouts_share_one_launch(ctx, fmt, mode):
             ctx.overlay_clear(500 + i)
     finally:
         ctx.set_batch(32, 200)
+
+
+def test_blend_host_many_equals_blend_host(ctx):
+    """One C call for a run of host frames: pinned pool frames (zero copy) and, through the
+    same call, pageable numpy frames (staging lanes) -- each must equal the oracle."""
+    fmt, w, h, n = "NV12", 320, 180, 6
+    rects = [dict(pixels=random_overlay(200, 40, 61), x=60, y=120)]
+    ctx.overlay_set_rectangles(9, rects)
+    frames = [random_frame(fmt, w, h, 700 + i) for i in range(n)]
+    pinned = [ctx.acquire(fmt, w, h, on_host=True) for _ in range(n)]
+    for hf, f in zip(pinned, frames):
+        for d, p in zip(hf.host_planes(), f):
+            d[...] = p
+    tickets = ctx.blend_host_many(ctx.Batch([9] * n, fmt, w, h, [hf.c for hf in pinned], [hf.c for hf in pinned]))
+    ctx.wait(tickets[n - 1])
+    for i in range(n):
+        want = oracle_blend(fmt, w, h, copy_planes(frames[i]), rects)
+        assert_planes_equal([np.array(p) for p in pinned[i].host_planes()], want, f"pinned {i}")
+    pageable = [copy_planes(f) for f in frames]
+    cfr = [pkg.ttmlblend._frame_from_arrays(p) for p in pageable]
+    tickets = ctx.blend_host_many(ctx.Batch([9] * n, fmt, w, h, cfr, cfr))
+    for t in tickets:
+        ctx.wait(t)
+    for i in range(n):
+        want = oracle_blend(fmt, w, h, copy_planes(frames[i]), rects)
+        assert_planes_equal(pageable[i], want, f"pageable {i}")
+    for hf in pinned:
+        hf.release()
