@@ -760,3 +760,81 @@ def test_blend_host_many_equals_blend_host(ctx):
         assert_planes_equal(pageable[i], want, f"pageable {i}")
     for hf in pinned:
         hf.release()
+
+
+def test_layout_cache_eviction_with_frames_queued(ctx):
+    """A prepared overlay keeps at most 8 layouts (one per stride / alignment combination) and
+    the context at most 16 format/size entries for frames without an overlay; building one more
+    while frames that use the oldest are still queued must launch those first. Twelve stride
+    combinations in ONE batch, with and without an overlay, plus twenty frame sizes."""
+    tb = pkg.ttmlblend
+    fmt, w, h = "GRAY8", 256, 32
+    rects = [dict(pixels=random_overlay(120, 16, 9), x=40, y=8)]
+    big_src = ctx.acquire(fmt, 8192, 64)
+    big_dst = ctx.acquire(fmt, 8192, 64)
+    ctx.set_batch(64, 0)
+    try:
+        for stream, with_cue in ((41, True), (42, False)):
+            if with_cue:
+                ctx.overlay_set_rectangles(stream, rects)
+            else:
+                ctx.overlay_clear(stream)
+            planes = random_frame(fmt, w, h, 31)
+            want = oracle_blend(fmt, w, h, copy_planes(planes), rects if with_cue else [])
+            strides = [256 + 16 * k for k in range(12)]            # 12 layouts, 4 of them misaligned below
+            views = []
+            for k, stride in enumerate(strides):
+                off = 16 * k + (4 if k % 3 == 2 else 0)            # every third frame 4-byte aligned only
+                sf, df = tb.Frame(), tb.Frame()
+                sf.plane[0] = big_src.c.plane[0] + off
+                df.plane[0] = big_dst.c.plane[0] + off
+                sf.stride[0] = df.stride[0] = stride
+                views.append((sf, df))
+            hsrc = tb._frame_from_arrays(planes)
+            # the views overlap in memory, so one at a time: upload, queue, and only then wait
+            for sf, df in views:
+                ctx._check(ctx.lib.fluc_ttmlblend_frame_upload(ctx.h, tb.FORMATS[fmt], w, h, hsrc, sf), "up")
+                t = ctx.submit(stream, fmt, w, h, sf, df)
+                ctx.wait(t)
+                got = [np.zeros((h, w), dtype=np.uint8)]
+                ctx._check(ctx.lib.fluc_ttmlblend_frame_download(ctx.h, tb.FORMATS[fmt], w, h, df,
+                                                                 tb._frame_from_arrays(got)), "down")
+                assert_planes_equal(got, want, f"stride {sf.stride[0]} cue={with_cue}")
+            # and all twelve queued together, each view in its own piece of the big buffer
+            views, base = [], 0
+            for k, stride in enumerate(strides):
+                sf, df = tb.Frame(), tb.Frame()
+                off = base + (4 if k % 3 == 2 else 0)
+                sf.plane[0] = big_src.c.plane[0] + off
+                df.plane[0] = big_dst.c.plane[0] + off
+                sf.stride[0] = df.stride[0] = stride
+                views.append((sf, df))
+                base += (stride * h + 4 + 255) // 256 * 256
+            assert base <= 8192 * 64
+            for sf, df in views:
+                ctx._check(ctx.lib.fluc_ttmlblend_frame_upload(ctx.h, tb.FORMATS[fmt], w, h, hsrc, sf), "up")
+            tickets = [ctx.submit(stream, fmt, w, h, sf, df) for sf, df in views]
+            ctx.wait(max(tickets))
+            for sf, df in views:
+                got = [np.zeros((h, w), dtype=np.uint8)]
+                ctx._check(ctx.lib.fluc_ttmlblend_frame_download(ctx.h, tb.FORMATS[fmt], w, h, df,
+                                                                 tb._frame_from_arrays(got)), "down")
+                assert_planes_equal(got, want, f"queued together, stride {sf.stride[0]} cue={with_cue}")
+        # twenty sizes without an overlay, all queued before the first wait
+        ctx.overlay_clear(43)
+        jobs = []
+        for k in range(20):
+            ww, hh = 64 + 16 * k, 16 + k
+            p = random_frame(fmt, ww, hh, 900 + k)
+            s_, d_ = ctx.acquire(fmt, ww, hh), ctx.acquire(fmt, ww, hh)
+            s_.upload(p)
+            jobs.append((ctx.submit(43, fmt, ww, hh, s_.c, d_.c), p, s_, d_))
+        for t, p, s_, d_ in jobs:
+            ctx.wait(t)
+            assert_planes_equal(d_.download(), p, "pass-through")
+            s_.release()
+            d_.release()
+    finally:
+        ctx.set_batch(32, 200)
+        big_src.release()
+        big_dst.release()
