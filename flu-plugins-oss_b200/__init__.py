@@ -12,6 +12,7 @@ The directory name is not a Python identifier; import it through
 __graft_entry__.load_package() (registers it as `flu_plugins_oss_b200`).
 """
 from . import sharding, ttmlblend, videooverlay, workloads  # noqa: F401
-from .ttmlblend import TtmlBlend, TtmlBlendError, load_library  # noqa: F401
+from .ttmlblend import TtmlBlend, TtmlBlendError, TtmlBlendMulti, load_library  # noqa: F401
 
-__all__ = ["sharding", "ttmlblend", "videooverlay", "workloads", "TtmlBlend", "TtmlBlendError", "load_library"]
+__all__ = ["sharding", "ttmlblend", "videooverlay", "workloads", "TtmlBlend", "TtmlBlendError", "TtmlBlendMulti",
+           "load_library"]

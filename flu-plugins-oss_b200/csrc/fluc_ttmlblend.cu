@@ -945,6 +945,118 @@ fluc_ttmlblend_blur_argb32 (FlucTtmlBlend *thiz, const uint8_t *src, int32_t w, 
   return 0;
 }
 
+/* ---- several GPUs in one process -------------------------------------- */
+
+struct _FlucTtmlBlendMulti {
+  std::vector<FlucTtmlBlend *> ctx;
+  std::vector<int> device;
+};
+
+int
+fluc_ttmlblend_multi_new (const int *devices, uint32_t n_devices, FlucTtmlBlendMulti **out)
+{
+  if (!out)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  *out = nullptr;
+  std::vector<int> devs;
+  if (devices && n_devices) {
+    devs.assign (devices, devices + n_devices);
+  } else {
+    const int n = fluc_ttmlblend_device_count ();
+    for (int i = 0; i < n; i++)
+      devs.push_back (i);
+  }
+  if (devs.empty ())
+    return FLUC_TTMLBLEND_ERROR_NO_DEVICE;
+  FlucTtmlBlendMulti *m = new (std::nothrow) FlucTtmlBlendMulti ();
+  if (!m)
+    return FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY;
+  for (int d : devs) {
+    FlucTtmlBlend *t = nullptr;
+    const int rc = d < 0 ? FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT : fluc_ttmlblend_new (d, &t);
+    if (rc) {
+      fluc_ttmlblend_multi_free (m);
+      return rc;
+    }
+    m->ctx.push_back (t);
+    m->device.push_back (d);
+  }
+  *out = m;
+  return 0;
+}
+
+void
+fluc_ttmlblend_multi_free (FlucTtmlBlendMulti *thiz)
+{
+  if (!thiz)
+    return;
+  for (FlucTtmlBlend *t : thiz->ctx)
+    fluc_ttmlblend_free (t);
+  delete thiz;
+}
+
+uint32_t
+fluc_ttmlblend_multi_size (FlucTtmlBlendMulti *thiz)
+{
+  return thiz ? (uint32_t) thiz->ctx.size () : 0u;
+}
+
+FlucTtmlBlend *
+fluc_ttmlblend_multi_context (FlucTtmlBlendMulti *thiz, uint32_t stream)
+{
+  return thiz && !thiz->ctx.empty () ? thiz->ctx[stream % thiz->ctx.size ()] : nullptr;
+}
+
+int
+fluc_ttmlblend_multi_device (FlucTtmlBlendMulti *thiz, uint32_t stream)
+{
+  return thiz && !thiz->ctx.empty () ? thiz->device[stream % thiz->ctx.size ()] : -1;
+}
+
+int
+fluc_ttmlblend_multi_sync (FlucTtmlBlendMulti *thiz)
+{
+  if (!thiz)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  int ret = 0;
+  /* launch everywhere first, then wait: the devices work at the same time */
+  for (FlucTtmlBlend *t : thiz->ctx) {
+    const int rc = fluc_ttmlblend_flush (t);
+    ret = ret ? ret : rc;
+  }
+  for (FlucTtmlBlend *t : thiz->ctx) {
+    const int rc = fluc_ttmlblend_sync (t);
+    ret = ret ? ret : rc;
+  }
+  return ret;
+}
+
+void
+fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *out)
+{
+  if (!thiz || !out)
+    return;
+  FlucTtmlBlendStats sum = {};
+  for (FlucTtmlBlend *t : thiz->ctx) {
+    FlucTtmlBlendStats s = {};
+    fluc_ttmlblend_stats_copy (t, &s);
+    sum.frames_blended += s.frames_blended;
+    sum.launches += s.launches;
+    sum.group_launches += s.group_launches;
+    sum.prepare_launches += s.prepare_launches;
+    sum.overlays_set += s.overlays_set;
+    sum.algorithmic_bytes += s.algorithmic_bytes;
+    sum.h2d_bytes += s.h2d_bytes;
+    sum.d2h_bytes += s.d2h_bytes;
+    sum.kernel_ms += s.kernel_ms;
+    sum.kernel_ms_launches += s.kernel_ms_launches;
+    sum.cache_bytes += s.cache_bytes;
+    sum.multi_launches += s.multi_launches;
+    sum.lazy_launches += s.lazy_launches;
+  }
+  *out = sum;
+}
+
 /* ---- observability --------------------------------------------------- */
 
 void

@@ -78,6 +78,13 @@ PROTOTYPES = {
     "fluc_ttmlblend_last_cuda_error": (C.c_char_p, [C.c_void_p]),
     "fluc_ttmlblend_device_count": (C.c_int, []),
     "fluc_ttmlblend_version": (C.c_char_p, []),
+    "fluc_ttmlblend_multi_new": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "fluc_ttmlblend_multi_free": (None, [C.c_void_p]),
+    "fluc_ttmlblend_multi_size": (C.c_uint32, [C.c_void_p]),
+    "fluc_ttmlblend_multi_context": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "fluc_ttmlblend_multi_device": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "fluc_ttmlblend_multi_sync": (C.c_int, [C.c_void_p]),
+    "fluc_ttmlblend_multi_stats_copy": (None, [C.c_void_p, C.POINTER(Stats)]),
     "fluc_ttmlblend_overlay_set": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32,
                                              C.c_int32, C.c_int32, C.POINTER(Rect), C.c_uint32]),
     "fluc_ttmlblend_overlay_set_rectangles": (C.c_int, [C.c_void_p, C.c_uint32,
@@ -236,8 +243,12 @@ class DeviceFrame:
 class TtmlBlend:
     """One context per GPU (FlucTtmlBlend)."""
 
-    def __init__(self, device: int = 0, lib_path: Optional[str] = None):
+    def __init__(self, device: int = 0, lib_path: Optional[str] = None, _borrowed=None):
         self.lib = load_library(lib_path)
+        self._owned = _borrowed is None
+        if _borrowed is not None:               # a context owned by a TtmlBlendMulti
+            self.h = C.c_void_p(_borrowed)
+            return
         self.h = C.c_void_p()
         rc = self.lib.fluc_ttmlblend_new(device, C.byref(self.h))
         if rc != OK:
@@ -246,7 +257,8 @@ class TtmlBlend:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.fluc_ttmlblend_free(self.h)
+            if self._owned:
+                self.lib.fluc_ttmlblend_free(self.h)
             self.h = None
 
     def __enter__(self):
@@ -423,6 +435,55 @@ class TtmlBlend:
 
     def scrub_l2(self, nbytes: int = 256 << 20):
         self._check(self.lib.fluc_ttmlblend_scrub_l2(self.h, nbytes), "scrub_l2")
+
+
+class TtmlBlendMulti:
+    """Several GPUs in one process (FlucTtmlBlendMulti): stream s lives on context s % n."""
+
+    def __init__(self, devices: Sequence[int] = ()):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        arr = (C.c_int * max(1, len(devices)))(*devices)
+        rc = self.lib.fluc_ttmlblend_multi_new(arr if devices else None, len(devices), C.byref(self.h))
+        if rc != OK:
+            self.h = None
+            raise TtmlBlendError(rc, "fluc_ttmlblend_multi_new", self.lib.fluc_ttmlblend_strerror(rc).decode())
+        self._ctx = {}
+
+    def size(self) -> int:
+        return self.lib.fluc_ttmlblend_multi_size(self.h)
+
+    def context(self, stream: int) -> TtmlBlend:
+        k = stream % self.size()
+        if k not in self._ctx:
+            self._ctx[k] = TtmlBlend(_borrowed=self.lib.fluc_ttmlblend_multi_context(self.h, stream))
+        return self._ctx[k]
+
+    def device(self, stream: int) -> int:
+        return self.lib.fluc_ttmlblend_multi_device(self.h, stream)
+
+    def sync(self):
+        rc = self.lib.fluc_ttmlblend_multi_sync(self.h)
+        if rc != OK:
+            raise TtmlBlendError(rc, "fluc_ttmlblend_multi_sync", self.lib.fluc_ttmlblend_strerror(rc).decode())
+
+    def stats(self) -> dict:
+        s = Stats()
+        self.lib.fluc_ttmlblend_multi_stats_copy(self.h, C.byref(s))
+        return {name: getattr(s, name) for name, _ in Stats._fields_}
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self._ctx.values():
+                c.h = None
+            self.lib.fluc_ttmlblend_multi_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def composition_blend(ctx: TtmlBlend, stream: int, fmt: str, width: int, height: int,

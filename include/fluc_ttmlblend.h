@@ -157,6 +157,22 @@ FLUC_EXPORT const char *fluc_ttmlblend_last_cuda_error (FlucTtmlBlend *thiz);
 FLUC_EXPORT int fluc_ttmlblend_device_count (void);
 FLUC_EXPORT const char *fluc_ttmlblend_version (void);
 
+/* ---- several GPUs in one process --------------------------------------
+ * Streams are independent, so a process that serves many of them (one GStreamer process,
+ * many elements) spreads them over the box's GPUs with no exchange between GPUs: one
+ * context per device, stream s lives on context s % n (the same
+ * partition flu-plugins-oss_b200/sharding.py uses across processes). Everything about a
+ * stream -- overlay_set, submit, blend_host, wait, pool frames -- is then done on
+ * fluc_ttmlblend_multi_context (m, stream). */
+typedef struct _FlucTtmlBlendMulti FlucTtmlBlendMulti;
+/* devices == NULL or n_devices == 0: every CUDA device of the box. */
+FLUC_EXPORT int fluc_ttmlblend_multi_new (const int *devices, uint32_t n_devices, FlucTtmlBlendMulti **out);
+FLUC_EXPORT void fluc_ttmlblend_multi_free (FlucTtmlBlendMulti *thiz);
+FLUC_EXPORT uint32_t fluc_ttmlblend_multi_size (FlucTtmlBlendMulti *thiz);
+FLUC_EXPORT FlucTtmlBlend *fluc_ttmlblend_multi_context (FlucTtmlBlendMulti *thiz, uint32_t stream);
+FLUC_EXPORT int fluc_ttmlblend_multi_device (FlucTtmlBlendMulti *thiz, uint32_t stream);
+FLUC_EXPORT int fluc_ttmlblend_multi_sync (FlucTtmlBlendMulti *thiz);     /* flush + wait, every device */
+
 /* ---- overlay cache: once per cue change ------------------------------ */
 /* ttmlrender form: one W*H premultiplied BGRA image (gen_buffer output) plus
  * the region rectangles that can hold non-transparent pixels. n_rects == 0
@@ -284,6 +300,8 @@ FLUC_EXPORT int fluc_ttmlblend_blur_argb32 (FlucTtmlBlend *thiz, const uint8_t *
 /* ---- observability --------------------------------------------------- */
 FLUC_EXPORT void fluc_ttmlblend_stats_copy (FlucTtmlBlend *thiz, FlucTtmlBlendStats *out);
 FLUC_EXPORT void fluc_ttmlblend_stats_reset (FlucTtmlBlend *thiz);
+/* Sum over the contexts of a multi (kernel_ms adds up device time spent in parallel). */
+FLUC_EXPORT void fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *out);
 /* Per-launch CUDA-event timing of the blend kernel into stats.kernel_ms:
  * 0 = off, 1 = every launch, n > 1 = every n-th launch (an event pair between
  * two launches keeps them from overlapping, ~2 % at 4K x 32 frames). */
