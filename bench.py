@@ -116,6 +116,8 @@ def dist_setup(n_gpus: int):
         import torch
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's version / debug lines go to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
             device = torch.device("cuda", local)
