@@ -177,6 +177,7 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
     std::unique_lock<std::mutex> lk (c->mu);
     c->quit = true;
     c->cv.notify_all ();
+    c->launched_cv.notify_all ();
   }
   if (c->sched.joinable ())
     c->sched.join ();
@@ -352,6 +353,8 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
     f.dst[pl] = static_cast<uint8_t *> (dst->plane[pl]);
   }
   f.ticket = ++c->next_ticket;
+  f.stream = stream;
+  note_stream (c, stream);
   if (ticket)
     *ticket = f.ticket;
   if (c->pending.empty ())
@@ -431,9 +434,24 @@ fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
     return 0;
   }
   if (!c->pending.empty () && ticket >= c->pending.front ().ticket) {
-    int rc = launch_pending (c);
-    if (rc)
-      return rc;
+    /* The frame has not been launched yet. A lone stream launches now (lowest latency). When
+     * several streams are active -- many elements calling blend + wait from their own
+     * streaming threads -- the batch is left to the scheduler thread for up to the linger
+     * time (or until it is full), so that the other streams' frames share the launch. */
+    if (c->linger_us && several_streams_active (c) && c->pending.size () < c->max_batch) {
+      c->cv.notify_all ();
+      c->launched_cv.wait (lk, [&] {
+        return c->quit || c->sticky || c->linger_us == 0 || c->pending.empty () ||
+            ticket < c->pending.front ().ticket;
+      });
+      if (c->sticky)
+        return c->sticky;
+    }
+    if (!c->pending.empty () && ticket >= c->pending.front ().ticket) {
+      int rc = launch_pending (c);
+      if (rc)
+        return rc;
+    }
   }
   cudaEvent_t ev = nullptr;
   for (auto &b : c->batches)
@@ -486,6 +504,7 @@ fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_frames, uint32_t lin
   c->max_batch = max_frames;
   c->linger_us = linger_us;
   c->cv.notify_all ();
+  c->launched_cv.notify_all ();
   return 0;
 }
 
@@ -597,6 +616,8 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
     f.overlay = ov;
     f.prep = prep;
     f.ticket = tk;
+    f.stream = stream;
+    note_stream (c, stream);
     if (c->pending_dst.count (zf.plane[0]) && (rc = launch_pending (c)))
       return rc;
     f.layout = find_layout (c, prep, ov->lazy_inplace, fmt, W, H, frame_flags, &zf, &zf, true);

@@ -248,6 +248,7 @@ launch_pending (Ctx *c)
   b.done = event_get (c);
   CU (c, cudaEventRecord (b.done, c->blend_stream));
   c->batches.push_back (std::move (b));
+  c->launched_cv.notify_all ();
   return 0;
 }
 
@@ -269,6 +270,7 @@ scheduler_main (Ctx *c)
         c->pending.clear ();
         c->pending_dst.clear ();
       }
+      c->launched_cv.notify_all ();   /* also when the launch failed: waiters must not sleep on */
     } else {
       c->cv.wait_until (lk, deadline);
     }

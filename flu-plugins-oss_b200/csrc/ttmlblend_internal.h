@@ -232,6 +232,7 @@ struct Overlay {
 
 struct PendingFrame {
   uint64_t ticket;
+  uint32_t stream;
   std::shared_ptr<Overlay> overlay;    /* keeps prep and layout alive */
   Prepared *prep;
   const Layout *layout;
@@ -303,7 +304,12 @@ constexpr int kTableSlots = 8;
 struct Ctx {
   int device = 0;
   std::mutex mu;
-  std::condition_variable cv;
+  std::condition_variable cv;          /* wakes the scheduler thread */
+  std::condition_variable launched_cv; /* a batch has been launched (waiters that let it linger) */
+  /* the streams of the last submissions: with more than one active, a synchronous caller's
+   * wait lets the batch linger so that other streams' frames can join its launch */
+  uint32_t recent_streams[16] = {};
+  uint32_t recent_pos = 0, recent_n = 0;
   int sticky = 0;
   std::string cuda_error;
 
@@ -417,6 +423,24 @@ void group_add (Group &g, const PendingFrame &f);
 void multi_start (MultiGroup &m, const PendingFrame &f);
 bool multi_add (MultiGroup &m, const PendingFrame &f);
 void emit_table_jobs (const std::vector<PlaneJob> &tmpl, const PendingFrame &f, std::vector<PlaneJob> *by_kind);
+
+inline void
+note_stream (Ctx *c, uint32_t stream)
+{
+  c->recent_streams[c->recent_pos] = stream;
+  c->recent_pos = (c->recent_pos + 1) % 16;
+  if (c->recent_n < 16)
+    c->recent_n++;
+}
+
+inline bool
+several_streams_active (const Ctx *c)
+{
+  for (uint32_t i = 1; i < c->recent_n; i++)
+    if (c->recent_streams[i] != c->recent_streams[0])
+      return true;
+  return false;
+}
 
 /* scheduler.cu */
 cudaEvent_t event_get (Ctx *c);

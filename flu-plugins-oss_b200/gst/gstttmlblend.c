@@ -81,6 +81,45 @@ G_DEFINE_TYPE (GstTTMLBlend, gst_ttmlblend, GST_TYPE_BASE_TRANSFORM);
 
 static guint32 next_stream_id = 1;
 
+/* One set of contexts for the whole process, shared by every ttmlblend element: frames of
+ * different elements (streams) then meet in the same batch scheduler and share launches, and
+ * the elements spread over the box's GPUs (device = -1: stream id % number of GPUs). */
+static GMutex shared_lock;
+static FlucTtmlBlendMulti *shared_multi = NULL;
+static guint shared_refs = 0;
+
+static FlucTtmlBlend *
+shared_context_acquire (gint device, guint32 stream_id, int *rc)
+{
+  FlucTtmlBlend *ctx = NULL;
+  g_mutex_lock (&shared_lock);
+  *rc = FLUC_TTMLBLEND_OK;
+  if (!shared_multi)
+    *rc = fluc_ttmlblend_multi_new (NULL, 0, &shared_multi);
+  if (*rc == FLUC_TTMLBLEND_OK) {
+    if (device >= (gint) fluc_ttmlblend_multi_size (shared_multi))
+      *rc = FLUC_TTMLBLEND_ERROR_NO_DEVICE;
+    else
+      /* every device of the box is in the set, in order: context i is device i */
+      ctx = fluc_ttmlblend_multi_context (shared_multi, device < 0 ? stream_id : (guint32) device);
+  }
+  if (ctx)
+    shared_refs++;
+  g_mutex_unlock (&shared_lock);
+  return ctx;
+}
+
+static void
+shared_context_release (void)
+{
+  g_mutex_lock (&shared_lock);
+  if (shared_refs > 0 && --shared_refs == 0) {
+    fluc_ttmlblend_multi_free (shared_multi);
+    shared_multi = NULL;
+  }
+  g_mutex_unlock (&shared_lock);
+}
+
 static FlucTtmlBlendFormat
 to_fluc_format (GstVideoFormat f)
 {
@@ -227,8 +266,9 @@ static gboolean
 gst_ttmlblend_start (GstBaseTransform * trans)
 {
   GstTTMLBlend *self = GST_TTMLBLEND (trans);
-  int rc = fluc_ttmlblend_new (self->device, &self->ctx);
-  if (rc != FLUC_TTMLBLEND_OK) {
+  int rc;
+  self->ctx = shared_context_acquire (self->device, self->stream_id, &rc);
+  if (!self->ctx) {
     GST_ELEMENT_ERROR (self, LIBRARY, INIT, ("no usable CUDA device"),
         ("%s", fluc_ttmlblend_strerror (rc)));
     return FALSE;
@@ -245,8 +285,11 @@ gst_ttmlblend_stop (GstBaseTransform * trans)
 {
   GstTTMLBlend *self = GST_TTMLBLEND (trans);
   g_mutex_lock (&self->lock);
-  if (self->ctx)
-    fluc_ttmlblend_free (self->ctx);
+  if (self->ctx) {
+    /* the context lives on for the other elements: drop only this stream's overlay */
+    fluc_ttmlblend_overlay_clear (self->ctx, self->stream_id);
+    shared_context_release ();
+  }
   self->ctx = NULL;
   self->have_overlay = FALSE;
   g_mutex_unlock (&self->lock);
@@ -302,7 +345,7 @@ gst_ttmlblend_class_init (GstTTMLBlendClass * klass)
   gobject_class->finalize = gst_ttmlblend_finalize;
   g_object_class_install_property (gobject_class, PROP_DEVICE,
       g_param_spec_int ("device", "CUDA device",
-          "CUDA device index (-1: FLUC_TTMLBLEND_DEVICE or 0)", -1, 64, -1,
+          "CUDA device index (-1: spread the elements over all GPUs, stream id % n)", -1, 64, -1,
           G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
 
   gst_element_class_add_static_pad_template (element_class, &video_sink_template);

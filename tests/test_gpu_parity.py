@@ -838,3 +838,61 @@ def test_layout_cache_eviction_with_frames_queued(ctx):
         ctx.set_batch(32, 200)
         big_src.release()
         big_dst.release()
+
+
+def test_synchronous_callers_of_many_streams_share_launches(ctx):
+    """What a GStreamer process with many ttmlblend elements does: every element's streaming
+    thread calls blend (host frame, in place) and waits for it, frame after frame. With several
+    streams active a wait lets the batch linger (up to the linger time) instead of launching
+    its own frame alone, so frames of different threads share launches; a single stream is
+    launched at once. Bit-exact either way."""
+    w, h, fmt, n_threads, n_frames = 320, 180, "NV12", 12, 25
+    errors = []
+    ctx.set_batch(32, 2000)                    # 2 ms linger: generous for Python threads
+    barrier = threading.Barrier(n_threads)
+
+    def worker(t):
+        try:
+            rects = [dict(pixels=random_overlay(200, 40, 800 + t), x=40 + t, y=100 + t)]
+            ctx.overlay_set_rectangles(700 + t, rects)
+            planes = random_frame(fmt, w, h, 2000 + t)
+            want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+            hf = ctx.acquire(fmt, w, h, on_host=True)
+            barrier.wait()
+            for i in range(n_frames):
+                for d, p in zip(hf.host_planes(), planes):
+                    d[...] = p
+                ctx.wait(ctx.blend_host_frame(700 + t, fmt, w, h, hf.c))
+                assert_planes_equal([np.array(p) for p in hf.host_planes()], want, f"thread {t} frame {i}")
+            hf.release()
+        except Exception as e:      # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    try:
+        ctx.sync()
+        ctx.stats_reset()
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        assert not errors, errors
+        st = ctx.stats()
+        assert st["frames_blended"] == n_threads * n_frames
+        assert st["launches"] < 0.7 * st["frames_blended"], st          # frames did share launches
+        # one stream alone is not made to wait: a launch per frame, no lingering
+        ctx.stats_reset()
+        import time
+        rects = [dict(pixels=random_overlay(200, 40, 899), x=40, y=100)]
+        ctx.overlay_set_rectangles(799, rects)
+        hf = ctx.acquire(fmt, w, h, on_host=True)
+        for _ in range(20):                       # the other streams drop out of the recent list
+            ctx.wait(ctx.blend_host_frame(799, fmt, w, h, hf.c))
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ctx.wait(ctx.blend_host_frame(799, fmt, w, h, hf.c))
+        per_frame = (time.perf_counter() - t0) / 50
+        assert per_frame < 1e-3, per_frame          # far below the 2 ms linger
+        hf.release()
+    finally:
+        ctx.set_batch(32, 200)
