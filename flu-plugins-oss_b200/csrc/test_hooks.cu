@@ -115,6 +115,84 @@ tb_hook_crop_runs (const int32_t *first, const int32_t *last, int rows, int min_
   return (int) r.size ();
 }
 
+/* Layout cache, canonical ids and multi-layout packing, without a GPU: `n_frames` GRAY8 frames
+ * of W x H; frame i belongs to "overlay" ov[i] (frames of one overlay share a Prepared) whose
+ * single rectangle is rects[ov[i]], and has stride[i]. Out per frame: the layout's id and which
+ * multi-layout launch (index) it was packed into; returns the number of launches, and in
+ * *n_band_lists the distinct band lists the launches carry in total. */
+__attribute__ ((visibility ("default"))) int
+tb_hook_pack_layouts (int W, int H, int n_frames, const int32_t *ov, int n_overlays, const TbHookRect *rects,
+    const int32_t *stride, uint64_t *layout_id, int32_t *launch_of, int32_t *n_band_lists)
+{
+  const int format = FLUC_TTMLBLEND_FORMAT_GRAY8;
+  Ctx c;                                /* no CUDA object is created or touched */
+  static RectRef fake_table[64];
+  std::vector<std::unique_ptr<Prepared>> preps;
+  for (int k = 0; k < n_overlays; k++) {
+    std::unique_ptr<Prepared> p (new Prepared ());
+    p->format = format;
+    p->W = W;
+    p->H = H;
+    RectRef r = {};
+    r.v0 = rects[k].v0; r.v1 = rects[k].v1; r.y0 = rects[k].y0; r.y1 = rects[k].y1;
+    r.pitch = (r.v1 - r.v0) * 16;
+    r.ga = 255;
+    p->h_rects[0].push_back (r);
+    p->d_rects[0] = fake_table;
+    p->d_rects_all = fake_table;
+    preps.push_back (std::move (p));
+  }
+  std::vector<PendingFrame> frames ((size_t) n_frames);
+  std::vector<std::unique_ptr<MultiGroup>> multis;
+  for (int i = 0; i < n_frames; i++) {
+    if (ov[i] < 0 || ov[i] >= n_overlays || stride[i] < W)
+      return -1;
+    FlucTtmlBlendFrame src = {}, dst = {};
+    src.plane[0] = (void *) (uintptr_t) (0x10000000u + 0x100000u * (unsigned) i);
+    dst.plane[0] = (void *) (uintptr_t) (0x50000000u + 0x100000u * (unsigned) i);
+    src.stride[0] = dst.stride[0] = stride[i];
+    PendingFrame &f = frames[(size_t) i];
+    f.prep = preps[(size_t) ov[i]].get ();
+    f.layout = find_layout (&c, f.prep, false, format, W, H, 0, &src, &dst, false);
+    f.src[0] = static_cast<const uint8_t *> (src.plane[0]);
+    f.dst[0] = static_cast<uint8_t *> (dst.plane[0]);
+    layout_id[i] = f.layout->id;
+    launch_of[i] = -1;
+    if (!f.layout->grouped)
+      continue;
+    for (size_t k = 0; k < multis.size () && launch_of[i] < 0; k++)
+      if (multi_add (*multis[k], f))
+        launch_of[i] = (int32_t) k;
+    if (launch_of[i] < 0) {
+      multis.emplace_back (new MultiGroup ());
+      multi_start (*multis.back (), f);
+      if (multi_add (*multis.back (), f))
+        launch_of[i] = (int32_t) multis.size () - 1;
+    }
+  }
+  int lists = 0;
+  for (auto &m : multis) {
+    lists += (int) m->layouts.size ();
+    /* the parameters must be self-consistent: frames partition the chunks, band lists in range */
+    const MultiParams &P = m->P;
+    for (uint32_t k = 0; k < P.n_frames; k++) {
+      if (P.frame_begin[k + 1] <= P.frame_begin[k] || P.frame_band0[k] + P.frame_nbands[k] > m->n_bands)
+        return -2;
+      uint32_t chunks = 0;
+      for (uint32_t b = 0; b < P.frame_nbands[k]; b++) {
+        if (P.bands[P.frame_band0[k] + b].chunk_begin != chunks)
+          return -3;
+        chunks += P.bands[P.frame_band0[k] + b].n_chunks;
+      }
+      if (chunks != P.frame_begin[k + 1] - P.frame_begin[k])
+        return -4;
+    }
+  }
+  if (n_band_lists)
+    *n_band_lists = lists;
+  return (int) multis.size ();
+}
+
 /* rows[3*i..] = (source row a, source row b, weight) of destination row i */
 __attribute__ ((visibility ("default"))) int
 tb_hook_scale_row_plan (int src_h, int dst_h, int32_t *rows)

@@ -50,6 +50,10 @@ def hooks():
     lib.tb_hook_crop_runs.restype = C.c_int
     lib.tb_hook_crop_runs.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int,
                                       C.c_int, C.POINTER(Rect), C.c_int]
+    lib.tb_hook_pack_layouts.restype = C.c_int
+    lib.tb_hook_pack_layouts.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int,
+                                         C.POINTER(HookRect), C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.tb_hook_scale_row_plan.restype = C.c_int
     lib.tb_hook_scale_row_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
     return lib
@@ -359,3 +363,50 @@ def test_scale_row_plan_is_the_simulated_line_cache(hooks, sh, dh):
         naive = [((i * y_inc) >> 16, (i * y_inc) >> 16, 0) if (i * y_inc) & 0xffff == 0 else
                  ((i * y_inc) >> 16, ((i * y_inc) >> 16) + 1, ((i * y_inc) & 0xffff) >> 8) for i in range(dh)]
         assert naive != got          # the quirk is really exercised
+
+
+# ---------------------------------------------------------------------------------------------
+
+def pack(hooks, W, H, ov, rects, strides):
+    n = len(ov)
+    ids = (C.c_uint64 * n)()
+    launch = (C.c_int32 * n)()
+    lists = C.c_int32(0)
+    k = hooks.tb_hook_pack_layouts(W, H, n, (C.c_int32 * n)(*ov), len(rects),
+                                   (HookRect * len(rects))(*[HookRect(*r) for r in rects]),
+                                   (C.c_int32 * n)(*strides), ids, launch, C.byref(lists))
+    assert k >= 0, k
+    return k, list(ids), list(launch), lists.value
+
+
+def test_layouts_are_shared_and_canonical(hooks):
+    W, H = 1920, 1080
+    box = (12, 108, 864, 1026)
+    # 6 frames: overlays 0 and 1 have the SAME rectangle, overlay 2 another one
+    k, ids, launch, lists = pack(hooks, W, H, [0, 0, 1, 1, 2, 2], [box, box, (12, 100, 800, 900)],
+                                 [1920] * 6)
+    assert ids[0] == ids[1] == ids[2] == ids[3]          # one layout per overlay, one id per band list
+    assert ids[4] == ids[5] != ids[0]
+    assert k == 1 and set(launch) == {0} and lists == 2   # one launch, two band lists
+    # another stride is another layout (and another launch: strides are per launch)
+    k, ids, launch, lists = pack(hooks, W, H, [0, 0, 0], [box], [1920, 2048, 1920])
+    assert ids[0] == ids[2] != ids[1]
+    assert k == 2 and launch[0] == launch[2] != launch[1]
+
+
+def test_multi_launch_limits(hooks):
+    W, H = 1920, 1080
+    # 100 frames of ONE layout: 64 frames per launch
+    k, ids, launch, lists = pack(hooks, W, H, [0] * 100, [(12, 108, 864, 1026)], [1920] * 100)
+    assert len(set(ids)) == 1 and k == 2 and lists == 2
+    assert launch.count(0) == 64 and launch.count(1) == 36
+    # 60 distinct layouts of 5 bands each (copy rows above, copy | one | copy, copy rows below)
+    # = 300 bands: one launch; 9 bands each (two text lines of different width) would not fit 576
+    rects = [(10 + i % 7, 100 + i, 800 + i, 900 + i) for i in range(60)]
+    k, ids, launch, lists = pack(hooks, W, H, list(range(60)), rects, [1920] * 60)
+    assert len(set(ids)) == 60 and k == 1 and lists == 60
+    rects = [(10 + i % 7, 100 + i, 40 + 6 * i, 60 + 6 * i) for i in range(64)]
+    k, ids, launch, lists = pack(hooks, W, H, list(range(64)) * 2, rects, [1920] * 128)
+    # 128 frames, 64 layouts x 5 bands = 320 bands: frames cap (64) decides -> 2 launches,
+    # and the second pass over the same overlays reuses the band lists already in a launch
+    assert k == 2 and lists in (64, 128) and launch.count(0) == 64 and launch.count(1) == 64
