@@ -186,7 +186,7 @@ def run_cpu_baseline(cfg, wl, target_s=12.0):
                       f"-O3 -march=native, {cores} pthreads, {t:.1f} s"}
 
 
-def run_reference_arm(args, cfg, wl, dist, device, world, rank):
+def run_reference_arm(args, cfg, wl, dist, device, world, rank, real_stdout):
     """--impl reference: the reference's CPU implementation of the path (oracle port; GStreamer
     cannot be installed here) on all host threads. Rank 0 only."""
     if rank != 0:
@@ -214,12 +214,23 @@ def run_reference_arm(args, cfg, wl, dist, device, world, rank):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
 
 
 # ---------------------------------------------------------------------------
 
+def protect_stdout():
+    """stdout carries exactly one JSON line. Native libraries (NCCL prints its version there) write
+    to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and
+    the line goes to a private duplicate of the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -244,7 +255,7 @@ def main():
     dist, device, world, rank, local = dist_setup(args.gpus)
 
     if args.impl == "reference":
-        run_reference_arm(args, cfg, wl, dist, device, world, rank)
+        run_reference_arm(args, cfg, wl, dist, device, world, rank, real_stdout)
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -416,7 +427,7 @@ def main():
                "one_synchronous_call_per_frame": sync_fps,
                "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps,
                "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
-               "steps": e2e_steps, "launches": st2["launches"],
+               "steps": e2e_steps, "launches": st2["launches"], "host_frames_numa_node": ctx.numa_node(),
                "api": "fluc_ttmlblend_blend_host_many on pinned host frames, in place: the kernel reads the rows "
                       "under the cue regions from host memory and writes them back over PCIe (zero copy), "
                       "one launch per batch; two sets of host frames alternate so that a batch is "
@@ -453,7 +464,7 @@ def main():
         }
         if inplace:
             line["inplace"] = inplace
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

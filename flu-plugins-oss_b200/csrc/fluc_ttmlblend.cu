@@ -17,6 +17,9 @@
  */
 #include "ttmlblend_internal.h"
 
+#include <ctype.h>
+#include <sched.h>
+
 using namespace tbh;
 
 struct _FlucTtmlBlend {
@@ -64,6 +67,80 @@ fluc_ttmlblend_device_count (void)
   }
   return n;
 }
+
+/* The NUMA node of the GPU and its CPUs, from sysfs (Linux; silently nothing elsewhere). */
+static void
+find_numa_cpus (Ctx *c)
+{
+  const char *e = getenv ("FLUC_TTMLBLEND_NUMA");
+  if (e && atoi (e) == 0)
+    return;
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId (bus, sizeof bus, c->device) != cudaSuccess) {
+    cudaGetLastError ();
+    return;
+  }
+  for (char *p = bus; *p; p++)
+    *p = (char) tolower ((unsigned char) *p);
+  char path[128];
+  snprintf (path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen (path, "r");
+  int node = -1;
+  if (f) {
+    if (fscanf (f, "%d", &node) != 1)
+      node = -1;
+    fclose (f);
+  }
+  if (node < 0)
+    return;
+  snprintf (path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen (path, "r");
+  if (!f)
+    return;
+  char list[4096] = "";
+  if (!fgets (list, sizeof list, f))
+    list[0] = 0;
+  fclose (f);
+  for (char *tok = strtok (list, ",\n"); tok; tok = strtok (nullptr, ",\n")) {
+    int a = -1, b = -1;
+    if (sscanf (tok, "%d-%d", &a, &b) == 2) {
+      for (int i = a; i <= b && i < CPU_SETSIZE; i++)
+        c->numa_cpus.push_back (i);
+    } else if (sscanf (tok, "%d", &a) == 1 && a < CPU_SETSIZE) {
+      c->numa_cpus.push_back (a);
+    }
+  }
+  if (!c->numa_cpus.empty ())
+    c->numa_node = node;
+  TBLOG (1, "device %d (%s) is on NUMA node %d, %zu CPUs", c->device, bus, node, c->numa_cpus.size ());
+}
+
+/* Runs the calling thread on the GPU's NUMA node for the lifetime of the object (first-touch /
+ * local allocation policy then places pinned pages there); the previous affinity comes back. */
+struct NumaScope {
+  cpu_set_t old_set;
+  bool moved = false;
+  explicit NumaScope (const Ctx *c)
+  {
+    if (c->numa_cpus.empty () || sched_getaffinity (0, sizeof old_set, &old_set) != 0)
+      return;
+    cpu_set_t want;
+    CPU_ZERO (&want);
+    int n = 0;
+    for (int cpu : c->numa_cpus)
+      if (CPU_ISSET (cpu, &old_set)) {    /* stay inside what the process is allowed (cgroups, taskset) */
+        CPU_SET (cpu, &want);
+        n++;
+      }
+    if (n && sched_setaffinity (0, sizeof want, &want) == 0)
+      moved = true;
+  }
+  ~NumaScope ()
+  {
+    if (moved)
+      sched_setaffinity (0, sizeof old_set, &old_set);
+  }
+};
 
 /* Streams, events and the memory pool fluc_ttmlblend_new creates (also its failure path). */
 static void
@@ -161,6 +238,7 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->host_mode = std::max (0, std::min (2, atoi (e)));
   if ((e = getenv ("FLUC_TTMLBLEND_LINGER_US")))
     c->linger_us = (uint32_t) std::max (0, atoi (e));
+  find_numa_cpus (c);
   c->sched = std::thread (scheduler_main, c);
   *out = t;
   TBLOG (1, "context on device %d", device);
@@ -232,6 +310,12 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
     destroy_cuda_objects (c);
   }
   delete thiz;
+}
+
+int
+fluc_ttmlblend_numa_node (FlucTtmlBlend *thiz)
+{
+  return thiz ? thiz->c.numa_node : -1;
 }
 
 const char *
@@ -850,10 +934,12 @@ fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt,
     off += (size_t) p.frame.stride[pl] * plane_rows (fmt, pl, H);
   }
   p.bytes = off;
-  if (on_host)
+  if (on_host) {
+    NumaScope numa (c);         /* pages next to the GPU's PCIe root */
     CU (c, cudaHostAlloc (&p.base, off, cudaHostAllocDefault));
-  else
+  } else {
     CU (c, cudaMalloc (&p.base, off));
+  }
   for (int pl = 0; pl < n_planes; pl++) {
     p.frame.plane[pl] = static_cast<uint8_t *> (p.base) + plane_off[pl];
     if (on_host)

@@ -359,6 +359,11 @@ struct Ctx {
   int next_lane = 0;
   std::map<uint64_t, int> lane_tickets;
 
+  /* CPUs of the NUMA node the GPU hangs off (empty: unknown / disabled). Pinned host frames are
+   * allocated with the calling thread moved there for the moment, so that their pages are local
+   * to the GPU's PCIe root and zero-copy traffic does not cross the socket interconnect. */
+  std::vector<int> numa_cpus;
+  int numa_node = -1;
   std::vector<PoolEntry> pool_free, pool_used;
   std::unordered_set<const void *> pinned_planes;   /* plane pointers of the pinned host pool frames */
   uint8_t *scrub = nullptr;

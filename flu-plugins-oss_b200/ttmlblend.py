@@ -77,6 +77,7 @@ PROTOTYPES = {
     "fluc_ttmlblend_strerror": (C.c_char_p, [C.c_int]),
     "fluc_ttmlblend_last_cuda_error": (C.c_char_p, [C.c_void_p]),
     "fluc_ttmlblend_device_count": (C.c_int, []),
+    "fluc_ttmlblend_numa_node": (C.c_int, [C.c_void_p]),
     "fluc_ttmlblend_version": (C.c_char_p, []),
     "fluc_ttmlblend_multi_new": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
     "fluc_ttmlblend_multi_free": (None, [C.c_void_p]),
@@ -278,6 +279,9 @@ class TtmlBlend:
             detail = self.lib.fluc_ttmlblend_strerror(rc).decode()
             cuda = self.lib.fluc_ttmlblend_last_cuda_error(self.h).decode() if self.h else ""
             raise TtmlBlendError(rc, what, f"{detail}; {cuda}" if cuda else detail)
+
+    def numa_node(self) -> int:
+        return self.lib.fluc_ttmlblend_numa_node(self.h)
 
     # -- overlay cache ---------------------------------------------------
     def overlay_set(self, stream: int, bgra: np.ndarray, rects: Iterable[Sequence[int]] = ()):

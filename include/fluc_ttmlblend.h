@@ -155,6 +155,9 @@ FLUC_EXPORT const char *fluc_ttmlblend_strerror (int err);
 /* Text of the last CUDA error seen by this context ("" if none). */
 FLUC_EXPORT const char *fluc_ttmlblend_last_cuda_error (FlucTtmlBlend *thiz);
 FLUC_EXPORT int fluc_ttmlblend_device_count (void);
+/* NUMA node of the context's GPU (-1: unknown or FLUC_TTMLBLEND_NUMA=0). Pinned pool frames
+ * (frame_pool_acquire with on_host) are allocated on that node. */
+FLUC_EXPORT int fluc_ttmlblend_numa_node (FlucTtmlBlend *thiz);
 FLUC_EXPORT const char *fluc_ttmlblend_version (void);
 
 /* ---- several GPUs in one process --------------------------------------
