@@ -112,6 +112,65 @@ def test_256_streams_each_with_its_own_cue(ctx):
         ctx.set_batch(32, 200)
 
 
+def test_256_streams_with_glyph_only_cues_of_different_layouts(ctx):
+    """Config 5 at full size (256 x 1080p I420, one frame per stream and step) when every
+    stream's cue has no background box and its own line widths: after the auto-crop the band
+    lists differ per stream, and the batch travels as multi-layout launches of up to 64 frames.
+    A sample of streams against the oracle, every stream against properties that need no
+    oracle: rows outside the region box are copied, and blending the result's source again
+    out of place gives the same bytes (the launch composition does not matter)."""
+    import dataclasses
+    cfg5 = wl.CONFIGS[5]
+    cfg = dataclasses.replace(cfg5, regions=[dataclasses.replace(cfg5.regions[0], bg=(0, 0, 0, 0))])
+    r = cfg.regions[0]
+    n, distinct = 256, 48
+    rng = np.random.default_rng(5)
+    ovs = []
+    for k in range(distinct):
+        ov = wl.overlay_for(cfg, stream=k)
+        ov[r.y:r.y + r.h // 2, r.x + int(rng.integers(r.w // 4, r.w)):] = 0
+        ov[r.y + r.h // 2:r.y + r.h, r.x + int(rng.integers(r.w // 4, r.w)):] = 0
+        ovs.append(ov)
+    ctx.set_batch(256, 0)
+    try:
+        for s in range(n):
+            ctx.overlay_set(2000 + s, ovs[s % distinct], wl.region_rects(cfg))
+        base = wl.frame_for(cfg, 0)
+        srcs = [ctx.acquire(cfg.fmt, cfg.width, cfg.height) for _ in range(n)]
+        dsts = [ctx.acquire(cfg.fmt, cfg.width, cfg.height) for _ in range(n)]
+        for s_ in srcs:
+            s_.upload(base)
+        ctx.sync()
+        ctx.stats_reset()
+        tk = ctx.submit_many(ctx.Batch([2000 + s for s in range(n)], cfg.fmt, cfg.width, cfg.height,
+                                       [s_.c for s_ in srcs], [d.c for d in dsts]))
+        ctx.wait(tk[n - 1])
+        st = ctx.stats()
+        assert st["frames_blended"] == n and st["multi_launches"] >= 4 and st["launches"] <= 8, st
+        outs = {}
+        for s in (0, 1, 47, 48, 100, 255):
+            outs[s] = dsts[s].download()
+            want = oracle_blend(cfg.fmt, cfg.width, cfg.height, copy_planes(base),
+                                oracle.ttmlrender_rectangles(ovs[s % distinct]))
+            assert_planes_equal(outs[s], want, f"stream {s}")
+        assert_planes_equal(outs[48], outs[0], "same cue, different launch")     # 48 % 48 == 0
+        for s in range(0, n, 5):
+            out = outs.get(s) or dsts[s].download()
+            assert np.array_equal(out[0][:r.y], base[0][:r.y]) and np.array_equal(out[0][r.y + r.h:], base[0][r.y + r.h:])
+            assert np.array_equal(out[1][:r.y // 2], base[1][:r.y // 2])
+            assert not np.array_equal(out[0][r.y:r.y + r.h], base[0][r.y:r.y + r.h])
+            one = ctx.acquire(cfg.fmt, cfg.width, cfg.height)
+            ctx.wait(ctx.submit(2000 + s, cfg.fmt, cfg.width, cfg.height, srcs[s].c, one.c))
+            assert_planes_equal(one.download(), out, f"stream {s} alone vs in the batch")
+            one.release()
+        for f in srcs + dsts:
+            f.release()
+        for s in range(n):
+            ctx.overlay_clear(2000 + s)
+    finally:
+        ctx.set_batch(32, 200)
+
+
 @pytest.mark.parametrize("mode", ["0", "1", "2"])
 @pytest.mark.parametrize("fmt,w,h", [("NV12", 1920, 1080), ("I420", 1279, 719), ("BGRA", 640, 360)])
 def test_host_modes_agree(monkeypatch, mode, fmt, w, h):
