@@ -142,13 +142,39 @@ prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Pr
         return rc;
       ref.a = a;
       ref.c = col;
-      pp.mode = format == FLUC_TTMLBLEND_FORMAT_YUY2 ? PM_YUY2 : PM_UYVY;
+      pp.mode = format == FLUC_TTMLBLEND_FORMAT_YUY2 ? PM_YUY2 : format == FLUC_TTMLBLEND_FORMAT_UYVY ? PM_UYVY :
+          format == FLUC_TTMLBLEND_FORMAT_YVYU ? PM_YVYU : PM_VYUY;
       pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
       pp.out_pitch = ref.pitch;
       pp.v0 = ref.v0;
       pp.row0 = cy0;
       pp.rows = cy1 - cy0;
       CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
+      c->stats.prepare_launches++;
+      P->h_rects[0].push_back (ref);
+    } else if (kind == PK_PLANE8 && format_packed_444_3 (format)) {
+      /* v308 / IYU2: one plane, three bytes per pixel, every byte its own alpha + colour */
+      RectRef ref = {};
+      ref.v0 = (3 * cx0) / 16;
+      ref.v1 = ceil_div (3 * cx1, 16);
+      ref.y0 = cy0;
+      ref.y1 = cy1;
+      ref.pitch = (ref.v1 - ref.v0) * 16;
+      ref.ga = 255;
+      const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+      uint8_t *a, *col;
+      int rc;
+      if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &col)))
+        return rc;
+      ref.a = a;
+      ref.c = col;
+      pp.mode = format == FLUC_TTMLBLEND_FORMAT_v308 ? PM_V308 : PM_IYU2;
+      pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
+      pp.out_pitch = ref.pitch;
+      pp.v0 = ref.v0;
+      pp.row0 = cy0;
+      pp.rows = cy1 - cy0;
+      CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
       c->stats.prepare_launches++;
       P->h_rects[0].push_back (ref);
     } else if (kind == PK_PLANE8) {
@@ -229,7 +255,8 @@ prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Pr
           int rc;
           if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &uv)))
             return rc;
-          pp.mode = format == FLUC_TTMLBLEND_FORMAT_NV21 ? PM_CHROMA_VU : PM_CHROMA_UV;
+          pp.mode = (format == FLUC_TTMLBLEND_FORMAT_NV21 || format == FLUC_TTMLBLEND_FORMAT_NV61) ?
+              PM_CHROMA_VU : PM_CHROMA_UV;
           pp.out_a = a; pp.out_c = uv; pp.out_c2 = nullptr;
           pp.out_pitch = ref.pitch;
           pp.v0 = ref.v0;

@@ -68,6 +68,7 @@ format_sub_x (int f)
     case FLUC_TTMLBLEND_FORMAT_NV21:
     case FLUC_TTMLBLEND_FORMAT_Y42B:
     case FLUC_TTMLBLEND_FORMAT_NV16:
+    case FLUC_TTMLBLEND_FORMAT_NV61:
       return 2;
     default:
       return 1;
@@ -91,7 +92,15 @@ format_sub_y (int f)
 inline bool
 format_packed_422 (int f)
 {
-  return f == FLUC_TTMLBLEND_FORMAT_YUY2 || f == FLUC_TTMLBLEND_FORMAT_UYVY;
+  return f == FLUC_TTMLBLEND_FORMAT_YUY2 || f == FLUC_TTMLBLEND_FORMAT_UYVY ||
+      f == FLUC_TTMLBLEND_FORMAT_YVYU || f == FLUC_TTMLBLEND_FORMAT_VYUY;
+}
+
+/* packed 4:4:4 with three bytes per pixel (no alpha byte) */
+inline bool
+format_packed_444_3 (int f)
+{
+  return f == FLUC_TTMLBLEND_FORMAT_v308 || f == FLUC_TTMLBLEND_FORMAT_IYU2;
 }
 
 inline int
@@ -106,6 +115,7 @@ format_planes (int f)
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
     case FLUC_TTMLBLEND_FORMAT_NV16:
+    case FLUC_TTMLBLEND_FORMAT_NV61:
     case FLUC_TTMLBLEND_FORMAT_NV24:
       return 2;
     default:
@@ -124,6 +134,7 @@ plane_row_bytes (int f, int plane, int w)
     case FLUC_TTMLBLEND_FORMAT_NV12:
     case FLUC_TTMLBLEND_FORMAT_NV21:
     case FLUC_TTMLBLEND_FORMAT_NV16:
+    case FLUC_TTMLBLEND_FORMAT_NV61:
       return plane == 0 ? w : 2 * ((w + 1) / 2);
     case FLUC_TTMLBLEND_FORMAT_NV24:
       return plane == 0 ? w : 2 * w;
@@ -132,7 +143,12 @@ plane_row_bytes (int f, int plane, int w)
       return w;
     case FLUC_TTMLBLEND_FORMAT_YUY2:
     case FLUC_TTMLBLEND_FORMAT_UYVY:
+    case FLUC_TTMLBLEND_FORMAT_YVYU:
+    case FLUC_TTMLBLEND_FORMAT_VYUY:
       return 4 * ((w + 1) / 2);     /* whole macropixels */
+    case FLUC_TTMLBLEND_FORMAT_v308:
+    case FLUC_TTMLBLEND_FORMAT_IYU2:
+      return 3 * w;
     default:
       return 4 * w;
   }

@@ -885,8 +885,30 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
       p.out_c[orow + 2 * i + 1] = p.mode == PM_CHROMA_UV ? v : u;
       break;
     }
+    case PM_V308:
+    case PM_IYU2:{
+      /* thread = one byte of the row: pixel = byte / 3, channel = byte % 3 */
+      const int byte = p.v0 * 16 + i, x = byte / 3, ch = byte - 3 * x, y = p.row0 + r;
+      uint8_t a = 0, c = 0;
+      if (x >= p.cx0 && x < p.cx1) {
+        const Ayuv s = bgra_to_ayuv (raw_px (p, x, y), premul);
+        const int asrc = s.a * p.ga / 255;
+        if (asrc) {
+          a = (uint8_t) asrc;
+          if (p.mode == PM_V308)
+            c = (uint8_t) (ch == 0 ? s.y : ch == 1 ? s.u : s.v);
+          else
+            c = (uint8_t) (ch == 0 ? s.u : ch == 1 ? s.y : s.v);
+        }
+      }
+      p.out_a[orow + i] = a;
+      p.out_c[orow + i] = c;
+      break;
+    }
     case PM_YUY2:
-    case PM_UYVY:{
+    case PM_UYVY:
+    case PM_YVYU:
+    case PM_VYUY:{
       /* packed 4:2:2: thread = macropixel; both lumas, chroma from the even pixel */
       const int x0 = 2 * (p.v0 * 4 + i), y = p.row0 + r;
       uint8_t a0 = 0, a1 = 0, y0 = 0, y1 = 0, u = 0, v = 0;
@@ -912,9 +934,15 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
       if (p.mode == PM_YUY2) {
         al = make_uchar4 (a0, a0, a1, a0);
         co = make_uchar4 (y0, u, y1, v);
-      } else {
+      } else if (p.mode == PM_YVYU) {
+        al = make_uchar4 (a0, a0, a1, a0);
+        co = make_uchar4 (y0, v, y1, u);
+      } else if (p.mode == PM_UYVY) {
         al = make_uchar4 (a0, a0, a0, a1);
         co = make_uchar4 (u, y0, v, y1);
+      } else {
+        al = make_uchar4 (a0, a0, a0, a1);
+        co = make_uchar4 (v, y0, u, y1);
       }
       reinterpret_cast<uchar4 *> (p.out_a + orow)[i] = al;
       reinterpret_cast<uchar4 *> (p.out_c + orow)[i] = co;

@@ -171,7 +171,11 @@ enum PrepareMode : int32_t {
   PM_PACKED_RGBA = 7,
   PM_PACKED_BGRA = 8,
   PM_YUY2 = 9,          /* one plane, macropixels Y0 U Y1 V: out_a / out_c per byte */
-  PM_UYVY = 10          /* macropixels U Y0 V Y1 */
+  PM_UYVY = 10,         /* macropixels U Y0 V Y1 */
+  PM_YVYU = 11,         /* macropixels Y0 V Y1 U */
+  PM_VYUY = 12,         /* macropixels V Y0 U Y1 */
+  PM_V308 = 13,         /* 3 bytes per pixel Y U V: out_a / out_c per byte, one thread per byte */
+  PM_IYU2 = 14          /* 3 bytes per pixel U Y V */
 };
 
 /* All jobs of one launch share one PlaneKind and one variant: fast (every

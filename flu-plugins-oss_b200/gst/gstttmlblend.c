@@ -64,7 +64,7 @@ enum
   PROP_DEVICE
 };
 
-#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8, NV16, NV24 }"
+#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8, NV16, NV24, NV61, YVYU, VYUY, v308, IYU2 }"
 
 static GstStaticPadTemplate video_sink_template = GST_STATIC_PAD_TEMPLATE ("sink",
     GST_PAD_SINK, GST_PAD_ALWAYS,
@@ -144,6 +144,11 @@ to_fluc_format (GstVideoFormat f)
     case GST_VIDEO_FORMAT_GRAY8: return FLUC_TTMLBLEND_FORMAT_GRAY8;
     case GST_VIDEO_FORMAT_NV16: return FLUC_TTMLBLEND_FORMAT_NV16;
     case GST_VIDEO_FORMAT_NV24: return FLUC_TTMLBLEND_FORMAT_NV24;
+    case GST_VIDEO_FORMAT_NV61: return FLUC_TTMLBLEND_FORMAT_NV61;
+    case GST_VIDEO_FORMAT_YVYU: return FLUC_TTMLBLEND_FORMAT_YVYU;
+    case GST_VIDEO_FORMAT_VYUY: return FLUC_TTMLBLEND_FORMAT_VYUY;
+    case GST_VIDEO_FORMAT_v308: return FLUC_TTMLBLEND_FORMAT_v308;
+    case GST_VIDEO_FORMAT_IYU2: return FLUC_TTMLBLEND_FORMAT_IYU2;
     default: return FLUC_TTMLBLEND_FORMAT_COUNT;
   }
 }

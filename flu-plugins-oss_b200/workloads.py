@@ -93,7 +93,7 @@ def plane_shapes(fmt: str, width: int, height: int):
         return [(height, width), (ch, cw), (ch, cw)]
     if f in ("NV12", "NV21"):
         return [(height, width), (ch, 2 * cw)]
-    if f == "NV16":
+    if f in ("NV16", "NV61"):
         return [(height, width), (height, 2 * cw)]
     if f == "NV24":
         return [(height, width), (height, 2 * width)]
@@ -101,8 +101,10 @@ def plane_shapes(fmt: str, width: int, height: int):
         return [(height, width), (height, cw), (height, cw)]
     if f == "Y444":
         return [(height, width)] * 3
-    if f in ("YUY2", "UYVY"):
+    if f in ("YUY2", "UYVY", "YVYU", "VYUY"):
         return [(height, 4 * cw)]
+    if f in ("V308", "IYU2"):
+        return [(height, 3 * width)]
     if f == "GRAY8":
         return [(height, width)]
     return [(height, 4 * width)]

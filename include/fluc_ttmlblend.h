@@ -78,6 +78,11 @@ typedef enum {
   FLUC_TTMLBLEND_FORMAT_GRAY8 = 17,
   FLUC_TTMLBLEND_FORMAT_NV16 = 18,      /* semi-planar 4:2:2 */
   FLUC_TTMLBLEND_FORMAT_NV24 = 19,      /* semi-planar 4:4:4 */
+  FLUC_TTMLBLEND_FORMAT_NV61 = 20,      /* NV16 with V before U */
+  FLUC_TTMLBLEND_FORMAT_YVYU = 21,      /* packed 4:2:2, bytes Y0 V Y1 U */
+  FLUC_TTMLBLEND_FORMAT_VYUY = 22,      /* packed 4:2:2, bytes V Y0 U Y1 */
+  FLUC_TTMLBLEND_FORMAT_v308 = 23,      /* packed 4:4:4, 3 bytes per pixel: Y U V */
+  FLUC_TTMLBLEND_FORMAT_IYU2 = 24,      /* packed 4:4:4, 3 bytes per pixel: U Y V */
   FLUC_TTMLBLEND_FORMAT_COUNT
 } FlucTtmlBlendFormat;
 
@@ -122,7 +127,7 @@ typedef struct {
 } FlucTtmlBlendRectangle;
 
 /* Plane pointers + strides of one frame (GstVideoFrame data[]/stride[]).
- * I420 / Y42B / Y444: Y,U,V. YV12: Y,V,U. NV12/NV21/NV16/NV24: Y,UV. Packed formats, GRAY8: plane[0]. */
+ * I420 / Y42B / Y444: Y,U,V. YV12: Y,V,U. NV12/NV21/NV16/NV61/NV24: Y,UV. Packed formats, GRAY8: plane[0]. */
 typedef struct {
   void *plane[3];
   int32_t stride[3];

@@ -40,7 +40,23 @@ is_yuv (int32_t f)
       f == TBREF_FORMAT_NV21 || f == TBREF_FORMAT_Y42B ||
       f == TBREF_FORMAT_Y444 || f == TBREF_FORMAT_YUY2 ||
       f == TBREF_FORMAT_UYVY || f == TBREF_FORMAT_GRAY8 ||
-      f == TBREF_FORMAT_NV16 || f == TBREF_FORMAT_NV24;
+      f == TBREF_FORMAT_NV16 || f == TBREF_FORMAT_NV24 ||
+      f == TBREF_FORMAT_NV61 || f == TBREF_FORMAT_YVYU ||
+      f == TBREF_FORMAT_VYUY || f == TBREF_FORMAT_v308 ||
+      f == TBREF_FORMAT_IYU2;
+}
+
+/* packed 4:2:2: byte positions of the first luma (the second is 2 further), U and V inside
+ * a macropixel -- unpack_/pack_ YUY2, UYVY, YVYU, VYUY of video-format.c */
+static void
+packed_422_order (int32_t f, int *oy, int *ou, int *ov)
+{
+  switch (f) {
+    case TBREF_FORMAT_YUY2: *oy = 0; *ou = 1; *ov = 3; break;
+    case TBREF_FORMAT_UYVY: *oy = 1; *ou = 0; *ov = 2; break;
+    case TBREF_FORMAT_YVYU: *oy = 0; *ou = 3; *ov = 1; break;
+    default: *oy = 1; *ou = 2; *ov = 0; break;      /* VYUY */
+  }
 }
 
 int32_t
@@ -56,6 +72,7 @@ tbref_n_planes (int32_t f)
     case TBREF_FORMAT_NV21:
     case TBREF_FORMAT_NV16:
     case TBREF_FORMAT_NV24:
+    case TBREF_FORMAT_NV61:
       return 2;
     default:
       return 1;
@@ -73,6 +90,7 @@ tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
     case TBREF_FORMAT_NV12:
     case TBREF_FORMAT_NV21:
     case TBREF_FORMAT_NV16:
+    case TBREF_FORMAT_NV61:
       return plane == 0 ? w : 2 * ((w + 1) / 2);
     case TBREF_FORMAT_NV24:
       return plane == 0 ? w : 2 * w;
@@ -81,7 +99,12 @@ tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
       return w;
     case TBREF_FORMAT_YUY2:
     case TBREF_FORMAT_UYVY:
+    case TBREF_FORMAT_YVYU:
+    case TBREF_FORMAT_VYUY:
       return 4 * ((w + 1) / 2);
+    case TBREF_FORMAT_v308:
+    case TBREF_FORMAT_IYU2:
+      return 3 * w;
     default:
       return 4 * w;
   }
@@ -135,15 +158,29 @@ unpack_line (const TbRefFrame *f, int y, uint8_t *d, int width)
       break;
     }
     case TBREF_FORMAT_NV16:
-    case TBREF_FORMAT_NV24:{       /* unpack_NV16 / unpack_NV24: UV interleaved, same line */
-      const int sh = f->format == TBREF_FORMAT_NV16 ? 1 : 0;
+    case TBREF_FORMAT_NV61:
+    case TBREF_FORMAT_NV24:{       /* unpack_NV16 / _NV61 / _NV24: UV (VU) interleaved, same line */
+      const int sh = f->format == TBREF_FORMAT_NV24 ? 0 : 1;
+      const int ou = f->format == TBREF_FORMAT_NV61 ? 1 : 0;
       const uint8_t *sy = f->data[0] + (size_t) f->stride[0] * y;
       const uint8_t *suv = f->data[1] + (size_t) f->stride[1] * y;
       for (x = 0; x < width; x++) {
         d[4 * x + 0] = 0xff;
         d[4 * x + 1] = sy[x];
-        d[4 * x + 2] = suv[(x >> sh) * 2 + 0];
-        d[4 * x + 3] = suv[(x >> sh) * 2 + 1];
+        d[4 * x + 2] = suv[(x >> sh) * 2 + ou];
+        d[4 * x + 3] = suv[(x >> sh) * 2 + (1 - ou)];
+      }
+      break;
+    }
+    case TBREF_FORMAT_v308:
+    case TBREF_FORMAT_IYU2:{       /* unpack_v308 (Y U V) / unpack_IYU2 (U Y V): 3 bytes per pixel */
+      const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
+      const int oy = f->format == TBREF_FORMAT_v308 ? 0 : 1, ou = f->format == TBREF_FORMAT_v308 ? 1 : 0;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = s[3 * x + oy];
+        d[4 * x + 2] = s[3 * x + ou];
+        d[4 * x + 3] = s[3 * x + 2];
       }
       break;
     }
@@ -172,10 +209,12 @@ unpack_line (const TbRefFrame *f, int y, uint8_t *d, int width)
       break;
     }
     case TBREF_FORMAT_YUY2:
-    case TBREF_FORMAT_UYVY:{       /* unpack_YUY2 / unpack_UYVY: macropixels of two pixels */
+    case TBREF_FORMAT_UYVY:
+    case TBREF_FORMAT_YVYU:
+    case TBREF_FORMAT_VYUY:{       /* unpack_YUY2 / _UYVY / _YVYU / _VYUY: macropixels of two pixels */
       const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
-      const int oy = f->format == TBREF_FORMAT_YUY2 ? 0 : 1;   /* Y at 0,2 or 1,3 */
-      const int ou = f->format == TBREF_FORMAT_YUY2 ? 1 : 0, ov = f->format == TBREF_FORMAT_YUY2 ? 3 : 2;
+      int oy, ou, ov;                                          /* Y at oy and oy + 2 */
+      packed_422_order (f->format, &oy, &ou, &ov);
       for (x = 0; x < width; x++) {
         const uint8_t *m = s + 4 * (x >> 1);
         d[4 * x + 0] = 0xff;
@@ -292,20 +331,33 @@ pack_line (TbRefFrame *f, int y, const uint8_t *s, int width)
       }
       break;
     }
-    case TBREF_FORMAT_NV16:{       /* pack_NV16: every line, UV from the even pixel */
+    case TBREF_FORMAT_NV16:
+    case TBREF_FORMAT_NV61:{       /* pack_NV16 / pack_NV61: every line, UV (VU) from the even pixel */
+      const int ou = f->format == TBREF_FORMAT_NV61 ? 1 : 0;
       uint8_t *dy = f->data[0] + (size_t) f->stride[0] * y;
       uint8_t *duv = f->data[1] + (size_t) f->stride[1] * y;
       for (i = 0; i < width / 2; i++) {
         dy[i * 2 + 0] = s[i * 8 + 1];
         dy[i * 2 + 1] = s[i * 8 + 5];
-        duv[i * 2 + 0] = s[i * 8 + 2];
-        duv[i * 2 + 1] = s[i * 8 + 3];
+        duv[i * 2 + ou] = s[i * 8 + 2];
+        duv[i * 2 + (1 - ou)] = s[i * 8 + 3];
       }
       if (width & 1) {
         i = width - 1;
         dy[i] = s[i * 4 + 1];
-        duv[i + 0] = s[i * 4 + 2];
-        duv[i + 1] = s[i * 4 + 3];
+        duv[i + ou] = s[i * 4 + 2];
+        duv[i + (1 - ou)] = s[i * 4 + 3];
+      }
+      break;
+    }
+    case TBREF_FORMAT_v308:
+    case TBREF_FORMAT_IYU2:{       /* pack_v308 / pack_IYU2: the alpha is dropped */
+      uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
+      const int oy = f->format == TBREF_FORMAT_v308 ? 0 : 1, ou = f->format == TBREF_FORMAT_v308 ? 1 : 0;
+      for (x = 0; x < width; x++) {
+        d[3 * x + oy] = s[4 * x + 1];
+        d[3 * x + ou] = s[4 * x + 2];
+        d[3 * x + 2] = s[4 * x + 3];
       }
       break;
     }
@@ -349,11 +401,13 @@ pack_line (TbRefFrame *f, int y, const uint8_t *s, int width)
       break;
     }
     case TBREF_FORMAT_YUY2:
-    case TBREF_FORMAT_UYVY:{       /* pack_YUY2 / pack_UYVY: chroma from the even pixel; an odd
-                                    * last pixel writes its Y, U and V, not the second luma */
+    case TBREF_FORMAT_UYVY:
+    case TBREF_FORMAT_YVYU:
+    case TBREF_FORMAT_VYUY:{       /* pack_YUY2 / _UYVY / _YVYU / _VYUY: chroma from the even pixel; an
+                                    * odd last pixel writes its Y, U and V, not the second luma */
       uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
-      const int oy = f->format == TBREF_FORMAT_YUY2 ? 0 : 1;
-      const int ou = f->format == TBREF_FORMAT_YUY2 ? 1 : 0, ov = f->format == TBREF_FORMAT_YUY2 ? 3 : 2;
+      int oy, ou, ov;
+      packed_422_order (f->format, &oy, &ou, &ov);
       for (i = 0; i < width / 2; i++) {
         d[i * 4 + oy] = s[i * 8 + 1];
         d[i * 4 + oy + 2] = s[i * 8 + 5];
@@ -538,7 +592,7 @@ tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src)
 
   if (!dest || !src || !src->pixels)
     return 0;
-  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_NV24 ||
+  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_IYU2 ||
       (dest->format > TBREF_FORMAT_ABGR && dest->format < TBREF_FORMAT_Y42B))
     return 0;
 

@@ -47,7 +47,12 @@ enum {
   TBREF_FORMAT_UYVY = 16,
   TBREF_FORMAT_GRAY8 = 17,
   TBREF_FORMAT_NV16 = 18,
-  TBREF_FORMAT_NV24 = 19
+  TBREF_FORMAT_NV24 = 19,
+  TBREF_FORMAT_NV61 = 20,
+  TBREF_FORMAT_YVYU = 21,
+  TBREF_FORMAT_VYUY = 22,
+  TBREF_FORMAT_v308 = 23,
+  TBREF_FORMAT_IYU2 = 24
 };
 
 #define TBREF_FLAG_PREMULTIPLIED_ALPHA 1u

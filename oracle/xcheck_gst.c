@@ -57,6 +57,11 @@ static const struct {
   { GST_VIDEO_FORMAT_GRAY8, TBREF_FORMAT_GRAY8, "GRAY8" },
   { GST_VIDEO_FORMAT_NV16, TBREF_FORMAT_NV16, "NV16" },
   { GST_VIDEO_FORMAT_NV24, TBREF_FORMAT_NV24, "NV24" },
+  { GST_VIDEO_FORMAT_NV61, TBREF_FORMAT_NV61, "NV61" },
+  { GST_VIDEO_FORMAT_YVYU, TBREF_FORMAT_YVYU, "YVYU" },
+  { GST_VIDEO_FORMAT_VYUY, TBREF_FORMAT_VYUY, "VYUY" },
+  { GST_VIDEO_FORMAT_v308, TBREF_FORMAT_v308, "v308" },
+  { GST_VIDEO_FORMAT_IYU2, TBREF_FORMAT_IYU2, "IYU2" },
 };
 
 /* geometry / flag cases: frame size, rectangle size and position (hanging over every

@@ -50,6 +50,11 @@ VECTORS = [
      True, False),
     ("bgra_scaled", "BGRA", 80, 48, [(25, 12, 10, 20, 0.7, False, 60, 20), (50, 40, 50, 30, 1.0, True, 45, 13)],
      False, False),
+    ("nv61", "NV61", 63, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
+    ("yvyu", "YVYU", 63, 40, [(40, 20, 11, 13, 1.0, True), (9, 9, 57, 35, 1.0, False)], True, False),
+    ("vyuy", "VYUY", 64, 40, [(41, 20, 10, 13, 1.0, True)], True, False),
+    ("v308", "v308", 61, 40, [(40, 20, 11, 13, 1.0, True), (9, 9, 55, 35, 0.5, True)], True, False),
+    ("iyu2", "IYU2", 62, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
 ]
 
 

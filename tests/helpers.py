@@ -10,9 +10,10 @@ import __graft_entry__ as graft
 pkg = graft.load_package()
 wl = pkg.workloads
 
-YUV_FORMATS = ("I420", "YV12", "NV12", "NV21", "AYUV", "Y42B", "Y444", "YUY2", "UYVY", "GRAY8", "NV16", "NV24")
 PLANAR_420 = ("I420", "YV12", "NV12", "NV21")
-MORE_YUV = ("Y42B", "Y444", "YUY2", "UYVY", "GRAY8", "NV16", "NV24")       # byte-plane formats beyond 4:2:0
+# byte-plane formats beyond 4:2:0 (GStreamer spells v308 in lower case)
+MORE_YUV = ("Y42B", "Y444", "YUY2", "UYVY", "GRAY8", "NV16", "NV24", "NV61", "YVYU", "VYUY", "v308", "IYU2")
+YUV_FORMATS = tuple(f.upper() for f in PLANAR_420 + ("AYUV",) + MORE_YUV)
 PACKED = ("AYUV", "ARGB", "ABGR", "RGBA", "BGRA")
 ALL_FORMATS = PLANAR_420 + PACKED + MORE_YUV
 
@@ -30,6 +31,16 @@ def yuv_views(fmt, planes, w):
         return planes[0], planes[1][:, 1::2], planes[1][:, 0::2], 2, 2
     if fmt == "NV16":
         return planes[0], planes[1][:, 0::2], planes[1][:, 1::2], 2, 1
+    if fmt == "NV61":
+        return planes[0], planes[1][:, 1::2], planes[1][:, 0::2], 2, 1
+    if fmt == "YVYU":
+        return planes[0][:, 0::2][:, :w], planes[0][:, 3::4], planes[0][:, 1::4], 2, 1
+    if fmt == "VYUY":
+        return planes[0][:, 1::2][:, :w], planes[0][:, 2::4], planes[0][:, 0::4], 2, 1
+    if fmt == "V308":
+        return planes[0][:, 0::3], planes[0][:, 1::3], planes[0][:, 2::3], 1, 1
+    if fmt == "IYU2":
+        return planes[0][:, 1::3], planes[0][:, 0::3], planes[0][:, 2::3], 1, 1
     if fmt == "NV24":
         return planes[0], planes[1][:, 0::2], planes[1][:, 1::2], 1, 1
     if fmt == "YUY2":
