@@ -152,8 +152,9 @@ prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Pr
       CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
       c->stats.prepare_launches++;
       P->h_rects[0].push_back (ref);
-    } else if (kind == PK_PLANE8 && format_packed_444_3 (format)) {
-      /* v308 / IYU2: one plane, three bytes per pixel, every byte its own alpha + colour */
+    } else if (kind == PK_PLANE8_RGB || (kind == PK_PLANE8 && format_packed_444_3 (format))) {
+      /* v308 / IYU2 / RGB / BGR: one plane, three bytes per pixel, every byte its own alpha +
+       * colour; the RGB pair keeps the source colours and the rectangle's flags for the blend */
       RectRef ref = {};
       ref.v0 = (3 * cx0) / 16;
       ref.v1 = ceil_div (3 * cx1, 16);
@@ -168,7 +169,12 @@ prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Pr
         return rc;
       ref.a = a;
       ref.c = col;
-      pp.mode = format == FLUC_TTMLBLEND_FORMAT_v308 ? PM_V308 : PM_IYU2;
+      if (kind == PK_PLANE8_RGB) {
+        ref.ga = rr.ga;
+        ref.src_premul = rr.premul ? 1 : 0;
+      }
+      pp.mode = format == FLUC_TTMLBLEND_FORMAT_v308 ? PM_V308 : format == FLUC_TTMLBLEND_FORMAT_IYU2 ? PM_IYU2 :
+          format == FLUC_TTMLBLEND_FORMAT_RGB ? PM_RGB24 : PM_BGR24;
       pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
       pp.out_pitch = ref.pitch;
       pp.v0 = ref.v0;

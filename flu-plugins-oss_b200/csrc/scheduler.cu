@@ -120,7 +120,7 @@ launch_pending (Ctx *c)
   reap_batches (c);
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
-  std::vector<PlaneJob> by_kind[6];     /* PlaneKind x {byte-granular, fast} */
+  std::vector<PlaneJob> by_kind[kPlaneKinds * 2];     /* PlaneKind x {byte-granular, fast} */
   std::vector<Group> &groups = c->groups;
   groups.clear ();
   size_t n_multis = 0;
@@ -162,7 +162,7 @@ launch_pending (Ctx *c)
    * whole-vector windows is going out anyway. */
   {
     size_t n_small = 0, n_table = 0;
-    for (int k = 1; k < 6; k += 2)
+    for (int k = 1; k < kPlaneKinds * 2; k += 2)
       n_table += by_kind[k].size ();
     for (Group &g : groups) {
       g.dissolved = (uint64_t) g.P.n_frames * g.P.chunks_per_frame < (uint64_t) kMinGroupChunks;
@@ -199,7 +199,7 @@ launch_pending (Ctx *c)
   size_t n_launches = n_multis;
   for (Group &g : groups)
     n_launches += g.dissolved ? 0 : 1;
-  for (int k = 0; k < 6; k++)
+  for (int k = 0; k < kPlaneKinds * 2; k++)
     n_launches += !by_kind[k].empty ();
   /* an event pair keeps the batch from overlapping its neighbours (~2 us of stream time):
    * sample every profile_every-th batch. A batch of several launches (several groups /
@@ -233,7 +233,7 @@ launch_pending (Ctx *c)
     if (m.P.flags & JF_LAZY)
       c->stats.lazy_launches++;
   }
-  for (int k = 0; k < 6; k++) {
+  for (int k = 0; k < kPlaneKinds * 2; k++) {
     if (by_kind[k].empty ())
       continue;
     TableSlot &s = c->slots[c->next_slot];

@@ -148,6 +148,8 @@ plane_row_bytes (int f, int plane, int w)
       return 4 * ((w + 1) / 2);     /* whole macropixels */
     case FLUC_TTMLBLEND_FORMAT_v308:
     case FLUC_TTMLBLEND_FORMAT_IYU2:
+    case FLUC_TTMLBLEND_FORMAT_RGB:
+    case FLUC_TTMLBLEND_FORMAT_BGR:
       return 3 * w;
     default:
       return 4 * w;
@@ -171,6 +173,9 @@ plane_kind (int f)
     case FLUC_TTMLBLEND_FORMAT_RGBA:
     case FLUC_TTMLBLEND_FORMAT_BGRA:
       return PK_PACKED_A3;
+    case FLUC_TTMLBLEND_FORMAT_RGB:
+    case FLUC_TTMLBLEND_FORMAT_BGR:
+      return PK_PLANE8_RGB;
     default:
       return PK_PLANE8;
   }

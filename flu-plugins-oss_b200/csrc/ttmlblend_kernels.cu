@@ -119,6 +119,47 @@ blend16_plane8 (uint4 f, const uint4 &a, const uint4 &c)
   return f;
 }
 
+/* PLANE8_RGB (24-bit RGB / BGR frames: no alpha byte, so adst = 255 and final_alpha = 255):
+ * the same per-byte alpha / colour planes as PLANE8, but an RGB destination keeps the source's
+ * premultiplied flag (BLENDSPEC section 2), so there are two operators per rectangle:
+ *   straight source:       (Cs * asrc + Cd * (255 - asrc)) / 255           = the PLANE8 formula
+ *   premultiplied source:  MIN (255, (Cs * ga + Cd * (255 - asrc)) / 255)
+ * With ga == 255 the latter is Cs + (Cd * (255 - asrc)) / 255, saturating: the PLANE8 formula
+ * on colour 0 plus a saturating byte add. ga < 255 needs 17-bit numerators: one byte at a time. */
+__device__ __forceinline__ uint32_t
+blend4_rgb24 (uint32_t f, uint32_t a, uint32_t c, uint32_t ga, bool sp)
+{
+  if (!sp)
+    return blend4_plane8 (f, a, c);
+  if (ga == 255u)
+    return __vaddus4 (blend4_plane8 (f, a, 0u), c);      /* a == 0 bytes: f + 0 (their colour is 0) */
+  uint32_t out = 0u;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const uint32_t as = (a >> k) & 0xffu, cs = (c >> k) & 0xffu, cd = (f >> k) & 0xffu;
+    const uint32_t v = as ? min ((cs * ga + cd * (255u - as)) / 255u, 255u) : cd;
+    out |= v << k;
+  }
+  return out;
+}
+
+__device__ __forceinline__ uint4
+blend16_rgb24 (uint4 f, const uint4 &a, const uint4 &c, uint32_t ga, bool sp)
+{
+  if (a.x) f.x = blend4_rgb24 (f.x, a.x, c.x, ga, sp);
+  if (a.y) f.y = blend4_rgb24 (f.y, a.y, c.y, ga, sp);
+  if (a.z) f.z = blend4_rgb24 (f.z, a.z, c.z, ga, sp);
+  if (a.w) f.w = blend4_rgb24 (f.w, a.w, c.w, ga, sp);
+  return f;
+}
+
+/* kinds whose prepared overlay is an alpha byte plane + a colour byte plane */
+__host__ __device__ constexpr bool
+kind_is_planes (int kind)
+{
+  return kind == PK_PLANE8 || kind == PK_PLANE8_RGB;
+}
+
 /* PACKED: one pixel word, alpha in byte AP, the other three bytes colours.
  * gst_video_blend's BLENDLOOP with the four OVERxy operators. */
 template <int AP>
@@ -212,6 +253,9 @@ blend_with_rect (uint4 f, const RectRef *r, const RectGeom &g, int v, int y,
   if (KIND == PK_PLANE8) {
     const uint4 oc = ld_overlay16 (ldg_ptr (&r->c) + off);
     return blend16_plane8 (f, oa, oc);
+  } else if (KIND == PK_PLANE8_RGB) {
+    const uint4 oc = ld_overlay16 (ldg_ptr (&r->c) + off);
+    return blend16_rgb24 (f, oa, oc, (uint32_t) __ldg (&r->ga), __ldg (&r->src_premul) != 0);
   } else {
     const uint32_t ga = (uint32_t) __ldg (&r->ga);
     const bool sp = __ldg (&r->src_premul) != 0;
@@ -262,7 +306,7 @@ __device__ __forceinline__ bool
 any_alpha (const uint4 &oa)
 {
   const uint32_t m = oa.x | oa.y | oa.z | oa.w;
-  return KIND == PK_PLANE8 ? m != 0u : ((m >> (KIND == PK_PACKED_A0 ? 0 : 24)) & 0xffu) != 0u;
+  return kind_is_planes (KIND) ? m != 0u : ((m >> (KIND == PK_PACKED_A0 ? 0 : 24)) & 0xffu) != 0u;
 }
 
 /* One chunk = kItemsPerChunk consecutive 16-byte vectors of one job. A job is
@@ -340,10 +384,10 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
         asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (bar));
         asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-            :: "r" (bar), "r" (KIND == PK_PLANE8 ? 2u * bytes : bytes) : "memory");
+            :: "r" (bar), "r" (kind_is_planes (KIND) ? 2u * bytes : bytes) : "memory");
         asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
             :: "r" (sm_a), "l" (ldg_ptr (&r->a) + off), "r" (bytes), "r" (bar) : "memory");
-        if (KIND == PK_PLANE8)
+        if (kind_is_planes (KIND))
           asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
               :: "r" (sm_a + kItemsPerChunk * 16), "l" (ldg_ptr (&r->c) + off), "r" (bytes), "r" (bar) : "memory");
       }
@@ -386,6 +430,9 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
           if (KIND == PK_PLANE8) {
             const uint4 oc = *reinterpret_cast<const uint4 *> (ov_smem + kItemsPerChunk * 16 + so);
             out = blend16_plane8 (f[k], oa, oc);
+          } else if (KIND == PK_PLANE8_RGB) {
+            const uint4 oc = *reinterpret_cast<const uint4 *> (ov_smem + kItemsPerChunk * 16 + so);
+            out = blend16_rgb24 (f[k], oa, oc, ga, sp);
           } else {
             out = blend16_packed<KIND == PK_PACKED_A0 ? 0 : 3> (f[k], oa, ga, sp, dp);
           }
@@ -405,8 +452,10 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
       for (int k = 0; k < kUnroll; k++)
         if (act[k])
           f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
-      if (KIND == PK_PLANE8) {
+      if (kind_is_planes (KIND)) {
         const uint8_t *pc = ldg_ptr (&r->c);
+        const uint32_t ga1 = KIND == PK_PLANE8 ? 255u : (uint32_t) __ldg (&r->ga);
+        const bool sp1 = KIND == PK_PLANE8 ? false : __ldg (&r->src_premul) != 0;
 #pragma unroll
         for (int k = 0; k < kUnroll; k++)
           if (act[k]) {
@@ -418,7 +467,8 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
         for (int k = 0; k < kUnroll; k++)
           if (act[k])
             st_frame16 (dst + (size_t) yy[k] * dst_pitch + (size_t) vv[k] * 16,
-                blend16_plane8 (f[k], oa[k], oc[k]));
+                KIND == PK_PLANE8 ? blend16_plane8 (f[k], oa[k], oc[k]) :
+                blend16_rgb24 (f[k], oa[k], oc[k], ga1, sp1));
       } else {
         const uint32_t ga = (uint32_t) __ldg (&r->ga);
         const bool sp = __ldg (&r->src_premul) != 0;
@@ -659,7 +709,7 @@ interleave_lanes (int kind)
   }
   if (env)
     return (uint32_t) env;
-  return kind == PK_PLANE8 ? 1u : 61u;
+  return kind_is_planes (kind) ? 1u : 61u;
 }
 
 template <int KIND>
@@ -712,6 +762,12 @@ launch_group (GroupParams &P, int kind, cudaStream_t stream)
       else
         ttmlblend_group_kernel<PK_PLANE8, false><<<grid, kThreads, smem_plane8, stream>>> (P);
       break;
+    case PK_PLANE8_RGB:
+      if (lazy)
+        ttmlblend_group_kernel<PK_PLANE8_RGB, true><<<grid, kThreads, smem_plane8, stream>>> (P);
+      else
+        ttmlblend_group_kernel<PK_PLANE8_RGB, false><<<grid, kThreads, smem_plane8, stream>>> (P);
+      break;
     case PK_PACKED_A0:
       if (lazy)
         ttmlblend_group_kernel<PK_PACKED_A0, true><<<grid, kThreads, smem_packed, stream>>> (P);
@@ -754,6 +810,12 @@ launch_multi (MultiParams &P, int kind, cudaStream_t stream)
       else
         ttmlblend_multi_kernel<PK_PLANE8, false><<<grid, kThreads, smem_plane8, stream>>> (P);
       break;
+    case PK_PLANE8_RGB:
+      if (lazy)
+        ttmlblend_multi_kernel<PK_PLANE8_RGB, true><<<grid, kThreads, smem_plane8, stream>>> (P);
+      else
+        ttmlblend_multi_kernel<PK_PLANE8_RGB, false><<<grid, kThreads, smem_plane8, stream>>> (P);
+      break;
     case PK_PACKED_A0:
       if (lazy)
         ttmlblend_multi_kernel<PK_PACKED_A0, true><<<grid, kThreads, smem_packed, stream>>> (P);
@@ -781,6 +843,8 @@ launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint3
   switch (kind) {
     case PK_PLANE8:
       return launch_blend_kind<PK_PLANE8> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
+    case PK_PLANE8_RGB:
+      return launch_blend_kind<PK_PLANE8_RGB> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
     case PK_PACKED_A0:
       return launch_blend_kind<PK_PACKED_A0> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
     case PK_PACKED_A3:
@@ -883,6 +947,25 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
       p.out_a[orow + 2 * i + 1] = a;
       p.out_c[orow + 2 * i] = p.mode == PM_CHROMA_UV ? u : v;
       p.out_c[orow + 2 * i + 1] = p.mode == PM_CHROMA_UV ? v : u;
+      break;
+    }
+    case PM_RGB24:
+    case PM_BGR24:{
+      /* thread = one byte of the row; the colour stays as the source has it (premultiplied or
+       * straight: the blend applies the operator that goes with the rectangle's flag) */
+      const int byte = p.v0 * 16 + i, x = byte / 3, ch = byte - 3 * x, y = p.row0 + r;
+      uint8_t a = 0, c = 0;
+      if (x >= p.cx0 && x < p.cx1) {
+        const uint32_t px = raw_px (p, x, y);
+        const int asrc = (int) (px >> 24) * p.ga / 255;
+        if (asrc) {
+          a = (uint8_t) asrc;
+          const int sh = p.mode == PM_RGB24 ? 16 - 8 * ch : 8 * ch;      /* BGRA word: B 0, G 8, R 16 */
+          c = (uint8_t) (px >> sh);
+        }
+      }
+      p.out_a[orow + i] = a;
+      p.out_c[orow + i] = c;
       break;
     }
     case PM_V308:

@@ -31,8 +31,10 @@ namespace tb {
 enum PlaneKind : int32_t {
   PK_PLANE8 = 0,
   PK_PACKED_A0 = 1,
-  PK_PACKED_A3 = 2
+  PK_PACKED_A3 = 2,
+  PK_PLANE8_RGB = 3     /* 24-bit RGB / BGR: PLANE8's byte planes, RGB operators (premultiplied flag kept) */
 };
+constexpr int kPlaneKinds = 4;
 
 enum JobFlags : int32_t {
   JF_VECTOR = 1,        /* src, dst and both pitches are 16-byte aligned */
@@ -175,7 +177,9 @@ enum PrepareMode : int32_t {
   PM_YVYU = 11,         /* macropixels Y0 V Y1 U */
   PM_VYUY = 12,         /* macropixels V Y0 U Y1 */
   PM_V308 = 13,         /* 3 bytes per pixel Y U V: out_a / out_c per byte, one thread per byte */
-  PM_IYU2 = 14          /* 3 bytes per pixel U Y V */
+  PM_IYU2 = 14,         /* 3 bytes per pixel U Y V */
+  PM_RGB24 = 15,        /* 3 bytes per pixel R G B, colour as in the source (no matrix) */
+  PM_BGR24 = 16
 };
 
 /* All jobs of one launch share one PlaneKind and one variant: fast (every

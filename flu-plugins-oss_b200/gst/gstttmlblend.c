@@ -64,7 +64,7 @@ enum
   PROP_DEVICE
 };
 
-#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8, NV16, NV24, NV61, YVYU, VYUY, v308, IYU2 }"
+#define VIDEO_FORMATS "{ I420, YV12, NV12, NV21, AYUV, ARGB, ABGR, RGBA, BGRA, RGBx, BGRx, xRGB, xBGR, Y42B, Y444, YUY2, UYVY, GRAY8, NV16, NV24, NV61, YVYU, VYUY, v308, IYU2, RGB, BGR }"
 
 static GstStaticPadTemplate video_sink_template = GST_STATIC_PAD_TEMPLATE ("sink",
     GST_PAD_SINK, GST_PAD_ALWAYS,
@@ -149,6 +149,8 @@ to_fluc_format (GstVideoFormat f)
     case GST_VIDEO_FORMAT_VYUY: return FLUC_TTMLBLEND_FORMAT_VYUY;
     case GST_VIDEO_FORMAT_v308: return FLUC_TTMLBLEND_FORMAT_v308;
     case GST_VIDEO_FORMAT_IYU2: return FLUC_TTMLBLEND_FORMAT_IYU2;
+    case GST_VIDEO_FORMAT_RGB: return FLUC_TTMLBLEND_FORMAT_RGB;
+    case GST_VIDEO_FORMAT_BGR: return FLUC_TTMLBLEND_FORMAT_BGR;
     default: return FLUC_TTMLBLEND_FORMAT_COUNT;
   }
 }

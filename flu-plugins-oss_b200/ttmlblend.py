@@ -26,7 +26,7 @@ FORMATS = {
     "YV12": 5, "NV21": 6, "ARGB": 7, "ABGR": 8,
     "RGBx": 9, "BGRx": 10, "xRGB": 11, "xBGR": 12,       # same paths as RGBA / BGRA / ARGB / ABGR
     "Y42B": 13, "Y444": 14, "YUY2": 15, "UYVY": 16, "GRAY8": 17, "NV16": 18, "NV24": 19,
-    "NV61": 20, "YVYU": 21, "VYUY": 22, "v308": 23, "IYU2": 24,
+    "NV61": 20, "YVYU": 21, "VYUY": 22, "v308": 23, "IYU2": 24, "RGB": 25, "BGR": 26,
 }
 FLAG_PREMULTIPLIED_ALPHA = 1
 MAX_RECTANGLES = 64
@@ -182,7 +182,7 @@ def plane_layout(fmt: str, width: int, height: int):
         return [(width, height)] * 3
     if f in ("YUY2", "UYVY", "YVYU", "VYUY"):
         return [(4 * ((width + 1) // 2), height)]
-    if f in ("V308", "IYU2"):
+    if f in ("V308", "IYU2", "RGB", "BGR"):
         return [(3 * width, height)]
     if f == "GRAY8":
         return [(width, height)]

@@ -103,7 +103,7 @@ def plane_shapes(fmt: str, width: int, height: int):
         return [(height, width)] * 3
     if f in ("YUY2", "UYVY", "YVYU", "VYUY"):
         return [(height, 4 * cw)]
-    if f in ("V308", "IYU2"):
+    if f in ("V308", "IYU2", "RGB", "BGR"):
         return [(height, 3 * width)]
     if f == "GRAY8":
         return [(height, width)]

@@ -83,6 +83,8 @@ typedef enum {
   FLUC_TTMLBLEND_FORMAT_VYUY = 22,      /* packed 4:2:2, bytes V Y0 U Y1 */
   FLUC_TTMLBLEND_FORMAT_v308 = 23,      /* packed 4:4:4, 3 bytes per pixel: Y U V */
   FLUC_TTMLBLEND_FORMAT_IYU2 = 24,      /* packed 4:4:4, 3 bytes per pixel: U Y V */
+  FLUC_TTMLBLEND_FORMAT_RGB = 25,       /* 24-bit R G B: no alpha byte, the destination counts as opaque */
+  FLUC_TTMLBLEND_FORMAT_BGR = 26,
   FLUC_TTMLBLEND_FORMAT_COUNT
 } FlucTtmlBlendFormat;
 

@@ -19,7 +19,7 @@ FORMATS = {"I420": 0, "NV12": 1, "AYUV": 2, "RGBA": 3, "BGRA": 4,
            # x formats use their alpha twins' pack/unpack in GStreamer (PACK_RGBA ...)
            "RGBx": 3, "BGRx": 4, "xRGB": 7, "xBGR": 8,
            "Y42B": 13, "Y444": 14, "YUY2": 15, "UYVY": 16, "GRAY8": 17, "NV16": 18, "NV24": 19,
-           "NV61": 20, "YVYU": 21, "VYUY": 22, "v308": 23, "IYU2": 24}
+           "NV61": 20, "YVYU": 21, "VYUY": 22, "v308": 23, "IYU2": 24, "RGB": 25, "BGR": 26}
 FLAG_PREMULTIPLIED_ALPHA = 1
 
 

@@ -104,6 +104,8 @@ tbref_plane_row_bytes (int32_t f, int32_t plane, int32_t w)
       return 4 * ((w + 1) / 2);
     case TBREF_FORMAT_v308:
     case TBREF_FORMAT_IYU2:
+    case TBREF_FORMAT_RGB:
+    case TBREF_FORMAT_BGR:
       return 3 * w;
     default:
       return 4 * w;
@@ -221,6 +223,18 @@ unpack_line (const TbRefFrame *f, int y, uint8_t *d, int width)
         d[4 * x + 1] = m[oy + 2 * (x & 1)];
         d[4 * x + 2] = m[ou];
         d[4 * x + 3] = m[ov];
+      }
+      break;
+    }
+    case TBREF_FORMAT_RGB:
+    case TBREF_FORMAT_BGR:{        /* unpack_RGB / unpack_BGR: A = 0xff */
+      const uint8_t *s = f->data[0] + (size_t) f->stride[0] * y;
+      const int orr = f->format == TBREF_FORMAT_RGB ? 0 : 2;
+      for (x = 0; x < width; x++) {
+        d[4 * x + 0] = 0xff;
+        d[4 * x + 1] = s[3 * x + orr];
+        d[4 * x + 2] = s[3 * x + 1];
+        d[4 * x + 3] = s[3 * x + (2 - orr)];
       }
       break;
     }
@@ -428,6 +442,17 @@ pack_line (TbRefFrame *f, int y, const uint8_t *s, int width)
         dy[x] = s[4 * x + 1];
       break;
     }
+    case TBREF_FORMAT_RGB:
+    case TBREF_FORMAT_BGR:{        /* pack_RGB / pack_BGR: the alpha is dropped */
+      uint8_t *d = f->data[0] + (size_t) f->stride[0] * y;
+      const int orr = f->format == TBREF_FORMAT_RGB ? 0 : 2;
+      for (x = 0; x < width; x++) {
+        d[3 * x + orr] = s[4 * x + 1];
+        d[3 * x + 1] = s[4 * x + 2];
+        d[3 * x + (2 - orr)] = s[4 * x + 3];
+      }
+      break;
+    }
     case TBREF_FORMAT_AYUV:
     case TBREF_FORMAT_ARGB:
       memcpy (f->data[0] + (size_t) f->stride[0] * y, s, (size_t) width * 4);
@@ -592,7 +617,7 @@ tbref_video_blend (TbRefFrame *dest, const TbRefRectangle *src)
 
   if (!dest || !src || !src->pixels)
     return 0;
-  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_IYU2 ||
+  if (dest->format < TBREF_FORMAT_I420 || dest->format > TBREF_FORMAT_BGR ||
       (dest->format > TBREF_FORMAT_ABGR && dest->format < TBREF_FORMAT_Y42B))
     return 0;
 

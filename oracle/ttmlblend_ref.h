@@ -52,7 +52,9 @@ enum {
   TBREF_FORMAT_YVYU = 21,
   TBREF_FORMAT_VYUY = 22,
   TBREF_FORMAT_v308 = 23,
-  TBREF_FORMAT_IYU2 = 24
+  TBREF_FORMAT_IYU2 = 24,
+  TBREF_FORMAT_RGB = 25,
+  TBREF_FORMAT_BGR = 26
 };
 
 #define TBREF_FLAG_PREMULTIPLIED_ALPHA 1u

@@ -62,6 +62,8 @@ static const struct {
   { GST_VIDEO_FORMAT_VYUY, TBREF_FORMAT_VYUY, "VYUY" },
   { GST_VIDEO_FORMAT_v308, TBREF_FORMAT_v308, "v308" },
   { GST_VIDEO_FORMAT_IYU2, TBREF_FORMAT_IYU2, "IYU2" },
+  { GST_VIDEO_FORMAT_RGB, TBREF_FORMAT_RGB, "RGB" },
+  { GST_VIDEO_FORMAT_BGR, TBREF_FORMAT_BGR, "BGR" },
 };
 
 /* geometry / flag cases: frame size, rectangle size and position (hanging over every

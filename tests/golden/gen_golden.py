@@ -55,6 +55,9 @@ VECTORS = [
     ("vyuy", "VYUY", 64, 40, [(41, 20, 10, 13, 1.0, True)], True, False),
     ("v308", "v308", 61, 40, [(40, 20, 11, 13, 1.0, True), (9, 9, 55, 35, 0.5, True)], True, False),
     ("iyu2", "IYU2", 62, 40, [(40, 20, 11, 13, 1.0, True)], True, False),
+    ("rgb", "RGB", 61, 40, [(40, 20, 11, 13, 1.0, True), (9, 9, 55, 35, 0.5, True), (20, 8, 3, 2, 0.8, False)],
+     True, False),
+    ("bgr", "BGR", 64, 40, [(41, 20, 10, 13, 1.0, True), (17, 9, 30, 3, 1.0, False)], True, False),
 ]
 
 

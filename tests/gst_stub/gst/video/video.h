@@ -9,7 +9,7 @@ typedef enum { GST_VIDEO_FORMAT_UNKNOWN, GST_VIDEO_FORMAT_I420, GST_VIDEO_FORMAT
   GST_VIDEO_FORMAT_xRGB, GST_VIDEO_FORMAT_xBGR, GST_VIDEO_FORMAT_Y42B, GST_VIDEO_FORMAT_Y444,
   GST_VIDEO_FORMAT_YUY2, GST_VIDEO_FORMAT_UYVY, GST_VIDEO_FORMAT_GRAY8, GST_VIDEO_FORMAT_NV16,
   GST_VIDEO_FORMAT_NV24, GST_VIDEO_FORMAT_NV61, GST_VIDEO_FORMAT_YVYU, GST_VIDEO_FORMAT_VYUY,
-  GST_VIDEO_FORMAT_v308, GST_VIDEO_FORMAT_IYU2 } GstVideoFormat;
+  GST_VIDEO_FORMAT_v308, GST_VIDEO_FORMAT_IYU2, GST_VIDEO_FORMAT_RGB, GST_VIDEO_FORMAT_BGR } GstVideoFormat;
 typedef enum { GST_VIDEO_FLAG_NONE = 0, GST_VIDEO_FLAG_PREMULTIPLIED_ALPHA = 2 } GstVideoFlags;
 typedef enum { GST_VIDEO_FRAME_FLAG_NONE = 0 } GstVideoFrameFlags;
 typedef enum { GST_VIDEO_COMP_A = 3 } GstVideoCompStub;

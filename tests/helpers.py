@@ -15,7 +15,8 @@ PLANAR_420 = ("I420", "YV12", "NV12", "NV21")
 MORE_YUV = ("Y42B", "Y444", "YUY2", "UYVY", "GRAY8", "NV16", "NV24", "NV61", "YVYU", "VYUY", "v308", "IYU2")
 YUV_FORMATS = tuple(f.upper() for f in PLANAR_420 + ("AYUV",) + MORE_YUV)
 PACKED = ("AYUV", "ARGB", "ABGR", "RGBA", "BGRA")
-ALL_FORMATS = PLANAR_420 + PACKED + MORE_YUV
+RGB24 = ("RGB", "BGR")                     # no alpha byte: the destination is opaque
+ALL_FORMATS = PLANAR_420 + PACKED + MORE_YUV + RGB24
 
 
 def yuv_views(fmt, planes, w):
@@ -186,7 +187,7 @@ def model_blend(fmt, w, h, planes, rectangles, dest_premul=False, chroma_average
             c1, c2, c3 = r, g, b
         asrc = a * ga // 255
         m = asrc > 0
-        if fmt not in PACKED_ORDER:
+        if fmt not in PACKED_ORDER and fmt not in RGB24:
             Y, U, V, sx, sy = yuv_views(fmt, planes, w)
             yd = Y[y0:y1, x0:x1].astype(np.int64)
             v, _ = _over(c1, yd, asrc, 255, ga, sp, dest_premul)
@@ -225,6 +226,15 @@ def model_blend(fmt, w, h, planes, rectangles, dest_premul=False, chroma_average
                     d = view.astype(np.int64)
                     vv, _ = _over(cc, d, ca, 255, ga, sp, dest_premul)
                     view[...] = np.where(cm, vv, d).astype(np.uint8)
+        elif fmt in RGB24:
+            # three bytes per pixel, adst = 255, the source keeps its premultiplied flag
+            P = planes[0]
+            rows = P[y0:y1, 3 * x0:3 * x1]
+            order = (0, 1, 2) if fmt == "RGB" else (2, 1, 0)
+            for idx, cs in zip(order, (c1, c2, c3)):
+                cd = rows[:, idx::3].astype(np.int64)
+                v, _ = _over(cs, cd, asrc, 255, ga, sp, dest_premul)
+                rows[:, idx::3] = np.where(m, v, cd).astype(np.uint8)
         else:
             ia, i1, i2, i3 = PACKED_ORDER[fmt]
             P = planes[0]

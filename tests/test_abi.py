@@ -52,7 +52,7 @@ def test_header_is_plain_c(tmp_path):
     """The boundary must compile as C99 with no CUDA / GLib / torch headers."""
     src = tmp_path / "t.c"
     src.write_text('#include "fluc_ttmlblend.h"\nint main(void){FlucTtmlBlendFrame f; FlucTtmlBlendStats s;'
-                   '(void)f;(void)s;return FLUC_TTMLBLEND_FORMAT_COUNT==25?0:1;}\n')
+                   '(void)f;(void)s;return FLUC_TTMLBLEND_FORMAT_COUNT==27?0:1;}\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I",
                            os.path.join(graft.ROOT, "include"), "-c", str(src), "-o",
                            str(tmp_path / "t.o")])
