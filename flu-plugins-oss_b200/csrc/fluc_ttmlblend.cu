@@ -338,7 +338,7 @@ fluc_ttmlblend_overlay_set_rectangles (FlucTtmlBlend *thiz, uint32_t stream,
     return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   if (n_rects > FLUC_TTMLBLEND_MAX_RECTANGLES)
     return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-  return overlay_install (c, stream, rects, n_rects);
+  return overlay_install (c, lk, stream, rects, n_rects);
 }
 
 int
@@ -376,7 +376,7 @@ fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream, const uint8_t 
     q.flags = FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA;   /* Cairo ARGB32, gstttmlrender.c:1446 */
     rr.push_back (q);
   }
-  return overlay_install (c, stream, rr.data (), (uint32_t) rr.size ());
+  return overlay_install (c, lk, stream, rr.data (), (uint32_t) rr.size ());
 }
 
 int
@@ -388,7 +388,7 @@ fluc_ttmlblend_overlay_set_regions (FlucTtmlBlend *thiz, uint32_t stream, int32_
     return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   if (n_regions > FLUC_TTMLBLEND_MAX_RECTANGLES)
     return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-  return overlay_install_regions (c, stream, W, H, regions, n_regions);
+  return overlay_install_regions (c, lk, stream, W, H, regions, n_regions);
 }
 
 int
@@ -567,14 +567,48 @@ fluc_ttmlblend_sync (FlucTtmlBlend *thiz)
   int rc = launch_pending (c);
   if (rc)
     return rc;
-  CU (c, cudaStreamSynchronize (c->blend_stream));
+  /* what is in flight now, then wait for it with the context unlocked: other threads keep
+   * submitting frames and changing cues meanwhile (their work is not waited for) */
+  uint64_t lane_ticket[kLanes];
+  bool lane_busy[kLanes];
   for (int i = 0; i < kLanes; i++) {
-    CU (c, cudaStreamSynchronize (c->lanes[i].stream));
-    c->lanes[i].busy = false;
-    c->lanes[i].keep.reset ();
+    lane_ticket[i] = c->lanes[i].ticket;
+    lane_busy[i] = c->lanes[i].busy;
   }
-  c->lane_tickets.clear ();
-  CU (c, cudaStreamSynchronize (c->up_stream));
+  cudaEvent_t ev[kLanes + 2];
+  int n_ev = 0;
+  cudaStream_t streams[kLanes + 2];
+  int n_streams = 0;
+  streams[n_streams++] = c->blend_stream;
+  streams[n_streams++] = c->up_stream;
+  for (int i = 0; i < kLanes; i++)
+    if (lane_busy[i])
+      streams[n_streams++] = c->lanes[i].stream;
+  for (int i = 0; i < n_streams; i++) {
+    cudaEvent_t e = event_get (c);
+    CU (c, cudaEventRecord (e, streams[i]));
+    ev[n_ev++] = e;
+  }
+  lk.unlock ();
+  cudaError_t err = cudaSuccess;
+  for (int i = 0; i < n_ev; i++) {
+    const cudaError_t e = cudaEventSynchronize (ev[i]);
+    err = err == cudaSuccess ? e : err;
+  }
+  lk.lock ();
+  for (int i = 0; i < n_ev; i++)
+    c->event_pool.push_back (ev[i]);
+  if (err != cudaSuccess) {
+    c->sticky = FLUC_TTMLBLEND_ERROR_CUDA;
+    c->cuda_error = std::string ("sync: ") + cudaGetErrorString (err);
+    return c->sticky;
+  }
+  for (int i = 0; i < kLanes; i++)
+    if (lane_busy[i] && c->lanes[i].busy && c->lanes[i].ticket == lane_ticket[i]) {
+      c->lanes[i].busy = false;
+      c->lanes[i].keep.reset ();
+      c->lane_tickets.erase (lane_ticket[i]);
+    }
   reap_batches (c);
   return 0;
 }

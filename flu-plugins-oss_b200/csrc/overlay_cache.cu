@@ -431,35 +431,66 @@ struct Up {
   std::vector<int> groups;      /* per row: 16-pixel groups with any alpha */
 };
 
+/* What an install does to the context's counters, added once the lock is held again. */
+struct InstallStats {
+  uint64_t h2d_bytes = 0;
+  uint32_t launches = 0;
+};
+
+/* CU for the parts of an install that run without the context lock: the lock is taken back
+ * before the error is recorded and reported. */
+#define CUU(ctx, lk, call) do {                                              \
+    cudaError_t eu_ = (call);                                                \
+    if (eu_ != cudaSuccess) {                                                \
+      if (!(lk).owns_lock ())                                                \
+        (lk).lock ();                                                        \
+      (ctx)->cuda_error = std::string (#call) + ": " + cudaGetErrorString (eu_); \
+      if (eu_ == cudaErrorMemoryAllocation) {                                \
+        cudaGetLastError ();                                                 \
+        return FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY;                           \
+      }                                                                      \
+      (ctx)->sticky = FLUC_TTMLBLEND_ERROR_CUDA;                             \
+      return FLUC_TTMLBLEND_ERROR_CUDA;                                      \
+    }                                                                        \
+  } while (0)
+
 /* Queues the row-span scan of one device-resident rectangle on the upload stream. */
 static int
-scan_rows (Ctx *c, Up &u)
+scan_rows (Ctx *c, std::unique_lock<std::mutex> &lk, Up &u)
 {
   if (!c->autocrop)
     return 0;
   void *sp = nullptr;
   const size_t nb = (size_t) u.rr.h * (sizeof (int2) + sizeof (int));
-  CU (c, cudaMallocFromPoolAsync (&sp, nb, c->mem_pool, c->up_stream));
+  CUU (c, lk, cudaMallocFromPoolAsync (&sp, nb, c->mem_pool, c->up_stream));
   u.spans.resize (u.rr.h);
   u.groups.resize (u.rr.h);
   int2 *d_spans = static_cast<int2 *> (sp);
   int *d_groups = reinterpret_cast<int *> (d_spans + u.rr.h);
-  CU (c, launch_rowspan (u.rr.dev, u.rr.pitch, u.rr.w, u.rr.h, d_spans, d_groups, c->up_stream));
-  CU (c, cudaMemcpyAsync (u.spans.data (), d_spans, (size_t) u.rr.h * sizeof (int2), cudaMemcpyDeviceToHost,
+  CUU (c, lk, launch_rowspan (u.rr.dev, u.rr.pitch, u.rr.w, u.rr.h, d_spans, d_groups, c->up_stream));
+  CUU (c, lk, cudaMemcpyAsync (u.spans.data (), d_spans, (size_t) u.rr.h * sizeof (int2), cudaMemcpyDeviceToHost,
           c->up_stream));
-  CU (c, cudaMemcpyAsync (u.groups.data (), d_groups, (size_t) u.rr.h * sizeof (int), cudaMemcpyDeviceToHost,
+  CUU (c, lk, cudaMemcpyAsync (u.groups.data (), d_groups, (size_t) u.rr.h * sizeof (int), cudaMemcpyDeviceToHost,
           c->up_stream));
-  CU (c, cudaFreeAsync (sp, c->up_stream));
+  CUU (c, lk, cudaFreeAsync (sp, c->up_stream));
   return 0;
 }
 
 /* Waits for uploads and scans, crops every rectangle to its non-transparent row runs and
  * swaps the stream's overlay. */
 static int
-finish_install (Ctx *c, uint32_t stream, std::shared_ptr<Overlay> ov, std::vector<Up> &ups)
+finish_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, std::shared_ptr<Overlay> ov,
+    std::vector<Up> &ups, const InstallStats &st)
 {
-  /* the caller's pixels must be consumed (and the row spans back) before we return */
-  CU (c, cudaStreamSynchronize (c->up_stream));
+  /* the caller's pixels must be consumed (and the row spans back) before we return; the
+   * context stays unlocked while that takes its time */
+  CUU (c, lk, cudaStreamSynchronize (c->up_stream));
+  if (!lk.owns_lock ())
+    lk.lock ();
+  if (c->sticky)
+    return c->sticky;
+  c->stats.h2d_bytes += st.h2d_bytes;
+  c->stats.prepare_launches += st.launches;
   uint64_t groups_all = 0, groups_on = 0;
   for (Up &u : ups) {
     if (!c->autocrop) {
@@ -532,23 +563,34 @@ scale_row_plan (int src_h, int dst_h)
 }
 
 int
-overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n)
+overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, const FlucTtmlBlendRectangle *rects,
+    uint32_t n)
 {
   NvtxRange nvtx ("ttmlblend.overlay_set");
-  std::shared_ptr<Overlay> ov (new Overlay ());
-  ov->ctx = c;
-  std::vector<Up> ups;
-  std::vector<std::vector<int4>> plans;     /* host side of async uploads: alive until finish_install */
   for (uint32_t i = 0; i < n; i++) {
     const FlucTtmlBlendRectangle &r = rects[i];
     if (!r.pixels || r.width <= 0 || r.height <= 0 || r.stride < r.width * 4 || r.render_width < 0 ||
         r.render_height < 0 || r.render_width > 32768 || r.render_height > 32768)
       return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+    const int rw = r.render_width ? r.render_width : r.width, rh = r.render_height ? r.render_height : r.height;
+    if ((rw != r.width || rh != r.height) && (r.width < 2 || r.height < 2))
+      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;   /* upstream reads outside the image here */
+  }
+  std::shared_ptr<Overlay> ov (new Overlay ());
+  ov->ctx = c;
+  std::vector<Up> ups;
+  std::vector<std::vector<int4>> plans;     /* host side of async uploads: alive until finish_install */
+  InstallStats st;
+  /* Uploading (a copy from pageable memory holds the caller for its whole length), scaling and
+   * scanning touch only this overlay-to-be and the upload stream: the context is unlocked
+   * meanwhile, so a cue change of one stream does not stall the frames of all the others. Any
+   * failure takes the lock back before it reports (CUU). */
+  lk.unlock ();
+  for (uint32_t i = 0; i < n; i++) {
+    const FlucTtmlBlendRectangle &r = rects[i];
     /* gst_video_overlay_rectangle_needs_scaling: render size != pixel size */
     const int rw = r.render_width ? r.render_width : r.width, rh = r.render_height ? r.render_height : r.height;
     const bool scaled = rw != r.width || rh != r.height;
-    if (scaled && (r.width < 2 || r.height < 2))
-      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;   /* upstream reads outside the image here */
     /* gst_video_blend: negative offsets skip source columns / rows */
     const int xoff = r.x < 0 ? -r.x : 0, yoff = r.y < 0 ? -r.y : 0;
     if (xoff >= rw || yoff >= rh)
@@ -566,42 +608,42 @@ overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, u
     if (!scaled) {
       rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
       void *d = nullptr;
-      CU (c, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rr.h, c->mem_pool, c->up_stream));
+      CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rr.h, c->mem_pool, c->up_stream));
       ov->raw_allocs.push_back (d);
       rr.dev = static_cast<uint8_t *> (d);
-      CU (c, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
+      CUU (c, lk, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
               r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
-      c->stats.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+      st.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
     } else {
       /* the whole source goes up, is scaled to the render size on the GPU, and the clipped
        * part of the scaled image is what gets blended */
       const int sp = (int) align_up ((size_t) r.width * 4, 256);
       void *s = nullptr, *d = nullptr, *p = nullptr;
-      CU (c, cudaMallocFromPoolAsync (&s, (size_t) sp * r.height, c->mem_pool, c->up_stream));
-      CU (c, cudaMemcpy2DAsync (s, sp, r.pixels, r.stride, (size_t) r.width * 4, r.height,
+      CUU (c, lk, cudaMallocFromPoolAsync (&s, (size_t) sp * r.height, c->mem_pool, c->up_stream));
+      CUU (c, lk, cudaMemcpy2DAsync (s, sp, r.pixels, r.stride, (size_t) r.width * 4, r.height,
               cudaMemcpyHostToDevice, c->up_stream));
-      c->stats.h2d_bytes += (uint64_t) r.width * 4 * r.height;
+      st.h2d_bytes += (uint64_t) r.width * 4 * r.height;
       plans.push_back (scale_row_plan (r.height, rh));
-      CU (c, cudaMallocFromPoolAsync (&p, (size_t) rh * sizeof (int4), c->mem_pool, c->up_stream));
-      CU (c, cudaMemcpyAsync (p, plans.back ().data (), (size_t) rh * sizeof (int4), cudaMemcpyHostToDevice,
+      CUU (c, lk, cudaMallocFromPoolAsync (&p, (size_t) rh * sizeof (int4), c->mem_pool, c->up_stream));
+      CUU (c, lk, cudaMemcpyAsync (p, plans.back ().data (), (size_t) rh * sizeof (int4), cudaMemcpyHostToDevice,
               c->up_stream));
       rr.pitch = (int) align_up ((size_t) rw * 4, 256);
-      CU (c, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rh, c->mem_pool, c->up_stream));
+      CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rh, c->mem_pool, c->up_stream));
       ov->raw_allocs.push_back (d);
       const int x_inc = rw == 1 ? 0 : ((r.width - 1) << 16) / (rw - 1) - 1;
-      CU (c, launch_scale (static_cast<const uint8_t *> (s), sp, static_cast<const int4 *> (p), x_inc,
+      CUU (c, lk, launch_scale (static_cast<const uint8_t *> (s), sp, static_cast<const int4 *> (p), x_inc,
               static_cast<uint8_t *> (d), rr.pitch, rw, rh, c->up_stream));
-      c->stats.prepare_launches++;
-      CU (c, cudaFreeAsync (s, c->up_stream));
-      CU (c, cudaFreeAsync (p, c->up_stream));
+      st.launches++;
+      CUU (c, lk, cudaFreeAsync (s, c->up_stream));
+      CUU (c, lk, cudaFreeAsync (p, c->up_stream));
       rr.dev = static_cast<uint8_t *> (d) + (size_t) yoff * rr.pitch + (size_t) xoff * 4;
     }
-    int rc = scan_rows (c, u);
+    int rc = scan_rows (c, lk, u);
     if (rc)
       return rc;
     ups.push_back (std::move (u));
   }
-  return finish_install (c, stream, ov, ups);
+  return finish_install (c, lk, stream, ov, ups, st);
 }
 
 /* Cairo's colour conversion: double components -> premultiplied 16-bit shorts
@@ -621,22 +663,37 @@ cairo_solid_pixel (uint32_t rgba8888)
  * a cleared frame-sized canvas, every region drawn onto it in list order by
  * ttmlblend_region_kernel, then installed like an uploaded image cropped to the boxes. */
 int
-overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTtmlBlendRegion *regions, uint32_t n)
+overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, int W, int H,
+    const FlucTtmlBlendRegion *regions, uint32_t n)
 {
   NvtxRange nvtx ("ttmlblend.overlay_set_regions");
-  std::shared_ptr<Overlay> ov (new Overlay ());
-  ov->ctx = c;
-  const int pitch = (int) align_up ((size_t) W * 4, 256);
-  void *canvas = nullptr;
-  CU (c, cudaMallocFromPoolAsync (&canvas, (size_t) pitch * H, c->mem_pool, c->up_stream));
-  ov->raw_allocs.push_back (canvas);
-  CU (c, cudaMemsetAsync (canvas, 0, (size_t) pitch * H, c->up_stream));   /* CAIRO_OPERATOR_CLEAR */
-  std::vector<void *> layers;
-  std::vector<FlucTtmlBlendRect> boxes;
   for (uint32_t i = 0; i < n; i++)
     if (regions[i].w <= 0 || regions[i].h <= 0 || !(regions[i].opacity >= 0.0 && regions[i].opacity <= 1.0) ||
         (regions[i].layer && regions[i].layer_stride < 4 * regions[i].w))
       return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  {
+    std::vector<FlucTtmlBlendRect> boxes;
+    for (uint32_t i = 0; i < n; i++) {
+      const FlucTtmlBlendRegion &r = regions[i];
+      const int x0 = std::max (r.x, 0), y0 = std::max (r.y, 0);
+      const int x1 = std::min (r.x + r.w, W), y1 = std::min (r.y + r.h, H);
+      if (x1 > x0 && y1 > y0 && (r.background_color || r.layer))
+        boxes.push_back ({ x0, y0, x1 - x0, y1 - y0 });
+    }
+    if (disjoint_cover (boxes).size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+      return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+  }
+  std::shared_ptr<Overlay> ov (new Overlay ());
+  ov->ctx = c;
+  InstallStats st;
+  lk.unlock ();                 /* as in overlay_install: only this overlay and the upload stream from here */
+  const int pitch = (int) align_up ((size_t) W * 4, 256);
+  void *canvas = nullptr;
+  CUU (c, lk, cudaMallocFromPoolAsync (&canvas, (size_t) pitch * H, c->mem_pool, c->up_stream));
+  ov->raw_allocs.push_back (canvas);
+  CUU (c, lk, cudaMemsetAsync (canvas, 0, (size_t) pitch * H, c->up_stream));   /* CAIRO_OPERATOR_CLEAR */
+  std::vector<void *> layers;
+  std::vector<FlucTtmlBlendRect> boxes;
   for (uint32_t i = 0; i < n; i++) {
     const FlucTtmlBlendRegion &r = regions[i];
     const int x0 = std::max (r.x, 0), y0 = std::max (r.y, 0);
@@ -653,22 +710,22 @@ overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTtmlBl
     if (r.layer) {
       const int lp = (int) align_up ((size_t) r.w * 4, 256);
       void *d = nullptr;
-      CU (c, cudaMallocFromPoolAsync (&d, (size_t) lp * r.h, c->mem_pool, c->up_stream));
+      CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) lp * r.h, c->mem_pool, c->up_stream));
       layers.push_back (d);
-      CU (c, cudaMemcpy2DAsync (d, lp, r.layer, r.layer_stride, (size_t) r.w * 4, r.h,
+      CUU (c, lk, cudaMemcpy2DAsync (d, lp, r.layer, r.layer_stride, (size_t) r.w * 4, r.h,
               cudaMemcpyHostToDevice, c->up_stream));
-      c->stats.h2d_bytes += (uint64_t) r.w * 4 * r.h;
+      st.h2d_bytes += (uint64_t) r.w * 4 * r.h;
       p.layer = static_cast<uint8_t *> (d);
       p.layer_pitch = lp;
     }
     if (!p.bg && !p.layer)
       continue;                 /* nothing to draw */
-    CU (c, launch_region (p, c->up_stream));
-    c->stats.prepare_launches++;
+    CUU (c, lk, launch_region (p, c->up_stream));
+    st.launches++;
     boxes.push_back ({ x0, y0, x1 - x0, y1 - y0 });
   }
   for (void *d : layers)
-    CU (c, cudaFreeAsync (d, c->up_stream));
+    CUU (c, lk, cudaFreeAsync (d, c->up_stream));
   std::vector<Up> ups;
   for (const FlucTtmlBlendRect &b : disjoint_cover (boxes)) {
     Up u;
@@ -678,14 +735,12 @@ overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTtmlBl
     u.rr.ga = 255;
     u.rr.premul = true;
     ov->declared.push_back (b);
-    int rc = scan_rows (c, u);
+    int rc = scan_rows (c, lk, u);
     if (rc)
       return rc;
     ups.push_back (std::move (u));
   }
-  if (ups.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
-    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-  return finish_install (c, stream, ov, ups);
+  return finish_install (c, lk, stream, ov, ups, st);
 }
 
 }  // namespace tbh

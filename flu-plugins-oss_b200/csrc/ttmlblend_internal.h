@@ -433,8 +433,12 @@ int prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **o
 std::vector<FlucTtmlBlendRect> disjoint_cover (const std::vector<FlucTtmlBlendRect> &in);
 std::vector<int4> scale_row_plan (int src_h, int dst_h);
 void crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, std::vector<FlucTtmlBlendRect> &out);
-int overlay_install (Ctx *c, uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n);
-int overlay_install_regions (Ctx *c, uint32_t stream, int W, int H, const FlucTtmlBlendRegion *regions, uint32_t n);
+/* both are entered with the context lock held (lk), drop it while they upload, and return with
+ * it held again whenever they got as far as dropping it */
+int overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, const FlucTtmlBlendRectangle *rects,
+    uint32_t n);
+int overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, int W, int H,
+    const FlucTtmlBlendRegion *regions, uint32_t n);
 
 /* jobs.cu */
 int check_frame (int fmt, int W, int H, const FlucTtmlBlendFrame *f);
