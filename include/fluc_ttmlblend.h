@@ -244,8 +244,14 @@ FLUC_EXPORT int fluc_ttmlblend_submit_many (FlucTtmlBlend *thiz, uint32_t n,
     uint32_t frame_flags, const FlucTtmlBlendFrame *srcs, const FlucTtmlBlendFrame *dsts,
     uint64_t *tickets);
 FLUC_EXPORT int fluc_ttmlblend_flush (FlucTtmlBlend *thiz);
+/* Returns when the frame is complete. A frame that is still queued is launched at once when its
+ * stream is the only active one; when several streams have been submitting, the batch is left
+ * to the scheduler thread for up to the linger time (or until it is full) so that synchronous
+ * callers of different streams share launches. linger_us = 0 turns that off. */
 FLUC_EXPORT int fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket);
-FLUC_EXPORT int fluc_ttmlblend_sync (FlucTtmlBlend *thiz);   /* flush + wait all */
+/* flush + wait for everything in flight at the time of the call (the context is not locked
+ * while waiting: other threads keep submitting). */
+FLUC_EXPORT int fluc_ttmlblend_sync (FlucTtmlBlend *thiz);
 /* Scheduler knobs: frames per launch (default 32, 1..1024) and how long the
  * scheduler thread lets a partial batch linger, in microseconds (default 200;
  * 0 = no scheduler thread launches, only flush/wait/limit). */
