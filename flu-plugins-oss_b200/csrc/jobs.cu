@@ -205,7 +205,8 @@ make_groupable (Layout &L, bool lazy_inplace)
   /* frame = umulhi (chunk, ceil (2^32 / cpf)) must be exact for every chunk of a full group */
   const uint64_t magic = ((1ull << 32) + total - 1) / total;
   const uint64_t e = magic * total - (1ull << 32);
-  if ((uint64_t) kMaxGroupFrames * total * e >= (1ull << 32) || (uint64_t) kMaxGroupFrames * total >= (1ull << 26)) {
+  if ((uint64_t) kMaxPlainGroupFrames * total * e >= (1ull << 32) ||
+      (uint64_t) kMaxPlainGroupFrames * total >= (1ull << 26)) {
     L.bands.clear ();
     return;
   }
@@ -364,7 +365,7 @@ emit_table_jobs (const std::vector<PlaneJob> &tmpl, const PendingFrame &f, std::
 bool
 group_accepts (const Group &g, const PendingFrame &f)
 {
-  return g.layout_id == f.layout->id && g.P.n_frames < (uint32_t) kMaxGroupFrames;
+  return g.layout_id == f.layout->id && g.P.n_frames < (uint32_t) kMaxPlainGroupFrames;
 }
 
 void

@@ -85,7 +85,11 @@ struct alignas (16) PlaneJob {
 };
 
 /* ---- group launch: frames that share geometry, tables in kernel parameters ---- */
-constexpr int kMaxGroupFrames = 64;
+constexpr int kMaxGroupFrames = 64;          /* multi-layout launches (parameter space) */
+#ifndef TTMLBLEND_GROUP_FRAMES
+#define TTMLBLEND_GROUP_FRAMES 256
+#endif
+constexpr int kMaxPlainGroupFrames = TTMLBLEND_GROUP_FRAMES;   /* plain group launches */
 constexpr int kMaxGroupBands = 64;
 
 struct BandDesc {             /* one band of rows of one plane, same for every frame */
@@ -113,11 +117,11 @@ struct GroupParams {
   int32_t rect_off[3];        /* first RectRef of plane p inside FramePtrs::rects */
   int32_t flags;              /* JobFlags shared by the group */
   BandDesc bands[kMaxGroupBands];
-  FramePtrs frames[kMaxGroupFrames];
+  FramePtrs frames[kMaxPlainGroupFrames];
 };
 /* > 4 KB of kernel parameters needs CUDA >= 12.1 and driver >= R530 (limit 32764 B), which
  * every sm_100a system has */
-static_assert (sizeof (GroupParams) <= 16384, "kernel parameters");
+static_assert (sizeof (GroupParams) <= 32764, "kernel parameters");
 
 /* ---- multi-layout group launch: frames of one format / size / pitch set whose cue layouts
  * (band lists) differ -- many streams, each showing its own text. Still everything in kernel
