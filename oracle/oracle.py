@@ -143,6 +143,41 @@ def scale_linear_rgba(img: np.ndarray, dest_width: int, dest_height: int, lib=No
     return out
 
 
+REF_PATH = os.path.join(_HERE, "_ref", "libttmlblur_ref.so")
+_ref = None
+
+
+def load_ref():
+    """oracle/_ref/libttmlblur_ref.so: the reference's own gstttmlblur.c compiled from
+    /root/reference against the stand-in headers of oracle/refstub/ (`make -C oracle ref`,
+    done by __graft_entry__.build() where /root/reference exists). None if it is not there."""
+    global _ref
+    if _ref is None and os.path.exists(REF_PATH):
+        lib = C.CDLL(REF_PATH)
+        lib.ttmlref_blur_argb32.restype = None
+        lib.ttmlref_blur_argb32.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_double, C.c_void_p, C.c_int32]
+        lib.ttmlref_last_filter_params.restype = C.c_int32
+        lib.ttmlref_last_filter_params.argtypes = [C.POINTER(C.c_int32), C.c_int32]
+        _ref = lib
+    return _ref
+
+
+def ref_blur_argb32(img: np.ndarray, radius: int, sigma: float):
+    """(blurred image, filter parameters) from the reference's gst_ttml_blur_image_surface: the
+    parameters are what it handed to pixman_image_set_filter (2 sizes + (2r+1)^2 taps, 16.16)."""
+    lib = load_ref()
+    assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 4 and img.strides[2] == 1
+    out = np.zeros_like(img)
+    lib.ttmlref_blur_argb32(img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], radius, sigma,
+                            out.ctypes.data, out.strides[0])
+    n = (2 * radius + 1) ** 2 + 2
+    buf = (C.c_int32 * n)()
+    got = lib.ttmlref_last_filter_params(buf, n)
+    assert got == n, (got, n)
+    return out, np.array(buf[:], dtype=np.int64)
+
+
 def blur_argb32(img: np.ndarray, radius: int, sigma: float, lib=None) -> np.ndarray:
     """gst_ttml_blur_image_surface (surface, radius, sigma) on an h x w x 4 uint8 image."""
     lib = lib or load()

@@ -835,12 +835,21 @@ void
 tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
     int32_t radius, double sigma, uint8_t *dst, int32_t dst_stride)
 {
-  /* bits_image_fetch_pixel_convolution: window [x-r, x+r] x [y-r, y+r], pixels outside the
-   * image are transparent black (REPEAT_NONE), 16.16 taps, (sum + 0x8000) >> 16, CLIP 0..255 */
   const int size = 2 * radius + 1;
   int32_t *taps = (int32_t *) malloc (sizeof (int32_t) * (size_t) size * size);
-  int x, y, i, j, c;
   tbref_gaussian_kernel (radius, sigma, taps);
+  tbref_convolve_argb32 (src, width, height, stride, size, taps, dst, dst_stride);
+  free (taps);
+}
+
+void
+tbref_convolve_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
+    int32_t size, const int32_t *taps, uint8_t *dst, int32_t dst_stride)
+{
+  /* bits_image_fetch_pixel_convolution: window [x-r, x+r] x [y-r, y+r], pixels outside the
+   * image are transparent black (REPEAT_NONE), 16.16 taps, (sum + 0x8000) >> 16, CLIP 0..255 */
+  const int radius = (size - 1) / 2;
+  int x, y, i, j, c;
   for (y = 0; y < height; y++)
     for (x = 0; x < width; x++) {
       int tot[4] = { 0, 0, 0, 0 };
@@ -857,7 +866,6 @@ tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t st
         dst[(size_t) y * dst_stride + 4 * (size_t) x + c] = (uint8_t) TB_CLAMP (v, 0, 255);
       }
     }
-  free (taps);
 }
 
 /* ---------------------------------------------------------------------- */

@@ -13,7 +13,9 @@
  * and does not vendor. The reference has no call site into it and no test
  * that pins a pixel. This file restates the published
  * algorithm (docs/BLENDSPEC.md); oracle/xcheck_gst.c diffs it against a real
- * libgstvideo wherever one is installed.
+ * libgstvideo wherever one is installed. One part is pinned by the reference's
+ * own code: tbref_gaussian_kernel against plugins/ttml/gstttmlblur.c compiled
+ * into oracle/_ref (oracle/refstub/README.md, tests/test_oracle.py).
  *
  * What the overlay contents are (premultiplied, native-endian ARGB32 = bytes
  * B,G,R,A; cleared to 0) is fixed by the reference itself:
@@ -105,6 +107,9 @@ void tbref_matrix_yuv_to_rgb (uint8_t *line, uint32_t width);
 int32_t tbref_gaussian_kernel (int32_t radius, double sigma, int32_t *taps);
 void tbref_blur_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
     int32_t radius, double sigma, uint8_t *dst, int32_t dst_stride);
+/* the convolution alone: size x size taps in 16.16 (what pixman gets from the reference) */
+void tbref_convolve_argb32 (const uint8_t *src, int32_t width, int32_t height, int32_t stride,
+    int32_t size, const int32_t *taps, uint8_t *dst, int32_t dst_stride);
 
 /* Region composition: what gst_ttmlrender_show_regions does
  * around the text (/root/reference/plugins/ttml/gstttmlrender.c:1250-1268,1375-1381) with

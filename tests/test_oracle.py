@@ -382,3 +382,38 @@ def test_scaled_rectangles_in_a_composition(fmt):
     for a, b in zip(got, again):
         assert np.array_equal(a, b)
     assert any(not np.array_equal(a, b) for a, b in zip(got, planes))
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own gstttmlblur.c, compiled from /root/reference
+
+needs_ref = pytest.mark.skipif(oracle.load_ref() is None,
+                               reason="oracle/_ref not built (needs /root/reference: make -C oracle ref)")
+
+
+@needs_ref
+@pytest.mark.parametrize("radius,sigma", [(0, 0.7), (1, 0.5), (2, 1.0), (3, 1.5), (5, 2.5), (8, 4.0), (12, 3.3),
+                                          (20, 10.0), (32, 8.0)])
+def test_gaussian_kernel_equals_the_references_own_code(radius, sigma):
+    """The taps the reference's gst_ttml_blur_create_gaussian_kernel hands to pixman
+    (/root/reference/plugins/ttml/gstttmlblur.c:28-67, executed) against the oracle's
+    restatement: bit for bit, every tap, plus the two size parameters."""
+    img = np.zeros((3, 3, 4), np.uint8)
+    _, params = oracle.ref_blur_argb32(img, radius, sigma)
+    size = 2 * radius + 1
+    assert params[0] == params[1] == size << 16
+    want = oracle.gaussian_kernel(radius, sigma).astype(np.int64).ravel()
+    assert np.array_equal(params[2:], want)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,radius,sigma", [(1, 1, 0.8), (2, 2, 1.0), (3, 4, 2.0), (4, 7, 3.0)])
+def test_blur_through_the_references_call_sequence(seed, radius, sigma):
+    """gst_ttml_blur_image_surface as the reference wrote it (surface -> pixman image, filter,
+    PIXMAN_OP_SRC onto a cleared image of the same stride, new surface) with the convolution
+    itself restated (oracle/refstub/README.md): equals tbref_blur_argb32."""
+    r = np.random.default_rng(seed)
+    a = r.integers(0, 256, (37, 53, 1), dtype=np.uint8)
+    img = np.concatenate([(r.integers(0, 256, (37, 53, 3)) * a // 255).astype(np.uint8), a], axis=2)
+    got, _ = oracle.ref_blur_argb32(img, radius, sigma)
+    assert np.array_equal(got, oracle.blur_argb32(img, radius, sigma))
