@@ -491,7 +491,7 @@ finish_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, std::
     return c->sticky;
   c->stats.h2d_bytes += st.h2d_bytes;
   c->stats.prepare_launches += st.launches;
-  uint64_t groups_all = 0, groups_on = 0;
+  uint64_t groups_all = 0, groups_on = 0, groups_opaque = 0;
   for (Up &u : ups) {
     if (!c->autocrop) {
       ov->rects.push_back (u.rr);
@@ -504,8 +504,11 @@ finish_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, std::
       /* how sparse is what remains after the crop: 16-pixel groups with some alpha against
        * all groups of the kept sub-rectangles */
       groups_all += (uint64_t) ceil_div (s.w, 16) * (uint64_t) s.h;
-      for (int y = s.y; y < s.y + s.h; y++)
-        groups_on += (uint64_t) u.groups[y];
+      for (int y = s.y; y < s.y + s.h; y++) {
+        groups_on += (uint64_t) (u.groups[y] & 0xffff);
+        if (u.rr.ga == 255)
+          groups_opaque += (uint64_t) (u.groups[y] >> 16);
+      }
       RawRect q = u.rr;
       q.dev = u.rr.dev + (size_t) s.y * u.rr.pitch + (size_t) s.x * 4;
       q.x = u.rr.x + s.x;
@@ -517,13 +520,16 @@ finish_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, std::
   }
   if (ov->rects.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
     return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-  /* Text without a background box leaves most 16-byte vectors under the cue untouched. In
-   * place (dst == src, host frames over PCIe) it then pays to look at the overlay before
-   * touching the frame; under a filled box it costs latency for nothing (tools/lazy_probe.py:
-   * +9 % with 44 % transparent vectors, -6 % with none). FLUC_TTMLBLEND_LAZY=0/1 forces it. */
+  /* Text without a background box leaves most 16-byte vectors under the cue untouched, and
+   * under an opaque box (alpha 255) the result does not depend on the frame at all. In place
+   * (dst == src, host frames over PCIe) it then pays to look at the overlay before touching
+   * the frame: transparent vectors are skipped, opaque ones are written without being read.
+   * Under a translucent box it costs latency for nothing (tools/lazy_probe.py).
+   * FLUC_TTMLBLEND_LAZY=0/1 forces it. */
   static const char *lazy_env = getenv ("FLUC_TTMLBLEND_LAZY");
   ov->transparent_fraction = groups_all ? 1.0 - (double) groups_on / (double) groups_all : 0.0;
-  ov->lazy_inplace = lazy_env ? atoi (lazy_env) != 0 : ov->transparent_fraction >= 0.3;
+  ov->opaque_fraction = groups_all ? (double) groups_opaque / (double) groups_all : 0.0;
+  ov->lazy_inplace = lazy_env ? atoi (lazy_env) != 0 : ov->transparent_fraction + ov->opaque_fraction >= 0.3;
   c->overlays[stream] = ov;       /* frames already queued keep the old one */
   c->stats.overlays_set++;
   return 0;

@@ -247,6 +247,7 @@ struct Overlay {
   std::vector<FlucTtmlBlendRect> declared;   /* rectangles as handed in (algorithmic bytes) */
   std::vector<std::unique_ptr<Prepared>> prepared;
   double transparent_fraction = 0.0;   /* of the 16-pixel groups under the kept rectangles */
+  double opaque_fraction = 0.0;        /* alpha 255 all over (and global alpha 1) */
   bool lazy_inplace = false;           /* in-place group launches look at the overlay first */
   ~Overlay ();
 };

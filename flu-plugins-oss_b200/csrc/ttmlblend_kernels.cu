@@ -309,6 +309,17 @@ any_alpha (const uint4 &oa)
   return kind_is_planes (KIND) ? m != 0u : ((m >> (KIND == PK_PACKED_A0 ? 0 : 24)) & 0xffu) != 0u;
 }
 
+/* Is every alpha of this vector 255? With ga == 255 that makes asrc = 255, and then all four
+ * OVER operators give (255, Cs) whatever the destination holds (its weight 255 - asrc is 0):
+ * the destination need not be read. */
+template <int KIND>
+__device__ __forceinline__ bool
+all_opaque (const uint4 &oa)
+{
+  const uint32_t m = oa.x & oa.y & oa.z & oa.w;
+  return kind_is_planes (KIND) ? m == 0xffffffffu : ((m >> (KIND == PK_PACKED_A0 ? 0 : 24)) & 0xffu) == 0xffu;
+}
+
 /* One chunk = kItemsPerChunk consecutive 16-byte vectors of one job. A job is
  * a window of one plane whose rows all see the same set of rectangles
  * (rect_mask): the host cuts every plane at the rectangles' top and bottom
@@ -407,16 +418,21 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
           "OV_DONE:\n"
           "}" :: "r" (bar) : "memory");
       if (LAZY) {
-        /* overlay first: only vectors with some alpha are fetched (all of them in flight
-         * together) and written back */
+        /* overlay first: only vectors with some alpha are written back, and of those only the
+         * ones that are not opaque all over are fetched (all fetches in flight together).
+         * Under an opaque vector the result is the overlay colour whatever the frame holds;
+         * a stand-in with an opaque alpha byte keeps the packed kinds on their fast path. */
+        const bool ga_full = kind_is_planes (KIND) && KIND != PK_PLANE8_RGB ? true :
+            __ldg (&r->ga) == 255;
+        const uint32_t fill = KIND == PK_PACKED_A0 ? 0x000000ffu : KIND == PK_PACKED_A3 ? 0xff000000u : 0u;
 #pragma unroll
-        for (int k = 0; k < kUnroll; k++)
-          act[k] = act[k] && any_alpha<KIND> (*reinterpret_cast<const uint4 *> (ov_smem +
-                  (threadIdx.x + k * kThreads) * 16u));
-#pragma unroll
-        for (int k = 0; k < kUnroll; k++)
-          if (act[k])
+        for (int k = 0; k < kUnroll; k++) {
+          const uint4 oa = *reinterpret_cast<const uint4 *> (ov_smem + (threadIdx.x + k * kThreads) * 16u);
+          act[k] = act[k] && any_alpha<KIND> (oa);
+          f[k] = make_uint4 (fill, fill, fill, fill);
+          if (act[k] && !(ga_full && all_opaque<KIND> (oa)))
             f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
+        }
       }
       const uint32_t ga = KIND == PK_PLANE8 ? 255u : (uint32_t) __ldg (&r->ga);
       const bool sp = KIND == PK_PLANE8 ? false : __ldg (&r->src_premul) != 0;
@@ -606,7 +622,7 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
  * front of it (the table search of the generic kernel above costs ~8 % of a
  * streaming copy: tools/copybench.cu "+prologue"). */
 template <int KIND, bool LAZY>
-__global__ void __launch_bounds__ (kThreads, TTMLBLEND_MIN_CTAS)
+__global__ void __launch_bounds__ (kThreads, LAZY ? 4 : TTMLBLEND_MIN_CTAS)
 ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
 {
   const uint32_t q = P.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, P.lanes_magic);
@@ -649,7 +665,7 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
  * constant-bank reads), then its band as above -- still no global load and no barrier before
  * the first frame load. */
 template <int KIND, bool LAZY>
-__global__ void __launch_bounds__ (kThreads, TTMLBLEND_MIN_CTAS)
+__global__ void __launch_bounds__ (kThreads, LAZY ? 4 : TTMLBLEND_MIN_CTAS)
 ttmlblend_multi_kernel (const __grid_constant__ MultiParams P)
 {
   const uint32_t q = P.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, P.lanes_magic);
@@ -1153,8 +1169,9 @@ launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream)
 /* once per cue: where is the rectangle not transparent?                   */
 
 /* One CTA per row: span[y] = (first x, last x) with alpha != 0, or (w, -1); groups[y] = how
- * many of the row's 16-pixel groups hold any alpha != 0 (how sparse the cue is: decides
- * whether in-place launches look at the overlay before touching the frame). */
+ * many of the row's 16-pixel groups hold any alpha != 0, in the low half, and how many are
+ * opaque all over (alpha 255), in the high half. How sparse / how opaque the cue is decides
+ * whether in-place launches look at the overlay before touching the frame. */
 __global__ void __launch_bounds__ (128)
 ttmlblend_rowspan_kernel (const uint8_t *__restrict__ raw, int pitch, int w, int2 *__restrict__ spans,
     int *__restrict__ groups)
@@ -1164,13 +1181,16 @@ ttmlblend_rowspan_kernel (const uint8_t *__restrict__ raw, int pitch, int w, int
   int lo = w, hi = -1, ng = 0;
   for (int base = 0; base < w; base += blockDim.x) {
     const int x = base + (int) threadIdx.x;
-    const bool on = x < w && (row[x] >> 24) != 0;
+    const uint32_t a = x < w ? row[x] >> 24 : 0u;
+    const bool on = a != 0u;
     if (on) {
       lo = min (lo, x);
       hi = max (hi, x);
     }
     const uint32_t b = __ballot_sync (0xffffffffu, on);      /* two groups of 16 pixels per warp */
+    const uint32_t q = __ballot_sync (0xffffffffu, a == 255u);
     ng += ((b & 0xffffu) ? 1 : 0) + ((b >> 16) ? 1 : 0);
+    ng += (((q & 0xffffu) == 0xffffu) ? 0x10000 : 0) + (((q >> 16) == 0xffffu) ? 0x10000 : 0);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -151,8 +151,9 @@ typedef struct {
   uint64_t cache_bytes;         /* device memory held by overlay caches right now (stream-ordered pool) */
   uint64_t multi_launches;      /* launches that carried frames with different cue layouts (band
                                  * lists of up to 64 frames in the kernel parameters) */
-  uint64_t lazy_launches;       /* group launches in place that read the overlay first and skipped
-                                 * the vectors it leaves untouched (sparse cues; exact either way) */
+  uint64_t lazy_launches;       /* launches in place that read the overlay first: vectors it leaves
+                                 * untouched are skipped, vectors it covers opaquely are written
+                                 * without being read (sparse cues, opaque boxes; exact either way) */
 } FlucTtmlBlendStats;
 
 /* ---- lifetime -------------------------------------------------------- */

@@ -654,8 +654,14 @@ def test_sparse_cues_take_the_overlay_first_path_in_place(ctx, fmt):
     r = cfg.regions[0]
     box = boxed[r.y:r.y + r.h, r.x:r.x + r.w]
     box[box[..., 3] == 0] = (0, 0, 0, 96)          # a translucent black box behind the glyphs
+    # an opaque box: the result under it does not depend on the frame, which is then not even
+    # read (the poisoned-source check below cannot tell, the oracle comparison can: any stale
+    # or garbage source byte leaking into the output would differ)
+    opaque = sparse.copy()
+    box = opaque[r.y:r.y + r.h, r.x:r.x + r.w]
+    box[box[..., 3] == 0] = (16, 16, 16, 255)
     planes = random_frame(fmt, w, h, 3)
-    for name, ov, lazy in (("sparse", sparse, True), ("boxed", boxed, False)):
+    for name, ov, lazy in (("sparse", sparse, True), ("boxed", boxed, False), ("opaque box", opaque, True)):
         want = oracle_blend(fmt, w, h, copy_planes(planes), oracle.ttmlrender_rectangles(ov))
         ctx.overlay_set(5, ov, wl.region_rects(cfg))
         for on_host in (False, True):

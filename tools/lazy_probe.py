@@ -22,7 +22,9 @@ base_cfg = wl.CONFIGS[3]
 n = 32
 for label, cfg in (("background box", base_cfg),
                    ("glyphs only", dataclasses.replace(base_cfg, regions=[dataclasses.replace(r, bg=(0, 0, 0, 0))
-                                                                       for r in base_cfg.regions]))):
+                                                                       for r in base_cfg.regions])),
+                   ("opaque box", dataclasses.replace(base_cfg, regions=[dataclasses.replace(r, opacity=1.0)
+                                                                      for r in base_cfg.regions]))):
     ctx = pkg.TtmlBlend(0)
     ov = wl.overlay_for(cfg)
     zero_vec = float((ov[..., 3].reshape(ov.shape[0], -1, 16).max(axis=2) == 0)[
