@@ -58,11 +58,34 @@ ldg_ptr (T *const *pp)
   return reinterpret_cast<T *> (__ldg (reinterpret_cast<const unsigned long long *> (pp)));
 }
 
-/* byte-granular fall-back for unaligned frames and the tail of a row */
+/* Fall-back for frames that are not 16-byte aligned and for the ragged tail of a row. GStreamer
+ * only guarantees strides that are multiples of 4 (a 1366 or 854 pixel wide frame has 1368 /
+ * 856 byte rows), so the 16 bytes of an item are moved with the widest accesses their address
+ * allows -- two 64-bit, four 32-bit -- and byte by byte only where even that fails or the
+ * row ends inside the item. */
 __device__ __forceinline__ uint4
 ld_frame_bytes (const uint8_t *p, int nvalid)
 {
   uint32_t w[4] = { 0u, 0u, 0u, 0u };
+  const uintptr_t a = reinterpret_cast<uintptr_t> (p);
+  if (nvalid == 16 && (a & 7u) == 0) {
+    const uint2 lo = *reinterpret_cast<const uint2 *> (p), hi = *reinterpret_cast<const uint2 *> (p + 8);
+    return make_uint4 (lo.x, lo.y, hi.x, hi.y);
+  }
+  if ((a & 3u) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (4 * i + 4 <= nvalid) {
+        w[i] = *reinterpret_cast<const uint32_t *> (p + 4 * i);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (4 * i + b < nvalid)
+            w[i] |= (uint32_t) p[4 * i + b] << (8 * b);
+      }
+    }
+    return make_uint4 (w[0], w[1], w[2], w[3]);
+  }
 #pragma unroll
   for (int i = 0; i < 16; i++)
     if (i < nvalid)
@@ -74,6 +97,26 @@ __device__ __forceinline__ void
 st_frame_bytes (uint8_t *p, const uint4 &v, int nvalid)
 {
   const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+  const uintptr_t a = reinterpret_cast<uintptr_t> (p);
+  if (nvalid == 16 && (a & 7u) == 0) {
+    *reinterpret_cast<uint2 *> (p) = make_uint2 (v.x, v.y);
+    *reinterpret_cast<uint2 *> (p + 8) = make_uint2 (v.z, v.w);
+    return;
+  }
+  if ((a & 3u) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (4 * i + 4 <= nvalid) {
+        *reinterpret_cast<uint32_t *> (p + 4 * i) = w[i];
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (4 * i + b < nvalid)
+            p[4 * i + b] = (uint8_t) (w[i] >> (8 * b));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 16; i++)
     if (i < nvalid)
