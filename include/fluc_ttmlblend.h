@@ -94,7 +94,7 @@ typedef enum {
   FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT = -1,
   FLUC_TTMLBLEND_ERROR_NO_DEVICE = -2,     /* no usable CUDA device */
   FLUC_TTMLBLEND_ERROR_CUDA = -3,          /* sticky: context is unusable */
-  FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY = -4,
+  FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY = -4,  /* this call failed; the context stays usable */
   FLUC_TTMLBLEND_ERROR_UNSUPPORTED_FORMAT = -5,
   FLUC_TTMLBLEND_ERROR_NOT_FOUND = -6,     /* unknown stream / ticket / frame */
   FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES = -7
@@ -144,8 +144,9 @@ typedef struct {
   uint64_t prepare_launches;    /* overlay prepare kernel launches */
   uint64_t overlays_set;
   uint64_t algorithmic_bytes;   /* 2*frame bytes (or touched bytes in place) + 4*overlay px */
-  uint64_t h2d_bytes, d2h_bytes;   /* zero-copy host frames: bytes of the windows under the cue
-                                    * (an upper bound when a lazy launch skips transparent vectors) */
+  uint64_t h2d_bytes, d2h_bytes;   /* zero-copy host frames: bytes of the windows under the cue (an
+                                    * upper bound when a lazy launch skips transparent vectors or
+                                    * does not read under opaque ones) */
   double kernel_ms;             /* sum of the CUDA-event times of the timed batches (profiling on) */
   uint64_t kernel_ms_launches;  /* batches included in kernel_ms (one launch each unless mixed) */
   uint64_t cache_bytes;         /* device memory held by overlay caches right now (stream-ordered pool) */
