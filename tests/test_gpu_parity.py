@@ -885,7 +885,7 @@ def test_synchronous_callers_of_many_streams_share_launches(ctx):
         assert not errors, errors
         st = ctx.stats()
         assert st["frames_blended"] == n_threads * n_frames
-        assert st["launches"] < 0.7 * st["frames_blended"], st          # frames did share launches
+        assert st["launches"] < 0.85 * st["frames_blended"], st         # frames did share launches
         # one stream alone is not made to wait: a launch per frame, no lingering
         ctx.stats_reset()
         import time
