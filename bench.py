@@ -347,6 +347,11 @@ def main():
     if os.path.exists(prof) and args.config == 3 and fmt == cfg.fmt:
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            if roofline["traffic"] and launch_ms > 0:
+                # the same launch time against the bytes DRAM really moved (ncu): below the
+                # algorithmic figure because the prepared overlay is 3 B/px and comes from L2
+                roofline["traffic_gbs"] = roofline["traffic"] / (launch_ms * 1e-3) / 1e9
+                roofline["frac_of_traffic"] = roofline["traffic_gbs"] / peak
         except Exception:   # noqa: BLE001
             pass
 
