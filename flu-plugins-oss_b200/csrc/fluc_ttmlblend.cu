@@ -230,6 +230,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->autocrop = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_GROUPS")))
     c->use_groups = atoi (e) != 0;
+  if ((e = getenv ("FLUC_TTMLBLEND_EAGER_PREPARE")))
+    c->eager_prepare = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_MULTI")))
     c->use_multi = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_AUTO_REGISTER")))
@@ -426,6 +428,7 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
     f.overlay = it->second;
     if ((rc = prepare_overlay (c, f.overlay.get (), fmt, W, H, &f.prep)))
       return rc;
+    f.prep->used = true;
   }
   /* a buffer written twice in one batch would race: launch what is queued first */
   if (c->pending_dst.count (dst->plane[0]) && (rc = launch_pending (c)))
@@ -693,6 +696,7 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
   Prepared *prep = nullptr;
   if ((rc = prepare_overlay (c, ov.get (), fmt, W, H, &prep)))
     return rc;
+  prep->used = true;
 
   /* Is the host frame device-accessible (pool frame / host_register)? Then the
    * kernel can reach it over PCIe itself. */

@@ -530,6 +530,20 @@ finish_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, std::
   ov->transparent_fraction = groups_all ? 1.0 - (double) groups_on / (double) groups_all : 0.0;
   ov->opaque_fraction = groups_all ? (double) groups_opaque / (double) groups_all : 0.0;
   ov->lazy_inplace = lazy_env ? atoi (lazy_env) != 0 : ov->transparent_fraction + ov->opaque_fraction >= 0.3;
+  /* The stream's frames will very likely keep the format and size they had: prepare the new
+   * cue for them now, on the upload stream, so that the first frame after a cue change only
+   * has an event to wait for instead of the prepare launches in front of it. */
+  auto prev = c->overlays.find (stream);
+  if (prev != c->overlays.end () && c->eager_prepare) {
+    for (auto &p : prev->second->prepared) {
+      if (!p->used || p->chroma_average != c->chroma_average)
+        continue;
+      Prepared *unused = nullptr;
+      const int rc = prepare_overlay (c, ov.get (), p->format, p->W, p->H, &unused);
+      if (rc)
+        return rc;
+    }
+  }
   c->overlays[stream] = ov;       /* frames already queued keep the old one */
   c->stats.overlays_set++;
   return 0;

@@ -237,6 +237,7 @@ struct Prepared {
   uint64_t overlay_px = 0;             /* sum of clipped w*h */
   cudaEvent_t ready = nullptr;
   bool blend_waited = false;           /* blend stream already ordered after `ready` */
+  bool used = false;                   /* a frame has been blended with it (worth preparing the next cue for) */
   std::vector<std::unique_ptr<Layout>> layouts;
 };
 
@@ -371,6 +372,7 @@ struct Ctx {
   bool chroma_average = false;         /* fluc_ttmlblend_set_chroma_mode (1): NOT bit-exact */
   bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
+  bool eager_prepare = true;           /* FLUC_TTMLBLEND_EAGER_PREPARE=0: prepare at the first frame only */
   bool use_multi = true;               /* FLUC_TTMLBLEND_MULTI=0: dissolved groups go to the table kernel */
   bool profiling = false;
   uint32_t profile_every = 1, profile_seq = 0;   /* FLUC_TTMLBLEND_PROFILE_EVERY */

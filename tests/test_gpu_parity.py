@@ -902,3 +902,30 @@ def test_synchronous_callers_of_many_streams_share_launches(ctx):
         hf.release()
     finally:
         ctx.set_batch(32, 200)
+
+
+def test_next_cue_is_prepared_at_the_cue_change(ctx):
+    """overlay_set prepares the new cue for the format / size the stream's frames have been
+    using, so the first frame after a cue change launches no prepare kernel; a format the
+    stream never used is not prepared ahead."""
+    fmt, w, h = "NV12", 320, 180
+    planes = random_frame(fmt, w, h, 8)
+    src, dst = ctx.acquire(fmt, w, h), ctx.acquire(fmt, w, h)
+    src.upload(planes)
+    ctx.overlay_clear(9731)                            # a stream no other test has touched
+    for k in range(3):
+        rects = [dict(pixels=random_overlay(200, 40, 70 + k), x=60, y=100 + k)]
+        ctx.sync()
+        ctx.stats_reset()
+        ctx.overlay_set_rectangles(9731, rects)
+        at_cue = ctx.stats()["prepare_launches"]
+        ctx.wait(ctx.submit(9731, fmt, w, h, src.c, dst.c))
+        at_frame = ctx.stats()["prepare_launches"] - at_cue
+        if k == 0:
+            assert at_cue == 0 and at_frame > 0          # nothing known about the stream yet
+        else:
+            assert at_cue > 0 and at_frame == 0, (k, at_cue, at_frame)
+        want = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+        assert_planes_equal(dst.download(), want, f"cue {k}")
+    src.release()
+    dst.release()
