@@ -431,6 +431,18 @@ struct Up {
   std::vector<int> groups;      /* per row: 16-pixel groups with any alpha */
 };
 
+/* Is this pointer device memory (a cue produced on the GPU, or left there by a previous stage)? */
+static bool
+on_device (const void *p)
+{
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes (&attr, p) != cudaSuccess) {
+    cudaGetLastError ();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice;
+}
+
 /* What an install does to the context's counters, added once the lock is held again. */
 struct InstallStats {
   uint64_t h2d_bytes = 0;
@@ -631,9 +643,11 @@ overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, cons
       CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rr.h, c->mem_pool, c->up_stream));
       ov->raw_allocs.push_back (d);
       rr.dev = static_cast<uint8_t *> (d);
+      /* cudaMemcpyDefault: the pixels may just as well be in device memory already (UVA tells) */
       CUU (c, lk, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
-              r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyHostToDevice, c->up_stream));
-      st.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+              r.stride, (size_t) rr.w * 4, rr.h, cudaMemcpyDefault, c->up_stream));
+      if (!on_device (r.pixels))
+        st.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
     } else {
       /* the whole source goes up, is scaled to the render size on the GPU, and the clipped
        * part of the scaled image is what gets blended */
@@ -641,8 +655,9 @@ overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, cons
       void *s = nullptr, *d = nullptr, *p = nullptr;
       CUU (c, lk, cudaMallocFromPoolAsync (&s, (size_t) sp * r.height, c->mem_pool, c->up_stream));
       CUU (c, lk, cudaMemcpy2DAsync (s, sp, r.pixels, r.stride, (size_t) r.width * 4, r.height,
-              cudaMemcpyHostToDevice, c->up_stream));
-      st.h2d_bytes += (uint64_t) r.width * 4 * r.height;
+              cudaMemcpyDefault, c->up_stream));
+      if (!on_device (r.pixels))
+        st.h2d_bytes += (uint64_t) r.width * 4 * r.height;
       plans.push_back (scale_row_plan (r.height, rh));
       CUU (c, lk, cudaMallocFromPoolAsync (&p, (size_t) rh * sizeof (int4), c->mem_pool, c->up_stream));
       CUU (c, lk, cudaMemcpyAsync (p, plans.back ().data (), (size_t) rh * sizeof (int4), cudaMemcpyHostToDevice,
@@ -733,8 +748,9 @@ overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stre
       CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) lp * r.h, c->mem_pool, c->up_stream));
       layers.push_back (d);
       CUU (c, lk, cudaMemcpy2DAsync (d, lp, r.layer, r.layer_stride, (size_t) r.w * 4, r.h,
-              cudaMemcpyHostToDevice, c->up_stream));
-      st.h2d_bytes += (uint64_t) r.w * 4 * r.h;
+              cudaMemcpyDefault, c->up_stream));
+      if (!on_device (r.layer))
+        st.h2d_bytes += (uint64_t) r.w * 4 * r.h;
       p.layer = static_cast<uint8_t *> (d);
       p.layer_pitch = lp;
     }

@@ -120,7 +120,8 @@ typedef struct {
  * gst_video_overlay_composition_blend does with gst_video_blend_scale_linear_RGBA
  * (once per cue, cached like everything else); its pixel size must then be >= 2x2. */
 typedef struct {
-  const uint8_t *pixels;   /* host memory, read before the call returns */
+  const uint8_t *pixels;   /* host memory -- or device memory of the context's GPU: a cue that is
+                            * already in HBM is copied there -- read before the call returns */
   int32_t width, height, stride;
   int32_t x, y;
   float global_alpha;      /* 1.0f for ttmlrender */

@@ -929,3 +929,34 @@ def test_next_cue_is_prepared_at_the_cue_change(ctx):
         assert_planes_equal(dst.download(), want, f"cue {k}")
     src.release()
     dst.release()
+
+
+def test_cue_pixels_already_in_device_memory(ctx):
+    """overlay_set / overlay_set_rectangles accept pixels that are in HBM already (a cue left
+    there by a previous GPU stage): same result, and nothing counted as host -> device."""
+    tb = pkg.ttmlblend
+    w, h = 320, 180
+    px = random_overlay(200, 40, 77)
+    holder = ctx.acquire("BGRA", 200, 40)              # a device BGRA surface to put the cue in
+    holder.upload([px.reshape(40, 800)])
+    ctx.sync()
+    ctx.stats_reset()
+    arr = (tb.Rectangle * 1)(tb.Rectangle(holder.c.plane[0], 200, 40, holder.c.stride[0], 60, 100, 1.0,
+                                          tb.FLAG_PREMULTIPLIED_ALPHA, 0, 0))
+    ctx._check(ctx.lib.fluc_ttmlblend_overlay_set_rectangles(ctx.h, 9801, arr, 1), "overlay_set_rectangles")
+    assert ctx.stats()["h2d_bytes"] == 0
+    for fmt in ("NV12", "BGRA"):
+        planes = random_frame(fmt, w, h, 9)
+        want = oracle_blend(fmt, w, h, copy_planes(planes), [dict(pixels=px, x=60, y=100)])
+        got = gpu_blend(ctx, fmt, w, h, planes, mode="out", stream=9801, set_overlay=False)
+        assert_planes_equal(got, want, f"device cue {fmt}")
+    # scaled, too
+    arr[0].render_width, arr[0].render_height = 260, 33
+    ctx._check(ctx.lib.fluc_ttmlblend_overlay_set_rectangles(ctx.h, 9801, arr, 1), "overlay_set_rectangles")
+    planes = random_frame("I420", w, h, 10)
+    want = oracle_blend("I420", w, h, copy_planes(planes), [dict(pixels=px, x=60, y=100, render_width=260,
+                                                                  render_height=33)])
+    got = gpu_blend(ctx, "I420", w, h, planes, mode="out", stream=9801, set_overlay=False)
+    assert_planes_equal(got, want, "device cue, scaled")
+    holder.release()
+    ctx.overlay_clear(9801)
