@@ -25,7 +25,7 @@ main (void)
 {
   static const int sizes[][2] = { {1, 1}, {2, 2}, {3, 5}, {17, 9}, {64, 48}, {63, 47}, {129, 3} };
   int fmt, s, k, fails = 0;
-  for (fmt = TBREF_FORMAT_I420; fmt <= TBREF_FORMAT_NV24; fmt++) {
+  for (fmt = TBREF_FORMAT_I420; fmt <= TBREF_FORMAT_BGR; fmt++) {
     if (fmt > TBREF_FORMAT_ABGR && fmt < TBREF_FORMAT_Y42B)
       continue;
     for (s = 0; s < (int) (sizeof sizes / sizeof sizes[0]); s++) {
@@ -90,6 +90,49 @@ main (void)
       img[i] = rnd ();
     tbref_gaussian_kernel (3, 1.5, taps);
     tbref_blur_argb32 (img, 7, 5, 28, 3, 1.5, out, 28);
+  }
+  {
+    /* rectangle scaling: exact-size buffers in and out, sizes that make the line cache jump,
+     * and a composition that scales before it blends */
+    static const int cases[][4] = { {2, 2, 1, 1}, {2, 2, 3, 3}, {7, 5, 20, 3}, {33, 40, 5, 90}, {64, 9, 1, 30},
+      {3, 1200, 4, 37}, {5, 37, 2, 1200} };
+    size_t c, i;
+    for (c = 0; c < sizeof cases / sizeof cases[0]; c++) {
+      const int sw = cases[c][0], sh = cases[c][1], dw = cases[c][2], dh = cases[c][3];
+      uint8_t *src = (uint8_t *) malloc ((size_t) sw * sh * 4), *dst = (uint8_t *) malloc ((size_t) dw * dh * 4);
+      uint8_t *y = (uint8_t *) malloc (64 * 48), *uv = (uint8_t *) malloc (64 * 24);
+      TbRefFrame f;
+      TbRefRectangle r;
+      for (i = 0; i < (size_t) sw * sh * 4; i++)
+        src[i] = rnd ();
+      tbref_scale_linear_rgba (src, sw, sh, sw * 4, dw, dh, dst);
+      memset (&f, 0, sizeof f);
+      f.format = TBREF_FORMAT_NV12;
+      f.width = 64;
+      f.height = 48;
+      f.data[0] = y;
+      f.data[1] = uv;
+      f.stride[0] = f.stride[1] = 64;
+      memset (y, 100, 64 * 48);
+      memset (uv, 128, 64 * 24);
+      memset (&r, 0, sizeof r);
+      r.pixels = src;
+      r.width = sw;
+      r.height = sh;
+      r.stride = sw * 4;
+      r.x = -3;
+      r.y = 5;
+      r.global_alpha = 1.0f;
+      r.flags = TBREF_FLAG_PREMULTIPLIED_ALPHA;
+      r.render_width = dw;
+      r.render_height = dh;
+      if (!tbref_composition_blend (&f, &r, 1))
+        fails++;
+      free (src);
+      free (dst);
+      free (y);
+      free (uv);
+    }
   }
   printf ("oracle selftest: %d failure(s)\n", fails);
   return fails ? 1 : 0;
