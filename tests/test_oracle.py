@@ -417,3 +417,29 @@ def test_blur_through_the_references_call_sequence(seed, radius, sigma):
     img = np.concatenate([(r.integers(0, 256, (37, 53, 3)) * a // 255).astype(np.uint8), a], axis=2)
     got, _ = oracle.ref_blur_argb32(img, radius, sigma)
     assert np.array_equal(got, oracle.blur_argb32(img, radius, sigma))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_scaled_compositions_oracle_vs_model(seed):
+    """Random compositions in which some rectangles carry a render size, every format in turn:
+    the line-structured oracle (scale, then gst_video_blend) against the numpy model."""
+    r = np.random.default_rng(12000 + seed)
+    fmt = ALL_FORMATS[seed % len(ALL_FORMATS)]
+    w, h = int(r.integers(8, 200)), int(r.integers(8, 120))
+    rects = []
+    for i in range(int(r.integers(1, 5))):
+        sw, sh = int(r.integers(2, 80)), int(r.integers(2, 60))
+        pm = bool(r.integers(0, 2))
+        d = dict(pixels=random_overlay(sw, sh, 50 * seed + i, premultiplied=pm), premultiplied=pm,
+                 global_alpha=float(r.choice([1.0, 1.0, 0.4])))
+        rw, rh = sw, sh
+        if r.random() < 0.7:
+            rw, rh = int(r.integers(1, 2 * w)), int(r.integers(1, 2 * h))
+            d.update(render_width=rw, render_height=rh)
+        d.update(x=int(r.integers(-rw, w)), y=int(r.integers(-rh, h)))
+        rects.append(d)
+    planes = random_frame(fmt, w, h, seed, opaque=fmt not in PACKED or bool(r.integers(0, 2)))
+    want = model_blend(fmt, w, h, copy_planes(planes), rects)
+    got = oracle_blend(fmt, w, h, copy_planes(planes), rects)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), (fmt, seed, i, int((a != b).sum()))
