@@ -187,6 +187,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     return FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY;
   Ctx *c = &t->c;
   c->device = device;
+  if (const char *sy = getenv ("FLUC_TTMLBLEND_SYNC"))
+    c->blocking_sync = strcmp (sy, "block") == 0;
   bool ok = true;
   ok &= cudaStreamCreateWithFlags (&c->blend_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->up_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -196,7 +198,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     ok &= cudaEventCreateWithFlags (&c->ev_fence[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < kLanes && ok; i++) {
     ok &= cudaStreamCreateWithFlags (&c->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok &= cudaEventCreateWithFlags (&c->lanes[i].done, cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags (&c->lanes[i].done,
+        cudaEventDisableTiming | (c->blocking_sync ? cudaEventBlockingSync : 0)) == cudaSuccess;
   }
   ok &= cudaEventCreate (&c->timer0) == cudaSuccess;
   ok &= cudaEventCreate (&c->timer1) == cudaSuccess;
@@ -325,8 +328,12 @@ fluc_ttmlblend_last_cuda_error (FlucTtmlBlend *thiz)
 {
   if (!thiz)
     return "";
+  /* a copy per calling thread: the context's own string changes under other threads' errors
+   * once the lock is dropped */
+  static thread_local std::string copy;
   std::unique_lock<std::mutex> lk (thiz->c.mu);
-  return thiz->c.cuda_error.c_str ();
+  copy = thiz->c.cuda_error;
+  return copy.c_str ();
 }
 
 /* ---- overlay --------------------------------------------------------- */
@@ -413,6 +420,69 @@ fluc_ttmlblend_set_chroma_mode (FlucTtmlBlend *thiz, int mode)
 
 /* ---- device-resident frames ------------------------------------------ */
 
+/* The bytes a frame's planes occupy, as at most three ranges (planes that are neighbours in
+ * memory -- pool frames, GStreamer's default layout -- come out as one). */
+struct FrameExtent {
+  uintptr_t lo[3], hi[3];
+  int n = 0;
+  FrameExtent (int fmt, int W, int H, const FlucTtmlBlendFrame *f)
+  {
+    for (int pl = 0; pl < format_planes (fmt); pl++) {
+      const uintptr_t a = (uintptr_t) f->plane[pl];
+      const uintptr_t b = a + (uintptr_t) f->stride[pl] * (uintptr_t) (plane_rows (fmt, pl, H) - 1) +
+          (uintptr_t) plane_row_bytes (fmt, pl, W);
+      if (n && a >= lo[n - 1] && a <= hi[n - 1] + 4096)
+        hi[n - 1] = std::max (hi[n - 1], b);
+      else {
+        lo[n] = a;
+        hi[n] = b;
+        n++;
+      }
+    }
+  }
+  uintptr_t hull_lo () const
+  {
+    uintptr_t v = lo[0];
+    for (int i = 1; i < n; i++)
+      v = std::min (v, lo[i]);
+    return v;
+  }
+  uintptr_t hull_hi () const
+  {
+    uintptr_t v = hi[0];
+    for (int i = 1; i < n; i++)
+      v = std::max (v, hi[i]);
+    return v;
+  }
+  bool hits (const IntervalSet &s) const
+  {
+    for (int i = 0; i < n; i++)
+      if (s.overlaps (lo[i], hi[i]))
+        return true;
+    return false;
+  }
+  void add_to (IntervalSet &s) const
+  {
+    for (int i = 0; i < n; i++)
+      s.add (lo[i], hi[i]);
+  }
+};
+
+/* A frame joins the pending batch only if no queued frame conflicts with it: the CTAs of one
+ * launch run in no particular order, so a frame that writes what a queued frame writes (the
+ * same buffer twice) or reads (ping-pong pools), or reads what a queued frame writes (chained
+ * overlays: stream A's output is stream B's input) has the batch launched first; launches on
+ * the blend stream then run in order. Frames that only share a source are fine. */
+static int
+order_against_pending (Ctx *c, const FrameExtent &src, const FrameExtent &dst, bool inplace)
+{
+  if (c->pending.empty ())
+    return 0;
+  if (dst.hits (c->pending_dst) || dst.hits (c->pending_src) || (!inplace && src.hits (c->pending_dst)))
+    return launch_pending (c);
+  return 0;
+}
+
 static int
 submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t frame_flags,
     const FlucTtmlBlendFrame *src, const FlucTtmlBlendFrame *dst, uint64_t *ticket)
@@ -430,8 +500,9 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
       return rc;
     f.prep->used = true;
   }
-  /* a buffer written twice in one batch would race: launch what is queued first */
-  if (c->pending_dst.count (dst->plane[0]) && (rc = launch_pending (c)))
+  const bool inplace = src->plane[0] == dst->plane[0];
+  const FrameExtent xs (fmt, W, H, src), xd (fmt, W, H, dst);
+  if ((rc = order_against_pending (c, xs, xd, inplace)))
     return rc;
   f.layout = find_layout (c, f.prep, f.overlay && f.overlay->lazy_inplace, fmt, W, H, frame_flags, src, dst,
       src->plane[0] == dst->plane[0]);
@@ -446,7 +517,9 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
     *ticket = f.ticket;
   if (c->pending.empty ())
     c->oldest_pending = std::chrono::steady_clock::now ();
-  c->pending_dst.insert (dst->plane[0]);
+  xd.add_to (c->pending_dst);
+  if (!inplace)
+    xs.add_to (c->pending_src);
   c->pending.push_back (std::move (f));
   if (c->pending.size () >= c->max_batch)
     return launch_pending (c);
@@ -540,6 +613,11 @@ fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
         return rc;
     }
   }
+  /* a batch whose launch failed half way: still synchronise with what went out, then say so */
+  int failed = 0;
+  for (const Ctx::FailedRange &fr : c->failed_ranges)
+    if (ticket >= fr.first && ticket <= fr.last)
+      failed = fr.rc;
   cudaEvent_t ev = nullptr;
   for (auto &b : c->batches)
     if (b.last_ticket >= ticket) {
@@ -547,7 +625,7 @@ fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
       break;
     }
   if (!ev) {
-    return 0;                   /* already reaped: finished */
+    return failed;              /* already reaped: finished */
   }
   /* the event stays valid while we wait: batches are only reaped under mu,
    * and a reaped event goes back to the pool, not destroyed */
@@ -560,7 +638,7 @@ fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
     return c->sticky;
   }
   reap_batches (c);
-  return 0;
+  return failed;
 }
 
 int
@@ -631,40 +709,71 @@ fluc_ttmlblend_set_batch (FlucTtmlBlend *thiz, uint32_t max_frames, uint32_t lin
 
 /* ---- host-resident frames -------------------------------------------- */
 
+/* Everything of ours that may still touch host memory has finished: queued frames launched,
+ * blend stream and staging lanes drained. Needed before a registration goes away. */
+static void
+drain_host_users (Ctx *c)
+{
+  launch_pending (c);
+  cudaStreamSynchronize (c->blend_stream);
+  for (int i = 0; i < kLanes; i++)
+    cudaStreamSynchronize (c->lanes[i].stream);
+}
+
+/* How many automatic plane registrations are kept: a pool's worth of buffers (16) times three
+ * planes for every stream that uses them, at least 192. */
+static size_t
+auto_reg_limit (const Ctx *c)
+{
+  return std::max<size_t> (192, std::min<size_t> (8192, 48 * c->auto_streams.size ()));
+}
+
 /* Opt-in (fluc_ttmlblend_set_auto_register): pin the memory of pageable host frames the
  * first time they are seen, so that later frames from the same buffers -- GStreamer buffer
  * pools recycle them -- take the zero-copy path (10.7 k instead of 1.7 k 4K frames/s,
- * tools/pageable_probe.py). Least recently used plane registrations are dropped beyond 192. The
- * caller promises not to free registered memory without host_unregister / context free. */
+ * tools/pageable_probe.py). Least recently used plane registrations are dropped beyond the limit.
+ * The owner of the memory must call host_forget / host_unregister before it frees it: a
+ * registration pins the physical pages, and a later allocation at the same address would be
+ * taken for the registered one while the GPU still reaches the old pages. */
 static void
-auto_register_frame (Ctx *c, int fmt, int H, const FlucTtmlBlendFrame *hf)
+auto_register_frame (Ctx *c, uint32_t stream, int fmt, int H, const FlucTtmlBlendFrame *hf)
 {
   /* plane by plane: the planes of a frame need not be neighbours in memory */
   for (int pl = 0; pl < format_planes (fmt); pl++) {
     const uintptr_t lo = (uintptr_t) hf->plane[pl];
     const uintptr_t hi = lo + (uintptr_t) hf->stride[pl] * plane_rows (fmt, pl, H);
-    bool known = false;
-    for (size_t i = 0; i < c->auto_regs.size () && !known; i++)
-      if (c->auto_regs[i].first <= lo && hi <= c->auto_regs[i].second) {
-        std::rotate (c->auto_regs.begin (), c->auto_regs.begin () + i, c->auto_regs.begin () + i + 1);
-        known = true;           /* now most recently used */
+    auto it = c->auto_regs.upper_bound (lo);
+    if (it != c->auto_regs.begin ()) {
+      --it;
+      if (it->first <= lo && hi <= it->second.hi) {
+        it->second.tick = ++c->auto_tick;      /* known: now most recently used */
+        continue;
       }
-    if (known)
-      continue;
+    }
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes (&attr, (void *) lo) == cudaSuccess && attr.type == cudaMemoryTypeHost)
       continue;                 /* already pinned by someone else */
     cudaGetLastError ();
-    if (c->auto_regs.size () >= 192) {
-      /* nothing queued may still read the oldest one */
-      launch_pending (c);
-      cudaStreamSynchronize (c->blend_stream);
-      cudaHostUnregister ((void *) c->auto_regs.back ().first);
-      c->auto_regs.pop_back ();
+    c->auto_streams.insert (stream);
+    if (c->auto_regs.size () >= auto_reg_limit (c)) {
+      /* nothing queued or in flight may still use the oldest one */
+      drain_host_users (c);
+      auto oldest = c->auto_regs.begin ();
+      for (auto k = c->auto_regs.begin (); k != c->auto_regs.end (); ++k)
+        if (k->second.tick < oldest->second.tick)
+          oldest = k;
+      cudaHostUnregister ((void *) oldest->first);
+      c->auto_regs.erase (oldest);
     }
-    if (cudaHostRegister ((void *) lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess)
-      c->auto_regs.insert (c->auto_regs.begin (), { lo, hi });
-    else
+    void *dev = nullptr;
+    if (cudaHostRegister ((void *) lo, hi - lo, cudaHostRegisterDefault) == cudaSuccess) {
+      if (cudaHostGetDevicePointer (&dev, (void *) lo, 0) == cudaSuccess)
+        c->auto_regs[lo] = { hi, ++c->auto_tick, (uintptr_t) dev };
+      else {
+        cudaGetLastError ();
+        cudaHostUnregister ((void *) lo);
+      }
+    } else
       cudaGetLastError ();      /* cannot pin (memlock limit, odd mapping): staged copies it is */
   }
 }
@@ -702,7 +811,7 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
    * kernel can reach it over PCIe itself. */
   const int n_planes = format_planes (fmt);
   if (c->auto_register && c->host_mode != HM_STAGED)
-    auto_register_frame (c, fmt, H, hf);
+    auto_register_frame (c, stream, fmt, H, hf);
   FlucTtmlBlendFrame zf = {};
   bool mapped = c->host_mode != HM_STAGED;
   for (int pl = 0; pl < n_planes && mapped; pl++) {
@@ -715,9 +824,26 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
         mapped = false;
       continue;
     }
-    cudaPointerAttributes attr;
+    const uintptr_t lo = (uintptr_t) hf->plane[pl];
+    const uintptr_t hi = lo + (uintptr_t) hf->stride[pl] * (uintptr_t) (plane_rows (fmt, pl, H) - 1) +
+        (uintptr_t) plane_row_bytes (fmt, pl, W);
+    /* planes this context registered itself are known too, with their whole range */
+    auto ar = c->auto_regs.upper_bound (lo);
+    if (ar != c->auto_regs.begin () && (--ar)->first <= lo && hi <= ar->second.hi) {
+      zf.plane[pl] = (void *) (ar->second.dev + (lo - ar->first));
+      zf.stride[pl] = hf->stride[pl];
+      if ((((uintptr_t) zf.plane[pl] | (uintptr_t) zf.stride[pl]) & 15u) != 0)
+        mapped = false;
+      continue;
+    }
+    /* anything else: ask the driver, for the first and for the last byte of the plane (a
+     * registration that ends inside the plane must not count) */
+    cudaPointerAttributes attr, attr_end;
     if (cudaPointerGetAttributes (&attr, hf->plane[pl]) != cudaSuccess ||
-        attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+        attr.type != cudaMemoryTypeHost || !attr.devicePointer ||
+        cudaPointerGetAttributes (&attr_end, (const void *) (hi - 1)) != cudaSuccess ||
+        attr_end.type != cudaMemoryTypeHost || !attr_end.devicePointer ||
+        (uintptr_t) attr_end.devicePointer - (uintptr_t) attr.devicePointer != hi - 1 - lo) {
       cudaGetLastError ();
       mapped = false;
     } else {
@@ -740,14 +866,23 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
     f.ticket = tk;
     f.stream = stream;
     note_stream (c, stream);
-    if (c->pending_dst.count (zf.plane[0]) && (rc = launch_pending (c)))
+    const FrameExtent xz (fmt, W, H, &zf), xh (fmt, W, H, hf);
+    if ((rc = order_against_pending (c, xz, xz, true)))
       return rc;
+    /* the same buffer still on its way through a staging lane (it was not device-accessible a
+     * moment ago): the blend stream waits for that lane */
+    for (int i = 0; i < kLanes; i++)
+      if (c->lanes[i].busy && xh.hull_lo () < c->lanes[i].host_hi && c->lanes[i].host_lo < xh.hull_hi ())
+        CU (c, cudaStreamWaitEvent (c->blend_stream, c->lanes[i].done, 0));
     f.layout = find_layout (c, prep, ov->lazy_inplace, fmt, W, H, frame_flags, &zf, &zf, true);
     for (int pl = 0; pl < 3; pl++) {
       f.src[pl] = static_cast<const uint8_t *> (zf.plane[pl]);
       f.dst[pl] = static_cast<uint8_t *> (zf.plane[pl]);
     }
-    c->pending_dst.insert (zf.plane[0]);
+    xz.add_to (c->pending_dst);
+    if (zf.plane[0] != hf->plane[0])
+      xh.add_to (c->pending_dst);       /* no unified addressing: known under both addresses */
+    xh.add_to (c->inflight_host);
     c->stats.h2d_bytes += f.layout->window_bytes;
     c->stats.d2h_bytes += f.layout->window_bytes;
     if (c->pending.empty ())
@@ -769,6 +904,17 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
     l.busy = false;
     l.keep.reset ();
   }
+  /* Ordering against other work on the same host buffer: two overlays on one frame through two
+   * lanes, or a zero-copy frame of this buffer that is queued or still running. */
+  const FrameExtent xh (fmt, W, H, hf);
+  const uintptr_t hull_lo = xh.hull_lo (), hull_hi = xh.hull_hi ();
+  if (xh.hits (c->pending_dst) && (rc = launch_pending (c)))
+    return rc;
+  if (xh.hits (c->inflight_host) && !c->batches.empty ())
+    CU (c, cudaStreamWaitEvent (l.stream, c->batches.back ().done, 0));
+  for (int i = 0; i < kLanes; i++)
+    if (i != lane_idx && c->lanes[i].busy && hull_lo < c->lanes[i].host_hi && c->lanes[i].host_lo < hull_hi)
+      CU (c, cudaStreamWaitEvent (l.stream, c->lanes[i].done, 0));
 
   /* device staging frame: same strides as a pool frame */
   FlucTtmlBlendFrame df = {};
@@ -852,6 +998,8 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
   CU (c, cudaEventRecord (l.done, l.stream));
   l.busy = true;
   l.ticket = tk;
+  l.host_lo = hull_lo;
+  l.host_hi = hull_hi;
   l.keep = ov;
   c->lane_tickets[tk] = lane_idx;
   c->stats.frames_blended++;
@@ -902,17 +1050,41 @@ int
 fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr)
 {
   ENTER (thiz);
-  for (size_t i = 0; i < c->auto_regs.size (); i++)
-    if (c->auto_regs[i].first == (uintptr_t) ptr) {
-      c->auto_regs.erase (c->auto_regs.begin () + i);
-      break;
-    }
+  /* frames of this memory may be queued or on the bus */
+  drain_host_users (c);
+  c->auto_regs.erase ((uintptr_t) ptr);
   cudaError_t e = cudaHostUnregister (ptr);
   if (e != cudaSuccess) {
     cudaGetLastError ();
     return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
   }
   return 0;
+}
+
+int
+fluc_ttmlblend_host_forget (FlucTtmlBlend *thiz, const void *ptr, size_t bytes)
+{
+  ENTER (thiz);
+  if (!ptr || !bytes)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  const uintptr_t lo = (uintptr_t) ptr, hi = lo + bytes;
+  bool drained = false;
+  int n = 0;
+  for (auto it = c->auto_regs.begin (); it != c->auto_regs.end ();) {
+    if (it->first < hi && lo < it->second.hi) {
+      if (!drained) {
+        drain_host_users (c);
+        drained = true;
+      }
+      if (cudaHostUnregister ((void *) it->first) != cudaSuccess)
+        cudaGetLastError ();
+      it = c->auto_regs.erase (it);
+      n++;
+    } else {
+      ++it;
+    }
+  }
+  return n;
 }
 
 /* ---- frame pool ------------------------------------------------------ */

@@ -17,7 +17,7 @@ event_get (Ctx *c)
     return e;
   }
   cudaEvent_t e = nullptr;
-  cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+  cudaEventCreateWithFlags (&e, cudaEventDisableTiming | (c->blocking_sync ? cudaEventBlockingSync : 0));
   return e;
 }
 
@@ -108,6 +108,8 @@ reap_batches (Ctx *c)
     c->event_pool.push_back (b.done);
     c->batches.pop_front ();
   }
+  if (c->batches.empty ())
+    c->inflight_host.clear ();
 }
 
 /* Launches everything pending as one batch (per plane kind). mu held. */
@@ -194,62 +196,89 @@ launch_pending (Ctx *c)
         emit_table_jobs (f.layout->gjobs, f, by_kind);
     }
   }
+  const uint64_t first_ticket = c->pending.front ().ticket;
   c->pending.clear ();
   c->pending_dst.clear ();
+  c->pending_src.clear ();
   size_t n_launches = n_multis;
   for (Group &g : groups)
     n_launches += g.dissolved ? 0 : 1;
   for (int k = 0; k < kPlaneKinds * 2; k++)
     n_launches += !by_kind[k].empty ();
-  /* an event pair keeps the batch from overlapping its neighbours (~2 us of stream time):
-   * sample every profile_every-th batch. A batch of several launches (several groups /
-   * kinds) is timed from before its first to after its last launch. */
-  if (c->profiling && n_launches >= 1 && (c->profile_seq++ % c->profile_every) == 0) {
-    for (cudaEvent_t *e : { &b.t0, &b.t1 }) {
-      if (!c->timing_pool.empty ()) {
-        *e = c->timing_pool.back ();
-        c->timing_pool.pop_back ();
-      } else {
-        CU (c, cudaEventCreate (e));
+  /* From here on the frames are no longer queued: whatever happens, a batch with a `done` event
+   * is pushed, so that wait() on these tickets synchronises with what did get launched, and a
+   * failure half way (out of memory for a table slot, say -- the context stays usable) is
+   * remembered for them instead of being reported as finished work. */
+  auto issue = [&]() -> int {
+    /* an event pair keeps the batch from overlapping its neighbours (~2 us of stream time):
+     * sample every profile_every-th batch. A batch of several launches (several groups /
+     * kinds) is timed from before its first to after its last launch. */
+    if (c->profiling && n_launches >= 1 && (c->profile_seq++ % c->profile_every) == 0) {
+      for (cudaEvent_t *e : { &b.t0, &b.t1 }) {
+        if (!c->timing_pool.empty ()) {
+          *e = c->timing_pool.back ();
+          c->timing_pool.pop_back ();
+        } else {
+          CU (c, cudaEventCreate (e));
+        }
       }
     }
+    if (b.t0)
+      CU (c, cudaEventRecord (b.t0, c->blend_stream));
+    for (Group &g : groups) {
+      if (g.dissolved)
+        continue;
+      CU (c, launch_group (g.P, g.kind, c->blend_stream));
+      c->stats.launches++;
+      c->stats.group_launches++;
+      if (g.P.flags & JF_LAZY)
+        c->stats.lazy_launches++;
+    }
+    for (size_t k = 0; k < n_multis; k++) {
+      MultiGroup &m = *c->multis[k];
+      CU (c, launch_multi (m.P, m.kind, c->blend_stream));
+      c->stats.launches++;
+      c->stats.multi_launches++;
+      if (m.P.flags & JF_LAZY)
+        c->stats.lazy_launches++;
+    }
+    for (int k = 0; k < kPlaneKinds * 2; k++) {
+      if (by_kind[k].empty ())
+        continue;
+      TableSlot &s = c->slots[c->next_slot];
+      c->next_slot = (c->next_slot + 1) % kTableSlots;
+      int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0,
+          c->blend_stream);
+      if (rc)
+        return rc;
+    }
+    if (b.t1)
+      CU (c, cudaEventRecord (b.t1, c->blend_stream));
+    return 0;
+  };
+  const int rc = issue ();
+  if (rc) {
+    if (c->failed_ranges.size () >= 64)
+      c->failed_ranges.pop_front ();
+    c->failed_ranges.push_back ({ first_ticket, b.last_ticket, rc });
+    if (b.t0) { c->timing_pool.push_back (b.t0); b.t0 = nullptr; }
+    if (b.t1) { c->timing_pool.push_back (b.t1); b.t1 = nullptr; }
   }
-  if (b.t0)
-    CU (c, cudaEventRecord (b.t0, c->blend_stream));
-  for (Group &g : groups) {
-    if (g.dissolved)
-      continue;
-    CU (c, launch_group (g.P, g.kind, c->blend_stream));
-    c->stats.launches++;
-    c->stats.group_launches++;
-    if (g.P.flags & JF_LAZY)
-      c->stats.lazy_launches++;
-  }
-  for (size_t k = 0; k < n_multis; k++) {
-    MultiGroup &m = *c->multis[k];
-    CU (c, launch_multi (m.P, m.kind, c->blend_stream));
-    c->stats.launches++;
-    c->stats.multi_launches++;
-    if (m.P.flags & JF_LAZY)
-      c->stats.lazy_launches++;
-  }
-  for (int k = 0; k < kPlaneKinds * 2; k++) {
-    if (by_kind[k].empty ())
-      continue;
-    TableSlot &s = c->slots[c->next_slot];
-    c->next_slot = (c->next_slot + 1) % kTableSlots;
-    int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0,
-        c->blend_stream);
-    if (rc)
-      return rc;
-  }
-  if (b.t1)
-    CU (c, cudaEventRecord (b.t1, c->blend_stream));
   b.done = event_get (c);
-  CU (c, cudaEventRecord (b.done, c->blend_stream));
-  c->batches.push_back (std::move (b));
+  if (b.done && cudaEventRecord (b.done, c->blend_stream) == cudaSuccess) {
+    c->batches.push_back (std::move (b));
+  } else {
+    /* not even an event: only a broken context gets here */
+    cudaGetLastError ();
+    if (b.done)
+      c->event_pool.push_back (b.done);
+    if (!c->sticky) {
+      c->sticky = FLUC_TTMLBLEND_ERROR_CUDA;
+      c->cuda_error = "launch_pending: cannot record the batch event";
+    }
+  }
   c->launched_cv.notify_all ();
-  return 0;
+  return rc ? rc : c->sticky;
 }
 
 void
@@ -269,6 +298,7 @@ scheduler_main (Ctx *c)
       else {
         c->pending.clear ();
         c->pending_dst.clear ();
+        c->pending_src.clear ();
       }
       c->launched_cv.notify_all ();   /* also when the launch failed: waiters must not sleep on */
     } else {

@@ -208,4 +208,26 @@ tb_hook_scale_row_plan (int src_h, int dst_h, int32_t *rows)
   return (int) plan.size ();
 }
 
+/* The hazard tracker's range set: ops[i] = (kind, lo, hi) with kind 0 = add, 1 = query; every
+ * query's answer goes to out[] in order. Returns the number of ranges held at the end, which
+ * are written to ranges[2*k], ranges[2*k+1] (up to max_ranges). */
+__attribute__ ((visibility ("default"))) int
+tb_hook_interval_set (const uint64_t *ops, int n_ops, int32_t *out, uint64_t *ranges, int max_ranges)
+{
+  IntervalSet s;
+  int q = 0;
+  for (int i = 0; i < n_ops; i++) {
+    const uint64_t kind = ops[3 * i], lo = ops[3 * i + 1], hi = ops[3 * i + 2];
+    if (kind == 0)
+      s.add ((uintptr_t) lo, (uintptr_t) hi);
+    else
+      out[q++] = s.overlaps ((uintptr_t) lo, (uintptr_t) hi) ? 1 : 0;
+  }
+  for (size_t k = 0; k < s.v.size () && (int) k < max_ranges; k++) {
+    ranges[2 * k] = s.v[k].first;
+    ranges[2 * k + 1] = s.v[k].second;
+  }
+  return (int) s.v.size ();
+}
+
 }  /* extern "C" */

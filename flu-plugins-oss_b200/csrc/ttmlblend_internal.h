@@ -300,6 +300,56 @@ struct TableSlot {
   cudaEvent_t uploaded = nullptr;      /* table copy has landed */
 };
 
+/* Byte ranges of the frames queued in `pending`, for the hazard check of submit / blend_host:
+ * sorted, disjoint, touching ranges merged. A flat vector -- a batch holds at most a few hundred
+ * frames and the planes of one frame are usually neighbours, so an insert is a binary search
+ * plus a short memmove, and nothing is allocated once the vector has grown. */
+struct IntervalSet {
+  std::vector<std::pair<uintptr_t, uintptr_t>> v;      /* [lo, hi) */
+  void clear () { v.clear (); }
+  bool empty () const { return v.empty (); }
+  /* first range that ends after lo */
+  size_t first_after (uintptr_t lo) const
+  {
+    size_t a = 0, b = v.size ();
+    while (a < b) {
+      const size_t m = (a + b) / 2;
+      if (v[m].second > lo) b = m; else a = m + 1;
+    }
+    return a;
+  }
+  bool overlaps (uintptr_t lo, uintptr_t hi) const
+  {
+    if (v.empty () || hi <= v.front ().first || lo >= v.back ().second)
+      return false;
+    const size_t i = first_after (lo);
+    return i < v.size () && v[i].first < hi;
+  }
+  void add (uintptr_t lo, uintptr_t hi)
+  {
+    if (hi <= lo)
+      return;
+    /* ranges that overlap or touch [lo, hi): those ending at or after lo and starting at or before hi */
+    size_t a = 0, b = v.size ();
+    while (a < b) {
+      const size_t m = (a + b) / 2;
+      if (v[m].second >= lo) b = m; else a = m + 1;
+    }
+    size_t e = a;
+    while (e < v.size () && v[e].first <= hi) {
+      lo = std::min (lo, v[e].first);
+      hi = std::max (hi, v[e].second);
+      e++;
+    }
+    if (e == a) {
+      v.insert (v.begin () + a, std::make_pair (lo, hi));
+    } else {
+      v[a] = std::make_pair (lo, hi);
+      v.erase (v.begin () + a + 1, v.begin () + e);
+    }
+  }
+};
+
 struct PoolEntry {
   void *base;
   size_t bytes;
@@ -312,6 +362,7 @@ struct Lane {
   cudaEvent_t done = nullptr;
   uint64_t ticket = 0;
   bool busy = false;
+  uintptr_t host_lo = 0, host_hi = 0;  /* the host frame in flight (hull of its planes) */
   uint8_t *dev = nullptr;
   size_t dev_bytes = 0;
   TableSlot table[2];
@@ -356,7 +407,14 @@ struct Ctx {
   std::vector<Group> groups;           /* scratch of launch_pending */
   std::vector<int> frame_group;        /* scratch: pending frame -> index into groups */
   std::vector<std::unique_ptr<MultiGroup>> multis;   /* scratch: multi-layout launches (reused) */
-  std::unordered_set<const void *> pending_dst;   /* destination buffers queued in `pending` */
+  /* what the frames queued in `pending` write and read: a frame that would write something a
+   * queued frame writes or reads, or read something a queued frame writes, must not share their
+   * launch (CTAs of one launch run in no order) -- the batch is launched first */
+  IntervalSet pending_dst, pending_src;
+  IntervalSet inflight_host;           /* host frames of zero-copy batches that have not been reaped yet */
+  /* batches whose launch failed half way (out of memory): wait() on their tickets reports it */
+  struct FailedRange { uint64_t first, last; int rc; };
+  std::deque<FailedRange> failed_ranges;
   std::vector<cudaEvent_t> timing_pool;
   std::chrono::steady_clock::time_point oldest_pending;
   uint64_t next_ticket = 0;
@@ -368,7 +426,12 @@ struct Ctx {
   uint32_t max_batch = 32, linger_us = 200;
   int host_mode = HM_ZEROCOPY;
   bool auto_register = false;          /* pin pageable host frames on first sight (opt-in) */
-  std::vector<std::pair<uintptr_t, uintptr_t>> auto_regs;   /* [lo, hi), most recently used first */
+  /* automatic registrations by first byte: [lo, hi) and when it was last used. At most
+   * auto_reg_limit () of them, least recently used dropped first. */
+  struct AutoReg { uintptr_t hi; uint64_t tick; uintptr_t dev; /* device address of the first byte */ };
+  std::map<uintptr_t, AutoReg> auto_regs;
+  uint64_t auto_tick = 0;
+  std::unordered_set<uint32_t> auto_streams;   /* streams whose frames have been registered */
   bool chroma_average = false;         /* fluc_ttmlblend_set_chroma_mode (1): NOT bit-exact */
   bool autocrop = true;                /* FLUC_TTMLBLEND_AUTOCROP=0: blend rectangles as handed in */
   bool use_groups = true;              /* FLUC_TTMLBLEND_GROUPS=0: generic table kernel only */
@@ -376,6 +439,10 @@ struct Ctx {
   bool use_multi = true;               /* FLUC_TTMLBLEND_MULTI=0: dissolved groups go to the table kernel */
   bool profiling = false;
   uint32_t profile_every = 1, profile_seq = 0;   /* FLUC_TTMLBLEND_PROFILE_EVERY */
+  /* FLUC_TTMLBLEND_SYNC=block: the events wait() / sync() sleep on are created with
+   * cudaEventBlockingSync, so a waiting thread gives its core away instead of spinning (many
+   * contexts / processes per box, tools/pcie_ceiling.cu); "spin" (default) has the lower latency */
+  bool blocking_sync = false;
   std::thread sched;
   bool quit = false;
 

@@ -113,6 +113,7 @@ PROTOTYPES = {
     "fluc_ttmlblend_set_auto_register": (C.c_int, [C.c_void_p, C.c_int]),
     "fluc_ttmlblend_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fluc_ttmlblend_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fluc_ttmlblend_host_forget": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fluc_ttmlblend_frame_pool_acquire": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, C.c_int32,
                                                     C.c_int, C.POINTER(Frame)]),
     "fluc_ttmlblend_frame_pool_release": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
@@ -406,6 +407,13 @@ class TtmlBlend:
 
     def host_unregister(self, arr: np.ndarray):
         self._check(self.lib.fluc_ttmlblend_host_unregister(self.h, arr.ctypes.data), "host_unregister")
+
+    def host_forget(self, arr: np.ndarray) -> int:
+        """Drops the automatic registrations inside `arr` (call before the memory is freed)."""
+        n = self.lib.fluc_ttmlblend_host_forget(self.h, arr.ctypes.data, arr.nbytes)
+        if n < 0:
+            self._check(n, "host_forget")
+        return n
 
     def blur_argb32(self, img: np.ndarray, radius: int, sigma: float) -> np.ndarray:
         """gst_ttml_blur_image_surface (surface, radius, sigma): h x w x 4 uint8 in and out."""

@@ -279,12 +279,19 @@ FLUC_EXPORT int fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream,
 FLUC_EXPORT int fluc_ttmlblend_blend_host_many (FlucTtmlBlend *thiz, uint32_t n,
     const uint32_t *streams, FlucTtmlBlendFormat fmt, int32_t width, int32_t height,
     uint32_t frame_flags, const FlucTtmlBlendFrame *host_frames, uint64_t *tickets);
-/* Opt-in: pin pageable host frames the first time blend_host sees them (up to 192 planes,
- * least recently used dropped), so that recycled buffers of a pool take the zero-copy path.
- * The caller must not free such memory while the context lives without host_unregister. */
+/* Opt-in: pin pageable host frames the first time blend_host sees them (48 planes per stream
+ * that uses it, at least 192; least recently used dropped), so that recycled buffers of a pool
+ * take the zero-copy path. A registration pins the physical pages: whoever owns such memory MUST
+ * call host_forget (or host_unregister) before freeing it -- a later allocation at the same
+ * address would otherwise be taken for the registered one while the GPU still reaches the old
+ * pages. (The GStreamer glue does so from the GstMemory's destroy notification.) */
 FLUC_EXPORT int fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled);
 FLUC_EXPORT int fluc_ttmlblend_host_register (FlucTtmlBlend *thiz, void *ptr, size_t bytes);
+/* Both wait for every frame of the context that is queued or in flight before they unpin. */
 FLUC_EXPORT int fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr);
+/* Drops every AUTOMATIC registration that intersects [ptr, ptr + bytes). Returns how many
+ * there were (>= 0), or a negative error. Memory that was never seen is not an error. */
+FLUC_EXPORT int fluc_ttmlblend_host_forget (FlucTtmlBlend *thiz, const void *ptr, size_t bytes);
 
 /* ---- frame pool ------------------------------------------------------ */
 /* Device frames (HBM) or pinned host staging frames, recycled by geometry.

@@ -1,0 +1,203 @@
+"""Frames of one batch that depend on each other: chained overlays (stream A's output is
+stream B's input), ping-pong buffers, the same buffer written twice, two overlays on one host
+frame. The CTAs of one launch run in no order, so the runtime must cut the batch at such
+frames; the result must equal the sequential composition computed by the oracle."""
+import numpy as np
+import pytest
+
+from helpers import assert_planes_equal, copy_planes, oracle_blend, pkg, random_frame, random_overlay, wl
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+W, H = 640, 360
+
+
+def _overlays(n, seed):
+    return [random_overlay(W, H, seed + i, density=0.5) for i in range(n)]
+
+
+def _rects(ov):
+    return [dict(pixels=ov, x=0, y=0)]
+
+
+@pytest.mark.parametrize("fmt", ["NV12", "I420", "BGRA"])
+def test_chain_a_to_b_to_c_inside_one_batch(ctx, fmt):
+    """src -> (stream 1) -> t1 -> (stream 2) -> t2 -> (stream 3) -> out, all queued before any
+    launch, several times over so that a race would show."""
+    ovs = _overlays(3, 900)
+    for i, ov in enumerate(ovs):
+        ctx.overlay_set_rectangles(700 + i, _rects(ov))
+    ctx.set_batch(64, 0)
+    try:
+        frame = random_frame(fmt, W, H, 41)
+        want = copy_planes(frame)
+        for ov in ovs:
+            want = oracle_blend(fmt, W, H, want, _rects(ov))
+        bufs = [ctx.acquire(fmt, W, H) for _ in range(4)]
+        bufs[0].upload(frame)
+        for rep in range(5):
+            before = ctx.stats()["launches"]
+            t = None
+            for i in range(3):
+                t = ctx.submit(700 + i, fmt, W, H, bufs[i].c, bufs[i + 1].c)
+            ctx.wait(t)
+            assert ctx.stats()["launches"] - before == 3, "dependent frames must not share a launch"
+            assert_planes_equal(bufs[3].download(), want, f"{fmt} chain, repetition {rep}")
+        for b in bufs:
+            b.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_ping_pong_and_write_after_read(ctx):
+    """A -> B then B -> A (the second frame overwrites what the first one reads), and a frame
+    whose destination is another queued frame's source."""
+    fmt = "NV12"
+    ov1, ov2 = _overlays(2, 910)
+    ctx.overlay_set_rectangles(710, _rects(ov1))
+    ctx.overlay_set_rectangles(711, _rects(ov2))
+    ctx.set_batch(64, 0)
+    try:
+        fa = random_frame(fmt, W, H, 42)
+        a, b = ctx.acquire(fmt, W, H), ctx.acquire(fmt, W, H)
+        a.upload(fa)
+        want_b = oracle_blend(fmt, W, H, copy_planes(fa), _rects(ov1))
+        want_a = oracle_blend(fmt, W, H, copy_planes(want_b), _rects(ov2))
+        for rep in range(5):
+            a.upload(fa)
+            ctx.submit(710, fmt, W, H, a.c, b.c)
+            ctx.wait(ctx.submit(711, fmt, W, H, b.c, a.c))
+            assert_planes_equal(b.download(), want_b, f"ping, repetition {rep}")
+            assert_planes_equal(a.download(), want_a, f"pong, repetition {rep}")
+        # write after read: frame 2 writes into the buffer frame 1 reads from
+        c = ctx.acquire(fmt, W, H)
+        fc = random_frame(fmt, W, H, 43)
+        for rep in range(5):
+            a.upload(fa)
+            c.upload(fc)
+            ctx.submit(710, fmt, W, H, a.c, b.c)          # reads a
+            ctx.wait(ctx.submit(711, fmt, W, H, c.c, a.c))  # writes a
+            assert_planes_equal(b.download(), want_b, f"reader of a, repetition {rep}")
+            assert_planes_equal(a.download(), oracle_blend(fmt, W, H, copy_planes(fc), _rects(ov2)),
+                                f"writer of a, repetition {rep}")
+        for f in (a, b, c):
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_shared_source_still_shares_a_launch(ctx):
+    """Frames that only READ the same buffer do not depend on each other."""
+    fmt = "NV12"
+    ov = _overlays(1, 920)[0]
+    ctx.overlay_set_rectangles(720, _rects(ov))
+    ctx.set_batch(64, 0)
+    try:
+        src = ctx.acquire(fmt, W, H)
+        frame = random_frame(fmt, W, H, 44)
+        src.upload(frame)
+        dsts = [ctx.acquire(fmt, W, H) for _ in range(6)]
+        before = ctx.stats()["launches"]
+        t = [ctx.submit(720, fmt, W, H, src.c, d.c) for d in dsts]
+        ctx.wait(t[-1])
+        assert ctx.stats()["launches"] - before == 1
+        want = oracle_blend(fmt, W, H, copy_planes(frame), _rects(ov))
+        for d in dsts:
+            assert_planes_equal(d.download(), want, "shared source")
+        for f in dsts + [src]:
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_overlapping_views_of_one_buffer_are_ordered(ctx):
+    """The second frame's destination is a sub-view (other base pointer) of the first frame's
+    destination: ranges are compared, not base pointers."""
+    fmt = "GRAY8"
+    ov_big = random_overlay(W, H, 930, density=0.6)
+    ov_small = random_overlay(W // 2, H // 2, 931, density=0.6)
+    ctx.overlay_set_rectangles(730, _rects(ov_big))
+    ctx.overlay_set_rectangles(731, _rects(ov_small))
+    ctx.set_batch(64, 0)
+    try:
+        big = ctx.acquire(fmt, W, H)
+        frame = random_frame(fmt, W, H, 45)
+        want = oracle_blend(fmt, W, H, copy_planes(frame), _rects(ov_big))
+        x0, y0 = 160, 90                      # 16-byte aligned sub-view
+        sub_want = [np.ascontiguousarray(want[0][y0:y0 + H // 2, x0:x0 + W // 2])]
+        sub_want = oracle_blend(fmt, W // 2, H // 2, sub_want, _rects(ov_small))
+        want[0][y0:y0 + H // 2, x0:x0 + W // 2] = sub_want[0]
+        F = pkg.ttmlblend.Frame
+        for rep in range(5):
+            big.upload(frame)
+            view = F()
+            view.plane[0] = big.c.plane[0] + y0 * big.c.stride[0] + x0
+            view.stride[0] = big.c.stride[0]
+            ctx.submit(730, fmt, W, H, big.c, big.c)
+            ctx.wait(ctx.submit(731, fmt, W // 2, H // 2, view, view))
+            assert_planes_equal(big.download(), want, f"sub-view, repetition {rep}")
+        big.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_two_overlays_on_one_host_frame(ctx, pinned):
+    """Two streams' cues blended onto the same host frame back to back (zero copy when the frame
+    is pinned, otherwise two staging lanes that must run one after the other)."""
+    fmt = "NV12"
+    ov1, ov2 = _overlays(2, 940)
+    ctx.overlay_set_rectangles(740, _rects(ov1))
+    ctx.overlay_set_rectangles(741, _rects(ov2))
+    frame = random_frame(fmt, W, H, 46)
+    want = oracle_blend(fmt, W, H, copy_planes(frame), _rects(ov1))
+    want = oracle_blend(fmt, W, H, want, _rects(ov2))
+    ctx.set_batch(64, 0)
+    try:
+        for rep in range(5):
+            if pinned:
+                hf = ctx.acquire(fmt, W, H, on_host=True)
+                views = hf.host_planes()
+                for v, p in zip(views, frame):
+                    v[...] = p
+                t1 = ctx.blend_host_frame(740, fmt, W, H, hf.c)
+                t2 = ctx.blend_host_frame(741, fmt, W, H, hf.c)
+                ctx.wait(t1)
+                ctx.wait(t2)
+                got = [v.copy() for v in views]
+                hf.release()
+            else:
+                got = copy_planes(frame)
+                t1 = ctx.blend_host(740, fmt, W, H, got)
+                t2 = ctx.blend_host(741, fmt, W, H, got)
+                ctx.wait(t1)
+                ctx.wait(t2)
+            assert_planes_equal(got, want, f"two overlays, pinned={pinned}, repetition {rep}")
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_host_forget_drops_automatic_registrations():
+    """auto-register pins pageable frames on first sight; host_forget (what the owner calls before
+    freeing the memory) unpins them again, and the next frame from such memory is staged or
+    re-registered -- never blended through a stale mapping."""
+    fmt = "NV12"
+    c = pkg.TtmlBlend(0)
+    try:
+        ov = random_overlay(W, H, 950)
+        c.overlay_set_rectangles(1, _rects(ov))
+        c.set_auto_register(True)
+        frame = random_frame(fmt, W, H, 47)
+        want = oracle_blend(fmt, W, H, copy_planes(frame), _rects(ov))
+        backing = np.empty(H * W * 2, dtype=np.uint8)        # both planes inside one allocation
+        planes = [backing[:H * W].reshape(H, W), backing[H * W:H * W + (H // 2) * W].reshape(H // 2, W)]
+        for rep in range(3):
+            for p, s in zip(planes, frame):
+                p[...] = s
+            c.wait(c.blend_host(1, fmt, W, H, planes))
+            assert_planes_equal(planes, want, f"auto-registered, repetition {rep}")
+            assert c.host_forget(backing) >= 1
+        assert c.host_forget(backing) == 0                   # nothing left
+    finally:
+        c.close()

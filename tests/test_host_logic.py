@@ -56,6 +56,9 @@ def hooks():
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.tb_hook_scale_row_plan.restype = C.c_int
     lib.tb_hook_scale_row_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    lib.tb_hook_interval_set.restype = C.c_int
+    lib.tb_hook_interval_set.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_uint64), C.c_int]
     return lib
 
 
@@ -410,3 +413,52 @@ def test_multi_launch_limits(hooks):
     # 128 frames, 64 layouts x 5 bands = 320 bands: frames cap (64) decides -> 2 launches,
     # and the second pass over the same overlays reuses the band lists already in a launch
     assert k == 2 and lists in (64, 128) and launch.count(0) == 64 and launch.count(1) == 64
+
+
+def _interval_ops(hooks, ops):
+    """ops: [(kind, lo, hi)], kind 0 add / 1 query -> (answers, ranges held at the end)"""
+    flat = (C.c_uint64 * (3 * len(ops)))(*[v for op in ops for v in op])
+    out = (C.c_int32 * max(1, len(ops)))()
+    ranges = (C.c_uint64 * 4096)()
+    n = hooks.tb_hook_interval_set(flat, len(ops), out, ranges, 2048)
+    nq = sum(1 for op in ops if op[0] == 1)
+    return [out[i] for i in range(nq)], [(ranges[2 * k], ranges[2 * k + 1]) for k in range(n)]
+
+
+def test_interval_set_simple(hooks):
+    """The range set behind the batch hazard check (frames that write / read what a queued frame
+    writes must not share its launch): half-open ranges, touching ranges merge."""
+    ans, held = _interval_ops(hooks, [
+        (1, 0, 100),                 # empty set
+        (0, 100, 200), (1, 0, 100), (1, 199, 300), (1, 200, 300), (1, 150, 160),
+        (0, 300, 400), (1, 200, 300), (0, 200, 300), (1, 250, 251),
+        (0, 1000, 1100), (0, 50, 60), (1, 60, 100), (1, 59, 61),
+    ])
+    assert ans == [0, 0, 1, 0, 1, 0, 1, 0, 1]
+    assert held == [(50, 60), (100, 400), (1000, 1100)]
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_interval_set_against_a_bitmap(hooks, seed):
+    rnd = random.Random(7000 + seed)
+    size = 4000
+    bitmap = np.zeros(size, dtype=bool)
+    ops, want = [], []
+    for _ in range(300):
+        lo = rnd.randrange(0, size - 1)
+        hi = min(size, lo + rnd.choice((1, 2, 5, 40, 300)))
+        if rnd.random() < 0.5:
+            ops.append((0, lo, hi))
+            bitmap[lo:hi] = True
+        else:
+            ops.append((1, lo, hi))
+            want.append(int(bitmap[lo:hi].any()))
+    ans, held = _interval_ops(hooks, ops)
+    assert ans == want
+    covered = np.zeros(size, dtype=bool)
+    prev_hi = -1
+    for lo, hi in held:
+        assert lo < hi and lo > prev_hi          # sorted, disjoint, not even touching
+        covered[lo:hi] = True
+        prev_hi = hi
+    assert np.array_equal(covered, bitmap)
