@@ -24,6 +24,7 @@ using namespace tbh;
 
 struct _FlucTtmlBlend {
   Ctx c;
+  uint32_t repeat_set = 0;      /* submit_many_repeat: next destination set */
 };
 
 #define ENTER(thiz)                                                          \
@@ -237,6 +238,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->eager_prepare = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_MULTI")))
     c->use_multi = atoi (e) != 0;
+  if ((e = getenv ("FLUC_TTMLBLEND_PDL")))
+    c->use_pdl = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_AUTO_REGISTER")))
     c->auto_register = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))
@@ -554,6 +557,25 @@ fluc_ttmlblend_submit_many (FlucTtmlBlend *thiz, uint32_t n, const uint32_t *str
   }
   if (c->linger_us && !c->pending.empty ())
     c->cv.notify_all ();
+  return 0;
+}
+
+int
+fluc_ttmlblend_submit_many_repeat (FlucTtmlBlend *thiz, uint32_t n, const uint32_t *streams,
+    FlucTtmlBlendFormat fmt, int32_t W, int32_t H, uint32_t frame_flags,
+    const FlucTtmlBlendFrame *srcs, const FlucTtmlBlendFrame *dsts, uint32_t dst_sets, uint32_t repeats)
+{
+  if (!thiz || dst_sets == 0)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  uint32_t &set = thiz->repeat_set;      /* carries on where the previous call stopped */
+  for (uint32_t r = 0; r < repeats; r++, set++) {
+    int rc = fluc_ttmlblend_submit_many (thiz, n, streams, fmt, W, H, frame_flags, srcs,
+        dsts + (size_t) (set % dst_sets) * n, nullptr);
+    if (rc == 0)
+      rc = fluc_ttmlblend_flush (thiz);
+    if (rc)
+      return rc;
+  }
   return 0;
 }
 
@@ -986,7 +1008,7 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
     for (int g = 0; g < 2; g++)
       if (!grp[g].empty ()) {
         if ((rc = launch_jobs (c, l.table[g], grp[g].data (), grp[g].size (), plane_kind (fmt),
-                    g == 1, l.stream)))
+                    g == 1, 0, l.stream)))
           return rc;
       }
   }
@@ -1370,6 +1392,7 @@ fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *o
     sum.cache_bytes += s.cache_bytes;
     sum.multi_launches += s.multi_launches;
     sum.lazy_launches += s.lazy_launches;
+    sum.dependent_launches += s.dependent_launches;
   }
   *out = sum;
 }
@@ -1456,6 +1479,76 @@ fluc_ttmlblend_scrub_l2 (FlucTtmlBlend *thiz, size_t bytes)
     c->scrub_bytes = bytes;
   }
   CU (c, launch_scrub (c->scrub, bytes, c->blend_stream));
+  return 0;
+}
+
+int
+fluc_ttmlblend_pcie_probe (FlucTtmlBlend *thiz, int mode, size_t bytes, double seconds, double *gbs)
+{
+  ENTER (thiz);
+  if (mode < 0 || mode > 1 || bytes < 4096 || bytes > ((size_t) 1 << 31) || !(seconds > 0.0) || seconds > 10.0)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+  bytes &= ~(size_t) 4095;
+  int rc = launch_pending (c);
+  if (rc)
+    return rc;
+  /* buffers of its own, nothing shared with frames in flight; the context stays unlocked while
+   * the probe runs (it touches only these buffers and two lane streams that are drained first) */
+  uint8_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+  auto cleanup = [&]() {
+    if (h_in) cudaFreeHost (h_in);
+    if (h_out) cudaFreeHost (h_out);
+    if (d_in) cudaFree (d_in);
+    if (d_out) cudaFree (d_out);
+  };
+  {
+    NumaScope numa (c);
+    if (cudaHostAlloc ((void **) &h_in, bytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc ((void **) &h_out, bytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc ((void **) &d_in, bytes) != cudaSuccess || cudaMalloc ((void **) &d_out, bytes) != cudaSuccess) {
+      cudaGetLastError ();
+      cleanup ();
+      return FLUC_TTMLBLEND_ERROR_OUT_OF_MEMORY;
+    }
+  }
+  memset (h_in, 0x5a, bytes);
+  memset (h_out, 0xa5, bytes);
+  cudaStream_t s1 = c->lanes[0].stream, s2 = c->lanes[1].stream;
+  cudaStreamSynchronize (s1);
+  cudaStreamSynchronize (s2);
+  lk.unlock ();
+  auto issue = [&]() -> cudaError_t {
+    if (mode == 0) {
+      cudaError_t e = cudaMemcpyAsync (d_in, h_in, bytes, cudaMemcpyHostToDevice, s1);
+      if (e != cudaSuccess)
+        return e;
+      return cudaMemcpyAsync (h_out, d_out, bytes, cudaMemcpyDeviceToHost, s2);
+    }
+    return launch_pcie_probe (h_in, bytes, s1);
+  };
+  cudaError_t e = issue ();
+  if (e == cudaSuccess) e = cudaStreamSynchronize (s1);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (s2);
+  const auto t0 = std::chrono::steady_clock::now ();
+  double t = 0.0;
+  uint64_t iters = 0;
+  while (e == cudaSuccess && t < seconds) {
+    e = issue ();
+    if (e == cudaSuccess) e = issue ();
+    if (e == cudaSuccess) e = cudaStreamSynchronize (s1);
+    if (e == cudaSuccess) e = cudaStreamSynchronize (s2);
+    iters += 2;
+    t = std::chrono::duration<double> (std::chrono::steady_clock::now () - t0).count ();
+  }
+  lk.lock ();
+  cleanup ();
+  if (e != cudaSuccess) {
+    c->cuda_error = std::string ("pcie_probe: ") + cudaGetErrorString (e);
+    c->sticky = FLUC_TTMLBLEND_ERROR_CUDA;
+    return c->sticky;
+  }
+  if (gbs)
+    *gbs = (double) bytes * (double) iters / t / 1e9;
   return 0;
 }
 

@@ -365,31 +365,31 @@ emit_table_jobs (const std::vector<PlaneJob> &tmpl, const PendingFrame &f, std::
 bool
 group_accepts (const Group &g, const PendingFrame &f)
 {
-  return g.layout_id == f.layout->id && g.P.n_frames < (uint32_t) kMaxPlainGroupFrames;
+  return g.layout_id == f.layout->id && g.P.h.n_frames < (uint32_t) kMaxPlainGroupFrames;
 }
 
 void
 group_start (Group &g, const PendingFrame &f)
 {
   const Layout &L = *f.layout;
-  memset (&g.P, 0, offsetof (GroupParams, bands));
+  memset (&g.P.h, 0, sizeof g.P.h);
   g.kind = L.kind;
   g.layout_id = L.id;
   g.dissolved = false;
-  g.P.n_bands = (uint32_t) L.bands.size ();
-  g.P.chunks_per_frame = L.chunks_per_frame;
-  g.P.cpf_magic = (uint32_t) (((1ull << 32) + L.chunks_per_frame - 1) / L.chunks_per_frame);
-  g.P.flags = L.gflags;
-  memcpy (g.P.src_pitch, L.src_pitch, sizeof g.P.src_pitch);
-  memcpy (g.P.dst_pitch, L.dst_pitch, sizeof g.P.dst_pitch);
-  memcpy (g.P.rect_off, L.rect_off, sizeof g.P.rect_off);
+  g.P.h.n_bands = (uint32_t) L.bands.size ();
+  g.P.h.chunks_per_frame = L.chunks_per_frame;
+  g.P.h.cpf_magic = (uint32_t) (((1ull << 32) + L.chunks_per_frame - 1) / L.chunks_per_frame);
+  g.P.h.flags = L.gflags;
+  memcpy (g.P.h.src_pitch, L.src_pitch, sizeof g.P.h.src_pitch);
+  memcpy (g.P.h.dst_pitch, L.dst_pitch, sizeof g.P.h.dst_pitch);
+  memcpy (g.P.h.rect_off, L.rect_off, sizeof g.P.h.rect_off);
   memcpy (g.P.bands, L.bands.data (), L.bands.size () * sizeof (BandDesc));
 }
 
 void
 group_add (Group &g, const PendingFrame &f)
 {
-  g.P.frames[g.P.n_frames++] = frame_ptrs (f);
+  g.P.frames[g.P.h.n_frames++] = frame_ptrs (f);
 }
 
 void

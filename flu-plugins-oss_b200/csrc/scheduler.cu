@@ -50,7 +50,7 @@ slot_reserve (Ctx *c, TableSlot &s, size_t n, size_t words)
  * array holds the first chunk of every job, then the coarse index (job of every
  * 2^kCoarseShift-th chunk) the kernel starts its search from. */
 int
-launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast,
+launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast, int sync,
     cudaStream_t stream)
 {
   if (n == 0)
@@ -83,19 +83,40 @@ launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, boo
           c->table_stream));
   CU (c, cudaEventRecord (s.uploaded, c->table_stream));
   CU (c, cudaStreamWaitEvent (stream, s.uploaded, 0));
-  CU (c, launch_blend (s.d_jobs, s.d_begin, s.d_begin + n, (int) n, total, kind, fast, stream));
+  CU (c, launch_blend (s.d_jobs, s.d_begin, s.d_begin + n, (int) n, total, kind, fast, sync, stream));
   CU (c, cudaEventRecord (s.copied, stream));    /* slot busy until this kernel is done */
   c->stats.launches++;
   return 0;
 }
 
+/* Retires the batches that have finished. Batches complete in launch order (one stream), so
+ * the boundary between finished and running ones is found by bisection: a handful of event
+ * queries however many batches are in flight, instead of one per batch. */
 void
 reap_batches (Ctx *c)
 {
-  while (!c->batches.empty ()) {
+  size_t n = c->batches.size ();
+  if (n == 0)
+    return;
+  size_t done = 0;              /* batches [0, done) have finished */
+  if (cudaEventQuery (c->batches[n - 1].done) == cudaSuccess) {
+    done = n;
+  } else {
+    cudaGetLastError ();
+    size_t lo = 0, hi = n - 1;  /* batch hi is running; find the first running one */
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (cudaEventQuery (c->batches[mid].done) == cudaSuccess)
+        lo = mid + 1;
+      else {
+        cudaGetLastError ();
+        hi = mid;
+      }
+    }
+    done = lo;
+  }
+  for (size_t i = 0; i < done; i++) {
     Batch &b = c->batches.front ();
-    if (cudaEventQuery (b.done) != cudaSuccess)
-      break;
     if (b.t0 && b.t1) {
       float ms = 0.f;
       if (cudaEventElapsedTime (&ms, b.t0, b.t1) == cudaSuccess) {
@@ -106,10 +127,16 @@ reap_batches (Ctx *c)
       c->timing_pool.push_back (b.t1);
     }
     c->event_pool.push_back (b.done);
+    b.keep.clear ();            /* drops the overlay references, keeps the capacity */
+    c->keep_pool.push_back (std::move (b.keep));
     c->batches.pop_front ();
   }
-  if (c->batches.empty ())
+  if (c->batches.empty ()) {
     c->inflight_host.clear ();
+    /* nothing is running any more: the next launch depends on nothing */
+    c->inflight_dst.clear ();
+    c->inflight_src.clear ();
+  }
 }
 
 /* Launches everything pending as one batch (per plane kind). mu held. */
@@ -119,10 +146,19 @@ launch_pending (Ctx *c)
   if (c->pending.empty ())
     return 0;
   NvtxRange nvtx ("ttmlblend.launch_batch");
-  reap_batches (c);
+  /* finished batches are retired in bulk: an event query per launch would be a fifth of the cost
+   * of a one-frame launch (wait / sync / stats retire them too) */
+  if (c->batches.size () >= 32)
+    reap_batches (c);
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
-  std::vector<PlaneJob> by_kind[kPlaneKinds * 2];     /* PlaneKind x {byte-granular, fast} */
+  if (!c->keep_pool.empty ()) {
+    b.keep = std::move (c->keep_pool.back ());
+    c->keep_pool.pop_back ();
+  }
+  std::vector<PlaneJob> *by_kind = c->by_kind;        /* PlaneKind x {byte-granular, fast}; scratch */
+  for (int k = 0; k < kPlaneKinds * 2; k++)
+    by_kind[k].clear ();
   std::vector<Group> &groups = c->groups;
   groups.clear ();
   size_t n_multis = 0;
@@ -147,8 +183,8 @@ launch_pending (Ctx *c)
       frame_group[fi] = gi;
     }
     fi++;
-    if (f.overlay)
-      b.keep.push_back (f.overlay);
+    if (f.overlay && (b.keep.empty () || b.keep.back () != f.overlay))
+      b.keep.push_back (f.overlay);     /* consecutive frames of one cue: one reference */
     if (f.prep && !f.prep->blend_waited) {
       /* once per prepared overlay: later launches follow in stream order */
       f.prep->blend_waited = true;
@@ -167,7 +203,7 @@ launch_pending (Ctx *c)
     for (int k = 1; k < kPlaneKinds * 2; k += 2)
       n_table += by_kind[k].size ();
     for (Group &g : groups) {
-      g.dissolved = (uint64_t) g.P.n_frames * g.P.chunks_per_frame < (uint64_t) kMinGroupChunks;
+      g.dissolved = (uint64_t) g.P.h.n_frames * g.P.h.chunks_per_frame < (uint64_t) kMinGroupChunks;
       n_small += g.dissolved ? 1 : 0;
     }
     if (n_small < 2 && n_table == 0)
@@ -197,6 +233,28 @@ launch_pending (Ctx *c)
     }
   }
   const uint64_t first_ticket = c->pending.front ().ticket;
+  /* Programmatic dependent launch: a launch may start while earlier ones still run. That is
+   * only right for frames that do not touch what those read or write: the ranges of every
+   * batch launched since the last dependent one are remembered, and a batch that writes into
+   * them, or reads what they write, has its first launch wait for everything before it
+   * (JF_DEP); after such a launch only its own ranges can still be in flight. */
+  int sync = 0;
+  if (c->use_pdl) {
+    const bool timed = c->profiling && (c->profile_seq % c->profile_every) == 0;
+    bool dep = c->inflight_dst.v.size () + c->inflight_src.v.size () > 4096 || timed || c->isolate_next;
+    c->isolate_next = timed;    /* an event pair measures one launch alone: neither it nor its successor overlaps */
+    if (!dep)
+      dep = sets_overlap (c->pending_dst, c->inflight_dst) || sets_overlap (c->pending_dst, c->inflight_src) ||
+          sets_overlap (c->pending_src, c->inflight_dst);
+    if (dep) {
+      c->inflight_dst.clear ();
+      c->inflight_src.clear ();
+      c->stats.dependent_launches++;
+    }
+    c->inflight_dst.merge (c->pending_dst);
+    c->inflight_src.merge (c->pending_src);
+    sync = JF_PDL | (dep ? JF_DEP : 0);
+  }
   c->pending.clear ();
   c->pending_dst.clear ();
   c->pending_src.clear ();
@@ -228,15 +286,17 @@ launch_pending (Ctx *c)
     for (Group &g : groups) {
       if (g.dissolved)
         continue;
-      CU (c, launch_group (g.P, g.kind, c->blend_stream));
+      CU (c, launch_group (g.P, g.kind, sync, c->blend_stream));
+      sync &= ~JF_DEP;          /* the launches of one batch are independent of each other */
       c->stats.launches++;
       c->stats.group_launches++;
-      if (g.P.flags & JF_LAZY)
+      if (g.P.h.flags & JF_LAZY)
         c->stats.lazy_launches++;
     }
     for (size_t k = 0; k < n_multis; k++) {
       MultiGroup &m = *c->multis[k];
-      CU (c, launch_multi (m.P, m.kind, c->blend_stream));
+      CU (c, launch_multi (m.P, m.kind, sync, c->blend_stream));
+      sync &= ~JF_DEP;
       c->stats.launches++;
       c->stats.multi_launches++;
       if (m.P.flags & JF_LAZY)
@@ -247,10 +307,11 @@ launch_pending (Ctx *c)
         continue;
       TableSlot &s = c->slots[c->next_slot];
       c->next_slot = (c->next_slot + 1) % kTableSlots;
-      int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0,
+      int rc = launch_jobs (c, s, by_kind[k].data (), by_kind[k].size (), k / 2, (k & 1) != 0, sync,
           c->blend_stream);
       if (rc)
         return rc;
+      sync &= ~JF_DEP;
     }
     if (b.t1)
       CU (c, cudaEventRecord (b.t1, c->blend_stream));

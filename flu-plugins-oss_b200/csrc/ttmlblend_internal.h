@@ -267,8 +267,9 @@ struct PendingFrame {
 struct Group {
   int kind;
   uint64_t layout_id;
-  bool dissolved = false;              /* too small to be worth a launch: frames go to the table kernel */
+  bool dissolved;                      /* too small to be worth a launch: frames go to the table kernel */
   GroupParams P;
+  Group () {}                          /* user-provided: no zeroing of the 19.5 KB block per launch (group_start fills in what is used) */
 };
 
 /* frames of one kind / pitch set / flag set with different band lists, packed into one
@@ -325,6 +326,11 @@ struct IntervalSet {
     const size_t i = first_after (lo);
     return i < v.size () && v[i].first < hi;
   }
+  void merge (const IntervalSet &o)
+  {
+    for (const auto &r : o.v)
+      add (r.first, r.second);
+  }
   void add (uintptr_t lo, uintptr_t hi)
   {
     if (hi <= lo)
@@ -349,6 +355,19 @@ struct IntervalSet {
     }
   }
 };
+
+/* do two range sets share a byte? walks the smaller one */
+inline bool
+sets_overlap (const IntervalSet &a, const IntervalSet &b)
+{
+  const IntervalSet &s = a.v.size () <= b.v.size () ? a : b, &l = a.v.size () <= b.v.size () ? b : a;
+  if (s.v.empty () || l.v.empty () || s.v.back ().second <= l.v.front ().first || l.v.back ().second <= s.v.front ().first)
+    return false;
+  for (const auto &r : s.v)
+    if (l.overlaps (r.first, r.second))
+      return true;
+  return false;
+}
 
 struct PoolEntry {
   void *base;
@@ -405,6 +424,8 @@ struct Ctx {
 
   std::vector<PendingFrame> pending;
   std::vector<Group> groups;           /* scratch of launch_pending */
+  std::vector<PlaneJob> by_kind[kPlaneKinds * 2];   /* scratch: table jobs per (kind, fast) */
+  std::vector<std::vector<std::shared_ptr<Overlay>>> keep_pool;   /* recycled Batch::keep vectors */
   std::vector<int> frame_group;        /* scratch: pending frame -> index into groups */
   std::vector<std::unique_ptr<MultiGroup>> multis;   /* scratch: multi-layout launches (reused) */
   /* what the frames queued in `pending` write and read: a frame that would write something a
@@ -412,6 +433,11 @@ struct Ctx {
    * launch (CTAs of one launch run in no order) -- the batch is launched first */
   IntervalSet pending_dst, pending_src;
   IntervalSet inflight_host;           /* host frames of zero-copy batches that have not been reaped yet */
+  /* programmatic dependent launch: what the batches launched since the last dependent (fully
+   * ordered) launch write and read; a new batch that conflicts with them is launched JF_DEP */
+  IntervalSet inflight_dst, inflight_src;
+  bool use_pdl = true;                 /* FLUC_TTMLBLEND_PDL=0: ordinary, serialised launches */
+  bool isolate_next = false;           /* the launch after a timed one must not overlap it */
   /* batches whose launch failed half way (out of memory): wait() on their tickets reports it */
   struct FailedRange { uint64_t first, last; int rc; };
   std::deque<FailedRange> failed_ranges;
@@ -544,7 +570,7 @@ several_streams_active (const Ctx *c)
 
 /* scheduler.cu */
 cudaEvent_t event_get (Ctx *c);
-int launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast, cudaStream_t stream);
+int launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast, int sync, cudaStream_t stream);
 void reap_batches (Ctx *c);
 int launch_pending (Ctx *c);
 void scheduler_main (Ctx *c);

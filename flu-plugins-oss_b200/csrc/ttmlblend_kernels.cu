@@ -21,6 +21,8 @@
 #include "ttmlblend_kernels.cuh"
 
 #include <cstdlib>
+#include <cstring>
+#include <utility>
 
 namespace tb {
 
@@ -121,6 +123,45 @@ st_frame_bytes (uint8_t *p, const uint4 &v, int nvalid)
   for (int i = 0; i < 16; i++)
     if (i < nvalid)
       p[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
+}
+
+/* ---------------------------------------------------------------------- */
+/* programmatic dependent launch (JF_PDL / JF_DEP, ttmlblend_kernels.cuh) */
+
+__device__ __forceinline__ void
+pdl_begin (int flags)
+{
+  if (flags & JF_DEP)
+    asm volatile ("griddepcontrol.wait;" ::: "memory");
+  if (flags & JF_PDL)
+    asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+/* a CTA's last act: grids complete in launch order, so "the previous grid has completed"
+ * always means "everything launched before has completed" */
+__device__ __forceinline__ void
+pdl_end (int flags)
+{
+  if (flags & JF_PDL)
+    asm volatile ("griddepcontrol.wait;" ::: "memory");
+}
+
+/* Launches `kernel` with or without the programmatic-serialisation attribute. */
+template <typename... KArgs, typename... Args>
+static cudaError_t
+launch_ex (void (*kernel) (KArgs...), uint32_t grid, size_t smem, cudaStream_t stream, bool pdl, Args &&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3 (grid);
+  cfg.blockDim = dim3 (kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx (&cfg, kernel, std::forward<Args> (args)...);
 }
 
 /* ---------------------------------------------------------------------- */
@@ -635,13 +676,16 @@ template <int KIND, bool FAST>
 __global__ void __launch_bounds__ (kThreads, FAST ? 4 : 2)
 ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
     const uint32_t *__restrict__ chunk_begin, const uint32_t *__restrict__ coarse, int n_jobs,
-    uint32_t total_chunks, uint32_t lanes, uint32_t per_lane, uint32_t lanes_magic)
+    uint32_t total_chunks, uint32_t lanes, uint32_t per_lane, uint32_t lanes_magic, int sync)
 {
+  pdl_begin (sync);
   const uint32_t q = lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, lanes_magic);
   const uint32_t r = blockIdx.x - q * lanes;
   const uint32_t chunk = r * per_lane + q;
-  if (chunk >= total_chunks)
+  if (chunk >= total_chunks) {
+    pdl_end (sync);
     return;
+  }
 
   /* which job: the host's coarse index names the job that holds the first chunk of this
    * chunk's block of kCoarseChunks; from there a short walk over the begins. Every thread does
@@ -653,6 +697,7 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
     j++;
   const JobRegs J = load_job (jobs + j);
   process_chunk<KIND, FAST, false> (J, chunk - __ldg (chunk_begin + j));
+  pdl_end (sync);
 }
 
 /* The common case -- a batch of frames that share format, size, strides and
@@ -664,20 +709,24 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
  * first frame load without a single dependent global load or barrier in
  * front of it (the table search of the generic kernel above costs ~8 % of a
  * streaming copy: tools/copybench.cu "+prologue"). */
-template <int KIND, bool LAZY>
+template <int KIND, bool LAZY, int NF, int NB>
 __global__ void __launch_bounds__ (kThreads, LAZY ? 4 : TTMLBLEND_MIN_CTAS)
-ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
+ttmlblend_group_kernel (const __grid_constant__ GroupParamsT<NF, NB> P)
 {
-  const uint32_t q = P.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, P.lanes_magic);
-  const uint32_t r = blockIdx.x - q * P.lanes;
-  const uint32_t chunk = r * P.per_lane + q;
-  if (chunk >= P.total_chunks)
+  const GroupHeader &Hd = P.h;
+  pdl_begin (Hd.flags);
+  const uint32_t q = Hd.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, Hd.lanes_magic);
+  const uint32_t r = blockIdx.x - q * Hd.lanes;
+  const uint32_t chunk = r * Hd.per_lane + q;
+  if (chunk >= Hd.total_chunks) {
+    pdl_end (Hd.flags);
     return;
+  }
   /* ceil (2^32 / 1) does not fit the magic: one chunk per frame is its own case */
-  const uint32_t frame = P.chunks_per_frame == 1u ? chunk : __umulhi (chunk, P.cpf_magic);
-  const uint32_t cif = chunk - frame * P.chunks_per_frame;
+  const uint32_t frame = Hd.chunks_per_frame == 1u ? chunk : __umulhi (chunk, Hd.cpf_magic);
+  const uint32_t cif = chunk - frame * Hd.chunks_per_frame;
   uint32_t b = 0;
-  for (uint32_t i = 1; i < P.n_bands; i++)
+  for (uint32_t i = 1; i < Hd.n_bands; i++)
     b += cif >= P.bands[i].chunk_begin ? 1u : 0u;
   const BandDesc &B = P.bands[b];
   const FramePtrs &F = P.frames[frame];
@@ -686,10 +735,10 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   JobRegs J;
   J.src = F.src[pl];
   J.dst = F.dst[pl];
-  J.rects = F.rects + P.rect_off[pl];
+  J.rects = F.rects + Hd.rect_off[pl];
   J.rect_mask = ((unsigned long long) B.rect_mask_hi << 32) | B.rect_mask_lo;
-  J.src_pitch = P.src_pitch[pl];
-  J.dst_pitch = P.dst_pitch[pl];
+  J.src_pitch = Hd.src_pitch[pl];
+  J.dst_pitch = Hd.dst_pitch[pl];
   J.win_v0 = B.win_v0;
   J.win_y0 = B.win_y0;
   J.win_nv = (uint32_t) B.win_nv;
@@ -697,9 +746,10 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParams P)
   J.magic = B.div_magic;
   J.cls = B.cls;
   J.one_rect = B.one_rect;
-  J.flags = P.flags;
+  J.flags = Hd.flags;
   J.row_bytes = 0;              /* FAST: never read */
   process_chunk<KIND, true, true, LAZY> (J, cif - B.chunk_begin);
+  pdl_end (Hd.flags);
 }
 
 /* The same for frames whose band lists differ (many streams, each with its own cue): the
@@ -711,11 +761,14 @@ template <int KIND, bool LAZY>
 __global__ void __launch_bounds__ (kThreads, LAZY ? 4 : TTMLBLEND_MIN_CTAS)
 ttmlblend_multi_kernel (const __grid_constant__ MultiParams P)
 {
+  pdl_begin (P.flags);
   const uint32_t q = P.lanes == 1u ? blockIdx.x : __umulhi (blockIdx.x, P.lanes_magic);
   const uint32_t r = blockIdx.x - q * P.lanes;
   const uint32_t chunk = r * P.per_lane + q;
-  if (chunk >= P.total_chunks)
+  if (chunk >= P.total_chunks) {
+    pdl_end (P.flags);
     return;
+  }
   uint32_t frame = 0;
 #pragma unroll
   for (uint32_t step = kMaxGroupFrames / 2; step > 0; step >>= 1) {
@@ -749,6 +802,7 @@ ttmlblend_multi_kernel (const __grid_constant__ MultiParams P)
   J.flags = P.flags;
   J.row_bytes = 0;              /* FAST: never read */
   process_chunk<KIND, true, true, LAZY> (J, cif - B.chunk_begin);
+  pdl_end (P.flags);
 }
 
 /* Number of interleaved streams the chunk list is walked in. Measured on the
@@ -774,7 +828,7 @@ interleave_lanes (int kind)
 template <int KIND>
 static cudaError_t
 launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint32_t *d_coarse, int n_jobs,
-    uint32_t total_chunks, bool fast, cudaStream_t stream)
+    uint32_t total_chunks, bool fast, int sync, cudaStream_t stream)
 {
   uint32_t lanes = interleave_lanes (KIND);
   if (total_chunks < lanes * 8u)
@@ -785,69 +839,87 @@ launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const 
   if ((unsigned long long) grid * lanes >= (1ull << 32))
     return cudaErrorInvalidValue;
   const uint32_t magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
+  const bool pdl = (sync & JF_PDL) != 0;
   if (fast)
-    ttmlblend_blend_kernel<KIND, true><<<grid, kThreads, 0, stream>>> (d_jobs,
-        d_chunk_begin, d_coarse, n_jobs, total_chunks, lanes, per_lane, magic);
-  else
-    ttmlblend_blend_kernel<KIND, false><<<grid, kThreads, 0, stream>>> (d_jobs,
-        d_chunk_begin, d_coarse, n_jobs, total_chunks, lanes, per_lane, magic);
-  return cudaGetLastError ();
+    return launch_ex (ttmlblend_blend_kernel<KIND, true>, grid, 0, stream, pdl, d_jobs, d_chunk_begin, d_coarse,
+        n_jobs, total_chunks, lanes, per_lane, magic, sync);
+  return launch_ex (ttmlblend_blend_kernel<KIND, false>, grid, 0, stream, pdl, d_jobs, d_chunk_begin, d_coarse,
+      n_jobs, total_chunks, lanes, per_lane, magic, sync);
+}
+
+/* One variant of the group kernel: copies what the launch needs into a parameter block of the
+ * variant's size (the full-size block itself when NF / NB are the maxima). */
+template <int KIND, bool LAZY, int NF, int NB>
+static cudaError_t
+launch_group_variant (const GroupParams &P, uint32_t grid, size_t smem, cudaStream_t stream)
+{
+  const bool pdl = (P.h.flags & JF_PDL) != 0;
+  if (NF == kMaxPlainGroupFrames && NB == kMaxGroupBands)
+    return launch_ex (ttmlblend_group_kernel<KIND, LAZY, kMaxPlainGroupFrames, kMaxGroupBands>, grid, smem, stream,
+        pdl, P);
+  GroupParamsT<NF, NB> S;
+  S.h = P.h;
+  memcpy (S.bands, P.bands, P.h.n_bands * sizeof (BandDesc));
+  memcpy (S.frames, P.frames, P.h.n_frames * sizeof (FramePtrs));
+  return launch_ex (ttmlblend_group_kernel<KIND, LAZY, NF, NB>, grid, smem, stream, pdl, S);
+}
+
+template <int KIND, bool LAZY>
+static cudaError_t
+launch_group_sized (const GroupParams &P, uint32_t grid, size_t smem, cudaStream_t stream)
+{
+  static const bool compact = !getenv ("FLUC_TTMLBLEND_COMPACT_PARAMS") || atoi (getenv ("FLUC_TTMLBLEND_COMPACT_PARAMS")) != 0;
+  if (compact && P.h.n_frames <= 4u && P.h.n_bands <= 16u)
+    return launch_group_variant<KIND, LAZY, 4, 16> (P, grid, smem, stream);
+  if (compact && P.h.n_frames <= 32u)
+    return launch_group_variant<KIND, LAZY, 32, kMaxGroupBands> (P, grid, smem, stream);
+  return launch_group_variant<KIND, LAZY, kMaxPlainGroupFrames, kMaxGroupBands> (P, grid, smem, stream);
 }
 
 cudaError_t
-launch_group (GroupParams &P, int kind, cudaStream_t stream)
+launch_group (GroupParams &P, int kind, int sync, cudaStream_t stream)
 {
-  P.total_chunks = P.n_frames * P.chunks_per_frame;
-  if (P.total_chunks == 0)
+  GroupHeader &Hd = P.h;
+  Hd.flags = (Hd.flags & ~(JF_PDL | JF_DEP)) | (sync & (JF_PDL | JF_DEP));
+  Hd.total_chunks = Hd.n_frames * Hd.chunks_per_frame;
+  if (Hd.total_chunks == 0)
     return cudaSuccess;
   uint32_t lanes = interleave_lanes (kind);
-  if (P.total_chunks < lanes * 8u)
+  if (Hd.total_chunks < lanes * 8u)
     lanes = 1;
-  P.lanes = lanes;
-  P.per_lane = (P.total_chunks + lanes - 1) / lanes;
-  const uint32_t grid = lanes * P.per_lane;
+  Hd.lanes = lanes;
+  Hd.per_lane = (Hd.total_chunks + lanes - 1) / lanes;
+  const uint32_t grid = lanes * Hd.per_lane;
   if ((unsigned long long) grid * lanes >= (1ull << 32))
     return cudaErrorInvalidValue;
-  P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
+  Hd.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
   /* shared memory for the TMA-staged overlay slice of a JC_ONE_BULK chunk */
   const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
   /* in place (dst == src, host frames over PCIe) under a sparse cue: the variant that reads
    * the overlay first and skips the vectors it would not change */
-  const bool lazy = (P.flags & JF_LAZY) != 0;
+  const bool lazy = (Hd.flags & JF_LAZY) != 0;
   switch (kind) {
     case PK_PLANE8:
-      if (lazy)
-        ttmlblend_group_kernel<PK_PLANE8, true><<<grid, kThreads, smem_plane8, stream>>> (P);
-      else
-        ttmlblend_group_kernel<PK_PLANE8, false><<<grid, kThreads, smem_plane8, stream>>> (P);
-      break;
+      return lazy ? launch_group_sized<PK_PLANE8, true> (P, grid, smem_plane8, stream) :
+          launch_group_sized<PK_PLANE8, false> (P, grid, smem_plane8, stream);
     case PK_PLANE8_RGB:
-      if (lazy)
-        ttmlblend_group_kernel<PK_PLANE8_RGB, true><<<grid, kThreads, smem_plane8, stream>>> (P);
-      else
-        ttmlblend_group_kernel<PK_PLANE8_RGB, false><<<grid, kThreads, smem_plane8, stream>>> (P);
-      break;
+      return lazy ? launch_group_sized<PK_PLANE8_RGB, true> (P, grid, smem_plane8, stream) :
+          launch_group_sized<PK_PLANE8_RGB, false> (P, grid, smem_plane8, stream);
     case PK_PACKED_A0:
-      if (lazy)
-        ttmlblend_group_kernel<PK_PACKED_A0, true><<<grid, kThreads, smem_packed, stream>>> (P);
-      else
-        ttmlblend_group_kernel<PK_PACKED_A0, false><<<grid, kThreads, smem_packed, stream>>> (P);
-      break;
+      return lazy ? launch_group_sized<PK_PACKED_A0, true> (P, grid, smem_packed, stream) :
+          launch_group_sized<PK_PACKED_A0, false> (P, grid, smem_packed, stream);
     case PK_PACKED_A3:
-      if (lazy)
-        ttmlblend_group_kernel<PK_PACKED_A3, true><<<grid, kThreads, smem_packed, stream>>> (P);
-      else
-        ttmlblend_group_kernel<PK_PACKED_A3, false><<<grid, kThreads, smem_packed, stream>>> (P);
-      break;
+      return lazy ? launch_group_sized<PK_PACKED_A3, true> (P, grid, smem_packed, stream) :
+          launch_group_sized<PK_PACKED_A3, false> (P, grid, smem_packed, stream);
     default:
       return cudaErrorInvalidValue;
   }
-  return cudaGetLastError ();
 }
 
 cudaError_t
-launch_multi (MultiParams &P, int kind, cudaStream_t stream)
+launch_multi (MultiParams &P, int kind, int sync, cudaStream_t stream)
 {
+  P.flags = (P.flags & ~(JF_PDL | JF_DEP)) | (sync & (JF_PDL | JF_DEP));
   P.total_chunks = P.frame_begin[P.n_frames];
   if (P.total_chunks == 0)
     return cudaSuccess;
@@ -862,52 +934,40 @@ launch_multi (MultiParams &P, int kind, cudaStream_t stream)
   P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
   const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
   const bool lazy = (P.flags & JF_LAZY) != 0;
+  const bool pdl = (P.flags & JF_PDL) != 0;
   switch (kind) {
     case PK_PLANE8:
-      if (lazy)
-        ttmlblend_multi_kernel<PK_PLANE8, true><<<grid, kThreads, smem_plane8, stream>>> (P);
-      else
-        ttmlblend_multi_kernel<PK_PLANE8, false><<<grid, kThreads, smem_plane8, stream>>> (P);
-      break;
+      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PLANE8, true>, grid, smem_plane8, stream, pdl, P) :
+          launch_ex (ttmlblend_multi_kernel<PK_PLANE8, false>, grid, smem_plane8, stream, pdl, P);
     case PK_PLANE8_RGB:
-      if (lazy)
-        ttmlblend_multi_kernel<PK_PLANE8_RGB, true><<<grid, kThreads, smem_plane8, stream>>> (P);
-      else
-        ttmlblend_multi_kernel<PK_PLANE8_RGB, false><<<grid, kThreads, smem_plane8, stream>>> (P);
-      break;
+      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PLANE8_RGB, true>, grid, smem_plane8, stream, pdl, P) :
+          launch_ex (ttmlblend_multi_kernel<PK_PLANE8_RGB, false>, grid, smem_plane8, stream, pdl, P);
     case PK_PACKED_A0:
-      if (lazy)
-        ttmlblend_multi_kernel<PK_PACKED_A0, true><<<grid, kThreads, smem_packed, stream>>> (P);
-      else
-        ttmlblend_multi_kernel<PK_PACKED_A0, false><<<grid, kThreads, smem_packed, stream>>> (P);
-      break;
+      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PACKED_A0, true>, grid, smem_packed, stream, pdl, P) :
+          launch_ex (ttmlblend_multi_kernel<PK_PACKED_A0, false>, grid, smem_packed, stream, pdl, P);
     case PK_PACKED_A3:
-      if (lazy)
-        ttmlblend_multi_kernel<PK_PACKED_A3, true><<<grid, kThreads, smem_packed, stream>>> (P);
-      else
-        ttmlblend_multi_kernel<PK_PACKED_A3, false><<<grid, kThreads, smem_packed, stream>>> (P);
-      break;
+      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PACKED_A3, true>, grid, smem_packed, stream, pdl, P) :
+          launch_ex (ttmlblend_multi_kernel<PK_PACKED_A3, false>, grid, smem_packed, stream, pdl, P);
     default:
       return cudaErrorInvalidValue;
   }
-  return cudaGetLastError ();
 }
 
 cudaError_t
 launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint32_t *d_coarse, int n_jobs,
-    uint32_t total_chunks, int kind, bool fast, cudaStream_t stream)
+    uint32_t total_chunks, int kind, bool fast, int sync, cudaStream_t stream)
 {
   if (n_jobs <= 0 || total_chunks == 0)
     return cudaSuccess;
   switch (kind) {
     case PK_PLANE8:
-      return launch_blend_kind<PK_PLANE8> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PLANE8> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, sync, stream);
     case PK_PLANE8_RGB:
-      return launch_blend_kind<PK_PLANE8_RGB> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PLANE8_RGB> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, sync, stream);
     case PK_PACKED_A0:
-      return launch_blend_kind<PK_PACKED_A0> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PACKED_A0> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, sync, stream);
     case PK_PACKED_A3:
-      return launch_blend_kind<PK_PACKED_A3> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, stream);
+      return launch_blend_kind<PK_PACKED_A3> (d_jobs, d_chunk_begin, d_coarse, n_jobs, total_chunks, fast, sync, stream);
     default:
       return cudaErrorInvalidValue;
   }
@@ -1492,6 +1552,35 @@ launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream)
     return cudaSuccess;
   ttmlblend_scrub_kernel<<<148 * 8, 256, 0, stream>>> (reinterpret_cast<uint4 *> (buf),
       bytes / 16, seed++);
+  return cudaGetLastError ();
+}
+
+/* bench helper (fluc_ttmlblend_pcie_probe): the zero-copy path's traffic shape with no blend in
+ * it -- one CTA per 16 KB, four 128-bit loads per thread in flight, the same bytes written back */
+__global__ void __launch_bounds__ (kThreads)
+ttmlblend_pcie_probe_kernel (uint8_t *buf, size_t n_vec)
+{
+  const size_t base = (size_t) blockIdx.x * kItemsPerChunk + threadIdx.x;
+  uint4 v[kUnroll];
+#pragma unroll
+  for (int k = 0; k < kUnroll; k++)
+    if (base + (size_t) k * kThreads < n_vec)
+      v[k] = ld_frame16 (buf + (base + (size_t) k * kThreads) * 16);
+#pragma unroll
+  for (int k = 0; k < kUnroll; k++)
+    if (base + (size_t) k * kThreads < n_vec) {
+      v[k].x ^= 1u;
+      st_frame16 (buf + (base + (size_t) k * kThreads) * 16, v[k]);
+    }
+}
+
+cudaError_t
+launch_pcie_probe (uint8_t *buf, size_t bytes, cudaStream_t stream)
+{
+  const size_t n_vec = bytes / 16;
+  if (n_vec == 0)
+    return cudaSuccess;
+  ttmlblend_pcie_probe_kernel<<<(unsigned) ((n_vec + kItemsPerChunk - 1) / kItemsPerChunk), kThreads, 0, stream>>> (buf, n_vec);
   return cudaGetLastError ();
 }
 

@@ -41,7 +41,19 @@ enum JobFlags : int32_t {
   JF_INPLACE = 2,       /* dst == src: bytes no rectangle covers are not touched */
   JF_DST_PREMUL = 4,    /* destination frame is premultiplied (packed kinds) */
   JF_FAST = 8,          /* host-side: JF_VECTOR and no ragged last vector -> fast kernel */
-  JF_LAZY = 16          /* host-side, group launches in place: overlay first, skip transparent vectors */
+  JF_LAZY = 16,         /* host-side, group launches in place: overlay first, skip transparent vectors */
+  /* Programmatic dependent launch (set per launch, not part of a layout). Every blend launch of
+   * the batch stream may start while its predecessor still runs -- frames of different batches
+   * are independent unless the host's range tracker says otherwise:
+   *   JF_PDL  launched with programmaticStreamSerializationAllowed: every CTA lets the next grid
+   *           start at once (griddepcontrol.launch_dependents) and, when its own work is done,
+   *           waits for the previous grid to have completed before it exits, so grids COMPLETE
+   *           in launch order;
+   *   JF_DEP  this launch touches memory an earlier launch that may still run reads or writes:
+   *           its CTAs wait for the previous grid to complete (and with it every grid before
+   *           that) before they touch anything. */
+  JF_DEP = 32,
+  JF_PDL = 64
 };
 
 /* One prepared rectangle as seen from one destination plane. */
@@ -110,18 +122,32 @@ struct FramePtrs {
   uint64_t pad_;
 };
 
-struct GroupParams {
+struct GroupHeader {
   uint32_t n_frames, n_bands, chunks_per_frame, cpf_magic;
   uint32_t total_chunks, lanes, per_lane, lanes_magic;
   int32_t src_pitch[3], dst_pitch[3];
   int32_t rect_off[3];        /* first RectRef of plane p inside FramePtrs::rects */
   int32_t flags;              /* JobFlags shared by the group */
-  BandDesc bands[kMaxGroupBands];
-  FramePtrs frames[kMaxPlainGroupFrames];
 };
+
+/* The parameter block of a group launch, sized by what it has to hold: a launch's parameters
+ * are copied whole by the driver and fetched by the GPU's front end before the first CTA starts
+ * (tools/launch_floor.cu: 3.0 us per launch with 1 KB of parameters, 5.1 us with 20 KB, 6.4 us
+ * with 32 KB), which is most of the cost of a one-frame launch at 720p / 1080p. The host keeps
+ * the full-size block and launches the smallest variant that fits. */
+template <int NF, int NB>
+struct GroupParamsT {
+  GroupHeader h;
+  BandDesc bands[NB];
+  FramePtrs frames[NF];
+};
+using GroupParams = GroupParamsT<kMaxPlainGroupFrames, kMaxGroupBands>;           /* 19.5 KB */
+using GroupParamsSmall = GroupParamsT<4, 16>;                                     /* 1.1 KB */
+using GroupParamsMedium = GroupParamsT<32, kMaxGroupBands>;                       /* 5.2 KB */
 /* > 4 KB of kernel parameters needs CUDA >= 12.1 and driver >= R530 (limit 32764 B), which
  * every sm_100a system has */
 static_assert (sizeof (GroupParams) <= 32764, "kernel parameters");
+static_assert (sizeof (GroupParamsSmall) <= 1280, "small group parameters");
 
 /* ---- multi-layout group launch: frames of one format / size / pitch set whose cue layouts
  * (band lists) differ -- many streams, each showing its own text. Still everything in kernel
@@ -190,15 +216,18 @@ enum PrepareMode : int32_t {
  * job 16-byte aligned with row_bytes % 16 == 0) or byte-granular. */
 /* d_coarse[i] = index of the job that holds chunk i << kCoarseShift. */
 constexpr int kCoarseShift = 4;
+/* sync = JF_PDL / JF_DEP bits of this launch (0: an ordinary, fully serialised launch) */
 cudaError_t launch_blend (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const uint32_t *d_coarse,
-    int n_jobs, uint32_t total_chunks, int kind, bool fast, cudaStream_t stream);
+    int n_jobs, uint32_t total_chunks, int kind, bool fast, int sync, cudaStream_t stream);
 /* Fills in total_chunks and the interleave fields of P, then launches. */
-cudaError_t launch_group (GroupParams &P, int kind, cudaStream_t stream);
+cudaError_t launch_group (GroupParams &P, int kind, int sync, cudaStream_t stream);
 /* Fills in total_chunks (from frame_begin[n_frames]) and the interleave fields, then launches. */
-cudaError_t launch_multi (MultiParams &P, int kind, cudaStream_t stream);
+cudaError_t launch_multi (MultiParams &P, int kind, int sync, cudaStream_t stream);
 /* n_elems = prepared elements per row (see PrepareMode). */
 cudaError_t launch_prepare (const PrepareParams &p, int n_elems, cudaStream_t stream);
 cudaError_t launch_scrub (uint8_t *buf, size_t bytes, cudaStream_t stream);
+/* bench helper: reads and rewrites `bytes` (multiple of 16) of mapped host memory in place */
+cudaError_t launch_pcie_probe (uint8_t *buf, size_t bytes, cudaStream_t stream);
 /* One TTML region composed onto the frame-sized premultiplied BGRA canvas (pixman 8-bit
  * arithmetic): background colour `bg` (premultiplied pixel, 0 = none), optional text layer,
  * group opacity mask `m8` (255 = none). Box already clipped to the canvas. */

@@ -68,7 +68,8 @@ class Stats(C.Structure):
                 ("algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("kernel_ms", C.c_double),
                 ("kernel_ms_launches", C.c_uint64), ("cache_bytes", C.c_uint64),
-                ("multi_launches", C.c_uint64), ("lazy_launches", C.c_uint64)]
+                ("multi_launches", C.c_uint64), ("lazy_launches", C.c_uint64),
+                ("dependent_launches", C.c_uint64)]
 
 
 # name -> (restype, argtypes); also the list tests check against the header
@@ -101,6 +102,10 @@ PROTOTYPES = {
     "fluc_ttmlblend_submit_many": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_int,
                                              C.c_int32, C.c_int32, C.c_uint32, C.POINTER(Frame),
                                              C.POINTER(Frame), C.POINTER(C.c_uint64)]),
+    "fluc_ttmlblend_submit_many_repeat": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_int,
+                                                    C.c_int32, C.c_int32, C.c_uint32, C.POINTER(Frame),
+                                                    C.POINTER(Frame), C.c_uint32, C.c_uint32]),
+    "fluc_ttmlblend_pcie_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.POINTER(C.c_double)]),
     "fluc_ttmlblend_flush": (C.c_int, [C.c_void_p]),
     "fluc_ttmlblend_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "fluc_ttmlblend_sync": (C.c_int, [C.c_void_p]),
@@ -350,11 +355,14 @@ class TtmlBlend:
         """Pre-marshalled arguments of submit_many (arrays of streams / frames / tickets)."""
 
         def __init__(self, streams, fmt, width, height, srcs, dsts, frame_flags=0):
+            """dsts may hold several sets of len(streams) frames (submit_many_repeat rotates them)."""
             n = len(streams)
+            assert len(dsts) % n == 0 and len(dsts) >= n
             self.n, self.fmt, self.width, self.height, self.flags = n, FORMATS[fmt], width, height, frame_flags
+            self.dst_sets = len(dsts) // n
             self.streams = (C.c_uint32 * n)(*streams)
             self.srcs = (Frame * n)(*srcs)
-            self.dsts = (Frame * n)(*dsts)
+            self.dsts = (Frame * len(dsts))(*dsts)
             self.tickets = (C.c_uint64 * n)()
 
     def submit_many(self, batch: "TtmlBlend.Batch"):
@@ -363,6 +371,20 @@ class TtmlBlend:
             self.h, batch.n, batch.streams, batch.fmt, batch.width, batch.height, batch.flags,
             batch.srcs, batch.dsts, batch.tickets), "submit_many")
         return batch.tickets
+
+    def submit_many_repeat(self, batch: "TtmlBlend.Batch", repeats: int):
+        """`repeats` x submit_many (+ flush) inside one C call (bench helper)."""
+        self._check(self.lib.fluc_ttmlblend_submit_many_repeat(
+            self.h, batch.n, batch.streams, batch.fmt, batch.width, batch.height, batch.flags,
+            batch.srcs, batch.dsts, batch.dst_sets, repeats), "submit_many_repeat")
+
+    def pcie_probe(self, mode: int, nbytes: int, seconds: float) -> float:
+        """GB/s per direction PCIe carries for this GPU right now: mode 0 copy engine both ways,
+        mode 1 a kernel rewriting host memory in place (bench helper)."""
+        g = C.c_double()
+        self._check(self.lib.fluc_ttmlblend_pcie_probe(self.h, mode, nbytes, float(seconds), C.byref(g)),
+                    "pcie_probe")
+        return g.value
 
     def flush(self):
         self._check(self.lib.fluc_ttmlblend_flush(self.h), "flush")

@@ -156,6 +156,10 @@ typedef struct {
   uint64_t lazy_launches;       /* launches in place that read the overlay first: vectors it leaves
                                  * untouched are skipped, vectors it covers opaquely are written
                                  * without being read (sparse cues, opaque boxes; exact either way) */
+  uint64_t dependent_launches;  /* batches that had to wait for everything launched before them: they
+                                 * write what an earlier batch that may still run reads or writes, or
+                                 * read what it writes (all others may overlap their predecessor's tail:
+                                 * programmatic dependent launch) */
 } FlucTtmlBlendStats;
 
 /* ---- lifetime -------------------------------------------------------- */
@@ -338,6 +342,23 @@ FLUC_EXPORT int fluc_ttmlblend_timer_begin (FlucTtmlBlend *thiz);
 FLUC_EXPORT int fluc_ttmlblend_timer_end (FlucTtmlBlend *thiz, double *ms);
 /* Writes `bytes` of device memory on the blend stream (L2 flush for benches). */
 FLUC_EXPORT int fluc_ttmlblend_scrub_l2 (FlucTtmlBlend *thiz, size_t bytes);
+/* Bench helper: `repeats` x submit_many of the same n frames (plus a flush each time the batch
+ * limit did not launch it) without returning to the caller in between. For one-frame batches a
+ * scripting-language loop around submit_many costs several times the launch itself. dsts holds
+ * dst_sets x n frames; repeat r writes into set r % dst_sets, as the frames of a running
+ * pipeline come out of a buffer pool rather than landing in the same buffers every time. */
+FLUC_EXPORT int fluc_ttmlblend_submit_many_repeat (FlucTtmlBlend *thiz, uint32_t n,
+    const uint32_t *streams, FlucTtmlBlendFormat fmt, int32_t width, int32_t height,
+    uint32_t frame_flags, const FlucTtmlBlendFrame *srcs, const FlucTtmlBlendFrame *dsts,
+    uint32_t dst_sets, uint32_t repeats);
+/* Bench helper: what PCIe carries for this GPU right now, with nothing of the blend in it. Moves
+ * `bytes` per iteration between pinned host memory and the device for about `seconds`:
+ *   mode 0  copy engine, both directions at once (the best a staged path could do)
+ *   mode 1  a kernel that reads and rewrites host memory in place (the zero-copy path's shape)
+ * and returns GB/s per direction. Call it on every GPU at the same time to measure a box
+ * (tools/pcie_ceiling.cu is the stand-alone version). */
+FLUC_EXPORT int fluc_ttmlblend_pcie_probe (FlucTtmlBlend *thiz, int mode, size_t bytes, double seconds,
+    double *gbs_per_direction);
 /* The cudaStream_t the batched blend launches on, as an opaque pointer. */
 FLUC_EXPORT void *fluc_ttmlblend_stream_handle (FlucTtmlBlend *thiz);
 

@@ -2,6 +2,8 @@
 stream B's input), ping-pong buffers, the same buffer written twice, two overlays on one host
 frame. The CTAs of one launch run in no order, so the runtime must cut the batch at such
 frames; the result must equal the sequential composition computed by the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -201,3 +203,77 @@ def test_host_forget_drops_automatic_registrations():
         assert c.host_forget(backing) == 0                   # nothing left
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("batch", [1, 3, 8])
+@pytest.mark.parametrize("seed", range(4))
+def test_random_dependency_chains(ctx, batch, seed):
+    """Launches may overlap their predecessors (programmatic dependent launch) unless the range
+    tracker finds a dependency: a random sequence of blends over a small pool of buffers --
+    sources and destinations picked at random, in place now and then -- must give exactly what
+    running them one after the other gives, whatever the batch size."""
+    import random
+    rnd = random.Random(9000 + seed)
+    fmt, w, h = ("NV12", 320, 180) if seed % 2 == 0 else ("BGRA", 256, 144)
+    ovs = [random_overlay(w, h, 960 + seed * 10 + i, density=0.5) for i in range(3)]
+    for i, ov in enumerate(ovs):
+        ctx.overlay_set_rectangles(760 + i, _rects(ov))
+    ctx.set_batch(batch, 0)
+    try:
+        n_buf = 6
+        bufs = [ctx.acquire(fmt, w, h) for _ in range(n_buf)]
+        model = [random_frame(fmt, w, h, 50 + seed * 10 + i) for i in range(n_buf)]
+        for b, m in zip(bufs, model):
+            b.upload(m)
+        before = ctx.stats()
+        t = None
+        for _ in range(80):
+            s, d, k = rnd.randrange(n_buf), rnd.randrange(n_buf), rnd.randrange(3)
+            if rnd.random() < 0.2:
+                d = s
+            t = ctx.submit(760 + k, fmt, w, h, bufs[s].c, bufs[d].c)
+            model[d] = oracle_blend(fmt, w, h, copy_planes(model[s]), _rects(ovs[k]))
+        ctx.flush()
+        ctx.wait(t)
+        after = ctx.stats()
+        for i, (b, m) in enumerate(zip(bufs, model)):
+            assert_planes_equal(b.download(), m, f"buffer {i} (batch {batch}, seed {seed})")
+        if os.environ.get("FLUC_TTMLBLEND_PDL") != "0":
+            assert after["dependent_launches"] > before["dependent_launches"]   # there were dependencies
+        for b in bufs:
+            b.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def test_independent_launches_are_not_serialised(ctx):
+    """Frames that share nothing with what is in flight are launched without waiting for it."""
+    fmt = "NV12"
+    ov = _overlays(1, 970)[0]
+    ctx.overlay_set_rectangles(770, _rects(ov))
+    ctx.set_batch(1, 0)
+    try:
+        srcs = [ctx.acquire(fmt, W, H) for _ in range(8)]
+        dsts = [ctx.acquire(fmt, W, H) for _ in range(8)]
+        frame = random_frame(fmt, W, H, 48)
+        for s in srcs:
+            s.upload(frame)
+        ctx.sync()
+        before = ctx.stats()
+        t = [ctx.submit(770, fmt, W, H, s.c, d.c) for s, d in zip(srcs, dsts)]
+        mid = ctx.stats()
+        assert mid["launches"] - before["launches"] == 8
+        assert mid["dependent_launches"] == before["dependent_launches"]
+        # the same destinations again, nothing waited for: now a launch writes what one that may
+        # still run writes
+        t = [ctx.submit(770, fmt, W, H, s.c, d.c) for s, d in zip(srcs, dsts)]
+        ctx.wait(t[-1])
+        if os.environ.get("FLUC_TTMLBLEND_PDL") != "0":
+            assert ctx.stats()["dependent_launches"] > mid["dependent_launches"]
+        want = oracle_blend(fmt, W, H, copy_planes(frame), _rects(ov))
+        for d in dsts:
+            assert_planes_equal(d.download(), want, "independent launches")
+        for f in srcs + dsts:
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)

@@ -35,6 +35,39 @@ k_copy (const uint4 *__restrict__ s, uint4 *__restrict__ d, size_t n)
       d[base + k * 256] = v[k];
 }
 
+/* the same copy, but every CTA lets the next grid of the stream start at once (programmatic
+ * dependent launch): launched with programmaticStreamSerializationAllowed, independent work */
+__global__ void __launch_bounds__ (256)
+k_copy_pdl (const uint4 *__restrict__ s, uint4 *__restrict__ d, size_t n)
+{
+  asm volatile ("griddepcontrol.launch_dependents;" ::: "memory");
+  const size_t base = (size_t) blockIdx.x * 1024 + threadIdx.x;
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (base + k * 256 < n)
+      v[k] = s[base + k * 256];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (base + k * 256 < n)
+      d[base + k * 256] = v[k];
+}
+
+static cudaError_t
+launch_pdl (const uint4 *s, uint4 *d, size_t n, cudaStream_t st)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3 ((unsigned) ((n + 1023) / 1024));
+  cfg.blockDim = dim3 (256);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx (&cfg, k_copy_pdl, s, d, n);
+}
+
 static double
 now ()
 {
@@ -43,9 +76,8 @@ now ()
 
 template <typename F>
 static int
-run (const char *name, F launch, cudaStream_t st, bool with_event)
+run (const char *name, F launch, cudaStream_t st, bool with_event, int n = 20000)
 {
-  const int n = 20000;
   cudaEvent_t a, b, evs[64];
   CK (cudaEventCreate (&a));
   CK (cudaEventCreate (&b));
@@ -87,6 +119,11 @@ main ()
   CK (cudaMalloc (&s, bytes));
   CK (cudaMalloc (&d, bytes));
   const size_t n16 = bytes / 16;
+  const size_t big = (size_t) 32 * 12441600;
+  uint4 *sb, *db;
+  CK (cudaMalloc (&sb, big));
+  CK (cudaMalloc (&db, big));
+  const size_t nbig = big / 16;
   for (int ev = 0; ev < 2; ev++) {
     const char *sfx = ev ? " + event record" : "";
     char name[96];
@@ -102,6 +139,12 @@ main ()
     run (name, [&] { k_params<20480><<<190, 256, 0, st>>> (p20, out); }, st, ev);
     snprintf (name, sizeof name, "1080p NV12 frame copy (3.1 MB -> 3.1 MB)%s", sfx);
     run (name, [&] { k_copy<<<(unsigned) ((n16 + 1023) / 1024), 256, 0, st>>> (s, d, n16); }, st, ev);
+    snprintf (name, sizeof name, "same, programmatic dependent launch%s", sfx);
+    run (name, [&] { launch_pdl (s, d, n16, st); }, st, ev);
+    snprintf (name, sizeof name, "398 MB copy (32 x 4K NV12)%s", sfx);
+    run (name, [&] { k_copy<<<(unsigned) ((nbig + 1023) / 1024), 256, 0, st>>> (sb, db, nbig); }, st, ev, 400);
+    snprintf (name, sizeof name, "same, programmatic dependent launch%s", sfx);
+    run (name, [&] { launch_pdl (sb, db, nbig, st); }, st, ev, 400);
   }
   return 0;
 }
