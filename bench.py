@@ -420,6 +420,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the legs beside the headline (distinct cues, config 5, multi, pageable, in place)")
+    ap.add_argument("--distinct-cues", action="store_true",
+                    help="headline workload = the distinct-cues variant (one stream and cue image per frame): "
+                         "for profiling that leg on its own")
     ap.add_argument("--event-pairs", type=int, default=12,
                     help="launches timed one by one with a CUDA-event pair AFTER the timed region "
                          "(cross-check of launch_ms)")
@@ -446,7 +449,7 @@ def main():
     extras = not args.no_extras
 
     # ---- headline: device-resident frames --------------------------------------------------
-    work = DeviceWorkload(ctx, wl, sh, cfg, fmt, world, rank)
+    work = DeviceWorkload(ctx, wl, sh, cfg, fmt, world, rank, distinct_cues=args.distinct_cues)
     batch = work.batch
     ctx.set_batch(min(batch, 1024), 0)     # one launch per `batch` frames, no linger timer
     work.steps(args.warmup)
@@ -500,7 +503,7 @@ def main():
 
     # ---- distinct cues: the prepared overlay exceeds L2 -------------------------------------
     distinct = None
-    if extras and cfg.streams == 1 and cfg.batch > 1:
+    if extras and cfg.streams == 1 and cfg.batch > 1 and not args.distinct_cues:
         try:
             dw = DeviceWorkload(ctx, wl, sh, cfg, fmt, world, rank, distinct_cues=True, stream_base=1000)
             dw.steps(args.warmup)

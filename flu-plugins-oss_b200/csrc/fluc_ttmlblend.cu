@@ -240,6 +240,11 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->use_multi = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_PDL")))
     c->use_pdl = atoi (e) != 0;
+  c->stage_threads = (int) std::max (2u, std::min (12u, std::thread::hardware_concurrency () / 2));
+  if ((e = getenv ("FLUC_TTMLBLEND_STAGE_THREADS")))
+    c->stage_threads = std::max (0, std::min (64, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_STAGE_SLOTS")))
+    c->stage_slots_max = std::max (1, std::min (4096, atoi (e)));
   if ((e = getenv ("FLUC_TTMLBLEND_AUTO_REGISTER")))
     c->auto_register = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_MODE")))
@@ -267,6 +272,7 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
   }
   if (c->sched.joinable ())
     c->sched.join ();
+  stage_shutdown (c);
   cudaSetDevice (c->device);
   /* our own streams only: other users of the device are none of our business */
   for (cudaStream_t st : { c->blend_stream, c->up_stream, c->table_stream })
@@ -305,6 +311,7 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
       free_slot (c->lanes[i].table[1]);
       if (c->lanes[i].dev) cudaFree (c->lanes[i].dev);
     }
+    stage_free_slots (c);
     for (auto &p : c->pool_free) {
       if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
     }
@@ -422,54 +429,6 @@ fluc_ttmlblend_set_chroma_mode (FlucTtmlBlend *thiz, int mode)
 }
 
 /* ---- device-resident frames ------------------------------------------ */
-
-/* The bytes a frame's planes occupy, as at most three ranges (planes that are neighbours in
- * memory -- pool frames, GStreamer's default layout -- come out as one). */
-struct FrameExtent {
-  uintptr_t lo[3], hi[3];
-  int n = 0;
-  FrameExtent (int fmt, int W, int H, const FlucTtmlBlendFrame *f)
-  {
-    for (int pl = 0; pl < format_planes (fmt); pl++) {
-      const uintptr_t a = (uintptr_t) f->plane[pl];
-      const uintptr_t b = a + (uintptr_t) f->stride[pl] * (uintptr_t) (plane_rows (fmt, pl, H) - 1) +
-          (uintptr_t) plane_row_bytes (fmt, pl, W);
-      if (n && a >= lo[n - 1] && a <= hi[n - 1] + 4096)
-        hi[n - 1] = std::max (hi[n - 1], b);
-      else {
-        lo[n] = a;
-        hi[n] = b;
-        n++;
-      }
-    }
-  }
-  uintptr_t hull_lo () const
-  {
-    uintptr_t v = lo[0];
-    for (int i = 1; i < n; i++)
-      v = std::min (v, lo[i]);
-    return v;
-  }
-  uintptr_t hull_hi () const
-  {
-    uintptr_t v = hi[0];
-    for (int i = 1; i < n; i++)
-      v = std::max (v, hi[i]);
-    return v;
-  }
-  bool hits (const IntervalSet &s) const
-  {
-    for (int i = 0; i < n; i++)
-      if (s.overlaps (lo[i], hi[i]))
-        return true;
-    return false;
-  }
-  void add_to (IntervalSet &s) const
-  {
-    for (int i = 0; i < n; i++)
-      s.add (lo[i], hi[i]);
-  }
-};
 
 /* A frame joins the pending batch only if no queued frame conflicts with it: the CTAs of one
  * launch run in no particular order, so a frame that writes what a queued frame writes (the
@@ -592,6 +551,9 @@ fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
   ENTER (thiz);
   if (ticket == 0 || ticket > c->next_ticket)
     return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
+  int staged_rc = 0;
+  if (stage_wait (c, lk, ticket, &staged_rc))
+    return staged_rc;
   auto lt = c->lane_tickets.find (ticket);
   if (lt != c->lane_tickets.end ()) {
     Lane &l = c->lanes[lt->second];
@@ -667,6 +629,7 @@ int
 fluc_ttmlblend_sync (FlucTtmlBlend *thiz)
 {
   ENTER (thiz);
+  stage_drain (c, lk, 0);       /* staged host frames: every copy-in has reached the batch */
   int rc = launch_pending (c);
   if (rc)
     return rc;
@@ -713,7 +676,8 @@ fluc_ttmlblend_sync (FlucTtmlBlend *thiz)
       c->lane_tickets.erase (lane_ticket[i]);
     }
   reap_batches (c);
-  return 0;
+  stage_drain (c, lk, 1);       /* ... and has been copied back into the caller's frame */
+  return c->sticky;
 }
 
 int
@@ -809,9 +773,57 @@ fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled)
 }
 
 
+}  /* extern "C" */
+
+/* A device-accessible host frame (zf: its device addresses, hf: its host addresses) joins the
+ * pending batch: the blend kernel reads the rows under the cue from host memory and writes them
+ * back, all over PCIe, one launch for every queued frame. Context locked. */
+int
+tbh::queue_mapped_frame (Ctx *c, uint64_t tk, uint32_t stream, const std::shared_ptr<Overlay> &ov, Prepared *prep,
+    int fmt, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *zfp, const FlucTtmlBlendFrame *hf)
+{
+  int rc;
+  const FlucTtmlBlendFrame &zf = *zfp;
+  PendingFrame f;
+  f.overlay = ov;
+  f.prep = prep;
+  f.ticket = tk;
+  f.stream = stream;
+  note_stream (c, stream);
+  const FrameExtent xz (fmt, W, H, &zf), xh (fmt, W, H, hf);
+  if ((rc = order_against_pending (c, xz, xz, true)))
+    return rc;
+  /* the same buffer still on its way through a staging lane (it was not device-accessible a
+   * moment ago): the blend stream waits for that lane */
+  for (int i = 0; i < kLanes; i++)
+    if (c->lanes[i].busy && xh.hull_lo () < c->lanes[i].host_hi && c->lanes[i].host_lo < xh.hull_hi ())
+      CU (c, cudaStreamWaitEvent (c->blend_stream, c->lanes[i].done, 0));
+  f.layout = find_layout (c, prep, ov->lazy_inplace, fmt, W, H, frame_flags, &zf, &zf, true);
+  for (int pl = 0; pl < 3; pl++) {
+    f.src[pl] = static_cast<const uint8_t *> (zf.plane[pl]);
+    f.dst[pl] = static_cast<uint8_t *> (zf.plane[pl]);
+  }
+  xz.add_to (c->pending_dst);
+  if (zf.plane[0] != hf->plane[0])
+    xh.add_to (c->pending_dst);         /* no unified addressing: known under both addresses */
+  xh.add_to (c->inflight_host);
+  c->stats.h2d_bytes += f.layout->window_bytes;
+  c->stats.d2h_bytes += f.layout->window_bytes;
+  if (c->pending.empty ())
+    c->oldest_pending = std::chrono::steady_clock::now ();
+  c->pending.push_back (std::move (f));
+  if (c->pending.size () >= c->max_batch)
+    return launch_pending (c);
+  if (c->linger_us)
+    c->cv.notify_all ();
+  return 0;
+}
+
+extern "C" {
+
 static int
-blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t frame_flags,
-    const FlucTtmlBlendFrame *hf, uint64_t *ticket)
+blend_host_locked (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, int fmt, int32_t W, int32_t H,
+    uint32_t frame_flags, const FlucTtmlBlendFrame *hf, uint64_t *ticket)
 {
   int rc;
   fmt = format_canon (fmt);
@@ -878,44 +890,14 @@ blend_host_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint3
     }
   }
 
-  if (mapped && c->host_mode == HM_ZEROCOPY) {
-    /* zero copy: the frame joins the batch; the blend kernel reads the rows
-     * under the cue from host memory and writes them back, all over PCIe,
-     * one launch for every queued frame */
-    PendingFrame f;
-    f.overlay = ov;
-    f.prep = prep;
-    f.ticket = tk;
-    f.stream = stream;
-    note_stream (c, stream);
-    const FrameExtent xz (fmt, W, H, &zf), xh (fmt, W, H, hf);
-    if ((rc = order_against_pending (c, xz, xz, true)))
-      return rc;
-    /* the same buffer still on its way through a staging lane (it was not device-accessible a
-     * moment ago): the blend stream waits for that lane */
-    for (int i = 0; i < kLanes; i++)
-      if (c->lanes[i].busy && xh.hull_lo () < c->lanes[i].host_hi && c->lanes[i].host_lo < xh.hull_hi ())
-        CU (c, cudaStreamWaitEvent (c->blend_stream, c->lanes[i].done, 0));
-    f.layout = find_layout (c, prep, ov->lazy_inplace, fmt, W, H, frame_flags, &zf, &zf, true);
-    for (int pl = 0; pl < 3; pl++) {
-      f.src[pl] = static_cast<const uint8_t *> (zf.plane[pl]);
-      f.dst[pl] = static_cast<uint8_t *> (zf.plane[pl]);
-    }
-    xz.add_to (c->pending_dst);
-    if (zf.plane[0] != hf->plane[0])
-      xh.add_to (c->pending_dst);       /* no unified addressing: known under both addresses */
-    xh.add_to (c->inflight_host);
-    c->stats.h2d_bytes += f.layout->window_bytes;
-    c->stats.d2h_bytes += f.layout->window_bytes;
-    if (c->pending.empty ())
-      c->oldest_pending = std::chrono::steady_clock::now ();
-    c->pending.push_back (std::move (f));
-    if (c->pending.size () >= c->max_batch)
-      return launch_pending (c);
-    if (c->linger_us)
-      c->cv.notify_all ();
-    return 0;
-  }
+  if (mapped && c->host_mode == HM_ZEROCOPY)
+    return queue_mapped_frame (c, tk, stream, ov, prep, fmt, W, H, frame_flags, &zf, hf);
+
+  /* Not device-accessible (ordinary pageable memory, or not 16-byte aligned): worker threads copy
+   * the rows under the cue into a pinned staging frame, that frame is blended zero copy like
+   * any other, and the rows are copied back (staging.cu). */
+  if (c->host_mode == HM_ZEROCOPY && c->stage_threads > 0)
+    return stage_frame (c, lk, tk, stream, ov, prep, fmt, W, H, frame_flags, hf);
 
   Lane &l = c->lanes[c->next_lane];
   const int lane_idx = c->next_lane;
@@ -1034,7 +1016,7 @@ fluc_ttmlblend_blend_host (FlucTtmlBlend *thiz, uint32_t stream, FlucTtmlBlendFo
     int32_t W, int32_t H, uint32_t frame_flags, const FlucTtmlBlendFrame *hf, uint64_t *ticket)
 {
   ENTER (thiz);
-  return blend_host_locked (c, stream, fmt, W, H, frame_flags, hf, ticket);
+  return blend_host_locked (c, lk, stream, fmt, W, H, frame_flags, hf, ticket);
 }
 
 int
@@ -1046,7 +1028,7 @@ fluc_ttmlblend_blend_host_many (FlucTtmlBlend *thiz, uint32_t n, const uint32_t 
   if (n && (!streams || !host_frames))
     return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   for (uint32_t i = 0; i < n; i++) {
-    int rc = blend_host_locked (c, streams[i], fmt, W, H, frame_flags, &host_frames[i],
+    int rc = blend_host_locked (c, lk, streams[i], fmt, W, H, frame_flags, &host_frames[i],
         tickets ? &tickets[i] : nullptr);
     if (rc)
       return rc;

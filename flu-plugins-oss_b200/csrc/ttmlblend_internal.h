@@ -356,6 +356,54 @@ struct IntervalSet {
   }
 };
 
+/* The bytes a frame's planes occupy, as at most three ranges (planes that are neighbours in
+ * memory -- pool frames, GStreamer's default layout -- come out as one). */
+struct FrameExtent {
+  uintptr_t lo[3], hi[3];
+  int n = 0;
+  FrameExtent (int fmt, int W, int H, const FlucTtmlBlendFrame *f)
+  {
+    for (int pl = 0; pl < format_planes (fmt); pl++) {
+      const uintptr_t a = (uintptr_t) f->plane[pl];
+      const uintptr_t b = a + (uintptr_t) f->stride[pl] * (uintptr_t) (plane_rows (fmt, pl, H) - 1) +
+          (uintptr_t) plane_row_bytes (fmt, pl, W);
+      if (n && a >= lo[n - 1] && a <= hi[n - 1] + 4096)
+        hi[n - 1] = std::max (hi[n - 1], b);
+      else {
+        lo[n] = a;
+        hi[n] = b;
+        n++;
+      }
+    }
+  }
+  uintptr_t hull_lo () const
+  {
+    uintptr_t v = lo[0];
+    for (int i = 1; i < n; i++)
+      v = std::min (v, lo[i]);
+    return v;
+  }
+  uintptr_t hull_hi () const
+  {
+    uintptr_t v = hi[0];
+    for (int i = 1; i < n; i++)
+      v = std::max (v, hi[i]);
+    return v;
+  }
+  bool hits (const IntervalSet &s) const
+  {
+    for (int i = 0; i < n; i++)
+      if (s.overlaps (lo[i], hi[i]))
+        return true;
+    return false;
+  }
+  void add_to (IntervalSet &s) const
+  {
+    for (int i = 0; i < n; i++)
+      s.add (lo[i], hi[i]);
+  }
+};
+
 /* do two range sets share a byte? walks the smaller one */
 inline bool
 sets_overlap (const IntervalSet &a, const IntervalSet &b)
@@ -386,6 +434,26 @@ struct Lane {
   size_t dev_bytes = 0;
   TableSlot table[2];
   std::shared_ptr<Overlay> keep;
+};
+
+/* ---- staged host frames (staging.cu) ---- */
+struct StageSpan { int plane, b0, nb, y0, rows; };       /* rows [y0, y0+rows), bytes [b0, b0+nb) of a plane */
+
+struct StageJob {
+  enum State { COPY_IN, ON_GPU, COPY_OUT, DONE };
+  uint64_t ticket = 0;                 /* what blend_host handed out */
+  uint64_t gpu_ticket = 0;             /* the staging frame's own ticket in the batch */
+  uint32_t stream = 0;
+  int fmt = 0, W = 0, H = 0;
+  uint32_t frame_flags = 0;
+  FlucTtmlBlendFrame user = {};        /* the caller's frame */
+  uintptr_t user_lo = 0, user_hi = 0;
+  PoolEntry slot = {};                 /* pinned staging frame */
+  std::shared_ptr<Overlay> ov;
+  Prepared *prep = nullptr;
+  std::vector<StageSpan> spans;
+  State state = COPY_IN;
+  int rc = 0;
 };
 
 /* How blend_host moves a device-accessible (pinned) host frame. */
@@ -475,6 +543,17 @@ struct Ctx {
   Lane lanes[kLanes];
   int next_lane = 0;
   std::map<uint64_t, int> lane_tickets;
+
+  /* staged host frames (staging.cu): FLUC_TTMLBLEND_STAGE_THREADS copy workers (0: the DMA lanes
+   * above instead), at most FLUC_TTMLBLEND_STAGE_SLOTS pinned staging frames in use */
+  int stage_threads = 0, stage_slots_max = 64, stage_slots_total = 0;
+  int stage_active = 0, stage_copying = 0;
+  std::vector<PoolEntry> stage_slots_free;
+  std::deque<std::shared_ptr<StageJob>> stage_in, stage_gpu, stage_out;
+  std::map<uint64_t, std::shared_ptr<StageJob>> stage_jobs;      /* by blend_host ticket */
+  std::condition_variable stage_cv, stage_gpu_cv, stage_done_cv;
+  std::vector<std::thread> stage_workers;
+  std::thread stage_completer;
 
   /* CPUs of the NUMA node the GPU hangs off (empty: unknown / disabled). Pinned host frames are
    * allocated with the calling thread moved there for the moment, so that their pages are local
@@ -567,6 +646,18 @@ several_streams_active (const Ctx *c)
       return true;
   return false;
 }
+
+/* fluc_ttmlblend.cu */
+int queue_mapped_frame (Ctx *c, uint64_t tk, uint32_t stream, const std::shared_ptr<Overlay> &ov, Prepared *prep,
+    int fmt, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *zf, const FlucTtmlBlendFrame *hf);
+
+/* staging.cu */
+int stage_frame (Ctx *c, std::unique_lock<std::mutex> &lk, uint64_t tk, uint32_t stream, const std::shared_ptr<Overlay> &ov,
+    Prepared *prep, int fmt, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *hf);
+int stage_wait (Ctx *c, std::unique_lock<std::mutex> &lk, uint64_t ticket, int *rc);
+void stage_drain (Ctx *c, std::unique_lock<std::mutex> &lk, int phase);
+void stage_shutdown (Ctx *c);
+void stage_free_slots (Ctx *c);
 
 /* scheduler.cu */
 cudaEvent_t event_get (Ctx *c);

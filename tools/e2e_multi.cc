@@ -49,7 +49,7 @@ barrier (Shared *sh, int n)
 
 struct Options {
   std::vector<int> gpus;
-  bool threads = false, pin = false, opaque = false;
+  bool threads = false, pin = false, opaque = false, pageable = false;
   double secs = 2.0;
   int batch = 32;
 };
@@ -99,16 +99,29 @@ worker (const Options &o, int w, Shared *sh)
   for (auto &set : sets) {
     set.resize ((size_t) o.batch);
     for (auto &f : set) {
-      OK (fluc_ttmlblend_frame_pool_acquire (ctx, FLUC_TTMLBLEND_FORMAT_NV12, W, H, 1, &f));
+      if (o.pageable) {         /* ordinary memory, GStreamer's default NV12 layout */
+        uint8_t *m = (uint8_t *) malloc ((size_t) W * H * 3 / 2);
+        f.plane[0] = m;
+        f.plane[1] = m + (size_t) W * H;
+        f.stride[0] = f.stride[1] = W;
+      } else {
+        OK (fluc_ttmlblend_frame_pool_acquire (ctx, FLUC_TTMLBLEND_FORMAT_NV12, W, H, 1, &f));
+      }
       memset (f.plane[0], 0x55, (size_t) f.stride[0] * H);
       memset (f.plane[1], 0x80, (size_t) f.stride[1] * (H / 2));
     }
   }
-  std::vector<uint64_t> tickets ((size_t) o.batch);
+  std::vector<uint64_t> tickets ((size_t) o.batch), prev_all;
   uint64_t prev = 0;
   auto step = [&](int i) {
     OK (fluc_ttmlblend_blend_host_many (ctx, (uint32_t) o.batch, streams.data (), FLUC_TTMLBLEND_FORMAT_NV12, W, H, 0,
             sets[i & 1].data (), tickets.data ()));
+    if (o.pageable) {           /* staged frames complete one by one: wait for each of the previous set */
+      for (uint64_t t : prev_all)
+        OK (fluc_ttmlblend_wait (ctx, t));
+      prev_all = tickets;
+      return;
+    }
     if (prev)
       OK (fluc_ttmlblend_wait (ctx, prev));
     prev = tickets.back ();
@@ -158,6 +171,8 @@ main (int argc, char **argv)
       o.pin = true;
     else if (a == "--opaque")
       o.opaque = true;
+    else if (a == "--pageable")
+      o.pageable = true;
     else if (a == "--secs")
       o.secs = atof (next ().c_str ());
     else if (a == "--batch")
@@ -208,7 +223,7 @@ main (int argc, char **argv)
   const char *sy = getenv ("FLUC_TTMLBLEND_SYNC"), *hm = getenv ("FLUC_TTMLBLEND_HOST_MODE");
   printf ("e2e %d GPU(s) as %s, pin=%d sync=%s host_mode=%s %s: %9.0f frames/s aggregate, %6.1f GB/s each way; per GPU:",
       G, o.threads ? "threads" : "processes", o.pin ? 1 : 0, sy ? sy : "spin", hm ? hm : "1",
-      o.opaque ? "opaque" : "translucent", fps, gbs);
+      o.pageable ? (o.opaque ? "opaque, pageable frames" : "translucent, pageable frames") : o.opaque ? "opaque" : "translucent", fps, gbs);
   for (int w = 0; w < G; w++)
     printf (" %.0f", sh->fps[w]);
   printf ("\n");
