@@ -395,7 +395,23 @@ fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream, const uint8_t 
     q.flags = FLUC_TTMLBLEND_FLAG_PREMULTIPLIED_ALPHA;   /* Cairo ARGB32, gstttmlrender.c:1446 */
     rr.push_back (q);
   }
-  return overlay_install (c, lk, stream, rr.data (), (uint32_t) rr.size ());
+  return overlay_install (c, lk, stream, rr.data (), (uint32_t) rr.size (), w, h);
+}
+
+int
+fluc_ttmlblend_overlay_update (FlucTtmlBlend *thiz, uint32_t stream, const uint8_t *bgra,
+    int32_t w, int32_t h, int32_t stride, const FlucTtmlBlendRect *changed, uint32_t n_changed)
+{
+  {
+    ENTER (thiz);
+    if (!bgra || w <= 0 || h <= 0 || stride < 4 * w || (n_changed && !changed))
+      return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
+    const int rc = overlay_update_image (c, lk, stream, bgra, w, h, stride, changed, n_changed);
+    if (rc != FLUC_TTMLBLEND_ERROR_NOT_FOUND)
+      return rc;
+  }
+  /* nothing to patch: the image whole (auto-crop finds what is in it) */
+  return fluc_ttmlblend_overlay_set (thiz, stream, bgra, w, h, stride, nullptr, 0);
 }
 
 int
@@ -1375,6 +1391,7 @@ fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *o
     sum.multi_launches += s.multi_launches;
     sum.lazy_launches += s.lazy_launches;
     sum.dependent_launches += s.dependent_launches;
+    sum.overlays_updated += s.overlays_updated;
   }
   *out = sum;
 }

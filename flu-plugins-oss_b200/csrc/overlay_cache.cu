@@ -32,14 +32,30 @@ free_deferred (Ctx *c, const std::vector<void *> &ptrs)
     cudaFreeAsync (p, c->reaper);
 }
 
+DevBlock::~DevBlock ()
+{
+  if (ctx && ptr)
+    free_deferred (ctx, { ptr });
+}
+
+/* Blocks nobody else holds are freed in one go (one fence per stream instead of one per block);
+ * blocks a newer overlay of the stream shares (overlay_update) live on with it. */
 Overlay::~Overlay ()
 {
   std::vector<void *> ptrs;
-  for (void *a : raw_allocs)
-    ptrs.push_back (a);
+  auto take = [&ptrs](std::shared_ptr<DevBlock> &b) {
+    if (b && b.use_count () == 1 && b->ptr) {
+      ptrs.push_back (b->ptr);
+      b->ptr = nullptr;
+    }
+  };
+  for (RawRect &r : rects)
+    take (r.block);
   for (auto &p : prepared) {
-    for (void *a : p->allocs)
-      ptrs.push_back (a);
+    for (PreparedRect &pr : p->per_rect)
+      for (auto &b : pr.blocks)
+        take (b);
+    take (p->table_block);
     if (p->ready)
       cudaEventDestroy (p->ready);
   }
@@ -50,13 +66,28 @@ Overlay::~Overlay ()
 /* ---------------------------------------------------------------------- */
 /* prepare: raw BGRA rectangle -> per-plane prepared overlay              */
 
-int
-dev_alloc (Ctx *c, Prepared *p, size_t bytes, uint8_t **out)
+/* a stream-ordered allocation on the upload stream */
+static int
+dev_block (Ctx *c, size_t bytes, std::shared_ptr<DevBlock> *out)
 {
   void *ptr = nullptr;
   CU (c, cudaMallocFromPoolAsync (&ptr, std::max<size_t> (bytes, 16), c->mem_pool, c->up_stream));
-  p->allocs.push_back (ptr);
-  *out = static_cast<uint8_t *> (ptr);
+  std::shared_ptr<DevBlock> b (new DevBlock ());
+  b->ctx = c;
+  b->ptr = ptr;
+  *out = std::move (b);
+  return 0;
+}
+
+static int
+dev_alloc (Ctx *c, PreparedRect *pr, size_t bytes, uint8_t **out)
+{
+  std::shared_ptr<DevBlock> b;
+  int rc = dev_block (c, bytes, &b);
+  if (rc)
+    return rc;
+  *out = static_cast<uint8_t *> (b->ptr);
+  pr->blocks.push_back (std::move (b));
   return 0;
 }
 
@@ -76,10 +107,7 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
   std::unique_ptr<Prepared> P (new Prepared ());
   const int rc = prepare_build (c, ov, format, W, H, P);
   if (rc) {
-    /* half-built (out of memory, too many rectangles): give back what it holds; only the
-     * upload stream has touched it */
-    for (void *a : P->allocs)
-      cudaFreeAsync (a, c->up_stream);
+    /* half-built (out of memory, too many rectangles): its blocks go back with it */
     if (P->ready)
       cudaEventDestroy (P->ready);
     return rc;
@@ -89,227 +117,227 @@ prepare_overlay (Ctx *c, Overlay *ov, int format, int W, int H, Prepared **out)
   return 0;
 }
 
+/* Prepares one rectangle for one destination format: allocates its planes, runs the prepare
+ * kernel(s) on the upload stream, and notes how each destination plane sees it. */
 static int
-prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Prepared> &P)
+prepare_rect (Ctx *c, const RawRect &rr, int format, int W, int H, bool chroma_average, PreparedRect &out)
 {
-  P->format = format;
-  P->W = W;
-  P->H = H;
-  P->chroma_average = c->chroma_average;
   const int kind = plane_kind (format);
   const int n_planes = format_planes (format);
+  /* gst_video_blend clipping: rr is already clipped at the left/top */
+  const int cx0 = rr.x, cy0 = rr.y;
+  const int cx1 = std::min (rr.x + rr.w, W), cy1 = std::min (rr.y + rr.h, H);
+  if (cx1 <= cx0 || cy1 <= cy0)
+    return 0;
+  if (rr.ga == 0)
+    return 0;                 /* asrc == 0 everywhere: blends nothing */
 
-  for (const FlucTtmlBlendRect &d : ov->declared) {
-    const int w = std::min (d.x + d.w, W) - d.x, h = std::min (d.y + d.h, H) - d.y;
-    if (w > 0 && h > 0)
-      P->overlay_px += (uint64_t) w * (uint64_t) h;
-  }
-  for (const RawRect &rr : ov->rects) {
-    /* gst_video_blend clipping: rr is already clipped at the left/top */
-    const int cx0 = rr.x, cy0 = rr.y;
-    const int cx1 = std::min (rr.x + rr.w, W), cy1 = std::min (rr.y + rr.h, H);
-    if (cx1 <= cx0 || cy1 <= cy0)
-      continue;
-    if (rr.ga == 0)
-      continue;                 /* asrc == 0 everywhere: blends nothing */
+  PrepareParams pp = {};
+  pp.raw = rr.dev;
+  pp.raw_pitch = rr.pitch;
+  pp.raw_w = rr.w;
+  pp.raw_h = rr.h;
+  pp.fx = rr.x;
+  pp.fy = rr.y;
+  pp.cx0 = cx0; pp.cy0 = cy0; pp.cx1 = cx1; pp.cy1 = cy1;
+  pp.ga = rr.ga;
+  pp.premul = rr.premul ? 1 : 0;
 
-    PrepareParams pp = {};
-    pp.raw = rr.dev;
-    pp.raw_pitch = rr.pitch;
-    pp.raw_w = rr.w;
-    pp.raw_h = rr.h;
-    pp.fx = rr.x;
-    pp.fy = rr.y;
-    pp.cx0 = cx0; pp.cy0 = cy0; pp.cx1 = cx1; pp.cy1 = cy1;
-    pp.ga = rr.ga;
-    pp.premul = rr.premul ? 1 : 0;
-
-    pp.sub_x = format_sub_x (format);
-    pp.sub_y = format_sub_y (format);
-    if (kind == PK_PLANE8 && format_packed_422 (format)) {
-      /* YUY2 / UYVY: one plane of macropixels, every byte gets its own alpha + colour */
+  pp.sub_x = format_sub_x (format);
+  pp.sub_y = format_sub_y (format);
+  if (kind == PK_PLANE8 && format_packed_422 (format)) {
+    /* YUY2 / UYVY: one plane of macropixels, every byte gets its own alpha + colour */
+    RectRef ref = {};
+    ref.v0 = (4 * (cx0 / 2)) / 16;
+    ref.v1 = ceil_div (4 * ceil_div (cx1, 2), 16);
+    ref.y0 = cy0;
+    ref.y1 = cy1;
+    ref.pitch = (ref.v1 - ref.v0) * 16;
+    ref.ga = 255;
+    const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+    uint8_t *a, *col;
+    int rc;
+    if ((rc = dev_alloc (c, &out, bytes, &a)) || (rc = dev_alloc (c, &out, bytes, &col)))
+      return rc;
+    ref.a = a;
+    ref.c = col;
+    pp.mode = format == FLUC_TTMLBLEND_FORMAT_YUY2 ? PM_YUY2 : format == FLUC_TTMLBLEND_FORMAT_UYVY ? PM_UYVY :
+        format == FLUC_TTMLBLEND_FORMAT_YVYU ? PM_YVYU : PM_VYUY;
+    pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
+    pp.out_pitch = ref.pitch;
+    pp.v0 = ref.v0;
+    pp.row0 = cy0;
+    pp.rows = cy1 - cy0;
+    CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
+    c->stats.prepare_launches++;
+    out.refs[out.n_refs++] = { 0, ref };
+  } else if (kind == PK_PLANE8_RGB || (kind == PK_PLANE8 && format_packed_444_3 (format))) {
+    /* v308 / IYU2 / RGB / BGR: one plane, three bytes per pixel, every byte its own alpha +
+     * colour; the RGB pair keeps the source colours and the rectangle's flags for the blend */
+    RectRef ref = {};
+    ref.v0 = (3 * cx0) / 16;
+    ref.v1 = ceil_div (3 * cx1, 16);
+    ref.y0 = cy0;
+    ref.y1 = cy1;
+    ref.pitch = (ref.v1 - ref.v0) * 16;
+    ref.ga = 255;
+    const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+    uint8_t *a, *col;
+    int rc;
+    if ((rc = dev_alloc (c, &out, bytes, &a)) || (rc = dev_alloc (c, &out, bytes, &col)))
+      return rc;
+    ref.a = a;
+    ref.c = col;
+    if (kind == PK_PLANE8_RGB) {
+      ref.ga = rr.ga;
+      ref.src_premul = rr.premul ? 1 : 0;
+    }
+    pp.mode = format == FLUC_TTMLBLEND_FORMAT_v308 ? PM_V308 : format == FLUC_TTMLBLEND_FORMAT_IYU2 ? PM_IYU2 :
+        format == FLUC_TTMLBLEND_FORMAT_RGB ? PM_RGB24 : PM_BGR24;
+    pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
+    pp.out_pitch = ref.pitch;
+    pp.v0 = ref.v0;
+    pp.row0 = cy0;
+    pp.rows = cy1 - cy0;
+    CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
+    c->stats.prepare_launches++;
+    out.refs[out.n_refs++] = { 0, ref };
+  } else if (kind == PK_PLANE8) {
+    /* luma plane: byte == pixel */
+    {
       RectRef ref = {};
-      ref.v0 = (4 * (cx0 / 2)) / 16;
-      ref.v1 = ceil_div (4 * ceil_div (cx1, 2), 16);
+      ref.v0 = cx0 / 16;
+      ref.v1 = ceil_div (cx1, 16);
       ref.y0 = cy0;
       ref.y1 = cy1;
       ref.pitch = (ref.v1 - ref.v0) * 16;
       ref.ga = 255;
       const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
-      uint8_t *a, *col;
+      uint8_t *a, *y;
       int rc;
-      if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &col)))
+      if ((rc = dev_alloc (c, &out, bytes, &a)) || (rc = dev_alloc (c, &out, bytes, &y)))
         return rc;
       ref.a = a;
-      ref.c = col;
-      pp.mode = format == FLUC_TTMLBLEND_FORMAT_YUY2 ? PM_YUY2 : format == FLUC_TTMLBLEND_FORMAT_UYVY ? PM_UYVY :
-          format == FLUC_TTMLBLEND_FORMAT_YVYU ? PM_YVYU : PM_VYUY;
-      pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
-      pp.out_pitch = ref.pitch;
-      pp.v0 = ref.v0;
-      pp.row0 = cy0;
-      pp.rows = cy1 - cy0;
-      CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
-      c->stats.prepare_launches++;
-      P->h_rects[0].push_back (ref);
-    } else if (kind == PK_PLANE8_RGB || (kind == PK_PLANE8 && format_packed_444_3 (format))) {
-      /* v308 / IYU2 / RGB / BGR: one plane, three bytes per pixel, every byte its own alpha +
-       * colour; the RGB pair keeps the source colours and the rectangle's flags for the blend */
-      RectRef ref = {};
-      ref.v0 = (3 * cx0) / 16;
-      ref.v1 = ceil_div (3 * cx1, 16);
-      ref.y0 = cy0;
-      ref.y1 = cy1;
-      ref.pitch = (ref.v1 - ref.v0) * 16;
-      ref.ga = 255;
-      const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
-      uint8_t *a, *col;
-      int rc;
-      if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &col)))
-        return rc;
-      ref.a = a;
-      ref.c = col;
-      if (kind == PK_PLANE8_RGB) {
-        ref.ga = rr.ga;
-        ref.src_premul = rr.premul ? 1 : 0;
-      }
-      pp.mode = format == FLUC_TTMLBLEND_FORMAT_v308 ? PM_V308 : format == FLUC_TTMLBLEND_FORMAT_IYU2 ? PM_IYU2 :
-          format == FLUC_TTMLBLEND_FORMAT_RGB ? PM_RGB24 : PM_BGR24;
-      pp.out_a = a; pp.out_c = col; pp.out_c2 = nullptr;
+      ref.c = y;
+      pp.mode = PM_LUMA;
+      pp.out_a = a; pp.out_c = y; pp.out_c2 = nullptr;
       pp.out_pitch = ref.pitch;
       pp.v0 = ref.v0;
       pp.row0 = cy0;
       pp.rows = cy1 - cy0;
       CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
       c->stats.prepare_launches++;
-      P->h_rects[0].push_back (ref);
-    } else if (kind == PK_PLANE8) {
-      /* luma plane: byte == pixel */
-      {
+      out.refs[out.n_refs++] = { 0, ref };
+    }
+    /* chroma: the samples sited on the even pixel of each pair / the even line of each
+     * line pair, as far as the format subsamples (parity); with the non-parity 2x2 average
+     * of 4:2:0 every sample with at least one covered pixel */
+    const int sx = pp.sub_x, sy = pp.sub_y;
+    const bool avg = chroma_average && sx == 2 && sy == 2;
+    pp.chroma_average = avg ? 1 : 0;
+    const int bx0 = avg ? cx0 / 2 : ceil_div (cx0, sx), bx1 = ceil_div (cx1, sx);
+    const int by0 = avg ? cy0 / 2 : ceil_div (cy0, sy), by1 = ceil_div (cy1, sy);
+    if (n_planes >= 2 && bx1 > bx0 && by1 > by0) {
+      if (n_planes == 3) {
         RectRef ref = {};
-        ref.v0 = cx0 / 16;
-        ref.v1 = ceil_div (cx1, 16);
-        ref.y0 = cy0;
-        ref.y1 = cy1;
+        ref.v0 = bx0 / 16;
+        ref.v1 = ceil_div (bx1, 16);
+        ref.y0 = by0;
+        ref.y1 = by1;
         ref.pitch = (ref.v1 - ref.v0) * 16;
         ref.ga = 255;
-        const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
-        uint8_t *a, *y;
+        const size_t bytes = (size_t) ref.pitch * (by1 - by0);
+        uint8_t *a, *u, *v;
         int rc;
-        if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &y)))
+        if ((rc = dev_alloc (c, &out, bytes, &a)) || (rc = dev_alloc (c, &out, bytes, &u))
+            || (rc = dev_alloc (c, &out, bytes, &v)))
           return rc;
-        ref.a = a;
-        ref.c = y;
-        pp.mode = PM_LUMA;
-        pp.out_a = a; pp.out_c = y; pp.out_c2 = nullptr;
+        pp.mode = PM_CHROMA_PLANAR;
+        pp.out_a = a; pp.out_c = u; pp.out_c2 = v;
         pp.out_pitch = ref.pitch;
         pp.v0 = ref.v0;
-        pp.row0 = cy0;
-        pp.rows = cy1 - cy0;
+        pp.row0 = by0;
+        pp.rows = by1 - by0;
         CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
         c->stats.prepare_launches++;
-        P->h_rects[0].push_back (ref);
+        const int pu = format == FLUC_TTMLBLEND_FORMAT_YV12 ? 2 : 1;
+        const int pv = 3 - pu;
+        ref.a = a;
+        ref.c = u;
+        out.refs[out.n_refs++] = { pu, ref };
+        ref.c = v;
+        out.refs[out.n_refs++] = { pv, ref };
+      } else {
+        RectRef ref = {};
+        ref.v0 = (2 * bx0) / 16;
+        ref.v1 = ceil_div (2 * bx1, 16);
+        ref.y0 = by0;
+        ref.y1 = by1;
+        ref.pitch = (ref.v1 - ref.v0) * 16;
+        ref.ga = 255;
+        const size_t bytes = (size_t) ref.pitch * (by1 - by0);
+        uint8_t *a, *uv;
+        int rc;
+        if ((rc = dev_alloc (c, &out, bytes, &a)) || (rc = dev_alloc (c, &out, bytes, &uv)))
+          return rc;
+        pp.mode = (format == FLUC_TTMLBLEND_FORMAT_NV21 || format == FLUC_TTMLBLEND_FORMAT_NV61) ?
+            PM_CHROMA_VU : PM_CHROMA_UV;
+        pp.out_a = a; pp.out_c = uv; pp.out_c2 = nullptr;
+        pp.out_pitch = ref.pitch;
+        pp.v0 = ref.v0;
+        pp.row0 = by0;
+        pp.rows = by1 - by0;
+        CU (c, launch_prepare (pp, ref.pitch / 2, c->up_stream));
+        c->stats.prepare_launches++;
+        ref.a = a;
+        ref.c = uv;
+        out.refs[out.n_refs++] = { 1, ref };
       }
-      /* chroma: the samples sited on the even pixel of each pair / the even line of each
-       * line pair, as far as the format subsamples (parity); with the non-parity 2x2 average
-       * of 4:2:0 every sample with at least one covered pixel */
-      const int sx = pp.sub_x, sy = pp.sub_y;
-      const bool avg = P->chroma_average && sx == 2 && sy == 2;
-      pp.chroma_average = avg ? 1 : 0;
-      const int bx0 = avg ? cx0 / 2 : ceil_div (cx0, sx), bx1 = ceil_div (cx1, sx);
-      const int by0 = avg ? cy0 / 2 : ceil_div (cy0, sy), by1 = ceil_div (cy1, sy);
-      if (n_planes >= 2 && bx1 > bx0 && by1 > by0) {
-        if (n_planes == 3) {
-          RectRef ref = {};
-          ref.v0 = bx0 / 16;
-          ref.v1 = ceil_div (bx1, 16);
-          ref.y0 = by0;
-          ref.y1 = by1;
-          ref.pitch = (ref.v1 - ref.v0) * 16;
-          ref.ga = 255;
-          const size_t bytes = (size_t) ref.pitch * (by1 - by0);
-          uint8_t *a, *u, *v;
-          int rc;
-          if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &u))
-              || (rc = dev_alloc (c, P.get (), bytes, &v)))
-            return rc;
-          pp.mode = PM_CHROMA_PLANAR;
-          pp.out_a = a; pp.out_c = u; pp.out_c2 = v;
-          pp.out_pitch = ref.pitch;
-          pp.v0 = ref.v0;
-          pp.row0 = by0;
-          pp.rows = by1 - by0;
-          CU (c, launch_prepare (pp, ref.pitch, c->up_stream));
-          c->stats.prepare_launches++;
-          const int pu = format == FLUC_TTMLBLEND_FORMAT_YV12 ? 2 : 1;
-          const int pv = 3 - pu;
-          ref.a = a;
-          ref.c = u;
-          P->h_rects[pu].push_back (ref);
-          ref.c = v;
-          P->h_rects[pv].push_back (ref);
-        } else {
-          RectRef ref = {};
-          ref.v0 = (2 * bx0) / 16;
-          ref.v1 = ceil_div (2 * bx1, 16);
-          ref.y0 = by0;
-          ref.y1 = by1;
-          ref.pitch = (ref.v1 - ref.v0) * 16;
-          ref.ga = 255;
-          const size_t bytes = (size_t) ref.pitch * (by1 - by0);
-          uint8_t *a, *uv;
-          int rc;
-          if ((rc = dev_alloc (c, P.get (), bytes, &a)) || (rc = dev_alloc (c, P.get (), bytes, &uv)))
-            return rc;
-          pp.mode = (format == FLUC_TTMLBLEND_FORMAT_NV21 || format == FLUC_TTMLBLEND_FORMAT_NV61) ?
-              PM_CHROMA_VU : PM_CHROMA_UV;
-          pp.out_a = a; pp.out_c = uv; pp.out_c2 = nullptr;
-          pp.out_pitch = ref.pitch;
-          pp.v0 = ref.v0;
-          pp.row0 = by0;
-          pp.rows = by1 - by0;
-          CU (c, launch_prepare (pp, ref.pitch / 2, c->up_stream));
-          c->stats.prepare_launches++;
-          ref.a = a;
-          ref.c = uv;
-          P->h_rects[1].push_back (ref);
-        }
-      }
-    } else {
-      RectRef ref = {};
-      ref.v0 = cx0 / 4;
-      ref.v1 = ceil_div (cx1, 4);
-      ref.y0 = cy0;
-      ref.y1 = cy1;
-      ref.pitch = (ref.v1 - ref.v0) * 16;
-      ref.ga = rr.ga;
-      const bool yuv = format == FLUC_TTMLBLEND_FORMAT_AYUV;
-      ref.src_premul = (!yuv && rr.premul) ? 1 : 0;
-      const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
-      uint8_t *w;
-      int rc;
-      if ((rc = dev_alloc (c, P.get (), bytes, &w)))
-        return rc;
-      switch (format) {
-        case FLUC_TTMLBLEND_FORMAT_AYUV: pp.mode = PM_PACKED_AYUV; break;
-        case FLUC_TTMLBLEND_FORMAT_ARGB: pp.mode = PM_PACKED_ARGB; break;
-        case FLUC_TTMLBLEND_FORMAT_ABGR: pp.mode = PM_PACKED_ABGR; break;
-        case FLUC_TTMLBLEND_FORMAT_RGBA: pp.mode = PM_PACKED_RGBA; break;
-        default: pp.mode = PM_PACKED_BGRA; break;
-      }
-      pp.out_a = w; pp.out_c = nullptr; pp.out_c2 = nullptr;
-      pp.out_pitch = ref.pitch;
-      pp.v0 = ref.v0;
-      pp.row0 = cy0;
-      pp.rows = cy1 - cy0;
-      CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
-      c->stats.prepare_launches++;
-      ref.a = w;
-      ref.c = nullptr;
-      P->h_rects[0].push_back (ref);
     }
+  } else {
+    RectRef ref = {};
+    ref.v0 = cx0 / 4;
+    ref.v1 = ceil_div (cx1, 4);
+    ref.y0 = cy0;
+    ref.y1 = cy1;
+    ref.pitch = (ref.v1 - ref.v0) * 16;
+    ref.ga = rr.ga;
+    const bool yuv = format == FLUC_TTMLBLEND_FORMAT_AYUV;
+    ref.src_premul = (!yuv && rr.premul) ? 1 : 0;
+    const size_t bytes = (size_t) ref.pitch * (cy1 - cy0);
+    uint8_t *w;
+    int rc;
+    if ((rc = dev_alloc (c, &out, bytes, &w)))
+      return rc;
+    switch (format) {
+      case FLUC_TTMLBLEND_FORMAT_AYUV: pp.mode = PM_PACKED_AYUV; break;
+      case FLUC_TTMLBLEND_FORMAT_ARGB: pp.mode = PM_PACKED_ARGB; break;
+      case FLUC_TTMLBLEND_FORMAT_ABGR: pp.mode = PM_PACKED_ABGR; break;
+      case FLUC_TTMLBLEND_FORMAT_RGBA: pp.mode = PM_PACKED_RGBA; break;
+      default: pp.mode = PM_PACKED_BGRA; break;
+    }
+    pp.out_a = w; pp.out_c = nullptr; pp.out_c2 = nullptr;
+    pp.out_pitch = ref.pitch;
+    pp.v0 = ref.v0;
+    pp.row0 = cy0;
+    pp.rows = cy1 - cy0;
+    CU (c, launch_prepare (pp, ref.pitch / 4, c->up_stream));
+    c->stats.prepare_launches++;
+    ref.a = w;
+    ref.c = nullptr;
+    out.refs[out.n_refs++] = { 0, ref };
   }
+  return 0;
+}
 
+static int
+prepare_assemble (Ctx *c, Prepared *P)
+{
+  for (int pl = 0; pl < 3; pl++)
+    P->h_rects[pl].clear ();
+  for (const PreparedRect &pr : P->per_rect)
+    for (int k = 0; k < pr.n_refs; k++)
+      P->h_rects[pr.refs[k].plane].push_back (pr.refs[k].ref);
   /* rectangle tables: one contiguous device array, plane after plane */
   {
     size_t total = 0;
@@ -323,10 +351,10 @@ prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Pr
       P->h_rects_all.clear ();
       for (int pl = 0; pl < 3; pl++)
         P->h_rects_all.insert (P->h_rects_all.end (), P->h_rects[pl].begin (), P->h_rects[pl].end ());
-      uint8_t *d;
       int rc;
-      if ((rc = dev_alloc (c, P.get (), total * sizeof (RectRef), &d)))
+      if ((rc = dev_block (c, total * sizeof (RectRef), &P->table_block)))
         return rc;
+      uint8_t *d = static_cast<uint8_t *> (P->table_block->ptr);
       /* h_rects_all lives as long as the Prepared: safe source for the async copy */
       CU (c, cudaMemcpyAsync (d, P->h_rects_all.data (), total * sizeof (RectRef),
               cudaMemcpyHostToDevice, c->up_stream));
@@ -340,6 +368,28 @@ prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Pr
   CU (c, cudaEventRecord (P->ready, c->up_stream));
   return 0;
 }
+
+static int
+prepare_build (Ctx *c, Overlay *ov, int format, int W, int H, std::unique_ptr<Prepared> &P)
+{
+  P->format = format;
+  P->W = W;
+  P->H = H;
+  P->chroma_average = c->chroma_average;
+  for (const FlucTtmlBlendRect &d : ov->declared) {
+    const int w = std::min (d.x + d.w, W) - d.x, h = std::min (d.y + d.h, H) - d.y;
+    if (w > 0 && h > 0)
+      P->overlay_px += (uint64_t) w * (uint64_t) h;
+  }
+  P->per_rect.resize (ov->rects.size ());
+  for (size_t i = 0; i < ov->rects.size (); i++) {
+    const int rc = prepare_rect (c, ov->rects[i], format, W, H, P->chroma_average, P->per_rect[i]);
+    if (rc)
+      return rc;
+  }
+  return prepare_assemble (c, P.get ());
+}
+
 
 /* ---------------------------------------------------------------------- */
 /* plane jobs                                                             */
@@ -424,6 +474,15 @@ crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, std::ve
     out.push_back ({ r.x0, r.y0, r.x1 - r.x0, r.y1 - r.y0 });
 }
 
+static std::shared_ptr<DevBlock>
+make_block (Ctx *c, void *ptr)
+{
+  std::shared_ptr<DevBlock> b (new DevBlock ());
+  b->ctx = c;
+  b->ptr = ptr;
+  return b;
+}
+
 /* A rectangle whose pixels already sit in device memory, on its way into an overlay. */
 struct Up {
   RawRect rr;
@@ -488,6 +547,63 @@ scan_rows (Ctx *c, std::unique_lock<std::mutex> &lk, Up &u)
   return 0;
 }
 
+/* One uploaded rectangle becomes a box of the overlay: cropped to its non-transparent row runs
+ * (or kept whole without auto-crop), with the sparsity figures of what remains. */
+static void
+append_box (Ctx *c, Overlay *ov, Up &u, size_t n_boxes)
+{
+  OverlayBox box;
+  box.declared = { u.rr.x, u.rr.y, u.rr.w, u.rr.h };
+  box.first_rect = (uint32_t) ov->rects.size ();
+  if (!c->autocrop) {
+    ov->rects.push_back (u.rr);
+  } else {
+    std::vector<FlucTtmlBlendRect> subs;
+    /* at most 8 runs per rectangle, and never more sub-rectangles than the 64-bit band masks hold */
+    crop_runs (u.spans, 16, std::max<size_t> (1, std::min<size_t> (8, FLUC_TTMLBLEND_MAX_RECTANGLES / std::max<size_t> (1, n_boxes))), subs);
+    for (const FlucTtmlBlendRect &s : subs) {
+      /* how sparse is what remains after the crop: 16-pixel groups with some alpha against
+       * all groups of the kept sub-rectangles */
+      box.groups_all += (uint64_t) ceil_div (s.w, 16) * (uint64_t) s.h;
+      for (int y = s.y; y < s.y + s.h; y++) {
+        box.groups_on += (uint64_t) (u.groups[y] & 0xffff);
+        if (u.rr.ga == 255)
+          box.groups_opaque += (uint64_t) (u.groups[y] >> 16);
+      }
+      RawRect q = u.rr;
+      q.dev = u.rr.dev + (size_t) s.y * u.rr.pitch + (size_t) s.x * 4;
+      q.x = u.rr.x + s.x;
+      q.y = u.rr.y + s.y;
+      q.w = s.w;
+      q.h = s.h;
+      ov->rects.push_back (q);
+    }
+  }
+  box.n_rects = (uint32_t) ov->rects.size () - box.first_rect;
+  ov->boxes.push_back (box);
+}
+
+/* Text without a background box leaves most 16-byte vectors under the cue untouched, and
+ * under an opaque box (alpha 255) the result does not depend on the frame at all. In place
+ * (dst == src, host frames over PCIe) it then pays to look at the overlay before touching
+ * the frame: transparent vectors are skipped, opaque ones are written without being read.
+ * Under a translucent box it costs latency for nothing (tools/lazy_probe.py).
+ * FLUC_TTMLBLEND_LAZY=0/1 forces it. */
+static void
+decide_lazy (Overlay *ov)
+{
+  static const char *lazy_env = getenv ("FLUC_TTMLBLEND_LAZY");
+  uint64_t groups_all = 0, groups_on = 0, groups_opaque = 0;
+  for (const OverlayBox &b : ov->boxes) {
+    groups_all += b.groups_all;
+    groups_on += b.groups_on;
+    groups_opaque += b.groups_opaque;
+  }
+  ov->transparent_fraction = groups_all ? 1.0 - (double) groups_on / (double) groups_all : 0.0;
+  ov->opaque_fraction = groups_all ? (double) groups_opaque / (double) groups_all : 0.0;
+  ov->lazy_inplace = lazy_env ? atoi (lazy_env) != 0 : ov->transparent_fraction + ov->opaque_fraction >= 0.3;
+}
+
 /* Waits for uploads and scans, crops every rectangle to its non-transparent row runs and
  * swaps the stream's overlay. */
 static int
@@ -503,45 +619,11 @@ finish_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, std::
     return c->sticky;
   c->stats.h2d_bytes += st.h2d_bytes;
   c->stats.prepare_launches += st.launches;
-  uint64_t groups_all = 0, groups_on = 0, groups_opaque = 0;
-  for (Up &u : ups) {
-    if (!c->autocrop) {
-      ov->rects.push_back (u.rr);
-      continue;
-    }
-    std::vector<FlucTtmlBlendRect> subs;
-    /* at most 8 runs per rectangle, and never more sub-rectangles than the 64-bit band masks hold */
-    crop_runs (u.spans, 16, std::max<size_t> (1, std::min<size_t> (8, FLUC_TTMLBLEND_MAX_RECTANGLES / ups.size ())), subs);
-    for (const FlucTtmlBlendRect &s : subs) {
-      /* how sparse is what remains after the crop: 16-pixel groups with some alpha against
-       * all groups of the kept sub-rectangles */
-      groups_all += (uint64_t) ceil_div (s.w, 16) * (uint64_t) s.h;
-      for (int y = s.y; y < s.y + s.h; y++) {
-        groups_on += (uint64_t) (u.groups[y] & 0xffff);
-        if (u.rr.ga == 255)
-          groups_opaque += (uint64_t) (u.groups[y] >> 16);
-      }
-      RawRect q = u.rr;
-      q.dev = u.rr.dev + (size_t) s.y * u.rr.pitch + (size_t) s.x * 4;
-      q.x = u.rr.x + s.x;
-      q.y = u.rr.y + s.y;
-      q.w = s.w;
-      q.h = s.h;
-      ov->rects.push_back (q);
-    }
-  }
+  for (Up &u : ups)
+    append_box (c, ov.get (), u, ups.size ());
   if (ov->rects.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
     return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
-  /* Text without a background box leaves most 16-byte vectors under the cue untouched, and
-   * under an opaque box (alpha 255) the result does not depend on the frame at all. In place
-   * (dst == src, host frames over PCIe) it then pays to look at the overlay before touching
-   * the frame: transparent vectors are skipped, opaque ones are written without being read.
-   * Under a translucent box it costs latency for nothing (tools/lazy_probe.py).
-   * FLUC_TTMLBLEND_LAZY=0/1 forces it. */
-  static const char *lazy_env = getenv ("FLUC_TTMLBLEND_LAZY");
-  ov->transparent_fraction = groups_all ? 1.0 - (double) groups_on / (double) groups_all : 0.0;
-  ov->opaque_fraction = groups_all ? (double) groups_opaque / (double) groups_all : 0.0;
-  ov->lazy_inplace = lazy_env ? atoi (lazy_env) != 0 : ov->transparent_fraction + ov->opaque_fraction >= 0.3;
+  decide_lazy (ov.get ());
   /* The stream's frames will very likely keep the format and size they had: prepare the new
    * cue for them now, on the upload stream, so that the first frame after a cue change only
    * has an event to wait for instead of the prepare launches in front of it. */
@@ -596,7 +678,7 @@ scale_row_plan (int src_h, int dst_h)
 
 int
 overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, const FlucTtmlBlendRectangle *rects,
-    uint32_t n)
+    uint32_t n, int image_w, int image_h)
 {
   NvtxRange nvtx ("ttmlblend.overlay_set");
   for (uint32_t i = 0; i < n; i++) {
@@ -610,6 +692,11 @@ overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, cons
   }
   std::shared_ptr<Overlay> ov (new Overlay ());
   ov->ctx = c;
+  /* image_w > 0: the rectangles are the (disjoint) region boxes of one image of that size at
+   * the frame's origin -- the ttmlrender form, which overlay_update can patch later */
+  ov->image_w = image_w;
+  ov->image_h = image_h;
+  ov->updatable = image_w > 0 && image_h > 0;
   std::vector<Up> ups;
   std::vector<std::vector<int4>> plans;     /* host side of async uploads: alive until finish_install */
   InstallStats st;
@@ -641,7 +728,7 @@ overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, cons
       rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
       void *d = nullptr;
       CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rr.h, c->mem_pool, c->up_stream));
-      ov->raw_allocs.push_back (d);
+      rr.block = make_block (c, d);
       rr.dev = static_cast<uint8_t *> (d);
       /* cudaMemcpyDefault: the pixels may just as well be in device memory already (UVA tells) */
       CUU (c, lk, cudaMemcpy2DAsync (rr.dev, rr.pitch, r.pixels + (size_t) yoff * r.stride + (size_t) xoff * 4,
@@ -664,7 +751,7 @@ overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, cons
               c->up_stream));
       rr.pitch = (int) align_up ((size_t) rw * 4, 256);
       CUU (c, lk, cudaMallocFromPoolAsync (&d, (size_t) rr.pitch * rh, c->mem_pool, c->up_stream));
-      ov->raw_allocs.push_back (d);
+      rr.block = make_block (c, d);
       const int x_inc = rw == 1 ? 0 : ((r.width - 1) << 16) / (rw - 1) - 1;
       CUU (c, lk, launch_scale (static_cast<const uint8_t *> (s), sp, static_cast<const int4 *> (p), x_inc,
               static_cast<uint8_t *> (d), rr.pitch, rw, rh, c->up_stream));
@@ -679,6 +766,144 @@ overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, cons
     ups.push_back (std::move (u));
   }
   return finish_install (c, lk, stream, ov, ups, st);
+}
+
+/* overlay_update: the stream's cue changed inside `changed` only (a <set> animation step, a
+ * roll-up line: the producer re-renders its whole image for every timeline event,
+ * /root/reference/plugins/ttml/gstttmlrender.c:1442-1452, /root/reference/plugins/ttml/gstttmlevent.c:208-233).
+ * Boxes of the current overlay that the changed rectangles do not touch keep their device
+ * pixels, their crop and their prepared planes -- the new overlay shares those blocks with the
+ * old one -- and only the touched boxes are uploaded, scanned and prepared again. Returns
+ * FLUC_TTMLBLEND_ERROR_NOT_FOUND when there is nothing to patch (no overlay from overlay_set of
+ * the same image size, or a change outside every box): the caller installs the image whole. */
+int
+overlay_update_image (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, const uint8_t *bgra, int w, int h,
+    int stride, const FlucTtmlBlendRect *changed, uint32_t n_changed)
+{
+  NvtxRange nvtx ("ttmlblend.overlay_update");
+  auto it = c->overlays.find (stream);
+  if (it == c->overlays.end () || !it->second->updatable || it->second->image_w != w || it->second->image_h != h)
+    return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
+  std::shared_ptr<Overlay> old = it->second;
+  std::vector<bool> touched (old->boxes.size (), false);
+  size_t n_touched = 0;
+  for (uint32_t k = 0; k < n_changed; k++) {
+    const int x0 = std::max (changed[k].x, 0), y0 = std::max (changed[k].y, 0);
+    const int x1 = std::min (changed[k].x + changed[k].w, w), y1 = std::min (changed[k].y + changed[k].h, h);
+    if (x1 <= x0 || y1 <= y0)
+      continue;
+    /* the boxes are disjoint: the change lies inside them iff the intersections add up to it */
+    uint64_t covered = 0;
+    for (size_t b = 0; b < old->boxes.size (); b++) {
+      const FlucTtmlBlendRect &d = old->boxes[b].declared;
+      const int ix0 = std::max (x0, d.x), iy0 = std::max (y0, d.y);
+      const int ix1 = std::min (x1, d.x + d.w), iy1 = std::min (y1, d.y + d.h);
+      if (ix1 > ix0 && iy1 > iy0) {
+        covered += (uint64_t) (ix1 - ix0) * (uint64_t) (iy1 - iy0);
+        if (!touched[b]) {
+          touched[b] = true;
+          n_touched++;
+        }
+      }
+    }
+    if (covered != (uint64_t) (x1 - x0) * (uint64_t) (y1 - y0))
+      return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
+  }
+  if (n_touched == 0)
+    return 0;                   /* nothing changed */
+
+  /* upload + scan of the touched boxes, context unlocked (as in overlay_install) */
+  std::vector<Up> ups (old->boxes.size ());
+  InstallStats st;
+  lk.unlock ();
+  for (size_t b = 0; b < old->boxes.size (); b++) {
+    if (!touched[b])
+      continue;
+    const FlucTtmlBlendRect &d = old->boxes[b].declared;
+    RawRect &rr = ups[b].rr;
+    rr.x = d.x; rr.y = d.y; rr.w = d.w; rr.h = d.h;
+    rr.ga = 255;
+    rr.premul = true;
+    rr.pitch = (int) align_up ((size_t) rr.w * 4, 256);
+    void *dev = nullptr;
+    CUU (c, lk, cudaMallocFromPoolAsync (&dev, (size_t) rr.pitch * rr.h, c->mem_pool, c->up_stream));
+    rr.block = make_block (c, dev);
+    rr.dev = static_cast<uint8_t *> (dev);
+    CUU (c, lk, cudaMemcpy2DAsync (rr.dev, rr.pitch, bgra + (size_t) d.y * stride + (size_t) d.x * 4, stride,
+            (size_t) rr.w * 4, rr.h, cudaMemcpyDefault, c->up_stream));
+    if (!on_device (bgra))
+      st.h2d_bytes += (uint64_t) rr.w * 4 * rr.h;
+    int rc = scan_rows (c, lk, ups[b]);
+    if (rc)
+      return rc;
+  }
+  CUU (c, lk, cudaStreamSynchronize (c->up_stream));
+  if (!lk.owns_lock ())
+    lk.lock ();
+  if (c->sticky)
+    return c->sticky;
+  auto now = c->overlays.find (stream);
+  if (now == c->overlays.end () || now->second != old)
+    return FLUC_TTMLBLEND_ERROR_NOT_FOUND;      /* replaced meanwhile by another thread */
+  c->stats.h2d_bytes += st.h2d_bytes;
+
+  std::shared_ptr<Overlay> nv (new Overlay ());
+  nv->ctx = c;
+  nv->image_w = w;
+  nv->image_h = h;
+  nv->updatable = true;
+  nv->declared = old->declared;
+  std::vector<int> from_old;    /* new rectangle -> the old overlay's rectangle it is, or -1 */
+  for (size_t b = 0; b < old->boxes.size (); b++) {
+    if (touched[b]) {
+      append_box (c, nv.get (), ups[b], old->boxes.size ());
+      from_old.resize (nv->rects.size (), -1);
+    } else {
+      OverlayBox box = old->boxes[b];
+      box.first_rect = (uint32_t) nv->rects.size ();
+      for (uint32_t k = 0; k < old->boxes[b].n_rects; k++) {
+        nv->rects.push_back (old->rects[old->boxes[b].first_rect + k]);
+        from_old.push_back ((int) (old->boxes[b].first_rect + k));
+      }
+      nv->boxes.push_back (box);
+    }
+  }
+  if (nv->rects.size () > FLUC_TTMLBLEND_MAX_RECTANGLES)
+    return FLUC_TTMLBLEND_ERROR_TOO_MANY_RECTANGLES;
+  decide_lazy (nv.get ());
+  /* prepared for the formats / sizes the stream's frames have been using: kept rectangles bring
+   * their prepared planes along, the others are prepared now */
+  for (auto &p : old->prepared) {
+    if (!p->used || p->chroma_average != c->chroma_average || p->per_rect.size () != old->rects.size ())
+      continue;
+    std::unique_ptr<Prepared> P (new Prepared ());
+    P->format = p->format;
+    P->W = p->W;
+    P->H = p->H;
+    P->chroma_average = p->chroma_average;
+    P->overlay_px = p->overlay_px;
+    P->used = true;
+    P->per_rect.resize (nv->rects.size ());
+    int rc = 0;
+    for (size_t i = 0; i < nv->rects.size () && !rc; i++) {
+      if (from_old[i] >= 0)
+        P->per_rect[i] = p->per_rect[(size_t) from_old[i]];
+      else
+        rc = prepare_rect (c, nv->rects[i], P->format, P->W, P->H, P->chroma_average, P->per_rect[i]);
+    }
+    if (!rc)
+      rc = prepare_assemble (c, P.get ());
+    if (rc) {
+      if (P->ready)
+        cudaEventDestroy (P->ready);
+      return rc;
+    }
+    nv->prepared.push_back (std::move (P));
+  }
+  c->overlays[stream] = nv;       /* frames already queued keep the old one */
+  c->stats.overlays_set++;
+  c->stats.overlays_updated++;
+  return 0;
 }
 
 /* Cairo's colour conversion: double components -> premultiplied 16-bit shorts
@@ -725,7 +950,7 @@ overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stre
   const int pitch = (int) align_up ((size_t) W * 4, 256);
   void *canvas = nullptr;
   CUU (c, lk, cudaMallocFromPoolAsync (&canvas, (size_t) pitch * H, c->mem_pool, c->up_stream));
-  ov->raw_allocs.push_back (canvas);
+  std::shared_ptr<DevBlock> canvas_block = make_block (c, canvas);
   CUU (c, lk, cudaMemsetAsync (canvas, 0, (size_t) pitch * H, c->up_stream));   /* CAIRO_OPERATOR_CLEAR */
   std::vector<void *> layers;
   std::vector<FlucTtmlBlendRect> boxes;
@@ -765,6 +990,7 @@ overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stre
   std::vector<Up> ups;
   for (const FlucTtmlBlendRect &b : disjoint_cover (boxes)) {
     Up u;
+    u.rr.block = canvas_block;
     u.rr.dev = static_cast<uint8_t *> (canvas) + (size_t) b.y * pitch + (size_t) b.x * 4;
     u.rr.pitch = pitch;
     u.rr.w = b.w; u.rr.h = b.h; u.rr.x = b.x; u.rr.y = b.y;

@@ -189,8 +189,18 @@ inline size_t align_up (size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Ctx;
 
+/* One stream-ordered device allocation of the overlay cache, shared by whoever points into it:
+ * a cue update keeps the untouched regions' pixels and prepared planes and both the old and the
+ * new overlay hold them. Freed (deferred, after a fence on every stream) with its last holder. */
+struct DevBlock {
+  Ctx *ctx = nullptr;
+  void *ptr = nullptr;
+  ~DevBlock ();
+};
+
 /* device copy of one rectangle's BGRA pixels (left/top clipped at 0) */
 struct RawRect {
+  std::shared_ptr<DevBlock> block;     /* the allocation `dev` points into */
   uint8_t *dev = nullptr;
   int pitch = 0, w = 0, h = 0;
   int x = 0, y = 0;
@@ -224,11 +234,19 @@ struct Layout {
   uint64_t window_bytes = 0;           /* bytes of all windows (what a zero-copy host frame moves each way) */
 };
 
+/* what one rectangle of the overlay looks like from the planes of one destination format */
+struct PreparedRect {
+  std::vector<std::shared_ptr<DevBlock>> blocks;      /* alpha / colour planes or pixel words */
+  struct { int plane; RectRef ref; } refs[3];
+  int n_refs = 0;
+};
+
 /* everything frame-independent, for one (format, W, H) */
 struct Prepared {
   int format = -1, W = 0, H = 0;
   bool chroma_average = false;         /* prepared with the non-parity 2x2 chroma mean */
-  std::vector<void *> allocs;
+  std::vector<PreparedRect> per_rect;  /* one per Overlay::rects entry, same order */
+  std::shared_ptr<DevBlock> table_block;              /* the RectRef tables */
   std::vector<RectRef> h_rects[3];     /* per plane, host copy */
   std::vector<RectRef> h_rects_all;
   RectRef *d_rects[3] = { nullptr, nullptr, nullptr };
@@ -241,11 +259,23 @@ struct Prepared {
   std::vector<std::unique_ptr<Layout>> layouts;
 };
 
+/* One rectangle as it was handed in (a region box of ttmlrender's image): the unit a cue update
+ * keeps or replaces. */
+struct OverlayBox {
+  FlucTtmlBlendRect declared = { 0, 0, 0, 0 };       /* frame coordinates, clipped at the left / top */
+  uint32_t first_rect = 0, n_rects = 0;              /* its cropped sub-rectangles in Overlay::rects */
+  uint64_t groups_all = 0, groups_on = 0, groups_opaque = 0;   /* 16-pixel groups under them: all / some alpha / opaque */
+};
+
 struct Overlay {
   Ctx *ctx = nullptr;
   std::vector<RawRect> rects;          /* what gets prepared: cropped to non-transparent pixels */
-  std::vector<void *> raw_allocs;      /* device copies the rects point into */
+  std::vector<OverlayBox> boxes;
   std::vector<FlucTtmlBlendRect> declared;   /* rectangles as handed in (algorithmic bytes) */
+  /* ttmlrender form (overlay_set): one w x h image at the frame's origin, premultiplied, global
+   * alpha 1 -- what overlay_update can patch */
+  int image_w = 0, image_h = 0;
+  bool updatable = false;
   std::vector<std::unique_ptr<Prepared>> prepared;
   double transparent_fraction = 0.0;   /* of the 16-pixel groups under the kept rectangles */
   double opaque_fraction = 0.0;        /* alpha 255 all over (and global alpha 1) */
@@ -611,7 +641,9 @@ void crop_runs (const std::vector<int2> &spans, int min_gap, size_t max_runs, st
 /* both are entered with the context lock held (lk), drop it while they upload, and return with
  * it held again whenever they got as far as dropping it */
 int overlay_install (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, const FlucTtmlBlendRectangle *rects,
-    uint32_t n);
+    uint32_t n, int image_w = 0, int image_h = 0);
+int overlay_update_image (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, const uint8_t *bgra, int w, int h,
+    int stride, const FlucTtmlBlendRect *changed, uint32_t n_changed);
 int overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, int W, int H,
     const FlucTtmlBlendRegion *regions, uint32_t n);
 

@@ -69,7 +69,7 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("kernel_ms", C.c_double),
                 ("kernel_ms_launches", C.c_uint64), ("cache_bytes", C.c_uint64),
                 ("multi_launches", C.c_uint64), ("lazy_launches", C.c_uint64),
-                ("dependent_launches", C.c_uint64)]
+                ("overlays_updated", C.c_uint64), ("dependent_launches", C.c_uint64)]
 
 
 # name -> (restype, argtypes); also the list tests check against the header
@@ -90,6 +90,8 @@ PROTOTYPES = {
     "fluc_ttmlblend_multi_stats_copy": (None, [C.c_void_p, C.POINTER(Stats)]),
     "fluc_ttmlblend_overlay_set": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32,
                                              C.c_int32, C.c_int32, C.POINTER(Rect), C.c_uint32]),
+    "fluc_ttmlblend_overlay_update": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32,
+                                                C.c_int32, C.c_int32, C.POINTER(Rect), C.c_uint32]),
     "fluc_ttmlblend_overlay_set_rectangles": (C.c_int, [C.c_void_p, C.c_uint32,
                                                         C.POINTER(Rectangle), C.c_uint32]),
     "fluc_ttmlblend_overlay_set_regions": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32,
@@ -301,6 +303,16 @@ class TtmlBlend:
         self._check(self.lib.fluc_ttmlblend_overlay_set(
             self.h, stream, bgra.ctypes.data, bgra.shape[1], bgra.shape[0], bgra.strides[0],
             arr if rl else None, len(rl)), "overlay_set")
+
+    def overlay_update(self, stream: int, bgra: np.ndarray, changed: Iterable[Sequence[int]]):
+        """The next state of the stream's cue: the new H x W x 4 image and the boxes (x, y, w, h)
+        outside which it equals the previous one. Untouched regions keep their prepared planes."""
+        assert bgra.dtype == np.uint8 and bgra.ndim == 3 and bgra.shape[2] == 4 and bgra.strides[2] == 1
+        rl = list(changed)
+        arr = (Rect * max(1, len(rl)))(*[Rect(*map(int, r)) for r in rl])
+        self._check(self.lib.fluc_ttmlblend_overlay_update(
+            self.h, stream, bgra.ctypes.data, bgra.shape[1], bgra.shape[0], bgra.strides[0],
+            arr if rl else None, len(rl)), "overlay_update")
 
     def overlay_set_rectangles(self, stream: int, rectangles: Sequence[dict]):
         """GstVideoOverlayComposition form. Each dict: pixels (h x w x 4 uint8 BGRA), x, y,

@@ -156,6 +156,7 @@ typedef struct {
   uint64_t lazy_launches;       /* launches in place that read the overlay first: vectors it leaves
                                  * untouched are skipped, vectors it covers opaquely are written
                                  * without being read (sparse cues, opaque boxes; exact either way) */
+  uint64_t overlays_updated;    /* of overlays_set: cue changes that kept the untouched regions (overlay_update) */
   uint64_t dependent_launches;  /* batches that had to wait for everything launched before them: they
                                  * write what an earlier batch that may still run reads or writes, or
                                  * read what it writes (all others may overlap their predecessor's tail:
@@ -198,6 +199,21 @@ FLUC_EXPORT int fluc_ttmlblend_multi_sync (FlucTtmlBlendMulti *thiz);     /* flu
 FLUC_EXPORT int fluc_ttmlblend_overlay_set (FlucTtmlBlend *thiz, uint32_t stream,
     const uint8_t *bgra_premul, int32_t w, int32_t h, int32_t stride,
     const FlucTtmlBlendRect *rects, uint32_t n_rects);
+/* The next state of the same cue: ttmlrender re-renders its whole image for every timeline
+ * event, including <set> animation steps and roll-up lines
+ * (/root/reference/plugins/ttml/gstttmlrender.c:1442-1452,
+ * /root/reference/plugins/ttml/gstttmlevent.c:208-233, /root/reference/plugins/ttml/gstttmlstyle.c:286-312),
+ * while only some regions differ from the image before. `bgra_premul` is the new w*h image,
+ * `changed_rects` cover every pixel that differs from the image the stream's overlay was built
+ * from (by overlay_set or a previous overlay_update, same w and h). Region boxes the changed
+ * rectangles do not touch keep their device pixels, their crop and their prepared planes; only
+ * the touched boxes are uploaded and prepared again. The result is the same as overlay_set with
+ * the new image and the old region boxes, swapped in as atomically. Falls back to installing the
+ * whole image (overlay_set without boxes) when the stream has no such overlay or a change lies
+ * outside every region box. n_changed == 0: nothing changed, nothing is done. */
+FLUC_EXPORT int fluc_ttmlblend_overlay_update (FlucTtmlBlend *thiz, uint32_t stream,
+    const uint8_t *bgra_premul, int32_t w, int32_t h, int32_t stride,
+    const FlucTtmlBlendRect *changed_rects, uint32_t n_changed);
 /* GstVideoOverlayComposition form: independent rectangles, blended in order. */
 FLUC_EXPORT int fluc_ttmlblend_overlay_set_rectangles (FlucTtmlBlend *thiz,
     uint32_t stream, const FlucTtmlBlendRectangle *rects, uint32_t n_rects);
