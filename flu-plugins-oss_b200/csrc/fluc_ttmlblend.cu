@@ -738,12 +738,14 @@ auto_reg_limit (const Ctx *c)
  * registration pins the physical pages, and a later allocation at the same address would be
  * taken for the registered one while the GPU still reaches the old pages. */
 static void
-auto_register_frame (Ctx *c, uint32_t stream, int fmt, int H, const FlucTtmlBlendFrame *hf)
+auto_register_frame (Ctx *c, uint32_t stream, int fmt, int W, int H, const FlucTtmlBlendFrame *hf)
 {
-  /* plane by plane: the planes of a frame need not be neighbours in memory */
-  for (int pl = 0; pl < format_planes (fmt); pl++) {
-    const uintptr_t lo = (uintptr_t) hf->plane[pl];
-    const uintptr_t hi = lo + (uintptr_t) hf->stride[pl] * plane_rows (fmt, pl, H);
+  /* range by range: planes that are neighbours in memory (GStreamer's default layout: one
+   * memory per frame) are pinned as one range -- two registrations may not share a page --
+   * while planes in allocations of their own get one each */
+  const FrameExtent x (fmt, W, H, hf);
+  for (int r = 0; r < x.n; r++) {
+    const uintptr_t lo = x.lo[r], hi = x.hi[r];
     auto it = c->auto_regs.upper_bound (lo);
     if (it != c->auto_regs.begin ()) {
       --it;
@@ -861,7 +863,7 @@ blend_host_locked (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, in
    * kernel can reach it over PCIe itself. */
   const int n_planes = format_planes (fmt);
   if (c->auto_register && c->host_mode != HM_STAGED)
-    auto_register_frame (c, stream, fmt, H, hf);
+    auto_register_frame (c, stream, fmt, W, H, hf);
   FlucTtmlBlendFrame zf = {};
   bool mapped = c->host_mode != HM_STAGED;
   for (int pl = 0; pl < n_planes && mapped; pl++) {
@@ -1023,6 +1025,7 @@ blend_host_locked (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t stream, in
   l.keep = ov;
   c->lane_tickets[tk] = lane_idx;
   c->stats.frames_blended++;
+  c->stats.staged_frames++;
   c->stats.algorithmic_bytes += algo;
   return 0;
 }
@@ -1392,6 +1395,7 @@ fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *o
     sum.lazy_launches += s.lazy_launches;
     sum.dependent_launches += s.dependent_launches;
     sum.overlays_updated += s.overlays_updated;
+    sum.staged_frames += s.staged_frames;
   }
   *out = sum;
 }

@@ -369,6 +369,7 @@ stage_frame (Ctx *c, std::unique_lock<std::mutex> &lk, uint64_t tk, uint32_t str
   }
   job->state = StageJob::COPY_IN;
   c->stage_active++;
+  c->stats.staged_frames++;
   /* finished jobs nobody waited for do not pile up */
   if (c->stage_jobs.size () > 4096)
     for (auto it = c->stage_jobs.begin (); it != c->stage_jobs.end () && c->stage_jobs.size () > 2048;)

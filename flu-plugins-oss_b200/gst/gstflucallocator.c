@@ -2,8 +2,9 @@
  * gstflucallocator.c -- GstAllocator handing out the context's pinned staging
  * frames (fluc_ttmlblend_frame_pool_acquire (..., on_host = 1, ...)).
  *
- * NOT BUILT IN THE GRAFT IMAGE (no GLib / GStreamer there); part of the
- * `-Dttml_cuda=enabled` build next to gstttmlblend.c.
+ * Part of the `-Dttml_cuda=enabled` build next to gstttmlblend.c. The graft
+ * image has no GLib / GStreamer: there it is compiled and RUN against the functional fake in
+ * tests/gst_stub/ (tests/test_gpu_gstglue.py).
  *
  * Why: fluc_ttmlblend_blend_host () blends device-accessible host memory
  * zero-copy -- the kernel reads the rows under the cue over PCIe and writes
@@ -20,10 +21,7 @@
 #include "config.h"
 #endif
 
-#include <gst/gst.h>
-#include <gst/video/video.h>
-
-#include "fluc_ttmlblend.h"
+#include "gstflucallocator.h"
 
 #define GST_TYPE_FLUC_ALLOCATOR (gst_fluc_allocator_get_type ())
 G_DECLARE_FINAL_TYPE (GstFlucAllocator, gst_fluc_allocator, GST, FLUC_ALLOCATOR, GstAllocator)
@@ -129,6 +127,33 @@ gst_fluc_allocator_fill_video_meta (GstAllocator * allocator, GstMemory * memory
     offset[p] = (guint8 *) mem->frame.plane[p] - (guint8 *) mem->frame.plane[0];
     stride[p] = mem->frame.stride[p];
   }
+}
+
+gboolean
+gst_is_fluc_memory (GstMemory * memory)
+{
+  return memory->allocator != NULL && memory->allocator->mem_type != NULL &&
+      strcmp (memory->allocator->mem_type, "FlucPinnedFrame") == 0;
+}
+
+GstBuffer *
+gst_fluc_allocator_alloc_video_buffer (GstAllocator * allocator)
+{
+  GstFlucAllocator *self = GST_FLUC_ALLOCATOR (allocator);
+  gsize offset[GST_VIDEO_MAX_PLANES] = { 0, };
+  gint stride[GST_VIDEO_MAX_PLANES] = { 0, };
+  GstMemory *mem = gst_allocator_alloc (allocator, 0, NULL);
+  GstBuffer *buf;
+
+  if (!mem)
+    return NULL;
+  buf = gst_buffer_new ();
+  gst_buffer_append_memory (buf, mem);
+  gst_fluc_allocator_fill_video_meta (allocator, mem, offset, stride);
+  gst_buffer_add_video_meta_full (buf, GST_VIDEO_FRAME_FLAG_NONE, GST_VIDEO_INFO_FORMAT (&self->info),
+      GST_VIDEO_INFO_WIDTH (&self->info), GST_VIDEO_INFO_HEIGHT (&self->info),
+      fluc_ttmlblend_format_planes (self->format), offset, stride);
+  return buf;
 }
 
 GstAllocator *

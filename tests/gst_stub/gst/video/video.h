@@ -1,4 +1,4 @@
-/* stub: see ../../README.md */
+/* functional fake: see ../../README.md */
 #ifndef GST_STUB_VIDEO_H
 #define GST_STUB_VIDEO_H
 #include <gst/gst.h>
@@ -25,7 +25,8 @@ typedef struct _GstVideoInfo { GstVideoFormat format; GstVideoFlags flags; gint 
 #define GST_VIDEO_INFO_COMP_POFFSET(i, c) ((i)->a_poffset + 0 * (c))
 gboolean gst_video_info_from_caps (GstVideoInfo *, const GstCaps *);
 gboolean gst_video_info_set_format (GstVideoInfo *, GstVideoFormat, guint, guint);
-typedef struct _GstVideoFrame { GstVideoInfo info; gpointer data[GST_VIDEO_MAX_PLANES]; } GstVideoFrame;
+typedef struct _GstVideoFrame { GstVideoInfo info; GstVideoFrameFlags flags; GstBuffer *buffer; gpointer meta; gint id;
+  gpointer data[GST_VIDEO_MAX_PLANES]; GstMapInfo map[GST_VIDEO_MAX_PLANES]; } GstVideoFrame;
 gboolean gst_video_frame_map (GstVideoFrame *, const GstVideoInfo *, GstBuffer *, GstMapFlags);
 void gst_video_frame_unmap (GstVideoFrame *);
 #define GST_VIDEO_FRAME_N_PLANES(f) ((f)->info.n_planes)
@@ -35,5 +36,17 @@ void gst_video_frame_unmap (GstVideoFrame *);
 #define GST_VIDEO_FRAME_WIDTH(f) ((f)->info.width)
 #define GST_VIDEO_FRAME_HEIGHT(f) ((f)->info.height)
 #define GST_VIDEO_CAPS_MAKE(fmts) "video/x-raw, format = (string) " fmts
-gpointer gst_buffer_add_video_meta (GstBuffer *, GstVideoFrameFlags, GstVideoFormat, guint, guint);
+typedef struct _GstVideoMeta { GstBuffer *buffer; GstVideoFrameFlags flags; GstVideoFormat format; gint id; guint width, height;
+  guint n_planes; gsize offset[GST_VIDEO_MAX_PLANES]; gint stride[GST_VIDEO_MAX_PLANES]; } GstVideoMeta;
+struct _GstVideoMetaFake { GstVideoMeta meta; };
+GstVideoMeta *gst_buffer_add_video_meta (GstBuffer *, GstVideoFrameFlags, GstVideoFormat, guint, guint);
+GstVideoMeta *gst_buffer_add_video_meta_full (GstBuffer *, GstVideoFrameFlags, GstVideoFormat, guint, guint, guint n_planes,
+    gsize offset[GST_VIDEO_MAX_PLANES], gint stride[GST_VIDEO_MAX_PLANES]);
+GstVideoMeta *gst_buffer_get_video_meta (GstBuffer *);
+GType gst_video_meta_api_get_type (void);
+#define GST_VIDEO_META_API_TYPE (gst_video_meta_api_get_type ())
+GstVideoFormat gst_video_format_from_string (const gchar *);
+const gchar *gst_video_format_to_string (GstVideoFormat);
+#define GST_VIDEO_INFO_FORMAT(i) ((i)->format)
+#define GST_VIDEO_INFO_SIZE(i) ((i)->size)
 #endif

@@ -156,3 +156,30 @@ def test_gstreamer_glue_is_syntactically_sound(src):
                         "-I", os.path.join(graft.ROOT, "include"), "-I", os.path.join(graft.ROOT, "oracle"),
                         os.path.join(graft.ROOT, src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_gstreamer_glue_builds_against_the_functional_fake():
+    """The element and the allocator are compiled (-Wall -Werror) and linked with the functional
+    fake of the GStreamer API (tests/gst_stub/gstfake.c) and the test harness; the library loads
+    and exports the harness entry points. What it does on a GPU: tests/test_gpu_gstglue.py."""
+    import ctypes
+    stub = os.path.join(graft.ROOT, "tests", "gst_stub")
+    r = subprocess.run(["make", "-s", "-C", stub], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(os.path.join(stub, "libgstglue_test.so"))
+    for sym in ("th_new", "th_start", "th_segment", "th_push_subtitle", "th_subtitle_event", "th_push_video",
+                "th_stats", "th_free"):
+        assert hasattr(lib, sym), sym
+    # no GPU here: the element is created, refuses to start without a CUDA device, and goes away cleanly
+    lib.th_new.restype = ctypes.c_void_p
+    lib.th_new.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.th_start.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    lib.th_free.argtypes = [ctypes.c_void_p]
+    lib.th_errors.argtypes = [ctypes.c_void_p]
+    import flu_plugins_oss_b200 as pkg_
+    if pkg_.load_library().fluc_ttmlblend_device_count() == 0:
+        h = lib.th_new(0, 0)
+        assert h
+        assert lib.th_start(h, b"NV12", 640, 360) == -1          # start () fails: no usable CUDA device
+        assert lib.th_errors(h) == 1                              # and says so through GST_ELEMENT_ERROR
+        lib.th_free(h)
