@@ -423,6 +423,8 @@ def main():
     ap.add_argument("--distinct-cues", action="store_true",
                     help="headline workload = the distinct-cues variant (one stream and cue image per frame): "
                          "for profiling that leg on its own")
+    ap.add_argument("--opaque-boxes", action="store_true",
+                    help="the config's regions with opacity 1.0 (probe: no frame read under opaque vectors)")
     ap.add_argument("--event-pairs", type=int, default=12,
                     help="launches timed one by one with a CUDA-event pair AFTER the timed region "
                          "(cross-check of launch_ms)")
@@ -434,6 +436,9 @@ def main():
     wl = pkg.workloads
     sh = pkg.sharding
     cfg = wl.CONFIGS[args.config]
+    if args.opaque_boxes:
+        cfg = dataclasses.replace(cfg, name=cfg.name + "+opaque_boxes",
+                                  regions=[dataclasses.replace(r, opacity=1.0) for r in cfg.regions])
     dist, device, world, rank, local = dist_setup(args.gpus)
 
     if args.impl == "reference":

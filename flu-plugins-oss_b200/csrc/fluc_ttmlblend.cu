@@ -482,8 +482,8 @@ submit_locked (Ctx *c, uint32_t stream, int fmt, int32_t W, int32_t H, uint32_t 
   const FrameExtent xs (fmt, W, H, src), xd (fmt, W, H, dst);
   if ((rc = order_against_pending (c, xs, xd, inplace)))
     return rc;
-  f.layout = find_layout (c, f.prep, f.overlay && f.overlay->lazy_inplace, fmt, W, H, frame_flags, src, dst,
-      src->plane[0] == dst->plane[0]);
+  f.layout = find_layout (c, f.prep, f.overlay && (inplace ? f.overlay->lazy_inplace : f.overlay->opaque_skip),
+      fmt, W, H, frame_flags, src, dst, inplace);
   for (int pl = 0; pl < 3; pl++) {
     f.src[pl] = static_cast<const uint8_t *> (src->plane[pl]);
     f.dst[pl] = static_cast<uint8_t *> (dst->plane[pl]);
@@ -1396,6 +1396,7 @@ fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *o
     sum.dependent_launches += s.dependent_launches;
     sum.overlays_updated += s.overlays_updated;
     sum.staged_frames += s.staged_frames;
+    sum.opaque_skip_launches += s.opaque_skip_launches;
   }
   *out = sum;
 }

@@ -210,8 +210,11 @@ make_groupable (Layout &L, bool lazy_inplace)
     L.bands.clear ();
     return;
   }
-  if ((gflags & JF_INPLACE) && lazy_inplace)
-    gflags |= JF_LAZY;
+  /* `look`: the overlay is worth looking at before the frame is touched -- in place that skips
+   * transparent vectors and does not read under opaque ones, out of place it does not read
+   * under opaque ones (the caller picks the overlay's figure that goes with the frame) */
+  if (lazy_inplace)
+    gflags |= (gflags & JF_INPLACE) ? JF_LAZY : JF_OPAQUE;
   for (const PlaneJob &j : L.jobs)
     if (j.flags & JF_FAST)
       L.gjobs.push_back (j);

@@ -602,6 +602,10 @@ decide_lazy (Overlay *ov)
   ov->transparent_fraction = groups_all ? 1.0 - (double) groups_on / (double) groups_all : 0.0;
   ov->opaque_fraction = groups_all ? (double) groups_opaque / (double) groups_all : 0.0;
   ov->lazy_inplace = lazy_env ? atoi (lazy_env) != 0 : ov->transparent_fraction + ov->opaque_fraction >= 0.3;
+  /* out of place every vector is written anyway; what can be saved is the read under an opaque
+   * box (FLUC_TTMLBLEND_OPAQUE_SKIP=0/1 forces it) */
+  static const char *skip_env = getenv ("FLUC_TTMLBLEND_OPAQUE_SKIP");
+  ov->opaque_skip = skip_env ? atoi (skip_env) != 0 : ov->opaque_fraction >= 0.3;
 }
 
 /* Waits for uploads and scans, crops every rectangle to its non-transparent row runs and

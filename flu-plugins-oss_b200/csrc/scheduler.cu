@@ -292,6 +292,8 @@ launch_pending (Ctx *c)
       c->stats.group_launches++;
       if (g.P.h.flags & JF_LAZY)
         c->stats.lazy_launches++;
+      if (g.P.h.flags & JF_OPAQUE)
+        c->stats.opaque_skip_launches++;
     }
     for (size_t k = 0; k < n_multis; k++) {
       MultiGroup &m = *c->multis[k];
@@ -301,6 +303,8 @@ launch_pending (Ctx *c)
       c->stats.multi_launches++;
       if (m.P.flags & JF_LAZY)
         c->stats.lazy_launches++;
+      if (m.P.flags & JF_OPAQUE)
+        c->stats.opaque_skip_launches++;
     }
     for (int k = 0; k < kPlaneKinds * 2; k++) {
       if (by_kind[k].empty ())

@@ -280,6 +280,7 @@ struct Overlay {
   double transparent_fraction = 0.0;   /* of the 16-pixel groups under the kept rectangles */
   double opaque_fraction = 0.0;        /* alpha 255 all over (and global alpha 1) */
   bool lazy_inplace = false;           /* in-place group launches look at the overlay first */
+  bool opaque_skip = false;            /* out-of-place group launches do: no frame read under opaque vectors */
   ~Overlay ();
 };
 

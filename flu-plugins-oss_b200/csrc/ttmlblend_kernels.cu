@@ -301,10 +301,49 @@ blend_px_packed (uint32_t f, uint32_t o, uint32_t ga, bool sp, bool dp)
   return out;
 }
 
+/* One pixel of the common case -- global alpha 1, straight destination whose alpha byte is 255 --
+ * without a branch: final_alpha = 255, and asrc == 0 falls out of the arithmetic (the weights
+ * are 0 and 255, x * 255 / 255 is exact; a premultiplied source word with alpha 0 is all zero,
+ * the prepare kernel sees to that). All four bytes at once on two 16-bit lanes per register
+ * (even bytes / odd bytes); every lane stays <= 255 * 255, and
+ * x / 255 == (x + 1 + (x >> 8)) >> 8 for x <= 65534. */
+template <int AP>
+__device__ __forceinline__ uint32_t
+blend_px_packed_opaque (uint32_t f, uint32_t o, bool sp)
+{
+  const uint32_t a = (o >> (8 * AP)) & 0xffu, na = 255u - a;
+  const uint32_t fe = f & 0x00ff00ffu, fo = (f >> 8) & 0x00ff00ffu;
+  uint32_t te, to;
+  if (sp) {
+    te = fe * na;                                     /* Cd * (255 - a) */
+    to = fo * na;
+  } else {
+    te = (o & 0x00ff00ffu) * a + fe * na;             /* Cs * a + Cd * (255 - a) */
+    to = ((o >> 8) & 0x00ff00ffu) * a + fo * na;
+  }
+  te = te + ((te >> 8) & 0x00ff00ffu) + 0x00010001u;
+  to = to + ((to >> 8) & 0x00ff00ffu) + 0x00010001u;
+  const uint32_t out = ((te >> 8) & 0x00ff00ffu) | (to & 0xff00ff00u);
+  /* OVER10: (Cs*255 + Cd*na)/255 = Cs + (Cd*na)/255, then MIN 255 -- a saturating byte add; the
+   * alpha byte comes out as a + (255*na)/255 = 255 by itself. OVER00: alpha byte = 255. */
+  return sp ? __vaddus4 (out, o) : (out | (0xffu << (8 * AP)));
+}
+
 template <int AP>
 __device__ __forceinline__ uint4
 blend16_packed (uint4 f, const uint4 &o, uint32_t ga, bool sp, bool dp)
 {
+  constexpr uint32_t AM = 0xffu << (8 * AP);
+  /* the four pixels of a vector nearly always share their case: decide once per vector */
+  if (ga == 255u && !dp && ((f.x & f.y & f.z & f.w) & AM) == AM) {
+    if (((o.x | o.y | o.z | o.w) & AM) == 0u)
+      return f;                                       /* transparent all over */
+    f.x = blend_px_packed_opaque<AP> (f.x, o.x, sp);
+    f.y = blend_px_packed_opaque<AP> (f.y, o.y, sp);
+    f.z = blend_px_packed_opaque<AP> (f.z, o.z, sp);
+    f.w = blend_px_packed_opaque<AP> (f.w, o.w, sp);
+    return f;
+  }
   f.x = blend_px_packed<AP> (f.x, o.x, ga, sp, dp);
   f.y = blend_px_packed<AP> (f.y, o.y, ga, sp, dp);
   f.z = blend_px_packed<AP> (f.z, o.z, ga, sp, dp);
@@ -425,7 +464,7 @@ all_opaque (const uint4 &oa)
  * overlay first and touches only the vectors it will change: a vector whose
  * alpha is zero everywhere is neither loaded nor stored -- for cues without a
  * background box most of the region never crosses the bus. */
-template <int KIND, bool FAST, bool BULK, bool LAZY = false>
+template <int KIND, bool FAST, bool BULK, int LAZY = 0>
 __device__ __forceinline__ void
 process_chunk (const JobRegs &J, uint32_t local_chunk)
 {
@@ -502,17 +541,20 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
           "OV_DONE:\n"
           "}" :: "r" (bar) : "memory");
       if (LAZY) {
-        /* overlay first: only vectors with some alpha are written back, and of those only the
-         * ones that are not opaque all over are fetched (all fetches in flight together).
-         * Under an opaque vector the result is the overlay colour whatever the frame holds;
-         * a stand-in with an opaque alpha byte keeps the packed kinds on their fast path. */
+        /* overlay first. LAZY 1 (in place): only vectors with some alpha are written back, and
+         * of those only the ones that are not opaque all over are fetched (all fetches in flight
+         * together). LAZY 2 (out of place, a cue with an opaque box): every vector is written,
+         * but the ones under an opaque vector are not fetched. Under an opaque vector the
+         * result is the overlay colour whatever the frame holds; a stand-in with an opaque
+         * alpha byte keeps the packed kinds on their fast path. */
         const bool ga_full = kind_is_planes (KIND) && KIND != PK_PLANE8_RGB ? true :
             __ldg (&r->ga) == 255;
         const uint32_t fill = KIND == PK_PACKED_A0 ? 0x000000ffu : KIND == PK_PACKED_A3 ? 0xff000000u : 0u;
 #pragma unroll
         for (int k = 0; k < kUnroll; k++) {
           const uint4 oa = *reinterpret_cast<const uint4 *> (ov_smem + (threadIdx.x + k * kThreads) * 16u);
-          act[k] = act[k] && any_alpha<KIND> (oa);
+          if (LAZY == 1)
+            act[k] = act[k] && any_alpha<KIND> (oa);
           f[k] = make_uint4 (fill, fill, fill, fill);
           if (act[k] && !(ga_full && all_opaque<KIND> (oa)))
             f[k] = ld_frame16 (src + (size_t) yy[k] * src_pitch + (size_t) vv[k] * 16);
@@ -605,7 +647,7 @@ process_chunk (const JobRegs &J, uint32_t local_chunk)
     for (unsigned long long m = mask; m; m &= m - 1) {
       const RectRef *r = rects + (__ffsll ((long long) m) - 1);
       const RectGeom g = rect_geom (r);
-      if (LAZY) {
+      if (LAZY == 1) {
         const int32_t pitch = __ldg (&r->pitch);
         const uint8_t *pa = ldg_ptr (&r->a);
 #pragma unroll
@@ -709,8 +751,8 @@ ttmlblend_blend_kernel (const PlaneJob *__restrict__ jobs,
  * first frame load without a single dependent global load or barrier in
  * front of it (the table search of the generic kernel above costs ~8 % of a
  * streaming copy: tools/copybench.cu "+prologue"). */
-template <int KIND, bool LAZY, int NF, int NB>
-__global__ void __launch_bounds__ (kThreads, LAZY ? 4 : TTMLBLEND_MIN_CTAS)
+template <int KIND, int LAZY, int NF, int NB>
+__global__ void __launch_bounds__ (kThreads, LAZY == 1 ? 4 : TTMLBLEND_MIN_CTAS)
 ttmlblend_group_kernel (const __grid_constant__ GroupParamsT<NF, NB> P)
 {
   const GroupHeader &Hd = P.h;
@@ -757,8 +799,8 @@ ttmlblend_group_kernel (const __grid_constant__ GroupParamsT<NF, NB> P)
  * uses. A CTA finds its frame by bisecting the frames' first chunks (six uniform
  * constant-bank reads), then its band as above -- still no global load and no barrier before
  * the first frame load. */
-template <int KIND, bool LAZY>
-__global__ void __launch_bounds__ (kThreads, LAZY ? 4 : TTMLBLEND_MIN_CTAS)
+template <int KIND, int LAZY>
+__global__ void __launch_bounds__ (kThreads, LAZY == 1 ? 4 : TTMLBLEND_MIN_CTAS)
 ttmlblend_multi_kernel (const __grid_constant__ MultiParams P)
 {
   pdl_begin (P.flags);
@@ -849,7 +891,7 @@ launch_blend_kind (const PlaneJob *d_jobs, const uint32_t *d_chunk_begin, const 
 
 /* One variant of the group kernel: copies what the launch needs into a parameter block of the
  * variant's size (the full-size block itself when NF / NB are the maxima). */
-template <int KIND, bool LAZY, int NF, int NB>
+template <int KIND, int LAZY, int NF, int NB>
 static cudaError_t
 launch_group_variant (const GroupParams &P, uint32_t grid, size_t smem, cudaStream_t stream)
 {
@@ -864,7 +906,7 @@ launch_group_variant (const GroupParams &P, uint32_t grid, size_t smem, cudaStre
   return launch_ex (ttmlblend_group_kernel<KIND, LAZY, NF, NB>, grid, smem, stream, pdl, S);
 }
 
-template <int KIND, bool LAZY>
+template <int KIND, int LAZY>
 static cudaError_t
 launch_group_sized (const GroupParams &P, uint32_t grid, size_t smem, cudaStream_t stream)
 {
@@ -897,23 +939,20 @@ launch_group (GroupParams &P, int kind, int sync, cudaStream_t stream)
   const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
   /* in place (dst == src, host frames over PCIe) under a sparse cue: the variant that reads
    * the overlay first and skips the vectors it would not change */
-  const bool lazy = (Hd.flags & JF_LAZY) != 0;
+  const int look = (Hd.flags & JF_LAZY) ? 1 : (Hd.flags & JF_OPAQUE) ? 2 : 0;
+#define GROUP_CASE(K, SM) \
+    case K: \
+      return look == 1 ? launch_group_sized<K, 1> (P, grid, SM, stream) : \
+          look == 2 ? launch_group_sized<K, 2> (P, grid, SM, stream) : launch_group_sized<K, 0> (P, grid, SM, stream);
   switch (kind) {
-    case PK_PLANE8:
-      return lazy ? launch_group_sized<PK_PLANE8, true> (P, grid, smem_plane8, stream) :
-          launch_group_sized<PK_PLANE8, false> (P, grid, smem_plane8, stream);
-    case PK_PLANE8_RGB:
-      return lazy ? launch_group_sized<PK_PLANE8_RGB, true> (P, grid, smem_plane8, stream) :
-          launch_group_sized<PK_PLANE8_RGB, false> (P, grid, smem_plane8, stream);
-    case PK_PACKED_A0:
-      return lazy ? launch_group_sized<PK_PACKED_A0, true> (P, grid, smem_packed, stream) :
-          launch_group_sized<PK_PACKED_A0, false> (P, grid, smem_packed, stream);
-    case PK_PACKED_A3:
-      return lazy ? launch_group_sized<PK_PACKED_A3, true> (P, grid, smem_packed, stream) :
-          launch_group_sized<PK_PACKED_A3, false> (P, grid, smem_packed, stream);
+    GROUP_CASE (PK_PLANE8, smem_plane8)
+    GROUP_CASE (PK_PLANE8_RGB, smem_plane8)
+    GROUP_CASE (PK_PACKED_A0, smem_packed)
+    GROUP_CASE (PK_PACKED_A3, smem_packed)
     default:
       return cudaErrorInvalidValue;
   }
+#undef GROUP_CASE
 }
 
 cudaError_t
@@ -933,24 +972,22 @@ launch_multi (MultiParams &P, int kind, int sync, cudaStream_t stream)
     return cudaErrorInvalidValue;
   P.lanes_magic = lanes == 1 ? 0u : (uint32_t) (((1ull << 32) + lanes - 1) / lanes);
   const size_t smem_plane8 = 2 * kItemsPerChunk * 16, smem_packed = kItemsPerChunk * 16;
-  const bool lazy = (P.flags & JF_LAZY) != 0;
+  const int look = (P.flags & JF_LAZY) ? 1 : (P.flags & JF_OPAQUE) ? 2 : 0;
   const bool pdl = (P.flags & JF_PDL) != 0;
+#define MULTI_CASE(K, SM) \
+    case K: \
+      return look == 1 ? launch_ex (ttmlblend_multi_kernel<K, 1>, grid, SM, stream, pdl, P) : \
+          look == 2 ? launch_ex (ttmlblend_multi_kernel<K, 2>, grid, SM, stream, pdl, P) : \
+          launch_ex (ttmlblend_multi_kernel<K, 0>, grid, SM, stream, pdl, P);
   switch (kind) {
-    case PK_PLANE8:
-      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PLANE8, true>, grid, smem_plane8, stream, pdl, P) :
-          launch_ex (ttmlblend_multi_kernel<PK_PLANE8, false>, grid, smem_plane8, stream, pdl, P);
-    case PK_PLANE8_RGB:
-      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PLANE8_RGB, true>, grid, smem_plane8, stream, pdl, P) :
-          launch_ex (ttmlblend_multi_kernel<PK_PLANE8_RGB, false>, grid, smem_plane8, stream, pdl, P);
-    case PK_PACKED_A0:
-      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PACKED_A0, true>, grid, smem_packed, stream, pdl, P) :
-          launch_ex (ttmlblend_multi_kernel<PK_PACKED_A0, false>, grid, smem_packed, stream, pdl, P);
-    case PK_PACKED_A3:
-      return lazy ? launch_ex (ttmlblend_multi_kernel<PK_PACKED_A3, true>, grid, smem_packed, stream, pdl, P) :
-          launch_ex (ttmlblend_multi_kernel<PK_PACKED_A3, false>, grid, smem_packed, stream, pdl, P);
+    MULTI_CASE (PK_PLANE8, smem_plane8)
+    MULTI_CASE (PK_PLANE8_RGB, smem_plane8)
+    MULTI_CASE (PK_PACKED_A0, smem_packed)
+    MULTI_CASE (PK_PACKED_A3, smem_packed)
     default:
       return cudaErrorInvalidValue;
   }
+#undef MULTI_CASE
 }
 
 cudaError_t
@@ -1177,6 +1214,8 @@ ttmlblend_prepare_kernel (const PrepareParams p, int n_elems)
             w = px;
             break;
         }
+        if (a == 0u)
+          w = 0u;               /* blends nothing whatever its colour bytes say: keep the word clean */
       }
       reinterpret_cast<uint32_t *> (p.out_a + orow)[i] = w;
       break;

@@ -53,7 +53,8 @@ enum JobFlags : int32_t {
    *           its CTAs wait for the previous grid to complete (and with it every grid before
    *           that) before they touch anything. */
   JF_DEP = 32,
-  JF_PDL = 64
+  JF_PDL = 64,
+  JF_OPAQUE = 128       /* host-side, group launches out of place: overlay first, no frame read under opaque vectors */
 };
 
 /* One prepared rectangle as seen from one destination plane. */

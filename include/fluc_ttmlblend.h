@@ -156,6 +156,8 @@ typedef struct {
   uint64_t lazy_launches;       /* launches in place that read the overlay first: vectors it leaves
                                  * untouched are skipped, vectors it covers opaquely are written
                                  * without being read (sparse cues, opaque boxes; exact either way) */
+  uint64_t opaque_skip_launches; /* launches out of place that read the overlay first and do not read the
+                                 * frame under vectors it covers opaquely (cues with an opaque box) */
   uint64_t staged_frames;       /* host frames the GPU could not reach directly (pageable or unaligned
                                  * memory): their cue rows went through pinned staging frames */
   uint64_t overlays_updated;    /* of overlays_set: cue changes that kept the untouched regions (overlay_update) */
