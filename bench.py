@@ -85,7 +85,8 @@ def load_traffic(workload: str, fmt: str):
     rec = table.get(f"{workload}:{fmt}") or table.get(workload)
     if not rec:
         return None, None
-    return rec.get("dram_bytes_per_launch"), rec.get("source")
+    # per frame: a rank of a sharded run launches fewer frames than the capture did
+    return rec.get("dram_bytes_per_frame"), rec.get("source")
 
 
 class ClockSampler:
@@ -367,6 +368,8 @@ def roofline_record(work, ms, st, steps, peak, peak_src, cfg_name, fmt, kernel):
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     pairs = int(st["kernel_ms_launches"])
     traffic, traffic_src = load_traffic(cfg_name, fmt)
+    if traffic:
+        traffic *= work.batch * steps / launches      # the table holds DRAM bytes per frame
     rec = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "traffic": traffic, "kernel": kernel, "launch_ms": launch_ms, "launches_timed": launches,
            "timing": "device time of the whole timed region (CUDA events on the blend stream) / its launches; "

@@ -680,8 +680,12 @@ def test_sparse_cues_take_the_overlay_first_path_in_place(ctx, fmt):
                 ctx.wait(ctx.submit(5, fmt, w, h, fr.c, fr.c))
                 got = fr.download()
             st = ctx.stats()
-            assert (st["lazy_launches"] > 0) == lazy, (name, on_host, st)
-            assert st["lazy_launches"] <= st["group_launches"]
+            # which variant ran is a property of the default configuration; under a knob that
+            # forces another code path (tools/knob_matrix.sh) only the bytes are checked
+            if not any(k in os.environ for k in ("FLUC_TTMLBLEND_LAZY", "FLUC_TTMLBLEND_GROUPS", "FLUC_TTMLBLEND_AUTOCROP",
+                                                 "FLUC_TTMLBLEND_HOST_MODE")):
+                assert (st["lazy_launches"] > 0) == lazy, (name, on_host, st)
+                assert st["lazy_launches"] <= st["group_launches"]
             assert_planes_equal(got, want, f"{fmt} {name} host={on_host}")
             fr.release()
         # out of place never skips a store: every byte of dst must be written. Under an opaque box
@@ -689,7 +693,7 @@ def test_sparse_cues_take_the_overlay_first_path_in_place(ctx, fmt):
         got = gpu_blend(ctx, fmt, w, h, planes, mode="out", stream=5, set_overlay=False)
         st_out = ctx.stats()
         assert st_out["lazy_launches"] == (st["lazy_launches"])
-        if "FLUC_TTMLBLEND_OPAQUE_SKIP" not in os.environ and os.environ.get("FLUC_TTMLBLEND_GROUPS") != "0":
+        if not any(k in os.environ for k in ("FLUC_TTMLBLEND_OPAQUE_SKIP", "FLUC_TTMLBLEND_GROUPS", "FLUC_TTMLBLEND_AUTOCROP")):
             assert (st_out["opaque_skip_launches"] > st["opaque_skip_launches"]) == (name == "opaque box"), (name, st_out)
         assert_planes_equal(got, want, f"{fmt} {name} out of place")
 
