@@ -157,7 +157,7 @@ destroy_cuda_objects (Ctx *c)
     c->lanes[i].done = nullptr;
     c->lanes[i].stream = nullptr;
   }
-  for (cudaStream_t *st : { &c->blend_stream, &c->up_stream, &c->reaper, &c->table_stream })
+  for (cudaStream_t *st : { &c->blend_stream, &c->up_stream, &c->reaper, &c->table_stream, &c->dma_in, &c->dma_out })
     if (*st) { cudaStreamDestroy (*st); *st = nullptr; }
   if (c->mem_pool) { cudaMemPoolDestroy (c->mem_pool); c->mem_pool = nullptr; }
 }
@@ -191,10 +191,15 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   if (const char *sy = getenv ("FLUC_TTMLBLEND_SYNC"))
     c->blocking_sync = strcmp (sy, "block") == 0;
   bool ok = true;
+  /* the copy streams of host DMA batches first */
+  ok &= cudaStreamCreateWithFlags (&c->dma_in, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaStreamCreateWithFlags (&c->dma_out, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->blend_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->up_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->reaper, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaStreamCreateWithFlags (&c->table_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < kDmaSets && ok; i++)
+    ok &= cudaEventCreateWithFlags (&c->dma_sets[i].done, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < kLanes + 2 && ok; i++)
     ok &= cudaEventCreateWithFlags (&c->ev_fence[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < kLanes && ok; i++) {
@@ -240,6 +245,8 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->use_multi = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_PDL")))
     c->use_pdl = atoi (e) != 0;
+  if ((e = getenv ("FLUC_TTMLBLEND_HOST_DMA")))
+    c->use_host_dma = atoi (e) != 0;
   c->stage_threads = (int) std::max (2u, std::min (12u, std::thread::hardware_concurrency () / 2));
   if ((e = getenv ("FLUC_TTMLBLEND_STAGE_THREADS")))
     c->stage_threads = std::max (0, std::min (64, atoi (e)));
@@ -274,8 +281,18 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
     c->sched.join ();
   stage_shutdown (c);
   cudaSetDevice (c->device);
+  if (!c->dma_trace.empty ()) {
+    cudaDeviceSynchronize ();
+    const size_t n = c->dma_trace.size (), a = n > 12 ? n - 12 : 0;
+    for (size_t i = a; i < n; i++) {
+      float t[4] = { 0, 0, 0, 0 };
+      for (int k = 0; k < 4; k++)
+        cudaEventElapsedTime (&t[k], c->dma_trace[a][0], c->dma_trace[i][k]);
+      fprintf (stderr, "dma batch %zu: copy-in %.3f .. %.3f ms, copy-out %.3f .. %.3f ms\n", i, t[0], t[1], t[2], t[3]);
+    }
+  }
   /* our own streams only: other users of the device are none of our business */
-  for (cudaStream_t st : { c->blend_stream, c->up_stream, c->table_stream })
+  for (cudaStream_t st : { c->blend_stream, c->up_stream, c->table_stream, c->dma_in, c->dma_out })
     cudaStreamSynchronize (st);
   for (int i = 0; i < kLanes; i++)
     cudaStreamSynchronize (c->lanes[i].stream);
@@ -312,11 +329,19 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
       if (c->lanes[i].dev) cudaFree (c->lanes[i].dev);
     }
     stage_free_slots (c);
-    for (auto &p : c->pool_free) {
-      if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
-    }
-    for (auto &p : c->pool_used) {
-      if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
+    for (auto &p : c->pool_free)
+      if (!p.in_slab) {
+        if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
+      }
+    for (auto &p : c->pool_used)
+      if (!p.in_slab) {
+        if (p.on_host) cudaFreeHost (p.base); else cudaFree (p.base);
+      }
+    for (void *slab : c->host_slabs)
+      cudaFreeHost (slab);
+    for (DmaSet &ds : c->dma_sets) {
+      if (ds.dev) cudaFree (ds.dev);
+      if (ds.done) cudaEventDestroy (ds.done);
     }
     for (auto &r : c->auto_regs)
       cudaHostUnregister ((void *) r.first);
@@ -657,12 +682,13 @@ fluc_ttmlblend_sync (FlucTtmlBlend *thiz)
     lane_ticket[i] = c->lanes[i].ticket;
     lane_busy[i] = c->lanes[i].busy;
   }
-  cudaEvent_t ev[kLanes + 2];
+  cudaEvent_t ev[kLanes + 3];
   int n_ev = 0;
-  cudaStream_t streams[kLanes + 2];
+  cudaStream_t streams[kLanes + 3];
   int n_streams = 0;
   streams[n_streams++] = c->blend_stream;
   streams[n_streams++] = c->up_stream;
+  streams[n_streams++] = c->dma_out;
   for (int i = 0; i < kLanes; i++)
     if (lane_busy[i])
       streams[n_streams++] = c->lanes[i].stream;
@@ -718,6 +744,8 @@ drain_host_users (Ctx *c)
 {
   launch_pending (c);
   cudaStreamSynchronize (c->blend_stream);
+  cudaStreamSynchronize (c->dma_in);
+  cudaStreamSynchronize (c->dma_out);
   for (int i = 0; i < kLanes; i++)
     cudaStreamSynchronize (c->lanes[i].stream);
 }
@@ -809,13 +837,19 @@ tbh::queue_mapped_frame (Ctx *c, uint64_t tk, uint32_t stream, const std::shared
   f.stream = stream;
   note_stream (c, stream);
   const FrameExtent xz (fmt, W, H, &zf), xh (fmt, W, H, hf);
+  f.host = true;
+  f.host_lo = xz.hull_lo ();
+  f.host_hi = xz.hull_hi ();
   if ((rc = order_against_pending (c, xz, xz, true)))
     return rc;
   /* the same buffer still on its way through a staging lane (it was not device-accessible a
    * moment ago): the blend stream waits for that lane */
   for (int i = 0; i < kLanes; i++)
     if (c->lanes[i].busy && xh.hull_lo () < c->lanes[i].host_hi && c->lanes[i].host_lo < xh.hull_hi ())
+    {
       CU (c, cudaStreamWaitEvent (c->blend_stream, c->lanes[i].done, 0));
+      c->blend_stream_waits = true;
+    }
   f.layout = find_layout (c, prep, ov->lazy_inplace, fmt, W, H, frame_flags, &zf, &zf, true);
   for (int pl = 0; pl < 3; pl++) {
     f.src[pl] = static_cast<const uint8_t *> (zf.plane[pl]);
@@ -1137,6 +1171,16 @@ fluc_ttmlblend_plane_rows (FlucTtmlBlendFormat fmt, int plane, int32_t height)
   return plane_rows (fmt, plane, height);
 }
 
+/* free frames are kept in address order, so that frames acquired one after the other are
+ * neighbours in their slab */
+static void
+pool_free_insert (Ctx *c, const PoolEntry &e)
+{
+  auto pos = std::lower_bound (c->pool_free.begin (), c->pool_free.end (), e,
+      [](const PoolEntry &a, const PoolEntry &b) { return (uintptr_t) a.base < (uintptr_t) b.base; });
+  c->pool_free.insert (pos, e);
+}
+
 int
 fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt, int32_t W,
     int32_t H, int on_host, FlucTtmlBlendFrame *out)
@@ -1168,16 +1212,40 @@ fluc_ttmlblend_frame_pool_acquire (FlucTtmlBlend *thiz, FlucTtmlBlendFormat fmt,
   }
   p.bytes = off;
   if (on_host) {
-    NumaScope numa (c);         /* pages next to the GPU's PCIe root */
-    CU (c, cudaHostAlloc (&p.base, off, cudaHostAllocDefault));
-  } else {
-    CU (c, cudaMalloc (&p.base, off));
+    /* a slab of frames at a constant spacing: 4 the first time, then as many as the pool already
+     * holds of this geometry (doubling), at most 32 frames or 512 MB */
+    size_t have = 0;
+    for (const PoolEntry &q : c->pool_used)
+      have += (q.on_host && q.fmt == fmt && q.W == W && q.H == H) ? 1 : 0;
+    size_t k = std::max<size_t> (4, std::min<size_t> (32, have));
+    k = std::max<size_t> (1, std::min<size_t> (k, ((size_t) 512 << 20) / off));
+    void *slab = nullptr;
+    {
+      NumaScope numa (c);       /* pages next to the GPU's PCIe root */
+      CU (c, cudaHostAlloc (&slab, off * k, cudaHostAllocDefault));
+    }
+    c->host_slabs.push_back (slab);
+    /* the first frame goes to the caller, the others wait in the pool in address order */
+    for (size_t i = k; i-- > 0;) {
+      PoolEntry q = p;
+      q.in_slab = true;
+      q.base = static_cast<uint8_t *> (slab) + i * off;
+      for (int pl = 0; pl < n_planes; pl++) {
+        q.frame.plane[pl] = static_cast<uint8_t *> (q.base) + plane_off[pl];
+        c->pinned_planes.insert (q.frame.plane[pl]);
+      }
+      if (i == 0) {
+        *out = q.frame;
+        c->pool_used.push_back (q);
+      } else {
+        pool_free_insert (c, q);
+      }
+    }
+    return 0;
   }
-  for (int pl = 0; pl < n_planes; pl++) {
+  CU (c, cudaMalloc (&p.base, off));
+  for (int pl = 0; pl < n_planes; pl++)
     p.frame.plane[pl] = static_cast<uint8_t *> (p.base) + plane_off[pl];
-    if (on_host)
-      c->pinned_planes.insert (p.frame.plane[pl]);
-  }
   *out = p.frame;
   c->pool_used.push_back (p);
   return 0;
@@ -1191,8 +1259,9 @@ fluc_ttmlblend_frame_pool_release (FlucTtmlBlend *thiz, const FlucTtmlBlendFrame
     return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   for (size_t i = 0; i < c->pool_used.size (); i++)
     if (c->pool_used[i].frame.plane[0] == frame->plane[0]) {
-      c->pool_free.push_back (c->pool_used[i]);
+      const PoolEntry e = c->pool_used[i];
       c->pool_used.erase (c->pool_used.begin () + i);
+      pool_free_insert (c, e);
       return 0;
     }
   return FLUC_TTMLBLEND_ERROR_NOT_FOUND;
@@ -1397,6 +1466,7 @@ fluc_ttmlblend_multi_stats_copy (FlucTtmlBlendMulti *thiz, FlucTtmlBlendStats *o
     sum.overlays_updated += s.overlays_updated;
     sum.staged_frames += s.staged_frames;
     sum.opaque_skip_launches += s.opaque_skip_launches;
+    sum.host_dma_batches += s.host_dma_batches;
   }
   *out = sum;
 }
@@ -1490,6 +1560,72 @@ int
 fluc_ttmlblend_pcie_probe (FlucTtmlBlend *thiz, int mode, size_t bytes, double seconds, double *gbs)
 {
   ENTER (thiz);
+  if (mode >= 2 && mode <= 5) {
+    /* diagnostic: the DMA-batch pipeline shape (copy-in stream, blend stream, copy-out stream, three
+     * device sets, 2-D copies) with buffers of its own, on this context's streams (mode 2) or on
+     * fresh ones (mode 3) */
+    int rc0 = launch_pending (c);
+    if (rc0)
+      return rc0;
+    /* modes 4, 5: whole 4K NV12 frames 12.4 MB apart, the pieces where the cue rows are; 5: the
+     * copy-out lands in pool frames */
+    const bool wide = mode >= 4;
+    const size_t piece[4] = { 1382400, 552960, 691200, 276480 }, fb = wide ? 12441600 : 2903040;
+    const size_t yoff_w[4] = { (size_t) 1728 * 3840, (size_t) 72 * 3840, (size_t) 3840 * 2160 + (size_t) 864 * 3840,
+      (size_t) 3840 * 2160 + (size_t) 36 * 3840 };
+    const size_t yoff_n[4] = { 0, 1382400, 1382400 + 552960, 1382400 + 552960 + 691200 };
+    const size_t *yoff = wide ? yoff_w : yoff_n;
+    const size_t total = fb * 32;
+    uint8_t *h[2] = { nullptr, nullptr }, *d[3] = { nullptr, nullptr, nullptr };
+    for (auto &p : h) { cudaHostAlloc ((void **) &p, total, cudaHostAllocDefault); memset (p, 1, total); }
+    for (auto &p : d) cudaMalloc ((void **) &p, total);
+    cudaStream_t s1 = c->dma_in, s2 = c->dma_out, s3 = c->blend_stream;
+    if (mode == 3) {
+      cudaStreamCreateWithFlags (&s1, cudaStreamNonBlocking);
+      cudaStreamCreateWithFlags (&s2, cudaStreamNonBlocking);
+      cudaStreamCreateWithFlags (&s3, cudaStreamNonBlocking);
+    }
+    cudaEvent_t ein[4], ek[4], done[4], setdone[3];
+    for (auto &e : ein) cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+    for (auto &e : ek) cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+    for (auto &e : done) cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+    for (auto &e : setdone) cudaEventCreateWithFlags (&e, cudaEventDisableTiming);
+    lk.unlock ();
+    auto batch = [&](int i) {
+      uint8_t *hh = h[i & 1], *dd = d[i % 3];
+      if (i >= 3) cudaStreamWaitEvent (s1, setdone[i % 3], 0);
+      for (int k = 0; k < 4; k++)
+        cudaMemcpy2DAsync (dd + yoff[k], fb, hh + yoff[k], fb, piece[k], 32, cudaMemcpyHostToDevice, s1);
+      cudaEventRecord (ein[i & 3], s1);
+      cudaStreamWaitEvent (s3, ein[i & 3], 0);
+      launch_pcie_probe (dd, wide ? total / 4 : total, s3);
+      cudaEventRecord (ek[i & 3], s3);
+      cudaStreamWaitEvent (s2, ek[i & 3], 0);
+      for (int k = 0; k < 4; k++)
+        cudaMemcpy2DAsync (hh + yoff[k], fb, dd + yoff[k], fb, piece[k], 32, cudaMemcpyDeviceToHost, s2);
+      cudaEventRecord (setdone[i % 3], s2);
+      cudaEventRecord (done[i & 3], s2);
+    };
+    for (int i = 0; i < 4; i++) { batch (i); if (i) cudaEventSynchronize (done[(i - 1) & 3]); }
+    cudaStreamSynchronize (s2);
+    const auto t0 = std::chrono::steady_clock::now ();
+    int i = 4, n = 0;
+    double t = 0;
+    do {
+      batch (i);
+      cudaEventSynchronize (done[(i - 1) & 3]);
+      i++; n++;
+      t = std::chrono::duration<double> (std::chrono::steady_clock::now () - t0).count ();
+    } while (t < seconds);
+    cudaStreamSynchronize (s2);
+    t = std::chrono::duration<double> (std::chrono::steady_clock::now () - t0).count ();
+    lk.lock ();
+    if (gbs)
+      *gbs = 92897280.0 * n / t / 1e9;
+    for (auto &p : h) cudaFreeHost (p);
+    for (auto &p : d) cudaFree (p);
+    return cudaGetLastError () == cudaSuccess ? 0 : FLUC_TTMLBLEND_ERROR_CUDA;
+  }
   if (mode < 0 || mode > 1 || bytes < 4096 || bytes > ((size_t) 1 << 31) || !(seconds > 0.0) || seconds > 10.0)
     return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   bytes &= ~(size_t) 4095;

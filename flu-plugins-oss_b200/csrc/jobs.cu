@@ -341,6 +341,32 @@ find_layout (Ctx *c, Prepared *prep, bool lazy_inplace, int format, int W, int H
   return list->back ().get ();
 }
 
+/* the rows a layout's windows touch, neighbouring bands of equal width merged */
+void
+layout_spans (const Layout *L, std::vector<StageSpan> &out)
+{
+  auto add = [&out](const PlaneJob &j) {
+    StageSpan s;
+    s.plane = j.plane;
+    s.b0 = j.win_v0 * 16;
+    s.nb = std::min (j.win_nv * 16, j.row_bytes - s.b0);
+    s.y0 = j.win_y0;
+    s.rows = j.win_rows;
+    if (s.nb <= 0 || s.rows <= 0)
+      return;
+    for (StageSpan &o : out)
+      if (o.plane == s.plane && o.b0 == s.b0 && o.nb == s.nb && o.y0 + o.rows == s.y0) {
+        o.rows += s.rows;
+        return;
+      }
+    out.push_back (s);
+  };
+  for (const PlaneJob &j : L->jobs)
+    add (j);
+  for (const PlaneJob &j : L->gjobs)
+    add (j);
+}
+
 static FramePtrs
 frame_ptrs (const PendingFrame &f)
 {

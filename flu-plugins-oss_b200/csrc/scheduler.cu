@@ -127,6 +127,13 @@ reap_batches (Ctx *c)
       c->timing_pool.push_back (b.t1);
     }
     c->event_pool.push_back (b.done);
+    if (b.ev_in)
+      c->event_pool.push_back (b.ev_in);
+    if (b.ev_blend)
+      c->event_pool.push_back (b.ev_blend);
+    if (b.dma && c->dma_outstanding)
+      c->dma_outstanding--;
+    b.host_ranges.clear ();
     b.keep.clear ();            /* drops the overlay references, keeps the capacity */
     c->keep_pool.push_back (std::move (b.keep));
     c->batches.pop_front ();
@@ -137,6 +144,147 @@ reap_batches (Ctx *c)
     c->inflight_dst.clear ();
     c->inflight_src.clear ();
   }
+}
+
+/* ---- host DMA batches ----------------------------------------------------------------
+ * A batch of device-accessible host frames is normally blended zero copy: the kernel reads the
+ * rows under the cue over PCIe and writes them back. SM-issued reads are the weak side of that
+ * when data flows both ways (36 GB/s each way on one GPU, tools/pcie_ceiling.cu), while the copy
+ * engines keep 44-49 GB/s -- but only in big pieces: the 128 row pieces of a 32-frame 4K batch,
+ * copied one by one, fall to 29 GB/s. Frames that sit at a constant spacing in host memory
+ * (pool frames come in slabs; a pipeline takes them one after the other) turn every piece shape
+ * into ONE two-dimensional copy for the whole run: rows under the cue -> full-size device staging
+ * frames (copy-in stream), the ordinary group launch blends them there in place (blend stream),
+ * rows -> host (copy-out stream); three staging sets, so copy-in of batch i+1, blend of i and
+ * copy-out of i-1 overlap. Taken for a batch iff every frame is such a host frame of one layout
+ * that is not "look at the overlay first" (under an opaque box zero copy moves the frame in one
+ * direction only, which beats any copy), its windows are (nearly) full rows, and the frames form
+ * few enough runs.
+ *
+ * OFF by default (FLUC_TTMLBLEND_HOST_DMA=1 turns it on). The bare pipeline shape reaches 47-48 GB/s
+ * each way on one GPU -- in a process of its own (tools/pcie_ceiling.cu, pattern dma_pipe) and inside
+ * this library on this context's own streams (fluc_ttmlblend_pcie_probe modes 2 / 4) -- but the
+ * batches issued from here do not: FLUC_TTMLBLEND_DMA_TRACE shows the copy-in of batch i+1 starting
+ * only when the copy-out of batch i has ended, with no event between them (27 GB/s each way from a
+ * C caller, 37.5 from a Python one; zero copy: 37.8). Not understood by the end of round 2
+ * (profiles/r02_host_dma_notes.md); parity-tested all the same (tests/test_gpu_hazards.py). */
+struct DmaRun { size_t first, n; ptrdiff_t spacing; };
+struct DmaPlan {
+  std::vector<DmaRun> runs;
+  std::vector<std::pair<const uint8_t *, uint8_t *>> host_ptrs;   /* per frame and plane, for the copies */
+  size_t slot = 0;              /* bytes per device staging frame */
+  DmaSet *set = nullptr;
+  ptrdiff_t plane_off[3] = { 0, 0, 0 };
+  const Layout *layout = nullptr;
+  uintptr_t host_lo = 0, host_hi = 0;
+};
+
+static bool
+plan_host_dma (Ctx *c, DmaPlan &plan)
+{
+  std::vector<PendingFrame> &pf = c->pending;
+  if (!c->use_host_dma || pf.size () < 4)
+    return false;
+  const Layout *L = pf[0].layout;
+  if (!pf[0].host || !L->grouped || !L->jobs.empty () || (L->gflags & JF_LAZY))
+    return false;
+  if (L->dma_ok < 0) {
+    layout_spans (L, L->spans);
+    L->dma_ok = L->spans.empty () ? 0 : 1;
+    for (const StageSpan &s : L->spans) {
+      const int pitch = L->dst_pitch[s.plane];
+      if (s.b0 != 0 || s.nb * 10 < pitch * 9)     /* narrow windows: full rows would move too much */
+        L->dma_ok = 0;
+    }
+  }
+  if (!L->dma_ok)
+    return false;
+  for (int pl = 0; pl < 3; pl++)
+    plan.plane_off[pl] = pf[0].dst[pl] ? pf[0].dst[pl] - pf[0].dst[0] : 0;
+  size_t hull = 0;
+  uintptr_t lo = ~(uintptr_t) 0, hi = 0;
+  for (size_t i = 0; i < pf.size (); i++) {
+    const PendingFrame &f = pf[i];
+    if (!f.host || f.layout->id != L->id || f.layout->windowed != L->windowed)
+      return false;
+    for (int pl = 0; pl < 3; pl++)
+      if ((f.dst[pl] ? f.dst[pl] - f.dst[0] : 0) != plan.plane_off[pl] || f.src[pl] != f.dst[pl])
+        return false;
+    hull = std::max<size_t> (hull, f.host_hi - f.host_lo);
+    lo = std::min (lo, f.host_lo);
+    hi = std::max (hi, f.host_hi);
+    if (f.host_lo != (uintptr_t) f.dst[0])
+      return false;             /* plane 0 first: the device frame mirrors the host frame's layout */
+  }
+  /* runs of frames at a constant spacing */
+  for (size_t i = 0; i < pf.size ();) {
+    DmaRun r = { i, 1, 0 };
+    if (i + 1 < pf.size ()) {
+      r.spacing = pf[i + 1].dst[0] - pf[i].dst[0];
+      if (r.spacing >= (ptrdiff_t) hull)
+        while (r.first + r.n < pf.size () && pf[r.first + r.n].dst[0] - pf[r.first + r.n - 1].dst[0] == r.spacing)
+          r.n++;
+    }
+    plan.runs.push_back (r);
+    i += r.n;
+  }
+  if (plan.runs.size () * L->spans.size () > 48 || plan.runs.size () * 3 > pf.size ())
+    return false;               /* too many copies for what they move: zero copy it is */
+  plan.slot = align_up (hull, 256);
+  plan.layout = L;
+  plan.host_lo = lo;
+  plan.host_hi = hi;
+  /* a staging set (its previous copy-out is waited for on the copy-in stream, not here) */
+  DmaSet &set = c->dma_sets[c->next_dma_set];
+  const size_t need = plan.slot * pf.size ();
+  if (set.bytes < need) {
+    if (set.used && cudaEventSynchronize (set.done) != cudaSuccess)
+      return false;
+    if (set.dev)
+      cudaFree (set.dev);
+    set.dev = nullptr;
+    set.bytes = 0;
+    if (cudaMalloc ((void **) &set.dev, need) != cudaSuccess) {
+      cudaGetLastError ();
+      return false;
+    }
+    set.bytes = need;
+  }
+  c->next_dma_set = (c->next_dma_set + 1) % kDmaSets;
+  plan.set = &set;
+  /* from here on the frames are blended where the copies put them */
+  plan.host_ptrs.resize (pf.size ());
+  for (size_t i = 0; i < pf.size (); i++) {
+    plan.host_ptrs[i] = { pf[i].src[0], pf[i].dst[0] };
+    uint8_t *dev = set.dev + i * plan.slot;
+    for (int pl = 0; pl < 3; pl++)
+      if (pf[i].dst[pl]) {
+        pf[i].dst[pl] = dev + plan.plane_off[pl];
+        pf[i].src[pl] = pf[i].dst[pl];
+      }
+  }
+  return true;
+}
+
+/* the 2-D copies of a DMA batch, one per run and span: a span's rows are contiguous (full rows) */
+static int
+dma_copies (Ctx *c, const DmaPlan &plan, bool in)
+{
+  const Layout *L = plan.layout;
+  for (const DmaRun &r : plan.runs)
+    for (const StageSpan &s : L->spans) {
+      const size_t pitch = (size_t) L->dst_pitch[s.plane];
+      const size_t off = (size_t) plan.plane_off[s.plane] + (size_t) s.y0 * pitch;
+      const size_t width = (size_t) (s.rows - 1) * pitch + (size_t) s.nb;
+      uint8_t *host = plan.host_ptrs[r.first].second + off;
+      uint8_t *dev = plan.set->dev + r.first * plan.slot + off;
+      const size_t hp = r.n > 1 ? (size_t) r.spacing : width, dp = plan.slot;
+      if (in)
+        CU (c, cudaMemcpy2DAsync (dev, dp, host, hp, width, r.n, cudaMemcpyHostToDevice, c->dma_in));
+      else
+        CU (c, cudaMemcpy2DAsync (host, hp, dev, dp, width, r.n, cudaMemcpyDeviceToHost, c->dma_out));
+    }
+  return 0;
 }
 
 /* Launches everything pending as one batch (per plane kind). mu held. */
@@ -150,8 +298,11 @@ launch_pending (Ctx *c)
    * of a one-frame launch (wait / sync / stats retire them too) */
   if (c->batches.size () >= 32)
     reap_batches (c);
+  DmaPlan plan;
+  const bool dma = plan_host_dma (c, plan);
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
+  b.dma = dma;
   if (!c->keep_pool.empty ()) {
     b.keep = std::move (c->keep_pool.back ());
     c->keep_pool.pop_back ();
@@ -183,12 +334,15 @@ launch_pending (Ctx *c)
       frame_group[fi] = gi;
     }
     fi++;
+    if (f.host)
+      b.host_ranges.add (f.host_lo, f.host_hi);
     if (f.overlay && (b.keep.empty () || b.keep.back () != f.overlay))
       b.keep.push_back (f.overlay);     /* consecutive frames of one cue: one reference */
     if (f.prep && !f.prep->blend_waited) {
       /* once per prepared overlay: later launches follow in stream order */
       f.prep->blend_waited = true;
       CU (c, cudaStreamWaitEvent (c->blend_stream, f.prep->ready, 0));
+      c->blend_stream_waits = true;
     }
     c->stats.frames_blended++;
     c->stats.algorithmic_bytes += f.layout->algo_bytes;
@@ -246,14 +400,22 @@ launch_pending (Ctx *c)
     if (!dep)
       dep = sets_overlap (c->pending_dst, c->inflight_dst) || sets_overlap (c->pending_dst, c->inflight_src) ||
           sets_overlap (c->pending_src, c->inflight_dst);
-    if (dep) {
+    /* Behind a stream wait (a new cue's prepare, a staging lane, the copies of a DMA batch) the
+     * launch goes out as an ordinary one: a programmatic launch behind a stream wait holds back
+     * the completion of what was recorded before the wait (measured: the copy-out gated by an
+     * event after kernel i did not start until the copy-in kernel i+1 waits for had finished).
+     * An ordinary launch is ordered after everything before it, like a dependent one. */
+    const bool behind_wait = c->blend_stream_waits || dma || c->dma_outstanding;
+    c->blend_stream_waits = false;
+    if (dep || behind_wait) {
       c->inflight_dst.clear ();
       c->inflight_src.clear ();
-      c->stats.dependent_launches++;
+      if (dep && !behind_wait)
+        c->stats.dependent_launches++;
     }
     c->inflight_dst.merge (c->pending_dst);
     c->inflight_src.merge (c->pending_src);
-    sync = JF_PDL | (dep ? JF_DEP : 0);
+    sync = behind_wait ? 0 : JF_PDL | (dep ? JF_DEP : 0);
   }
   c->pending.clear ();
   c->pending_dst.clear ();
@@ -280,6 +442,51 @@ launch_pending (Ctx *c)
           CU (c, cudaEventCreate (e));
         }
       }
+    }
+    if (dma) {
+      /* copy-in: after the staging set's previous copy-out, and after the newest batch still in
+       * flight that touches the same host frames (its copy-out / its zero-copy kernel) */
+      if (plan.set->used)
+        CU (c, cudaStreamWaitEvent (c->dma_in, plan.set->done, 0));
+      int waited_on = -1, back = 0;
+      for (auto it = c->batches.rbegin (); it != c->batches.rend (); ++it, ++back)
+        if (sets_overlap (it->host_ranges, b.host_ranges)) {
+          CU (c, cudaStreamWaitEvent (c->dma_in, it->done, 0));
+          waited_on = back;
+          break;
+        }
+      TBLOG (2, "dma batch: %zu frames, %zu run(s) x %zu span(s), %zu host range(s), %zu batches in flight, copy-in waits for batch -%d",
+          frame_group.size (), plan.runs.size (), plan.layout->spans.size (), b.host_ranges.v.size (), c->batches.size (),
+          waited_on + 1);
+      static const bool trace = getenv ("FLUC_TTMLBLEND_DMA_TRACE") != nullptr;
+      cudaEvent_t tr[4] = { nullptr, nullptr, nullptr, nullptr };
+      if (trace) {
+        for (auto &e : tr)
+          cudaEventCreate (&e);
+        cudaEventRecord (tr[0], c->dma_in);
+      }
+      int rc = dma_copies (c, plan, true);
+      if (rc)
+        return rc;
+      if (trace) {
+        cudaEventRecord (tr[1], c->dma_in);
+        c->dma_trace.push_back ({ tr[0], tr[1], tr[2], tr[3] });
+      }
+      /* events of its own for every hand-over between the three streams, kept until the batch is
+       * retired: an event that is recorded again on another stream while a wait on its earlier
+       * record is still queued is not something to lean on */
+      b.ev_in = event_get (c);
+      CU (c, cudaEventRecord (b.ev_in, c->dma_in));
+      CU (c, cudaStreamWaitEvent (c->blend_stream, b.ev_in, 0));
+      c->stats.host_dma_batches++;
+    } else if (c->dma_outstanding) {
+      /* zero-copy or device frames after DMA batches: batches complete in launch order (wait and
+       * the bulk retirement rely on it), and a zero-copy frame may be one a copy-out still writes */
+      for (auto it = c->batches.rbegin (); it != c->batches.rend (); ++it)
+        if (it->dma) {
+          CU (c, cudaStreamWaitEvent (c->blend_stream, it->done, 0));
+          break;
+        }
     }
     if (b.t0)
       CU (c, cudaEventRecord (b.t0, c->blend_stream));
@@ -319,6 +526,20 @@ launch_pending (Ctx *c)
     }
     if (b.t1)
       CU (c, cudaEventRecord (b.t1, c->blend_stream));
+    if (dma) {
+      b.ev_blend = event_get (c);
+      CU (c, cudaEventRecord (b.ev_blend, c->blend_stream));
+      CU (c, cudaStreamWaitEvent (c->dma_out, b.ev_blend, 0));
+      if (!c->dma_trace.empty () && c->dma_trace.back ()[2])
+        cudaEventRecord (c->dma_trace.back ()[2], c->dma_out);
+      int rc = dma_copies (c, plan, false);
+      if (rc)
+        return rc;
+      if (!c->dma_trace.empty () && c->dma_trace.back ()[3])
+        cudaEventRecord (c->dma_trace.back ()[3], c->dma_out);
+      CU (c, cudaEventRecord (plan.set->done, c->dma_out));
+      plan.set->used = true;
+    }
     return 0;
   };
   const int rc = issue ();
@@ -330,7 +551,9 @@ launch_pending (Ctx *c)
     if (b.t1) { c->timing_pool.push_back (b.t1); b.t1 = nullptr; }
   }
   b.done = event_get (c);
-  if (b.done && cudaEventRecord (b.done, c->blend_stream) == cudaSuccess) {
+  if (b.done && cudaEventRecord (b.done, dma ? c->dma_out : c->blend_stream) == cudaSuccess) {
+    if (dma)
+      c->dma_outstanding++;
     c->batches.push_back (std::move (b));
   } else {
     /* not even an event: only a broken context gets here */

@@ -15,6 +15,7 @@
 #include <nvtx3/nvToolsExt.h>       /* header-only: ranges show up in nsys / ncu timelines */
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -184,6 +185,61 @@ plane_kind (int f)
 inline int ceil_div (int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up (size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+/* Byte ranges of the frames queued in `pending`, for the hazard check of submit / blend_host:
+ * sorted, disjoint, touching ranges merged. A flat vector -- a batch holds at most a few hundred
+ * frames and the planes of one frame are usually neighbours, so an insert is a binary search
+ * plus a short memmove, and nothing is allocated once the vector has grown. */
+struct IntervalSet {
+  std::vector<std::pair<uintptr_t, uintptr_t>> v;      /* [lo, hi) */
+  void clear () { v.clear (); }
+  bool empty () const { return v.empty (); }
+  /* first range that ends after lo */
+  size_t first_after (uintptr_t lo) const
+  {
+    size_t a = 0, b = v.size ();
+    while (a < b) {
+      const size_t m = (a + b) / 2;
+      if (v[m].second > lo) b = m; else a = m + 1;
+    }
+    return a;
+  }
+  bool overlaps (uintptr_t lo, uintptr_t hi) const
+  {
+    if (v.empty () || hi <= v.front ().first || lo >= v.back ().second)
+      return false;
+    const size_t i = first_after (lo);
+    return i < v.size () && v[i].first < hi;
+  }
+  void merge (const IntervalSet &o)
+  {
+    for (const auto &r : o.v)
+      add (r.first, r.second);
+  }
+  void add (uintptr_t lo, uintptr_t hi)
+  {
+    if (hi <= lo)
+      return;
+    /* ranges that overlap or touch [lo, hi): those ending at or after lo and starting at or before hi */
+    size_t a = 0, b = v.size ();
+    while (a < b) {
+      const size_t m = (a + b) / 2;
+      if (v[m].second >= lo) b = m; else a = m + 1;
+    }
+    size_t e = a;
+    while (e < v.size () && v[e].first <= hi) {
+      lo = std::min (lo, v[e].first);
+      hi = std::max (hi, v[e].second);
+      e++;
+    }
+    if (e == a) {
+      v.insert (v.begin () + a, std::make_pair (lo, hi));
+    } else {
+      v[a] = std::make_pair (lo, hi);
+      v.erase (v.begin () + a + 1, v.begin () + e);
+    }
+  }
+};
+
 /* ---------------------------------------------------------------------- */
 /* overlay cache                                                          */
 
@@ -207,6 +263,8 @@ struct RawRect {
   int ga = 255;
   bool premul = true;
 };
+
+struct StageSpan { int plane, b0, nb, y0, rows; };       /* rows [y0, y0+rows), bytes [b0, b0+nb) of a plane */
 
 /* The work of one frame minus its pointers: windows, classes, band list. It depends on the
  * prepared overlay, the strides, the alignment of the planes, in place or not and the frame
@@ -232,6 +290,10 @@ struct Layout {
   const RectRef *rects_all = nullptr;
   uint64_t algo_bytes = 0;
   uint64_t window_bytes = 0;           /* bytes of all windows (what a zero-copy host frame moves each way) */
+  /* host DMA batches: the rows the windows touch (neighbouring bands merged), and whether they
+   * are (nearly) full rows, so that a window's rows are one contiguous run of bytes */
+  mutable std::vector<StageSpan> spans;
+  mutable int dma_ok = -1;             /* -1: not looked at yet */
 };
 
 /* what one rectangle of the overlay looks like from the planes of one destination format */
@@ -287,6 +349,8 @@ struct Overlay {
 struct PendingFrame {
   uint64_t ticket;
   uint32_t stream;
+  bool host = false;                   /* a device-accessible HOST frame, blended in place (zero copy or DMA batch) */
+  uintptr_t host_lo = 0, host_hi = 0;  /* its bytes (hull of the planes) */
   std::shared_ptr<Overlay> overlay;    /* keeps prep and layout alive */
   Prepared *prep;
   const Layout *layout;
@@ -322,7 +386,19 @@ struct Batch {
   cudaEvent_t done;
   cudaEvent_t t0, t1;                  /* profiling pair (may be null) */
   std::vector<std::shared_ptr<Overlay>> keep;
+  bool dma = false;                    /* host frames moved by the copy engines: `done` is on the copy-out stream */
+  IntervalSet host_ranges;             /* the host frames of the batch (zero copy or DMA), for ordering later DMA batches */
+  cudaEvent_t ev_in = nullptr, ev_blend = nullptr;   /* DMA batch: copy-in done, blend done (back to the pool with the batch) */
 };
+
+/* device staging for one DMA batch of host frames: full-size device frames at a constant spacing */
+struct DmaSet {
+  uint8_t *dev = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t done = nullptr;          /* the copy back out of this set has finished */
+  bool used = false;
+};
+constexpr int kDmaSets = 3;
 
 struct TableSlot {
   PlaneJob *h_jobs = nullptr, *d_jobs = nullptr;
@@ -330,61 +406,6 @@ struct TableSlot {
   size_t cap = 0, cap_words = 0;       /* jobs / words (job begins + coarse index) */
   cudaEvent_t copied = nullptr;        /* last kernel that read the slot has finished */
   cudaEvent_t uploaded = nullptr;      /* table copy has landed */
-};
-
-/* Byte ranges of the frames queued in `pending`, for the hazard check of submit / blend_host:
- * sorted, disjoint, touching ranges merged. A flat vector -- a batch holds at most a few hundred
- * frames and the planes of one frame are usually neighbours, so an insert is a binary search
- * plus a short memmove, and nothing is allocated once the vector has grown. */
-struct IntervalSet {
-  std::vector<std::pair<uintptr_t, uintptr_t>> v;      /* [lo, hi) */
-  void clear () { v.clear (); }
-  bool empty () const { return v.empty (); }
-  /* first range that ends after lo */
-  size_t first_after (uintptr_t lo) const
-  {
-    size_t a = 0, b = v.size ();
-    while (a < b) {
-      const size_t m = (a + b) / 2;
-      if (v[m].second > lo) b = m; else a = m + 1;
-    }
-    return a;
-  }
-  bool overlaps (uintptr_t lo, uintptr_t hi) const
-  {
-    if (v.empty () || hi <= v.front ().first || lo >= v.back ().second)
-      return false;
-    const size_t i = first_after (lo);
-    return i < v.size () && v[i].first < hi;
-  }
-  void merge (const IntervalSet &o)
-  {
-    for (const auto &r : o.v)
-      add (r.first, r.second);
-  }
-  void add (uintptr_t lo, uintptr_t hi)
-  {
-    if (hi <= lo)
-      return;
-    /* ranges that overlap or touch [lo, hi): those ending at or after lo and starting at or before hi */
-    size_t a = 0, b = v.size ();
-    while (a < b) {
-      const size_t m = (a + b) / 2;
-      if (v[m].second >= lo) b = m; else a = m + 1;
-    }
-    size_t e = a;
-    while (e < v.size () && v[e].first <= hi) {
-      lo = std::min (lo, v[e].first);
-      hi = std::max (hi, v[e].second);
-      e++;
-    }
-    if (e == a) {
-      v.insert (v.begin () + a, std::make_pair (lo, hi));
-    } else {
-      v[a] = std::make_pair (lo, hi);
-      v.erase (v.begin () + a + 1, v.begin () + e);
-    }
-  }
 };
 
 /* The bytes a frame's planes occupy, as at most three ranges (planes that are neighbours in
@@ -449,8 +470,9 @@ sets_overlap (const IntervalSet &a, const IntervalSet &b)
 }
 
 struct PoolEntry {
-  void *base;
+  void *base;                          /* slab members: the frame's first byte inside the slab */
   size_t bytes;
+  bool in_slab;                        /* pinned host frames come in slabs (Ctx::host_slabs), freed with them */
   int fmt, W, H, on_host;
   FlucTtmlBlendFrame frame;
 };
@@ -468,8 +490,6 @@ struct Lane {
 };
 
 /* ---- staged host frames (staging.cu) ---- */
-struct StageSpan { int plane, b0, nb, y0, rows; };       /* rows [y0, y0+rows), bytes [b0, b0+nb) of a plane */
-
 struct StageJob {
   enum State { COPY_IN, ON_GPU, COPY_OUT, DONE };
   uint64_t ticket = 0;                 /* what blend_host handed out */
@@ -537,6 +557,11 @@ struct Ctx {
   IntervalSet inflight_dst, inflight_src;
   bool use_pdl = true;                 /* FLUC_TTMLBLEND_PDL=0: ordinary, serialised launches */
   bool isolate_next = false;           /* the launch after a timed one must not overlap it */
+  /* the blend stream has been told to wait for an event since the last launch: the next launch
+   * goes out as an ordinary one. A programmatic launch behind a stream wait holds back the
+   * completion of what was recorded before the wait (measured: a copy-out gated by an event
+   * after kernel i did not start until the copy-in that kernel i+1 waits for had finished) */
+  bool blend_stream_waits = false;
   /* batches whose launch failed half way (out of memory): wait() on their tickets reports it */
   struct FailedRange { uint64_t first, last; int rc; };
   std::deque<FailedRange> failed_ranges;
@@ -592,6 +617,17 @@ struct Ctx {
   std::vector<int> numa_cpus;
   int numa_node = -1;
   std::vector<PoolEntry> pool_free, pool_used;
+  /* pinned host frames are allocated several at a time, at a constant spacing: the frames a
+   * pipeline takes from the pool one after the other then form runs that one two-dimensional
+   * copy can move (host DMA batches, scheduler.cu) */
+  std::vector<void *> host_slabs;
+  /* host DMA batches: FLUC_TTMLBLEND_HOST_DMA=1 turns them on (default: zero copy only; see scheduler.cu) */
+  bool use_host_dma = false;
+  cudaStream_t dma_in = nullptr, dma_out = nullptr;
+  DmaSet dma_sets[kDmaSets];
+  int next_dma_set = 0;
+  uint32_t dma_outstanding = 0;        /* DMA batches in `batches` */
+  std::vector<std::array<cudaEvent_t, 4>> dma_trace;   /* FLUC_TTMLBLEND_DMA_TRACE: copy-in begin / end, copy-out begin / end */
   std::unordered_set<const void *> pinned_planes;   /* plane pointers of the pinned host pool frames */
   uint8_t *scrub = nullptr;
   size_t scrub_bytes = 0;
@@ -649,6 +685,7 @@ int overlay_install_regions (Ctx *c, std::unique_lock<std::mutex> &lk, uint32_t 
     const FlucTtmlBlendRegion *regions, uint32_t n);
 
 /* jobs.cu */
+void layout_spans (const Layout *L, std::vector<StageSpan> &out);
 int check_frame (int fmt, int W, int H, const FlucTtmlBlendFrame *f);
 uint64_t build_jobs (int format, int W, int H, uint32_t frame_flags, const FlucTtmlBlendFrame *src,
     const FlucTtmlBlendFrame *dst, const Prepared *prep, bool windowed, std::vector<PlaneJob> &jobs);

@@ -69,7 +69,7 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_uint64), ("kernel_ms", C.c_double),
                 ("kernel_ms_launches", C.c_uint64), ("cache_bytes", C.c_uint64),
                 ("multi_launches", C.c_uint64), ("lazy_launches", C.c_uint64),
-                ("opaque_skip_launches", C.c_uint64), ("staged_frames", C.c_uint64),
+                ("host_dma_batches", C.c_uint64), ("opaque_skip_launches", C.c_uint64), ("staged_frames", C.c_uint64),
                 ("overlays_updated", C.c_uint64), ("dependent_launches", C.c_uint64)]
 
 

@@ -156,6 +156,9 @@ typedef struct {
   uint64_t lazy_launches;       /* launches in place that read the overlay first: vectors it leaves
                                  * untouched are skipped, vectors it covers opaquely are written
                                  * without being read (sparse cues, opaque boxes; exact either way) */
+  uint64_t host_dma_batches;    /* batches of pinned host frames moved by the copy engines (2-D copies of
+                                 * the rows under the cue, frames at a constant spacing) instead of
+                                 * being read and written by the kernel over PCIe */
   uint64_t opaque_skip_launches; /* launches out of place that read the overlay first and do not read the
                                  * frame under vectors it covers opaquely (cues with an opaque box) */
   uint64_t staged_frames;       /* host frames the GPU could not reach directly (pageable or unaligned

@@ -277,3 +277,61 @@ def test_independent_launches_are_not_serialised(ctx):
             f.release()
     finally:
         ctx.set_batch(32, 200)
+
+
+def test_host_dma_batches(ctx):
+    """Pinned pool frames come in slabs (constant spacing), so a batch of them can be moved by the
+    copy engines -- one 2-D copy per piece of rows and run of frames -- blended in device staging and
+    copied back (FLUC_TTMLBLEND_HOST_DMA=1; zero copy otherwise). Same bytes as the oracle either
+    way; a second batch on the same frames waits for the first one, and so does a single zero-copy
+    frame."""
+    fmt, W, H = "NV12", 1024, 360          # 1024: pool stride == row bytes, the windows are whole rows
+    box = lambda seed: np.ascontiguousarray(np.concatenate(
+        [np.zeros((200, W, 4), np.uint8), _opaque_free(random_overlay(W, 120, seed, density=0.9)), np.zeros((40, W, 4), np.uint8)]))
+    ov1, ov2 = box(980), box(981)
+    ctx.overlay_set(780, ov1, [(0, 200, W, 120)])
+    ctx.overlay_set(781, ov2, [(0, 200, W, 120)])
+    n = 16
+    ctx.set_batch(n, 0)
+    try:
+        hosts = [ctx.acquire(fmt, W, H, on_host=True) for _ in range(n)]
+        frames = [random_frame(fmt, W, H, 70 + i) for i in range(n)]
+        for rep in range(3):
+            for hf, fr in zip(hosts, frames):
+                for v, p in zip(hf.host_planes(), fr):
+                    v[...] = p
+            before = ctx.stats()
+            b1 = ctx.Batch([780] * n, fmt, W, H, [h.c for h in hosts], [h.c for h in hosts])
+            b2 = ctx.Batch([781] * n, fmt, W, H, [h.c for h in hosts], [h.c for h in hosts])
+            t1 = ctx.blend_host_many(b1)
+            t2 = ctx.blend_host_many(b2)                            # the same frames again, nothing waited for
+            t3 = ctx.blend_host_frame(780, fmt, W, H, hosts[3].c)   # and one of them once more, zero copy
+            ctx.flush()
+            ctx.wait(t1[n - 1])
+            ctx.wait(t2[n - 1])
+            ctx.wait(t3)
+            after = ctx.stats()
+            if os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1" and os.environ.get("FLUC_TTMLBLEND_HOST_MODE", "1") == "1" \
+                    and "FLUC_TTMLBLEND_GROUPS" not in os.environ and "FLUC_TTMLBLEND_LAZY" not in os.environ:
+                assert after["host_dma_batches"] - before["host_dma_batches"] == 2, after
+            for i, (hf, fr) in enumerate(zip(hosts, frames)):
+                want = oracle_blend(fmt, W, H, copy_planes(fr), _rects(ov1))
+                want = oracle_blend(fmt, W, H, want, _rects(ov2))
+                if i == 3:
+                    want = oracle_blend(fmt, W, H, want, _rects(ov1))
+                assert_planes_equal([v.copy() for v in hf.host_planes()], want, f"host frame {i}, repetition {rep}")
+        for h in hosts:
+            h.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
+def _opaque_free(img):
+    """A translucent cue (no opaque vectors: such batches take the copy engines)."""
+    img = img.copy()
+    a = img[..., 3].astype(np.uint32)
+    a = np.minimum(a, 200)
+    a[a == 0] = 120                                   # a translucent box behind everything
+    img[..., 3] = a
+    img[..., :3] = np.minimum(img[..., :3], img[..., 3:4])      # stays valid premultiplied data
+    return img

@@ -52,6 +52,7 @@ struct Options {
   bool threads = false, pin = false, opaque = false, pageable = false;
   double secs = 2.0;
   int batch = 32;
+  int depth = 1;                /* batches handed over before the oldest one is waited for */
 };
 
 #define OK(x) do { int rc_ = (x); if (rc_) { fprintf (stderr, "%s: %s\n", #x, fluc_ttmlblend_strerror (rc_)); _exit (3); } } while (0)
@@ -94,9 +95,11 @@ worker (const Options &o, int w, Shared *sh)
       }
   OK (fluc_ttmlblend_overlay_set (ctx, 1, img.data (), W, H, W * 4, regions, 2));
   OK (fluc_ttmlblend_set_batch (ctx, (uint32_t) o.batch, 0));
-  std::vector<FlucTtmlBlendFrame> sets[2];
+  std::vector<FlucTtmlBlendFrame> sets[8];
+  const int n_sets = o.depth + 1;
   std::vector<uint32_t> streams ((size_t) o.batch, 1u);
-  for (auto &set : sets) {
+  for (int si = 0; si < n_sets; si++) {
+    auto &set = sets[si];
     set.resize ((size_t) o.batch);
     for (auto &f : set) {
       if (o.pageable) {         /* ordinary memory, GStreamer's default NV12 layout */
@@ -113,18 +116,27 @@ worker (const Options &o, int w, Shared *sh)
   }
   std::vector<uint64_t> tickets ((size_t) o.batch), prev_all;
   uint64_t prev = 0;
+  double t_submit = 0, t_wait = 0;
+  std::vector<uint64_t> ring;
   auto step = [&](int i) {
+    const double ta = now ();
     OK (fluc_ttmlblend_blend_host_many (ctx, (uint32_t) o.batch, streams.data (), FLUC_TTMLBLEND_FORMAT_NV12, W, H, 0,
-            sets[i & 1].data (), tickets.data ()));
+            sets[i % n_sets].data (), tickets.data ()));
+    t_submit += now () - ta;
     if (o.pageable) {           /* staged frames complete one by one: wait for each of the previous set */
       for (uint64_t t : prev_all)
         OK (fluc_ttmlblend_wait (ctx, t));
       prev_all = tickets;
       return;
     }
-    if (prev)
-      OK (fluc_ttmlblend_wait (ctx, prev));
-    prev = tickets.back ();
+    const double tb = now ();
+    ring.push_back (tickets.back ());
+    if ((int) ring.size () > o.depth) {
+      OK (fluc_ttmlblend_wait (ctx, ring.front ()));
+      ring.erase (ring.begin ());
+    }
+    t_wait += now () - tb;
+    (void) prev;
   };
   for (int i = 0; i < 4; i++)
     step (i);
@@ -143,6 +155,9 @@ worker (const Options &o, int w, Shared *sh)
   t = now () - t0;
   FlucTtmlBlendStats st;
   fluc_ttmlblend_stats_copy (ctx, &st);
+  if (getenv ("E2E_TIMES"))
+    fprintf (stderr, "worker %d: %d steps, %.3f ms in blend_host_many and %.3f ms in wait per step\n", w, n + 4,
+        t_submit / (n + 4) * 1e3, t_wait / (n + 4) * 1e3);
   sh->fps[w] = (double) n * o.batch / t;
   sh->gbs[w] = (double) st.h2d_bytes / t / 1e9;
   barrier (sh, G);
@@ -177,6 +192,8 @@ main (int argc, char **argv)
       o.secs = atof (next ().c_str ());
     else if (a == "--batch")
       o.batch = atoi (next ().c_str ());
+    else if (a == "--depth")
+      o.depth = std::max (1, std::min (6, atoi (next ().c_str ())));
     else
       return 2;
   }

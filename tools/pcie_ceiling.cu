@@ -17,6 +17,8 @@
 //             zcr_dmaw     kernel reads host || copy engine writes host
 //             dmar_zcw     copy engine reads host || kernel writes host
 //             dma_pieces   dma_both in the 128 row pieces of a 32-frame 4K NV12 batch per direction
+//             dma_2d       the same pieces as 4 two-dimensional copies per direction (frames at a constant spacing)
+//             dma_2d_zcw   2-D copies in || kernel writes host
 //
 //   build/pcie_ceiling --gpus 0,1,2,3 [--threads] [--secs 0.5] [--sync spin|yield|block]
 //                      [--pin] [--alloc default|portable|wc|register] [--patterns a,b,..]
@@ -162,6 +164,19 @@ worker (const Options &o, int w, Shared *sh)
   CK (cudaMemset (d1, 2, bytes));
   CK (cudaMemset (d2, 3, bytes));
   cudaStream_t s1, s2;
+  /* PCIE_DUMMY_STREAMS=n: n other streams are created first (does the order of creation decide
+   * which copy engine a stream's copies use?) */
+  if (const char *ds = getenv ("PCIE_DUMMY_STREAMS"))
+    for (int i = 0; i < atoi (ds); i++) {
+      cudaStream_t dummy;
+      CK (cudaStreamCreateWithFlags (&dummy, cudaStreamNonBlocking));
+      if (getenv ("PCIE_DUMMY_USED")) {         /* ... and used: a copy each way and a kernel */
+        CK (cudaMemcpyAsync (d1, h1, 1 << 20, cudaMemcpyHostToDevice, dummy));
+        CK (cudaMemcpyAsync (h2, d2, 1 << 20, cudaMemcpyDeviceToHost, dummy));
+        move16<4><<<64, 256, 0, dummy>>> ((const uint4 *) d1, (uint4 *) d2, 65536);
+        CK (cudaStreamSynchronize (dummy));
+      }
+    }
   CK (cudaStreamCreateWithFlags (&s1, cudaStreamNonBlocking));
   CK (cudaStreamCreateWithFlags (&s2, cudaStreamNonBlocking));
   const size_t n16 = bytes / 16;
@@ -208,11 +223,110 @@ worker (const Options &o, int w, Shared *sh)
             off += pc;
           }
         in_bytes = out_bytes = (double) bytes;
+      } else if (p == "dma_2d") {             /* the same pieces, but one 2-D copy per piece shape moves it for all 32
+                                               * frames (frames at a constant spacing): 4 copies per direction */
+        size_t off = 0;
+        for (size_t pc : piece) {
+          CK (cudaMemcpy2DAsync (d1 + off, per_frame, h1 + off, per_frame, pc, 32, cudaMemcpyHostToDevice, s1));
+          CK (cudaMemcpy2DAsync (h2 + off, per_frame, d2 + off, per_frame, pc, 32, cudaMemcpyDeviceToHost, s2));
+          off += pc;
+        }
+        in_bytes = out_bytes = (double) bytes;
+      } else if (p == "dma_2d_zcw") {         /* 2-D copies in, a kernel writes the result back to the host */
+        size_t off = 0;
+        for (size_t pc : piece) {
+          CK (cudaMemcpy2DAsync (d1 + off, per_frame, h1 + off, per_frame, pc, 32, cudaMemcpyHostToDevice, s1));
+          off += pc;
+        }
+        move16<4><<<grid, 256, 0, s2>>> ((const uint4 *) d2, (uint4 *) h2, n16);
+        in_bytes = out_bytes = (double) bytes;
       } else {                  /* zc_inplace */
         move16<4><<<grid, 256, 0, s1>>> ((const uint4 *) h1, (uint4 *) h1, n16);
         in_bytes = out_bytes = (double) bytes;
       }
     };
+    if (p == "dma_2d_wide") {
+      /* as dma_2d, but the 32 frames are whole 4K NV12 frames (12.4 MB apart), as in the product */
+      const size_t fb = 12441600, yoff[4] = { (size_t) 1728 * 3840, (size_t) 72 * 3840, (size_t) 3840 * 2160 + (size_t) 864 * 3840,
+        (size_t) 3840 * 2160 + (size_t) 36 * 3840 };
+      uint8_t *hw1, *hw2, *dw1, *dw2;
+      CK (cudaHostAlloc ((void **) &hw1, fb * 32, cudaHostAllocDefault));
+      CK (cudaHostAlloc ((void **) &hw2, fb * 32, cudaHostAllocDefault));
+      CK (cudaMalloc ((void **) &dw1, fb * 32));
+      CK (cudaMalloc ((void **) &dw2, fb * 32));
+      memset (hw1, 1, fb * 32);
+      memset (hw2, 1, fb * 32);
+      auto go = [&]() {
+        for (int k = 0; k < 4; k++) {
+          CK (cudaMemcpy2DAsync (dw1 + yoff[k], fb, hw1 + yoff[k], fb, piece[k], 32, cudaMemcpyHostToDevice, s1));
+          CK (cudaMemcpy2DAsync (hw2 + yoff[k], fb, dw2 + yoff[k], fb, piece[k], 32, cudaMemcpyDeviceToHost, s2));
+        }
+      };
+      go ();
+      CK (cudaStreamSynchronize (s1));
+      CK (cudaStreamSynchronize (s2));
+      barrier (sh, G);
+      const double t0 = now ();
+      int n = 0;
+      double t = 0;
+      do {
+        go ();
+        go ();
+        CK (cudaStreamSynchronize (s1));
+        CK (cudaStreamSynchronize (s2));
+        n += 2;
+        t = now () - t0;
+      } while (t < o.secs);
+      sh->gbs_in[pi][w] = sh->gbs_out[pi][w] = (double) bytes * n / t / 1e9;
+      barrier (sh, G);
+      cudaFreeHost (hw1); cudaFreeHost (hw2); cudaFree (dw1); cudaFree (dw2);
+      continue;
+    }
+    if (p == "dma_pipe") {
+      /* the product's DMA batch pipeline: copy-in stream, blend stream, copy-out stream, three
+       * device sets; the host hands over batch i+1 once batch i-1 has come back */
+      cudaStream_t s3;
+      CK (cudaStreamCreateWithFlags (&s3, cudaStreamNonBlocking));
+      cudaEvent_t ein, ek, done[4], setdone[3];
+      CK (cudaEventCreateWithFlags (&ein, cudaEventDisableTiming));
+      CK (cudaEventCreateWithFlags (&ek, cudaEventDisableTiming));
+      for (auto &e : done) CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+      for (auto &e : setdone) CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+      uint8_t *dset[3];
+      for (auto &d : dset) CK (cudaMalloc ((void **) &d, bytes));
+      auto batch = [&](int i) {
+        uint8_t *h = (i & 1) ? h2 : h1, *d = dset[i % 3];
+        if (i >= 3) CK (cudaStreamWaitEvent (s1, setdone[i % 3], 0));
+        size_t off = 0;
+        for (size_t pc : piece) { CK (cudaMemcpy2DAsync (d + off, per_frame, h + off, per_frame, pc, 32, cudaMemcpyHostToDevice, s1)); off += pc; }
+        CK (cudaEventRecord (ein, s1));
+        CK (cudaStreamWaitEvent (s3, ein, 0));
+        move16<4><<<grid, 256, 0, s3>>> ((const uint4 *) d, (uint4 *) d, n16);
+        CK (cudaEventRecord (ek, s3));
+        CK (cudaStreamWaitEvent (s2, ek, 0));
+        off = 0;
+        for (size_t pc : piece) { CK (cudaMemcpy2DAsync (h + off, per_frame, d + off, per_frame, pc, 32, cudaMemcpyDeviceToHost, s2)); off += pc; }
+        CK (cudaEventRecord (setdone[i % 3], s2));
+        CK (cudaEventRecord (done[i & 3], s2));
+      };
+      for (int i = 0; i < 4; i++) { batch (i); if (i) CK (cudaEventSynchronize (done[(i - 1) & 3])); }
+      CK (cudaStreamSynchronize (s2));
+      barrier (sh, G);
+      const double t0 = now ();
+      int i = 4, n = 0;
+      double t = 0;
+      do {
+        batch (i);
+        CK (cudaEventSynchronize (done[(i - 1) & 3]));
+        i++; n++;
+        t = now () - t0;
+      } while (t < o.secs);
+      CK (cudaStreamSynchronize (s2));
+      t = now () - t0;
+      sh->gbs_in[pi][w] = sh->gbs_out[pi][w] = (double) bytes * n / t / 1e9;
+      barrier (sh, G);
+      continue;
+    }
     for (int i = 0; i < 2; i++)
       issue ();
     CK (cudaStreamSynchronize (s1));
