@@ -247,7 +247,7 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
     c->use_pdl = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_DMA")))
     c->use_host_dma = atoi (e) != 0;
-  c->stage_threads = (int) std::max (2u, std::min (12u, std::thread::hardware_concurrency () / 2));
+  c->stage_threads = (int) std::max (2u, std::min (12u, std::thread::hardware_concurrency () * 3 / 4));
   if ((e = getenv ("FLUC_TTMLBLEND_STAGE_THREADS")))
     c->stage_threads = std::max (0, std::min (64, atoi (e)));
   if ((e = getenv ("FLUC_TTMLBLEND_STAGE_SLOTS")))

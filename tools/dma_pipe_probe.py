@@ -5,16 +5,18 @@ import numpy as np
 import __graft_entry__ as g
 pkg = g.load_package(); wl = pkg.workloads
 c = pkg.TtmlBlend(0)
-print('bare pipeline, fresh context: mode 4', round(c.pcie_probe(4, 1 << 20, 0.4), 1), 'GB/s each way')
+import os
+if os.environ.get('PROBE_FIRST'): print('bare pipeline, fresh context: mode 4', round(c.pcie_probe(4, 1 << 20, 0.4), 1), 'GB/s each way')
 cfg = wl.CONFIGS[3]
 c.overlay_set(1, wl.overlay_for(cfg), wl.region_rects(cfg))
 c.set_batch(32, 0)
-sets = [[c.acquire('NV12', 3840, 2160, on_host=True) for _ in range(32)] for _ in range(2)]
+NS = int(os.environ.get('HOST_SETS', '2'))
+sets = [[c.acquire('NV12', 3840, 2160, on_host=True) for _ in range(32)] for _ in range(NS)]
 bs = [c.Batch([1] * 32, 'NV12', 3840, 2160, [f.c for f in s], [f.c for f in s]) for s in sets]
 def loop(n):
     prev = None
     for i in range(n):
-        t = c.blend_host_many(bs[i & 1])
+        t = c.blend_host_many(bs[i % NS])
         if prev is not None: c.wait(prev)
         prev = t[31]
     c.wait(prev)

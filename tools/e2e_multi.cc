@@ -119,6 +119,8 @@ worker (const Options &o, int w, Shared *sh)
   double t_submit = 0, t_wait = 0;
   std::vector<uint64_t> ring;
   auto step = [&](int i) {
+    if (const char *d = getenv ("E2E_DELAY_US"))
+      usleep ((useconds_t) atoi (d));
     const double ta = now ();
     OK (fluc_ttmlblend_blend_host_many (ctx, (uint32_t) o.batch, streams.data (), FLUC_TTMLBLEND_FORMAT_NV12, W, H, 0,
             sets[i % n_sets].data (), tickets.data ()));

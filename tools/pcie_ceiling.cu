@@ -315,9 +315,12 @@ worker (const Options &o, int w, Shared *sh)
       const double t0 = now ();
       int i = 4, n = 0;
       double t = 0;
+      /* PCIE_PIPE_DEPTH=2: the host runs two batches ahead, so the copy-in of batch i+1 is queued
+       * while the copy-out of batch i still waits for its event */
+      const int depth = getenv ("PCIE_PIPE_DEPTH") ? atoi (getenv ("PCIE_PIPE_DEPTH")) : 1;
       do {
         batch (i);
-        CK (cudaEventSynchronize (done[(i - 1) & 3]));
+        CK (cudaEventSynchronize (done[(i - depth) & 3]));
         i++; n++;
         t = now () - t0;
       } while (t < o.secs);
