@@ -488,6 +488,7 @@ struct Up {
   RawRect rr;
   std::vector<int2> spans;
   std::vector<int> groups;      /* per row: 16-pixel groups with any alpha */
+  std::vector<int> raw;         /* both as they come back from the GPU in one copy: h x int2, then h x int */
 };
 
 /* Is this pointer device memory (a cue produced on the GPU, or left there by a previous stage)? */
@@ -534,17 +535,27 @@ scan_rows (Ctx *c, std::unique_lock<std::mutex> &lk, Up &u)
   void *sp = nullptr;
   const size_t nb = (size_t) u.rr.h * (sizeof (int2) + sizeof (int));
   CUU (c, lk, cudaMallocFromPoolAsync (&sp, nb, c->mem_pool, c->up_stream));
-  u.spans.resize (u.rr.h);
-  u.groups.resize (u.rr.h);
+  u.raw.resize ((size_t) u.rr.h * 3);
   int2 *d_spans = static_cast<int2 *> (sp);
   int *d_groups = reinterpret_cast<int *> (d_spans + u.rr.h);
   CUU (c, lk, launch_rowspan (u.rr.dev, u.rr.pitch, u.rr.w, u.rr.h, d_spans, d_groups, c->up_stream));
-  CUU (c, lk, cudaMemcpyAsync (u.spans.data (), d_spans, (size_t) u.rr.h * sizeof (int2), cudaMemcpyDeviceToHost,
-          c->up_stream));
-  CUU (c, lk, cudaMemcpyAsync (u.groups.data (), d_groups, (size_t) u.rr.h * sizeof (int), cudaMemcpyDeviceToHost,
-          c->up_stream));
+  CUU (c, lk, cudaMemcpyAsync (u.raw.data (), sp, nb, cudaMemcpyDeviceToHost, c->up_stream));   /* one copy for both */
   CUU (c, lk, cudaFreeAsync (sp, c->up_stream));
   return 0;
+}
+
+/* after the upload stream has been waited for: the scan's two arrays apart */
+static void
+unpack_scan (Up &u)
+{
+  if (u.raw.empty ())
+    return;
+  const size_t h = (size_t) u.rr.h;
+  u.spans.resize (h);
+  u.groups.resize (h);
+  memcpy (u.spans.data (), u.raw.data (), h * sizeof (int2));
+  memcpy (u.groups.data (), u.raw.data () + 2 * h, h * sizeof (int));
+  u.raw.clear ();
 }
 
 /* One uploaded rectangle becomes a box of the overlay: cropped to its non-transparent row runs
@@ -552,6 +563,7 @@ scan_rows (Ctx *c, std::unique_lock<std::mutex> &lk, Up &u)
 static void
 append_box (Ctx *c, Overlay *ov, Up &u, size_t n_boxes)
 {
+  unpack_scan (u);
   OverlayBox box;
   box.declared = { u.rr.x, u.rr.y, u.rr.w, u.rr.h };
   box.first_rect = (uint32_t) ov->rects.size ();
