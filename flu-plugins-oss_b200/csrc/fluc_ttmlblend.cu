@@ -643,12 +643,15 @@ fluc_ttmlblend_wait (FlucTtmlBlend *thiz, uint64_t ticket)
   for (const Ctx::FailedRange &fr : c->failed_ranges)
     if (ticket >= fr.first && ticket <= fr.last)
       failed = fr.rc;
+  /* a ticket whose batch has been retired is finished; it must not fall through to the next batch
+   * in flight (a caller that waits one batch behind would then wait for the newest one) */
   cudaEvent_t ev = nullptr;
-  for (auto &b : c->batches)
-    if (b.last_ticket >= ticket) {
-      ev = b.done;
-      break;
-    }
+  if (ticket > c->retired_through)
+    for (auto &b : c->batches)
+      if (b.last_ticket >= ticket) {
+        ev = b.done;
+        break;
+      }
   if (!ev) {
     return failed;              /* already reaped: finished */
   }

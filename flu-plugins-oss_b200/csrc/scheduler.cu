@@ -117,6 +117,8 @@ reap_batches (Ctx *c)
   }
   for (size_t i = 0; i < done; i++) {
     Batch &b = c->batches.front ();
+    if (b.last_ticket > c->retired_through)
+      c->retired_through = b.last_ticket;
     if (b.t0 && b.t1) {
       float ms = 0.f;
       if (cudaEventElapsedTime (&ms, b.t0, b.t1) == cudaSuccess) {

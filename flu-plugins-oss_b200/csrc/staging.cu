@@ -233,12 +233,13 @@ stage_completer_main (Ctx *c)
     }
     cudaEvent_t ev = nullptr;
     uint64_t upto = want;
-    for (auto &b : c->batches)
-      if (b.last_ticket >= want) {
-        ev = b.done;
-        upto = b.last_ticket;
-        break;
-      }
+    if (want > c->retired_through)
+      for (auto &b : c->batches)
+        if (b.last_ticket >= want) {
+          ev = b.done;
+          upto = b.last_ticket;
+          break;
+        }
     int rc = 0;
     if (ev) {
       /* the event stays valid while we wait (reaped events go back to the pool, and a pooled

@@ -568,6 +568,7 @@ struct Ctx {
   std::vector<cudaEvent_t> timing_pool;
   std::chrono::steady_clock::time_point oldest_pending;
   uint64_t next_ticket = 0;
+  uint64_t retired_through = 0;        /* every batch ticket up to here has finished and been retired */
   std::deque<Batch> batches;
   std::vector<cudaEvent_t> event_pool;
   TableSlot slots[kTableSlots];

@@ -279,6 +279,50 @@ def test_independent_launches_are_not_serialised(ctx):
         ctx.set_batch(32, 200)
 
 
+def test_wait_for_a_retired_ticket_does_not_wait_for_the_batch_in_flight(ctx):
+    """A caller that stays one batch behind waits for ticket i-1 after submitting batch i. When
+    batch i-1 has already been retired, that wait is over at once -- it must not resolve to the next
+    batch that is still in flight (it did: a C caller's pipeline then ran one batch at a time)."""
+    import time
+    fmt, w, h = "NV12", 1920, 1080
+    ov = random_overlay(w, 120, 990, density=0.9)
+    ctx.overlay_set_rectangles(790, [dict(pixels=ov, x=0, y=800)])
+    n = 32
+    ctx.set_batch(n, 0)
+    try:
+        srcs = [ctx.acquire(fmt, w, h) for _ in range(n)]
+        dsts = [ctx.acquire(fmt, w, h) for _ in range(n)]
+        frame = random_frame(fmt, w, h, 49)
+        for s in srcs:
+            s.upload(frame)
+        ctx.sync()
+        batch = ctx.Batch([790] * n, fmt, w, h, [s.c for s in srcs], [d.c for d in dsts])
+        best = None
+        for attempt in range(3):
+            old = ctx.submit_many(batch)[n - 1]
+            ctx.flush()
+            ctx.wait(old)                               # finished and retired
+            ctx.submit_many_repeat(batch, 400)          # 12800 frames in flight: tens of ms
+            newest = ctx.submit_many(batch)[n - 1]
+            ctx.flush()
+            t0 = time.perf_counter()
+            ctx.wait(old)
+            t1 = time.perf_counter()
+            ctx.wait(newest)
+            t2 = time.perf_counter()
+            ratio = (t1 - t0) / max(t2 - t0, 1e-9)
+            best = ratio if best is None else min(best, ratio)
+            if best < 0.1:
+                break
+        assert best < 0.1, f"wait (retired ticket) took {best:.2f} of the time the work in flight needed"
+        want = oracle_blend(fmt, w, h, copy_planes(frame), [dict(pixels=ov, x=0, y=800)])
+        assert_planes_equal(dsts[n - 1].download(), want, "after the waits")
+        for f in srcs + dsts:
+            f.release()
+    finally:
+        ctx.set_batch(32, 200)
+
+
 def test_host_dma_batches(ctx):
     """Pinned pool frames come in slabs (constant spacing), so a batch of them can be moved by the
     copy engines -- one 2-D copy per piece of rows and run of frames -- blended in device staging and
