@@ -606,6 +606,47 @@ def main():
                 e2e["same_layout_with_opaque_boxes"] = batch * n_op / (time.perf_counter() - t0)
             except Exception as e:      # noqa: BLE001
                 e2e["same_layout_with_opaque_boxes"] = f"failed: {e!r}"
+            # a caller that keeps THREE sets of host frames going (waits two batches behind), with the
+            # default zero-copy path and with the opt-in host DMA batches (fluc_ttmlblend_set_host_dma:
+            # copy engines both ways + blend in device staging). One GPU only: on GPUs that share a
+            # host bridge both are bound by it (profiles/r02_pcie_ceiling_summary.md).
+            if world == 1:
+                try:
+                    third = [ctx.acquire(fmt, W, H, on_host=True) for _ in range(batch)]
+                    for i, hf in enumerate(third):
+                        for dstp, srcp in zip(hf.host_planes(), base):
+                            dstp[...] = np.roll(srcp, i * 16, axis=1)
+                    host_sets.append(third)
+                    hb3 = host_batches + [ctx.Batch(stream_ids, fmt, W, H, [hf.c for hf in third], [hf.c for hf in third])]
+
+                    def deep_loop(n_steps):
+                        ring = []
+                        for i in range(n_steps):
+                            t = ctx.blend_host_many(hb3[i % 3])
+                            ring.append(t[len(t) - 1])
+                            if len(ring) > 2:
+                                ctx.wait(ring.pop(0))
+                        for r in ring:
+                            ctx.wait(r)
+
+                    deep = {}
+                    n_deep = max(6, min(e2e_steps, 60))
+                    for name, on in (("zero_copy", False), ("host_dma", True)):
+                        ctx.set_host_dma(on)
+                        deep_loop(6)
+                        ctx.sync()
+                        before = ctx.stats()["host_dma_batches"]
+                        t0 = time.perf_counter()
+                        deep_loop(n_deep)
+                        ctx.sync()
+                        deep[name] = batch * n_deep / (time.perf_counter() - t0)
+                        deep[name + "_dma_batches"] = int(ctx.stats()["host_dma_batches"] - before)
+                    deep["unit"] = UNIT
+                    e2e["three_sets_two_batches_behind"] = deep
+                except Exception as e:      # noqa: BLE001
+                    e2e["three_sets_two_batches_behind"] = {"failed": repr(e)}
+                finally:
+                    ctx.set_host_dma(os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1")
             # the same frames, one synchronous call per frame through the C mirror of the GStreamer
             # call (fluc_video_overlay_composition_blend == gst_video_overlay_composition_blend):
             # what a single streaming thread sees; not batched, so latency-bound

@@ -821,6 +821,20 @@ fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled)
   return 0;
 }
 
+int
+fluc_ttmlblend_set_host_dma (FlucTtmlBlend *thiz, int enabled)
+{
+  ENTER (thiz);
+  /* what is queued goes out the way it was queued for */
+  if (!c->pending.empty ()) {
+    int rc = launch_pending (c);
+    if (rc)
+      return rc;
+  }
+  c->use_host_dma = enabled != 0;
+  return 0;
+}
+
 
 }  /* extern "C" */
 

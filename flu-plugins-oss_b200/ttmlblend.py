@@ -119,6 +119,7 @@ PROTOTYPES = {
                                                  C.c_int32, C.c_int32, C.c_uint32, C.POINTER(Frame),
                                                  C.POINTER(C.c_uint64)]),
     "fluc_ttmlblend_set_auto_register": (C.c_int, [C.c_void_p, C.c_int]),
+    "fluc_ttmlblend_set_host_dma": (C.c_int, [C.c_void_p, C.c_int]),
     "fluc_ttmlblend_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fluc_ttmlblend_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fluc_ttmlblend_host_forget": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -435,6 +436,10 @@ class TtmlBlend:
 
     def set_auto_register(self, on: bool):
         self._check(self.lib.fluc_ttmlblend_set_auto_register(self.h, 1 if on else 0), "set_auto_register")
+
+    def set_host_dma(self, on: bool):
+        """Batches of pinned pool frames through the copy engines instead of zero copy (opt-in)."""
+        self._check(self.lib.fluc_ttmlblend_set_host_dma(self.h, 1 if on else 0), "set_host_dma")
 
     def host_register(self, arr: np.ndarray):
         self._check(self.lib.fluc_ttmlblend_host_register(self.h, arr.ctypes.data, arr.nbytes),

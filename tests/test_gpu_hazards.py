@@ -326,9 +326,10 @@ def test_wait_for_a_retired_ticket_does_not_wait_for_the_batch_in_flight(ctx):
 def test_host_dma_batches(ctx):
     """Pinned pool frames come in slabs (constant spacing), so a batch of them can be moved by the
     copy engines -- one 2-D copy per piece of rows and run of frames -- blended in device staging and
-    copied back (FLUC_TTMLBLEND_HOST_DMA=1; zero copy otherwise). Same bytes as the oracle either
+    copied back (fluc_ttmlblend_set_host_dma; zero copy otherwise). Same bytes as the oracle either
     way; a second batch on the same frames waits for the first one, and so does a single zero-copy
-    frame."""
+    frame. Repetition 0 runs with the context's default (zero copy unless the environment says
+    otherwise), 1 and 2 with the copy engines."""
     fmt, W, H = "NV12", 1024, 360          # 1024: pool stride == row bytes, the windows are whole rows
     box = lambda seed: np.ascontiguousarray(np.concatenate(
         [np.zeros((200, W, 4), np.uint8), _opaque_free(random_overlay(W, 120, seed, density=0.9)), np.zeros((40, W, 4), np.uint8)]))
@@ -341,6 +342,8 @@ def test_host_dma_batches(ctx):
         hosts = [ctx.acquire(fmt, W, H, on_host=True) for _ in range(n)]
         frames = [random_frame(fmt, W, H, 70 + i) for i in range(n)]
         for rep in range(3):
+            if rep == 1:
+                ctx.set_host_dma(True)
             for hf, fr in zip(hosts, frames):
                 for v, p in zip(hf.host_planes(), fr):
                     v[...] = p
@@ -355,7 +358,8 @@ def test_host_dma_batches(ctx):
             ctx.wait(t2[n - 1])
             ctx.wait(t3)
             after = ctx.stats()
-            if os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1" and os.environ.get("FLUC_TTMLBLEND_HOST_MODE", "1") == "1" \
+            if (rep >= 1 or os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1") \
+                    and os.environ.get("FLUC_TTMLBLEND_HOST_MODE", "1") == "1" \
                     and "FLUC_TTMLBLEND_GROUPS" not in os.environ and "FLUC_TTMLBLEND_LAZY" not in os.environ:
                 assert after["host_dma_batches"] - before["host_dma_batches"] == 2, after
             for i, (hf, fr) in enumerate(zip(hosts, frames)):
@@ -367,6 +371,7 @@ def test_host_dma_batches(ctx):
         for h in hosts:
             h.release()
     finally:
+        ctx.set_host_dma(os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1")
         ctx.set_batch(32, 200)
 
 
