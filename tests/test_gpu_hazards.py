@@ -199,7 +199,9 @@ def test_host_forget_drops_automatic_registrations():
                 p[...] = s
             c.wait(c.blend_host(1, fmt, W, H, planes))
             assert_planes_equal(planes, want, f"auto-registered, repetition {rep}")
-            assert c.host_forget(backing) >= 1
+            forgotten = c.host_forget(backing)
+            if os.environ.get("FLUC_TTMLBLEND_HOST_MODE", "1") != "0":     # mode 0 stages everything: nothing is pinned
+                assert forgotten >= 1
         assert c.host_forget(backing) == 0                   # nothing left
     finally:
         c.close()
