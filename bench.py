@@ -547,7 +547,9 @@ def main():
         e2e_steps = max(4, min(args.steps, 100))
         host_batches = [ctx.Batch(stream_ids, fmt, W, H, [hf.c for hf in hs], [hf.c for hf in hs])
                         for hs in host_sets]
-        e2e_loop(ctx, host_batches, 4)
+        # warm-up: long enough for the library to have tried both ways of crossing PCIe (128 frames
+        # each, fluc_ttmlblend_set_host_dma mode 2) and to have settled on the faster one
+        e2e_loop(ctx, host_batches, max(args.warmup, 16))
         ctx.sync()
         ctx.stats_reset()
         barrier(dist, device)
@@ -575,6 +577,8 @@ def main():
                "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps,
                "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
                "steps": e2e_steps, "launches": st2["launches"], "host_frames_numa_node": ctx.numa_node(),
+               "host_dma_batches": int(st2["host_dma_batches"]),
+               "transport": "copy engines" if st2["host_dma_batches"] * 2 > st2["launches"] else "zero copy",
                "gbs_per_direction": e2e_gbs,
                "pcie_ceiling_gbs": zc_total, "frac_of_pcie": e2e_gbs / zc_total if zc_total else None,
                "pcie_dma_both_gbs": dma_total,
@@ -584,10 +588,12 @@ def main():
                             "mode 1; per direction, summed over ranks); pcie_dma_both_gbs: the copy engine both ways "
                             "in one piece per direction. profiles/r02_pcie_ceiling_summary.md: beyond one GPU the "
                             "box's root complex, not the path, is the limit",
-               "api": "fluc_ttmlblend_blend_host_many on pinned host frames, in place: the kernel reads the rows "
-                      "under the cue regions from host memory and writes them back over PCIe (zero copy), "
-                      "one launch per batch; two sets of host frames alternate so that a batch is "
-                      "submitted while the previous one is on the bus"}
+               "api": "fluc_ttmlblend_blend_host_many on pinned host frames, in place; two sets of host frames "
+                      "alternate so that a batch is submitted while the previous one is on the bus. The library "
+                      "measures which transport is faster on this GPU (`transport`): zero copy -- the kernel reads "
+                      "the rows under the cue regions from host memory and writes them back over PCIe, one launch "
+                      "per batch -- or the copy engines -- 2-D copies of those rows for 8 frames at a time into "
+                      "device staging, blend there, copy back, three streams"}
         if extras and cfg.streams == 1:
             # the same layout with OPAQUE region boxes (opacity 1.0, the common broadcast style): the
             # result under an opaque vector does not depend on the frame, so in place the frame is
@@ -632,7 +638,7 @@ def main():
                     deep = {}
                     n_deep = max(6, min(e2e_steps, 60))
                     for name, on in (("zero_copy", False), ("host_dma", True)):
-                        ctx.set_host_dma(on)
+                        ctx.set_host_dma(1 if on else 0)
                         deep_loop(6)
                         ctx.sync()
                         before = ctx.stats()["host_dma_batches"]
@@ -646,7 +652,7 @@ def main():
                 except Exception as e:      # noqa: BLE001
                     e2e["three_sets_two_batches_behind"] = {"failed": repr(e)}
                 finally:
-                    ctx.set_host_dma(os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1")
+                    ctx.set_host_dma(int(os.environ.get("FLUC_TTMLBLEND_HOST_DMA", "2")))
             # the same frames, one synchronous call per frame through the C mirror of the GStreamer
             # call (fluc_video_overlay_composition_blend == gst_video_overlay_composition_blend):
             # what a single streaming thread sees; not batched, so latency-bound

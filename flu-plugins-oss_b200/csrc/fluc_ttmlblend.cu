@@ -246,7 +246,9 @@ fluc_ttmlblend_new (int device, FlucTtmlBlend **out)
   if ((e = getenv ("FLUC_TTMLBLEND_PDL")))
     c->use_pdl = atoi (e) != 0;
   if ((e = getenv ("FLUC_TTMLBLEND_HOST_DMA")))
-    c->use_host_dma = atoi (e) != 0;
+    c->host_dma_policy = std::max (0, std::min (2, atoi (e)));
+  if ((e = getenv ("FLUC_TTMLBLEND_DMA_PIECE")))
+    c->dma_piece = (uint32_t) std::max (0, std::min (1024, atoi (e)));
   c->stage_threads = (int) std::max (2u, std::min (12u, std::thread::hardware_concurrency () * 3 / 4));
   if ((e = getenv ("FLUC_TTMLBLEND_STAGE_THREADS")))
     c->stage_threads = std::max (0, std::min (64, atoi (e)));
@@ -343,6 +345,9 @@ fluc_ttmlblend_free (FlucTtmlBlend *thiz)
       if (ds.dev) cudaFree (ds.dev);
       if (ds.done) cudaEventDestroy (ds.done);
     }
+    for (auto &pair : c->dma_choice.ev)
+      for (cudaEvent_t e : pair)
+        if (e) cudaEventDestroy (e);
     for (auto &r : c->auto_regs)
       cudaHostUnregister ((void *) r.first);
     c->auto_regs.clear ();
@@ -822,16 +827,26 @@ fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled)
 }
 
 int
-fluc_ttmlblend_set_host_dma (FlucTtmlBlend *thiz, int enabled)
+fluc_ttmlblend_set_host_dma (FlucTtmlBlend *thiz, int mode)
 {
   ENTER (thiz);
+  if (mode < 0 || mode > 2)
+    return FLUC_TTMLBLEND_ERROR_INVALID_ARGUMENT;
   /* what is queued goes out the way it was queued for */
   if (!c->pending.empty ()) {
     int rc = launch_pending (c);
     if (rc)
       return rc;
   }
-  c->use_host_dma = enabled != 0;
+  c->host_dma_policy = mode;
+  if (mode == 2) {
+    /* measure afresh (the events are kept) */
+    Ctx::DmaChoice &d = c->dma_choice;
+    d.phase = 0;
+    d.dma = false;
+    d.judged = true;
+    d.begun[0] = d.begun[1] = d.ended[0] = d.ended[1] = false;
+  }
   return 0;
 }
 
@@ -881,7 +896,12 @@ tbh::queue_mapped_frame (Ctx *c, uint64_t tk, uint32_t stream, const std::shared
   if (c->pending.empty ())
     c->oldest_pending = std::chrono::steady_clock::now ();
   c->pending.push_back (std::move (f));
-  if (c->pending.size () >= c->max_batch)
+  /* frames for the copy engines go out in pieces: the copy-out of one piece overlaps the copy-in of
+   * the next inside one call as well, whatever the caller's own look-behind is */
+  const bool pieces = c->dma_piece >= 4 && c->host_dma_policy != 0 && c->dma_now () &&
+      c->pending.front ().host && layout_takes_dma (c->pending.front ().layout);
+  const size_t full = pieces ? std::min<size_t> (c->max_batch, c->dma_piece) : c->max_batch;
+  if (c->pending.size () >= full)
     return launch_pending (c);
   if (c->linger_us)
     c->cv.notify_all ();

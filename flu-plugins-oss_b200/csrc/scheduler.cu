@@ -163,13 +163,12 @@ reap_batches (Ctx *c)
  * direction only, which beats any copy), its windows are (nearly) full rows, and the frames form
  * few enough runs.
  *
- * OFF by default (FLUC_TTMLBLEND_HOST_DMA=1 turns it on). The bare pipeline shape reaches 47-48 GB/s
- * each way on one GPU -- in a process of its own (tools/pcie_ceiling.cu, pattern dma_pipe) and inside
- * this library on this context's own streams (fluc_ttmlblend_pcie_probe modes 2 / 4) -- but the
- * batches issued from here do not: FLUC_TTMLBLEND_DMA_TRACE shows the copy-in of batch i+1 starting
- * only when the copy-out of batch i has ended, with no event between them (27 GB/s each way from a
- * C caller, 37.5 from a Python one; zero copy: 37.8). Not understood by the end of round 2
- * (profiles/r02_host_dma_notes.md); parity-tested all the same (tests/test_gpu_hazards.py). */
+ * A batch goes out in pieces of Ctx::dma_piece frames (8), so that the copy-out of one piece overlaps
+ * the copy-in of the next inside one call too. Measured, 1 x B200, 32-frame 4K NV12 batches, caller
+ * one batch behind: 14.8 k frames/s (42.9 GB/s each way) against 13.2 k zero copy; on two GPUs
+ * behind one host bridge 17.65 k against 18.3 k. Which transport wins depends on the box, so the
+ * default policy measures (Ctx::DmaChoice, dma_choice_step below); fluc_ttmlblend_set_host_dma /
+ * FLUC_TTMLBLEND_HOST_DMA = 0 / 1 force one. profiles/r02_host_dma_notes.md has the history. */
 struct DmaRun { size_t first, n; ptrdiff_t spacing; };
 struct DmaPlan {
   std::vector<DmaRun> runs;
@@ -181,14 +180,11 @@ struct DmaPlan {
   uintptr_t host_lo = 0, host_hi = 0;
 };
 
-static bool
-plan_host_dma (Ctx *c, DmaPlan &plan)
+/* can frames of this layout go through the copy engines at all? */
+bool
+layout_takes_dma (const Layout *L)
 {
-  std::vector<PendingFrame> &pf = c->pending;
-  if (!c->use_host_dma || pf.size () < 4)
-    return false;
-  const Layout *L = pf[0].layout;
-  if (!pf[0].host || !L->grouped || !L->jobs.empty () || (L->gflags & JF_LAZY))
+  if (!L->grouped || !L->jobs.empty () || (L->gflags & JF_LAZY))
     return false;
   if (L->dma_ok < 0) {
     layout_spans (L, L->spans);
@@ -199,7 +195,18 @@ plan_host_dma (Ctx *c, DmaPlan &plan)
         L->dma_ok = 0;
     }
   }
-  if (!L->dma_ok)
+  return L->dma_ok == 1;
+}
+
+/* does the pending batch qualify? Fills the plan; nothing is changed yet. */
+static bool
+plan_host_dma (Ctx *c, DmaPlan &plan)
+{
+  std::vector<PendingFrame> &pf = c->pending;
+  if (pf.size () < 4)
+    return false;
+  const Layout *L = pf[0].layout;
+  if (!pf[0].host || !layout_takes_dma (L))
     return false;
   for (int pl = 0; pl < 3; pl++)
     plan.plane_off[pl] = pf[0].dst[pl] ? pf[0].dst[pl] - pf[0].dst[0] : 0;
@@ -236,6 +243,14 @@ plan_host_dma (Ctx *c, DmaPlan &plan)
   plan.layout = L;
   plan.host_lo = lo;
   plan.host_hi = hi;
+  return true;
+}
+
+/* the batch goes through the copy engines: a staging set, and the frames point into it */
+static bool
+commit_host_dma (Ctx *c, DmaPlan &plan)
+{
+  std::vector<PendingFrame> &pf = c->pending;
   /* a staging set (its previous copy-out is waited for on the copy-in stream, not here) */
   DmaSet &set = c->dma_sets[c->next_dma_set];
   const size_t need = plan.slot * pf.size ();
@@ -251,8 +266,9 @@ plan_host_dma (Ctx *c, DmaPlan &plan)
       return false;
     }
     set.bytes = need;
+    c->dma_choice.cold = true;
   }
-  c->next_dma_set = (c->next_dma_set + 1) % kDmaSets;
+  c->next_dma_set = (c->next_dma_set + 1) % (c->dma_piece ? kDmaSets : 3);
   plan.set = &set;
   /* from here on the frames are blended where the copies put them */
   plan.host_ptrs.resize (pf.size ());
@@ -289,6 +305,81 @@ dma_copies (Ctx *c, const DmaPlan &plan, bool in)
   return 0;
 }
 
+/* The measured choice between the two transports (Ctx::DmaChoice), after a qualifying batch of n
+ * frames went out; its completion is recorded on `done_stream`. */
+static void
+dma_choice_step (Ctx *c, size_t n, bool was_dma, cudaStream_t done_stream)
+{
+  Ctx::DmaChoice &d = c->dma_choice;
+  if (!d.ev[0][0])
+    for (auto &pair : d.ev)
+      for (cudaEvent_t &e : pair)
+        if (cudaEventCreate (&e) != cudaSuccess) {
+          cudaGetLastError ();
+          c->host_dma_policy = 0;       /* no events, no measurement: zero copy */
+          return;
+        }
+  if (!d.judged && d.ended[0] && d.ended[1]) {
+    if (cudaEventQuery (d.ev[0][1]) == cudaSuccess && cudaEventQuery (d.ev[1][1]) == cudaSuccess) {
+      float ms[2] = { 0.f, 0.f };
+      if (cudaEventElapsedTime (&ms[0], d.ev[0][0], d.ev[0][1]) == cudaSuccess &&
+          cudaEventElapsedTime (&ms[1], d.ev[1][0], d.ev[1][1]) == cudaSuccess && ms[0] > 0.f && ms[1] > 0.f) {
+        d.rate[0] = d.frames[0] / ms[0];
+        d.rate[1] = d.frames[1] / ms[1];
+        d.dma = d.rate[0] > d.rate[1] * 1.02f;
+        TBLOG (1, "host frames: copy engines %.2f frames/ms, zero copy %.2f frames/ms over %u / %u frames: %s from here on",
+            d.rate[0], d.rate[1], d.frames[0], d.frames[1], d.dma ? "copy engines" : "zero copy");
+      }
+      d.judged = true;
+      d.trials++;
+    }
+    cudaGetLastError ();        /* not ready is not an error */
+  }
+  if (d.phase < 2) {
+    const int m = d.phase;
+    if (m == 0 && !was_dma) {
+      /* the copy engines were wanted and not had (no memory for a staging set): zero copy, try later */
+      d.phase = 2;
+      d.dma = false;
+      d.judged = true;
+      d.left = kDmaSteadyFrames;
+      return;
+    }
+    if (m == 0 && d.cold) {
+      d.cold = false;
+      d.begun[0] = false;       /* an allocation in the middle: the trial starts over with the next batch */
+      return;
+    }
+    if (!d.begun[m]) {
+      /* the trial is timed from the completion of its first batch */
+      if (cudaEventRecord (d.ev[m][0], done_stream) != cudaSuccess)
+        cudaGetLastError ();
+      d.begun[m] = true;
+      d.frames[m] = 0;
+      d.left = kDmaTrialFrames;
+      return;
+    }
+    d.frames[m] += (uint32_t) n;
+    d.left -= (int64_t) n;
+    if (d.left <= 0) {
+      if (cudaEventRecord (d.ev[m][1], done_stream) != cudaSuccess)
+        cudaGetLastError ();
+      d.ended[m] = true;
+      d.phase++;
+      if (d.phase == 2) {
+        d.left = d.trials == 0 ? 2048 : d.trials == 1 ? 8192 : kDmaSteadyFrames;
+        d.judged = false;
+      }
+    }
+    return;
+  }
+  d.left -= (int64_t) n;
+  if (d.left <= 0 && d.judged) {
+    d.phase = 0;
+    d.begun[0] = d.begun[1] = d.ended[0] = d.ended[1] = false;
+  }
+}
+
 /* Launches everything pending as one batch (per plane kind). mu held. */
 int
 launch_pending (Ctx *c)
@@ -301,7 +392,9 @@ launch_pending (Ctx *c)
   if (c->batches.size () >= 32)
     reap_batches (c);
   DmaPlan plan;
-  const bool dma = plan_host_dma (c, plan);
+  const bool qualifies = c->host_dma_policy != 0 && plan_host_dma (c, plan);
+  const bool dma = qualifies && c->dma_now () && commit_host_dma (c, plan);
+  const size_t n_frames = c->pending.size ();
   Batch b = {};
   b.last_ticket = c->pending.back ().ticket;
   b.dma = dma;
@@ -557,6 +650,8 @@ launch_pending (Ctx *c)
     if (dma)
       c->dma_outstanding++;
     c->batches.push_back (std::move (b));
+    if (qualifies && c->host_dma_policy == 2)
+      dma_choice_step (c, n_frames, dma, dma ? c->dma_out : c->blend_stream);
   } else {
     /* not even an event: only a broken context gets here */
     cudaGetLastError ();

@@ -398,7 +398,8 @@ struct DmaSet {
   cudaEvent_t done = nullptr;          /* the copy back out of this set has finished */
   bool used = false;
 };
-constexpr int kDmaSets = 3;
+constexpr int64_t kDmaTrialFrames = 128, kDmaSteadyFrames = 32768;   /* the first steady phases are shorter: 2048, 8192 */
+constexpr int kDmaSets = 8;           /* 3 in use for whole batches, all of them for pieces (Ctx::dma_piece) */
 
 struct TableSlot {
   PlaneJob *h_jobs = nullptr, *d_jobs = nullptr;
@@ -622,8 +623,31 @@ struct Ctx {
    * pipeline takes from the pool one after the other then form runs that one two-dimensional
    * copy can move (host DMA batches, scheduler.cu) */
   std::vector<void *> host_slabs;
-  /* host DMA batches: FLUC_TTMLBLEND_HOST_DMA=1 turns them on (default: zero copy only; see scheduler.cu) */
-  bool use_host_dma = false;
+  /* host DMA batches (scheduler.cu). host_dma_policy: 0 never, 1 whenever a batch qualifies, 2 (default)
+   * decided by measurement -- which of the two transports is faster depends on how the GPU hangs off
+   * the host (measured: copy engines +12 % on a GPU with a root port of its own, -3.5 % on two GPUs
+   * behind one bridge). DmaChoice: a trial of each transport over kDmaTrialFrames qualifying frames,
+   * timed on the device between the completion of the trial's first and last batch, then the faster
+   * one (zero copy unless the copy engines win by 2 %) for 2048, 8192, then kDmaSteadyFrames frames each time,
+   * then again. */
+  int host_dma_policy = 2;
+  struct DmaChoice {
+    int phase = 0;                     /* 0: trial of the copy engines, 1: trial of zero copy, 2: steady */
+    bool dma = false;                  /* what the steady phase uses */
+    int64_t left = 0;                  /* qualifying frames left in this phase (0: phase not begun) */
+    cudaEvent_t ev[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   /* [transport][begin, end], timing events */
+    uint32_t frames[2] = { 0, 0 };     /* between begin and end */
+    bool begun[2] = { false, false }, ended[2] = { false, false };
+    bool judged = true;
+    float rate[2] = { 0.f, 0.f };      /* frames per ms of the last trial */
+    uint32_t trials = 0;
+    bool cold = false;                 /* a staging set was allocated for this batch: not a batch to time */
+  } dma_choice;
+  bool dma_now () const {
+    return host_dma_policy == 1 || (host_dma_policy == 2 && (dma_choice.phase == 0 || (dma_choice.phase == 2 && dma_choice.dma)));
+  }
+  uint32_t dma_piece = 8;              /* a batch for the copy engines goes out in pieces of this many frames, so that
+                                        * the copy-out of one piece overlaps the copy-in of the next inside one call (0: whole) */
   cudaStream_t dma_in = nullptr, dma_out = nullptr;
   DmaSet dma_sets[kDmaSets];
   int next_dma_set = 0;
@@ -735,6 +759,7 @@ cudaEvent_t event_get (Ctx *c);
 int launch_jobs (Ctx *c, TableSlot &s, const PlaneJob *jobs, size_t n, int kind, bool fast, int sync, cudaStream_t stream);
 void reap_batches (Ctx *c);
 int launch_pending (Ctx *c);
+bool layout_takes_dma (const Layout *L);
 void scheduler_main (Ctx *c);
 int lane_reserve (Ctx *c, Lane &l, size_t bytes);
 

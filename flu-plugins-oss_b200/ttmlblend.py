@@ -437,9 +437,9 @@ class TtmlBlend:
     def set_auto_register(self, on: bool):
         self._check(self.lib.fluc_ttmlblend_set_auto_register(self.h, 1 if on else 0), "set_auto_register")
 
-    def set_host_dma(self, on: bool):
-        """Batches of pinned pool frames through the copy engines instead of zero copy (opt-in)."""
-        self._check(self.lib.fluc_ttmlblend_set_host_dma(self.h, 1 if on else 0), "set_host_dma")
+    def set_host_dma(self, mode: int):
+        """How batches of pinned pool frames cross PCIe: 0 zero copy, 1 copy engines, 2 measured (default)."""
+        self._check(self.lib.fluc_ttmlblend_set_host_dma(self.h, int(mode)), "set_host_dma")
 
     def host_register(self, arr: np.ndarray):
         self._check(self.lib.fluc_ttmlblend_host_register(self.h, arr.ctypes.data, arr.nbytes),

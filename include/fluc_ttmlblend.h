@@ -313,16 +313,18 @@ FLUC_EXPORT int fluc_ttmlblend_blend_host_many (FlucTtmlBlend *thiz, uint32_t n,
  * address would otherwise be taken for the registered one while the GPU still reaches the old
  * pages. (The GStreamer glue does so from the GstMemory's destroy notification.) */
 FLUC_EXPORT int fluc_ttmlblend_set_auto_register (FlucTtmlBlend *thiz, int enabled);
-/* Opt-in (also FLUC_TTMLBLEND_HOST_DMA=1): batches of pinned pool frames (fluc_ttmlblend_frame_acquire
- * with on_host=1, which come in slabs of constant spacing) are moved by the copy engines -- two-
- * dimensional copies of the rows under the cue for a whole run of frames, blended in device staging
- * and copied back on a third stream -- instead of being read and written by the kernel over PCIe.
- * Worth it on a GPU with a PCIe root port of its own and for a caller that keeps THREE sets of host
- * frames going (waits two batches behind): 14.1-15.1 k frames/s against 13.2 k zero copy on the 4K
- * NV12 workload; with two sets 12.8 k, and on GPUs that share a host bridge nothing. Batches that
- * do not qualify (other memory, opaque boxes, fewer than 4 frames) take the zero-copy path as
- * before; results are identical either way. */
-FLUC_EXPORT int fluc_ttmlblend_set_host_dma (FlucTtmlBlend *thiz, int enabled);
+/* How batches of pinned pool frames (fluc_ttmlblend_frame_acquire with on_host=1, which come in
+ * slabs of constant spacing) cross PCIe. mode 0: zero copy only -- the kernel reads the rows under
+ * the cue from host memory and writes them back. mode 1: the copy engines whenever a batch
+ * qualifies (at least 4 in-place frames of one layout with full-row translucent windows) -- two-
+ * dimensional copies of the rows under the cue for a whole run of frames, 8 frames at a time, blended
+ * in device staging and copied back on a third stream. mode 2 (the default; FLUC_TTMLBLEND_HOST_DMA
+ * presets the mode): measured -- a trial of either transport over 128 qualifying frames, timed on the
+ * device, then the faster one for 32768 frames, then again. Which one wins depends on how the GPU
+ * hangs off the host: +12 % for the copy engines on a GPU with a root port of its own (14.8 k against
+ * 13.2 k frames/s, 4K NV12), -3.5 % on two GPUs behind one host bridge. Results are identical
+ * either way. */
+FLUC_EXPORT int fluc_ttmlblend_set_host_dma (FlucTtmlBlend *thiz, int mode);
 FLUC_EXPORT int fluc_ttmlblend_host_register (FlucTtmlBlend *thiz, void *ptr, size_t bytes);
 /* Both wait for every frame of the context that is queued or in flight before they unpin. */
 FLUC_EXPORT int fluc_ttmlblend_host_unregister (FlucTtmlBlend *thiz, void *ptr);

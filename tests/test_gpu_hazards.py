@@ -330,8 +330,8 @@ def test_host_dma_batches(ctx):
     copy engines -- one 2-D copy per piece of rows and run of frames -- blended in device staging and
     copied back (fluc_ttmlblend_set_host_dma; zero copy otherwise). Same bytes as the oracle either
     way; a second batch on the same frames waits for the first one, and so does a single zero-copy
-    frame. Repetition 0 runs with the context's default (zero copy unless the environment says
-    otherwise), 1 and 2 with the copy engines."""
+    frame. Repetition 0 runs with the context's default (the transport is chosen by measurement unless
+    the environment says otherwise), 1 and 2 with the copy engines."""
     fmt, W, H = "NV12", 1024, 360          # 1024: pool stride == row bytes, the windows are whole rows
     box = lambda seed: np.ascontiguousarray(np.concatenate(
         [np.zeros((200, W, 4), np.uint8), _opaque_free(random_overlay(W, 120, seed, density=0.9)), np.zeros((40, W, 4), np.uint8)]))
@@ -345,7 +345,7 @@ def test_host_dma_batches(ctx):
         frames = [random_frame(fmt, W, H, 70 + i) for i in range(n)]
         for rep in range(3):
             if rep == 1:
-                ctx.set_host_dma(True)
+                ctx.set_host_dma(1)
             for hf, fr in zip(hosts, frames):
                 for v, p in zip(hf.host_planes(), fr):
                     v[...] = p
@@ -363,7 +363,7 @@ def test_host_dma_batches(ctx):
             if (rep >= 1 or os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1") \
                     and os.environ.get("FLUC_TTMLBLEND_HOST_MODE", "1") == "1" \
                     and "FLUC_TTMLBLEND_GROUPS" not in os.environ and "FLUC_TTMLBLEND_LAZY" not in os.environ:
-                assert after["host_dma_batches"] - before["host_dma_batches"] == 2, after
+                assert after["host_dma_batches"] - before["host_dma_batches"] >= 2, after     # in pieces of 8 frames
             for i, (hf, fr) in enumerate(zip(hosts, frames)):
                 want = oracle_blend(fmt, W, H, copy_planes(fr), _rects(ov1))
                 want = oracle_blend(fmt, W, H, want, _rects(ov2))
@@ -373,7 +373,7 @@ def test_host_dma_batches(ctx):
         for h in hosts:
             h.release()
     finally:
-        ctx.set_host_dma(os.environ.get("FLUC_TTMLBLEND_HOST_DMA") == "1")
+        ctx.set_host_dma(int(os.environ.get("FLUC_TTMLBLEND_HOST_DMA", "2")))
         ctx.set_batch(32, 200)
 
 
