@@ -28,9 +28,12 @@ plus profiles/r02_roofline_traffic.json):
                 more than L2, so the overlay really streams from HBM (config 3 only).
   e2e           frames/s through fluc_ttmlblend_blend_host_many (the drop-in for
                 gst_video_overlay_composition_blend): pinned HOST frames, the rows the overlay
-                touches cross PCIe both ways inside the timed region; pcie_ceiling_gbs is what
-                the same traffic shape reaches with no blend in it, measured in the same run on
-                all ranks at once, frac_of_pcie = e2e bytes/s per direction over it. `pageable`:
+                touches cross PCIe both ways inside the timed region (`transport`: zero copy or
+                the copy engines, whichever the library's own timed trial found faster on this
+                GPU); pcie_ceiling_gbs is what the same traffic reaches with no blend in it -- a
+                kernel rewriting host memory in place, or the copy engine both ways, the larger
+                -- measured in the same run on all ranks at once, frac_of_pcie = e2e bytes/s per
+                direction over it. `pageable`:
                 the same through ordinary (not pinned) host memory.
   cfg5          BASELINE config 5 beside the headline: 256 1080p I420 streams sharded
                 stream % N over the ranks (strong scaling).
@@ -580,14 +583,16 @@ def main():
                "host_dma_batches": int(st2["host_dma_batches"]),
                "transport": "copy engines" if st2["host_dma_batches"] * 2 > st2["launches"] else "zero copy",
                "gbs_per_direction": e2e_gbs,
-               "pcie_ceiling_gbs": zc_total, "frac_of_pcie": e2e_gbs / zc_total if zc_total else None,
-               "pcie_dma_both_gbs": dma_total,
-               "pcie_ceiling_per_rank": [round(r[0], 1) for r in ceil],
-               "pcie_note": "pcie_ceiling_gbs: all ranks at once, a kernel that reads and rewrites as many pinned "
-                            "host bytes per iteration as one e2e step moves, nothing else (fluc_ttmlblend_pcie_probe "
-                            "mode 1; per direction, summed over ranks); pcie_dma_both_gbs: the copy engine both ways "
-                            "in one piece per direction. profiles/r02_pcie_ceiling_summary.md: beyond one GPU the "
-                            "box's root complex, not the path, is the limit",
+               "pcie_ceiling_gbs": max(zc_total, dma_total),
+               "frac_of_pcie": e2e_gbs / max(zc_total, dma_total) if max(zc_total, dma_total) else None,
+               "pcie_zero_copy_gbs": zc_total, "pcie_dma_both_gbs": dma_total,
+               "pcie_ceiling_per_rank": [round(max(r[0], r[1]), 1) for r in ceil],
+               "pcie_note": "measured in this run, all ranks at once, per direction, summed over ranks. "
+                            "pcie_zero_copy_gbs: a kernel that reads and rewrites as many pinned host bytes per "
+                            "iteration as one e2e step moves, nothing else (fluc_ttmlblend_pcie_probe mode 1); "
+                            "pcie_dma_both_gbs: the copy engine both ways, one piece per direction (mode 0); "
+                            "pcie_ceiling_gbs: the larger of the two. profiles/r02_pcie_ceiling_summary.md: beyond "
+                            "one GPU the box's root complex, not the path, is the limit",
                "api": "fluc_ttmlblend_blend_host_many on pinned host frames, in place; two sets of host frames "
                       "alternate so that a batch is submitted while the previous one is on the bus. The library "
                       "measures which transport is faster on this GPU (`transport`): zero copy -- the kernel reads "
