@@ -836,7 +836,7 @@ def run_multi_leg(pkg, wl, cfg, fmt, n_dev, steps):
             for k, c in enumerate(ctxs):
                 c.wait(prev[k])
 
-        loop(2)
+        loop(16)                # long enough for every context to have tried both transports (see the e2e leg)
         m.sync()
         t0 = time.perf_counter()
         loop(e2e_steps)
