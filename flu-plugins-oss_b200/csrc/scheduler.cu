@@ -350,6 +350,22 @@ dma_choice_step (Ctx *c, size_t n, bool was_dma, cudaStream_t done_stream)
       d.begun[0] = false;       /* an allocation in the middle: the trial starts over with the next batch */
       return;
     }
+    /* a trial times the bus, not the caller: a pause in the middle (several batch times) voids it,
+     * and a caller that keeps pausing is not bound by the bus -- zero copy, look again later */
+    const auto now = std::chrono::steady_clock::now ();
+    const bool paused = d.begun[m] && now - d.last > std::chrono::milliseconds (20);
+    d.last = now;
+    if (paused) {
+      d.begun[m] = false;
+      if (++d.gaps >= 8) {
+        d.gaps = 0;
+        d.phase = 2;
+        d.dma = false;
+        d.judged = true;
+        d.left = 2048;
+        return;
+      }
+    }
     if (!d.begun[m]) {
       /* the trial is timed from the completion of its first batch */
       if (cudaEventRecord (d.ev[m][0], done_stream) != cudaSuccess)

@@ -642,6 +642,8 @@ struct Ctx {
     float rate[2] = { 0.f, 0.f };      /* frames per ms of the last trial */
     uint32_t trials = 0;
     bool cold = false;                 /* a staging set was allocated for this batch: not a batch to time */
+    std::chrono::steady_clock::time_point last;   /* when the previous qualifying batch went out */
+    uint32_t gaps = 0;                 /* trials given up because the caller paused in the middle */
   } dma_choice;
   bool dma_now () const {
     return host_dma_policy == 1 || (host_dma_policy == 2 && (dma_choice.phase == 0 || (dma_choice.phase == 2 && dma_choice.dma)));
