@@ -157,8 +157,8 @@ reap_batches (Ctx *c)
  * (pool frames come in slabs; a pipeline takes them one after the other) turn every piece shape
  * into ONE two-dimensional copy for the whole run: rows under the cue -> full-size device staging
  * frames (copy-in stream), the ordinary group launch blends them there in place (blend stream),
- * rows -> host (copy-out stream); three staging sets, so copy-in of batch i+1, blend of i and
- * copy-out of i-1 overlap. Taken for a batch iff every frame is such a host frame of one layout
+ * rows -> host (copy-out stream); several staging sets (3 for whole batches, 8 for pieces), so
+ * copy-in of batch i+1, blend of i and copy-out of i-1 overlap. Taken for a batch iff every frame is such a host frame of one layout
  * that is not "look at the overlay first" (under an opaque box zero copy moves the frame in one
  * direction only, which beats any copy), its windows are (nearly) full rows, and the frames form
  * few enough runs.
